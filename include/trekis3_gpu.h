@@ -1,0 +1,232 @@
+/*
+ * trekis3_gpu.h -- C ABI of the B200-native TREKIS-3 Monte-Carlo cascade engine.
+ *
+ * Drop-in boundary: the reference's only public symbol of MODULE Monte_Carlo is
+ *     subroutine do_Monte_Carlo(NMC, SHI, SHI_MFP, diff_SHI_MFP, Target_atoms, ...)
+ * (Source_files/Monte_Carlo.f90:39-44, sole caller Universal_MC_for_SHI_MAIN.f90:271-276).
+ * Its 52 dummy arguments are Fortran derived types with allocatable components and are
+ * therefore not C-interoperable; the structs below are the flattened (SoA, fp64) image of
+ * those arguments, and trk3_mc_run() is the replacement of the call.  A Fortran
+ * ISO_C_BINDING shim that flattens the derived types and calls these entry points is shown
+ * in INTEGRATION.md.
+ *
+ * Plain C: pointers and sizes only, no C++/torch types.  All real data are double (the
+ * reference is compiled with -real-size 64), all indices are 0-based in this header.
+ */
+#ifndef TREKIS3_GPU_H
+#define TREKIS3_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRK3_MAX_ATOMS   8
+#define TRK3_MAX_SHELLS  32
+#define TRK3_NR          50    /* radial bins, Sorting_output_data.f90:1373 */
+#define TRK3_NTHETA      180   /* Out_theta1(180), Sorting_output_data.f90:1193 */
+#define TRK3_MAX_NT      256   /* max number of output time-grid points */
+
+/* ---------------------------------------------------------------------------------
+ * Scalars and switches: image of SHI (Objects.f90:44-53), Matter (Objects.f90:86-105),
+ * NumPar (Objects.f90:129-167), Tim, dt, NMC as passed to do_Monte_Carlo.
+ * ------------------------------------------------------------------------------- */
+typedef struct trk3_config {
+    /* ion (type Ion) */
+    double shi_E;          /* [eV]  SHI%E */
+    double shi_mass;       /* [proton masses] SHI%Mass */
+    double shi_fixed_Zeff; /* SHI%fixed_Zeff */
+    int32_t shi_Z;         /* SHI%Zat */
+    int32_t shi_kind_Zeff; /* 0 Barkas,1 Bohr,2 ND,3 SG,4 fixed (Cross_sections.f90:2657) */
+    /* time grid (Monte_Carlo.f90:2118-2149) */
+    double Tim;            /* [fs] */
+    double dt;             /* [fs] step (linear) or factor (log) */
+    int32_t dt_flag;       /* <=0 linear, >=1 logarithmic */
+    int32_t include_photons; /* NumPar%include_photons */
+    /* material scalars (type Solid) */
+    double cut_off;        /* [eV] */
+    double layer;          /* [A]  */
+    double hole_mass;      /* [me]; <0 => effective mass from DOS (Monte_Carlo.f90:783-788) */
+    double work_function;  /* [eV]; <=0 => no emission */
+    double bar_length;     /* [A] */
+    double bar_height;     /* [eV] */
+    /* numerics */
+    int32_t kind_of_EMFP;  /* 0 Mott, 1 CDF phonons (2 DSF unsupported) */
+    int32_t reserved0;
+    /* engine (not in the reference) */
+    uint64_t seed;         /* Philox key; histories are keyed (seed, iteration, particle id) */
+} trk3_config;
+
+/* ---------------------------------------------------------------------------------
+ * Tables: image of Target_atoms, SHI_MFP, diff_SHI_MFP, Total_el_MFPs, Elastic_MFP,
+ * Total_Hole_MFPs, Elastic_Hole_MFP, Total_Photon_MFPs, aidCS, Mat_DOS, Out_R, Out_V.
+ * Shells are flattened in (atom, shell) order; matrices are row-major [shell][energy].
+ * Differential tables are CSR: row r occupies [off[r], off[r+1]).
+ * All pointers are host pointers owned by the caller; trk3_mc_create copies them.
+ * ------------------------------------------------------------------------------- */
+typedef struct trk3_tables {
+    int32_t n_atoms;
+    int32_t n_shells;                 /* total over atoms */
+    int32_t vb_shell;                 /* flat index of (Lowest_Ip_At, Lowest_Ip_Shl) */
+    int32_t nshl_atom1;               /* size(Target_atoms(1)%Ip): 4th dim of Out_nh etc. */
+    int32_t atom_Z[TRK3_MAX_ATOMS];
+    int32_t atom_nshl[TRK3_MAX_ATOMS];
+    int32_t atom_first[TRK3_MAX_ATOMS];   /* flat index of first shell of atom */
+    double  atom_mass[TRK3_MAX_ATOMS];    /* [proton masses] */
+    double  atom_pers[TRK3_MAX_ATOMS];    /* stoichiometry */
+    int32_t shell_atom[TRK3_MAX_SHELLS];  /* 0-based atom of flat shell */
+    int32_t shell_num[TRK3_MAX_SHELLS];   /* 0-based shell index inside its atom */
+    double  shell_Ip[TRK3_MAX_SHELLS];
+    double  shell_Nel[TRK3_MAX_SHELLS];
+    double  shell_auger[TRK3_MAX_SHELLS];   /* [fs] */
+    double  shell_radiat[TRK3_MAX_SHELLS];  /* [fs] */
+
+    /* electron inelastic: Total_el_MFPs(:)%ELMFP(:)%{E,L} */
+    int32_t n_ei;  const double *ei_E;  const double *ei_L;   /* [n_shells][n_ei] */
+    /* electron elastic: Elastic_MFP%Total%{E,L} */
+    int32_t n_ee;  const double *ee_E;  const double *ee_L;   /* [n_ee] */
+    /* VB-hole inelastic / elastic */
+    int32_t n_hi;  const double *hi_E;  const double *hi_L;   /* [n_shells][n_hi] */
+    int32_t n_he;  const double *he_E;  const double *he_L;   /* [n_he] */
+    /* photon (n_ph = 0 when photons are off) */
+    int32_t n_ph;  const double *ph_E;  const double *ph_L;   /* [n_shells][n_ph] */
+    /* SHI: SHI_MFP(:)%ELMFP(:)%{E,L,dEdx} */
+    int32_t n_shi; const double *shi_E; const double *shi_L; const double *shi_dEdx;
+    /* diff_SHI_MFP: per shell cumulative (E = transferred energy, L = MFP) */
+    const int64_t *dshi_off;  /* [n_shells+1] */
+    const double  *dshi_E;  const double *dshi_L;
+    /* aidCS%EIdCS: rows (shell, iE); EEdCS rows iE; HIdCS; HEdCS */
+    const int64_t *eid_off;   /* [n_shells*n_ei + 1] */
+    const double  *eid_hw;  const double *eid_L;
+    const int64_t *eed_off;   /* [n_ee + 1] */
+    const double  *eed_hw;  const double *eed_L;
+    const int64_t *hid_off;   /* [n_hi + 1] */
+    const double  *hid_hw;  const double *hid_L;
+    const int64_t *hed_off;   /* [n_he + 1] */
+    const double  *hed_hw;  const double *hed_L;
+    /* Mat_DOS (hole-energy grid, increasing) */
+    int32_t n_dos; const double *dos_E; const double *dos_DOS; const double *dos_int; const double *dos_effm;
+    /* Out_R / Out_V (Sorting_output_data.f90:1403-1434) */
+    int32_t n_r;   const double *out_R; const double *out_V;
+} trk3_tables;
+
+/* ---------------------------------------------------------------------------------
+ * Tallies: one contiguous fp64 buffer; every Out_* array of do_Monte_Carlo lives at a
+ * fixed offset in Fortran (column-major) element order, so a Fortran caller can
+ * c_f_pointer straight onto it.  The engine ADDS per-iteration contributions (the
+ * caller pre-zeroes and later divides by NMC, MAIN.f90:281-314).
+ * ------------------------------------------------------------------------------- */
+enum trk3_tally_id {
+    TRK3_OUT_NE = 0,       /* (Nt,NR)            */
+    TRK3_OUT_EE,           /* (Nt,NR)            */
+    TRK3_OUT_NPHOT,        /* (Nt,NR)            */
+    TRK3_OUT_EPHOT,        /* (Nt,NR)            */
+    TRK3_OUT_EE_VS_E,      /* (Nt,NR)            */
+    TRK3_OUT_EH_VS_E,      /* (Nt,Ndos)          */
+    TRK3_OUT_ELAT,         /* (Nt,NR)            */
+    TRK3_OUT_NH,           /* (Nt,NR,Nat,Nsh1)   */
+    TRK3_OUT_EH,           /* (Nt,NR,Nat,Nsh1)   */
+    TRK3_OUT_EHKIN,        /* (Nt,NR,Nat,Nsh1)   */
+    TRK3_OUT_TOT_NE,       /* (Nt)               */
+    TRK3_OUT_TOT_NPHOT,    /* (Nt)               */
+    TRK3_OUT_TOT_E,        /* (Nt)               */
+    TRK3_OUT_E_E,          /* (Nt)               */
+    TRK3_OUT_E_PHOT,       /* (Nt)               */
+    TRK3_OUT_E_AT,         /* (Nt)               */
+    TRK3_OUT_E_H,          /* (Nt,Nat,Nsh1)      */
+    TRK3_OUT_EAT_DENS,     /* (Nt,NR) never written by the reference */
+    TRK3_OUT_THETA,        /* (Nt+1,180)         */
+    TRK3_OUT_THETA_H,      /* (Nt+1,180)         */
+    TRK3_OUT_NE_EM,        /* (Nt)               */
+    TRK3_OUT_E_EM,         /* (Nt)               */
+    TRK3_OUT_EE_VS_E_EM,   /* (Nt,NR)            */
+    TRK3_OUT_FIELD_ALL,    /* (Nt,NR) dead code in the reference, stays 0 */
+    TRK3_OUT_E_FIELD,      /* (Nt)    dead code in the reference, stays 0 */
+    TRK3_OUT_DIFF_COEFF,   /* (Nt)               */
+    TRK3_N_TALLIES
+};
+
+typedef struct trk3_tally_layout {
+    int32_t Nt, n_r, n_atoms, nshl1, n_dos, reserved;
+    int64_t off[TRK3_N_TALLIES];   /* element offset of each array */
+    int64_t len[TRK3_N_TALLIES];   /* element count of each array  */
+    int64_t total;                 /* doubles in the whole buffer  */
+    double  time_grid[TRK3_MAX_NT + 1]; /* set_time_grid, Monte_Carlo.f90:2118 (Nt+1 entries) */
+} trk3_tally_layout;
+
+/* Event classes: one pass through `select case (KOP)`,
+ * Monte_Carlo.f90:587-627, split by channel. */
+enum trk3_event_class {
+    TRK3_EV_SHI = 0, TRK3_EV_EL_INEL, TRK3_EV_EL_ELAST, TRK3_EV_VBH_INEL, TRK3_EV_VBH_ELAST,
+    TRK3_EV_AUGER, TRK3_EV_RADIATIVE, TRK3_EV_AUGER_FROZEN, TRK3_EV_PHOTON, TRK3_N_EVENT_CLASSES
+};
+
+/* Error counters carry the reference's error numbers (Monte_Carlo.f90:2227-2960). */
+enum trk3_error_code {
+    TRK3_ERR_10 = 0, TRK3_ERR_20, TRK3_ERR_21, TRK3_ERR_22, TRK3_ERR_23, TRK3_ERR_25, TRK3_ERR_30,
+    TRK3_ERR_40, TRK3_ERR_41, TRK3_ERR_50, TRK3_ERR_51, TRK3_ERR_52,
+    TRK3_ERR_QUEUE_OVERFLOW, TRK3_ERR_NAN, TRK3_ERR_AUGER_BALANCE, TRK3_N_ERRORS
+};
+
+typedef struct trk3_stats {
+    uint64_t events[TRK3_N_EVENT_CLASSES];
+    uint64_t errors[TRK3_N_ERRORS];
+    uint64_t n_electrons;       /* total electrons created */
+    uint64_t n_photons;         /* total photons created   */
+    uint64_t n_waves;           /* kernel generations launched */
+    uint64_t kernel_launches;   /* CUDA kernels launched by the engine */
+    double   device_ms;         /* CUDA-event time of the MC section */
+    double   algorithmic_bytes; /* sum_class events*bytes */
+    double   max_energy_drift;  /* max_it max_i |tot_E(it,i)-tot_E(it,Nt)|/tot_E(it,Nt), i >= first grid time after the ion left */
+} trk3_stats;
+
+/* Return codes */
+#define TRK3_OK                 0
+#define TRK3_E_INVALID         -1
+#define TRK3_E_CUDA            -2
+#define TRK3_E_UNSUPPORTED     -3
+#define TRK3_E_NOMEM           -4
+#define TRK3_E_OVERFLOW        -5
+
+typedef struct trk3_engine trk3_engine;   /* opaque; owns all device memory */
+
+/* Fill `lay` for a given configuration/tables (host only, no GPU needed).
+ * Mirrors Radius_for_distributions / Allocate_out_arrays / set_time_grid. */
+int trk3_tally_layout_init(const trk3_config *cfg, const trk3_tables *tab, trk3_tally_layout *lay);
+
+/* Validate + upload tables once (replaces the per-iteration How_many_electrons
+ * table flattening, Monte_Carlo.f90:1902-2057).  device < 0 => current device. */
+int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, trk3_engine **out);
+
+/* Run iterations [it_begin, it_end) (global 0-based iteration indices; RNG streams are keyed
+ * by the global index so the union over ranks is independent of the split) and ADD their
+ * contributions to `tallies` (host buffer of lay.total doubles, caller pre-zeroed).
+ * Replaces do_Monte_Carlo (Monte_Carlo.f90:39).  `stats` may be NULL. */
+int trk3_mc_run(trk3_engine *eng, int64_t it_begin, int64_t it_end, double *tallies, trk3_stats *stats);
+
+/* Same, but leaves the tally sums in the engine's device buffer (for an NCCL all-reduce
+ * issued by the caller on trk3_mc_device_tallies()).  */
+int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_stats *stats);
+double *trk3_mc_device_tallies(trk3_engine *eng);      /* device pointer, lay.total doubles */
+int trk3_mc_zero_device_tallies(trk3_engine *eng);
+int trk3_mc_download_tallies(trk3_engine *eng, double *tallies_add_into);
+
+/* Per-iteration total energy at every grid time, [n_iter][Nt] row-major, for the
+ * conservation check (Total_numbers.txt, manual section VI).  Valid after a run. */
+int trk3_mc_iteration_energies(trk3_engine *eng, double *out, int64_t capacity_doubles, int64_t *n_iter);
+
+/* Tunables: batch of iterations in flight, queue capacity per iteration, threads per block */
+int trk3_mc_set_option(trk3_engine *eng, const char *name, double value);
+
+const trk3_tally_layout *trk3_mc_layout(const trk3_engine *eng);
+const char *trk3_mc_last_error(const trk3_engine *eng);
+void trk3_mc_destroy(trk3_engine *eng);
+
+/* Library identity, used by tests to prove the CUDA library (not a fallback) is loaded. */
+const char *trk3_gpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TREKIS3_GPU_H */

@@ -1,0 +1,60 @@
+/*
+ * trekis3_host.h -- C ABI of the host half of the drop-in (libtrekis3_host.so, no CUDA).
+ *
+ * It replaces what the Fortran host does around do_Monte_Carlo:
+ *   Read_input_file            Reading_files_and_parameters.f90:162   -> trk3h_load
+ *   Analytical_ion_dEdx / Analytical_electron_dEdx / SHI_TotIMFP
+ *                              Universal_MC_for_SHI_MAIN.f90:146-247  -> trk3h_build_tables
+ *   Save_output                Sorting_output_data.f90:340            -> trk3h_save_output
+ * and hands the flattened tables (trk3_config / trk3_tables of trekis3_gpu.h) to the engine.
+ */
+#ifndef TREKIS3_HOST_H
+#define TREKIS3_HOST_H
+#include "trekis3_gpu.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct trk3h_case trk3h_case;
+
+/* Parse <dir>/INPUT_PARAMETERS.txt, <dir>/INPUT_CDF/<material>.cdf, <dir>/INPUT_DOS/<material>.dos,
+ * <dir>/INPUT_EADL/INPUT_atomic_data.dat [, <dir>/INPUT_EADL/radiative_widths.dat]. NULL on error. */
+trk3h_case *trk3h_load(const char *dir, char *err, int errlen);
+void trk3h_free(trk3h_case *c);
+
+/* Build all MFP / differential cross-section tables on the host (OpenMP over grid points).
+ * threads<=0: all cores.  shi_window_only!=0: only the SHI-grid points the ion can visit. */
+int trk3h_build_tables(trk3h_case *c, int threads, int shi_window_only, int verbose, char *err, int errlen);
+int trk3h_save_tables(trk3h_case *c, const char *path, char *err, int errlen);
+int trk3h_load_tables(trk3h_case *c, const char *path, char *err, int errlen);
+
+/* Flattened views; valid until the next trk3h_* call that modifies the case. */
+const trk3_config *trk3h_config(trk3h_case *c);
+const trk3_tables *trk3h_tables(trk3h_case *c);
+
+/* Scalar overrides applied before packing (benchmarks, tests). */
+int trk3h_set(trk3h_case *c, const char *key, double value);
+double trk3h_get(trk3h_case *c, const char *key);
+int trk3h_get_string(trk3h_case *c, const char *key, char *out, int outlen);
+int trk3h_num_warnings(trk3h_case *c);
+int trk3h_warning(trk3h_case *c, int i, char *out, int outlen);
+
+/* Single-point evaluations of the table builder (parity tests of Cross_sections.f90 routines). */
+int trk3h_eval_TotIMFP(trk3h_case *c, double E, int atom, int shell, int kind, double *L, double *dEdx);
+int trk3h_eval_EMFP(trk3h_case *c, double E, int kind, double *L, double *dEdx);
+int trk3h_eval_SHI(trk3h_case *c, double E, int atom, int shell, double *inv_L, double *dEdx, double *Zeff);
+int trk3h_eval_photon(trk3h_case *c, double E, int atom, int shell, double *L);
+int trk3h_sumrules(trk3h_case *c, int atom, int shell, double *ksum, double *fsum);   /* atom<0: phonon CDF */
+int trk3h_grid(trk3h_case *c, double Emin, double Emax, double *out, int cap);        /* get_grid_4CS */
+
+/* Write the reference's output directory tree; tallies are the SUMS returned by trk3_mc_run
+ * (division by NMC happens here, MAIN.f90:281-314).  out_dir receives the created directory. */
+int trk3h_save_output(trk3h_case *c, const trk3_tally_layout *lay, const double *tallies, int NMC,
+                      const char *out_root, char *out_dir, int out_dir_len, char *err, int errlen);
+
+const char *trk3_host_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

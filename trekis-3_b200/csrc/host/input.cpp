@@ -1,0 +1,455 @@
+// input.cpp -- readers of the reference's input contract:
+//   INPUT_PARAMETERS.txt            Reading_files_and_parameters.f90:162-634, 948-1116
+//   INPUT_CDF/<material>.cdf        Reading_files_and_parameters.f90:1185-1644
+//   INPUT_DOS/<material>.dos        Reading_files_and_parameters.f90:2317-2454
+//   INPUT_EADL/INPUT_atomic_data.dat (periodic table; same numbers as Dealing_with_EADL.f90:1217-1705)
+// The files are parsed with the semantics of Fortran list-directed input (blank lines are
+// skipped, the rest of a record after the requested items is ignored, d-exponents are legal).
+#include "trk3_host.hpp"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <sys/stat.h>
+
+namespace trk3 {
+
+namespace {
+
+struct Lines {
+    std::vector<std::string> l;
+    size_t pos = 0;
+    bool load(const std::string &path) {
+        std::ifstream f(path);
+        if (!f) return false;
+        std::string s;
+        while (std::getline(f, s)) {
+            if (!s.empty() && s.back() == '\r') s.pop_back();
+            l.push_back(s);
+        }
+        return true;
+    }
+    bool eof() const { return pos >= l.size(); }
+    bool read_line(std::string &s) { if (eof()) return false; s = l[pos++]; return true; }
+    void backspace() { if (pos > 0) --pos; }
+};
+
+// split a record into list-directed tokens (blank, tab, comma separated; quotes honoured)
+std::vector<std::string> tokens(const std::string &s) {
+    std::vector<std::string> t;
+    size_t i = 0, n = s.size();
+    while (i < n) {
+        while (i < n && (s[i] == ' ' || s[i] == '\t' || s[i] == ',')) ++i;
+        if (i >= n) break;
+        if (s[i] == '\'' || s[i] == '"') {
+            char q = s[i++]; size_t j = i;
+            while (j < n && s[j] != q) ++j;
+            t.push_back(s.substr(i, j - i)); i = (j < n) ? j + 1 : n;
+        } else {
+            size_t j = i;
+            while (j < n && s[j] != ' ' && s[j] != '\t' && s[j] != ',') ++j;
+            t.push_back(s.substr(i, j - i)); i = j;
+        }
+    }
+    return t;
+}
+
+bool parse_real(const std::string &tok, double &v) {
+    if (tok.empty()) return false;
+    std::string s = tok;
+    for (auto &ch : s) if (ch == 'd' || ch == 'D') ch = 'e';
+    char *end = nullptr;
+    v = std::strtod(s.c_str(), &end);
+    return end && *end == '\0' && end != s.c_str();
+}
+bool parse_int(const std::string &tok, int &v) {
+    if (tok.empty()) return false;
+    char *end = nullptr;
+    long x = std::strtol(tok.c_str(), &end, 10);
+    if (!(end && *end == '\0' && end != tok.c_str())) return false;   // "1.0" is not a valid integer item
+    v = (int)x; return true;
+}
+
+// READ(unit,*) of n items: consume records until n tokens are collected.
+// reason: 0 ok, -1 end of file, +1 conversion error (checked by the caller through the parse_* calls)
+int read_list(Lines &f, size_t n, std::vector<std::string> &out) {
+    out.clear();
+    while (out.size() < n) {
+        std::string s;
+        if (!f.read_line(s)) return -1;
+        auto t = tokens(s);
+        for (auto &x : t) { if (out.size() < n) out.push_back(x); }
+    }
+    return 0;
+}
+
+bool file_exists(const std::string &p) { struct stat st; return ::stat(p.c_str(), &st) == 0; }
+
+struct PT { std::string name, full; double mass, nvb; };
+bool load_periodic_table(const std::string &dir, std::vector<PT> &pt, std::string &err) {
+    std::string path = dir + "/INPUT_EADL/INPUT_atomic_data.dat";
+    Lines f;
+    if (!f.load(path)) { err = "File " + path + " is not found!"; return false; }
+    pt.assign(130, PT{"", "", 0.0, 0.0});
+    for (size_t i = 1; i < f.l.size(); ++i) {
+        auto t = tokens(f.l[i]);
+        int z; double m, nvb;
+        if (t.size() < 5 || !parse_int(t[0], z) || !parse_real(t[3], m) || !parse_real(t[4], nvb)) continue;
+        if (z > 0 && z < 130) pt[z] = PT{t[2], t[1], m, nvb};
+    }
+    // The reference takes element names/masses from the hard-coded Find_element_name
+    // (Dealing_with_EADL.f90:1217-1705), which differs from the data file for these entries:
+    auto fix = [&](int z, const char *n, const char *fn, double m) { if (z < (int)pt.size()) { pt[z].name = n; pt[z].full = fn; pt[z].mass = m; } };
+    fix(56, "Ba", "Barium", 137.327); fix(77, "Ir", "Iridium", 192.217); fix(94, "Pu", "Plutonium", 244.0);
+    fix(111, "Rg", "Roentgenium", 281.0); fix(115, "Uup", "Ununpentium", 288.0);
+    fix(117, "Uus", "Ununseptium", 294.0); fix(118, "Uuo", "Ununoctium", 294.0);
+    return true;
+}
+
+// define_PQN, Dealing_with_EADL.f90:1016-1214: ENDL shell designator -> name, principal quantum number
+void define_PQN(int d, std::string &name, int &pqn) {
+    static const char *names[] = {"", "K-shell", "L-shell", "L1-shell", "L23-shell", "L2-shell", "L3-shell", "M-shell",
+        "M1-shell", "M23-shell", "M2-shell", "M3-shell", "M45-shell", "M4-shell", "M5-shell", "N-shell", "N1-shell",
+        "N23-shell", "N2-shell", "N3-shell", "N45-shell", "N4-shell", "N5-shell", "N67-shell", "N6-shell", "N7-shell",
+        "O-shell", "O1-shell", "O23-shell", "O2-shell", "O3-shell", "O45-shell", "O4-shell", "O5-shell", "O67-shell",
+        "O6-shell", "O7-shell", "O89-shell", "O8-shell", "O9-shell", "P-shell", "P1-shell", "P23-shell", "P2-shell",
+        "P3-shell", "P45-shell", "P4-shell", "P5-shell", "P67-shell", "P6-shell", "P7-shell", "P89-shell", "P8-shell",
+        "P9-shell", "P1011-shell", "P10-shell", "P11-shell", "Q-shell", "Q1-shell", "Q23-shell", "Q2-shell", "Q3-shell"};
+    if (d >= 63) { name = "Valence"; pqn = 0; return; }
+    if (d >= 1 && d <= 61) name = names[d]; else name = "Shell";
+    if (d == 1) pqn = 1; else if (d <= 6) pqn = 2; else if (d <= 14) pqn = 3; else if (d <= 25) pqn = 4;
+    else if (d <= 39) pqn = 5; else if (d <= 56) pqn = 6; else pqn = 7;
+}
+
+// interpret_additional_data_INPUT, Reading_files_and_parameters.f90:948-1116
+void interpret_flag(const std::string &line, NumPar &np) {
+    auto t = tokens(line);
+    if (t.empty()) return;
+    const std::string &k = t[0];
+    auto is = [&](std::initializer_list<const char *> names) { for (auto n : names) if (k == n) return true; return false; };
+    int iv;
+    if (is({"grid", "GRID", "Grid"})) { if (t.size() > 1 && parse_int(t[1], iv)) np.CS_method = iv; }
+    else if (is({"UNITS", "Units", "units"})) { if (t.size() > 1 && parse_int(t[1], iv)) np.out_dim = iv; }
+    else if (is({"CDF", "Cdf", "cdf"})) { if (t.size() > 1) np.CDF_file = t[1]; }
+    else if (is({"DOS", "Dos", "dos"})) { if (t.size() > 1) np.DOS_file = t[1]; }
+    else if (is({"gnuplot", "plot", "gnu", "GNUPLOT", "PLOT", "GNU"})) {
+        np.do_gnuplot = true;
+        np.plot_extension = (t.size() > 1) ? t[1] : "jpeg";
+        if (np.plot_extension == "NO" || np.plot_extension == "No" || np.plot_extension == "no") np.do_gnuplot = false;
+    }
+    else if (is({"redo_MFP", "REDO_MFP", "Redo_MFP", "redo_mfp"})) { np.redo_IMFP = np.redo_EMFP = np.redo_IMFP_SHI = true; }
+    else if (is({"redo_MFP_SHI", "REDO_MFP_SHI", "Redo_MFP_SHI", "redo_mfp_shi", "redo_IMFP_SHI", "REDO_IMFP_SHI", "Redo_IMFP_SHI", "redo_imfp_shi"})) np.redo_IMFP_SHI = true;
+    else if (is({"redo_IMFP", "REDO_IMFP", "Redo_IMFP", "redo_imfp"})) np.redo_IMFP = true;
+    else if (is({"redo_EMFP", "REDO_EMFP", "Redo_EMFP", "redo_emfp"})) np.redo_EMFP = true;
+    else if (is({"get_thermal", "thermal", "make_thermal", "Get_thermal", "Thermal", "Make_thermal"})) np.get_thermal = true;
+    else if (is({"print_CDF", "Print_CDF", "print_cdf", "PRINT_CDF"})) np.print_CDF = true;
+    else if (is({"print_optical", "Print_optical", "Print_Optical", "print_optical_cdf", "PRINT_OPTICAL_CDF"})) np.print_CDF_optical = true;
+    else if (is({"Verbose", "verbose", "VERBOSE"})) np.verbose = true;
+    else if (is({"Very_verbose", "very_verbose", "VERY_VERBOSE", "Very_Verbose", "Very-verbose", "very-verbose", "VERY-VERBOSE", "Very-Verbose"})) { np.verbose = true; np.very_verbose = true; }
+}
+
+bool read_input_parameters(const std::string &dir, Case &c, const std::vector<PT> &pt, std::string &err) {
+    Lines f;
+    std::string path = dir + "/INPUT_PARAMETERS.txt";
+    if (!f.load(path)) { err = "File INPUT_PARAMETERS.txt is not found!"; return false; }
+    c.input_lines = f.l;
+    std::vector<std::string> t;
+    int line = 0;
+    auto fail = [&](const char *what) { err = std::string("Problem reading INPUT_PARAMETERS.txt in line ") + std::to_string(line) + ": " + what; return false; };
+    auto need = [&](size_t n) { ++line; return read_list(f, n, t) == 0; };
+    double M;
+    if (!need(1)) return fail("material name");
+    c.Material_name = t[0];
+    if (!need(1) || !parse_int(t[0], c.SHI.Zat)) return fail("SHI atomic number");
+    if (c.SHI.Zat > 0) {
+        int z = std::abs(c.SHI.Zat);
+        if (z >= (int)pt.size() || pt[z].mass <= 0) return fail("unknown SHI element");
+        c.SHI.Name = pt[z].name; c.SHI.Full_Name = pt[z].full; c.SHI.Mass = pt[z].mass;
+    }
+    if (!need(1) || !parse_real(t[0], c.SHI.E)) return fail("SHI energy");
+    c.SHI.E *= 1.0e6;
+    if (!need(1) || !parse_real(t[0], M)) return fail("SHI mass");
+    if (M > 0.0) c.SHI.Mass = M;
+    if (!need(1) || !parse_real(t[0], c.Tim)) return fail("total time");
+    if (!need(2) || !parse_real(t[0], c.dt) || !parse_int(t[1], c.numpar.dt_flag)) return fail("time step");
+    if (c.dt > c.Tim && c.numpar.dt_flag <= 0) c.dt = c.Tim;
+    if (c.dt < 2 && c.numpar.dt_flag >= 1) c.dt = 2;
+    if (!need(1) || !parse_real(t[0], c.Matter.cut_off)) return fail("cut-off");
+    if (!need(1) || !parse_real(t[0], c.Matter.Layer)) return fail("layer");
+    if (!need(1) || !parse_real(t[0], c.Matter.temp)) return fail("temperature");
+    if (!need(2) || !parse_int(t[0], c.SHI.Kind_Zeff) || !parse_real(t[1], c.SHI.fixed_Zeff)) return fail("Zeff kind");
+    if (c.SHI.fixed_Zeff <= 0.0 || c.SHI.fixed_Zeff > c.SHI.Zat) c.SHI.fixed_Zeff = c.SHI.Zat;
+    if (!need(1) || !parse_int(t[0], c.SHI.Kind_ion)) return fail("kind of ion");
+    if (!need(2) || !parse_int(t[0], c.numpar.kind_of_EMFP) || !parse_int(t[1], c.numpar.CDF_elast_Zeff)) return fail("elastic model");
+    if (!need(2) || !parse_int(t[0], c.numpar.kind_of_DR) || !parse_real(t[1], c.Matter.El_eff_mass)) return fail("dispersion relation");
+    if (c.numpar.kind_of_DR <= 0 || c.numpar.kind_of_DR > 4) c.numpar.kind_of_DR = 1;
+    if (c.Matter.El_eff_mass < 0) c.Matter.El_eff_mass = 1.0;
+    int tmp;
+    if (!need(1) || !parse_int(t[0], tmp)) return fail("plasmon flag");
+    c.numpar.plasmon_Emax = (tmp == 1);
+    if (!need(1) || !parse_real(t[0], c.Matter.hole_mass)) return fail("hole mass");
+    if (!need(1) || !parse_int(t[0], tmp)) return fail("photon flag");
+    c.numpar.include_photons = (tmp == 1);
+    if (!need(3) || !parse_real(t[0], c.Matter.work_function) || !parse_real(t[1], c.Matter.bar_length) || !parse_real(t[2], c.Matter.bar_height)) return fail("work function");
+    if (c.Matter.work_function <= 0.0) c.Matter.work_function = 0.0;
+    if (c.Matter.bar_length <= 0.0) c.Matter.work_function = 0.0;
+    if (c.Matter.bar_height <= 0.0) c.Matter.work_function = 0.0;
+    if (!need(1) || !parse_int(t[0], c.NMC)) return fail("NMC");
+    if (!need(1) || !parse_int(t[0], c.Num_th)) return fail("threads");
+    std::string s;
+    while (f.read_line(s)) interpret_flag(s, c.numpar);
+    return true;
+}
+
+// reading_material_parameters, Reading_files_and_parameters.f90:1185-1644 (full-CDF branch;
+// the single-pole/EADL-only branch needs EADL2023.ALL and is reported as unsupported)
+bool read_cdf(const std::string &dir, Case &c, const std::vector<PT> &pt, std::string &err) {
+    std::string name = c.numpar.CDF_file.empty() ? (c.Material_name + ".cdf") : c.numpar.CDF_file;
+    std::string path = dir + "/INPUT_CDF/" + name;
+    Lines f;
+    if (!f.load(path)) { err = "File " + path + " is not found!"; return false; }
+    c.numpar.CDF_file = "INPUT_CDF/" + name;
+    std::vector<std::string> t;
+    std::string s;
+    auto bad = [&](const std::string &w) { err = "Problem reading " + path + ": " + w; return false; };
+    // name line: text before '!' or TAB
+    if (!f.read_line(s)) return bad("empty file");
+    {
+        std::string nm = s;
+        size_t p = s.find('!');
+        if (p != std::string::npos && p >= 1) nm = s.substr(0, p);
+        size_t tb = s.find('\t');
+        if (tb != std::string::npos) { if (tb >= 1) nm = s.substr(0, tb); else nm = s.substr(1); }
+        size_t a = nm.find_first_not_of(" \t"), b = nm.find_last_not_of(" \t");
+        c.Matter.Target_name = (a == std::string::npos) ? "" : nm.substr(a, b - a + 1);
+    }
+    int N = 0;
+    if (read_list(f, 1, t) != 0) return bad("number of elements");
+    if (!parse_int(t[0], N)) return bad("chemical-formula .cdf files need EADL data (Decompose_compound); not supported");
+    if (N < 1 || N > TRK3_MAX_ATOMS) return bad("unsupported number of elements");
+    c.atoms.assign(N, Atom{});
+    c.Matter.Chem.clear();
+    for (int j = 0; j < N; ++j) {
+        Atom &a = c.atoms[j];
+        if (read_list(f, 2, t) != 0 || !parse_int(t[0], a.Zat) || !parse_real(t[1], a.Pers)) return bad("element line");
+        if (a.Zat <= 0 || a.Zat >= (int)pt.size() || pt[a.Zat].mass <= 0) return bad("unknown element");
+        a.Name = pt[a.Zat].name; a.Full_Name = pt[a.Zat].full; a.Mass = pt[a.Zat].mass;
+        char buf[64] = "";
+        if (std::fabs(a.Pers - 1.0) > 1.0e-6) std::snprintf(buf, sizeof buf, "%.2f", a.Pers);   // write(temp,'(f10.2)')
+        c.Matter.Chem += a.Name + buf;
+    }
+    // density, speed of sound, Fermi energy [, gap]: formatted read of one line, then list-directed from it
+    if (!f.read_line(s)) return bad("density line");
+    {
+        auto tk = tokens(s);
+        double v[4]; int got = 0;
+        for (size_t i = 0; i < tk.size() && got < 4; ++i) { if (parse_real(tk[i], v[got])) ++got; else break; }
+        if (got >= 4) { c.Matter.Dens = v[0]; c.Matter.Vsound = v[1]; c.Matter.E_F = v[2]; c.Matter.Egap = v[3]; }
+        else if (got == 3) { c.Matter.Dens = v[0]; c.Matter.Vsound = v[1]; c.Matter.E_F = v[2]; c.Matter.Egap = 0.0; }
+        else return bad("density line needs 'density v_sound E_fermi [E_gap]' (old-format file?)");
+        if (c.Matter.Egap < 1.0e-1) c.Matter.Egap = 1.0e-1;
+    }
+    {
+        double sm = 0, sp = 0;
+        for (auto &a : c.atoms) { sm += a.Mass * a.Pers; sp += a.Pers; }
+        c.Matter.At_Dens = 1.0e-3 * c.Matter.Dens / (g_Mp * sm / sp);
+        c.Matter.v_f = std::sqrt(2.0 * c.Matter.E_F / g_me);
+    }
+    // number of shells of the first element, or a keyword (single-pole mode)
+    if (!f.read_line(s)) return bad("shell block");
+    {
+        auto tk = tokens(s); int Shl;
+        if (tk.empty() || !parse_int(tk[0], Shl))
+            return bad("single-pole / VALENCE / PHONON keyword files need EADL2023.ALL (check_atomic_parameters, "
+                       "Dealing_with_EADL.f90:312) which is not available; not supported");
+        f.backspace();
+    }
+    c.numpar.kind_of_CDF = 0;
+    for (int j = 0; j < N; ++j) {
+        Atom &a = c.atoms[j];
+        int Shl;
+        if (read_list(f, 1, t) != 0 || !parse_int(t[0], Shl) || Shl < 1) return bad("number of shells");
+        a.Shell_name.assign(Shl, ""); a.Shl_num.assign(Shl, 0); a.Nel.assign(Shl, 0.0); a.Ip.assign(Shl, -1.0e15);
+        a.Ek.assign(Shl, -1.0e-15); a.Auger.assign(Shl, 1.0e31); a.Radiat.assign(Shl, 2.0e31); a.PQN.assign(Shl, 0);
+        a.KOCS.assign(Shl, 0); a.KOCS_SHI.assign(Shl, 0); a.Ritchi.assign(Shl, CDFosc{});
+        for (int k = 0; k < Shl; ++k) {
+            int ncdf, des;
+            if (read_list(f, 5, t) != 0 || !parse_int(t[0], ncdf) || !parse_int(t[1], des) || !parse_real(t[2], a.Ip[k]) ||
+                !parse_real(t[3], a.Nel[k]) || !parse_real(t[4], a.Auger[k])) return bad("shell line");
+            a.Shl_num[k] = std::abs(des);
+            define_PQN(a.Shl_num[k], a.Shell_name[k], a.PQN[k]);
+            if (a.Shl_num[k] >= 63) c.Matter.N_VB_el = a.Nel[k];
+            // check_atomic_parameters (Dealing_with_EADL.f90:350-370) without the EPICS files:
+            // only the decay times are decided here; Nel/Ip/Auger must come from the .cdf.
+            if (a.Nel[k] <= 0 || a.Ip[k] <= -1.0e-14) return bad("shell without Nel/Ip needs EADL2023.ALL; not supported");
+            if (a.Shl_num[k] >= 63 || !c.numpar.include_photons) a.Radiat[k] = 1.0e23;
+            else a.Radiat[k] = -1.0;                       // resolved by apply_radiative_data()
+            if (a.Shl_num[k] >= 63) a.Auger[k] = 1.0e23;
+            else if (a.Auger[k] <= 0.0 || a.Auger[k] > 1.0e30) return bad("shell without Auger time needs EADL2023.ALL; not supported");
+            if (a.Ip[k] < 1.0e-1) a.Ip[k] = 1.0e-1;
+            if (ncdf > 0) {
+                a.KOCS_SHI[k] = 1;
+                a.KOCS[k] = (des > 0) ? 1 : 2;
+                CDFosc &o = a.Ritchi[k];
+                o.E0.resize(ncdf); o.A.resize(ncdf); o.Gamma.resize(ncdf);
+                for (int l = 0; l < ncdf; ++l)
+                    if (read_list(f, 3, t) != 0 || !parse_real(t[0], o.E0[l]) || !parse_real(t[1], o.A[l]) || !parse_real(t[2], o.Gamma[l]))
+                        return bad("CDF oscillator line");
+            } else { a.KOCS[k] = 2; a.KOCS_SHI[k] = 2; }
+            if (a.KOCS[k] != 1 || a.KOCS_SHI[k] != 1) return bad("BEB shells (negative designator / no CDF) are not supported yet");
+        }
+    }
+    // phonon peaks (optional)
+    int ncdf = 0;
+    int reason = read_list(f, 1, t);
+    if (reason != 0) { c.numpar.kind_of_CDF_ph = 1; }
+    else if (!parse_int(t[0], ncdf)) { c.numpar.kind_of_CDF_ph = 1; return bad("phonon block"); }
+    else {
+        c.CDF_Phonon.E0.resize(ncdf); c.CDF_Phonon.A.resize(ncdf); c.CDF_Phonon.Gamma.resize(ncdf);
+        for (int l = 0; l < ncdf; ++l)
+            if (read_list(f, 3, t) != 0 || !parse_real(t[0], c.CDF_Phonon.E0[l]) || !parse_real(t[1], c.CDF_Phonon.A[l]) || !parse_real(t[2], c.CDF_Phonon.Gamma[l]))
+                return bad("phonon oscillator line");
+        c.numpar.kind_of_CDF_ph = 0;
+    }
+    if (c.numpar.kind_of_CDF_ph == 1) { c.CDF_Phonon.E0.assign(1, 0.0); c.CDF_Phonon.A.assign(1, 0.0); c.CDF_Phonon.Gamma.assign(1, 0.0); }
+    return true;
+}
+
+// Radiative decay times (Dealing_with_EADL.f90:350-360: t[fs] = 1e15*hbar/(e*Gamma_R[eV]); Gamma_R<1e-6 => 1.1e35).
+// EADL2023.ALL is not redistributable with the reference tree, so the widths are taken from an optional side-car
+//   INPUT_EADL/radiative_widths.dat :  "Z  designator  Gamma_R[eV]"  per line ('!' comments)
+// If a shell has no entry, the channel is closed (1e23 fs, the reference's value for "not included") and a warning is kept.
+void apply_radiative_data(const std::string &dir, Case &c) {
+    if (!c.numpar.include_photons) return;
+    struct W { int z, d; double g; };
+    std::vector<W> w;
+    Lines f;
+    if (f.load(dir + "/INPUT_EADL/radiative_widths.dat")) {
+        for (auto &s : f.l) {
+            auto t = tokens(s); W x;
+            if (t.size() >= 3 && parse_int(t[0], x.z) && parse_int(t[1], x.d) && parse_real(t[2], x.g)) w.push_back(x);
+        }
+    }
+    for (auto &a : c.atoms)
+        for (int k = 0; k < a.nshl(); ++k) {
+            if (a.Radiat[k] >= 0.0) continue;
+            bool found = false;
+            for (auto &x : w) if (x.z == a.Zat && x.d == a.Shl_num[k]) {
+                a.Radiat[k] = (x.g < 1.0e-6) ? 1.1e35 : 1.0e15 * g_h / (g_e * x.g);
+                found = true; break;
+            }
+            if (!found) {
+                a.Radiat[k] = 1.0e23;
+                c.warnings.push_back("no radiative width for Z=" + std::to_string(a.Zat) + " shell designator " + std::to_string(a.Shl_num[k]) +
+                                     " (EADL2023.ALL / radiative_widths.dat absent): radiative channel closed for this shell");
+            }
+        }
+}
+
+// Linear_approx_2d(Array, In_val, Value1, El1, El2), Reading_files_and_parameters.f90:3272
+double linear_approx_2d(const std::vector<double> &X, const std::vector<double> &Y, double v, double El1, double El2) {
+    int N = (int)X.size();
+    int num = find_monoton_2d(X.data(), 1, N, v);
+    if (num == 1) return El2 + (Y[0] - El2) / (X[0] - El1) * (v - El1);
+    if (Y[num - 2] > 1e20) return Y[num - 2];
+    return Y[num - 2] + (Y[num - 1] - Y[num - 2]) / (X[num - 1] - X[num - 2]) * (v - X[num - 2]);
+}
+
+// reading_material_DOS, Reading_files_and_parameters.f90:2317-2454
+bool read_dos(const std::string &dir, Case &c, std::string &err) {
+    std::string name = c.numpar.DOS_file.empty() ? (c.Material_name + ".dos") : c.numpar.DOS_file;
+    std::string path = dir + "/INPUT_DOS/" + name;
+    if (!file_exists(path)) {
+        std::string fr = dir + "/INPUT_DOS/Free_electron_DOS.dos";
+        if (!file_exists(fr)) { err = "Files " + path + " and " + fr + " are not found!"; return false; }
+        path = fr; name = "Free_electron_DOS.dos";
+    }
+    c.numpar.DOS_file = "INPUT_DOS/" + name;
+    Lines f;
+    if (!f.load(path)) { err = "cannot open " + path; return false; }
+    std::vector<double> X, Y;
+    // Count_lines_in_file counts records (list-directed empty reads); every record must then hold two reals
+    for (auto &s : f.l) {
+        auto t = tokens(s);
+        double a, b;
+        if (t.size() < 2 || !parse_real(t[0], a) || !parse_real(t[1], b)) {
+            if (t.empty()) continue;      // trailing blank record: a list-directed read would hit EOF instead
+            err = "Problem reading " + path; return false;
+        }
+        X.push_back(a); Y.push_back(b);
+    }
+    int N = (int)X.size();
+    if (N < 2) { err = "DOS file too short: " + path; return false; }
+    double top = X[N - 1];
+    for (auto &x : X) x = x - top;
+    const double dE = 0.1;
+    int M = (int)std::floor((X[N - 1] - X[0]) / dE);
+    DOS &d = c.dos;
+    d.E.assign(M, 0); d.dos.assign(M, 0); d.int_DOS.assign(M, 0); d.k.assign(M, 0); d.Eff_m.assign(M, 0);
+    d.DOS_inv.assign(M, 0); d.int_DOS_inv.assign(M, 0); d.k_inv.assign(M, 0); d.Eff_m_inv.assign(M, 0);
+    double E = X[0];
+    for (int i = 0; i < M; ++i) {
+        E = E + dE;
+        d.E[i] = E;
+        d.dos[i] = linear_approx_2d(X, Y, E, X[0] - dE, 0.0);
+    }
+    double Elast = d.E[M - 1];
+    for (auto &x : d.E) x = std::fabs(x - Elast);
+    std::reverse(d.E.begin(), d.E.end());
+    std::reverse(d.dos.begin(), d.dos.end());
+    d.DOS_inv = d.dos; std::reverse(d.DOS_inv.begin(), d.DOS_inv.end());
+    double s = 0, si = 0;
+    for (int i = 0; i < M; ++i) { s += d.dos[i]; d.int_DOS[i] = s; si += d.DOS_inv[i]; d.int_DOS_inv[i] = si; }
+    double SUM = d.int_DOS[M - 1];
+    for (int i = 0; i < M; ++i) { d.dos[i] = d.dos[i] / SUM * c.Matter.N_VB_el; d.int_DOS[i] = d.int_DOS[i] / SUM * c.Matter.N_VB_el; }
+    double spers = 0; for (auto &a : c.atoms) spers += a.Pers;
+    s = 0;
+    for (int i = 0; i < M; ++i) {
+        s += d.dos[i];
+        d.k[i] = std::pow(3.0 * 2.0 * g_Pi * g_Pi / 2.0 * s * c.Matter.At_Dens / spers * 1e6, 1.0 / 3.0);
+        if (d.E[i] < 1.0e-10) d.Eff_m[i] = 1.0;
+        else d.Eff_m[i] = g_h * g_h * d.k[i] * d.k[i] / (2.0 * d.E[i] * g_e) / g_me;
+    }
+    SUM = d.int_DOS_inv[M - 1];
+    for (int i = 0; i < M; ++i) { d.DOS_inv[i] = d.DOS_inv[i] / SUM * c.Matter.N_VB_el; d.int_DOS_inv[i] = d.int_DOS_inv[i] / SUM * c.Matter.N_VB_el; }
+    for (int i = 0; i < M; ++i) {
+        d.k_inv[i] = std::pow(3.0 * 2.0 * g_Pi * g_Pi / 2.0 * d.int_DOS_inv[i] * c.Matter.At_Dens / spers * 1e6, 1.0 / 3.0);
+        if (d.E[i] < 1.0e-10) d.Eff_m_inv[i] = 1.0;
+        else d.Eff_m_inv[i] = g_h * g_h * d.k_inv[i] * d.k_inv[i] / (2.0 * d.E[i] * g_e) / g_me;
+    }
+    return true;
+}
+
+}  // namespace
+
+void set_default_numpar(NumPar &np) { np = NumPar{}; }
+
+bool read_case(const std::string &dir, Case &c, std::string &err) {
+    c = Case{};
+    c.dir = dir;
+    set_default_numpar(c.numpar);
+    std::vector<PT> pt;
+    if (!load_periodic_table(dir, pt, err)) return false;
+    if (!read_input_parameters(dir, c, pt, err)) return false;
+    if (!read_cdf(dir, c, pt, err)) return false;
+    apply_radiative_data(dir, c);
+    if (c.SHI.Kind_ion == 1) { err = "Brandt-Kitagawa ion (Kind_ion=1) is not supported yet"; return false; }
+    if (c.numpar.kind_of_DR == 4) { err = "Delta-CDF (kind_of_DR=4) is not supported"; return false; }
+    if (c.numpar.kind_of_EMFP == 2) { err = "DSF elastic cross sections (kind_of_EMFP=2) need INPUT_DSF files; not supported"; return false; }
+    if (c.numpar.CDF_elast_Zeff >= 2) { err = "CDF_elast_Zeff=2/3 (form-factor / CDF screening) is not supported yet"; return false; }
+    if (c.numpar.CS_method != 1) { err = "only 'grid 1' (tabulated differential cross sections, the reference default) is supported"; return false; }
+    if (c.SHI.Zat > 0) {
+        // Reading_files_and_parameters.f90:509-535
+        const Atom &a1 = c.atoms[0];
+        double M = c.SHI.Mass * g_Mp;
+        double Emin = (M + g_me) * (M + g_me) / (M * g_me) * a1.Ip.back() / 4.0;
+        if (c.SHI.E <= Emin) { err = "The SHI energy is smaller than the minimum allowed energy"; return false; }
+        if (c.SHI.E >= 175.0e6 / 2.0 * c.SHI.Mass) { err = "The SHI energy is higher than the maximum allowed energy"; return false; }
+    }
+    if (!read_dos(dir, c, err)) return false;
+    return true;
+}
+
+}  // namespace trk3

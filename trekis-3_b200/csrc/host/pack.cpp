@@ -1,0 +1,89 @@
+// pack.cpp -- flatten the host data model (ragged Atom->Shell->array objects of the reference,
+// Objects.f90:184-275) into the SoA / CSR image declared in include/trekis3_gpu.h.
+#include "trk3_host.hpp"
+#include <cstring>
+
+namespace trk3 {
+
+namespace {
+void pack_rows(const DiffCS &d, std::vector<int64_t> &off, std::vector<double> &hw, std::vector<double> &L) {
+    for (auto &r : d.row) {
+        hw.insert(hw.end(), r.hw.begin(), r.hw.end());
+        L.insert(L.end(), r.L.begin(), r.L.end());
+        off.push_back((int64_t)hw.size());
+    }
+}
+}  // namespace
+
+void pack_case(const Case &c, Packed &p) {
+    p = Packed{};
+    trk3_config &g = p.cfg;
+    g.shi_E = c.SHI.E; g.shi_mass = c.SHI.Mass; g.shi_fixed_Zeff = c.SHI.fixed_Zeff; g.shi_Z = c.SHI.Zat; g.shi_kind_Zeff = c.SHI.Kind_Zeff;
+    g.Tim = c.Tim; g.dt = c.dt; g.dt_flag = c.numpar.dt_flag; g.include_photons = c.numpar.include_photons ? 1 : 0;
+    g.cut_off = c.Matter.cut_off; g.layer = c.Matter.Layer; g.hole_mass = c.Matter.hole_mass;
+    g.work_function = c.Matter.work_function; g.bar_length = c.Matter.bar_length; g.bar_height = c.Matter.bar_height;
+    g.kind_of_EMFP = c.numpar.kind_of_EMFP; g.seed = 20260101ull;
+
+    trk3_tables &t = p.tab;
+    const int Nat = (int)c.atoms.size();
+    t.n_atoms = Nat; t.n_shells = c.n_shells(); t.nshl_atom1 = c.atoms[0].nshl();
+    int s = 0;
+    for (int a = 0; a < Nat; ++a) {
+        const Atom &at = c.atoms[a];
+        t.atom_Z[a] = at.Zat; t.atom_nshl[a] = at.nshl(); t.atom_first[a] = s; t.atom_mass[a] = at.Mass; t.atom_pers[a] = at.Pers;
+        for (int k = 0; k < at.nshl(); ++k, ++s) {
+            t.shell_atom[s] = a; t.shell_num[s] = k; t.shell_Ip[s] = at.Ip[k]; t.shell_Nel[s] = at.Nel[k];
+            t.shell_auger[s] = at.Auger[k]; t.shell_radiat[s] = at.Radiat[k];
+            if (a == c.Lowest_Ip_At && k == c.Lowest_Ip_Shl) t.vb_shell = s;
+        }
+    }
+    const int NS = t.n_shells;
+    auto pack_mfp = [&](const std::vector<std::vector<MFP>> &T, std::vector<double> &E, std::vector<double> &L, std::vector<double> *dEdx) {
+        E = T[0][0].E;
+        const size_t N = E.size();
+        L.assign((size_t)NS * N, 0.0);
+        if (dEdx) dEdx->assign((size_t)NS * N, 0.0);
+        int q = 0;
+        for (int a = 0; a < Nat; ++a) for (int k = 0; k < c.atoms[a].nshl(); ++k, ++q) {
+            std::memcpy(&L[(size_t)q * N], T[a][k].L.data(), N * 8);
+            if (dEdx) std::memcpy(&(*dEdx)[(size_t)q * N], T[a][k].dEdx.data(), N * 8);
+        }
+    };
+    pack_mfp(c.Total_el_MFPs, p.ei_E, p.ei_L, nullptr);
+    pack_mfp(c.Total_Hole_MFPs, p.hi_E, p.hi_L, nullptr);
+    pack_mfp(c.SHI_MFP, p.shi_E, p.shi_L, &p.shi_dEdx);
+    if (!c.Total_Photon_MFPs.empty()) pack_mfp(c.Total_Photon_MFPs, p.ph_E, p.ph_L, nullptr);
+    p.ee_E = c.Elastic_MFP.E; p.ee_L = c.Elastic_MFP.L;
+    p.he_E = c.Elastic_Hole_MFP.E; p.he_L = c.Elastic_Hole_MFP.L;
+    // differential tables
+    p.dshi_off.push_back(0);
+    for (int a = 0; a < Nat; ++a) for (int k = 0; k < c.atoms[a].nshl(); ++k) {
+        const MFP &m = c.diff_SHI_MFP[a][k];
+        p.dshi_E.insert(p.dshi_E.end(), m.E.begin(), m.E.end());
+        p.dshi_L.insert(p.dshi_L.end(), m.L.begin(), m.L.end());
+        p.dshi_off.push_back((int64_t)p.dshi_E.size());
+    }
+    p.eid_off.push_back(0);
+    for (int a = 0; a < Nat; ++a) for (int k = 0; k < c.atoms[a].nshl(); ++k) pack_rows(c.EIdCS[a][k], p.eid_off, p.eid_hw, p.eid_L);
+    p.eed_off.push_back(0); pack_rows(c.EEdCS, p.eed_off, p.eed_hw, p.eed_L);
+    p.hid_off.push_back(0); pack_rows(c.HIdCS, p.hid_off, p.hid_hw, p.hid_L);
+    p.hed_off.push_back(0); pack_rows(c.HEdCS, p.hed_off, p.hed_hw, p.hed_L);
+    p.dos_E = c.dos.E; p.dos_DOS = c.dos.dos; p.dos_int = c.dos.int_DOS; p.dos_effm = c.dos.Eff_m;
+    p.out_R = c.Out_R; p.out_V = c.Out_V;
+
+    t.n_ei = (int)p.ei_E.size(); t.ei_E = p.ei_E.data(); t.ei_L = p.ei_L.data();
+    t.n_ee = (int)p.ee_E.size(); t.ee_E = p.ee_E.data(); t.ee_L = p.ee_L.data();
+    t.n_hi = (int)p.hi_E.size(); t.hi_E = p.hi_E.data(); t.hi_L = p.hi_L.data();
+    t.n_he = (int)p.he_E.size(); t.he_E = p.he_E.data(); t.he_L = p.he_L.data();
+    t.n_ph = (int)p.ph_E.size(); t.ph_E = p.ph_E.empty() ? nullptr : p.ph_E.data(); t.ph_L = p.ph_L.empty() ? nullptr : p.ph_L.data();
+    t.n_shi = (int)p.shi_E.size(); t.shi_E = p.shi_E.data(); t.shi_L = p.shi_L.data(); t.shi_dEdx = p.shi_dEdx.data();
+    t.dshi_off = p.dshi_off.data(); t.dshi_E = p.dshi_E.data(); t.dshi_L = p.dshi_L.data();
+    t.eid_off = p.eid_off.data(); t.eid_hw = p.eid_hw.data(); t.eid_L = p.eid_L.data();
+    t.eed_off = p.eed_off.data(); t.eed_hw = p.eed_hw.data(); t.eed_L = p.eed_L.data();
+    t.hid_off = p.hid_off.data(); t.hid_hw = p.hid_hw.data(); t.hid_L = p.hid_L.data();
+    t.hed_off = p.hed_off.data(); t.hed_hw = p.hed_hw.data(); t.hed_L = p.hed_L.data();
+    t.n_dos = (int)p.dos_E.size(); t.dos_E = p.dos_E.data(); t.dos_DOS = p.dos_DOS.data(); t.dos_int = p.dos_int.data(); t.dos_effm = p.dos_effm.data();
+    t.n_r = (int)p.out_R.size(); t.out_R = p.out_R.data(); t.out_V = p.out_V.data();
+}
+
+}  // namespace trk3
