@@ -1,0 +1,130 @@
+"""CUDA engine binding (libtrekis3_gpu.so).  There is no CPU fallback: every entry point raises
+if the CUDA library cannot be loaded or no GPU is present."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import Config, Tables, TallyLayout, Stats
+
+_lib = None
+
+
+def _gpu():
+    global _lib
+    if _lib is None:
+        path = _abi.lib_path("gpu")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: the CUDA engine has no CPU fallback. Build it with "
+                               "`python -c 'import __graft_entry__ as g; g.build()'`.")
+        lib = C.CDLL(path)
+        PD = C.POINTER(C.c_double)
+        lib.trk3_mc_create.argtypes = [C.POINTER(Config), C.POINTER(Tables), C.c_int, C.POINTER(C.c_void_p)]
+        lib.trk3_mc_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64, PD, C.POINTER(Stats)]
+        lib.trk3_mc_run_device.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Stats)]
+        lib.trk3_mc_device_tallies.restype = C.c_void_p
+        lib.trk3_mc_device_tallies.argtypes = [C.c_void_p]
+        lib.trk3_mc_zero_device_tallies.argtypes = [C.c_void_p]
+        lib.trk3_mc_download_tallies.argtypes = [C.c_void_p, PD]
+        lib.trk3_mc_iteration_energies.argtypes = [C.c_void_p, PD, C.c_int64, C.POINTER(C.c_int64)]
+        lib.trk3_mc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        lib.trk3_mc_layout.restype = C.POINTER(TallyLayout)
+        lib.trk3_mc_layout.argtypes = [C.c_void_p]
+        lib.trk3_mc_last_error.restype = C.c_char_p
+        lib.trk3_mc_last_error.argtypes = [C.c_void_p]
+        lib.trk3_mc_destroy.argtypes = [C.c_void_p]
+        lib.trk3_gpu_version.restype = C.c_char_p
+        _lib = lib
+    return _lib
+
+
+def gpu_library_loaded():
+    """True once libtrekis3_gpu.so is mapped into this process (used by tests to prove no fallback ran)."""
+    return _lib is not None
+
+
+class Engine:
+    """One engine per GPU: tables uploaded once, iterations run in batches of wavefronts."""
+
+    def __init__(self, case, device=-1, seed=None, **options):
+        lib = _gpu()
+        self.case = case
+        cfg = Config.from_buffer_copy(case.config)
+        if seed is not None:
+            cfg.seed = int(seed)
+        self._cfg = cfg
+        h = C.c_void_p()
+        rc = lib.trk3_mc_create(C.byref(cfg), C.byref(case.tables), int(device), C.byref(h))
+        if rc != 0 or not h:
+            msg = lib.trk3_mc_last_error(h).decode() if h else "no engine"
+            raise RuntimeError(f"trk3_mc_create failed ({rc}): {msg}")
+        self._h = h
+        self.layout = lib.trk3_mc_layout(h).contents
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def set_option(self, name, value):
+        rc = _gpu().trk3_mc_set_option(self._h, name.encode(), float(value))
+        if rc != 0:
+            raise KeyError(name)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {_gpu().trk3_mc_last_error(self._h).decode()}")
+
+    def run(self, it_begin, it_end, tallies=None):
+        """Run iterations [it_begin, it_end); host buffers in, host buffers out (copies inside)."""
+        if tallies is None:
+            tallies = np.zeros(self.layout.total, dtype=np.float64)
+        st = Stats()
+        self._check(_gpu().trk3_mc_run(self._h, int(it_begin), int(it_end),
+                                       tallies.ctypes.data_as(C.POINTER(C.c_double)), C.byref(st)), "trk3_mc_run")
+        return tallies, st.as_dict()
+
+    def run_device(self, it_begin, it_end):
+        st = Stats()
+        self._check(_gpu().trk3_mc_run_device(self._h, int(it_begin), int(it_end), C.byref(st)), "trk3_mc_run_device")
+        return st.as_dict()
+
+    def device_tallies_ptr(self):
+        return _gpu().trk3_mc_device_tallies(self._h)
+
+    def zero_device_tallies(self):
+        self._check(_gpu().trk3_mc_zero_device_tallies(self._h), "zero")
+
+    def download_tallies(self, into=None):
+        if into is None:
+            into = np.zeros(self.layout.total, dtype=np.float64)
+        self._check(_gpu().trk3_mc_download_tallies(self._h, into.ctypes.data_as(C.POINTER(C.c_double))), "download")
+        return into
+
+    def iteration_energies(self, n_max):
+        buf = np.zeros((n_max, self.layout.Nt), dtype=np.float64)
+        n = C.c_int64()
+        self._check(_gpu().trk3_mc_iteration_energies(self._h, buf.ctypes.data_as(C.POINTER(C.c_double)), buf.size,
+                                                      C.byref(n)), "iteration_energies")
+        return buf[: n.value]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _gpu().trk3_mc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def do_Monte_Carlo(case, NMC=None, device=-1, seed=None, it_begin=0, **options):
+    """Replacement of `call do_Monte_Carlo(NMC, SHI, ...)` (Monte_Carlo.f90:39): returns the summed
+    Out_* tallies (not yet divided by NMC, as in the reference) and the run statistics."""
+    n = int(NMC if NMC is not None else case.get("NMC"))
+    eng = Engine(case, device=device, seed=seed, **options)
+    try:
+        tallies, stats = eng.run(it_begin, it_begin + n)
+    finally:
+        eng.close()
+    return tallies, stats
