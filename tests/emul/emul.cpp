@@ -1,0 +1,96 @@
+// emul.cpp -- TEST INFRASTRUCTURE: CPU emulation of the wavefront engine.
+//
+// Compiles the very same physics.cuh / finalize.cuh that the CUDA kernels are built from, with a
+// context whose side effects are plain host operations, and drives it generation by generation like
+// engine.cu does.  It exists because the development container has no GPU: the no-GPU test-suite uses
+// it to check the wavefront re-formulation (independent histories + snapshots + per-iteration
+// normalisation) against the time-ordered oracle.  It is never reachable from the product API.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "../../trekis-3_b200/csrc/cuda/physics.cuh"
+#include "../../trekis-3_b200/csrc/cuda/finalize.cuh"
+#include "../../trekis-3_b200/csrc/cuda/engine_host.h"
+
+using namespace trk3;
+
+namespace {
+struct EmuCtx {
+    const DevP &p;
+    std::vector<Rec> *next;     // [N_SPECIES]
+    unsigned long long *ev, *er, *nel, *nph;
+    void push(int sp, const Rec &r) { next[sp].push_back(r); }
+    void tally(int id, int64_t idx, double v) { p.tally[p.g_off[id] + idx] += v; }
+    void add_u32(uint32_t *b, size_t i) { b[i] += 1u; }
+    void add_f64(double *b, size_t i, double v) { b[i] += v; }
+    void event(int c) { ev[c]++; }
+    void error(int c) { er[c]++; }
+    void count_electron() { (*nel)++; }
+    void count_photon() { (*nph)++; }
+};
+}  // namespace
+
+extern "C" int trk3_emul_run(const trk3_config *cfg, const trk3_tables *tab, int64_t it_begin, int64_t it_end, int batch,
+                             double *tallies, trk3_stats *stats, double *iter_totE, double *iter_totNel) {
+    trk3_tally_layout lay;
+    int rc = trk3_tally_layout_init(cfg, tab, &lay);
+    if (rc != TRK3_OK) return rc;
+    DevP p;
+    rc = fill_devp_scalars(*cfg, *tab, lay, p);
+    if (rc != TRK3_OK) return rc;
+    HostTotals tot; compute_totals(*tab, tot);
+    p.ei_E = tab->ei_E; p.ei_L = tab->ei_L; p.ei_tot = tot.ei_tot.data(); p.ee_E = tab->ee_E; p.ee_L = tab->ee_L;
+    p.hi_E = tab->hi_E; p.hi_L = tab->hi_L; p.hi_tot = tot.hi_tot.data(); p.he_E = tab->he_E; p.he_L = tab->he_L;
+    p.ph_E = tab->ph_E; p.ph_L = tab->ph_L; p.ph_tot = tot.ph_tot.data();
+    p.shi_E = tab->shi_E; p.shi_L = tab->shi_L; p.shi_tot = tot.shi_tot.data();
+    p.dshi_off = tab->dshi_off; p.dshi_E = tab->dshi_E; p.dshi_L = tab->dshi_L;
+    p.eid_off = tab->eid_off; p.eid_hw = tab->eid_hw; p.eid_L = tab->eid_L; p.eed_off = tab->eed_off; p.eed_hw = tab->eed_hw; p.eed_L = tab->eed_L;
+    p.hid_off = tab->hid_off; p.hid_hw = tab->hid_hw; p.hid_L = tab->hid_L; p.hed_off = tab->hed_off; p.hed_hw = tab->hed_hw; p.hed_L = tab->hed_L;
+    p.dos_E = tab->dos_E; p.dos_DOS = tab->dos_DOS; p.dos_int = tab->dos_int; p.dos_effm = tab->dos_effm; p.out_R = tab->out_R; p.out_V = tab->out_V;
+    p.tally = tallies;
+    unsigned long long ev[TRK3_N_EVENT_CLASSES] = {0}, er[TRK3_N_ERRORS] = {0}, nel = 0, nph = 0;
+    uint64_t waves = 0;
+    if (batch < 1) batch = 64;
+    const int Nt = lay.Nt;
+    std::vector<double> Dcoef(Nt, 0.0);
+    for (int i = 0; i < Nt; ++i) Dcoef[i] = 0.0;
+    for (int64_t b0 = it_begin; b0 < it_end; b0 += batch) {
+        const uint32_t nb = (uint32_t)std::min<int64_t>(batch, it_end - b0);
+        p.batch_begin = (uint32_t)b0; p.batch_n = nb;
+        ScratchLayout sl = scratch_layout(p, nb);
+        std::vector<uint32_t> U(sl.u32_total, 0u); std::vector<double> D(sl.f64_total, 0.0);
+        bind_scratch(p, sl, U.data(), D.data());
+        std::vector<Rec> cur[N_SPECIES], nxt[N_SPECIES];
+        EmuCtx c{p, nxt, ev, er, &nel, &nph};
+        for (uint32_t k = 0; k < nb; ++k) shi_history(c, (uint32_t)(b0 + k));
+        for (;;) {
+            size_t n = 0;
+            for (int s = 0; s < N_SPECIES; ++s) { cur[s].swap(nxt[s]); nxt[s].clear(); n += cur[s].size(); }
+            if (!n) break;
+            ++waves;
+            for (Rec r : cur[SP_ELECTRON]) { int ig; begin_electron(c, r, ig); while (step_electron(c, r, ig)) {} }
+            for (Rec r : cur[SP_VBHOLE]) { int ig = interval_of(p, r.t0); while (step_vbhole(c, r, ig)) {} }
+            for (Rec r : cur[SP_COREHOLE]) { int ig = interval_of(p, r.t0); while (step_corehole(c, r, ig)) {} }
+            for (Rec r : cur[SP_PHOTON]) { int ig = interval_of(p, r.t0); while (step_photon(c, r, ig)) {} }
+        }
+        std::vector<double> a0((size_t)nb * Nt), a1((size_t)nb * Nt), a2((size_t)nb * Nt), a3((size_t)nb * Nt), a4((size_t)nb * Nt);
+        FoldAux fa{a0.data(), a1.data(), a2.data(), a3.data(), a4.data()};
+        for (uint32_t il = 0; il < nb; ++il) iter_prefix(p, fa, il);
+        for (int64_t j = 0, nj = fold_num_jobs(p); j < nj; ++j) fold_job(p, fa, j);
+        for (uint32_t il = 0; il < nb; ++il) for (int i = 0; i < Nt; ++i) {
+            size_t o = (size_t)il * Nt + i;
+            Dcoef[i] = Dcoef[i] + p.it.diffS[o];
+            if (p.it.diffN[o] > 0) Dcoef[i] = Dcoef[i] / (double)p.it.diffN[o];
+            if (iter_totE) iter_totE[(size_t)(b0 - it_begin + il) * Nt + i] = a1[o];
+            if (iter_totNel) iter_totNel[(size_t)(b0 - it_begin + il) * Nt + i] = a0[o];
+        }
+    }
+    for (int i = 0; i < Nt; ++i) tallies[lay.off[TRK3_OUT_DIFF_COEFF] + i] += Dcoef[i];
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        for (int q = 0; q < TRK3_N_EVENT_CLASSES; ++q) stats->events[q] = ev[q];
+        for (int q = 0; q < TRK3_N_ERRORS; ++q) stats->errors[q] = er[q];
+        stats->n_electrons = nel; stats->n_photons = nph; stats->n_waves = waves;
+    }
+    return TRK3_OK;
+}

@@ -1,0 +1,551 @@
+// engine.cu -- B200 (sm_100a) wavefront Monte-Carlo engine behind the C ABI of include/trekis3_gpu.h.
+//
+// Replaces do_Monte_Carlo / Monte_Carlo_modelling (Monte_Carlo.f90:39-679).  Structure:
+//   * a batch of iterations is in flight at once; the ion tracks of the batch are walked by k_shi,
+//     which fills the first generation of the species queues (electrons, valence holes, core holes);
+//   * k_wave<species> consumes one generation: a warp pulls records from the queue (one atomic per
+//     refill, lanes that finish are refilled so warps stay full), every lane follows its particle to
+//     the end of its history with the state in registers, secondaries are appended to the
+//     next-generation queues with warp-aggregated atomics (one atomicAdd per species per warp);
+//   * radial x time tallies are accumulated in a shared-memory private copy per block and flushed once
+//     per block; spectra that the reference normalises per iteration go to per-iteration integer
+//     histograms and are folded by k_fold (no atomics, fixed summation order);
+//   * the tally sums stay in one packed device buffer so that multi-GPU runs need a single all-reduce.
+// No tensor cores: nothing here is a dense contraction.  No CPU fallback: every entry point fails if CUDA does.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "physics.cuh"
+#include "finalize.cuh"
+#include "engine_host.h"
+
+using namespace trk3;
+
+__constant__ DevP c_p;
+
+struct QueueSet { Queue q[N_SPECIES]; };
+
+#define TRK_BLOCK 128
+#define S_EV 0                      // s_cnt layout: events[TRK3_N_EVENT_CLASSES], n_el, n_ph
+#define S_NEL TRK3_N_EVENT_CLASSES
+#define S_NPH (TRK3_N_EVENT_CLASSES + 1)
+#define S_NCNT (TRK3_N_EVENT_CLASSES + 2)
+
+// ------------------------------------------------------------------------------------------------
+// device context: the side effects of physics.cuh
+// ------------------------------------------------------------------------------------------------
+struct DevCtx {
+    const DevP &p;
+    const QueueSet &out;
+    double *s_tally;        // block-private tallies (nullptr: straight to global)
+    unsigned int *s_cnt;
+
+    __device__ void push(int sp, const Rec &r) {
+        // warp-aggregated append: lanes pushing to the same species share one atomicAdd
+        const unsigned am = __activemask();
+        const unsigned m = __match_any_sync(am, sp);
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(m) - 1;
+        const Queue &q = out.q[sp];
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(q.count, (unsigned)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
+        if (slot >= q.cap) { atomicAdd(&p.errors[TRK3_ERR_QUEUE_OVERFLOW], 1ull); return; }
+        q.col[0][slot] = r.E; q.col[1][slot] = r.Ehkin; q.col[2][slot] = r.Mass; q.col[3][slot] = r.t0; q.col[4][slot] = r.tn;
+        q.col[5][slot] = r.X; q.col[6][slot] = r.Y; q.col[7][slot] = r.Z; q.col[8][slot] = r.L; q.col[9][slot] = r.theta; q.col[10][slot] = r.phi;
+        q.id[slot] = r.id; q.ctr[slot] = r.ctr; q.iter[slot] = r.iter; q.shell[slot] = r.shell;
+    }
+    __device__ void tally(int id, int64_t idx, double v) {
+        const int so = p.s_off[id];
+        if (s_tally && so >= 0) atomicAdd(&s_tally[so + idx], v);
+        else atomicAdd(&p.tally[p.g_off[id] + idx], v);
+    }
+    __device__ void add_u32(uint32_t *b, size_t i) { atomicAdd(b + i, 1u); }
+    __device__ void add_f64(double *b, size_t i, double v) { atomicAdd(b + i, v); }
+    __device__ void event(int cls) { atomicAdd(&s_cnt[S_EV + cls], 1u); }
+    __device__ void error(int code) { atomicAdd(&p.errors[code], 1ull); }
+    __device__ void count_electron() { atomicAdd(&s_cnt[S_NEL], 1u); }
+    __device__ void count_photon() { atomicAdd(&s_cnt[S_NPH], 1u); }
+};
+
+__device__ inline void load_rec(const Queue &q, uint32_t i, Rec &r) {
+    r.E = q.col[0][i]; r.Ehkin = q.col[1][i]; r.Mass = q.col[2][i]; r.t0 = q.col[3][i]; r.tn = q.col[4][i];
+    r.X = q.col[5][i]; r.Y = q.col[6][i]; r.Z = q.col[7][i]; r.L = q.col[8][i]; r.theta = q.col[9][i]; r.phi = q.col[10][i];
+    r.id = q.id[i]; r.ctr = q.ctr[i]; r.iter = q.iter[i]; r.shell = q.shell[i];
+}
+
+__device__ inline void block_prologue(double *s_tally, unsigned int *s_cnt, int s_total) {
+    for (int i = threadIdx.x; i < s_total; i += blockDim.x) s_tally[i] = 0.0;
+    if (threadIdx.x < S_NCNT) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+}
+__device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned int *s_cnt) {
+    __syncthreads();
+    if (s_tally) {
+        // flush the private copy once per block (non-zero bins only)
+        for (int id = 0; id < TRK3_N_TALLIES; ++id) {
+            const int so = p.s_off[id];
+            if (so < 0) continue;
+            double *g = p.tally + p.g_off[id];
+            for (int i = threadIdx.x; i < p.s_len[id]; i += blockDim.x) {
+                const double v = s_tally[so + i];
+                if (v != 0.0) atomicAdd(g + i, v);
+            }
+        }
+    }
+    if (threadIdx.x < TRK3_N_EVENT_CLASSES) { unsigned v = s_cnt[S_EV + threadIdx.x]; if (v) atomicAdd(&p.events[threadIdx.x], (unsigned long long)v); }
+    if (threadIdx.x == 0) {
+        if (s_cnt[S_NEL]) atomicAdd(p.cnt_el, (unsigned long long)s_cnt[S_NEL]);
+        if (s_cnt[S_NPH]) atomicAdd(p.cnt_ph, (unsigned long long)s_cnt[S_NPH]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+// k_shi: the ion track of every iteration of the batch (SHI_Monte_Carlo, Monte_Carlo.f90:2153-2249).
+__global__ void __launch_bounds__(32) k_shi(QueueSet qout) {
+    __shared__ unsigned int s_cnt[S_NCNT];
+    block_prologue(nullptr, s_cnt, 0);
+    DevCtx c{c_p, qout, nullptr, s_cnt};
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < c_p.batch_n) shi_history(c, c_p.batch_begin + k);
+    block_epilogue(c_p, nullptr, s_cnt);
+}
+
+// k_wave<SP>: one generation of species SP, histories run to completion with lane refill.
+template <int SP>
+__global__ void __launch_bounds__(TRK_BLOCK) k_wave(Queue qin, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min) {
+    extern __shared__ double s_dyn[];
+    __shared__ unsigned int s_cnt[S_NCNT];
+    double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
+    block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? c_p.s_total : 0);
+    DevCtx c{c_p, qout, s_tally, s_cnt};
+    const int lane = threadIdx.x & 31;
+    bool active = false, exhausted = false;
+    Rec r;
+    int ig = 0;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle && !exhausted && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
+            const int nidle = __popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(head, (uint32_t)nidle);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + (uint32_t)nidle >= n_in) exhausted = true;
+            if (!active) {
+                const uint32_t my = base + __popc(idle & ((1u << lane) - 1u));
+                if (my < n_in) {
+                    load_rec(qin, my, r);
+                    active = true;
+                    if (SP == SP_ELECTRON) begin_electron(c, r, ig);
+                    else ig = interval_of(c_p, r.t0);
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; continue; }
+        if (active) {
+            bool cont;
+            if (SP == SP_ELECTRON) cont = step_electron(c, r, ig);
+            else if (SP == SP_VBHOLE) cont = step_vbhole(c, r, ig);
+            else if (SP == SP_COREHOLE) cont = step_corehole(c, r, ig);
+            else cont = step_photon(c, r, ig);
+            if (!cont) active = false;
+        }
+    }
+    block_epilogue(c_p, s_tally, s_cnt);
+}
+
+__global__ void k_iter_prefix(FoldAux a) {
+    const uint32_t il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il < c_p.batch_n) iter_prefix(c_p, a, il);
+}
+__global__ void k_fold(FoldAux a, int64_t njobs) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < njobs) fold_job(c_p, a, j);
+}
+__global__ void k_axpy(double *dst, const double *src, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct trk3_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    trk3_config cfg{};
+    trk3_tally_layout lay{};
+    DevP hp{};                         // host image of c_p (device pointers inside)
+    std::vector<void *> allocs;
+    double nel_est = 1000.0;
+    // options
+    int opt_batch = 512, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 4096;
+    double opt_cap_factor = 2.0;
+    size_t opt_queue_bytes_max = (size_t)24 << 30;
+    // per-batch resources
+    uint32_t nb_alloc = 0;
+    QueueSet qs[2]{};
+    uint32_t *d_qcount = nullptr;      // [2][N_SPECIES] counts + [N_SPECIES] heads
+    uint32_t *d_u32 = nullptr; double *d_f64 = nullptr; ScratchLayout sl{};
+    FoldAux fa{};
+    double *d_tally = nullptr, *d_small = nullptr, *d_tally_bak = nullptr;
+    unsigned long long *d_counters = nullptr, *d_counters_bak = nullptr;      // events, errors, n_el, n_ph
+    int n_sm = 0, smem_optin = 0;
+    // results
+    std::vector<double> iter_totE;
+    std::vector<double> Dcoef;
+    std::string err;
+    uint64_t launches = 0;
+};
+
+namespace {
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { eng->err = std::string(#call) + ": " + cudaGetErrorString(e_); return TRK3_E_CUDA; } } while (0)
+
+template <class T>
+int dev_alloc(trk3_engine *eng, T **p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    CK(cudaMalloc((void **)p, n * sizeof(T)));
+    eng->allocs.push_back((void *)*p);
+    return TRK3_OK;
+}
+template <class T>
+int dev_upload(trk3_engine *eng, const T **dst, const T *src, size_t n) {
+    T *d = nullptr;
+    int rc = dev_alloc(eng, &d, n);
+    if (rc) return rc;
+    if (n && src) CK(cudaMemcpy(d, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = d;
+    return TRK3_OK;
+}
+void dev_free(trk3_engine *eng, void *p) {
+    if (!p) return;
+    cudaFree(p);
+    eng->allocs.erase(std::remove(eng->allocs.begin(), eng->allocs.end(), p), eng->allocs.end());
+}
+
+int alloc_queue(trk3_engine *eng, Queue &q, uint32_t cap, uint32_t *count) {
+    q.cap = cap; q.count = count;
+    for (int k = 0; k < TRK_NCOL; ++k) { int rc = dev_alloc(eng, &q.col[k], cap); if (rc) return rc; }
+    int rc;
+    if ((rc = dev_alloc(eng, &q.id, cap))) return rc;
+    if ((rc = dev_alloc(eng, &q.ctr, cap))) return rc;
+    if ((rc = dev_alloc(eng, &q.iter, cap))) return rc;
+    if ((rc = dev_alloc(eng, &q.shell, cap))) return rc;
+    return TRK3_OK;
+}
+void free_queue(trk3_engine *eng, Queue &q) {
+    for (int k = 0; k < TRK_NCOL; ++k) { dev_free(eng, q.col[k]); q.col[k] = nullptr; }
+    dev_free(eng, q.id); dev_free(eng, q.ctr); dev_free(eng, q.iter); dev_free(eng, q.shell);
+    q.id = nullptr; q.ctr = nullptr; q.iter = nullptr; q.shell = nullptr; q.cap = 0;
+}
+
+// per-iteration capacities of the species queues (records of ONE generation)
+void queue_caps(const trk3_engine *eng, double cap[N_SPECIES]) {
+    const double n = eng->nel_est * eng->opt_cap_factor + 512.0;
+    cap[SP_ELECTRON] = n; cap[SP_VBHOLE] = n; cap[SP_COREHOLE] = 0.5 * n + 256.0;
+    cap[SP_PHOTON] = eng->cfg.include_photons ? 0.25 * n + 64.0 : 1.0;
+}
+
+int ensure_batch(trk3_engine *eng, uint32_t nb) {
+    if (nb <= eng->nb_alloc) return TRK3_OK;
+    // release the previous batch resources
+    for (int b = 0; b < 2; ++b) for (int s = 0; s < N_SPECIES; ++s) free_queue(eng, eng->qs[b].q[s]);
+    dev_free(eng, eng->d_u32); dev_free(eng, eng->d_f64);
+    dev_free(eng, eng->fa.totnel); dev_free(eng, eng->fa.totE); dev_free(eng, eng->fa.latcum); dev_free(eng, eng->fa.emcnt); dev_free(eng, eng->fa.emE);
+    eng->d_u32 = nullptr; eng->d_f64 = nullptr; eng->fa = FoldAux{};
+    double cap[N_SPECIES]; queue_caps(eng, cap);
+    for (int b = 0; b < 2; ++b) for (int s = 0; s < N_SPECIES; ++s) {
+        double c = cap[s] * (double)nb;
+        if (c > 4.0e9) { eng->err = "queue capacity exceeds 2^32 records; lower the batch"; return TRK3_E_NOMEM; }
+        int rc = alloc_queue(eng, eng->qs[b].q[s], (uint32_t)c, eng->d_qcount + b * N_SPECIES + s);
+        if (rc) return rc;
+    }
+    eng->sl = scratch_layout(eng->hp, nb);
+    int rc;
+    if ((rc = dev_alloc(eng, &eng->d_u32, eng->sl.u32_total))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_f64, eng->sl.f64_total))) return rc;
+    const size_t n = (size_t)nb * eng->lay.Nt;
+    if ((rc = dev_alloc(eng, &eng->fa.totnel, n))) return rc;
+    if ((rc = dev_alloc(eng, &eng->fa.totE, n))) return rc;
+    if ((rc = dev_alloc(eng, &eng->fa.latcum, n))) return rc;
+    if ((rc = dev_alloc(eng, &eng->fa.emcnt, n))) return rc;
+    if ((rc = dev_alloc(eng, &eng->fa.emE, n))) return rc;
+    bind_scratch(eng->hp, eng->sl, eng->d_u32, eng->d_f64);
+    eng->nb_alloc = nb;
+    return TRK3_OK;
+}
+
+template <int SP>
+int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t n, uint32_t *head, const QueueSet &qout) {
+    size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
+    int use_smem = eng->opt_use_smem;
+    const size_t smem_max = (size_t)eng->smem_optin - 1024;             // static shared memory + driver reserve
+    if (smem > smem_max) { smem = 8; use_smem = 0; }                    // too many output times for shared memory: global atomics
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_wave<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = eng->opt_blocks_per_sm;
+    if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_wave<SP>, TRK_BLOCK, smem)); if (bps < 1) bps = 1; }
+    // persistent-style grid: a multiple of the SM count, never more blocks than there is work for
+    uint32_t want = (n + TRK_BLOCK - 1) / TRK_BLOCK;
+    uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
+    if (grid < 1) grid = 1;
+    k_wave<SP><<<grid, TRK_BLOCK, smem, eng->stream>>>(qin, n, head, qout, use_smem, eng->opt_refill_min);
+    CK(cudaGetLastError());
+    eng->launches++;
+    return TRK3_OK;
+}
+}  // namespace
+
+extern "C" {
+
+const char *trk3_gpu_version(void) { return "trekis3_gpu 0.1 (sm_100a wavefront Monte-Carlo engine)"; }
+
+int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, trk3_engine **out) {
+    if (!cfg || !tab || !out) return TRK3_E_INVALID;
+    *out = nullptr;
+    trk3_engine *eng = new trk3_engine();
+    *out = eng;                                   // returned even on failure so that the caller can read last_error
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { eng->err = "no CUDA device: the engine has no CPU fallback"; return TRK3_E_CUDA; }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    eng->device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    eng->n_sm = prop.multiProcessorCount;
+    eng->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    eng->cfg = *cfg;
+    int rc = trk3_tally_layout_init(cfg, tab, &eng->lay);
+    if (rc != TRK3_OK) { eng->err = "invalid time grid / layout"; return rc; }
+    rc = fill_devp_scalars(*cfg, *tab, eng->lay, eng->hp);
+    if (rc != TRK3_OK) { eng->err = (rc == TRK3_E_UNSUPPORTED) ? "unsupported option (DSF elastic scattering)" : "invalid tables"; return rc; }
+    CK(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&eng->ev0)); CK(cudaEventCreate(&eng->ev1));
+    DevP &p = eng->hp;
+    HostTotals tot; compute_totals(*tab, tot);
+    const size_t NS = tab->n_shells;
+#define UP(dst, src, n) do { rc = dev_upload(eng, &p.dst, src, (size_t)(n)); if (rc) return rc; } while (0)
+    UP(ei_E, tab->ei_E, tab->n_ei); UP(ei_L, tab->ei_L, NS * tab->n_ei); UP(ei_tot, tot.ei_tot.data(), tab->n_ei);
+    UP(ee_E, tab->ee_E, tab->n_ee); UP(ee_L, tab->ee_L, tab->n_ee);
+    UP(hi_E, tab->hi_E, tab->n_hi); UP(hi_L, tab->hi_L, NS * tab->n_hi); UP(hi_tot, tot.hi_tot.data(), tab->n_hi);
+    UP(he_E, tab->he_E, tab->n_he); UP(he_L, tab->he_L, tab->n_he);
+    UP(ph_E, tab->ph_E, tab->n_ph); UP(ph_L, tab->ph_L, NS * tab->n_ph); UP(ph_tot, tot.ph_tot.data(), tab->n_ph);
+    UP(shi_E, tab->shi_E, tab->n_shi); UP(shi_L, tab->shi_L, NS * tab->n_shi); UP(shi_tot, tot.shi_tot.data(), tab->n_shi);
+    UP(dshi_off, tab->dshi_off, NS + 1); UP(dshi_E, tab->dshi_E, tab->dshi_off[NS]); UP(dshi_L, tab->dshi_L, tab->dshi_off[NS]);
+    const size_t n_eid = NS * tab->n_ei;
+    UP(eid_off, tab->eid_off, n_eid + 1); UP(eid_hw, tab->eid_hw, tab->eid_off[n_eid]); UP(eid_L, tab->eid_L, tab->eid_off[n_eid]);
+    UP(eed_off, tab->eed_off, tab->n_ee + 1); UP(eed_hw, tab->eed_hw, tab->eed_off[tab->n_ee]); UP(eed_L, tab->eed_L, tab->eed_off[tab->n_ee]);
+    UP(hid_off, tab->hid_off, tab->n_hi + 1); UP(hid_hw, tab->hid_hw, tab->hid_off[tab->n_hi]); UP(hid_L, tab->hid_L, tab->hid_off[tab->n_hi]);
+    UP(hed_off, tab->hed_off, tab->n_he + 1); UP(hed_hw, tab->hed_hw, tab->hed_off[tab->n_he]); UP(hed_L, tab->hed_L, tab->hed_off[tab->n_he]);
+    UP(dos_E, tab->dos_E, tab->n_dos); UP(dos_DOS, tab->dos_DOS, tab->n_dos); UP(dos_int, tab->dos_int, tab->n_dos); UP(dos_effm, tab->dos_effm, tab->n_dos);
+    UP(out_R, tab->out_R, tab->n_r); UP(out_V, tab->out_V, tab->n_r);
+#undef UP
+    if ((rc = dev_alloc(eng, &eng->d_tally, (size_t)eng->lay.total))) return rc;
+    CK(cudaMemset(eng->d_tally, 0, (size_t)eng->lay.total * sizeof(double)));
+    if ((rc = dev_alloc(eng, &eng->d_tally_bak, (size_t)eng->lay.total))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_small, (size_t)TRK3_MAX_NT))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_counters, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 2)))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_counters_bak, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 2)))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_qcount, (size_t)(3 * N_SPECIES)))) return rc;
+    p.tally = eng->d_tally;
+    p.events = eng->d_counters; p.errors = eng->d_counters + TRK3_N_EVENT_CLASSES;
+    p.cnt_el = eng->d_counters + TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS; p.cnt_ph = p.cnt_el + 1;
+    eng->nel_est = estimate_nel(*cfg, *tab);
+    return TRK3_OK;
+}
+
+int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
+    if (!eng || !name) return TRK3_E_INVALID;
+    std::string k(name);
+    if (k == "batch") eng->opt_batch = std::max(1, (int)v);
+    else if (k == "use_smem") eng->opt_use_smem = (v != 0.0);
+    else if (k == "refill_min") eng->opt_refill_min = std::min(32, std::max(1, (int)v));
+    else if (k == "blocks_per_sm") eng->opt_blocks_per_sm = (int)v;
+    else if (k == "cap_factor") { eng->opt_cap_factor = std::max(0.1, v); eng->nb_alloc = 0; }
+    else if (k == "queue_gib") eng->opt_queue_bytes_max = (size_t)(v * (double)(1ull << 30));
+    else if (k == "max_generations") eng->opt_max_generations = std::max(1, (int)v);
+    else return TRK3_E_INVALID;
+    return TRK3_OK;
+}
+
+const trk3_tally_layout *trk3_mc_layout(const trk3_engine *eng) { return eng ? &eng->lay : nullptr; }
+const char *trk3_mc_last_error(const trk3_engine *eng) { return eng ? eng->err.c_str() : "no engine"; }
+double *trk3_mc_device_tallies(trk3_engine *eng) { return eng ? eng->d_tally : nullptr; }
+
+int trk3_mc_zero_device_tallies(trk3_engine *eng) {
+    if (!eng) return TRK3_E_INVALID;
+    CK(cudaSetDevice(eng->device));
+    CK(cudaMemsetAsync(eng->d_tally, 0, (size_t)eng->lay.total * sizeof(double), eng->stream));
+    CK(cudaStreamSynchronize(eng->stream));
+    return TRK3_OK;
+}
+
+int trk3_mc_download_tallies(trk3_engine *eng, double *dst) {
+    if (!eng || !dst) return TRK3_E_INVALID;
+    CK(cudaSetDevice(eng->device));
+    std::vector<double> tmp((size_t)eng->lay.total);
+    CK(cudaMemcpyAsync(tmp.data(), eng->d_tally, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, eng->stream));
+    CK(cudaStreamSynchronize(eng->stream));
+    for (size_t i = 0; i < tmp.size(); ++i) dst[i] += tmp[i];
+    return TRK3_OK;
+}
+
+int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_stats *stats) {
+    if (!eng || it_end < it_begin || it_begin < 0 || it_end > 0xffffffffll) return TRK3_E_INVALID;
+    CK(cudaSetDevice(eng->device));
+    const int Nt = eng->lay.Nt;
+    const int64_t n_it = it_end - it_begin;
+    eng->iter_totE.assign((size_t)n_it * Nt, 0.0);
+    eng->Dcoef.assign(Nt, 0.0);
+    // batch size: bounded by the option and by the queue-memory budget
+    double cap[N_SPECIES]; queue_caps(eng, cap);
+    double bytes_per_iter = 0; for (int s = 0; s < N_SPECIES; ++s) bytes_per_iter += 2.0 * cap[s] * (TRK_NCOL * 8 + 20);
+    int64_t nb_max = std::min<int64_t>(eng->opt_batch, std::max<int64_t>(1, (int64_t)((double)eng->opt_queue_bytes_max / bytes_per_iter)));
+    nb_max = std::min<int64_t>(nb_max, std::max<int64_t>(n_it, 1));
+    int rc = ensure_batch(eng, (uint32_t)nb_max);
+    if (rc) return rc;
+    const size_t n_counters = TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 2;
+    CK(cudaMemsetAsync(eng->d_counters, 0, n_counters * sizeof(unsigned long long), eng->stream));
+    uint64_t waves = 0; const uint64_t launches0 = eng->launches;
+    std::vector<double> h_diffS, h_totE; std::vector<uint32_t> h_diffN;
+    uint32_t *heads = eng->d_qcount + 2 * N_SPECIES;
+    CK(cudaEventRecord(eng->ev0, eng->stream));
+    int retries = 0;
+    for (int64_t b0 = it_begin; b0 < it_end;) {
+        const uint32_t nb = (uint32_t)std::min<int64_t>(nb_max, it_end - b0);
+        // snapshot of the accumulators: a batch whose queues overflow is rolled back and re-run with larger queues
+        CK(cudaMemcpyAsync(eng->d_tally_bak, eng->d_tally, (size_t)eng->lay.total * sizeof(double), cudaMemcpyDeviceToDevice, eng->stream));
+        CK(cudaMemcpyAsync(eng->d_counters_bak, eng->d_counters, n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, eng->stream));
+        eng->hp.batch_begin = (uint32_t)b0; eng->hp.batch_n = nb;
+        CK(cudaMemcpyToSymbolAsync(c_p, &eng->hp, sizeof(DevP), 0, cudaMemcpyHostToDevice, eng->stream));
+        CK(cudaMemsetAsync(eng->d_u32, 0, eng->sl.u32_total * sizeof(uint32_t), eng->stream));
+        CK(cudaMemsetAsync(eng->d_f64, 0, eng->sl.f64_total * sizeof(double), eng->stream));
+        CK(cudaMemsetAsync(eng->d_qcount, 0, 3 * N_SPECIES * sizeof(uint32_t), eng->stream));
+        k_shi<<<(nb + 31) / 32, 32, 0, eng->stream>>>(eng->qs[0]);
+        CK(cudaGetLastError());
+        eng->launches++;
+        int cur = 0;
+        bool overflow = false;
+        for (int gen = 0; gen < eng->opt_max_generations; ++gen) {
+            uint32_t h_cnt[N_SPECIES];
+            CK(cudaMemcpyAsync(h_cnt, eng->d_qcount + cur * N_SPECIES, sizeof h_cnt, cudaMemcpyDeviceToHost, eng->stream));
+            CK(cudaStreamSynchronize(eng->stream));
+            uint64_t total = 0;
+            for (int s = 0; s < N_SPECIES; ++s) { if (h_cnt[s] > eng->qs[cur].q[s].cap) { overflow = true; h_cnt[s] = eng->qs[cur].q[s].cap; } total += h_cnt[s]; }
+            if (!total || overflow) break;
+            ++waves;
+            const int nxt = cur ^ 1;
+            CK(cudaMemsetAsync(eng->d_qcount + nxt * N_SPECIES, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
+            CK(cudaMemsetAsync(heads, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
+            if (h_cnt[SP_ELECTRON]) { rc = launch_wave<SP_ELECTRON>(eng, eng->qs[cur].q[SP_ELECTRON], h_cnt[SP_ELECTRON], heads + SP_ELECTRON, eng->qs[nxt]); if (rc) return rc; }
+            if (h_cnt[SP_VBHOLE]) { rc = launch_wave<SP_VBHOLE>(eng, eng->qs[cur].q[SP_VBHOLE], h_cnt[SP_VBHOLE], heads + SP_VBHOLE, eng->qs[nxt]); if (rc) return rc; }
+            if (h_cnt[SP_COREHOLE]) { rc = launch_wave<SP_COREHOLE>(eng, eng->qs[cur].q[SP_COREHOLE], h_cnt[SP_COREHOLE], heads + SP_COREHOLE, eng->qs[nxt]); if (rc) return rc; }
+            if (h_cnt[SP_PHOTON]) { rc = launch_wave<SP_PHOTON>(eng, eng->qs[cur].q[SP_PHOTON], h_cnt[SP_PHOTON], heads + SP_PHOTON, eng->qs[nxt]); if (rc) return rc; }
+            cur = nxt;
+        }
+        if (overflow) {
+            if (++retries > 6) { eng->err = "particle queue overflow persists after 6 capacity doublings"; return TRK3_E_OVERFLOW; }
+            CK(cudaMemcpyAsync(eng->d_tally, eng->d_tally_bak, (size_t)eng->lay.total * sizeof(double), cudaMemcpyDeviceToDevice, eng->stream));
+            CK(cudaMemcpyAsync(eng->d_counters, eng->d_counters_bak, n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, eng->stream));
+            CK(cudaStreamSynchronize(eng->stream));
+            eng->opt_cap_factor *= 2.0; eng->nb_alloc = 0;
+            queue_caps(eng, cap);
+            bytes_per_iter = 0; for (int s = 0; s < N_SPECIES; ++s) bytes_per_iter += 2.0 * cap[s] * (TRK_NCOL * 8 + 20);
+            int64_t nb_new = std::min<int64_t>(nb_max, std::max<int64_t>(1, (int64_t)((double)eng->opt_queue_bytes_max / bytes_per_iter)));
+            rc = ensure_batch(eng, (uint32_t)nb_new);
+            if (rc) return rc;
+            nb_max = nb_new;
+            continue;                // re-run from the same b0 (histories are keyed by the global iteration index: same result)
+        }
+        k_iter_prefix<<<(nb + 127) / 128, 128, 0, eng->stream>>>(eng->fa);
+        CK(cudaGetLastError());
+        const int64_t njobs = fold_num_jobs(eng->hp);
+        k_fold<<<(unsigned)((njobs + 127) / 128), 128, 0, eng->stream>>>(eng->fa, njobs);
+        CK(cudaGetLastError());
+        eng->launches += 2;
+        // per-iteration results back to the host: total energies (conservation check) and the
+        // Out_diff_coeff recurrence (Monte_Carlo.f90:1094-1098), which is sequential over iterations
+        const size_t n = (size_t)nb * Nt;
+        h_diffS.resize(n); h_diffN.resize(n); h_totE.resize(n);
+        CK(cudaMemcpyAsync(h_diffS.data(), eng->hp.it.diffS, n * sizeof(double), cudaMemcpyDeviceToHost, eng->stream));
+        CK(cudaMemcpyAsync(h_diffN.data(), eng->hp.it.diffN, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, eng->stream));
+        CK(cudaMemcpyAsync(h_totE.data(), eng->fa.totE, n * sizeof(double), cudaMemcpyDeviceToHost, eng->stream));
+        CK(cudaStreamSynchronize(eng->stream));
+        for (uint32_t il = 0; il < nb; ++il) for (int i = 0; i < Nt; ++i) {
+            const size_t o = (size_t)il * Nt + i;
+            eng->Dcoef[i] = eng->Dcoef[i] + h_diffS[o];
+            if (h_diffN[o] > 0) eng->Dcoef[i] = eng->Dcoef[i] / (double)h_diffN[o];
+            eng->iter_totE[(size_t)(b0 - it_begin + il) * Nt + i] = h_totE[o];
+        }
+        b0 += nb;
+    }
+    CK(cudaMemcpyAsync(eng->d_small, eng->Dcoef.data(), Nt * sizeof(double), cudaMemcpyHostToDevice, eng->stream));
+    k_axpy<<<1, 256, 0, eng->stream>>>(eng->d_tally + eng->lay.off[TRK3_OUT_DIFF_COEFF], eng->d_small, Nt);
+    CK(cudaGetLastError());
+    eng->launches++;
+    CK(cudaEventRecord(eng->ev1, eng->stream));
+    std::vector<unsigned long long> h_c(n_counters);
+    CK(cudaMemcpyAsync(h_c.data(), eng->d_counters, n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToHost, eng->stream));
+    CK(cudaStreamSynchronize(eng->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
+    trk3_stats st; std::memset(&st, 0, sizeof st);
+    for (int q = 0; q < TRK3_N_EVENT_CLASSES; ++q) st.events[q] = h_c[q];
+    for (int q = 0; q < TRK3_N_ERRORS; ++q) st.errors[q] = h_c[TRK3_N_EVENT_CLASSES + q];
+    st.n_electrons = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS]; st.n_photons = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 1];
+    st.n_waves = waves; st.kernel_launches = eng->launches - launches0; st.device_ms = ms;
+    static const double ev_bytes[TRK3_N_EVENT_CLASSES] = {176, 320, 144, 384, 208, 384, 280, 208, 248};
+    for (int q = 0; q < TRK3_N_EVENT_CLASSES; ++q) st.algorithmic_bytes += ev_bytes[q] * (double)st.events[q];
+    // energy conservation: after the ion has left, the total energy of an iteration must not change
+    double drift = 0.0;
+    for (int64_t k = 0; k < n_it; ++k) {
+        const double *e = &eng->iter_totE[(size_t)k * Nt];
+        const double ref = e[Nt - 1];
+        if (!(ref > 0.0)) continue;
+        for (int i = 0; i < Nt - 1; ++i) {
+            // only grid times after the ion left the layer are comparable; the energy is non-decreasing before
+            if (e[i] >= ref * (1.0 - 1e-6)) drift = std::max(drift, std::fabs(e[i] - ref) / ref);
+        }
+    }
+    st.max_energy_drift = drift;
+    if (stats) *stats = st;
+    if (st.errors[TRK3_ERR_QUEUE_OVERFLOW]) { eng->err = "particle queue overflow: raise the 'cap_factor' option"; return TRK3_E_OVERFLOW; }
+    return TRK3_OK;
+}
+
+int trk3_mc_run(trk3_engine *eng, int64_t it_begin, int64_t it_end, double *tallies, trk3_stats *stats) {
+    if (!eng || !tallies) return TRK3_E_INVALID;
+    int rc = trk3_mc_zero_device_tallies(eng);
+    if (rc) return rc;
+    rc = trk3_mc_run_device(eng, it_begin, it_end, stats);
+    if (rc) return rc;
+    return trk3_mc_download_tallies(eng, tallies);
+}
+
+int trk3_mc_iteration_energies(trk3_engine *eng, double *out, int64_t capacity, int64_t *n_iter) {
+    if (!eng || !out || !n_iter) return TRK3_E_INVALID;
+    const int64_t n = (int64_t)eng->iter_totE.size();
+    const int64_t m = std::min<int64_t>(n, capacity);
+    std::memcpy(out, eng->iter_totE.data(), (size_t)m * sizeof(double));
+    *n_iter = m / eng->lay.Nt;
+    return TRK3_OK;
+}
+
+void trk3_mc_destroy(trk3_engine *eng) {
+    if (!eng) return;
+    cudaSetDevice(eng->device);
+    for (void *p : eng->allocs) cudaFree(p);
+    if (eng->ev0) cudaEventDestroy(eng->ev0);
+    if (eng->ev1) cudaEventDestroy(eng->ev1);
+    if (eng->stream) cudaStreamDestroy(eng->stream);
+    delete eng;
+}
+
+}  // extern "C"

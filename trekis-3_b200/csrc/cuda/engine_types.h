@@ -1,0 +1,104 @@
+// engine_types.h -- device-side data model of the wavefront engine (shared by the CUDA build and the
+// host emulation build used by the CPU tests).
+//
+// Layout decisions (DESIGN.md "Data layout in HBM"):
+//  * tables: one flat fp64 image per family on a shared energy grid, rows [shell][energy]; totals
+//    (How_many_electrons, Monte_Carlo.f90:1902) are precomputed once at upload; differential tables are CSR.
+//  * particles: struct-of-arrays queues, one per species (electron, valence hole, core hole, photon), double
+//    buffered per wavefront generation; a record is consumed exactly once and run to its end of history.
+//  * tallies: the packed Out_* buffer of include/trekis3_gpu.h in global memory; the radial x time arrays
+//    that are written from inside the event loop are privatised per block in shared memory and flushed once.
+//  * per-iteration scratch: integer histograms for the three spectra that the reference normalises per
+//    iteration (1/Tot_Nel, 1/N_VB_h_tot, Monte_Carlo.f90:1026-1069) and per-iteration energy sums.
+#pragma once
+#include <stdint.h>
+#include "../../../include/trekis3_gpu.h"
+
+#if defined(__CUDACC__)
+#define TRK_HD __host__ __device__ inline
+#define TRK_D __device__ inline
+#else
+#define TRK_HD inline
+#define TRK_D inline
+#endif
+
+namespace trk3 {
+
+enum Species { SP_ELECTRON = 0, SP_VBHOLE = 1, SP_COREHOLE = 2, SP_PHOTON = 3, N_SPECIES = 4 };
+
+// One particle (registers while in flight; SoA columns in a queue).  Objects.f90:31-68 minus the
+// never-used velocities/accelerations, plus the Philox stream (id, ctr) and the iteration index.
+struct Rec {
+    double E, Ehkin, Mass, t0, tn, X, Y, Z, L, theta, phi;
+    uint64_t id;      // Philox stream id of this particle
+    uint32_t ctr;     // next draw index of the stream
+    uint32_t iter;    // global iteration index (4th Philox counter word)
+    int32_t shell;    // flat shell of a hole (unused for electrons/photons)
+};
+
+#define TRK_NCOL 11   // double columns of a queue
+
+struct Queue {        // SoA particle queue in global memory
+    double *col[TRK_NCOL];
+    uint64_t *id; uint32_t *ctr; uint32_t *iter; int32_t *shell;
+    uint32_t *count;  // number of records pushed (may exceed capacity on overflow; clamp when reading)
+    uint32_t cap;
+};
+
+// Per-iteration scratch arrays (index it_local = iter - batch_begin)
+struct IterArrays {
+    uint32_t *created;   // [nb][Nt+2]  electrons created in time interval iv (1..Nt+1)
+    uint32_t *nvb;       // [nb][Nt]    valence holes alive at grid time i
+    uint32_t *nph;       // [nb][Nt]    photons alive at grid time i
+    uint32_t *spec_e;    // [nb][Nt][n_r]
+    uint32_t *spec_h;    // [nb][Nt][n_dos]
+    uint32_t *th_e;      // [nb][Nt][180]
+    uint32_t *th_h;      // [nb][Nt][180]
+    uint32_t *diffN;     // [nb][Nt]
+    double *diffS;       // [nb][Nt]
+    double *esnap;       // [nb][Nt]    sum of particle energies at grid time i
+    double *elat;        // [nb][Nt+2]  lattice energy deposited in interval iv
+    uint32_t *em_cnt;    // [nb][Nt+2]  emitted electrons per interval
+    double *em_E;        // [nb][Nt+2]
+    uint32_t *em_spec;   // [nb][Nt+2][n_r]
+};
+
+struct DevP {
+    // ---- scalars (trk3_config)
+    double ion_E, ion_mass, ion_fixed_Zeff, ion_Zeff0;
+    double Tim, cut_off, layer, hole_mass, work_function, bar_height, Em_E1, Em_gamma;
+    double Egap, Mtarget, sum_pers;
+    int32_t ion_Z, ion_kind_Zeff, include_photons, kind_of_EMFP;
+    uint32_t seed_lo, seed_hi;
+    // ---- target (trk3_tables header)
+    int32_t n_atoms, n_shells, vb_shell, nshl_atom1;
+    int32_t atom_Z[TRK3_MAX_ATOMS], atom_first[TRK3_MAX_ATOMS], atom_nshl[TRK3_MAX_ATOMS];
+    double atom_mass[TRK3_MAX_ATOMS], atom_pers[TRK3_MAX_ATOMS];
+    int32_t shell_atom[TRK3_MAX_SHELLS], shell_num[TRK3_MAX_SHELLS];
+    double shell_Ip[TRK3_MAX_SHELLS], shell_Nel[TRK3_MAX_SHELLS], shell_auger[TRK3_MAX_SHELLS], shell_radiat[TRK3_MAX_SHELLS];
+    // ---- tables (device pointers)
+    int32_t n_ei, n_ee, n_hi, n_he, n_ph, n_shi, n_dos, n_r;
+    const double *ei_E, *ei_L, *ei_tot, *ee_E, *ee_L, *hi_E, *hi_L, *hi_tot, *he_E, *he_L, *ph_E, *ph_L, *ph_tot;
+    const double *shi_E, *shi_L, *shi_tot;
+    const int64_t *dshi_off, *eid_off, *eed_off, *hid_off, *hed_off;
+    const double *dshi_E, *dshi_L, *eid_hw, *eid_L, *eed_hw, *eed_L, *hid_hw, *hid_L, *hed_hw, *hed_L;
+    const double *dos_E, *dos_DOS, *dos_int, *dos_effm, *out_R, *out_V;
+    // ---- time grid: tg[i-1] = min(time_grid(i), Tim), i = 1..Nt
+    int32_t Nt;
+    double tg[TRK3_MAX_NT];
+    // ---- tallies
+    double *tally;                       // packed Out_* buffer (global)
+    int64_t g_off[TRK3_N_TALLIES];       // offsets in `tally`
+    int32_t s_off[TRK3_N_TALLIES];       // offsets in the block-private copy, -1 = not privatised
+    int32_t s_len[TRK3_N_TALLIES];       // lengths of the privatised arrays
+    int32_t s_total;                     // doubles in the block-private copy (0 = privatisation off)
+    // ---- per-iteration scratch
+    IterArrays it;
+    uint32_t batch_begin, batch_n;       // global index of the first iteration of the batch, iterations in it
+    // ---- counters
+    unsigned long long *events;          // [TRK3_N_EVENT_CLASSES]
+    unsigned long long *errors;          // [TRK3_N_ERRORS]
+    unsigned long long *cnt_el, *cnt_ph;
+};
+
+}  // namespace trk3

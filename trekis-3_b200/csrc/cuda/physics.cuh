@@ -1,0 +1,910 @@
+// physics.cuh -- per-history physics of the TREKIS-3 cascade, written for the wavefront engine.
+//
+// The reference advances ALL particles of an iteration in one global time-ordered loop
+// (Monte_Carlo.f90:572-665, Find_min_time_particle :2060).  Particles never interact (the field code
+// :3018-3244 is dead), so the same tallies are obtained by following every particle independently
+// and depositing a SNAPSHOT of its state at each output grid time its current free flight spans
+// (Calculated_statistics, :881-1110).  Each routine below names the Fortran it re-expresses.
+//
+// All functions are templates over a context `C` that provides the side effects:
+//   c.p                      const DevP&  (tables, switches, time grid)
+//   c.push(species, rec)     append a new particle to the next-generation queue
+//   c.tally(id, idx, v)      add v to element idx of Out_* array `id` (block-private or global)
+//   c.add_u32(base, idx)     atomic ++ on a per-iteration integer histogram
+//   c.add_f64(base, idx, v)  atomic += on a per-iteration double array
+//   c.event(cls) / c.error(code) / c.count_electron() / c.count_photon()
+// so that the identical code runs in the CUDA kernels (engine.cu) and in the CPU emulation used by
+// the no-GPU tests (tests/emul).  fp64 throughout (the reference is built with -real-size 64).
+#pragma once
+#include <math.h>
+#include "engine_types.h"
+
+namespace trk3 {
+
+// ---- Universal_Constants.f90:24-107
+#define TRK_PI 3.1415926535897932384626433832795
+#define TRK_GE 1.602176487e-19
+#define TRK_ME 9.1093821545e-31
+#define TRK_CVEL 299792458.0
+#define TRK_MP (1836.1526724780 * TRK_ME)
+#define TRK_HBAR 1.05457162853e-34
+#define TRK_RY 13.6056981
+#define TRK_A0 0.5291772085936
+#define TRK_E0 8.854187817620e-12
+
+TRK_HD bool trk_isnan(double x) { return x != x; }
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (Salmon et al., SC'11).  Stream = (particle id, draw index,
+// iteration); key = user seed.  Replaces the unseeded compiler random_number of the reference.
+// ------------------------------------------------------------------------------------------------
+TRK_HD uint32_t trk_mulhi(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+TRK_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = trk_mulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = trk_mulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1;
+}
+// uniform in (0,1]: the reference can draw RN = 0 (log(RN), L/RN -> inf); we exclude it
+TRK_HD double rn(const DevP &p, Rec &r) {
+    uint32_t a, b;
+    philox4x32_10((uint32_t)r.id, (uint32_t)(r.id >> 32), r.ctr++, r.iter, p.seed_lo, p.seed_hi, a, b);
+    uint64_t bits = (uint64_t)a | ((uint64_t)b << 32);
+    return (double)((bits >> 11) + 1) * (1.0 / 9007199254740992.0);
+}
+// id of a particle created by `parent` (tag 1 electron, 2 hole, 3 photon)
+TRK_HD uint64_t child_id(const DevP &p, Rec &parent, uint32_t tag) {
+    uint32_t a, b;
+    philox4x32_10((uint32_t)parent.id, (uint32_t)(parent.id >> 32), parent.ctr++, parent.iter, p.seed_lo, p.seed_hi ^ (0x80000000u | tag), a, b);
+    return (uint64_t)a | ((uint64_t)b << 32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Searches (Reading_files_and_parameters.f90:3376-3559), same bisection paths as the Fortran
+// (results depend on the path at exact grid hits and in padded, non-monotone table tails).
+// All return the 1-based Fortran index.
+// ------------------------------------------------------------------------------------------------
+TRK_HD int find_1d(const double *A, int N, double v) {                 // Find_in_monotonous_1D_array
+    if (v < A[0]) return 1;
+    if (v >= A[N - 1]) return N;
+    int i_1 = 1, i_2 = N, i_cur = (1 + N) >> 1;
+    double temp_val = A[i_cur - 1];
+    while (i_1 != i_2 - 1) {
+        if (temp_val <= v) i_1 = i_cur; else i_2 = i_cur;
+        i_cur = (i_1 + i_2) >> 1;
+        temp_val = A[i_cur - 1];
+    }
+    return i_cur + 1;
+}
+TRK_HD int find_2d(const double *A, int N, double v) {                 // Find_in_monotonous_2D_array
+    if (v < A[0]) return 1;
+    if (v >= A[N - 1]) return N;
+    int i_1 = 1, i_2 = N, i_cur = (1 + N) >> 1;
+    double temp_val = A[i_cur - 1];
+    for (int coun = 0; coun <= 1000; ++coun) {
+        if (v >= temp_val && v <= A[i_cur]) break;
+        if (temp_val <= v) i_1 = i_cur; else i_2 = i_cur;
+        i_cur = (i_1 + i_2) >> 1;
+        temp_val = A[i_cur - 1];
+    }
+    return i_cur + 1;
+}
+TRK_HD int find_dec(const double *A, int N, double v) {                // Find_in_monoton_array_decreasing
+    if (v < A[N - 1]) return N;
+    if (v > A[0]) return 1;
+    int i_1 = 1, i_2 = N, i_cur = (1 + N) >> 1;
+    double temp_val = A[i_cur - 1];
+    int coun = 0;
+    while ((i_2 - i_1 > 1 || i_1 - i_2 > 1) && coun <= 1000) {
+        if (temp_val > v) i_1 = i_cur; else i_2 = i_cur;
+        i_cur = (i_1 + i_2) >> 1;
+        temp_val = A[i_cur - 1];
+        ++coun;
+    }
+    return i_cur;
+}
+// Interpolate, Cross_sections.f90:4051-4086 (modes 1 and 5 are the only ones the MC uses)
+TRK_HD double interp5(double E1, double E2, double S1, double S2, double En) {
+    if (fabs(E2 - E1) < 1.0e-6) return (S1 > S2) ? S1 : S2;
+    if (En == E1) return S1;
+    double E2l = log(E2), E1l = log(E1), El = log(En), S1l = log(S1), S2l = log(S2);
+    return exp(S1l + (S2l - S1l) / (E2l - E1l) * (El - E1l));
+}
+TRK_HD double interp1(double E1, double E2, double S1, double S2, double En) {
+    if (fabs(E2 - E1) < 1.0e-6) return (S1 > S2) ? S1 : S2;
+    if (En == E1) return S1;
+    return S1 + (S2 - S1) / (E2 - E1) * (En - E1);
+}
+
+// Next_free_path_1d / _2d, Monte_Carlo.f90:1835-1899
+TRK_HD double nfp_1d(double E, const double *Ea, const double *La, int N) {
+    int n = find_1d(Ea, N, E);
+    if (n == 1) {
+        double MFP = interp1(Ea[0], Ea[1], La[0], La[1], E);
+        if (MFP < Ea[0]) MFP = Ea[0];           // sic (:1854): clamped against the energy array
+        return MFP;
+    }
+    double Ll = La[n - 2];
+    if (Ll >= 1.0e16) return Ll;
+    return interp5(Ea[n - 2], Ea[n - 1], Ll, La[n - 1], E);
+}
+TRK_HD double nfp_2d(double E, const double *Ea, const double *La, int N) {
+    int n = find_2d(Ea, N, E);
+    if (n == 1) {
+        double MFP = interp1(Ea[0], Ea[1], La[0], La[1], E);
+        if (MFP < La[0]) MFP = La[0];
+        return MFP;
+    }
+    double Ll = La[n - 2];
+    if (Ll >= 1.0e16) return Ll;
+    return interp5(Ea[n - 2], Ea[n - 1], Ll, La[n - 1], E);
+}
+
+// Which_shell, Monte_Carlo.f90:1786-1832: shell roulette on 1/lambda_shell(E); returns the flat shell
+TRK_HD int which_shell(const DevP &p, Rec &r, const double *Ea, const double *Lmat, int N, double E) {
+    double Temp[TRK3_MAX_SHELLS];
+    double MFP_tot = 0.0;
+    const int n = find_1d(Ea, N, E);            // all shells share the grid (MAIN.f90:234-236)
+    for (int s = 0; s < p.n_shells; ++s) {
+        const double *La = Lmat + (size_t)s * N;
+        double MFP;
+        if (n == 1) MFP = 1.0e20;
+        else {
+            double a = La[n - 2], b = La[n - 1];
+            if (a == b || a > 1e20) MFP = a;
+            else MFP = interp5(Ea[n - 2], Ea[n - 1], a, b, E);
+        }
+        Temp[s] = 1.0 / MFP;
+        MFP_tot = MFP_tot + Temp[s];
+    }
+    double RN = rn(p, r);
+    MFP_tot = RN * MFP_tot;
+    double MFP_sum = 0.0;
+    int sel = p.n_shells - 1;
+    for (int s = 0; s < p.n_shells; ++s) { MFP_sum = MFP_sum + Temp[s]; if (MFP_sum >= MFP_tot) { sel = s; break; } }
+    return sel;
+}
+
+// Get_velosity, Monte_Carlo.f90:850-878 (non-relativistic for massive particles)
+TRK_HD double vel_electron(double E) { return sqrt(2.0 * E * TRK_GE / TRK_ME); }
+TRK_HD double vel_hole(const Rec &h) {
+    if (h.Mass < 1.0e6) {
+        if (h.Ehkin < -1.0e-6 || h.Mass < 1.0e-10) return 0.0;
+        if (fabs(h.Ehkin) < 1.0e-6) return 0.0;
+        return sqrt(2.0 * h.Ehkin * TRK_GE / (h.Mass * TRK_ME));
+    }
+    return 0.0;
+}
+// Get_time_of_next_event, :795-848
+TRK_HD double next_time(double t0, double V, double MFP) { return (V > 1.0e-10) ? t0 + MFP / V * 1e5 : 1.0e25; }
+
+// time-interval index of an event/creation time: smallest i (1-based) with t < tg(i); Nt+1 if t >= Tim
+TRK_HD int interval_of(const DevP &p, double t) {
+    int i = 1;
+    while (i <= p.Nt && !(t < p.tg[i - 1])) ++i;
+    return i;
+}
+
+// interpolate_transferred_energy, Cross_sections.f90:1968-2045, on a CSR differential table
+TRK_HD double sample_row(const double *hw, const double *L, int n, double L_need) {
+    int i_hw = find_dec(L, n, L_need);
+    if (i_hw == 1 || i_hw == n) return hw[i_hw - 1];
+    return interp5(L[i_hw - 1], L[i_hw], hw[i_hw - 1], hw[i_hw], L_need);
+}
+TRK_HD double transferred_energy(double Ele, const double *Eg, int NE, const int64_t *off, const double *hwA, const double *LA, double L_need) {
+    int i_E = find_1d(Eg, NE, Ele);
+    if (i_E > 1) { if (fabs(Eg[i_E - 2] - Ele) < 1.0e-6) i_E = i_E - 1; }
+    int64_t o = off[i_E - 1];
+    double hw_1 = sample_row(hwA + o, LA + o, (int)(off[i_E] - o), L_need);
+    if (i_E <= 1) return hw_1;
+    i_E = i_E - 1;
+    o = off[i_E - 1];
+    double hw_2 = sample_row(hwA + o, LA + o, (int)(off[i_E] - o), L_need);
+    if (hw_1 < 1.0e-10 || hw_2 < 1.0e-10) return interp1(Eg[i_E - 1], Eg[i_E], hw_1, hw_2, Ele);
+    return interp5(Eg[i_E - 1], Eg[i_E], hw_1, hw_2, Ele);
+}
+
+// effective hole mass from the DOS, e.g. Cross_sections.f90:1820-1825
+TRK_HD double hole_mass_dos(const DevP &p, double E) { int m = find_1d(p.dos_E, p.n_dos, E); return p.dos_effm[m - 1]; }
+
+// Electron_energy_transfer_inelastic (CS_method = 1), Cross_sections.f90:1793-1871
+TRK_HD double inelastic_dE(const DevP &p, Rec &r, double Ele, int shell, double L_tot, bool hole) {
+    double RN = rn(p, r);
+    double L_need = L_tot / RN;
+    double Emin = p.shell_Ip[shell];
+    if (Emin <= 1.0e-3) Emin = 1.0e-3;
+    double Emax, E;
+    if (!hole) {
+        Emax = (Ele + Emin) / 2.0;
+        E = transferred_energy(Ele, p.ei_E, p.n_ei, p.eid_off + (size_t)shell * p.n_ei, p.eid_hw, p.eid_L, L_need);
+    } else {
+        double Mass = (p.hole_mass >= 0) ? p.hole_mass : hole_mass_dos(p, Ele);
+        Emax = 4.0 * Ele * Mass / ((Mass + 1.0) * (Mass + 1.0));
+        E = transferred_energy(Ele, p.hi_E, p.n_hi, p.hid_off, p.hid_hw, p.hid_L, L_need);
+    }
+    if (E < Emin) E = Emin;
+    if (E > Emax) E = Emax;
+    if (trk_isnan(E)) E = Emin;
+    return E;
+}
+
+// rest_energy, Cross_sections.f90:1557
+TRK_HD double rest_energy(double M0) { return M0 * TRK_CVEL * TRK_CVEL / TRK_GE; }
+
+// NRG_transfer_elastic_atomic (Mott), Cross_sections.f90:3517-3613
+TRK_HD double mott_dE(const DevP &p, Rec &r, double Mat, double Zat, double Ee, double M_eff) {
+    double RN = rn(p, r);
+    double theta;
+    double Erest = rest_energy(TRK_ME);
+    double fact = Ee / Erest + 1.0;
+    double v = TRK_CVEL * sqrt(1.0 - 1.0 / (fact * fact));
+    if (v < 1.0e-6) theta = 0.0;
+    else {
+        double beta = v / TRK_CVEL, beta2 = beta * beta, tau = Ee / Erest;
+        double alpha = TRK_GE * TRK_GE / (TRK_HBAR * TRK_CVEL * 4.0 * TRK_PI * TRK_E0);
+        double nu = 1.7e-5 * pow(Zat, 2.0 / 3.0) * (1.0 - beta2) / beta2 * (1.13 + 3.76 * alpha * alpha / beta2 * Zat * Zat * sqrt(tau / (1.0 + tau)));
+        double mu = (RN * (2.0 * nu + 1.0) - nu) / (RN + nu);
+        theta = acos(mu);
+    }
+    double mc2 = rest_energy(TRK_ME * M_eff), Mct2 = rest_energy(Mat);
+    double ct = cos(theta), ct2 = ct * ct, st2 = 1.0 - ct2;
+    double Emc = Ee + mc2, E2mc = Ee + 2.0 * mc2, EmcMc = Emc + Mct2;
+    double W1 = Emc * st2 + Mct2 - ct * sqrt(Mct2 * Mct2 - mc2 * mc2 * st2);
+    double W2 = Ee * E2mc / (EmcMc * EmcMc - Ee * E2mc * ct2);
+    return W1 * W2;
+}
+// elastic energy transfer: the kind_of_EMFP switch of Monte_Carlo.f90:2387-2407 / :2668-2692
+TRK_HD double elastic_dE(const DevP &p, Rec &r, double Eel, double EMFP, bool hole, double M_eff) {
+    if (p.kind_of_EMFP == 1) {      // Electron_energy_transfer_elastic, Cross_sections.f90:2403-2413
+        double RN = rn(p, r);
+        double L_need = EMFP / RN;
+        double hw = hole ? transferred_energy(Eel, p.he_E, p.n_he, p.hed_off, p.hed_hw, p.hed_L, L_need)
+                         : transferred_energy(Eel, p.ee_E, p.n_ee, p.eed_off, p.eed_hw, p.eed_L, L_need);
+        if (hw >= Eel) hw = Eel;
+        return hw;
+    }
+    double dE = 0.0;
+    for (int ii = 0; ii < p.n_atoms; ++ii) {
+        double dE_loc = mott_dE(p, r, p.atom_mass[ii] * TRK_MP, (double)p.atom_Z[ii], Eel, hole ? M_eff : 1.0);
+        dE = dE + dE_loc * p.atom_pers[ii];
+    }
+    return dE / p.sum_pers;
+}
+
+// cos_theta_from_W + Update_particle_angles_lat, Monte_Carlo.f90:1252-1299
+TRK_HD void angles_lattice(const DevP &p, Rec &r, double E, double W, double M_eff, double &theta, double &phi) {
+    double Erest_in = rest_energy(M_eff * TRK_ME), Erest_t = rest_energy(p.Mtarget);
+    double E2mc = E + 2.0 * Erest_in, EmW = E - W;
+    double W1 = E * E2mc - W * (E + Erest_in + Erest_t);
+    double W2 = E * E2mc * EmW * (E2mc - W);
+    double mu = (W2 > 0.0) ? W1 / sqrt(W2) : 0.0;
+    if (fabs(mu) > 1.0) { double RN = rn(p, r); mu = cos(TRK_PI * RN); }
+    theta = acos(mu);
+    double RN2 = rn(p, r);
+    phi = 2.0 * TRK_PI * RN2;
+}
+// New_Angles_both, Monte_Carlo.f90:1328-1360 (not a rotation; kept as is)
+TRK_HD void new_angles(double phi0, double theta0, double theta, double psi, double &phi1, double &theta1) {
+    phi1 = phi0 + theta * cos(theta0) * sin(psi);
+    theta1 = theta0 + theta * cos(psi);
+    while (theta1 < 0.0) { theta1 = fabs(theta1); phi1 = phi1 + TRK_PI; }
+    while (theta1 > TRK_PI) { theta1 = 2.0 * TRK_PI - theta1; phi1 = phi1 - TRK_PI; }
+    if (phi1 > 2.0 * TRK_PI) phi1 = phi1 - floor(phi1 / (2.0 * TRK_PI)) * 2.0 * TRK_PI;
+    if (phi1 < 0.0) phi1 = phi1 + ceil(fabs(phi1) / (2.0 * TRK_PI)) * 2.0 * TRK_PI;
+}
+// Update_holes_angles_SHI, :1132-1140: isotropic in ANGLE (theta uniform), as the reference
+TRK_HD void random_angles(const DevP &p, Rec &r, double &theta, double &phi) {
+    double RN = rn(p, r); theta = TRK_PI * RN;
+    double RN2 = rn(p, r); phi = 2.0 * TRK_PI * RN2;
+}
+
+// inverse-CDF level in the valence band (shared tail of From_where_in_VB :1522 and Electron_recieves_E :1653)
+TRK_HD double vb_level(const DevP &p, Rec &r, int M_temp) {
+    double Sum_DOS = p.dos_int[M_temp - 2];
+    double RN = rn(p, r);
+    double Tot_N = RN * Sum_DOS;
+    int n = find_1d(p.dos_int, p.n_dos, Tot_N);
+    if (n > 1) return p.dos_E[n - 2] + (p.dos_E[n - 1] - p.dos_E[n - 2]) * (Tot_N - p.dos_int[n - 2]) / (p.dos_int[n - 1] - p.dos_int[n - 2]);
+    return p.dos_E[n - 1];
+}
+// Electron_recieves_E, Monte_Carlo.f90:1653-1716
+template <class C>
+TRK_HD double electron_receives_E(C &c, Rec &r, double dE, int shell) {
+    const DevP &p = c.p;
+    double E = dE - p.shell_Ip[shell], dE_cur = E;
+    if (shell == p.vb_shell && !(dE <= p.shell_Ip[shell])) {
+        int N = p.n_dos;
+        int M_temp = (E < p.dos_E[N - 1]) ? find_1d(p.dos_E, N, E) : N + 1;
+        if (M_temp > 1) dE_cur = E - vb_level(p, r, M_temp);
+    }
+    if (dE_cur < 0.0) c.error(TRK3_ERR_10);
+    return dE_cur;
+}
+// From_where_in_VB, :1522-1573
+TRK_HD double from_where_in_VB(const DevP &p, Rec &r, bool haveE, double E) {
+    int N = p.n_dos;
+    if (!haveE) return vb_level(p, r, N + 1);
+    int M_temp = (E < p.dos_E[N - 1]) ? find_1d(p.dos_E, N, E) : N + 1;
+    if (M_temp > 1) return vb_level(p, r, M_temp);
+    return 0.0;
+}
+
+// Hole_parameters (+Assign_holes_mass), Monte_Carlo.f90:724-792.  `Ehkin_prev` is the hole's kinetic energy
+// before the update (0 for a newly created hole: How_many_electrons initialises Ehkin = 0).
+TRK_HD void hole_parameters(const DevP &p, Rec &st, Rec &h, double Eh, double Ehkin_prev) {
+    if (h.shell == p.vb_shell) {
+        h.Ehkin = Eh - p.Egap;
+        h.E = p.Egap;
+        h.Mass = (p.hole_mass > 0) ? p.hole_mass : hole_mass_dos(p, h.Ehkin);
+        if (h.Mass < 1.0e3) {
+            double HIMFP = nfp_2d(h.Ehkin, p.hi_E, p.hi_tot, p.n_hi);
+            double HEMFP = (Ehkin_prev == (Eh - p.Egap)) ? 1.0e30 : nfp_2d(h.Ehkin, p.he_E, p.he_L, p.n_he);
+            double RN = rn(p, st);
+            double MFP_tot = -log(RN) / (1.0 / HIMFP + 1.0 / HEMFP);
+            h.tn = next_time(h.t0, vel_hole(h), MFP_tot);
+            h.L = MFP_tot;
+        } else { h.L = 1.0e30; h.tn = 1.0e30; }
+    } else {
+        h.Mass = 1.0e29;
+        double RN = rn(p, st);
+        double nu = 1.0 / p.shell_auger[h.shell] + 1.0 / p.shell_radiat[h.shell];
+        h.tn = h.t0 - log(RN) / nu;
+        h.L = 1.0e30; h.E = Eh; h.Ehkin = 0.0;
+    }
+    // cut_off, :3008-3012
+    if (h.Mass < 1e15 && h.Ehkin < p.cut_off) h.tn = 1.0e20;
+}
+
+// a new electron at (X,Y,Z,t) with energy Ee and direction (theta,phi): the block repeated in every handler
+// (:2212-2225, :2331-2342, :2606-2621, :2800-2813, :2921-2931); draws use the stream of the event particle `st`
+template <class C>
+TRK_HD void emit_electron(C &c, Rec &st, uint64_t id, double Ee, double t, double X, double Y, double Z, double theta, double phi, int err_code) {
+    const DevP &p = c.p;
+    Rec e;
+    double IMFP = nfp_2d(Ee, p.ei_E, p.ei_tot, p.n_ei);
+    double EMFP = nfp_2d(Ee, p.ee_E, p.ee_L, p.n_ee);
+    double RN = rn(p, st);
+    double MFP_tot = -log(RN) / (1.0 / IMFP + 1.0 / EMFP);
+    e.E = Ee; e.Ehkin = 0.0; e.Mass = 1.0; e.t0 = t; e.X = X; e.Y = Y; e.Z = Z; e.L = MFP_tot; e.theta = theta; e.phi = phi;
+    e.tn = next_time(t, vel_electron(Ee), MFP_tot);
+    if (e.E < p.cut_off) e.tn = 1.0e20;
+    if (e.E < -1.0e-9 || trk_isnan(e.E)) c.error(err_code);
+    e.id = id; e.ctr = 0; e.iter = st.iter; e.shell = -1;
+    c.count_electron();
+    c.push(SP_ELECTRON, e);
+}
+// a new hole in `shell` with total energy Eh and random direction (:2236-2240 and the identical blocks)
+template <class C>
+TRK_HD void emit_hole(C &c, Rec &st, uint64_t id, int shell, double Eh, double t, double X, double Y, double Z, int err_code) {
+    const DevP &p = c.p;
+    Rec h;
+    double htheta, hphi;
+    random_angles(p, st, htheta, hphi);
+    h.E = 0.0; h.Ehkin = 0.0; h.Mass = 1.0e30; h.t0 = t; h.tn = 1.0e21; h.X = X; h.Y = Y; h.Z = Z; h.L = 1.0e30; h.theta = htheta; h.phi = hphi;
+    h.shell = shell; h.id = id; h.ctr = 0; h.iter = st.iter;
+    hole_parameters(p, st, h, Eh, 0.0);
+    if (h.Ehkin < -1.0e-9 || trk_isnan(h.Ehkin)) c.error(err_code);
+    c.push(shell == p.vb_shell ? SP_VBHOLE : SP_COREHOLE, h);
+}
+
+// Equilibrium_charge_SHI, Cross_sections.f90:2641-2680
+TRK_HD double shi_zeff(const DevP &p, double E) {
+    double vp = (E > 0.0) ? sqrt(2.0 * E * TRK_GE / (p.ion_mass * TRK_MP)) : 0.0;
+    double Zp = (double)p.ion_Z;
+    const double g_v0 = sqrt(2.0 * TRK_RY * TRK_GE / TRK_ME);
+    switch (p.ion_kind_Zeff) {
+    case 1: return Zp * (1.0 - exp(-(vp / g_v0 / pow(Zp, 0.66666666))));
+    case 2: { double c1 = 0.6, c2 = 0.45; return Zp * pow(1.0 + pow(vp / (pow(Zp, c2) * g_v0 * 4.0 / 3.0), -1.0 / c1), -c1); }
+    case 3: {
+        double sz = 0; for (int a = 0; a < p.n_atoms; ++a) sz += p.atom_Z[a] * p.atom_pers[a];
+        double Zt = sz / p.sum_pers;
+        double c1 = 1.0 - 0.26 * exp(-Zt / 11.0 - (Zt - Zp) * (Zt - Zp) / 9.0);
+        double vpvo = pow(Zp, -0.543) * vp / g_v0;
+        double c2 = 1.0 + 0.03 * vpvo * log(Zt);
+        double x = c1 * pow(vpvo / c2 / 1.54, 1.0 + 1.83 / Zp), x2 = x * x, x4 = x2 * x2;
+        return Zp * (8.29 * x + x4) / (0.06 / x + 4.0 + 7.4 * x + x4); }
+    case 4: return p.ion_fixed_Zeff;
+    default: return Zp * (1.0 - exp(-(vp * 125.0 / TRK_CVEL / pow(Zp, 0.66666666))));
+    }
+}
+// SHI_energy_transfer (CDF shells), Monte_Carlo.f90:1719-1780.  The reference's linear search over 1/L
+// (Find_in_1D_array) is kept as a forward scan from the threshold row: same first index with 1/L >= Tot_N.
+TRK_HD double shi_energy_transfer(const DevP &p, Rec &r, int shell) {
+    const double *Ea = p.dshi_E + p.dshi_off[shell], *La = p.dshi_L + p.dshi_off[shell];
+    int N = (int)(p.dshi_off[shell + 1] - p.dshi_off[shell]);
+    double RN = rn(p, r);
+    double E_cur = p.shell_Ip[shell], dL;
+    int M_temp = find_1d(Ea, N, E_cur);
+    if (M_temp > 1) {
+        if (La[M_temp - 2] > 1.0e-10) dL = interp5(Ea[M_temp - 2], Ea[M_temp - 1], La[M_temp - 2], La[M_temp - 1], E_cur);
+        else dL = interp1(Ea[M_temp - 2], Ea[M_temp - 1], La[M_temp - 2], La[M_temp - 1], E_cur);
+    } else dL = La[0];
+    double Tot_N = (dL > 0.0 && La[N - 1] > 0.0) ? 1.0 / dL + RN * (1.0 / La[N - 1] - 1.0 / dL) : 1.5e21;
+    int N_temmp;
+    if (Tot_N < 1e20) {
+        // 1/L is non-decreasing (cumulative cross section): bisection for the first index with 1/L >= Tot_N
+        int lo = 1, hi = N;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (1.0 / La[mid - 1] < Tot_N) lo = mid + 1; else hi = mid; }
+        N_temmp = lo;
+    } else N_temmp = M_temp;
+    if (N_temmp > M_temp) return interp5(1.0 / La[N_temmp - 2], 1.0 / La[N_temmp - 1], Ea[N_temmp - 2], Ea[N_temmp - 1], Tot_N);
+    return p.shell_Ip[shell];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Snapshots: the per-particle share of Calculated_statistics (Monte_Carlo.f90:881-1110) at grid time i
+// ------------------------------------------------------------------------------------------------
+template <class C>
+TRK_HD void snapshot_electron(C &c, const Rec &e, int i) {
+    const DevP &p = c.p;
+    const double tim = p.tg[i - 1];
+    const uint32_t il = e.iter - p.batch_begin;
+    const double cut = (p.cut_off > 0.0) ? p.cut_off : 0.0;
+    double L0 = 0.0, theta0 = 0.0, phi0 = 0.0;
+    if (e.E > cut) { L0 = vel_electron(e.E) * (tim - e.t0) * 1.0e-5; if (L0 < 0.0) L0 = 0.0; theta0 = e.theta; phi0 = e.phi; }
+    double st = sin(theta0);
+    double X = e.X + L0 * st * sin(phi0), Y = e.Y + L0 * st * cos(phi0);
+    double R = sqrt(X * X + Y * Y);
+    int j = find_1d(p.out_R, p.n_r, R);
+    c.tally(TRK3_OUT_NE, (i - 1) + (int64_t)p.Nt * (j - 1), p.out_V[j - 1]);
+    c.tally(TRK3_OUT_EE, (i - 1) + (int64_t)p.Nt * (j - 1), e.E * p.out_V[j - 1]);
+    c.tally(TRK3_OUT_E_E, i - 1, e.E);
+    c.add_f64(p.it.esnap, (size_t)il * p.Nt + (i - 1), e.E);
+    j = find_1d(p.out_R, p.n_r, e.E);                 // sic (:1024): the radius grid doubles as the energy grid
+    c.add_u32(p.it.spec_e, ((size_t)il * p.Nt + (i - 1)) * p.n_r + (j - 1));
+    if (e.E > 0.0) {
+        double xx = theta0 / TRK_PI * 180.0;
+        int jt = (xx < 1.0) ? 1 : ((xx >= 180.0) ? 180 : (int)floor(xx) + 1);   // Find(Out_theta1 = 1..180, xx)
+        c.add_u32(p.it.th_e, ((size_t)il * p.Nt + (i - 1)) * TRK3_NTHETA + (jt - 1));
+    }
+}
+template <class C>
+TRK_HD void snapshot_hole(C &c, const Rec &h, int i) {
+    const DevP &p = c.p;
+    const double tim = p.tg[i - 1];
+    const uint32_t il = h.iter - p.batch_begin;
+    const size_t base = (size_t)il * p.Nt + (i - 1);
+    const double cut = (p.cut_off > 0.0) ? p.cut_off : 0.0;
+    const bool vb = (h.shell == p.vb_shell);
+    if (vb) {
+        c.add_u32(p.it.nvb, base);
+        int j = find_1d(p.dos_E, p.n_dos, h.Ehkin);
+        c.add_u32(p.it.spec_h, base * p.n_dos + (j - 1));
+    }
+    double Xh = h.X, Yh = h.Y;
+    if (h.Mass < 1.0e3 && h.Ehkin > cut) {
+        double L0 = vel_hole(h) * (tim - h.t0) * 1.0e-5; if (L0 < 0.0) L0 = 0.0;
+        double st = sin(h.theta);
+        Xh = h.X + L0 * st * sin(h.phi); Yh = h.Y + L0 * st * cos(h.phi);
+        double xx = h.theta / TRK_PI * 180.0;
+        int jt = (xx < 1.0) ? 1 : ((xx >= 180.0) ? 180 : (int)floor(xx) + 1);
+        c.add_u32(p.it.th_h, base * TRK3_NTHETA + (jt - 1));
+    }
+    double R = sqrt(Xh * Xh + Yh * Yh);
+    int j = find_1d(p.out_R, p.n_r, R);
+    int l = p.shell_atom[h.shell], m = p.shell_num[h.shell];     // 0-based (KOA-1, Shl-1)
+    if (m < p.nshl_atom1) {
+        int64_t idx = (i - 1) + (int64_t)p.Nt * ((j - 1) + (int64_t)p.n_r * (l + (int64_t)p.n_atoms * m));
+        c.tally(TRK3_OUT_NH, idx, p.out_V[j - 1]);
+        c.tally(TRK3_OUT_EH, idx, h.E * p.out_V[j - 1]);
+        c.tally(TRK3_OUT_EHKIN, idx, h.Ehkin * p.out_V[j - 1]);
+        c.tally(TRK3_OUT_E_H, (i - 1) + (int64_t)p.Nt * (l + (int64_t)p.n_atoms * m), h.E + h.Ehkin);
+    }
+    c.add_f64(p.it.esnap, base, h.E + h.Ehkin);
+    if (h.Mass < 1.0e3 && h.L < 1.0e3) {      // Out_diff_coeff, :1089-1096
+        c.add_u32(p.it.diffN, base);
+        c.add_f64(p.it.diffS, base, 1.0 / 3.0 * vel_hole(h) * h.L * 1.0e-6);
+    }
+}
+template <class C>
+TRK_HD void snapshot_photon(C &c, const Rec &ph, int i) {
+    const DevP &p = c.p;
+    if (!(ph.E > 0.0)) return;
+    const double tim = p.tg[i - 1];
+    const uint32_t il = ph.iter - p.batch_begin;
+    const size_t base = (size_t)il * p.Nt + (i - 1);
+    double L0 = TRK_CVEL * (tim - ph.t0) * 1.0e-5; if (L0 < 0.0) L0 = 0.0;
+    double st = sin(ph.theta);
+    double X = ph.X + L0 * st * sin(ph.phi), Y = ph.Y + L0 * st * cos(ph.phi);
+    double R = sqrt(X * X + Y * Y);
+    int j = find_1d(p.out_R, p.n_r, R);
+    c.tally(TRK3_OUT_NPHOT, (i - 1) + (int64_t)p.Nt * (j - 1), p.out_V[j - 1]);
+    c.tally(TRK3_OUT_EPHOT, (i - 1) + (int64_t)p.Nt * (j - 1), ph.E * p.out_V[j - 1]);
+    c.tally(TRK3_OUT_E_PHOT, i - 1, ph.E);
+    c.add_u32(p.it.nph, base);
+    c.add_f64(p.it.esnap, base, ph.E);
+}
+
+// lattice energy of an elastic event in time interval iv at radius R (Monte_Carlo.f90:2414-2436, :2702-2719)
+template <class C>
+TRK_HD void deposit_lattice(C &c, const Rec &r, int iv, double X, double Y, double dE) {
+    const DevP &p = c.p;
+    double R = sqrt(X * X + Y * Y);
+    if (trk_isnan(R)) { c.error(TRK3_ERR_NAN); return; }
+    int j = find_1d(p.out_R, p.n_r, R);
+    c.tally(TRK3_OUT_ELAT, (iv - 1) + (int64_t)p.Nt * (j - 1), dE * p.out_V[j - 1]);
+    c.add_f64(p.it.elat, (size_t)(r.iter - p.batch_begin) * (p.Nt + 2) + iv, dE);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Event handlers.  Each processes the collision of particle `r` at time r.tn (< Tim) and leaves `r`
+// in its post-collision state with a new tn.  `iv` is the time interval of the event.
+// ------------------------------------------------------------------------------------------------
+
+// Electron_Monte_Carlo, Monte_Carlo.f90:2253-2474
+template <class C>
+TRK_HD void electron_event(C &c, Rec &e, int iv) {
+    const DevP &p = c.p;
+    const double Eel = e.E;
+    double IMFP = nfp_2d(Eel, p.ei_E, p.ei_tot, p.n_ei);
+    double EMFP = nfp_2d(Eel, p.ee_E, p.ee_L, p.n_ee);
+    double RN = rn(p, e);
+    const double L = e.L, theta0 = e.theta, phi0 = e.phi;
+    const double st0 = sin(theta0);
+    const double X = e.X + L * st0 * sin(phi0), Y = e.Y + L * st0 * cos(phi0), Z = e.Z + L * cos(theta0);
+    const double t_ev = e.tn;
+    double dE, theta, phi;
+    if (RN * (1.0 / IMFP + 1.0 / EMFP) < 1.0 / IMFP) {          // inelastic: impact ionisation
+        c.event(TRK3_EV_EL_INEL);
+        int shell = which_shell(p, e, p.ei_E, p.ei_L, p.n_ei, Eel);
+        uint64_t id_e = child_id(p, e, 1), id_h = child_id(p, e, 2);
+        IMFP = nfp_1d(Eel, p.ei_E, p.ei_L + (size_t)shell * p.n_ei, p.n_ei);
+        dE = inelastic_dE(p, e, Eel, shell, IMFP, false);
+        theta = acos((Eel - dE) / sqrt(Eel * (Eel - dE)));       // Update_electron_angles_El :1189
+        if (trk_isnan(theta)) { double r2 = rn(p, e); theta = r2 * TRK_PI; }
+        { double r2 = rn(p, e); phi = 2.0 * TRK_PI * r2; }
+        double dE_cur = electron_receives_E(c, e, dE, shell);
+        double phi1, theta1;
+        new_angles(phi0, theta0, TRK_PI / 2.0 - theta, phi + TRK_PI, phi1, theta1);
+        emit_electron(c, e, id_e, dE_cur, t_ev, X, Y, Z, theta1, phi1, TRK3_ERR_21);
+        emit_hole(c, e, id_h, shell, dE - dE_cur, t_ev, X, Y, Z, TRK3_ERR_20);
+    } else {                                                     // elastic: energy to the lattice
+        c.event(TRK3_EV_EL_ELAST);
+        EMFP = nfp_1d(Eel, p.ee_E, p.ee_L, p.n_ee);
+        dE = elastic_dE(p, e, Eel, EMFP, false, 1.0);
+        angles_lattice(p, e, Eel, dE, 1.0, theta, phi);
+        if (trk_isnan(theta) || trk_isnan(phi)) c.error(TRK3_ERR_NAN);
+        deposit_lattice(c, e, iv, X, Y, dE);
+    }
+    IMFP = nfp_2d(Eel - dE, p.ei_E, p.ei_tot, p.n_ei);
+    EMFP = nfp_2d(Eel - dE, p.ee_E, p.ee_L, p.n_ee);
+    RN = rn(p, e);
+    double MFP_tot = -log(RN) / (1.0 / IMFP + 1.0 / EMFP);
+    double phi1, theta1;
+    new_angles(phi0, theta0, theta, phi, phi1, theta1);
+    e.E = Eel - dE; e.t0 = t_ev; e.X = X; e.Y = Y; e.Z = Z; e.L = MFP_tot; e.theta = theta1; e.phi = phi1;
+    e.tn = next_time(e.t0, vel_electron(e.E), MFP_tot);
+    if (e.E < p.cut_off) e.tn = 1.0e20;
+    if (p.work_function > 0 && e.Z < 0.0) {                      // calculate_emission, :2477-2513
+        bool emitted = false; double Ekin = 0.0;
+        if (e.E >= 1.5 * p.bar_height) { emitted = true; Ekin = e.E - p.work_function; }
+        else {
+            double r2 = rn(p, e);
+            double Em_Penetr = 1.0 / (1.0 + exp(p.Em_gamma * (p.Em_E1 - e.E)));
+            Ekin = e.E - p.work_function;
+            if (Ekin > 0.0 && r2 < Em_Penetr) emitted = true;
+            else if (cos(e.theta) < 0) e.theta = TRK_PI - e.theta;
+        }
+        if (emitted) {
+            e.tn = 1.0e30; e.L = 1.0e30;
+            const size_t b = (size_t)(e.iter - p.batch_begin) * (p.Nt + 2) + iv;
+            c.add_u32(p.it.em_cnt, b);
+            c.add_f64(p.it.em_E, b, Ekin);
+            // Out_E = Out_R/10 (:940-941)
+            int j = 1; { double v = Ekin * 10.0; j = find_1d(p.out_R, p.n_r, v); }
+            c.add_u32(p.it.em_spec, b * p.n_r + (j - 1));
+        }
+    }
+    if (e.E < -1.0e-9 || trk_isnan(e.E)) c.error(TRK3_ERR_22);
+}
+
+// check_hole_parameters, Monte_Carlo.f90:682-721: snap the scattered hole to a populated DOS level
+TRK_HD void check_hole_level(const DevP &p, double Eel, double &dE, double &Ehole, double *E_new_electron) {
+    Ehole = Eel - dE;
+    int mhole = find_1d(p.dos_E, p.n_dos, Ehole);
+    if (p.dos_DOS[mhole - 1] < 1.0e-4) {
+        if (E_new_electron) {
+            while (mhole > 1 && p.dos_DOS[mhole - 1] < 1.0e-4) mhole = mhole - 1;
+            double Eloc = p.dos_E[mhole - 1];
+            *E_new_electron = *E_new_electron + (Ehole - Eloc);
+            Ehole = Eloc;
+        } else {
+            while (mhole < p.n_dos && p.dos_DOS[mhole - 1] < 1.0e-4) mhole = mhole + 1;
+            double Eloc = p.dos_E[mhole - 1];
+            dE = dE + (Ehole - Eloc);
+            Ehole = Eloc;
+        }
+    }
+}
+
+// Hole_Monte_Carlo, valence-band branch, Monte_Carlo.f90:2560-2738
+template <class C>
+TRK_HD void vbhole_event(C &c, Rec &h, int iv) {
+    const DevP &p = c.p;
+    const double Eel = h.Ehkin;
+    double HIMFP = nfp_2d(Eel, p.hi_E, p.hi_tot, p.n_hi);
+    double HEMFP = nfp_2d(Eel, p.he_E, p.he_L, p.n_he);
+    double RN = rn(p, h);
+    const double L = h.L, theta0 = h.theta, phi0 = h.phi;
+    const double st0 = sin(theta0);
+    const double X = h.X + L * st0 * sin(phi0), Y = h.Y + L * st0 * cos(phi0), Z = h.Z + L * cos(theta0);
+    const double t_ev = h.tn;
+    double dE, Ehole, htheta1, hphi1;
+    if (RN * (1.0 / HIMFP + 1.0 / HEMFP) < 1.0 / HIMFP && HIMFP < 1e15) {
+        c.event(TRK3_EV_VBH_INEL);
+        int shell = which_shell(p, h, p.hi_E, p.hi_L, p.n_hi, Eel);
+        uint64_t id_e = child_id(p, h, 1), id_h = child_id(p, h, 2);
+        HIMFP = nfp_1d(Eel, p.hi_E, p.hi_L + (size_t)shell * p.n_hi, p.n_hi);
+        dE = inelastic_dE(p, h, Eel, shell, HIMFP, true);
+        // Update_holes_angles_el, :1142-1168
+        double E11 = Eel - dE, Mh = h.Mass * TRK_ME;
+        double htheta = acos(sqrt((Mh + TRK_ME) * (Mh + TRK_ME) / (4.0 * Mh * TRK_ME) * dE / Eel));
+        double hphi; { double r2 = rn(p, h); hphi = 2.0 * TRK_PI * r2; }
+        if (trk_isnan(htheta)) { double r2 = rn(p, h); htheta = TRK_PI * r2; }
+        htheta1 = acos((Eel * (Mh - TRK_ME) + E11 * (Mh + TRK_ME)) / (2 * Mh * sqrt(Eel * E11)));
+        hphi1 = hphi + TRK_PI;
+        if (trk_isnan(htheta1)) { double r2 = rn(p, h); htheta1 = TRK_PI * r2; }
+        double dE_cur = electron_receives_E(c, h, dE, shell);
+        // the new electron is fully sampled first (:2606-2621), then the level check may add the surplus to it (:2660)
+        double IMFP = nfp_2d(dE_cur, p.ei_E, p.ei_tot, p.n_ei);
+        double EMFP = nfp_2d(dE_cur, p.ee_E, p.ee_L, p.n_ee);
+        RN = rn(p, h);
+        double MFP_tot = -log(RN) / (1.0 / IMFP + 1.0 / EMFP);
+        RN = rn(p, h);                                           // sic (:2611): drawn and discarded
+        double phi1, theta1;
+        new_angles(phi0, theta0, htheta, hphi, phi1, theta1);
+        Rec e;
+        e.E = dE_cur; e.Ehkin = 0.0; e.Mass = 1.0; e.t0 = t_ev; e.X = X; e.Y = Y; e.Z = Z; e.L = MFP_tot; e.theta = theta1; e.phi = phi1;
+        e.tn = next_time(t_ev, vel_electron(dE_cur), MFP_tot);
+        if (e.E < p.cut_off) e.tn = 1.0e20;
+        if (e.E < -1.0e-9 || trk_isnan(e.E)) c.error(TRK3_ERR_40);
+        e.id = id_e; e.ctr = 0; e.iter = h.iter; e.shell = -1;
+        emit_hole(c, h, id_h, shell, dE - dE_cur, t_ev, X, Y, Z, TRK3_ERR_41);
+        check_hole_level(p, Eel, dE, Ehole, &e.E);               // NB: tn/L of the new electron keep the pre-shift energy, as in the reference
+        c.count_electron();
+        c.push(SP_ELECTRON, e);
+    } else {
+        c.event(TRK3_EV_VBH_ELAST);
+        HEMFP = nfp_1d(Eel, p.he_E, p.he_L, p.n_he);
+        dE = elastic_dE(p, h, Eel, HEMFP, true, h.Mass);
+        angles_lattice(p, h, Eel, dE, h.Mass, htheta1, hphi1);
+        check_hole_level(p, Eel, dE, Ehole, nullptr);
+        deposit_lattice(c, h, iv, X, Y, dE);
+    }
+    double hphi2, htheta2;
+    new_angles(phi0, theta0, htheta1, hphi1, hphi2, htheta2);
+    h.t0 = t_ev; h.X = X; h.Y = Y; h.Z = Z; h.theta = htheta2; h.phi = hphi2;
+    hole_parameters(p, h, h, Ehole + p.Egap, Eel);
+    if (h.Ehkin < -1.0e-9 || trk_isnan(h.Ehkin)) c.error(TRK3_ERR_20);
+}
+
+// count_for_Auger_shells / Choose_for_Auger_shell, Monte_Carlo.f90:1576-1647
+TRK_HD double auger_count(const DevP &p, double NRG, bool second_e) {
+    double coun = 0.0;
+    for (int s = 0; s < p.n_shells; ++s) {
+        double E_delta = second_e ? 1.0e10 : NRG - p.shell_Ip[s];
+        if (NRG > p.shell_Ip[s] + 1.0e-3 && E_delta >= p.Egap) coun = coun + p.shell_Nel[s];
+    }
+    return coun;
+}
+TRK_HD int auger_choose(const DevP &p, double NRG, double Shel, bool second_e, int dflt) {
+    double coun_sh = 0.0;
+    int sel = dflt;
+    for (int s = 0; s < p.n_shells; ++s) {
+        double E_delta = second_e ? 1.0e10 : NRG - p.shell_Ip[s];
+        if (NRG > p.shell_Ip[s] + 1.0e-3 && E_delta >= p.Egap) {
+            coun_sh = coun_sh + p.shell_Nel[s];
+            if (coun_sh >= Shel) sel = s;
+        }
+        if (coun_sh >= Shel) break;
+    }
+    return sel;
+}
+
+// Hole_Monte_Carlo, deep-shell branch (Auger / radiative decay), Monte_Carlo.f90:2739-2868 with
+// Auger_decay :1366-1443 and Radiative_decay :2969-2997
+template <class C>
+TRK_HD void corehole_event(C &c, Rec &h) {
+    const DevP &p = c.p;
+    const double t_ev = h.tn;
+    const int sh0 = h.shell;
+    double RN = rn(p, h);
+    const double t_Auger = p.shell_auger[sh0], t_Radiat = p.shell_radiat[sh0];
+    const double Ip0 = p.shell_Ip[sh0];
+    if (RN * (1.0 / t_Auger + 1.0 / t_Radiat) < 1.0 / t_Auger) {
+        double coun = auger_count(p, Ip0, false);
+        RN = rn(p, h);
+        int s1 = auger_choose(p, Ip0, RN * coun, false, sh0);
+        double dE_cur = (s1 == p.vb_shell) ? from_where_in_VB(p, h, false, 0.0) : 0.0;
+        double E_new1 = dE_cur + p.shell_Ip[s1];
+        double Energy_diff = Ip0 - E_new1;
+        coun = auger_count(p, Energy_diff, true);
+        int s2 = -1; double Ee = -1.0e-10, E_new2 = 0.0;
+        if (coun > 0.0) {
+            RN = rn(p, h);
+            s2 = auger_choose(p, Energy_diff, RN * coun, true, -1);
+        }
+        if (s2 >= 0) {
+            dE_cur = (s2 == p.vb_shell) ? from_where_in_VB(p, h, true, Energy_diff - p.shell_Ip[s2]) : 0.0;
+            E_new2 = dE_cur + p.shell_Ip[s2];
+            Ee = Energy_diff - E_new2;
+        }
+        if (Ee < 0.0 || E_new1 < 0.0 || E_new2 < 0.0) c.error(TRK3_ERR_25);
+        if (s2 >= 0) {
+            c.event(TRK3_EV_AUGER);
+            if (fabs(h.E - (Ee + E_new1 + E_new2)) > 1e-10) c.error(TRK3_ERR_AUGER_BALANCE);
+            double htheta, hphi;
+            random_angles(p, h, htheta, hphi);
+            const double Ehk_prev = h.Ehkin;
+            h.t0 = t_ev; h.shell = s1; h.theta = htheta; h.phi = hphi;
+            hole_parameters(p, h, h, E_new1, Ehk_prev);
+            uint64_t id_e = child_id(p, h, 1), id_h = child_id(p, h, 2);
+            emit_hole(c, h, id_h, s2, E_new2, t_ev, h.X, h.Y, h.Z, TRK3_ERR_20);
+            // Auger electron: isotropic in angle (:2800-2813); phi is drawn before theta
+            double IMFP = nfp_2d(Ee, p.ei_E, p.ei_tot, p.n_ei);
+            double EMFP = nfp_2d(Ee, p.ee_E, p.ee_L, p.n_ee);
+            RN = rn(p, h);
+            double MFP_tot = -log(RN) / (1.0 / IMFP + 1.0 / EMFP);
+            RN = rn(p, h); double phi1 = 2.0 * TRK_PI * RN;
+            RN = rn(p, h); double theta1 = TRK_PI * RN;
+            Rec e;
+            e.E = Ee; e.Ehkin = 0.0; e.Mass = 1.0; e.t0 = t_ev; e.X = h.X; e.Y = h.Y; e.Z = h.Z; e.L = MFP_tot; e.theta = theta1; e.phi = phi1;
+            e.tn = next_time(t_ev, vel_electron(Ee), MFP_tot);
+            if (e.E < p.cut_off) e.tn = 1.0e20;
+            if (e.E < -1.0e-9 || trk_isnan(e.E)) c.error(TRK3_ERR_23);
+            e.id = id_e; e.ctr = 0; e.iter = h.iter; e.shell = -1;
+            c.count_electron();
+            c.push(SP_ELECTRON, e);
+        } else {
+            c.event(TRK3_EV_AUGER_FROZEN);
+            h.t0 = t_ev; h.tn = 1e21;                             // :2828
+        }
+    } else {
+        c.event(TRK3_EV_RADIATIVE);
+        double coun = auger_count(p, Ip0, true);
+        RN = rn(p, h);
+        int s1 = auger_choose(p, Ip0, RN * coun, true, sh0);
+        double dE_cur = (s1 == p.vb_shell) ? from_where_in_VB(p, h, false, 0.0) : 0.0;
+        double E_new1 = dE_cur + p.shell_Ip[s1];
+        double dE = Ip0 - E_new1;
+        double htheta, hphi;
+        random_angles(p, h, htheta, hphi);
+        const double Ehk_prev = h.Ehkin;
+        h.t0 = t_ev; h.shell = s1; h.theta = htheta; h.phi = hphi;
+        hole_parameters(p, h, h, E_new1, Ehk_prev);
+        // photon (:2843-2866); the reference's slot-reuse bug (:2844 vs :2963) does not exist here
+        uint64_t id_p = child_id(p, h, 3);
+        double IMFP = nfp_2d(dE, p.ph_E, p.ph_tot, p.n_ph);
+        RN = rn(p, h);
+        double MFP_tot = -log(RN) * IMFP;
+        RN = rn(p, h); double phi1 = 2.0 * TRK_PI * RN;
+        RN = rn(p, h); double theta1 = TRK_PI * RN;
+        Rec ph;
+        ph.E = dE; ph.Ehkin = 0.0; ph.Mass = 0.0; ph.t0 = t_ev; ph.X = h.X; ph.Y = h.Y; ph.Z = h.Z; ph.L = MFP_tot; ph.theta = theta1; ph.phi = phi1;
+        ph.tn = next_time(t_ev, TRK_CVEL, MFP_tot);
+        if (ph.E < -1.0e-9 || trk_isnan(ph.E)) c.error(TRK3_ERR_30);
+        ph.id = id_p; ph.ctr = 0; ph.iter = h.iter; ph.shell = -1;
+        c.count_photon();
+        c.push(SP_PHOTON, ph);
+    }
+}
+
+// Photon_Monte_Carlo, Monte_Carlo.f90:2873-2965: photoabsorption; the photon disappears
+template <class C>
+TRK_HD void photon_event(C &c, Rec &ph) {
+    const DevP &p = c.p;
+    c.event(TRK3_EV_PHOTON);
+    const double Eel = ph.E, L = ph.L, theta0 = ph.theta, phi0 = ph.phi, t_ev = ph.tn;
+    const double st0 = sin(theta0);
+    const double X = ph.X + L * st0 * sin(phi0), Y = ph.Y + L * st0 * cos(phi0), Z = ph.Z + L * cos(theta0);
+    int shell = which_shell(p, ph, p.ph_E, p.ph_L, p.n_ph, Eel);
+    uint64_t id_e = child_id(p, ph, 1), id_h = child_id(p, ph, 2);
+    double dE_cur = electron_receives_E(c, ph, Eel, shell);
+    double phi1, theta1;
+    new_angles(phi0, theta0, TRK_PI / 2.0, 0.0, phi1, theta1);
+    emit_electron(c, ph, id_e, dE_cur, t_ev, X, Y, Z, theta1, phi1, TRK3_ERR_50);
+    emit_hole(c, ph, id_h, shell, Eel - dE_cur, t_ev, X, Y, Z, TRK3_ERR_51);
+    ph.E = 0.0; ph.t0 = 1.0e27; ph.tn = 1.0e27;
+}
+
+// SHI_Monte_Carlo + the ion part of Monte_Carlo_modelling (:548-570, :593-597, :2153-2249):
+// the whole trajectory of the ion of one iteration; emits an (electron, hole) pair per collision.
+template <class C>
+TRK_HD void shi_history(C &c, uint32_t iter) {
+    const DevP &p = c.p;
+    Rec s;      // E, t0, tn, X, Y, Z, L as the Ion; Mass/Zeff in locals
+    s.E = p.ion_E; s.t0 = 0.0; s.tn = 0.0; s.X = 0.0; s.Y = 0.0; s.Z = 0.0; s.L = 0.0; s.theta = 0.0; s.phi = 0.0; s.Ehkin = 0.0; s.Mass = p.ion_mass;
+    s.id = 0; s.ctr = 0; s.iter = iter; s.shell = -1;
+    const double MSHI = p.ion_mass * TRK_MP;
+    double Zeff = p.ion_Zeff0;
+    {
+        double lam = nfp_2d(s.E, p.shi_E, p.shi_tot, p.n_shi);
+        double RN = rn(p, s);
+        s.L = -lam * log(RN);
+        s.tn = next_time(s.t0, sqrt(2.0 * s.E * TRK_GE / MSHI), s.L);
+    }
+    while (s.tn < p.Tim) {
+        c.event(TRK3_EV_SHI);
+        int shell = which_shell(p, s, p.shi_E, p.shi_L, p.n_shi, s.E);
+        double dE = shi_energy_transfer(p, s, shell);
+        double lam = nfp_2d(s.E, p.shi_E, p.shi_tot, p.n_shi);
+        double RN = rn(p, s);
+        double SHI_IMFP = -lam * log(RN);
+        double Z = s.Z + s.L;
+        s.E = s.E - dE; s.t0 = s.tn; s.Z = Z; s.L = SHI_IMFP;
+        s.tn = next_time(s.t0, sqrt(2.0 * s.E * TRK_GE / MSHI), SHI_IMFP);
+        Zeff = shi_zeff(p, s.E);
+        uint64_t id_e = child_id(p, s, 1), id_h = child_id(p, s, 2);
+        double dE_cur = electron_receives_E(c, s, dE, shell);
+        // Update_electron_angles_SHI (:1170-1187) with the UPDATED ion energy
+        double theta = (s.E <= 0.0) ? TRK_PI / 2.0 : acos(sqrt((MSHI + TRK_ME) * (MSHI + TRK_ME) / (4.0 * MSHI * TRK_ME) * dE / s.E));
+        double phi; { double r2 = rn(p, s); phi = 2.0 * TRK_PI * r2; }
+        // Impact_parameter (:1113-1126) is evaluated after the electron's free path is sampled (:2212-2218)
+        double A = 1.0 + MSHI / TRK_ME;
+        double b = TRK_A0 * Zeff * TRK_RY / s.E * sqrt(4.0 * s.E / dE * MSHI / TRK_ME - A * A);
+        double X = s.X + b * sin(phi), Y = s.Y + b * cos(phi);
+        emit_electron(c, s, id_e, dE_cur, s.t0, X, Y, Z, theta, phi, TRK3_ERR_20);
+        emit_hole(c, s, id_h, shell, dE - dE_cur, s.t0, X, Y, Z, TRK3_ERR_20);
+        if (s.Z >= p.layer) s.tn = 1e16;                          // :597 the ion has left the layer
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Histories: follow one particle from its record to Tim, depositing snapshots on the way.
+// Returns true when the record is finished, false when it must continue in another species queue.
+// `ig` = next grid index to snapshot (first i with t0 < tg(i)).
+// ------------------------------------------------------------------------------------------------
+template <class C>
+TRK_HD void begin_electron(C &c, const Rec &e, int &ig) {
+    const DevP &p = c.p;
+    ig = interval_of(p, e.t0);
+    c.add_u32(p.it.created, (size_t)(e.iter - p.batch_begin) * (p.Nt + 2) + ig);    // Tot_Nel bookkeeping
+}
+// one step = snapshots spanned by the current free flight, then the collision at tn; false when history ended
+template <class C>
+TRK_HD bool step_electron(C &c, Rec &e, int &ig) {
+    const DevP &p = c.p;
+    while (ig <= p.Nt && p.tg[ig - 1] <= e.tn) { snapshot_electron(c, e, ig); ++ig; }
+    if (ig > p.Nt) return false;
+    electron_event(c, e, ig);
+    return true;
+}
+template <class C>
+TRK_HD bool step_vbhole(C &c, Rec &h, int &ig) {
+    const DevP &p = c.p;
+    while (ig <= p.Nt && p.tg[ig - 1] <= h.tn) { snapshot_hole(c, h, ig); ++ig; }
+    if (ig > p.Nt) return false;
+    vbhole_event(c, h, ig);
+    return true;
+}
+// core hole: after a decay the hole may have hopped into the valence band -> continue as a VB hole (other queue)
+template <class C>
+TRK_HD bool step_corehole(C &c, Rec &h, int &ig) {
+    const DevP &p = c.p;
+    while (ig <= p.Nt && p.tg[ig - 1] <= h.tn) { snapshot_hole(c, h, ig); ++ig; }
+    if (ig > p.Nt) return false;
+    corehole_event(c, h);
+    if (h.shell == p.vb_shell) { c.push(SP_VBHOLE, h); return false; }
+    return true;
+}
+template <class C>
+TRK_HD bool step_photon(C &c, Rec &ph, int &ig) {
+    const DevP &p = c.p;
+    while (ig <= p.Nt && p.tg[ig - 1] <= ph.tn) { snapshot_photon(c, ph, ig); ++ig; }
+    if (ig > p.Nt) return false;
+    photon_event(c, ph);
+    return false;
+}
+
+}  // namespace trk3
