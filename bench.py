@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the TREKIS-3 Monte-Carlo hot path on B200.
+
+Metric (BASELINE.json): MC iterations/s (whole job, all GPUs); events/s reported beside it.
+Workload at N=1: BASELINE.json configs[1] -- Au 2187 MeV in SiO2_cryst, photon transport and Auger/radiative
+decays on, 1000 MC iterations per step.  A step is one do_Monte_Carlo call (1000 ion impacts + full cascades
+to 100 fs).  N>1: weak scaling -- every rank runs its own 1000 iterations (disjoint global iteration ranges,
+Philox streams keyed by the global index) followed by ONE NCCL all-reduce of the packed tally buffer.
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA engine
+  python bench.py --impl reference ...                      the CPU restatement of the reference on the host cores
+
+One JSON line on stdout (rank 0).  See the task contract for the keys.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "MC iterations/s (Monte_Carlo.f90 cascade engine, whole job)"
+UNIT = "iterations/s"
+
+
+def load_case(config, nmc):
+    import trekis3_b200 as tk
+    run_dir = os.path.join(ROOT, ".bench_run", f"{config}_{os.getpid()}")
+    tk.make_run_dir(run_dir, config, nmc=nmc)
+    case = tk.Case.load(run_dir)
+    case.build_tables(shi_window_only=True, cache_dir=os.path.join(ROOT, ".table_cache"))
+    return case
+
+
+def workload_name(config, nmc):
+    import trekis3_b200 as tk
+    mat, z, e, ph, _ = tk.CONFIGS[config]
+    ion = {54: "Xe", 79: "Au", 92: "U"}.get(z, str(z))
+    return f"{config}: {ion} {e:g} MeV in {mat}, photons {'on' if ph else 'off'}, {nmc} MC iterations per step, T=100 fs"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(case, seconds, threads=0):
+    """Oracle (CPU restatement of the reference algorithm, all host threads) on a bounded sample."""
+    import oracle_api
+    cores = os.cpu_count() or 1
+    n_done, t0 = 0, time.perf_counter()
+    chunk = max(cores, 1)
+    events = 0
+    while True:
+        _, st, _, _ = oracle_api.run(case, n_done, n_done + chunk, rng_mode=0, threads=threads)
+        n_done += chunk
+        events += st["total_events"]
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            break
+        # grow the chunk so that the thread pool start-up does not dominate
+        chunk = min(max(chunk, int(chunk * 2)), max(cores, int((seconds - dt) / max(dt / n_done, 1e-9))))
+        if chunk < 1:
+            break
+    dt = time.perf_counter() - t0
+    return n_done / dt, events / dt, n_done, dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    case = load_case(args.config, args.nmc)
+    per_step = max(2.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_reference_rate(case, min(per_step, 2.0))
+    rates, ev_rates, n_tot, t_tot = [], [], 0, 0.0
+    for _ in range(args.steps):
+        r, e, n, dt, cores = cpu_reference_rate(case, per_step)
+        rates.append(r); ev_rates.append(e); n_tot += n; t_tot += dt
+    value = n_tot / t_tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, args.nmc), "sample": f"{n_tot} iterations in {t_tot:.1f} s"},
+        "events_per_s": sum(ev_rates) / len(ev_rates),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"oracle/trk3_oracle.cpp (reference algorithm incl. O(N) next-event search), "
+                                   f"{n_tot} iterations of the same workload in {t_tot:.1f} s on {os.cpu_count()} threads; "
+                                   "the Fortran reference cannot be built here (no Fortran compiler in the image)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def table_bytes(case):
+    return int(sum(a.nbytes for a in case.table_arrays().values()))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import trekis3_b200 as tk
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    case = load_case(args.config, args.nmc)
+    nmc = args.nmc
+    lay = case.layout()
+    stream = torch.cuda.Stream()
+    tally = torch.zeros(lay.total, dtype=torch.float64, device="cuda")
+    eng = tk.Engine(case, device=local_rank, batch=args.batch)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_device_tallies(tally.data_ptr())
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")     # > 126 MB L2
+
+    def step(k):
+        # iterations of this rank for step k: disjoint global ranges -> independent Philox streams
+        first = ((k * world) + rank) * nmc
+        with torch.cuda.stream(stream):
+            tally.zero_()
+            st = eng.run_device(first, first + nmc)
+            if dist is not None:
+                dist.all_reduce(tally)          # the single collective of the path (MPI_Reduce x26 in the reference)
+        return st
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    eng.set_option("profile", 1)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    events_total, launches, drift, errors = 0, 0, 0.0, {}
+    ev_by_class = {}
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                            # L2 flush between timed iterations (untimed)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            ev[k][0].record(stream)
+        st = step(args.warmup + k)
+        with torch.cuda.stream(stream):
+            ev[k][1].record(stream)
+        events_total += st["total_events"]; launches += st["kernel_launches"]
+        drift = max(drift, st["max_energy_drift"])
+        for n, v in st["events"].items():
+            ev_by_class[n] = ev_by_class.get(n, 0) + v
+        for n, v in st["errors"].items():
+            errors[n] = errors.get(n, 0) + v
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms, float(events_total)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, events_all = float(tmax[0]), float(tsum[1])
+    else:
+        events_all = float(events_total)
+    value = world * nmc * args.steps / (ms * 1e-3)
+    ktimes = eng.kernel_times()
+
+    # ---- end-to-end through the public API with HOST buffers (tables H2D + tallies D2H inside the timed region)
+    e2e_steps = max(1, min(args.steps, 3))
+    host_tally = np.zeros(lay.total)
+    tk.do_Monte_Carlo(case, NMC=nmc, device=local_rank, batch=args.batch)            # warm-up of the public path
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        first = ((k * world) + rank) * nmc
+        tl, _ = tk.do_Monte_Carlo(case, NMC=nmc, device=local_rank, it_begin=first, batch=args.batch)
+        if dist is not None:
+            g = torch.from_numpy(tl).cuda(); dist.all_reduce(g); tl = g.cpu().numpy()
+        host_tally += tl
+    torch.cuda.synchronize()
+    e2e_t = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([e2e_t], dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); e2e_t = float(tt[0])
+    e2e_value = world * nmc * e2e_steps / e2e_t
+    h2d = table_bytes(case) + 4096
+    d2h = int(lay.total * 8 + nmc * lay.Nt * 20)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (per-class CUDA-event times measured live above)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+    B = tk.EVENT_BYTES
+    class_bytes = {
+        "k_wave<electron>": ev_by_class.get("el_inelastic", 0) * B["el_inelastic"] + ev_by_class.get("el_elastic", 0) * B["el_elastic"],
+        "k_wave<vbhole>": ev_by_class.get("vbh_inelastic", 0) * B["vbh_inelastic"] + ev_by_class.get("vbh_elastic", 0) * B["vbh_elastic"],
+        "k_wave<corehole>": ev_by_class.get("auger", 0) * B["auger"] + ev_by_class.get("radiative", 0) * B["radiative"] + ev_by_class.get("auger_frozen", 0) * B["auger_frozen"],
+        "k_wave<photon>": ev_by_class.get("photon", 0) * B["photon"],
+        "k_shi": ev_by_class.get("shi", 0) * B["shi"],
+    }
+    dom = max((k for k in ktimes if k in class_bytes), key=lambda k: ktimes[k]["ms"])
+    dom_ms, dom_n = ktimes[dom]["ms"], max(1, ktimes[dom]["launches"])
+    achieved = class_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "launches": dom_n, "avg_launch_ms": dom_ms / dom_n,
+                "algorithmic_bytes_per_launch": class_bytes[dom] / dom_n,
+                "kernel_share_of_step": dom_ms / ms if ms > 0 else None,
+                "note": "algorithmic bytes = events x compulsory particle-state bytes (SURVEY.md 8d); histories stay in "
+                        "registers between events and tables are L2-resident, so the kernel is FP64/latency bound, not HBM bound"}
+
+    # ---- CPU baseline: oracle on the host cores, bounded sample of the same workload
+    cpu = None
+    if not args.no_cpu_baseline:
+        r, e, n, dt, cores = cpu_reference_rate(case, args.cpu_seconds)
+        cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port", "events_per_s": e,
+               "sample": f"oracle/trk3_oracle.cpp (restated reference, incl. its O(N) next-event search), {n} iterations of the "
+                         f"same workload in {dt:.1f} s on {cores} host threads"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, nmc), "iterations_in_flight": args.batch,
+                   "l2": "256 MiB buffer written between timed steps (L2 flush); queues stream through HBM",
+                   "parallelism": f"iterations sharded over {world} GPU(s), one NCCL all-reduce of {lay.total} doubles per step",
+                   "inputs": "shipped INPUT_CDF/INPUT_DOS files; radiative widths from data/INPUT_EADL/radiative_widths.dat "
+                             "(approximate, EADL2023.ALL is not redistributable)"},
+        "events_per_s": events_all / (ms * 1e-3), "events_per_s_per_gpu": events_all / (ms * 1e-3) / world,
+        "events_by_class": ev_by_class, "wall_s": t_wall,
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "trekis3_b200.do_Monte_Carlo(case): engine create + table upload + MC + tally download + destroy per step"},
+        "gpu_launches": launches,
+        "kernel_times_ms": ktimes,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "max_energy_drift": drift, "errors": errors,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--nmc", type=int, default=None, help="iterations per step (default: the config's NMC)")
+    ap.add_argument("--batch", type=int, default=512, help="iterations in flight on the GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    import trekis3_b200 as tk
+    if args.nmc is None:
+        args.nmc = tk.CONFIGS[args.config][4]
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 0)
+    if not all(os.path.exists(tk.lib_path(n)) for n in ("host", "gpu", "oracle")):
+        import __graft_entry__ as g
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            g.build()
+        else:
+            for _ in range(600):
+                if all(os.path.exists(tk.lib_path(n)) for n in ("host", "gpu", "oracle")):
+                    break
+                time.sleep(0.5)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

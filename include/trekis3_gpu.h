@@ -216,7 +216,14 @@ int trk3_mc_download_tallies(trk3_engine *eng, double *tallies_add_into);
  * conservation check (Total_numbers.txt, manual section VI).  Valid after a run. */
 int trk3_mc_iteration_energies(trk3_engine *eng, double *out, int64_t capacity_doubles, int64_t *n_iter);
 
-/* Tunables: batch of iterations in flight, queue capacity per iteration, threads per block */
+/* Plumbing for frameworks that own the stream / the tally buffer (torch.distributed + NCCL all-reduce). */
+int trk3_mc_set_stream(trk3_engine *eng, void *cuda_stream);
+int trk3_mc_set_device_tallies(trk3_engine *eng, double *device_buffer);
+/* Device time per kernel class since option "profile"=1 (0 electron wave, 1 valence-hole wave, 2 core-hole
+ * wave, 3 photon wave, 4 ion tracks, 5 finalize); returns the number of classes. */
+int trk3_mc_kernel_times(trk3_engine *eng, double *ms, uint64_t *launches, int n);
+
+/* Tunables: "batch" iterations in flight, "cap_factor" queue capacity, "use_smem", "refill_min", "profile" ... */
 int trk3_mc_set_option(trk3_engine *eng, const char *name, double value);
 
 const trk3_tally_layout *trk3_mc_layout(const trk3_engine *eng);

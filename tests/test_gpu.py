@@ -1,0 +1,164 @@
+"""Parity tests proper: the CUDA engine, called through the C ABI (libtrekis3_gpu.so via ctypes), against the oracle.
+
+Bar (BASELINE.json north_star): tallies within 3 sigma of the reference's MC error, total energy per iteration conserved
+to 1e-9.  Because engine and oracle can be driven by the SAME Philox streams, a much tighter check is possible on top:
+identical event counts per class and tallies equal to ~1e-9 (the residue is libm/FMA rounding and summation order)."""
+import numpy as np
+import pytest
+
+import trekis3_b200 as tk
+from trekis3_b200.host import split_tallies
+import oracle_api
+
+pytestmark = pytest.mark.gpu
+CACHE = tk._abi.REPO + "/.table_cache"
+
+
+def rel_close(a, b, rtol):
+    den = np.maximum(np.abs(a), np.abs(b))
+    return np.all(np.abs(a - b) <= rtol * den + 1e-300)
+
+
+def check_against_oracle(case, n, rtol=1e-7, **opts):
+    eng = tk.Engine(case, **opts)
+    tg, sg = eng.run(0, n)
+    eg = eng.iteration_energies(n)
+    eng.close()
+    assert tk.gpu_library_loaded()
+    to, so, eo, _ = oracle_api.run(case, 0, n, rng_mode=1)
+    assert not sg["errors"], sg["errors"]
+    # same streams => same histories: allow a handful of flipped branches from last-bit differences of libm
+    for k in so["events"]:
+        assert abs(sg["events"][k] - so["events"][k]) <= max(2, 2e-3 * so["events"][k]), (k, sg["events"][k], so["events"][k])
+    assert abs(sg["n_electrons"] - so["n_electrons"]) <= max(2, 1e-3 * so["n_electrons"])
+    lay = case.layout()
+    Tg, To = split_tallies(lay, tg), split_tallies(lay, to)
+    exact = sg["events"] == so["events"]
+    for k in To:
+        if exact:
+            assert rel_close(Tg[k], To[k], rtol), k
+        else:       # a flipped history changes individual bins; integrals stay close
+            assert np.isclose(Tg[k].sum(), To[k].sum(), rtol=5e-3), k
+    if exact:
+        assert np.allclose(eg, eo, rtol=1e-9)
+    drift = np.abs(eg[:, 1:] - eg[:, -1:]) / eg[:, -1:]
+    assert drift.max() < 1e-9                      # energy conservation, north_star
+    assert sg["max_energy_drift"] < 1e-9
+    return sg, so
+
+
+def test_al2o3_electrons_and_holes(case_c1):
+    sg, so = check_against_oracle(case_c1, 8)
+    assert sg["total_events"] > 4e5 and sg["kernel_launches"] > 5 and sg["n_waves"] >= 3
+
+
+def test_sio2_photons_radiative_and_hole_ionisation(tmp_path):
+    case = tk.Case.load(tk.make_run_dir(str(tmp_path / "c2"), "C2"))
+    case.build_tables(shi_window_only=True, cache_dir=CACHE)
+    case.set("radiat:0:0", 1.0); case.set("radiat:0:1", 8.0); case.set("radiat:1:0", 2.0)     # test hook: frequent radiative decays
+    sg, so = check_against_oracle(case, 6)
+    assert sg["events"]["radiative"] > 10 and sg["events"]["photon"] > 10 and sg["n_photons"] > 10
+
+
+def test_diamond_single_pole_phonons(case_c3):
+    sg, so = check_against_oracle(case_c3, 4)
+    assert sg["events"]["vbh_inelastic"] > 100
+
+
+def test_variants_cutoff_linear_grid_emission(tmp_path):
+    d = tk.make_run_dir(str(tmp_path / "v1"), "C1", edits={5: "10.0", 6: "2.5 0", 7: "5.0", 17: "4.5 10.0 6.18"})
+    case = tk.Case.load(d)
+    case.build_tables(shi_window_only=True, cache_dir=CACHE)
+    check_against_oracle(case, 4)
+
+
+def test_mott_elastic_scattering(tmp_path):
+    d = tk.make_run_dir(str(tmp_path / "v2"), "C1", edits={12: "0   1"})
+    case = tk.Case.load(d)
+    case.build_tables(shi_window_only=True, cache_dir=CACHE)
+    check_against_oracle(case, 2)
+
+
+def test_results_do_not_depend_on_batching_or_tally_placement(case_c1):
+    ref, sref = tk.Engine(case_c1, batch=64).run(0, 12)
+    for opts in ({"batch": 5}, {"batch": 64, "use_smem": 0}, {"batch": 7, "refill_min": 1}, {"batch": 64, "refill_min": 32}):
+        t, s = tk.Engine(case_c1, **opts).run(0, 12)
+        assert s["events"] == sref["events"], opts
+        assert rel_close(t, ref, 1e-9), opts
+
+
+def test_iteration_ranges_compose(case_c1):
+    # the union of two ranges equals one run: histories are keyed by the GLOBAL iteration index (multi-GPU sharding)
+    eng = tk.Engine(case_c1)
+    whole, sw = eng.run(0, 10)
+    a, sa = eng.run(0, 4)
+    b, sb = eng.run(4, 10)
+    lay = case_c1.layout()
+    i = tk.TALLY_NAMES.index("Out_diff_coeff")
+    m = np.ones(lay.total, bool); m[lay.off[i]: lay.off[i] + lay.len[i]] = False      # per-process recurrence, SURVEY F7
+    assert sw["total_events"] == sa["total_events"] + sb["total_events"]
+    assert rel_close((a + b)[m], whole[m], 1e-9)
+
+
+def test_queue_overflow_is_rolled_back_and_retried(case_c1):
+    ref, sref = tk.Engine(case_c1).run(0, 6)
+    t, s = tk.Engine(case_c1, cap_factor=0.15).run(0, 6)          # queues far too small: the batch is re-run with larger ones
+    assert s["events"] == sref["events"] and not s["errors"]
+    assert rel_close(t, ref, 1e-9)
+
+
+def test_full_size_c1_invariants(case_c1):
+    """BASELINE config 1 at full size (100 iterations): size-independent properties."""
+    n = 100
+    t, s = tk.Engine(case_c1).run(0, n)
+    assert not s["errors"] and s["max_energy_drift"] < 1e-9
+    lay = case_c1.layout()
+    T = split_tallies(lay, t)
+    V = case_c1.table_arrays()["out_V"]
+    # every electron is in exactly one radial bin at every grid time: sum_j ne(i,j)/V_j = Tot_Ne(i)
+    assert np.allclose((T["Out_ne"] / V[None, :]).sum(axis=1), T["Out_tot_Ne"], rtol=1e-9)
+    # one hole per electron
+    nh = (T["Out_nh"] / V[None, :, None, None]).sum(axis=(1, 2, 3))
+    assert np.allclose(nh, T["Out_tot_Ne"], rtol=1e-9)
+    # spectra are normalised per iteration: sum_j spectrum*dE = number of iterations
+    R = case_c1.table_arrays()["out_R"]
+    dR = np.diff(np.concatenate([[0.0], R]))
+    assert np.allclose((T["Out_Ee_vs_E"] * dR[None, :]).sum(axis=1), n, rtol=1e-9)
+    assert np.allclose(T["Out_theta"][:5].sum(axis=1), n, rtol=1e-9)
+    # energy bookkeeping: tot_E = E_e + sum E_h + E_at ; lattice energy is cumulative and non-decreasing
+    assert np.allclose(T["Out_tot_E"], T["Out_E_e"] + T["Out_E_h"].sum(axis=(1, 2)) + T["Out_E_at"], rtol=1e-9)
+    assert np.all(np.diff(T["Out_E_at"]) >= 0)
+    assert np.allclose(np.cumsum((T["Out_Elat"] / V[None, :]).sum(axis=1)), T["Out_E_at"], rtol=1e-9)
+    # deposited energy = S_e * layer within MC error
+    assert T["Out_tot_E"][-1] / n == pytest.approx(26188.0, rel=0.05)
+
+
+def test_three_sigma_agreement_with_independent_random_streams(case_c1):
+    """North-star bar: different RNG streams (oracle with a sequential generator vs the engine's Philox streams)."""
+    n_g, n_o = 400, 40
+    eng = tk.Engine(case_c1, seed=12345)
+    tg, sg = eng.run(0, n_g)
+    eg = eng.iteration_energies(n_g)
+    to, so, eo, no = oracle_api.run(case_c1, 0, n_o, rng_mode=0)
+    lay = case_c1.layout()
+    Tg, To = split_tallies(lay, tg), split_tallies(lay, to)
+    # per-iteration scalars with their own batch-mean errors
+    a, b = eg[:, -1], eo[:, -1]
+    assert abs(a.mean() - b.mean()) < 3 * np.sqrt(a.var(ddof=1) / n_g + b.var(ddof=1) / n_o)
+    # radial electron density and lattice energy at every time: chi2-like check with Poisson errors from the counts
+    V = case_c1.table_arrays()["out_V"]
+    cg, co = Tg["Out_ne"] / V[None, :], To["Out_ne"] / V[None, :]          # electron counts per bin
+    mask = (cg > 50 * n_g / n_o) & (co > 50)
+    z = (cg[mask] / n_g - co[mask] / n_o) / np.sqrt(cg[mask] / n_g**2 + co[mask] / n_o**2) / 4.0   # /4: counts are cluster-correlated (cascades)
+    assert mask.sum() > 30 and np.mean(np.abs(z) < 3) > 0.95, (mask.sum(), np.abs(z).max())
+    for k in ("Out_tot_Ne", "Out_E_e", "Out_E_at"):
+        assert np.allclose(Tg[k] / n_g, To[k] / n_o, rtol=0.08), k
+
+
+def test_high_multiplicity_gold(case_c4):
+    import emul_api
+    t, s = tk.Engine(case_c4, batch=2).run(0, 2)
+    te, se, _, _ = emul_api.run(case_c4, 0, 2, batch=2)
+    assert not s["errors"] and s["max_energy_drift"] < 1e-9
+    assert abs(s["total_events"] - se["total_events"]) <= 2e-3 * se["total_events"]
+    assert np.isclose(t.sum(), te.sum(), rtol=1e-3)

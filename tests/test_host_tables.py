@@ -1,0 +1,237 @@
+"""Host half: input readers and the CDF table builder (restating Cross_sections.f90 / Analytical_IMFPs.f90).
+
+The reference ships no golden tables (parity unpinned), so the checks are: an independent numpy
+restatement of the integrators at a few points (1e-12), closed-form limits, sum rules, and structural invariants."""
+import math
+
+import numpy as np
+import pytest
+
+import trekis3_b200 as tk
+
+g_Pi = 3.1415926535897932384626433832795
+g_e = 1.602176487e-19
+g_me = 9.1093821545e-31
+g_cvel = 299792458.0
+g_h = 1.05457162853e-34
+g_a0 = 0.5291772085936
+g_Mp = 1836.1526724780 * g_me
+
+AL2O3 = {  # INPUT_CDF/Al2O3.cdf
+    "Ip": [1559.1, 89.0, 8.8, 538.0], "Nel": [2, 8, 24, 2], "auger": [1.8, 20.6, 1e23, 3.98],
+    "vb_osc": [(25.4, 275.0, 12.5), (38.0, 520.0, 38.0), (36.0, 84.0, 6.0)],
+}
+
+
+def test_cdf_and_input_parsing(case_c1):
+    t = case_c1.tables
+    assert (t.n_atoms, t.n_shells, t.vb_shell, t.nshl_atom1) == (2, 4, 2, 3)
+    assert list(t.atom_Z[:2]) == [13, 8] and list(t.atom_pers[:2]) == [2.0, 3.0]
+    assert list(t.atom_mass[:2]) == [26.9815386, 15.9992]            # Dealing_with_EADL.f90:1217-1705
+    assert np.allclose(list(t.shell_Ip[:4]), AL2O3["Ip"]) and np.allclose(list(t.shell_Nel[:4]), AL2O3["Nel"])
+    assert np.allclose(list(t.shell_auger[:4]), AL2O3["auger"])
+    assert all(r == 1e23 for r in t.shell_radiat[:4])                   # photons off => not included (Dealing_with_EADL.f90:350)
+    c = case_c1.config
+    assert (c.shi_Z, c.shi_E, c.shi_mass) == (54, 167e6, 131.293)
+    assert (c.Tim, c.dt, c.dt_flag, c.cut_off, c.layer) == (100.0, 10.0, 1, 0.0, 10.0)
+    assert c.hole_mass == -1.0e30 and c.work_function == 0.0 and c.kind_of_EMFP == 1
+    # At_Dens = 1e-3*Dens/(g_Mp*SUM(M*Pers)/SUM(Pers)), Reading_files_and_parameters.f90:1338
+    at_dens = 1.0e-3 * 3.99 / (g_Mp * (26.9815386 * 2 + 15.9992 * 3) / 5.0)
+    assert case_c1.get("At_Dens") == pytest.approx(at_dens, rel=1e-15)
+
+
+def test_gold_file_with_blank_lines_d_exponents_and_zero_gap(case_c4):
+    t = case_c4.tables
+    assert t.n_atoms == 1 and t.n_shells == 6 and t.vb_shell == 5
+    assert list(t.shell_Ip[:6]) == [80700.0, 11400.0, 2066.0, 390.0, 55.0, 0.1]   # Ip<0.1 -> 0.1, :1554
+    assert list(t.shell_Nel[:6]) == [2, 8, 18, 18, 22, 11]
+
+
+def test_dos_processing(case_c1):
+    a = case_c1.table_arrays()
+    E, D, I = a["dos_E"], a["dos_DOS"], a["dos_int"]
+    assert len(E) == case_c1.tables.n_dos and E[0] == 0.0
+    assert np.all(np.diff(E) > 0) and np.allclose(np.diff(E), 0.1, atol=1e-9)
+    assert I[-1] == pytest.approx(24.0, rel=1e-12)                     # normalised to N_VB_el
+    assert np.allclose(np.cumsum(D), I, rtol=1e-12)
+    assert a["dos_effm"][0] == 1.0                                     # E < 1e-10 => free mass, :2432-2434
+
+
+def test_energy_grids(case_c1):
+    t = case_c1.tables
+    assert (t.n_ei, t.n_ee, t.n_hi, t.n_he) == (478, 487, 92, 101)      # ~478/~487
+    g = case_c1.grid(0.1, 175.6e6 * 2.0 / 1836.0)
+    a = case_c1.table_arrays()
+    assert np.array_equal(g, a["ei_E"])
+    assert np.all(np.diff(g) >= 0)
+    for ip in AL2O3["Ip"]:                                              # two extra points around every Ip, :2921-2930
+        assert np.any(np.isclose(g, ip - 1e-3, rtol=0, atol=1e-12)) and np.any(np.isclose(g, ip + 1e-3, rtol=0, atol=1e-12))
+    assert g[0] == pytest.approx(0.1, abs=1e-12) and g[-1] >= 175.6e6 * 2.0 / 1836.0
+    # 1..10 eV in steps of 0.1, 10..100 in steps of 1
+    assert np.any(np.isclose(g, 5.5, atol=1e-9)) and np.any(np.isclose(g, 57.0, atol=1e-9))
+
+
+def loss_function(osc, hw, sqq=0.0):
+    return sum(A * G * hw / ((hw * hw - (E0 + sqq) ** 2) ** 2 + G * G * hw * hw) for E0, A, G in osc)
+
+
+def test_photon_imfp_closed_form(case_c1):
+    # Tot_Phot_IMFP, Cross_sections.f90:846-853: lambda = c*hbar/(Im(-1/eps)(E,0)*E*e)*1e10
+    for E in (10.0, 25.4, 100.0):
+        lam = g_cvel * g_h / (loss_function(AL2O3["vb_osc"], E) * E * g_e) * 1e10
+        assert case_c1.eval_photon(E, 0, 2) == pytest.approx(lam, rel=1e-13)
+    assert case_c1.eval_photon(5.0, 0, 2) == 1e30                       # below Ip
+
+
+def numpy_TotIMFP_electron(case, Ele, osc, Ip, dos_k, dos_effm):
+    """Independent restatement of TotIMFP + Diff_cross_section (Cross_sections.f90:881-1050, 2217-2282) for an
+    electron, free-electron dispersion, effective mass from the DOS, T = 0."""
+    sq_ge = math.sqrt(g_e)
+
+    def imewq(hw, q):
+        hq2 = g_h * g_h * q * q
+        qlim = abs(q) * sq_ge
+        if qlim <= dos_k[-1]:
+            j = int(np.searchsorted(dos_k, qlim, side="right"))
+            j = min(max(j, 0), len(dos_k) - 1)
+            mass = dos_effm[j]
+        else:
+            mass = 1.0
+        return loss_function(osc, hw, hq2 / (2.0 * mass * g_me))
+
+    def dcs(hw):
+        pre = math.sqrt(2.0 * g_me) / g_h
+        if hw > Ele:
+            return 0.0
+        qmin = pre * (math.sqrt(Ele) - math.sqrt(Ele - hw)); qmax = pre * (math.sqrt(Ele) + math.sqrt(Ele - hw))
+        s, hq, prev = 0.0, qmin, 0.0
+        while hq < qmax:
+            dq = hq / 100.0
+            a = imewq(hw, hq + dq / 2.0); b = imewq(hw, hq + dq)
+            s = s + dq / 6.0 * (prev + 4.0 * a + b) / hq
+            prev = b; hq = hq + dq
+        return 1.0 / (g_Pi * g_a0 * Ele) * s
+
+    Emin, Emax = Ip, (Ele + Ip) / 2.0
+    lo = max(min(e0 - 5 * g for e0, _, g in osc), Emin); hi = min(max(e0 + 5 * g for e0, _, g in osc), Emax)
+    E, tot, dedx, L0 = Emin, 0.0, 0.0, dcs(Emin)
+    while E <= Emax:
+        dE = max((hi - lo) / 100.0 if lo < E < hi else E / 100.0, 0.001)
+        a = dcs(E + dE / 2.0); b = dcs(E + dE)
+        t2 = dE / 6.0 * (L0 + 4.0 * a + b)
+        tot += t2; dedx += E * t2; L0 = b; E += dE
+    return 1.0 / tot, dedx
+
+
+def test_TotIMFP_against_independent_numpy_restatement(case_c1):
+    a = case_c1.table_arrays()
+    # recover k(E) of the DOS exactly as reading_material_DOS does (:2423-2437)
+    at_dens = case_c1.get("At_Dens")
+    k = (3.0 * 2.0 * g_Pi * g_Pi / 2.0 * np.cumsum(a["dos_DOS"]) * at_dens / 5.0 * 1e6) ** (1.0 / 3.0)
+    for Ele in (30.0, 100.0):
+        L, d = numpy_TotIMFP_electron(case_c1, Ele, AL2O3["vb_osc"], 8.8, k, a["dos_effm"])
+        Lc, dc = case_c1.eval_TotIMFP(Ele, 0, 2, 0)
+        assert Lc == pytest.approx(L, rel=1e-11), Ele
+        assert dc == pytest.approx(d, rel=1e-11), Ele
+
+
+def test_table_values_equal_single_point_evaluations(case_c1):
+    a = case_c1.table_arrays()
+    for i in (150, 250, 400):
+        for (at, sh, flat) in ((0, 2, 2), (0, 1, 1), (1, 0, 3)):
+            L, _ = case_c1.eval_TotIMFP(float(a["ei_E"][i]), at, sh, 0)
+            assert a["ei_L"][flat, i] == L
+    for i in (50, 200, 450):
+        L, _ = case_c1.eval_EMFP(float(a["ee_E"][i]), 0)
+        assert a["ee_L"][i] == L
+    assert np.all(a["ei_L"][2, a["ei_E"] < 8.8 - 1e-3] == 1e20)         # below threshold: Sigma = 1e20, :1010-1012
+
+
+def test_differential_tables_are_cumulative_and_end_at_the_total(case_c1):
+    a = case_c1.table_arrays()
+    t = case_c1.tables
+    off = a["eid_off"]
+    checked = 0
+    for flat in range(t.n_shells):
+        for iE in range(200, t.n_ei, 37):
+            o0, o1 = off[flat * t.n_ei + iE], off[flat * t.n_ei + iE + 1]
+            hw, L = a["eid_hw"][o0:o1], a["eid_L"][o0:o1]
+            assert len(hw) >= 10                                        # get_diff_CS_grid_size: max(i,10), :1341
+            filled = hw > 0
+            if filled.sum() < 2:
+                continue
+            assert np.all(np.diff(hw[filled]) > 0) and np.all(np.diff(L[filled]) <= 0)
+            assert np.all(L[~filled] == 1e15)                           # padding (0, 1e15), :1021-1026
+            if filled.all():                                            # cumulative MFP at the last point = total MFP
+                assert L[-1] == pytest.approx(a["ei_L"][flat, iE], rel=1e-12)
+                checked += 1
+    assert checked > 10
+    o = a["eed_off"]
+    for iE in range(0, t.n_ee, 23):
+        hw, L = a["eed_hw"][o[iE]:o[iE + 1]], a["eed_L"][o[iE]:o[iE + 1]]
+        f = hw > 0
+        assert np.all(np.diff(hw[f]) > 0) and np.all(L[~f] == 1e20)
+
+
+def test_sum_rules(case_c1, case_c3):
+    # k-sum ~ number of electrons in the shell, f-sum ~ 1 (Sorting_output_data.f90:286-331 prints these)
+    for case, shells in ((case_c1, [(0, 2, 24.0)]), (case_c3, [(0, 1, 4.0)])):
+        for at, sh, nel in shells:
+            ks, fs = case.sumrules(at, sh)
+            assert ks == pytest.approx(nel, rel=0.15), (ks, nel)
+            assert 0.5 < fs < 1.2, fs
+
+
+def test_single_pole_phonon_cdf_for_diamond(case_c3):
+    # Diamond.cdf has no phonon block -> get_single_pole (Cross_sections.f90:656-676)
+    assert case_c3.get("kind_of_CDF_ph") == 1
+    at_dens, vs = case_c3.get("At_Dens"), 12000.0
+    qd = (6.0 * g_Pi * g_Pi * (at_dens * 1e6)) ** 0.33333333
+    E0 = 2.0 * (g_h * vs * qd / g_e) * (g_Pi / 6.0) ** (1.0 / 3.0)
+    assert case_c3.get("phonon_E0") == pytest.approx(E0, rel=1e-14)
+    assert case_c3.get("phonon_Gamma") == pytest.approx(0.5 * E0, rel=1e-14)
+    ks, _ = case_c3.sumrules(-1, 0)
+    assert ks == pytest.approx(1.0, rel=1e-10)                          # A = N_at_mol/ksum renormalisation
+
+
+def test_ion_stopping_and_effective_charge(case_c1):
+    inv_L, dEdx, zeff = 0.0, 0.0, 0.0
+    for at, sh in ((0, 0), (0, 1), (0, 2), (1, 0)):
+        s, d, zeff = case_c1.eval_SHI(167e6, at, sh)
+        inv_L += s; dEdx += d
+    assert 2400.0 < dEdx < 2800.0                                       # Xe 167 MeV in Al2O3: S_e ~ 26 keV/nm
+    v = math.sqrt(2.0 * 167e6 * g_e / (131.293 * g_Mp))
+    assert zeff == pytest.approx(54.0 * (1.0 - math.exp(-(v * 125.0 / g_cvel / 54.0 ** 0.66666666))), rel=1e-14)   # Barkas, :2675
+
+
+def test_time_grid_and_layout(case_c1):
+    lay = case_c1.layout()
+    assert lay.Nt == 5 and list(lay.time_grid[:6]) == pytest.approx([0.01, 0.1, 1.0, 10.0, 100.0, 110.0], rel=1e-12)
+    assert lay.len[tk.TALLY_NAMES.index("Out_nh")] == 5 * 50 * 2 * 3
+    assert lay.len[tk.TALLY_NAMES.index("Out_theta")] == 6 * 180
+    assert lay.total == sum(lay.len)
+    a = case_c1.table_arrays()
+    R = a["out_R"]
+    assert list(R[:11]) == [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 15] and R[-1] == 100000.0 and len(R) == 50
+    assert a["out_V"][0] == pytest.approx(1.0 / (g_Pi * 10.0), rel=1e-15)
+
+
+def test_table_cache_round_trip(case_c1, tmp_path):
+    d = tk.make_run_dir(str(tmp_path / "run"), "C1")
+    c2 = tk.Case.load(d)
+    c2.build_tables(shi_window_only=True, cache_dir=tk._abi.REPO + "/.table_cache")       # from cache
+    a, b = case_c1.table_arrays(), c2.table_arrays()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_unsupported_inputs_are_reported_not_guessed(tmp_path):
+    d = tk.make_run_dir(str(tmp_path / "r1"), "C1", edits={11: "1   ! Brandt-Kitagawa"})
+    with pytest.raises(RuntimeError, match="Brandt-Kitagawa"):
+        tk.Case.load(d)
+    d = tk.make_run_dir(str(tmp_path / "r2"), "C1", extra_lines=("grid 0",))
+    with pytest.raises(RuntimeError, match="grid 1"):
+        tk.Case.load(d)
+    d = tk.make_run_dir(str(tmp_path / "r3"), ("NoSuchMaterial", 54, 167.0, 0, 10))
+    with pytest.raises(RuntimeError, match="not found"):
+        tk.Case.load(d)

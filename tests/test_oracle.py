@@ -1,0 +1,122 @@
+"""The CPU oracle (time-ordered restatement of Monte_Carlo.f90) and the wavefront re-formulation.
+
+No golden Monte-Carlo outputs exist in the reference (unseeded RNG, no tests), so the oracle is pinned by the
+reference's own run-time invariants, and the wavefront engine (same header as the CUDA kernels, compiled for the
+CPU in tests/emul) is required to reproduce the oracle event by event when both use the same Philox streams."""
+import numpy as np
+import pytest
+
+import trekis3_b200 as tk
+from trekis3_b200.host import split_tallies
+import emul_api
+import oracle_api
+
+CACHE = tk._abi.REPO + "/.table_cache"
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    assert oracle_api.philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert oracle_api.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert oracle_api.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def assert_same(case, to, te, so, se, rtol=1e-9):
+    assert so["events"] == se["events"]
+    assert so["n_electrons"] == se["n_electrons"] and so["n_photons"] == se["n_photons"]
+    lay = case.layout()
+    To, Te = split_tallies(lay, to), split_tallies(lay, te)
+    for k in To:
+        assert np.allclose(To[k], Te[k], rtol=rtol, atol=1e-300), k
+
+
+@pytest.mark.parametrize("rng_mode", [0, 1])
+def test_energy_is_conserved_per_iteration(case_c1, rng_mode):
+    # manual section VI: "total energy in Total_numbers.txt is conserved"; north_star: 1e-9 relative
+    _, st, totE, totN = oracle_api.run(case_c1, 0, 6, rng_mode=rng_mode)
+    assert not st["errors"]
+    # the ion (v = 156 A/fs) has left the 10 A layer long before 0.1 fs: rows 1.. must be equal
+    drift = np.abs(totE[:, 1:] - totE[:, -1:]) / totE[:, -1:]
+    assert drift.max() < 1e-9
+    assert np.all(np.diff(totN, axis=1) >= 0) and np.all(totN[:, -1] > 500)
+    # deposited energy ~ S_e * layer = 2.6 keV/A * 10 A
+    assert 15e3 < totE[:, -1].mean() < 40e3
+
+
+def test_wavefront_equals_time_ordered_loop_al2o3(case_c1):
+    to, so, eo, no = oracle_api.run(case_c1, 0, 5, rng_mode=1)
+    te, se, ee, ne = emul_api.run(case_c1, 0, 5, batch=2)
+    assert_same(case_c1, to, te, so, se)
+    assert np.array_equal(no, ne) and np.allclose(eo, ee, rtol=1e-12)
+    assert se["n_waves"] >= 3
+
+
+def test_wavefront_equals_time_ordered_loop_photons_and_radiative_decay(tmp_path):
+    d = tk.make_run_dir(str(tmp_path / "c2"), "C2")
+    case = tk.Case.load(d)
+    case.build_tables(shi_window_only=True, cache_dir=CACHE)
+    assert not case.warnings                                       # side-car radiative widths were found
+    # short radiative times (test hook) so that the photon channel is exercised by a handful of iterations
+    case.set("radiat:0:0", 1.0); case.set("radiat:0:1", 8.0); case.set("radiat:1:0", 2.0)
+    to, so, eo, no = oracle_api.run(case, 0, 4, rng_mode=1)
+    te, se, ee, ne = emul_api.run(case, 0, 4, batch=3)
+    assert so["events"]["radiative"] > 5 and so["events"]["photon"] > 5 and so["events"]["vbh_inelastic"] > 50
+    assert_same(case, to, te, so, se)
+    drift = np.abs(eo[:, 1:] - eo[:, -1:]) / eo[:, -1:]
+    assert drift.max() < 1e-9 and not so["errors"]
+
+
+def test_wavefront_equals_time_ordered_loop_diamond_hole_ionisation(case_c3):
+    to, so, eo, no = oracle_api.run(case_c3, 0, 3, rng_mode=1)
+    te, se, ee, ne = emul_api.run(case_c3, 0, 3, batch=8)
+    assert so["events"]["vbh_inelastic"] > 100
+    assert_same(case_c3, to, te, so, se)
+
+
+def test_variants_cutoff_linear_grid_emission_mott(tmp_path):
+    # cut-off 5 eV, linear time grid of 2.5 fs up to 10 fs, electron emission on
+    d = tk.make_run_dir(str(tmp_path / "v1"), "C1", edits={5: "10.0", 6: "2.5 0", 7: "5.0", 17: "4.5 10.0 6.18"})
+    case = tk.Case.load(d)
+    case.build_tables(shi_window_only=True, cache_dir=CACHE)
+    lay = case.layout()
+    assert lay.Nt == 4 and case.config.work_function == 4.5
+    to, so, eo, no = oracle_api.run(case, 0, 4, rng_mode=1)
+    te, se, ee, ne = emul_api.run(case, 0, 4, batch=4)
+    assert_same(case, to, te, so, se)
+    T = split_tallies(lay, to)
+    assert T["Out_Ne_Em"][-1] > 0 and T["Out_E_Em"][-1] > 0 and T["Out_Ee_vs_E_Em"].sum() > 0
+    # Mott elastic scattering (kind_of_EMFP = 0)
+    d = tk.make_run_dir(str(tmp_path / "v2"), "C1", edits={12: "0   1"})
+    case = tk.Case.load(d)
+    case.build_tables(shi_window_only=True, cache_dir=CACHE)
+    assert case.config.kind_of_EMFP == 0
+    to, so, eo, no = oracle_api.run(case, 0, 2, rng_mode=1)
+    te, se, ee, ne = emul_api.run(case, 0, 2, batch=2)
+    assert_same(case, to, te, so, se)
+    drift = np.abs(eo[:, 1:] - eo[:, -1:]) / eo[:, -1:]
+    assert drift.max() < 1e-9
+
+
+def test_batching_does_not_change_results(case_c1):
+    t1, s1, _, _ = emul_api.run(case_c1, 3, 9, batch=1)
+    t2, s2, _, _ = emul_api.run(case_c1, 3, 9, batch=6)
+    assert s1["events"] == s2["events"]
+    assert np.allclose(t1, t2, rtol=1e-11, atol=1e-300)
+
+
+def test_sequential_and_philox_streams_agree_statistically(case_c1):
+    # the two RNG modes are different random sequences: means must agree within 3 sigma of the batch-mean error
+    n = 24
+    _, _, e0, n0 = oracle_api.run(case_c1, 0, n, rng_mode=0)
+    _, _, e1, n1 = oracle_api.run(case_c1, 1000, 1000 + n, rng_mode=1)
+    for a, b in ((e0[:, -1], e1[:, -1]), (n0[:, -1], n1[:, -1]), (n0[:, 2], n1[:, 2])):
+        sig = np.sqrt(a.var(ddof=1) / n + b.var(ddof=1) / n)
+        assert abs(a.mean() - b.mean()) < 3.0 * sig + 1e-12
+
+
+def test_high_multiplicity_metal_runs_in_the_wavefront_engine(case_c4):
+    # U 2600 MeV in Au: >1e5 carriers per iteration (the reference's O(N^2) loop would need hours)
+    te, se, ee, ne = emul_api.run(case_c4, 0, 1, batch=1)
+    assert ne[0, -1] > 5e4 and not se["errors"]
+    assert abs(ee[0, 2] - ee[0, -1]) / ee[0, -1] < 1e-9

@@ -198,6 +198,12 @@ struct trk3_engine {
     double *d_tally = nullptr, *d_small = nullptr, *d_tally_bak = nullptr;
     unsigned long long *d_counters = nullptr, *d_counters_bak = nullptr;      // events, errors, n_el, n_ph
     int n_sm = 0, smem_optin = 0;
+    bool own_stream = true, own_tally = true;
+    int opt_profile = 0;               // 1: time every kernel class with CUDA events (bench.py roofline)
+    double class_ms[N_SPECIES + 2] = {0, 0, 0, 0, 0, 0};      // k_wave<species>, k_shi, finalize
+    uint64_t class_launches[N_SPECIES + 2] = {0, 0, 0, 0, 0, 0};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    std::vector<std::pair<int, int>> ev_pending;   // (class, pool index)
     // results
     std::vector<double> iter_totE;
     std::vector<double> Dcoef;
@@ -207,6 +213,30 @@ struct trk3_engine {
 
 namespace {
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { eng->err = std::string(#call) + ": " + cudaGetErrorString(e_); return TRK3_E_CUDA; } } while (0)
+
+// optional per-kernel-class timing: events are recorded on the launching stream around every launch
+int prof_begin(trk3_engine *eng, int cls) {
+    if (!eng->opt_profile) return -1;
+    size_t used = eng->ev_pending.size();
+    if (used >= eng->ev_pool.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return -1;
+        eng->ev_pool.push_back({a, b});
+    }
+    cudaEventRecord(eng->ev_pool[used].first, eng->stream);
+    eng->ev_pending.push_back({cls, (int)used});
+    return (int)used;
+}
+void prof_end(trk3_engine *eng, int idx) { if (idx >= 0) cudaEventRecord(eng->ev_pool[idx].second, eng->stream); }
+void prof_collect(trk3_engine *eng) {      // call after a stream synchronize
+    for (auto &pe : eng->ev_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, eng->ev_pool[pe.second].first, eng->ev_pool[pe.second].second) == cudaSuccess) {
+            eng->class_ms[pe.first] += ms; eng->class_launches[pe.first]++;
+        }
+    }
+    eng->ev_pending.clear();
+}
 
 template <class T>
 int dev_alloc(trk3_engine *eng, T **p, size_t n) {
@@ -296,7 +326,9 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t n, uint32_t *head, 
     uint32_t want = (n + TRK_BLOCK - 1) / TRK_BLOCK;
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (grid < 1) grid = 1;
+    const int pi = prof_begin(eng, SP);
     k_wave<SP><<<grid, TRK_BLOCK, smem, eng->stream>>>(qin, n, head, qout, use_smem, eng->opt_refill_min);
+    prof_end(eng, pi);
     CK(cudaGetLastError());
     eng->launches++;
     return TRK3_OK;
@@ -371,6 +403,7 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "cap_factor") { eng->opt_cap_factor = std::max(0.1, v); eng->nb_alloc = 0; }
     else if (k == "queue_gib") eng->opt_queue_bytes_max = (size_t)(v * (double)(1ull << 30));
     else if (k == "max_generations") eng->opt_max_generations = std::max(1, (int)v);
+    else if (k == "profile") { eng->opt_profile = (v != 0.0); for (auto &x : eng->class_ms) x = 0; for (auto &x : eng->class_launches) x = 0; }
     else return TRK3_E_INVALID;
     return TRK3_OK;
 }
@@ -428,7 +461,9 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         CK(cudaMemsetAsync(eng->d_u32, 0, eng->sl.u32_total * sizeof(uint32_t), eng->stream));
         CK(cudaMemsetAsync(eng->d_f64, 0, eng->sl.f64_total * sizeof(double), eng->stream));
         CK(cudaMemsetAsync(eng->d_qcount, 0, 3 * N_SPECIES * sizeof(uint32_t), eng->stream));
-        k_shi<<<(nb + 31) / 32, 32, 0, eng->stream>>>(eng->qs[0]);
+        { const int pi = prof_begin(eng, N_SPECIES);
+          k_shi<<<(nb + 31) / 32, 32, 0, eng->stream>>>(eng->qs[0]);
+          prof_end(eng, pi); }
         CK(cudaGetLastError());
         eng->launches++;
         int cur = 0;
@@ -464,10 +499,12 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             nb_max = nb_new;
             continue;                // re-run from the same b0 (histories are keyed by the global iteration index: same result)
         }
+        const int pf = prof_begin(eng, N_SPECIES + 1);
         k_iter_prefix<<<(nb + 127) / 128, 128, 0, eng->stream>>>(eng->fa);
         CK(cudaGetLastError());
         const int64_t njobs = fold_num_jobs(eng->hp);
         k_fold<<<(unsigned)((njobs + 127) / 128), 128, 0, eng->stream>>>(eng->fa, njobs);
+        prof_end(eng, pf);
         CK(cudaGetLastError());
         eng->launches += 2;
         // per-iteration results back to the host: total energies (conservation check) and the
@@ -496,6 +533,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
     CK(cudaStreamSynchronize(eng->stream));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
+    prof_collect(eng);
     trk3_stats st; std::memset(&st, 0, sizeof st);
     for (int q = 0; q < TRK3_N_EVENT_CLASSES; ++q) st.events[q] = h_c[q];
     for (int q = 0; q < TRK3_N_ERRORS; ++q) st.errors[q] = h_c[TRK3_N_EVENT_CLASSES + q];
@@ -538,13 +576,37 @@ int trk3_mc_iteration_energies(trk3_engine *eng, double *out, int64_t capacity, 
     return TRK3_OK;
 }
 
+// Use a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream) for all engine work.
+int trk3_mc_set_stream(trk3_engine *eng, void *stream) {
+    if (!eng) return TRK3_E_INVALID;
+    CK(cudaSetDevice(eng->device));
+    CK(cudaStreamSynchronize(eng->stream));
+    if (eng->own_stream && eng->stream) cudaStreamDestroy(eng->stream);
+    eng->stream = (cudaStream_t)stream; eng->own_stream = false;
+    return TRK3_OK;
+}
+// Accumulate into a caller-owned DEVICE buffer of lay.total doubles (e.g. a torch tensor that is then all-reduced).
+int trk3_mc_set_device_tallies(trk3_engine *eng, double *dptr) {
+    if (!eng || !dptr) return TRK3_E_INVALID;
+    eng->d_tally = dptr; eng->own_tally = false; eng->hp.tally = dptr;
+    return TRK3_OK;
+}
+// Per-kernel-class device time of the runs since option "profile" was set: classes are
+// 0 electron wave, 1 valence-hole wave, 2 core-hole wave, 3 photon wave, 4 ion tracks, 5 finalize.
+int trk3_mc_kernel_times(trk3_engine *eng, double *ms, uint64_t *launches, int n) {
+    if (!eng || !ms || !launches) return TRK3_E_INVALID;
+    for (int i = 0; i < n && i < N_SPECIES + 2; ++i) { ms[i] = eng->class_ms[i]; launches[i] = eng->class_launches[i]; }
+    return N_SPECIES + 2;
+}
+
 void trk3_mc_destroy(trk3_engine *eng) {
     if (!eng) return;
     cudaSetDevice(eng->device);
     for (void *p : eng->allocs) cudaFree(p);
     if (eng->ev0) cudaEventDestroy(eng->ev0);
     if (eng->ev1) cudaEventDestroy(eng->ev1);
-    if (eng->stream) cudaStreamDestroy(eng->stream);
+    for (auto &e : eng->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (eng->own_stream && eng->stream) cudaStreamDestroy(eng->stream);
     delete eng;
 }
 

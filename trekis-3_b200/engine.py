@@ -34,6 +34,9 @@ def _gpu():
         lib.trk3_mc_last_error.restype = C.c_char_p
         lib.trk3_mc_last_error.argtypes = [C.c_void_p]
         lib.trk3_mc_destroy.argtypes = [C.c_void_p]
+        lib.trk3_mc_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        lib.trk3_mc_set_device_tallies.argtypes = [C.c_void_p, C.c_void_p]
+        lib.trk3_mc_kernel_times.argtypes = [C.c_void_p, PD, C.POINTER(C.c_uint64), C.c_int]
         lib.trk3_gpu_version.restype = C.c_char_p
         _lib = lib
     return _lib
@@ -86,6 +89,21 @@ class Engine:
         st = Stats()
         self._check(_gpu().trk3_mc_run_device(self._h, int(it_begin), int(it_end), C.byref(st)), "trk3_mc_run_device")
         return st.as_dict()
+
+    def set_stream(self, cuda_stream_handle):
+        self._check(_gpu().trk3_mc_set_stream(self._h, C.c_void_p(int(cuda_stream_handle))), "set_stream")
+
+    def set_device_tallies(self, device_ptr):
+        """Accumulate into a caller-owned device buffer (layout.total float64), e.g. tensor.data_ptr()."""
+        self._check(_gpu().trk3_mc_set_device_tallies(self._h, C.c_void_p(int(device_ptr))), "set_device_tallies")
+
+    KERNEL_CLASSES = ("k_wave<electron>", "k_wave<vbhole>", "k_wave<corehole>", "k_wave<photon>", "k_shi", "finalize")
+
+    def kernel_times(self):
+        ms = (C.c_double * 6)()
+        n = (C.c_uint64 * 6)()
+        _gpu().trk3_mc_kernel_times(self._h, ms, n, 6)
+        return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(self.KERNEL_CLASSES)}
 
     def device_tallies_ptr(self):
         return _gpu().trk3_mc_device_tallies(self._h)
