@@ -35,7 +35,9 @@ if n_cmp > 0:
         rel = np.abs(a - b) / den
         print("%-16s max rel %.3e  median rel %.3e  sum o=%.8e g=%.8e" % (k, rel.max(), np.median(rel[den > 0]), a.sum(), b.sum()))
 if n_time > 0:
+    eng.set_option("profile", 1)
     for rep in range(3):
         t = time.time(); st = eng.run_device(0, n_time); dt = time.time() - t
         print("time: %d its wall %.4fs dev %.3f ms -> %.1f it/s, %.3e events/s, waves %d launches %d drift %.2e errors %s" % (
             n_time, dt, st["device_ms"], n_time / (st["device_ms"] * 1e-3), st["total_events"] / (st["device_ms"] * 1e-3), st["n_waves"], st["kernel_launches"], st["max_energy_drift"], st["errors"]))
+    print("kernel ms (3 reps):", {k: round(v["ms"], 2) for k, v in eng.kernel_times().items()})

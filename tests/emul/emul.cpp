@@ -47,6 +47,15 @@ extern "C" int trk3_emul_run(const trk3_config *cfg, const trk3_tables *tab, int
     p.eid_off = tab->eid_off; p.eid_hw = tab->eid_hw; p.eid_L = tab->eid_L; p.eed_off = tab->eed_off; p.eed_hw = tab->eed_hw; p.eed_L = tab->eed_L;
     p.hid_off = tab->hid_off; p.hid_hw = tab->hid_hw; p.hid_L = tab->hid_L; p.hed_off = tab->hed_off; p.hed_hw = tab->hed_hw; p.hed_L = tab->hed_L;
     p.dos_E = tab->dos_E; p.dos_DOS = tab->dos_DOS; p.dos_int = tab->dos_int; p.dos_effm = tab->dos_effm; p.out_R = tab->out_R; p.out_V = tab->out_V;
+    // companions of the tables (logs, reciprocals) and the cold ranges, as engine.cu prepares them on the device
+    std::vector<std::vector<double>> comp;
+    const size_t NS = tab->n_shells;
+    const trk3_tables &T = *tab;
+#define X(dst, src, n, op) { comp.emplace_back((size_t)(n)); std::vector<double> &v = comp.back(); for (size_t i = 0; i < v.size(); ++i) v[i] = companion_value((src)[i], op); p.dst = v.data(); }
+    TRK3_COMPANIONS(X, p, T, NS)
+#undef X
+    cold_range(p.ei_E, p.ei_tot, p.n_ei, p.e_cold, p.e_imfp_cold);
+    cold_range(p.hi_E, p.hi_tot, p.n_hi, p.h_cold, p.h_imfp_cold);
     p.tally = tallies;
     unsigned long long ev[TRK3_N_EVENT_CLASSES] = {0}, er[TRK3_N_ERRORS] = {0}, nel = 0, nph = 0;
     uint64_t waves = 0;
@@ -68,8 +77,8 @@ extern "C" int trk3_emul_run(const trk3_config *cfg, const trk3_tables *tab, int
             for (int s = 0; s < N_SPECIES; ++s) { cur[s].swap(nxt[s]); nxt[s].clear(); n += cur[s].size(); }
             if (!n) break;
             ++waves;
-            for (Rec r : cur[SP_ELECTRON]) { int ig; begin_electron(c, r, ig); while (step_electron(c, r, ig)) {} }
-            for (Rec r : cur[SP_VBHOLE]) { int ig = interval_of(p, r.t0); while (step_vbhole(c, r, ig)) {} }
+            for (Rec r : cur[SP_ELECTRON]) { int ig; Cache k{}; begin_electron(c, r, ig, k); while (step_electron(c, r, ig, k)) {} }
+            for (Rec r : cur[SP_VBHOLE]) { int ig; Cache k{}; begin_vbhole(p, r, ig, k); while (step_vbhole(c, r, ig, k)) {} }
             for (Rec r : cur[SP_COREHOLE]) { int ig = interval_of(p, r.t0); while (step_corehole(c, r, ig)) {} }
             for (Rec r : cur[SP_PHOTON]) { int ig = interval_of(p, r.t0); while (step_photon(c, r, ig)) {} }
         }

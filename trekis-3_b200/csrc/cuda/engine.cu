@@ -28,7 +28,10 @@ __constant__ DevP c_p;
 
 struct QueueSet { Queue q[N_SPECIES]; };
 
-#define TRK_BLOCK 128
+#define TRK_BLOCK_MAX 256          // compile-time upper bound of the wave-kernel block size (launch bounds)
+#ifndef TRK_MIN_BLOCKS
+#define TRK_MIN_BLOCKS 3
+#endif
 #define S_EV 0                      // s_cnt layout: events[TRK3_N_EVENT_CLASSES], n_el, n_ph
 #define S_NEL TRK3_N_EVENT_CLASSES
 #define S_NPH (TRK3_N_EVENT_CLASSES + 1)
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(32) k_shi(QueueSet qout) {
 
 // k_wave<SP>: one generation of species SP, histories run to completion with lane refill.
 template <int SP>
-__global__ void __launch_bounds__(TRK_BLOCK) k_wave(Queue qin, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(TRK_BLOCK) k_wave(Queue qin, uint32_t n_in, ui
     const int lane = threadIdx.x & 31;
     bool active = false, exhausted = false;
     Rec r;
+    Cache k{};
     int ig = 0;
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
@@ -142,7 +146,8 @@ __global__ void __launch_bounds__(TRK_BLOCK) k_wave(Queue qin, uint32_t n_in, ui
                 if (my < n_in) {
                     load_rec(qin, my, r);
                     active = true;
-                    if (SP == SP_ELECTRON) begin_electron(c, r, ig);
+                    if (SP == SP_ELECTRON) begin_electron(c, r, ig, k);
+                    else if (SP == SP_VBHOLE) begin_vbhole(c_p, r, ig, k);
                     else ig = interval_of(c_p, r.t0);
                 }
             }
@@ -150,8 +155,8 @@ __global__ void __launch_bounds__(TRK_BLOCK) k_wave(Queue qin, uint32_t n_in, ui
         if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; continue; }
         if (active) {
             bool cont;
-            if (SP == SP_ELECTRON) cont = step_electron(c, r, ig);
-            else if (SP == SP_VBHOLE) cont = step_vbhole(c, r, ig);
+            if (SP == SP_ELECTRON) cont = step_electron(c, r, ig, k);
+            else if (SP == SP_VBHOLE) cont = step_vbhole(c, r, ig, k);
             else if (SP == SP_COREHOLE) cont = step_corehole(c, r, ig);
             else cont = step_photon(c, r, ig);
             if (!cont) active = false;
@@ -167,6 +172,11 @@ __global__ void k_iter_prefix(FoldAux a) {
 __global__ void k_fold(FoldAux a, int64_t njobs) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < njobs) fold_job(c_p, a, j);
+}
+// companion arrays of the tables (TRK3_COMPANIONS): evaluated on the device so that they carry the device's log()
+__global__ void k_companion(double *dst, const double *src, size_t n, int op) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = companion_value(src[i], op);
 }
 __global__ void k_axpy(double *dst, const double *src, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,7 +196,7 @@ struct trk3_engine {
     std::vector<void *> allocs;
     double nel_est = 1000.0;
     // options
-    int opt_batch = 512, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 4096;
+    int opt_batch = 1024, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 4096, opt_block = 256;
     double opt_cap_factor = 2.0;
     size_t opt_queue_bytes_max = (size_t)24 << 30;
     // per-batch resources
@@ -321,13 +331,14 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t n, uint32_t *head, 
     if (smem > smem_max) { smem = 8; use_smem = 0; }                    // too many output times for shared memory: global atomics
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_wave<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = eng->opt_blocks_per_sm;
-    if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_wave<SP>, TRK_BLOCK, smem)); if (bps < 1) bps = 1; }
+    const int block = eng->opt_block;
+    if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_wave<SP>, block, smem)); if (bps < 1) bps = 1; }
     // persistent-style grid: a multiple of the SM count, never more blocks than there is work for
-    uint32_t want = (n + TRK_BLOCK - 1) / TRK_BLOCK;
+    uint32_t want = (n + block - 1) / block;
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (grid < 1) grid = 1;
     const int pi = prof_begin(eng, SP);
-    k_wave<SP><<<grid, TRK_BLOCK, smem, eng->stream>>>(qin, n, head, qout, use_smem, eng->opt_refill_min);
+    k_wave<SP><<<grid, block, smem, eng->stream>>>(qin, n, head, qout, use_smem, eng->opt_refill_min);
     prof_end(eng, pi);
     CK(cudaGetLastError());
     eng->launches++;
@@ -379,6 +390,17 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
     UP(dos_E, tab->dos_E, tab->n_dos); UP(dos_DOS, tab->dos_DOS, tab->n_dos); UP(dos_int, tab->dos_int, tab->n_dos); UP(dos_effm, tab->dos_effm, tab->n_dos);
     UP(out_R, tab->out_R, tab->n_r); UP(out_V, tab->out_V, tab->n_r);
 #undef UP
+    {   // log / reciprocal companions (one exp() per log-log interpolation instead of five log() + exp())
+        const trk3_tables &T = *tab;
+#define X(dst, src, n, op) { double *d_ = nullptr; const size_t n_ = (size_t)(n); if ((rc = dev_alloc(eng, &d_, n_))) return rc; \
+        if (n_) k_companion<<<(unsigned)((n_ + 255) / 256), 256, 0, eng->stream>>>(d_, src, n_, op); p.dst = d_; }
+        TRK3_COMPANIONS(X, p, T, NS)
+#undef X
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(eng->stream));
+        cold_range(tab->ei_E, tot.ei_tot.data(), tab->n_ei, p.e_cold, p.e_imfp_cold);
+        cold_range(tab->hi_E, tot.hi_tot.data(), tab->n_hi, p.h_cold, p.h_imfp_cold);
+    }
     if ((rc = dev_alloc(eng, &eng->d_tally, (size_t)eng->lay.total))) return rc;
     CK(cudaMemset(eng->d_tally, 0, (size_t)eng->lay.total * sizeof(double)));
     if ((rc = dev_alloc(eng, &eng->d_tally_bak, (size_t)eng->lay.total))) return rc;
@@ -402,6 +424,7 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "blocks_per_sm") eng->opt_blocks_per_sm = (int)v;
     else if (k == "cap_factor") { eng->opt_cap_factor = std::max(0.1, v); eng->nb_alloc = 0; }
     else if (k == "queue_gib") eng->opt_queue_bytes_max = (size_t)(v * (double)(1ull << 30));
+    else if (k == "block") eng->opt_block = std::min(TRK_BLOCK_MAX, std::max(32, ((int)v / 32) * 32));
     else if (k == "max_generations") eng->opt_max_generations = std::max(1, (int)v);
     else if (k == "profile") { eng->opt_profile = (v != 0.0); for (auto &x : eng->class_ms) x = 0; for (auto &x : eng->class_launches) x = 0; }
     else return TRK3_E_INVALID;

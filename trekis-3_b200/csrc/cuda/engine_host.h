@@ -28,6 +28,36 @@ inline void compute_totals(const trk3_tables &T, HostTotals &h) {
     for (auto &v : h.ph_tot) v = (v < 1.0e-10) ? 1.0e30 : 1.0 / v;
 }
 
+// The "cold" range of a total inelastic MFP table: the leading run of identical entries >= 1e16 (energies below the
+// lowest ionisation threshold).  For E < E[m] (m = last index of the run, m >= 1) Next_free_path returns exactly that
+// constant whatever the search path, so the kernels skip the lookup.  Returns false if there is no such run.
+inline bool cold_range(const double *E, const double *L, int N, double &e_cold, double &l_cold) {
+    e_cold = -1.0e300; l_cold = 0.0;
+    if (N < 2 || !(L[0] >= 1.0e16) || std::fabs(E[1] - E[0]) < 1.0e-6) return false;
+    int m = 0;
+    while (m + 1 < N && L[m + 1] == L[0]) ++m;
+    if (m < 1) return false;
+    e_cold = E[m]; l_cold = L[0];
+    return true;
+}
+
+// Companion arrays of the tables (natural logarithms, reciprocals): X(dst, src, n, op) with op 0 = log(src),
+// 1 = 1/src, 2 = log(1/src).  The CUDA engine evaluates them on the device, the emulation on the host.
+#define TRK3_COMPANIONS(X, p, T, NS)                                                                              \
+    X(lei_E, p.ei_E, T.n_ei, 0) X(lei_L, p.ei_L, (NS) * T.n_ei, 0) X(lei_tot, p.ei_tot, T.n_ei, 0)                  \
+    X(lee_E, p.ee_E, T.n_ee, 0) X(lee_L, p.ee_L, T.n_ee, 0)                                                        \
+    X(lhi_E, p.hi_E, T.n_hi, 0) X(lhi_L, p.hi_L, (NS) * T.n_hi, 0) X(lhi_tot, p.hi_tot, T.n_hi, 0)                  \
+    X(lhe_E, p.he_E, T.n_he, 0) X(lhe_L, p.he_L, T.n_he, 0)                                                        \
+    X(lph_E, p.ph_E, T.n_ph, 0) X(lph_L, p.ph_L, (NS) * T.n_ph, 0) X(lph_tot, p.ph_tot, T.n_ph, 0)                  \
+    X(lshi_E, p.shi_E, T.n_shi, 0) X(lshi_L, p.shi_L, (NS) * T.n_shi, 0) X(lshi_tot, p.shi_tot, T.n_shi, 0)         \
+    X(ldshi_E, p.dshi_E, T.dshi_off[NS], 0) X(dshi_iL, p.dshi_L, T.dshi_off[NS], 1) X(ldshi_iL, p.dshi_L, T.dshi_off[NS], 2) \
+    X(leid_hw, p.eid_hw, T.eid_off[(NS) * T.n_ei], 0) X(leid_L, p.eid_L, T.eid_off[(NS) * T.n_ei], 0)               \
+    X(leed_hw, p.eed_hw, T.eed_off[T.n_ee], 0) X(leed_L, p.eed_L, T.eed_off[T.n_ee], 0)                            \
+    X(lhid_hw, p.hid_hw, T.hid_off[T.n_hi], 0) X(lhid_L, p.hid_L, T.hid_off[T.n_hi], 0)                            \
+    X(lhed_hw, p.hed_hw, T.hed_off[T.n_he], 0) X(lhed_L, p.hed_L, T.hed_off[T.n_he], 0)
+
+TRK_HD double companion_value(double x, int op) { return op == 0 ? log(x) : (op == 1 ? 1.0 / x : log(1.0 / x)); }
+
 // Equilibrium_charge_SHI for the incoming ion (MAIN.f90:171)
 inline double host_shi_zeff(const trk3_config &c, const trk3_tables &T) {
     const double g_e = 1.602176487e-19, g_me = 9.1093821545e-31, g_Mp = 1836.1526724780 * g_me, g_cvel = 299792458.0, g_Ry = 13.6056981;

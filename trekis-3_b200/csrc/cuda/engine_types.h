@@ -76,13 +76,21 @@ struct DevP {
     double atom_mass[TRK3_MAX_ATOMS], atom_pers[TRK3_MAX_ATOMS];
     int32_t shell_atom[TRK3_MAX_SHELLS], shell_num[TRK3_MAX_SHELLS];
     double shell_Ip[TRK3_MAX_SHELLS], shell_Nel[TRK3_MAX_SHELLS], shell_auger[TRK3_MAX_SHELLS], shell_radiat[TRK3_MAX_SHELLS];
-    // ---- tables (device pointers)
+    // ---- tables (device pointers).  Every table has a companion of natural logarithms (prefix l) computed once
+    //      at upload with the same log() the kernels use, so that the log-log interpolation of the reference
+    //      (Interpolate(5,...), Cross_sections.f90:4074-4081) costs one exp() instead of five log() + exp().
     int32_t n_ei, n_ee, n_hi, n_he, n_ph, n_shi, n_dos, n_r;
     const double *ei_E, *ei_L, *ei_tot, *ee_E, *ee_L, *hi_E, *hi_L, *hi_tot, *he_E, *he_L, *ph_E, *ph_L, *ph_tot;
     const double *shi_E, *shi_L, *shi_tot;
+    const double *lei_E, *lei_L, *lei_tot, *lee_E, *lee_L, *lhi_E, *lhi_L, *lhi_tot, *lhe_E, *lhe_L, *lph_E, *lph_L, *lph_tot;
+    const double *lshi_E, *lshi_L, *lshi_tot;
     const int64_t *dshi_off, *eid_off, *eed_off, *hid_off, *hed_off;
     const double *dshi_E, *dshi_L, *eid_hw, *eid_L, *eed_hw, *eed_L, *hid_hw, *hid_L, *hed_hw, *hed_L;
+    const double *ldshi_E, *dshi_iL, *ldshi_iL;          // log(E), 1/L and log(1/L) of the SHI cumulative tables
+    const double *leid_hw, *leid_L, *leed_hw, *leed_L, *lhid_hw, *lhid_L, *lhed_hw, *lhed_L;
     const double *dos_E, *dos_DOS, *dos_int, *dos_effm, *out_R, *out_V;
+    // below these energies the total inelastic MFP is one constant >= 1e16 (no ionisation possible): lookup skipped
+    double e_cold, e_imfp_cold, h_cold, h_imfp_cold;
     // ---- time grid: tg[i-1] = min(time_grid(i), Tim), i = 1..Nt
     int32_t Nt;
     double tg[TRK3_MAX_NT];

@@ -121,38 +121,90 @@ TRK_HD double interp5(double E1, double E2, double S1, double S2, double En) {
     double E2l = log(E2), E1l = log(E1), El = log(En), S1l = log(S1), S2l = log(S2);
     return exp(S1l + (S2l - S1l) / (E2l - E1l) * (El - E1l));
 }
+// same with the logarithms of the table entries precomputed (identical arithmetic, identical result)
+TRK_HD double interp5t(double E1, double E2, double S1, double S2, double lE1, double lE2, double lS1, double lS2, double En, double lEn) {
+    if (fabs(E2 - E1) < 1.0e-6) return (S1 > S2) ? S1 : S2;
+    if (En == E1) return S1;
+    return exp(lS1 + (lS2 - lS1) / (lE2 - lE1) * (lEn - lE1));
+}
 TRK_HD double interp1(double E1, double E2, double S1, double S2, double En) {
     if (fabs(E2 - E1) < 1.0e-6) return (S1 > S2) ? S1 : S2;
     if (En == E1) return S1;
     return S1 + (S2 - S1) / (E2 - E1) * (En - E1);
 }
 
-// Next_free_path_1d / _2d, Monte_Carlo.f90:1835-1899
-TRK_HD double nfp_1d(double E, const double *Ea, const double *La, int N) {
-    int n = find_1d(Ea, N, E);
-    if (n == 1) {
-        double MFP = interp1(Ea[0], Ea[1], La[0], La[1], E);
-        if (MFP < Ea[0]) MFP = Ea[0];           // sic (:1854): clamped against the energy array
-        return MFP;
-    }
-    double Ll = La[n - 2];
-    if (Ll >= 1.0e16) return Ll;
-    return interp5(Ea[n - 2], Ea[n - 1], Ll, La[n - 1], E);
+// A 1-D mean-free-path table with its log companion
+struct Tab { const double *E, *L, *lE, *lL; int N; };
+
+// Find_in_monotonous_2D_array gives the same index as the 1D variant unless the value sits exactly on the lower
+// bracketing grid point, where the result depends on the bisection path: only then is the 2D search really run.
+TRK_HD int find_2d_from_1d(const double *A, int N, double v, int n1) {
+    if (n1 > 1 && v == A[n1 - 2]) return find_2d(A, N, v);
+    return n1;
 }
-TRK_HD double nfp_2d(double E, const double *Ea, const double *La, int N) {
-    int n = find_2d(Ea, N, E);
+// Next_free_path_1d / _2d, Monte_Carlo.f90:1835-1899, for a known search index n
+TRK_HD double nfp_at(const Tab &t, int n, bool two_d, double E, double lE) {
     if (n == 1) {
-        double MFP = interp1(Ea[0], Ea[1], La[0], La[1], E);
-        if (MFP < La[0]) MFP = La[0];
+        double MFP = interp1(t.E[0], t.E[1], t.L[0], t.L[1], E);
+        const double lo = two_d ? t.L[0] : t.E[0];      // sic (:1854 vs :1888): the 1d variant clamps against the energy array
+        if (MFP < lo) MFP = lo;
         return MFP;
     }
-    double Ll = La[n - 2];
+    const double Ll = t.L[n - 2];
     if (Ll >= 1.0e16) return Ll;
-    return interp5(Ea[n - 2], Ea[n - 1], Ll, La[n - 1], E);
+    return interp5t(t.E[n - 2], t.E[n - 1], Ll, t.L[n - 1], t.lE[n - 2], t.lE[n - 1], t.lL[n - 2], t.lL[n - 1], E, lE);
+}
+TRK_HD double nfp_1d(const Tab &t, double E, double lE) { return nfp_at(t, find_1d(t.E, t.N, E), false, E, lE); }
+TRK_HD double nfp_2d(const Tab &t, double E, double lE) { return nfp_at(t, find_2d(t.E, t.N, E), true, E, lE); }
+
+TRK_HD Tab tab_ei_tot(const DevP &p) { return Tab{p.ei_E, p.ei_tot, p.lei_E, p.lei_tot, p.n_ei}; }
+TRK_HD Tab tab_ee(const DevP &p) { return Tab{p.ee_E, p.ee_L, p.lee_E, p.lee_L, p.n_ee}; }
+TRK_HD Tab tab_hi_tot(const DevP &p) { return Tab{p.hi_E, p.hi_tot, p.lhi_E, p.lhi_tot, p.n_hi}; }
+TRK_HD Tab tab_he(const DevP &p) { return Tab{p.he_E, p.he_L, p.lhe_E, p.lhe_L, p.n_he}; }
+TRK_HD Tab tab_ph_tot(const DevP &p) { return Tab{p.ph_E, p.ph_tot, p.lph_E, p.lph_tot, p.n_ph}; }
+TRK_HD Tab tab_shi_tot(const DevP &p) { return Tab{p.shi_E, p.shi_tot, p.lshi_E, p.lshi_tot, p.n_shi}; }
+TRK_HD Tab tab_shell(const double *E, const double *lE, const double *Lmat, const double *lLmat, int N, int shell) {
+    return Tab{E, Lmat + (size_t)shell * N, lE, lLmat + (size_t)shell * N, N};
 }
 
+// total inelastic / elastic MFP of an electron (El_IMFP, El_EMFP of How_many_electrons, both searched with the 2D routine)
+TRK_HD double electron_imfp(const DevP &p, double E, double lE) {
+    if (E < p.e_cold) return p.e_imfp_cold;            // below the lowest threshold the table is one constant >= 1e16
+    return nfp_2d(tab_ei_tot(p), E, lE);
+}
+TRK_HD double hole_imfp(const DevP &p, double E, double lE) {
+    if (E < p.h_cold) return p.h_imfp_cold;
+    return nfp_2d(tab_hi_tot(p), E, lE);
+}
+
+// Lookups of a particle's current energy that the next collision needs again: carried in registers between events
+// (the reference recomputes them at the start of every event: Monte_Carlo.f90:2298-2299 == :2449-2450 of the previous one)
+struct Cache {
+    double lE;      // log(E)
+    double emfp;    // elastic MFP from the 2D-searched table (El_EMFP / Hole_EMFP)
+    double imfp;    // total inelastic MFP (El_IMFP / Hole_IMFP)
+    int n1, n2;     // 1D / 2D search indices of E in the elastic grid
+};
+TRK_HD void cache_fill(const Tab &el, double E, Cache &k) {
+    k.lE = log(E);
+    k.n1 = find_1d(el.E, el.N, E);
+    k.n2 = find_2d_from_1d(el.E, el.N, E, k.n1);
+    k.emfp = nfp_at(el, k.n2, true, E, k.lE);
+    k.imfp = 0.0;
+}
+// Elastic_MFP%Total searched with the 1D routine (:2385, :2664): same table as El_EMFP, so the value is shared
+// whenever both searches agree and the energy is inside the grid
+TRK_HD double elastic_total(const Tab &el, double E, const Cache &k) {
+    if (k.n1 > 1 && k.n1 == k.n2) return k.emfp;
+    return nfp_at(el, k.n1, false, E, k.lE);
+}
+
+// all lookups of an electron / valence hole of kinetic energy E (what :2298-2299 / :2579-2580 evaluate at the start of an event)
+TRK_HD void cache_electron(const DevP &p, double E, Cache &k) { cache_fill(tab_ee(p), E, k); k.imfp = electron_imfp(p, E, k.lE); }
+TRK_HD void cache_vbhole(const DevP &p, double E, Cache &k) { cache_fill(tab_he(p), E, k); k.imfp = hole_imfp(p, E, k.lE); }
+
 // Which_shell, Monte_Carlo.f90:1786-1832: shell roulette on 1/lambda_shell(E); returns the flat shell
-TRK_HD int which_shell(const DevP &p, Rec &r, const double *Ea, const double *Lmat, int N, double E) {
+TRK_HD int which_shell(const DevP &p, Rec &r, const double *Ea, const double *lEa, const double *Lmat, const double *lLmat, int N, double E, double lE) {
     double Temp[TRK3_MAX_SHELLS];
     double MFP_tot = 0.0;
     const int n = find_1d(Ea, N, E);            // all shells share the grid (MAIN.f90:234-236)
@@ -163,7 +215,7 @@ TRK_HD int which_shell(const DevP &p, Rec &r, const double *Ea, const double *Lm
         else {
             double a = La[n - 2], b = La[n - 1];
             if (a == b || a > 1e20) MFP = a;
-            else MFP = interp5(Ea[n - 2], Ea[n - 1], a, b, E);
+            else { const double *lLa = lLmat + (size_t)s * N; MFP = interp5t(Ea[n - 2], Ea[n - 1], a, b, lEa[n - 2], lEa[n - 1], lLa[n - 2], lLa[n - 1], E, lE); }
         }
         Temp[s] = 1.0 / MFP;
         MFP_tot = MFP_tot + Temp[s];
@@ -196,30 +248,38 @@ TRK_HD int interval_of(const DevP &p, double t) {
     return i;
 }
 
-// interpolate_transferred_energy, Cross_sections.f90:1968-2045, on a CSR differential table
-TRK_HD double sample_row(const double *hw, const double *L, int n, double L_need) {
+// interpolate_transferred_energy, Cross_sections.f90:1968-2045, on a CSR differential table with log companions.
+// i_E is the 1D search index of Ele in the table's energy grid (shared with the MFP lookup: same grid).
+struct Csr { const double *Eg, *lEg; int NE; const int64_t *off; const double *hw, *L, *lhw, *lL; };
+TRK_HD double sample_row(const Csr &t, int64_t o, int n, double L_need, double lLn) {
+    const double *L = t.L + o, *hw = t.hw + o;
     int i_hw = find_dec(L, n, L_need);
     if (i_hw == 1 || i_hw == n) return hw[i_hw - 1];
-    return interp5(L[i_hw - 1], L[i_hw], hw[i_hw - 1], hw[i_hw], L_need);
+    const double *lL = t.lL + o, *lhw = t.lhw + o;
+    return interp5t(L[i_hw - 1], L[i_hw], hw[i_hw - 1], hw[i_hw], lL[i_hw - 1], lL[i_hw], lhw[i_hw - 1], lhw[i_hw], L_need, lLn);
 }
-TRK_HD double transferred_energy(double Ele, const double *Eg, int NE, const int64_t *off, const double *hwA, const double *LA, double L_need) {
-    int i_E = find_1d(Eg, NE, Ele);
-    if (i_E > 1) { if (fabs(Eg[i_E - 2] - Ele) < 1.0e-6) i_E = i_E - 1; }
-    int64_t o = off[i_E - 1];
-    double hw_1 = sample_row(hwA + o, LA + o, (int)(off[i_E] - o), L_need);
+TRK_HD double transferred_energy(const Csr &t, double Ele, double lE, int i_E, double L_need) {
+    if (i_E > 1) { if (fabs(t.Eg[i_E - 2] - Ele) < 1.0e-6) i_E = i_E - 1; }
+    const double lLn = log(L_need);
+    int64_t o = t.off[i_E - 1];
+    double hw_1 = sample_row(t, o, (int)(t.off[i_E] - o), L_need, lLn);
     if (i_E <= 1) return hw_1;
     i_E = i_E - 1;
-    o = off[i_E - 1];
-    double hw_2 = sample_row(hwA + o, LA + o, (int)(off[i_E] - o), L_need);
-    if (hw_1 < 1.0e-10 || hw_2 < 1.0e-10) return interp1(Eg[i_E - 1], Eg[i_E], hw_1, hw_2, Ele);
-    return interp5(Eg[i_E - 1], Eg[i_E], hw_1, hw_2, Ele);
+    o = t.off[i_E - 1];
+    double hw_2 = sample_row(t, o, (int)(t.off[i_E] - o), L_need, lLn);
+    if (hw_1 < 1.0e-10 || hw_2 < 1.0e-10) return interp1(t.Eg[i_E - 1], t.Eg[i_E], hw_1, hw_2, Ele);
+    return interp5t(t.Eg[i_E - 1], t.Eg[i_E], hw_1, hw_2, t.lEg[i_E - 1], t.lEg[i_E], log(hw_1), log(hw_2), Ele, lE);
 }
+TRK_HD Csr csr_eid(const DevP &p, int shell) { return Csr{p.ei_E, p.lei_E, p.n_ei, p.eid_off + (size_t)shell * p.n_ei, p.eid_hw, p.eid_L, p.leid_hw, p.leid_L}; }
+TRK_HD Csr csr_eed(const DevP &p) { return Csr{p.ee_E, p.lee_E, p.n_ee, p.eed_off, p.eed_hw, p.eed_L, p.leed_hw, p.leed_L}; }
+TRK_HD Csr csr_hid(const DevP &p) { return Csr{p.hi_E, p.lhi_E, p.n_hi, p.hid_off, p.hid_hw, p.hid_L, p.lhid_hw, p.lhid_L}; }
+TRK_HD Csr csr_hed(const DevP &p) { return Csr{p.he_E, p.lhe_E, p.n_he, p.hed_off, p.hed_hw, p.hed_L, p.lhed_hw, p.lhed_L}; }
 
 // effective hole mass from the DOS, e.g. Cross_sections.f90:1820-1825
 TRK_HD double hole_mass_dos(const DevP &p, double E) { int m = find_1d(p.dos_E, p.n_dos, E); return p.dos_effm[m - 1]; }
 
 // Electron_energy_transfer_inelastic (CS_method = 1), Cross_sections.f90:1793-1871
-TRK_HD double inelastic_dE(const DevP &p, Rec &r, double Ele, int shell, double L_tot, bool hole) {
+TRK_HD double inelastic_dE(const DevP &p, Rec &r, double Ele, double lE, int shell, double L_tot, bool hole) {
     double RN = rn(p, r);
     double L_need = L_tot / RN;
     double Emin = p.shell_Ip[shell];
@@ -227,11 +287,11 @@ TRK_HD double inelastic_dE(const DevP &p, Rec &r, double Ele, int shell, double 
     double Emax, E;
     if (!hole) {
         Emax = (Ele + Emin) / 2.0;
-        E = transferred_energy(Ele, p.ei_E, p.n_ei, p.eid_off + (size_t)shell * p.n_ei, p.eid_hw, p.eid_L, L_need);
+        E = transferred_energy(csr_eid(p, shell), Ele, lE, find_1d(p.ei_E, p.n_ei, Ele), L_need);
     } else {
         double Mass = (p.hole_mass >= 0) ? p.hole_mass : hole_mass_dos(p, Ele);
         Emax = 4.0 * Ele * Mass / ((Mass + 1.0) * (Mass + 1.0));
-        E = transferred_energy(Ele, p.hi_E, p.n_hi, p.hid_off, p.hid_hw, p.hid_L, L_need);
+        E = transferred_energy(csr_hid(p), Ele, lE, find_1d(p.hi_E, p.n_hi, Ele), L_need);
     }
     if (E < Emin) E = Emin;
     if (E > Emax) E = Emax;
@@ -265,12 +325,11 @@ TRK_HD double mott_dE(const DevP &p, Rec &r, double Mat, double Zat, double Ee, 
     return W1 * W2;
 }
 // elastic energy transfer: the kind_of_EMFP switch of Monte_Carlo.f90:2387-2407 / :2668-2692
-TRK_HD double elastic_dE(const DevP &p, Rec &r, double Eel, double EMFP, bool hole, double M_eff) {
+TRK_HD double elastic_dE(const DevP &p, Rec &r, double Eel, const Cache &k, double EMFP, bool hole, double M_eff) {
     if (p.kind_of_EMFP == 1) {      // Electron_energy_transfer_elastic, Cross_sections.f90:2403-2413
         double RN = rn(p, r);
         double L_need = EMFP / RN;
-        double hw = hole ? transferred_energy(Eel, p.he_E, p.n_he, p.hed_off, p.hed_hw, p.hed_L, L_need)
-                         : transferred_energy(Eel, p.ee_E, p.n_ee, p.eed_off, p.eed_hw, p.eed_L, L_need);
+        double hw = transferred_energy(hole ? csr_hed(p) : csr_eed(p), Eel, k.lE, k.n1, L_need);
         if (hw >= Eel) hw = Eel;
         return hw;
     }
@@ -342,14 +401,18 @@ TRK_HD double from_where_in_VB(const DevP &p, Rec &r, bool haveE, double E) {
 
 // Hole_parameters (+Assign_holes_mass), Monte_Carlo.f90:724-792.  `Ehkin_prev` is the hole's kinetic energy
 // before the update (0 for a newly created hole: How_many_electrons initialises Ehkin = 0).
-TRK_HD void hole_parameters(const DevP &p, Rec &st, Rec &h, double Eh, double Ehkin_prev) {
+// `kout` (optional) receives the lookups of the new kinetic energy for the hole's next collision.
+TRK_HD void hole_parameters(const DevP &p, Rec &st, Rec &h, double Eh, double Ehkin_prev, Cache *kout = nullptr) {
     if (h.shell == p.vb_shell) {
         h.Ehkin = Eh - p.Egap;
         h.E = p.Egap;
         h.Mass = (p.hole_mass > 0) ? p.hole_mass : hole_mass_dos(p, h.Ehkin);
         if (h.Mass < 1.0e3) {
-            double HIMFP = nfp_2d(h.Ehkin, p.hi_E, p.hi_tot, p.n_hi);
-            double HEMFP = (Ehkin_prev == (Eh - p.Egap)) ? 1.0e30 : nfp_2d(h.Ehkin, p.he_E, p.he_L, p.n_he);
+            Cache k;
+            cache_vbhole(p, h.Ehkin, k);
+            if (kout) *kout = k;
+            double HIMFP = k.imfp;
+            double HEMFP = (Ehkin_prev == (Eh - p.Egap)) ? 1.0e30 : k.emfp;
             double RN = rn(p, st);
             double MFP_tot = -log(RN) / (1.0 / HIMFP + 1.0 / HEMFP);
             h.tn = next_time(h.t0, vel_hole(h), MFP_tot);
@@ -372,8 +435,9 @@ template <class C>
 TRK_HD void emit_electron(C &c, Rec &st, uint64_t id, double Ee, double t, double X, double Y, double Z, double theta, double phi, int err_code) {
     const DevP &p = c.p;
     Rec e;
-    double IMFP = nfp_2d(Ee, p.ei_E, p.ei_tot, p.n_ei);
-    double EMFP = nfp_2d(Ee, p.ee_E, p.ee_L, p.n_ee);
+    const double lE = log(Ee);
+    double IMFP = electron_imfp(p, Ee, lE);
+    double EMFP = nfp_2d(tab_ee(p), Ee, lE);
     double RN = rn(p, st);
     double MFP_tot = -log(RN) / (1.0 / IMFP + 1.0 / EMFP);
     e.E = Ee; e.Ehkin = 0.0; e.Mass = 1.0; e.t0 = t; e.X = X; e.Y = Y; e.Z = Z; e.L = MFP_tot; e.theta = theta; e.phi = phi;
@@ -421,8 +485,9 @@ TRK_HD double shi_zeff(const DevP &p, double E) {
 // SHI_energy_transfer (CDF shells), Monte_Carlo.f90:1719-1780.  The reference's linear search over 1/L
 // (Find_in_1D_array) is kept as a forward scan from the threshold row: same first index with 1/L >= Tot_N.
 TRK_HD double shi_energy_transfer(const DevP &p, Rec &r, int shell) {
-    const double *Ea = p.dshi_E + p.dshi_off[shell], *La = p.dshi_L + p.dshi_off[shell];
-    int N = (int)(p.dshi_off[shell + 1] - p.dshi_off[shell]);
+    const int64_t o = p.dshi_off[shell];
+    const double *Ea = p.dshi_E + o, *La = p.dshi_L + o, *lEa = p.ldshi_E + o, *iLa = p.dshi_iL + o, *liLa = p.ldshi_iL + o;
+    int N = (int)(p.dshi_off[shell + 1] - o);
     double RN = rn(p, r);
     double E_cur = p.shell_Ip[shell], dL;
     int M_temp = find_1d(Ea, N, E_cur);
@@ -435,10 +500,10 @@ TRK_HD double shi_energy_transfer(const DevP &p, Rec &r, int shell) {
     if (Tot_N < 1e20) {
         // 1/L is non-decreasing (cumulative cross section): bisection for the first index with 1/L >= Tot_N
         int lo = 1, hi = N;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (1.0 / La[mid - 1] < Tot_N) lo = mid + 1; else hi = mid; }
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (iLa[mid - 1] < Tot_N) lo = mid + 1; else hi = mid; }
         N_temmp = lo;
     } else N_temmp = M_temp;
-    if (N_temmp > M_temp) return interp5(1.0 / La[N_temmp - 2], 1.0 / La[N_temmp - 1], Ea[N_temmp - 2], Ea[N_temmp - 1], Tot_N);
+    if (N_temmp > M_temp) return interp5t(iLa[N_temmp - 2], iLa[N_temmp - 1], Ea[N_temmp - 2], Ea[N_temmp - 1], liLa[N_temmp - 2], liLa[N_temmp - 1], lEa[N_temmp - 2], lEa[N_temmp - 1], Tot_N, log(Tot_N));
     return p.shell_Ip[shell];
 }
 
@@ -544,11 +609,10 @@ TRK_HD void deposit_lattice(C &c, const Rec &r, int iv, double X, double Y, doub
 
 // Electron_Monte_Carlo, Monte_Carlo.f90:2253-2474
 template <class C>
-TRK_HD void electron_event(C &c, Rec &e, int iv) {
+TRK_HD void electron_event(C &c, Rec &e, int iv, Cache &k) {
     const DevP &p = c.p;
     const double Eel = e.E;
-    double IMFP = nfp_2d(Eel, p.ei_E, p.ei_tot, p.n_ei);
-    double EMFP = nfp_2d(Eel, p.ee_E, p.ee_L, p.n_ee);
+    double IMFP = k.imfp, EMFP = k.emfp;                          // :2298-2299, already looked up for this energy
     double RN = rn(p, e);
     const double L = e.L, theta0 = e.theta, phi0 = e.phi;
     const double st0 = sin(theta0);
@@ -557,10 +621,10 @@ TRK_HD void electron_event(C &c, Rec &e, int iv) {
     double dE, theta, phi;
     if (RN * (1.0 / IMFP + 1.0 / EMFP) < 1.0 / IMFP) {          // inelastic: impact ionisation
         c.event(TRK3_EV_EL_INEL);
-        int shell = which_shell(p, e, p.ei_E, p.ei_L, p.n_ei, Eel);
+        int shell = which_shell(p, e, p.ei_E, p.lei_E, p.ei_L, p.lei_L, p.n_ei, Eel, k.lE);
         uint64_t id_e = child_id(p, e, 1), id_h = child_id(p, e, 2);
-        IMFP = nfp_1d(Eel, p.ei_E, p.ei_L + (size_t)shell * p.n_ei, p.n_ei);
-        dE = inelastic_dE(p, e, Eel, shell, IMFP, false);
+        IMFP = nfp_1d(tab_shell(p.ei_E, p.lei_E, p.ei_L, p.lei_L, p.n_ei, shell), Eel, k.lE);
+        dE = inelastic_dE(p, e, Eel, k.lE, shell, IMFP, false);
         theta = acos((Eel - dE) / sqrt(Eel * (Eel - dE)));       // Update_electron_angles_El :1189
         if (trk_isnan(theta)) { double r2 = rn(p, e); theta = r2 * TRK_PI; }
         { double r2 = rn(p, e); phi = 2.0 * TRK_PI * r2; }
@@ -571,14 +635,14 @@ TRK_HD void electron_event(C &c, Rec &e, int iv) {
         emit_hole(c, e, id_h, shell, dE - dE_cur, t_ev, X, Y, Z, TRK3_ERR_20);
     } else {                                                     // elastic: energy to the lattice
         c.event(TRK3_EV_EL_ELAST);
-        EMFP = nfp_1d(Eel, p.ee_E, p.ee_L, p.n_ee);
-        dE = elastic_dE(p, e, Eel, EMFP, false, 1.0);
+        EMFP = elastic_total(tab_ee(p), Eel, k);
+        dE = elastic_dE(p, e, Eel, k, EMFP, false, 1.0);
         angles_lattice(p, e, Eel, dE, 1.0, theta, phi);
         if (trk_isnan(theta) || trk_isnan(phi)) c.error(TRK3_ERR_NAN);
         deposit_lattice(c, e, iv, X, Y, dE);
     }
-    IMFP = nfp_2d(Eel - dE, p.ei_E, p.ei_tot, p.n_ei);
-    EMFP = nfp_2d(Eel - dE, p.ee_E, p.ee_L, p.n_ee);
+    cache_electron(p, Eel - dE, k);                               // :2449-2450, kept for the next collision
+    IMFP = k.imfp; EMFP = k.emfp;
     RN = rn(p, e);
     double MFP_tot = -log(RN) / (1.0 / IMFP + 1.0 / EMFP);
     double phi1, theta1;
@@ -630,11 +694,10 @@ TRK_HD void check_hole_level(const DevP &p, double Eel, double &dE, double &Ehol
 
 // Hole_Monte_Carlo, valence-band branch, Monte_Carlo.f90:2560-2738
 template <class C>
-TRK_HD void vbhole_event(C &c, Rec &h, int iv) {
+TRK_HD void vbhole_event(C &c, Rec &h, int iv, Cache &k) {
     const DevP &p = c.p;
     const double Eel = h.Ehkin;
-    double HIMFP = nfp_2d(Eel, p.hi_E, p.hi_tot, p.n_hi);
-    double HEMFP = nfp_2d(Eel, p.he_E, p.he_L, p.n_he);
+    double HIMFP = k.imfp, HEMFP = k.emfp;                        // :2579-2580
     double RN = rn(p, h);
     const double L = h.L, theta0 = h.theta, phi0 = h.phi;
     const double st0 = sin(theta0);
@@ -643,10 +706,10 @@ TRK_HD void vbhole_event(C &c, Rec &h, int iv) {
     double dE, Ehole, htheta1, hphi1;
     if (RN * (1.0 / HIMFP + 1.0 / HEMFP) < 1.0 / HIMFP && HIMFP < 1e15) {
         c.event(TRK3_EV_VBH_INEL);
-        int shell = which_shell(p, h, p.hi_E, p.hi_L, p.n_hi, Eel);
+        int shell = which_shell(p, h, p.hi_E, p.lhi_E, p.hi_L, p.lhi_L, p.n_hi, Eel, k.lE);
         uint64_t id_e = child_id(p, h, 1), id_h = child_id(p, h, 2);
-        HIMFP = nfp_1d(Eel, p.hi_E, p.hi_L + (size_t)shell * p.n_hi, p.n_hi);
-        dE = inelastic_dE(p, h, Eel, shell, HIMFP, true);
+        HIMFP = nfp_1d(tab_shell(p.hi_E, p.lhi_E, p.hi_L, p.lhi_L, p.n_hi, shell), Eel, k.lE);
+        dE = inelastic_dE(p, h, Eel, k.lE, shell, HIMFP, true);
         // Update_holes_angles_el, :1142-1168
         double E11 = Eel - dE, Mh = h.Mass * TRK_ME;
         double htheta = acos(sqrt((Mh + TRK_ME) * (Mh + TRK_ME) / (4.0 * Mh * TRK_ME) * dE / Eel));
@@ -657,8 +720,9 @@ TRK_HD void vbhole_event(C &c, Rec &h, int iv) {
         if (trk_isnan(htheta1)) { double r2 = rn(p, h); htheta1 = TRK_PI * r2; }
         double dE_cur = electron_receives_E(c, h, dE, shell);
         // the new electron is fully sampled first (:2606-2621), then the level check may add the surplus to it (:2660)
-        double IMFP = nfp_2d(dE_cur, p.ei_E, p.ei_tot, p.n_ei);
-        double EMFP = nfp_2d(dE_cur, p.ee_E, p.ee_L, p.n_ee);
+        const double lEn = log(dE_cur);
+        double IMFP = electron_imfp(p, dE_cur, lEn);
+        double EMFP = nfp_2d(tab_ee(p), dE_cur, lEn);
         RN = rn(p, h);
         double MFP_tot = -log(RN) / (1.0 / IMFP + 1.0 / EMFP);
         RN = rn(p, h);                                           // sic (:2611): drawn and discarded
@@ -676,8 +740,8 @@ TRK_HD void vbhole_event(C &c, Rec &h, int iv) {
         c.push(SP_ELECTRON, e);
     } else {
         c.event(TRK3_EV_VBH_ELAST);
-        HEMFP = nfp_1d(Eel, p.he_E, p.he_L, p.n_he);
-        dE = elastic_dE(p, h, Eel, HEMFP, true, h.Mass);
+        HEMFP = elastic_total(tab_he(p), Eel, k);
+        dE = elastic_dE(p, h, Eel, k, HEMFP, true, h.Mass);
         angles_lattice(p, h, Eel, dE, h.Mass, htheta1, hphi1);
         check_hole_level(p, Eel, dE, Ehole, nullptr);
         deposit_lattice(c, h, iv, X, Y, dE);
@@ -685,7 +749,7 @@ TRK_HD void vbhole_event(C &c, Rec &h, int iv) {
     double hphi2, htheta2;
     new_angles(phi0, theta0, htheta1, hphi1, hphi2, htheta2);
     h.t0 = t_ev; h.X = X; h.Y = Y; h.Z = Z; h.theta = htheta2; h.phi = hphi2;
-    hole_parameters(p, h, h, Ehole + p.Egap, Eel);
+    hole_parameters(p, h, h, Ehole + p.Egap, Eel, &k);
     if (h.Ehkin < -1.0e-9 || trk_isnan(h.Ehkin)) c.error(TRK3_ERR_20);
 }
 
@@ -752,8 +816,9 @@ TRK_HD void corehole_event(C &c, Rec &h) {
             uint64_t id_e = child_id(p, h, 1), id_h = child_id(p, h, 2);
             emit_hole(c, h, id_h, s2, E_new2, t_ev, h.X, h.Y, h.Z, TRK3_ERR_20);
             // Auger electron: isotropic in angle (:2800-2813); phi is drawn before theta
-            double IMFP = nfp_2d(Ee, p.ei_E, p.ei_tot, p.n_ei);
-            double EMFP = nfp_2d(Ee, p.ee_E, p.ee_L, p.n_ee);
+            const double lEn = log(Ee);
+            double IMFP = electron_imfp(p, Ee, lEn);
+            double EMFP = nfp_2d(tab_ee(p), Ee, lEn);
             RN = rn(p, h);
             double MFP_tot = -log(RN) / (1.0 / IMFP + 1.0 / EMFP);
             RN = rn(p, h); double phi1 = 2.0 * TRK_PI * RN;
@@ -785,7 +850,7 @@ TRK_HD void corehole_event(C &c, Rec &h) {
         hole_parameters(p, h, h, E_new1, Ehk_prev);
         // photon (:2843-2866); the reference's slot-reuse bug (:2844 vs :2963) does not exist here
         uint64_t id_p = child_id(p, h, 3);
-        double IMFP = nfp_2d(dE, p.ph_E, p.ph_tot, p.n_ph);
+        double IMFP = nfp_2d(tab_ph_tot(p), dE, log(dE));
         RN = rn(p, h);
         double MFP_tot = -log(RN) * IMFP;
         RN = rn(p, h); double phi1 = 2.0 * TRK_PI * RN;
@@ -808,7 +873,7 @@ TRK_HD void photon_event(C &c, Rec &ph) {
     const double Eel = ph.E, L = ph.L, theta0 = ph.theta, phi0 = ph.phi, t_ev = ph.tn;
     const double st0 = sin(theta0);
     const double X = ph.X + L * st0 * sin(phi0), Y = ph.Y + L * st0 * cos(phi0), Z = ph.Z + L * cos(theta0);
-    int shell = which_shell(p, ph, p.ph_E, p.ph_L, p.n_ph, Eel);
+    int shell = which_shell(p, ph, p.ph_E, p.lph_E, p.ph_L, p.lph_L, p.n_ph, Eel, log(Eel));
     uint64_t id_e = child_id(p, ph, 1), id_h = child_id(p, ph, 2);
     double dE_cur = electron_receives_E(c, ph, Eel, shell);
     double phi1, theta1;
@@ -829,16 +894,17 @@ TRK_HD void shi_history(C &c, uint32_t iter) {
     const double MSHI = p.ion_mass * TRK_MP;
     double Zeff = p.ion_Zeff0;
     {
-        double lam = nfp_2d(s.E, p.shi_E, p.shi_tot, p.n_shi);
+        double lam = nfp_2d(tab_shi_tot(p), s.E, log(s.E));
         double RN = rn(p, s);
         s.L = -lam * log(RN);
         s.tn = next_time(s.t0, sqrt(2.0 * s.E * TRK_GE / MSHI), s.L);
     }
     while (s.tn < p.Tim) {
         c.event(TRK3_EV_SHI);
-        int shell = which_shell(p, s, p.shi_E, p.shi_L, p.n_shi, s.E);
+        const double lEs = log(s.E);
+        int shell = which_shell(p, s, p.shi_E, p.lshi_E, p.shi_L, p.lshi_L, p.n_shi, s.E, lEs);
         double dE = shi_energy_transfer(p, s, shell);
-        double lam = nfp_2d(s.E, p.shi_E, p.shi_tot, p.n_shi);
+        double lam = nfp_2d(tab_shi_tot(p), s.E, lEs);
         double RN = rn(p, s);
         double SHI_IMFP = -lam * log(RN);
         double Z = s.Z + s.L;
@@ -866,26 +932,32 @@ TRK_HD void shi_history(C &c, uint32_t iter) {
 // `ig` = next grid index to snapshot (first i with t0 < tg(i)).
 // ------------------------------------------------------------------------------------------------
 template <class C>
-TRK_HD void begin_electron(C &c, const Rec &e, int &ig) {
+TRK_HD void begin_electron(C &c, const Rec &e, int &ig, Cache &k) {
     const DevP &p = c.p;
+    cache_electron(p, e.E, k);
     ig = interval_of(p, e.t0);
     c.add_u32(p.it.created, (size_t)(e.iter - p.batch_begin) * (p.Nt + 2) + ig);    // Tot_Nel bookkeeping
 }
 // one step = snapshots spanned by the current free flight, then the collision at tn; false when history ended
 template <class C>
-TRK_HD bool step_electron(C &c, Rec &e, int &ig) {
+TRK_HD bool step_electron(C &c, Rec &e, int &ig, Cache &k) {
     const DevP &p = c.p;
     while (ig <= p.Nt && p.tg[ig - 1] <= e.tn) { snapshot_electron(c, e, ig); ++ig; }
     if (ig > p.Nt) return false;
-    electron_event(c, e, ig);
+    electron_event(c, e, ig, k);
     return true;
 }
+// a valence hole taken from a queue: the lookups of its kinetic energy (only mobile holes ever collide)
+TRK_HD void begin_vbhole(const DevP &p, const Rec &h, int &ig, Cache &k) {
+    ig = interval_of(p, h.t0);
+    if (h.tn < p.Tim) cache_vbhole(p, h.Ehkin, k);
+}
 template <class C>
-TRK_HD bool step_vbhole(C &c, Rec &h, int &ig) {
+TRK_HD bool step_vbhole(C &c, Rec &h, int &ig, Cache &k) {
     const DevP &p = c.p;
     while (ig <= p.Nt && p.tg[ig - 1] <= h.tn) { snapshot_hole(c, h, ig); ++ig; }
     if (ig > p.Nt) return false;
-    vbhole_event(c, h, ig);
+    vbhole_event(c, h, ig, k);
     return true;
 }
 // core hole: after a decay the hole may have hopped into the valence band -> continue as a VB hole (other queue)
