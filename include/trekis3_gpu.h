@@ -219,8 +219,8 @@ int trk3_mc_iteration_energies(trk3_engine *eng, double *out, int64_t capacity_d
 /* Plumbing for frameworks that own the stream / the tally buffer (torch.distributed + NCCL all-reduce). */
 int trk3_mc_set_stream(trk3_engine *eng, void *cuda_stream);
 int trk3_mc_set_device_tallies(trk3_engine *eng, double *device_buffer);
-/* Device time per kernel class since option "profile"=1 (0 electron wave, 1 valence-hole wave, 2 core-hole
- * wave, 3 photon wave, 4 ion tracks, 5 finalize); returns the number of classes. */
+/* Device time per kernel class since option "profile"=1 (0 hot electron wave, 1 hot valence-hole wave, 2 core-hole
+ * wave, 3 photon wave, 4 ion tracks, 5 finalize, 6 cold electrons, 7 cold valence holes); returns the number of classes. */
 int trk3_mc_kernel_times(trk3_engine *eng, double *ms, uint64_t *launches, int n);
 
 /* Tunables: "batch" iterations in flight, "cap_factor" queue capacity, "use_smem", "refill_min", "profile" ... */

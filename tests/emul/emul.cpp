@@ -17,9 +17,15 @@ using namespace trk3;
 namespace {
 struct EmuCtx {
     const DevP &p;
-    std::vector<Rec> *next;     // [N_SPECIES]
+    std::vector<Rec> *next;     // [N_SPECIES] next hot generation
+    std::vector<Rec> *cold;     // [2] cold electrons / valence holes (consumed after the hot generations)
     unsigned long long *ev, *er, *nel, *nph;
-    void push(int sp, const Rec &r) { next[sp].push_back(r); }
+    void push_hot(int sp, const Rec &r) { next[sp].push_back(r); }
+    void push(int sp, const Rec &r) {       // same routing as DevCtx::push in engine.cu
+        if (sp == SP_ELECTRON && electron_is_cold(p, r)) cold[0].push_back(r);
+        else if (sp == SP_VBHOLE && vbhole_is_cold(p, r)) cold[1].push_back(r);
+        else next[sp].push_back(r);
+    }
     void tally(int id, int64_t idx, double v) { p.tally[p.g_off[id] + idx] += v; }
     void add_u32(uint32_t *b, size_t i) { b[i] += 1u; }
     void add_f64(double *b, size_t i, double v) { b[i] += v; }
@@ -28,6 +34,17 @@ struct EmuCtx {
     void count_electron() { (*nel)++; }
     void count_photon() { (*nph)++; }
 };
+// run one record through step function `step` until it leaves the kernel
+template <class F>
+void follow(EmuCtx &c, int sp, Rec r, int ig, Cache k, F step) {
+    for (;;) {
+        const int st = step(c, r, ig, k);
+        if (st == ST_CONT) continue;
+        if (st == ST_MOVE) c.push(sp, r);
+        else if (st == ST_MOVE_HOT) c.push_hot(sp, r);
+        return;
+    }
+}
 }  // namespace
 
 extern "C" int trk3_emul_run(const trk3_config *cfg, const trk3_tables *tab, int64_t it_begin, int64_t it_end, int batch,
@@ -69,18 +86,26 @@ extern "C" int trk3_emul_run(const trk3_config *cfg, const trk3_tables *tab, int
         ScratchLayout sl = scratch_layout(p, nb);
         std::vector<uint32_t> U(sl.u32_total, 0u); std::vector<double> D(sl.f64_total, 0.0);
         bind_scratch(p, sl, U.data(), D.data());
-        std::vector<Rec> cur[N_SPECIES], nxt[N_SPECIES];
-        EmuCtx c{p, nxt, ev, er, &nel, &nph};
+        std::vector<Rec> cur[N_SPECIES], nxt[N_SPECIES], cold[2], cold_cur[2];
+        EmuCtx c{p, nxt, cold, ev, er, &nel, &nph};
         for (uint32_t k = 0; k < nb; ++k) shi_history(c, (uint32_t)(b0 + k));
         for (;;) {
             size_t n = 0;
             for (int s = 0; s < N_SPECIES; ++s) { cur[s].swap(nxt[s]); nxt[s].clear(); n += cur[s].size(); }
-            if (!n) break;
+            if (n) {        // one hot generation
+                ++waves;
+                for (const Rec &r : cur[SP_ELECTRON]) { int ig; Cache k{}; begin_electron(p, r, ig, k); follow(c, SP_ELECTRON, r, ig, k, [](EmuCtx &c, Rec &r, int &ig, Cache &k) { return step_electron<false>(c, r, ig, k); }); }
+                for (const Rec &r : cur[SP_VBHOLE]) { int ig; Cache k{}; begin_vbhole(p, r, ig, k); follow(c, SP_VBHOLE, r, ig, k, [](EmuCtx &c, Rec &r, int &ig, Cache &k) { return step_vbhole<false>(c, r, ig, k); }); }
+                for (const Rec &r : cur[SP_COREHOLE]) { follow(c, SP_COREHOLE, r, interval_of(p, r.t0), Cache{}, [](EmuCtx &c, Rec &r, int &ig, Cache &) { return step_corehole(c, r, ig); }); }
+                for (const Rec &r : cur[SP_PHOTON]) { follow(c, SP_PHOTON, r, interval_of(p, r.t0), Cache{}, [](EmuCtx &c, Rec &r, int &ig, Cache &) { return step_photon(c, r, ig); }); }
+                continue;
+            }
+            if (cold[0].empty() && cold[1].empty()) break;
+            // the hot cascade has died out: drain the cold queues (elastic scattering + snapshots only)
             ++waves;
-            for (Rec r : cur[SP_ELECTRON]) { int ig; Cache k{}; begin_electron(c, r, ig, k); while (step_electron(c, r, ig, k)) {} }
-            for (Rec r : cur[SP_VBHOLE]) { int ig; Cache k{}; begin_vbhole(p, r, ig, k); while (step_vbhole(c, r, ig, k)) {} }
-            for (Rec r : cur[SP_COREHOLE]) { int ig = interval_of(p, r.t0); while (step_corehole(c, r, ig)) {} }
-            for (Rec r : cur[SP_PHOTON]) { int ig = interval_of(p, r.t0); while (step_photon(c, r, ig)) {} }
+            cold_cur[0].swap(cold[0]); cold[0].clear(); cold_cur[1].swap(cold[1]); cold[1].clear();
+            for (const Rec &r : cold_cur[0]) { int ig; Cache k{}; begin_electron(p, r, ig, k); follow(c, SP_ELECTRON, r, ig, k, [](EmuCtx &c, Rec &r, int &ig, Cache &k) { return step_electron<true>(c, r, ig, k); }); }
+            for (const Rec &r : cold_cur[1]) { int ig; Cache k{}; begin_vbhole(p, r, ig, k); follow(c, SP_VBHOLE, r, ig, k, [](EmuCtx &c, Rec &r, int &ig, Cache &k) { return step_vbhole<true>(c, r, ig, k); }); }
         }
         std::vector<double> a0((size_t)nb * Nt), a1((size_t)nb * Nt), a2((size_t)nb * Nt), a3((size_t)nb * Nt), a4((size_t)nb * Nt);
         FoldAux fa{a0.data(), a1.data(), a2.data(), a3.data(), a4.data()};

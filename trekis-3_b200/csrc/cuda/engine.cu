@@ -3,10 +3,13 @@
 // Replaces do_Monte_Carlo / Monte_Carlo_modelling (Monte_Carlo.f90:39-679).  Structure:
 //   * a batch of iterations is in flight at once; the ion tracks of the batch are walked by k_shi,
 //     which fills the first generation of the species queues (electrons, valence holes, core holes);
-//   * k_wave<species> consumes one generation: a warp pulls records from the queue (one atomic per
-//     refill, lanes that finish are refilled so warps stay full), every lane follows its particle to
-//     the end of its history with the state in registers, secondaries are appended to the
-//     next-generation queues with warp-aggregated atomics (one atomicAdd per species per warp);
+//   * k_wave<species, HOT> consumes one generation of particles that can still ionise: a warp pulls records
+//     from the queue (one atomic per refill, lanes that finish are refilled so warps stay full), every lane
+//     follows its particle with the state in registers, secondaries are appended to the next-generation
+//     queues with warp-aggregated atomics (one atomicAdd per queue per warp);
+//   * particles that can no longer ionise (below the lowest threshold: >90 % of all collisions) are routed to
+//     the COLD queues and drained by k_wave<species, COLD> once the hot cascade has died out: those kernels
+//     contain only snapshots + elastic scattering, so warps do not diverge into the ionisation code;
 //   * radial x time tallies are accumulated in a shared-memory private copy per block and flushed once
 //     per block; spectra that the reference normalises per iteration go to per-iteration integer
 //     histograms and are folded by k_fold (no atomics, fixed summation order);
@@ -26,7 +29,12 @@ using namespace trk3;
 
 __constant__ DevP c_p;
 
-struct QueueSet { Queue q[N_SPECIES]; };
+// queue ids: 0..3 = next hot generation per species, 4 / 5 = cold electrons / cold valence holes
+#define Q_EL_COLD N_SPECIES
+#define Q_VB_COLD (N_SPECIES + 1)
+#define N_QUEUES (N_SPECIES + 2)
+struct QueueSet { Queue q[N_QUEUES]; };
+#define N_CLASSES (N_SPECIES + 4)     // timing classes: hot waves per species, k_shi, finalize, cold electrons, cold holes
 
 #define TRK_BLOCK_MAX 256          // compile-time upper bound of the wave-kernel block size (launch bounds)
 #ifndef TRK_MIN_BLOCKS
@@ -47,12 +55,19 @@ struct DevCtx {
     unsigned int *s_cnt;
 
     __device__ void push(int sp, const Rec &r) {
-        // warp-aggregated append: lanes pushing to the same species share one atomicAdd
+        int qi = sp;
+        if (sp == SP_ELECTRON) { if (electron_is_cold(p, r)) qi = Q_EL_COLD; }
+        else if (sp == SP_VBHOLE) { if (vbhole_is_cold(p, r)) qi = Q_VB_COLD; }
+        push_q(qi, r);
+    }
+    __device__ void push_hot(int sp, const Rec &r) { push_q(sp, r); }
+    __device__ void push_q(int qi, const Rec &r) {
+        // warp-aggregated append: lanes pushing to the same queue share one atomicAdd
         const unsigned am = __activemask();
-        const unsigned m = __match_any_sync(am, sp);
+        const unsigned m = __match_any_sync(am, qi);
         const int lane = threadIdx.x & 31;
         const int leader = __ffs(m) - 1;
-        const Queue &q = out.q[sp];
+        const Queue &q = out.q[qi];
         unsigned base = 0;
         if (lane == leader) base = atomicAdd(q.count, (unsigned)__popc(m));
         base = __shfl_sync(m, base, leader);
@@ -120,9 +135,10 @@ __global__ void __launch_bounds__(32) k_shi(QueueSet qout) {
     block_epilogue(c_p, nullptr, s_cnt);
 }
 
-// k_wave<SP>: one generation of species SP, histories run to completion with lane refill.
-template <int SP>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min) {
+// k_wave<SP, COLD>: records [first, n_in) of queue qin, histories followed with lane refill until they end or
+// have to change queue (hot -> cold when the particle can no longer ionise, core hole -> valence hole, ...).
+template <int SP, bool COLD>
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
@@ -139,14 +155,14 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
             const int nidle = __popc(idle);
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(head, (uint32_t)nidle);
-            base = __shfl_sync(0xffffffffu, base, 0);
+            base = __shfl_sync(0xffffffffu, base, 0) + first;
             if (base + (uint32_t)nidle >= n_in) exhausted = true;
             if (!active) {
                 const uint32_t my = base + __popc(idle & ((1u << lane) - 1u));
                 if (my < n_in) {
                     load_rec(qin, my, r);
                     active = true;
-                    if (SP == SP_ELECTRON) begin_electron(c, r, ig, k);
+                    if (SP == SP_ELECTRON) begin_electron(c_p, r, ig, k);
                     else if (SP == SP_VBHOLE) begin_vbhole(c_p, r, ig, k);
                     else ig = interval_of(c_p, r.t0);
                 }
@@ -154,12 +170,16 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
         }
         if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; continue; }
         if (active) {
-            bool cont;
-            if (SP == SP_ELECTRON) cont = step_electron(c, r, ig, k);
-            else if (SP == SP_VBHOLE) cont = step_vbhole(c, r, ig, k);
-            else if (SP == SP_COREHOLE) cont = step_corehole(c, r, ig);
-            else cont = step_photon(c, r, ig);
-            if (!cont) active = false;
+            int st;
+            if (SP == SP_ELECTRON) st = step_electron<COLD>(c, r, ig, k);
+            else if (SP == SP_VBHOLE) st = step_vbhole<COLD>(c, r, ig, k);
+            else if (SP == SP_COREHOLE) st = step_corehole(c, r, ig);
+            else st = step_photon(c, r, ig);
+            if (st != ST_CONT) {
+                if (st == ST_MOVE) c.push(SP, r);
+                else if (st == ST_MOVE_HOT) c.push_hot(SP, r);
+                active = false;
+            }
         }
     }
     block_epilogue(c_p, s_tally, s_cnt);
@@ -202,7 +222,7 @@ struct trk3_engine {
     // per-batch resources
     uint32_t nb_alloc = 0;
     QueueSet qs[2]{};
-    uint32_t *d_qcount = nullptr;      // [2][N_SPECIES] counts + [N_SPECIES] heads
+    uint32_t *d_qcount = nullptr;      // QC_* layout below: hot counts of both generations, cold counts, heads
     uint32_t *d_u32 = nullptr; double *d_f64 = nullptr; ScratchLayout sl{};
     FoldAux fa{};
     double *d_tally = nullptr, *d_small = nullptr, *d_tally_bak = nullptr;
@@ -210,8 +230,8 @@ struct trk3_engine {
     int n_sm = 0, smem_optin = 0;
     bool own_stream = true, own_tally = true;
     int opt_profile = 0;               // 1: time every kernel class with CUDA events (bench.py roofline)
-    double class_ms[N_SPECIES + 2] = {0, 0, 0, 0, 0, 0};      // k_wave<species>, k_shi, finalize
-    uint64_t class_launches[N_SPECIES + 2] = {0, 0, 0, 0, 0, 0};
+    double class_ms[N_CLASSES] = {0};          // hot k_wave<species>, k_shi, finalize, cold electrons, cold holes
+    uint64_t class_launches[N_CLASSES] = {0};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     std::vector<std::pair<int, int>> ev_pending;   // (class, pool index)
     // results
@@ -220,6 +240,13 @@ struct trk3_engine {
     std::string err;
     uint64_t launches = 0;
 };
+
+// d_qcount layout (uint32): [0..3] hot counts generation A, [4..7] generation B, [8..9] cold counts,
+// [10..13] hot heads, [14..15] cold heads
+#define QC_HOT(b) ((b) * N_SPECIES)
+#define QC_COLD (2 * N_SPECIES)
+#define QC_HEAD (2 * N_SPECIES + 2)
+#define QC_TOTAL (3 * N_SPECIES + 4)
 
 namespace {
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { eng->err = std::string(#call) + ": " + cudaGetErrorString(e_); return TRK3_E_CUDA; } } while (0)
@@ -288,25 +315,38 @@ void free_queue(trk3_engine *eng, Queue &q) {
 }
 
 // per-iteration capacities of the species queues (records of ONE generation)
-void queue_caps(const trk3_engine *eng, double cap[N_SPECIES]) {
+void queue_caps(const trk3_engine *eng, double cap[N_QUEUES]) {
     const double n = eng->nel_est * eng->opt_cap_factor + 512.0;
     cap[SP_ELECTRON] = n; cap[SP_VBHOLE] = n; cap[SP_COREHOLE] = 0.5 * n + 256.0;
     cap[SP_PHOTON] = eng->cfg.include_photons ? 0.25 * n + 64.0 : 1.0;
+    cap[Q_EL_COLD] = n; cap[Q_VB_COLD] = n;       // every carrier of an iteration ends up here once
+}
+double queue_bytes_per_iteration(const trk3_engine *eng) {
+    double cap[N_QUEUES]; queue_caps(eng, cap);
+    double b = 0;
+    for (int s = 0; s < N_SPECIES; ++s) b += 2.0 * cap[s] * (TRK_NCOL * 8 + 20);
+    for (int s = N_SPECIES; s < N_QUEUES; ++s) b += cap[s] * (TRK_NCOL * 8 + 20);
+    return b;
 }
 
 int ensure_batch(trk3_engine *eng, uint32_t nb) {
     if (nb <= eng->nb_alloc) return TRK3_OK;
     // release the previous batch resources
     for (int b = 0; b < 2; ++b) for (int s = 0; s < N_SPECIES; ++s) free_queue(eng, eng->qs[b].q[s]);
+    for (int s = N_SPECIES; s < N_QUEUES; ++s) { free_queue(eng, eng->qs[0].q[s]); eng->qs[1].q[s] = Queue{}; }
     dev_free(eng, eng->d_u32); dev_free(eng, eng->d_f64);
     dev_free(eng, eng->fa.totnel); dev_free(eng, eng->fa.totE); dev_free(eng, eng->fa.latcum); dev_free(eng, eng->fa.emcnt); dev_free(eng, eng->fa.emE);
     eng->d_u32 = nullptr; eng->d_f64 = nullptr; eng->fa = FoldAux{};
-    double cap[N_SPECIES]; queue_caps(eng, cap);
+    double cap[N_QUEUES]; queue_caps(eng, cap);
+    for (int s = 0; s < N_QUEUES; ++s) if (cap[s] * (double)nb > 4.0e9) { eng->err = "queue capacity exceeds 2^32 records; lower the batch"; return TRK3_E_NOMEM; }
     for (int b = 0; b < 2; ++b) for (int s = 0; s < N_SPECIES; ++s) {
-        double c = cap[s] * (double)nb;
-        if (c > 4.0e9) { eng->err = "queue capacity exceeds 2^32 records; lower the batch"; return TRK3_E_NOMEM; }
-        int rc = alloc_queue(eng, eng->qs[b].q[s], (uint32_t)c, eng->d_qcount + b * N_SPECIES + s);
+        int rc = alloc_queue(eng, eng->qs[b].q[s], (uint32_t)(cap[s] * (double)nb), eng->d_qcount + QC_HOT(b) + s);
         if (rc) return rc;
+    }
+    for (int s = N_SPECIES; s < N_QUEUES; ++s) {      // the cold queues are shared by both generations
+        int rc = alloc_queue(eng, eng->qs[0].q[s], (uint32_t)(cap[s] * (double)nb), eng->d_qcount + QC_COLD + (s - N_SPECIES));
+        if (rc) return rc;
+        eng->qs[1].q[s] = eng->qs[0].q[s];
     }
     eng->sl = scratch_layout(eng->hp, nb);
     int rc;
@@ -323,22 +363,23 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
     return TRK3_OK;
 }
 
-template <int SP>
-int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t n, uint32_t *head, const QueueSet &qout) {
+template <int SP, bool COLD>
+int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_in, uint32_t *head, const QueueSet &qout) {
+    const uint32_t n = n_in - first;
     size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
     int use_smem = eng->opt_use_smem;
     const size_t smem_max = (size_t)eng->smem_optin - 1024;             // static shared memory + driver reserve
     if (smem > smem_max) { smem = 8; use_smem = 0; }                    // too many output times for shared memory: global atomics
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_wave<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_wave<SP, COLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = eng->opt_blocks_per_sm;
     const int block = eng->opt_block;
-    if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_wave<SP>, block, smem)); if (bps < 1) bps = 1; }
+    if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_wave<SP, COLD>, block, smem)); if (bps < 1) bps = 1; }
     // persistent-style grid: a multiple of the SM count, never more blocks than there is work for
     uint32_t want = (n + block - 1) / block;
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (grid < 1) grid = 1;
-    const int pi = prof_begin(eng, SP);
-    k_wave<SP><<<grid, block, smem, eng->stream>>>(qin, n, head, qout, use_smem, eng->opt_refill_min);
+    const int pi = prof_begin(eng, COLD ? N_SPECIES + 2 + SP : SP);
+    k_wave<SP, COLD><<<grid, block, smem, eng->stream>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min);
     prof_end(eng, pi);
     CK(cudaGetLastError());
     eng->launches++;
@@ -407,7 +448,7 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
     if ((rc = dev_alloc(eng, &eng->d_small, (size_t)TRK3_MAX_NT))) return rc;
     if ((rc = dev_alloc(eng, &eng->d_counters, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 2)))) return rc;
     if ((rc = dev_alloc(eng, &eng->d_counters_bak, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 2)))) return rc;
-    if ((rc = dev_alloc(eng, &eng->d_qcount, (size_t)(3 * N_SPECIES)))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_qcount, (size_t)QC_TOTAL))) return rc;
     p.tally = eng->d_tally;
     p.events = eng->d_counters; p.errors = eng->d_counters + TRK3_N_EVENT_CLASSES;
     p.cnt_el = eng->d_counters + TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS; p.cnt_ph = p.cnt_el + 1;
@@ -461,9 +502,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
     eng->iter_totE.assign((size_t)n_it * Nt, 0.0);
     eng->Dcoef.assign(Nt, 0.0);
     // batch size: bounded by the option and by the queue-memory budget
-    double cap[N_SPECIES]; queue_caps(eng, cap);
-    double bytes_per_iter = 0; for (int s = 0; s < N_SPECIES; ++s) bytes_per_iter += 2.0 * cap[s] * (TRK_NCOL * 8 + 20);
-    int64_t nb_max = std::min<int64_t>(eng->opt_batch, std::max<int64_t>(1, (int64_t)((double)eng->opt_queue_bytes_max / bytes_per_iter)));
+    int64_t nb_max = std::min<int64_t>(eng->opt_batch, std::max<int64_t>(1, (int64_t)((double)eng->opt_queue_bytes_max / queue_bytes_per_iteration(eng))));
     nb_max = std::min<int64_t>(nb_max, std::max<int64_t>(n_it, 1));
     int rc = ensure_batch(eng, (uint32_t)nb_max);
     if (rc) return rc;
@@ -471,7 +510,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
     CK(cudaMemsetAsync(eng->d_counters, 0, n_counters * sizeof(unsigned long long), eng->stream));
     uint64_t waves = 0; const uint64_t launches0 = eng->launches;
     std::vector<double> h_diffS, h_totE; std::vector<uint32_t> h_diffN;
-    uint32_t *heads = eng->d_qcount + 2 * N_SPECIES;
+    uint32_t *heads = eng->d_qcount + QC_HEAD;
     CK(cudaEventRecord(eng->ev0, eng->stream));
     int retries = 0;
     for (int64_t b0 = it_begin; b0 < it_end;) {
@@ -483,7 +522,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         CK(cudaMemcpyToSymbolAsync(c_p, &eng->hp, sizeof(DevP), 0, cudaMemcpyHostToDevice, eng->stream));
         CK(cudaMemsetAsync(eng->d_u32, 0, eng->sl.u32_total * sizeof(uint32_t), eng->stream));
         CK(cudaMemsetAsync(eng->d_f64, 0, eng->sl.f64_total * sizeof(double), eng->stream));
-        CK(cudaMemsetAsync(eng->d_qcount, 0, 3 * N_SPECIES * sizeof(uint32_t), eng->stream));
+        CK(cudaMemsetAsync(eng->d_qcount, 0, QC_TOTAL * sizeof(uint32_t), eng->stream));
         { const int pi = prof_begin(eng, N_SPECIES);
           k_shi<<<(nb + 31) / 32, 32, 0, eng->stream>>>(eng->qs[0]);
           prof_end(eng, pi); }
@@ -491,21 +530,32 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         eng->launches++;
         int cur = 0;
         bool overflow = false;
+        uint32_t cold_done[2] = {0, 0};
         for (int gen = 0; gen < eng->opt_max_generations; ++gen) {
-            uint32_t h_cnt[N_SPECIES];
-            CK(cudaMemcpyAsync(h_cnt, eng->d_qcount + cur * N_SPECIES, sizeof h_cnt, cudaMemcpyDeviceToHost, eng->stream));
+            uint32_t h_cnt[QC_COLD + 2];       // hot counts of both generations + cold counts
+            CK(cudaMemcpyAsync(h_cnt, eng->d_qcount, sizeof h_cnt, cudaMemcpyDeviceToHost, eng->stream));
             CK(cudaStreamSynchronize(eng->stream));
+            uint32_t *hot = h_cnt + QC_HOT(cur), *cold = h_cnt + QC_COLD;
             uint64_t total = 0;
-            for (int s = 0; s < N_SPECIES; ++s) { if (h_cnt[s] > eng->qs[cur].q[s].cap) { overflow = true; h_cnt[s] = eng->qs[cur].q[s].cap; } total += h_cnt[s]; }
-            if (!total || overflow) break;
+            for (int s = 0; s < N_SPECIES; ++s) { if (hot[s] > eng->qs[cur].q[s].cap) { overflow = true; hot[s] = eng->qs[cur].q[s].cap; } total += hot[s]; }
+            for (int s = 0; s < 2; ++s) if (cold[s] > eng->qs[0].q[N_SPECIES + s].cap) { overflow = true; cold[s] = eng->qs[0].q[N_SPECIES + s].cap; }
+            if (overflow) break;
+            const bool cold_pending = cold[0] > cold_done[0] || cold[1] > cold_done[1];
+            if (!total && !cold_pending) break;
             ++waves;
             const int nxt = cur ^ 1;
-            CK(cudaMemsetAsync(eng->d_qcount + nxt * N_SPECIES, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
-            CK(cudaMemsetAsync(heads, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
-            if (h_cnt[SP_ELECTRON]) { rc = launch_wave<SP_ELECTRON>(eng, eng->qs[cur].q[SP_ELECTRON], h_cnt[SP_ELECTRON], heads + SP_ELECTRON, eng->qs[nxt]); if (rc) return rc; }
-            if (h_cnt[SP_VBHOLE]) { rc = launch_wave<SP_VBHOLE>(eng, eng->qs[cur].q[SP_VBHOLE], h_cnt[SP_VBHOLE], heads + SP_VBHOLE, eng->qs[nxt]); if (rc) return rc; }
-            if (h_cnt[SP_COREHOLE]) { rc = launch_wave<SP_COREHOLE>(eng, eng->qs[cur].q[SP_COREHOLE], h_cnt[SP_COREHOLE], heads + SP_COREHOLE, eng->qs[nxt]); if (rc) return rc; }
-            if (h_cnt[SP_PHOTON]) { rc = launch_wave<SP_PHOTON>(eng, eng->qs[cur].q[SP_PHOTON], h_cnt[SP_PHOTON], heads + SP_PHOTON, eng->qs[nxt]); if (rc) return rc; }
+            CK(cudaMemsetAsync(eng->d_qcount + QC_HOT(nxt), 0, N_SPECIES * sizeof(uint32_t), eng->stream));
+            CK(cudaMemsetAsync(heads, 0, N_QUEUES * sizeof(uint32_t), eng->stream));
+            if (total) {        // one generation of the hot cascade
+                if (hot[SP_ELECTRON]) { rc = launch_wave<SP_ELECTRON, false>(eng, eng->qs[cur].q[SP_ELECTRON], 0, hot[SP_ELECTRON], heads + SP_ELECTRON, eng->qs[nxt]); if (rc) return rc; }
+                if (hot[SP_VBHOLE]) { rc = launch_wave<SP_VBHOLE, false>(eng, eng->qs[cur].q[SP_VBHOLE], 0, hot[SP_VBHOLE], heads + SP_VBHOLE, eng->qs[nxt]); if (rc) return rc; }
+                if (hot[SP_COREHOLE]) { rc = launch_wave<SP_COREHOLE, false>(eng, eng->qs[cur].q[SP_COREHOLE], 0, hot[SP_COREHOLE], heads + SP_COREHOLE, eng->qs[nxt]); if (rc) return rc; }
+                if (hot[SP_PHOTON]) { rc = launch_wave<SP_PHOTON, false>(eng, eng->qs[cur].q[SP_PHOTON], 0, hot[SP_PHOTON], heads + SP_PHOTON, eng->qs[nxt]); if (rc) return rc; }
+            } else {            // the hot cascade has died out: drain the cold queues (they may hand particles back)
+                if (cold[0] > cold_done[0]) { rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[0].q[Q_EL_COLD], cold_done[0], cold[0], heads + Q_EL_COLD, eng->qs[nxt]); if (rc) return rc; }
+                if (cold[1] > cold_done[1]) { rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[0].q[Q_VB_COLD], cold_done[1], cold[1], heads + Q_VB_COLD, eng->qs[nxt]); if (rc) return rc; }
+                cold_done[0] = cold[0]; cold_done[1] = cold[1];
+            }
             cur = nxt;
         }
         if (overflow) {
@@ -514,9 +564,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             CK(cudaMemcpyAsync(eng->d_counters, eng->d_counters_bak, n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, eng->stream));
             CK(cudaStreamSynchronize(eng->stream));
             eng->opt_cap_factor *= 2.0; eng->nb_alloc = 0;
-            queue_caps(eng, cap);
-            bytes_per_iter = 0; for (int s = 0; s < N_SPECIES; ++s) bytes_per_iter += 2.0 * cap[s] * (TRK_NCOL * 8 + 20);
-            int64_t nb_new = std::min<int64_t>(nb_max, std::max<int64_t>(1, (int64_t)((double)eng->opt_queue_bytes_max / bytes_per_iter)));
+            int64_t nb_new = std::min<int64_t>(nb_max, std::max<int64_t>(1, (int64_t)((double)eng->opt_queue_bytes_max / queue_bytes_per_iteration(eng))));
             rc = ensure_batch(eng, (uint32_t)nb_new);
             if (rc) return rc;
             nb_max = nb_new;
@@ -618,8 +666,8 @@ int trk3_mc_set_device_tallies(trk3_engine *eng, double *dptr) {
 // 0 electron wave, 1 valence-hole wave, 2 core-hole wave, 3 photon wave, 4 ion tracks, 5 finalize.
 int trk3_mc_kernel_times(trk3_engine *eng, double *ms, uint64_t *launches, int n) {
     if (!eng || !ms || !launches) return TRK3_E_INVALID;
-    for (int i = 0; i < n && i < N_SPECIES + 2; ++i) { ms[i] = eng->class_ms[i]; launches[i] = eng->class_launches[i]; }
-    return N_SPECIES + 2;
+    for (int i = 0; i < n && i < N_CLASSES; ++i) { ms[i] = eng->class_ms[i]; launches[i] = eng->class_launches[i]; }
+    return N_CLASSES;
 }
 
 void trk3_mc_destroy(trk3_engine *eng) {

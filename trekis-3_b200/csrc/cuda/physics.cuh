@@ -8,7 +8,8 @@
 //
 // All functions are templates over a context `C` that provides the side effects:
 //   c.p                      const DevP&  (tables, switches, time grid)
-//   c.push(species, rec)     append a new particle to the next-generation queue
+//   c.push(species, rec)     append a particle to a queue (the context routes it: hot/cold, see electron_is_cold)
+//   c.push_hot(species, rec) append to the queue of the full handlers regardless of the routing rule
 //   c.tally(id, idx, v)      add v to element idx of Out_* array `id` (block-private or global)
 //   c.add_u32(base, idx)     atomic ++ on a per-iteration integer histogram
 //   c.add_f64(base, idx, v)  atomic += on a per-iteration double array
@@ -429,6 +430,16 @@ TRK_HD void hole_parameters(const DevP &p, Rec &st, Rec &h, double Eh, double Eh
     if (h.Mass < 1e15 && h.Ehkin < p.cut_off) h.tn = 1.0e20;
 }
 
+// hand a newly created electron to the engine: Tot_Nel bookkeeping (the electron exists from the time interval of its
+// creation on, Monte_Carlo.f90:1026) + append to the queue
+template <class C>
+TRK_HD void push_new_electron(C &c, const Rec &e) {
+    const DevP &p = c.p;
+    c.count_electron();
+    c.add_u32(p.it.created, (size_t)(e.iter - p.batch_begin) * (p.Nt + 2) + interval_of(p, e.t0));
+    c.push(SP_ELECTRON, e);
+}
+
 // a new electron at (X,Y,Z,t) with energy Ee and direction (theta,phi): the block repeated in every handler
 // (:2212-2225, :2331-2342, :2606-2621, :2800-2813, :2921-2931); draws use the stream of the event particle `st`
 template <class C>
@@ -445,8 +456,7 @@ TRK_HD void emit_electron(C &c, Rec &st, uint64_t id, double Ee, double t, doubl
     if (e.E < p.cut_off) e.tn = 1.0e20;
     if (e.E < -1.0e-9 || trk_isnan(e.E)) c.error(err_code);
     e.id = id; e.ctr = 0; e.iter = st.iter; e.shell = -1;
-    c.count_electron();
-    c.push(SP_ELECTRON, e);
+    push_new_electron(c, e);
 }
 // a new hole in `shell` with total energy Eh and random direction (:2236-2240 and the identical blocks)
 template <class C>
@@ -607,19 +617,23 @@ TRK_HD void deposit_lattice(C &c, const Rec &r, int iv, double X, double Y, doub
 // in its post-collision state with a new tn.  `iv` is the time interval of the event.
 // ------------------------------------------------------------------------------------------------
 
-// Electron_Monte_Carlo, Monte_Carlo.f90:2253-2474
-template <class C>
-TRK_HD void electron_event(C &c, Rec &e, int iv, Cache &k) {
+// Electron_Monte_Carlo, Monte_Carlo.f90:2253-2474.
+// COLD = true is the instantiation for electrons below the lowest ionisation threshold (DevP::e_cold): the impact-
+// ionisation branch is not compiled in; in the (probability ~1e-16) case that the channel roulette still selects it,
+// the draw is given back and false is returned so that the caller re-queues the electron for the full handler.
+template <bool COLD, class C>
+TRK_HD bool electron_event_t(C &c, Rec &e, int iv, Cache &k) {
     const DevP &p = c.p;
     const double Eel = e.E;
     double IMFP = k.imfp, EMFP = k.emfp;                          // :2298-2299, already looked up for this energy
     double RN = rn(p, e);
+    if (COLD) { if (RN * (1.0 / IMFP + 1.0 / EMFP) < 1.0 / IMFP) { e.ctr--; return false; } }
     const double L = e.L, theta0 = e.theta, phi0 = e.phi;
     const double st0 = sin(theta0);
     const double X = e.X + L * st0 * sin(phi0), Y = e.Y + L * st0 * cos(phi0), Z = e.Z + L * cos(theta0);
     const double t_ev = e.tn;
     double dE, theta, phi;
-    if (RN * (1.0 / IMFP + 1.0 / EMFP) < 1.0 / IMFP) {          // inelastic: impact ionisation
+    if (!COLD && RN * (1.0 / IMFP + 1.0 / EMFP) < 1.0 / IMFP) { // inelastic: impact ionisation
         c.event(TRK3_EV_EL_INEL);
         int shell = which_shell(p, e, p.ei_E, p.lei_E, p.ei_L, p.lei_L, p.n_ei, Eel, k.lE);
         uint64_t id_e = child_id(p, e, 1), id_h = child_id(p, e, 2);
@@ -671,7 +685,10 @@ TRK_HD void electron_event(C &c, Rec &e, int iv, Cache &k) {
         }
     }
     if (e.E < -1.0e-9 || trk_isnan(e.E)) c.error(TRK3_ERR_22);
+    return true;
 }
+template <class C>
+TRK_HD void electron_event(C &c, Rec &e, int iv, Cache &k) { electron_event_t<false>(c, e, iv, k); }
 
 // check_hole_parameters, Monte_Carlo.f90:682-721: snap the scattered hole to a populated DOS level
 TRK_HD void check_hole_level(const DevP &p, double Eel, double &dE, double &Ehole, double *E_new_electron) {
@@ -692,9 +709,10 @@ TRK_HD void check_hole_level(const DevP &p, double Eel, double &dE, double &Ehol
     }
 }
 
-// Hole_Monte_Carlo, valence-band branch, Monte_Carlo.f90:2560-2738
-template <class C>
-TRK_HD void vbhole_event(C &c, Rec &h, int iv, Cache &k) {
+// Hole_Monte_Carlo, valence-band branch, Monte_Carlo.f90:2560-2738.  COLD: holes below DevP::h_cold, whose total
+// inelastic MFP is >= 1e16, can never take the impact-ionisation branch (it requires HIMFP < 1e15): not compiled in.
+template <bool COLD, class C>
+TRK_HD void vbhole_event_t(C &c, Rec &h, int iv, Cache &k) {
     const DevP &p = c.p;
     const double Eel = h.Ehkin;
     double HIMFP = k.imfp, HEMFP = k.emfp;                        // :2579-2580
@@ -704,7 +722,7 @@ TRK_HD void vbhole_event(C &c, Rec &h, int iv, Cache &k) {
     const double X = h.X + L * st0 * sin(phi0), Y = h.Y + L * st0 * cos(phi0), Z = h.Z + L * cos(theta0);
     const double t_ev = h.tn;
     double dE, Ehole, htheta1, hphi1;
-    if (RN * (1.0 / HIMFP + 1.0 / HEMFP) < 1.0 / HIMFP && HIMFP < 1e15) {
+    if (!COLD && RN * (1.0 / HIMFP + 1.0 / HEMFP) < 1.0 / HIMFP && HIMFP < 1e15) {
         c.event(TRK3_EV_VBH_INEL);
         int shell = which_shell(p, h, p.hi_E, p.lhi_E, p.hi_L, p.lhi_L, p.n_hi, Eel, k.lE);
         uint64_t id_e = child_id(p, h, 1), id_h = child_id(p, h, 2);
@@ -736,8 +754,7 @@ TRK_HD void vbhole_event(C &c, Rec &h, int iv, Cache &k) {
         e.id = id_e; e.ctr = 0; e.iter = h.iter; e.shell = -1;
         emit_hole(c, h, id_h, shell, dE - dE_cur, t_ev, X, Y, Z, TRK3_ERR_41);
         check_hole_level(p, Eel, dE, Ehole, &e.E);               // NB: tn/L of the new electron keep the pre-shift energy, as in the reference
-        c.count_electron();
-        c.push(SP_ELECTRON, e);
+        push_new_electron(c, e);
     } else {
         c.event(TRK3_EV_VBH_ELAST);
         HEMFP = elastic_total(tab_he(p), Eel, k);
@@ -752,6 +769,8 @@ TRK_HD void vbhole_event(C &c, Rec &h, int iv, Cache &k) {
     hole_parameters(p, h, h, Ehole + p.Egap, Eel, &k);
     if (h.Ehkin < -1.0e-9 || trk_isnan(h.Ehkin)) c.error(TRK3_ERR_20);
 }
+template <class C>
+TRK_HD void vbhole_event(C &c, Rec &h, int iv, Cache &k) { vbhole_event_t<false>(c, h, iv, k); }
 
 // count_for_Auger_shells / Choose_for_Auger_shell, Monte_Carlo.f90:1576-1647
 TRK_HD double auger_count(const DevP &p, double NRG, bool second_e) {
@@ -829,8 +848,7 @@ TRK_HD void corehole_event(C &c, Rec &h) {
             if (e.E < p.cut_off) e.tn = 1.0e20;
             if (e.E < -1.0e-9 || trk_isnan(e.E)) c.error(TRK3_ERR_23);
             e.id = id_e; e.ctr = 0; e.iter = h.iter; e.shell = -1;
-            c.count_electron();
-            c.push(SP_ELECTRON, e);
+            push_new_electron(c, e);
         } else {
             c.event(TRK3_EV_AUGER_FROZEN);
             h.t0 = t_ev; h.tn = 1e21;                             // :2828
@@ -927,56 +945,71 @@ TRK_HD void shi_history(C &c, uint32_t iter) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Histories: follow one particle from its record to Tim, depositing snapshots on the way.
-// Returns true when the record is finished, false when it must continue in another species queue.
+// Histories: follow one particle from its record towards Tim, depositing snapshots on the way.
 // `ig` = next grid index to snapshot (first i with t0 < tg(i)).
 // ------------------------------------------------------------------------------------------------
-template <class C>
-TRK_HD void begin_electron(C &c, const Rec &e, int &ig, Cache &k) {
-    const DevP &p = c.p;
+// Queue routing.  Particles that can no longer ionise ("cold": below the lowest threshold of their total inelastic
+// MFP table, or without any further collision before Tim) are handled by the cold kernels, whose code contains only
+// snapshots + elastic scattering; everything else goes through the full ("hot") handlers.
+TRK_HD bool electron_is_cold(const DevP &p, const Rec &e) { return e.E < p.e_cold || !(e.tn < p.Tim); }
+TRK_HD bool vbhole_is_cold(const DevP &p, const Rec &h) { return h.Ehkin < p.h_cold || !(h.tn < p.Tim); }
+
+enum StepStatus { ST_DONE = 0, ST_CONT = 1, ST_MOVE = 2, ST_MOVE_HOT = 3 };
+// ST_DONE: history finished.  ST_CONT: call again.  ST_MOVE: hand the record to push() (it now belongs to the other
+// temperature class or another species).  ST_MOVE_HOT: hand it to push_hot() (full handler required, see electron_event_t).
+
+TRK_HD void begin_electron(const DevP &p, const Rec &e, int &ig, Cache &k) {
     cache_electron(p, e.E, k);
     ig = interval_of(p, e.t0);
-    c.add_u32(p.it.created, (size_t)(e.iter - p.batch_begin) * (p.Nt + 2) + ig);    // Tot_Nel bookkeeping
 }
-// one step = snapshots spanned by the current free flight, then the collision at tn; false when history ended
-template <class C>
-TRK_HD bool step_electron(C &c, Rec &e, int &ig, Cache &k) {
+// one step = snapshots spanned by the current free flight, then the collision at tn
+template <bool COLD, class C>
+TRK_HD int step_electron(C &c, Rec &e, int &ig, Cache &k) {
     const DevP &p = c.p;
     while (ig <= p.Nt && p.tg[ig - 1] <= e.tn) { snapshot_electron(c, e, ig); ++ig; }
-    if (ig > p.Nt) return false;
-    electron_event(c, e, ig, k);
-    return true;
+    if (ig > p.Nt) return ST_DONE;
+    if (COLD) {
+        if (!(e.E < p.e_cold)) return ST_MOVE;
+        return electron_event_t<true>(c, e, ig, k) ? ST_CONT : ST_MOVE_HOT;
+    }
+    electron_event_t<false>(c, e, ig, k);
+    return (e.E < p.e_cold && e.tn < p.Tim) ? ST_MOVE : ST_CONT;
 }
 // a valence hole taken from a queue: the lookups of its kinetic energy (only mobile holes ever collide)
 TRK_HD void begin_vbhole(const DevP &p, const Rec &h, int &ig, Cache &k) {
     ig = interval_of(p, h.t0);
     if (h.tn < p.Tim) cache_vbhole(p, h.Ehkin, k);
 }
-template <class C>
-TRK_HD bool step_vbhole(C &c, Rec &h, int &ig, Cache &k) {
+template <bool COLD, class C>
+TRK_HD int step_vbhole(C &c, Rec &h, int &ig, Cache &k) {
     const DevP &p = c.p;
     while (ig <= p.Nt && p.tg[ig - 1] <= h.tn) { snapshot_hole(c, h, ig); ++ig; }
-    if (ig > p.Nt) return false;
-    vbhole_event(c, h, ig, k);
-    return true;
+    if (ig > p.Nt) return ST_DONE;
+    if (COLD) {
+        if (!(h.Ehkin < p.h_cold)) return ST_MOVE;
+        vbhole_event_t<true>(c, h, ig, k);
+        return (h.Ehkin < p.h_cold) ? ST_CONT : ST_MOVE;
+    }
+    vbhole_event_t<false>(c, h, ig, k);
+    return (h.Ehkin < p.h_cold && h.tn < p.Tim) ? ST_MOVE : ST_CONT;
 }
 // core hole: after a decay the hole may have hopped into the valence band -> continue as a VB hole (other queue)
 template <class C>
-TRK_HD bool step_corehole(C &c, Rec &h, int &ig) {
+TRK_HD int step_corehole(C &c, Rec &h, int &ig) {
     const DevP &p = c.p;
     while (ig <= p.Nt && p.tg[ig - 1] <= h.tn) { snapshot_hole(c, h, ig); ++ig; }
-    if (ig > p.Nt) return false;
+    if (ig > p.Nt) return ST_DONE;
     corehole_event(c, h);
-    if (h.shell == p.vb_shell) { c.push(SP_VBHOLE, h); return false; }
-    return true;
+    if (h.shell == p.vb_shell) { c.push(SP_VBHOLE, h); return ST_DONE; }
+    return ST_CONT;
 }
 template <class C>
-TRK_HD bool step_photon(C &c, Rec &ph, int &ig) {
+TRK_HD int step_photon(C &c, Rec &ph, int &ig) {
     const DevP &p = c.p;
     while (ig <= p.Nt && p.tg[ig - 1] <= ph.tn) { snapshot_photon(c, ph, ig); ++ig; }
-    if (ig > p.Nt) return false;
+    if (ig > p.Nt) return ST_DONE;
     photon_event(c, ph);
-    return false;
+    return ST_DONE;
 }
 
 }  // namespace trk3

@@ -97,12 +97,13 @@ class Engine:
         """Accumulate into a caller-owned device buffer (layout.total float64), e.g. tensor.data_ptr()."""
         self._check(_gpu().trk3_mc_set_device_tallies(self._h, C.c_void_p(int(device_ptr))), "set_device_tallies")
 
-    KERNEL_CLASSES = ("k_wave<electron>", "k_wave<vbhole>", "k_wave<corehole>", "k_wave<photon>", "k_shi", "finalize")
+    KERNEL_CLASSES = ("k_wave<electron,hot>", "k_wave<vbhole,hot>", "k_wave<corehole>", "k_wave<photon>", "k_shi", "finalize",
+                      "k_wave<electron,cold>", "k_wave<vbhole,cold>")
 
     def kernel_times(self):
-        ms = (C.c_double * 6)()
-        n = (C.c_uint64 * 6)()
-        _gpu().trk3_mc_kernel_times(self._h, ms, n, 6)
+        ms = (C.c_double * 8)()
+        n = (C.c_uint64 * 8)()
+        _gpu().trk3_mc_kernel_times(self._h, ms, n, 8)
         return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(self.KERNEL_CLASSES)}
 
     def device_tallies_ptr(self):
