@@ -640,12 +640,15 @@ struct MC {
         Check_size(Tot_Nel);
         Electron &el = All_electrons[Tot_Nel - 1]; Hole &ho = All_holes[Tot_Nel - 1];
         el.rng = rng.child(st, 1); ho.rng = rng.child(st, 2);
-        double dE_cur = Electron_recieves_E(dE, Nat_cur, Nshl_cur, st);
+        // stream convention of the engine (physics.cuh, shi_emit): the draws that create the electron come from the
+        // electron's own stream, those that create the hole from the hole's (the ion's chain does not depend on them)
+        Stream &se = el.rng, &sh = ho.rng;
+        double dE_cur = Electron_recieves_E(dE, Nat_cur, Nshl_cur, se);
         double theta, phi;
-        Update_electron_angles_SHI(SHI_loc, dE, theta, phi, st);
+        Update_electron_angles_SHI(SHI_loc, dE, theta, phi, se);
         double IMFP = Next_free_path_2d(dE_cur, T.ei_E, El_IMFP.data(), T.n_ei);
         double EMFP = Next_free_path_2d(dE_cur, T.ee_E, T.ee_L, T.n_ee);
-        RN = rng.rn(st);
+        RN = rng.rn(se);
         double MFP_tot = -std::log(RN) / (1.0 / IMFP + 1.0 / EMFP);
         double L = Impact_parameter(SHI_loc, dE);
         double X = SHI_loc.X + L * std::sin(phi), Y = SHI_loc.Y + L * std::cos(phi);
@@ -654,9 +657,9 @@ struct MC {
         cut_off_e(el);
         if (el.E < -1.0e-9 || std::isnan(el.E)) er[TRK3_ERR_20]++;
         double htheta, hphi;
-        Update_holes_angles_SHI(htheta, hphi, st);
+        Update_holes_angles_SHI(htheta, hphi, sh);
         ho.t0 = SHI_loc.t0; ho.X = X; ho.Y = Y; ho.Z = Z; ho.KOA = Nat_cur; ho.Shl = Nshl_cur; ho.theta = htheta; ho.phi = hphi;
-        Hole_parameters(ho, dE - dE_cur, st);
+        Hole_parameters(ho, dE - dE_cur, sh);
         cut_off_h(ho);
         if (ho.Ehkin < -1.0e-9 || std::isnan(ho.Ehkin)) er[TRK3_ERR_20]++;
     }

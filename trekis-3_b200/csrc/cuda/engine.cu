@@ -126,19 +126,49 @@ __device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned i
 // kernels
 // ------------------------------------------------------------------------------------------------
 // k_shi: the ion track of every iteration of the batch (SHI_Monte_Carlo, Monte_Carlo.f90:2153-2249).
-__global__ void __launch_bounds__(32) k_shi(QueueSet qout) {
+// k_shi: the ion tracks of the batch (SHI_Monte_Carlo, Monte_Carlo.f90:2153-2249).  An ion track is one serial chain
+// of a few hundred collisions (latency bound): one warp per ion with a single working lane, so that the chains of
+// different ions never serialise each other through divergence.  Only the ion's own part of a collision runs here; the
+// collision is written to a staging queue and its electron-hole pair is created by k_shi_emit, one thread per collision.
+#define SHI_WARPS 4
+__global__ void __launch_bounds__(32 * SHI_WARPS) k_shi(Queue stage, QueueSet qout) {
     __shared__ unsigned int s_cnt[S_NCNT];
     block_prologue(nullptr, s_cnt, 0);
     DevCtx c{c_p, qout, nullptr, s_cnt};
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < c_p.batch_n) shi_history(c, c_p.batch_begin + k);
+    const uint32_t k = blockIdx.x * SHI_WARPS + (threadIdx.x >> 5);
+    if ((threadIdx.x & 31) == 0 && k < c_p.batch_n) {
+        Rec s;
+        shi_begin(c_p, s, c_p.batch_begin + k);
+        while (s.tn < c_p.Tim) {
+            ShiEvent ev;
+            shi_step(c, s, ev);
+            const unsigned slot = atomicAdd(stage.count, 1u);
+            if (slot < stage.cap) {
+                stage.col[0][slot] = ev.dE; stage.col[1][slot] = ev.E_after; stage.col[2][slot] = ev.Zeff; stage.col[3][slot] = ev.t0; stage.col[4][slot] = ev.Z;
+                stage.shell[slot] = ev.shell; stage.ctr[slot] = ev.ctr0; stage.iter[slot] = ev.iter;
+            }
+        }
+    }
+    block_epilogue(c_p, nullptr, s_cnt);
+}
+__global__ void __launch_bounds__(256) k_shi_emit(Queue stage, QueueSet qout) {
+    __shared__ unsigned int s_cnt[S_NCNT];
+    block_prologue(nullptr, s_cnt, 0);
+    DevCtx c{c_p, qout, nullptr, s_cnt};
+    const uint32_t n = min(*stage.count, stage.cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        ShiEvent ev;
+        ev.dE = stage.col[0][i]; ev.E_after = stage.col[1][i]; ev.Zeff = stage.col[2][i]; ev.t0 = stage.col[3][i]; ev.Z = stage.col[4][i];
+        ev.shell = stage.shell[i]; ev.ctr0 = stage.ctr[i]; ev.iter = stage.iter[i];
+        shi_emit(c, ev);
+    }
     block_epilogue(c_p, nullptr, s_cnt);
 }
 
 // k_wave<SP, COLD>: records [first, n_in) of queue qin, histories followed with lane refill until they end or
 // have to change queue (hot -> cold when the particle can no longer ionise, core hole -> valence hole, ...).
 template <int SP, bool COLD>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
@@ -148,7 +178,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
     bool active = false, exhausted = false;
     Rec r;
     Cache k{};
-    int ig = 0;
+    int ig = 0, nev = 0;
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
         if (idle && !exhausted && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
@@ -161,7 +191,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
                 const uint32_t my = base + __popc(idle & ((1u << lane) - 1u));
                 if (my < n_in) {
                     load_rec(qin, my, r);
-                    active = true;
+                    active = true; nev = 0;
                     if (SP == SP_ELECTRON) begin_electron(c_p, r, ig, k);
                     else if (SP == SP_VBHOLE) begin_vbhole(c_p, r, ig, k);
                     else ig = interval_of(c_p, r.t0);
@@ -175,6 +205,9 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
             else if (SP == SP_VBHOLE) st = step_vbhole<COLD>(c, r, ig, k);
             else if (SP == SP_COREHOLE) st = step_corehole(c, r, ig);
             else st = step_photon(c, r, ig);
+            // time slicing of the hot cascade: after `slice` collisions the record goes back to the queue, so that the
+            // duration of a generation is bounded and the work of long histories spreads over many lanes
+            if (!COLD && st == ST_CONT && ++nev >= slice) st = ST_MOVE_HOT;
             if (st != ST_CONT) {
                 if (st == ST_MOVE) c.push(SP, r);
                 else if (st == ST_MOVE_HOT) c.push_hot(SP, r);
@@ -185,13 +218,86 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
     block_epilogue(c_p, s_tally, s_cnt);
 }
 
+// k_hot<SP>: one generation of carriers that can still ionise (SP = electron or valence hole).  The two collision
+// channels have very different code (an impact ionisation creates two particles), so letting every lane branch on its
+// own would make each warp pay for both channels in every round.  Instead the lanes of a warp vote: lanes whose
+// channel roulette selected the ionisation wait until `inel_min` of them have gathered (or nothing else is left to
+// do), and then take that path together; elastic collisions are never delayed.
+template <int SP> __device__ inline bool hot_roulette(const Cache &k, double RN) { return SP == SP_ELECTRON ? electron_roulette_inelastic(k, RN) : vbhole_roulette_inelastic(k, RN); }
+template <int SP, int MODE> __device__ inline void hot_event(DevCtx &c, Rec &r, int ig, Cache &k, double RN) {
+    if (SP == SP_ELECTRON) electron_event_t<MODE>(c, r, ig, k, RN); else vbhole_event_t<MODE>(c, r, ig, k, RN);
+}
+template <int SP> __device__ inline bool hot_leaves(const Rec &r) { return SP == SP_ELECTRON ? electron_leaves_hot(c_p, r) : vbhole_leaves_hot(c_p, r); }
+
+template <int SP>
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(Queue qin, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int inel_min) {
+    extern __shared__ double s_dyn[];
+    __shared__ unsigned int s_cnt[S_NCNT];
+    double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
+    block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? c_p.s_total : 0);
+    DevCtx c{c_p, qout, s_tally, s_cnt};
+    const int lane = threadIdx.x & 31;
+    bool active = false, exhausted = false, have_rn = false;
+    Rec r;
+    Cache k{};
+    double RN = 0.0;
+    int ig = 0, nev = 0;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle && !exhausted && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
+            const int nidle = __popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(head, (uint32_t)nidle);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + (uint32_t)nidle >= n_in) exhausted = true;
+            if (!active) {
+                const uint32_t my = base + __popc(idle & ((1u << lane) - 1u));
+                if (my < n_in) {
+                    load_rec(qin, my, r);
+                    active = true; nev = 0; have_rn = false;
+                    if (SP == SP_ELECTRON) begin_electron(c_p, r, ig, k); else begin_vbhole(c_p, r, ig, k);
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; continue; }
+        // snapshots of the current free flight, then the channel roulette of the collision that ends it
+        int want = 0;       // 1 elastic, 2 inelastic
+        if (active) {
+            while (ig <= c_p.Nt && c_p.tg[ig - 1] <= r.tn) { if (SP == SP_ELECTRON) snapshot_electron(c, r, ig); else snapshot_hole(c, r, ig); ++ig; }
+            if (ig > c_p.Nt) active = false;
+            else {
+                if (!have_rn) { RN = rn(c_p, r); have_rn = true; }
+                want = hot_roulette<SP>(k, RN) ? 2 : 1;
+            }
+        }
+        const unsigned m_in = __ballot_sync(0xffffffffu, want == 2), m_el = __ballot_sync(0xffffffffu, want == 1);
+        bool done_event = false;
+        if (m_in && (__popc(m_in) >= inel_min || !m_el)) {
+            if (want == 2) { hot_event<SP, EV_INELASTIC>(c, r, ig, k, RN); done_event = true; }
+        }
+        if (want == 1) { hot_event<SP, EV_ELASTIC>(c, r, ig, k, RN); done_event = true; }
+        if (done_event) {
+            have_rn = false;
+            // leave when the carrier can no longer ionise (cold queue) or, after `slice` collisions, back to the hot queue
+            if (hot_leaves<SP>(r)) { c.push(SP, r); active = false; }
+            else if (++nev >= slice && r.tn < c_p.Tim) { c.push_hot(SP, r); active = false; }
+        }
+    }
+    block_epilogue(c_p, s_tally, s_cnt);
+}
+
 __global__ void k_iter_prefix(FoldAux a) {
     const uint32_t il = blockIdx.x * blockDim.x + threadIdx.x;
     if (il < c_p.batch_n) iter_prefix(c_p, a, il);
 }
-__global__ void k_fold(FoldAux a, int64_t njobs) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < njobs) fold_job(c_p, a, j);
+__global__ void k_fold(FoldAux a, int64_t njobs) {      // one warp per output element
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= njobs) return;
+    double *dst;
+    double sum = fold_partial(c_p, a, j, threadIdx.x & 31, 32, &dst);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0 && dst) *dst += sum;
 }
 // companion arrays of the tables (TRK3_COMPANIONS): evaluated on the device so that they carry the device's log()
 __global__ void k_companion(double *dst, const double *src, size_t n, int op) {
@@ -216,7 +322,8 @@ struct trk3_engine {
     std::vector<void *> allocs;
     double nel_est = 1000.0;
     // options
-    int opt_batch = 1024, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 4096, opt_block = 256;
+    int opt_batch = 1024, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
+    int opt_hot_slice = 1 << 30, opt_inel_min = 12;
     double opt_cap_factor = 2.0;
     size_t opt_queue_bytes_max = (size_t)24 << 30;
     // per-batch resources
@@ -379,7 +486,27 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_i
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (grid < 1) grid = 1;
     const int pi = prof_begin(eng, COLD ? N_SPECIES + 2 + SP : SP);
-    k_wave<SP, COLD><<<grid, block, smem, eng->stream>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min);
+    k_wave<SP, COLD><<<grid, block, smem, eng->stream>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice);
+    prof_end(eng, pi);
+    CK(cudaGetLastError());
+    eng->launches++;
+    return TRK3_OK;
+}
+template <int SP>
+int launch_hot(trk3_engine *eng, const Queue &qin, uint32_t n, uint32_t *head, const QueueSet &qout) {
+    size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
+    int use_smem = eng->opt_use_smem;
+    const size_t smem_max = (size_t)eng->smem_optin - 1024;
+    if (smem > smem_max) { smem = 8; use_smem = 0; }
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_hot<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = eng->opt_blocks_per_sm;
+    const int block = eng->opt_block;
+    if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_hot<SP>, block, smem)); if (bps < 1) bps = 1; }
+    uint32_t want = (n + block - 1) / block;
+    uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
+    if (grid < 1) grid = 1;
+    const int pi = prof_begin(eng, SP);
+    k_hot<SP><<<grid, block, smem, eng->stream>>>(qin, n, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice, eng->opt_inel_min);
     prof_end(eng, pi);
     CK(cudaGetLastError());
     eng->launches++;
@@ -466,6 +593,8 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "cap_factor") { eng->opt_cap_factor = std::max(0.1, v); eng->nb_alloc = 0; }
     else if (k == "queue_gib") eng->opt_queue_bytes_max = (size_t)(v * (double)(1ull << 30));
     else if (k == "block") eng->opt_block = std::min(TRK_BLOCK_MAX, std::max(32, ((int)v / 32) * 32));
+    else if (k == "hot_slice") eng->opt_hot_slice = std::max(1, (int)v);
+    else if (k == "inel_min") eng->opt_inel_min = std::min(32, std::max(1, (int)v));
     else if (k == "max_generations") eng->opt_max_generations = std::max(1, (int)v);
     else if (k == "profile") { eng->opt_profile = (v != 0.0); for (auto &x : eng->class_ms) x = 0; for (auto &x : eng->class_launches) x = 0; }
     else return TRK3_E_INVALID;
@@ -524,10 +653,13 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         CK(cudaMemsetAsync(eng->d_f64, 0, eng->sl.f64_total * sizeof(double), eng->stream));
         CK(cudaMemsetAsync(eng->d_qcount, 0, QC_TOTAL * sizeof(uint32_t), eng->stream));
         { const int pi = prof_begin(eng, N_SPECIES);
-          k_shi<<<(nb + 31) / 32, 32, 0, eng->stream>>>(eng->qs[0]);
+          // collisions are staged in the (still unused) electron queue of the other generation
+          const Queue &stage = eng->qs[1].q[SP_ELECTRON];
+          k_shi<<<(nb + SHI_WARPS - 1) / SHI_WARPS, 32 * SHI_WARPS, 0, eng->stream>>>(stage, eng->qs[0]);
+          k_shi_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(stage, eng->qs[0]);
           prof_end(eng, pi); }
         CK(cudaGetLastError());
-        eng->launches++;
+        eng->launches += 2;
         int cur = 0;
         bool overflow = false;
         uint32_t cold_done[2] = {0, 0};
@@ -537,6 +669,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             CK(cudaStreamSynchronize(eng->stream));
             uint32_t *hot = h_cnt + QC_HOT(cur), *cold = h_cnt + QC_COLD;
             uint64_t total = 0;
+            if (gen == 0 && h_cnt[QC_HOT(1) + SP_ELECTRON] > eng->qs[1].q[SP_ELECTRON].cap) overflow = true;     // staged ion collisions
             for (int s = 0; s < N_SPECIES; ++s) { if (hot[s] > eng->qs[cur].q[s].cap) { overflow = true; hot[s] = eng->qs[cur].q[s].cap; } total += hot[s]; }
             for (int s = 0; s < 2; ++s) if (cold[s] > eng->qs[0].q[N_SPECIES + s].cap) { overflow = true; cold[s] = eng->qs[0].q[N_SPECIES + s].cap; }
             if (overflow) break;
@@ -547,8 +680,8 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             CK(cudaMemsetAsync(eng->d_qcount + QC_HOT(nxt), 0, N_SPECIES * sizeof(uint32_t), eng->stream));
             CK(cudaMemsetAsync(heads, 0, N_QUEUES * sizeof(uint32_t), eng->stream));
             if (total) {        // one generation of the hot cascade
-                if (hot[SP_ELECTRON]) { rc = launch_wave<SP_ELECTRON, false>(eng, eng->qs[cur].q[SP_ELECTRON], 0, hot[SP_ELECTRON], heads + SP_ELECTRON, eng->qs[nxt]); if (rc) return rc; }
-                if (hot[SP_VBHOLE]) { rc = launch_wave<SP_VBHOLE, false>(eng, eng->qs[cur].q[SP_VBHOLE], 0, hot[SP_VBHOLE], heads + SP_VBHOLE, eng->qs[nxt]); if (rc) return rc; }
+                if (hot[SP_ELECTRON]) { rc = launch_hot<SP_ELECTRON>(eng, eng->qs[cur].q[SP_ELECTRON], hot[SP_ELECTRON], heads + SP_ELECTRON, eng->qs[nxt]); if (rc) return rc; }
+                if (hot[SP_VBHOLE]) { rc = launch_hot<SP_VBHOLE>(eng, eng->qs[cur].q[SP_VBHOLE], hot[SP_VBHOLE], heads + SP_VBHOLE, eng->qs[nxt]); if (rc) return rc; }
                 if (hot[SP_COREHOLE]) { rc = launch_wave<SP_COREHOLE, false>(eng, eng->qs[cur].q[SP_COREHOLE], 0, hot[SP_COREHOLE], heads + SP_COREHOLE, eng->qs[nxt]); if (rc) return rc; }
                 if (hot[SP_PHOTON]) { rc = launch_wave<SP_PHOTON, false>(eng, eng->qs[cur].q[SP_PHOTON], 0, hot[SP_PHOTON], heads + SP_PHOTON, eng->qs[nxt]); if (rc) return rc; }
             } else {            // the hot cascade has died out: drain the cold queues (they may hand particles back)
@@ -574,7 +707,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         k_iter_prefix<<<(nb + 127) / 128, 128, 0, eng->stream>>>(eng->fa);
         CK(cudaGetLastError());
         const int64_t njobs = fold_num_jobs(eng->hp);
-        k_fold<<<(unsigned)((njobs + 127) / 128), 128, 0, eng->stream>>>(eng->fa, njobs);
+        k_fold<<<(unsigned)((njobs * 32 + 255) / 256), 256, 0, eng->stream>>>(eng->fa, njobs);
         prof_end(eng, pf);
         CK(cudaGetLastError());
         eng->launches += 2;

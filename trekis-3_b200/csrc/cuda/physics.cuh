@@ -441,7 +441,8 @@ TRK_HD void push_new_electron(C &c, const Rec &e) {
 }
 
 // a new electron at (X,Y,Z,t) with energy Ee and direction (theta,phi): the block repeated in every handler
-// (:2212-2225, :2331-2342, :2606-2621, :2800-2813, :2921-2931); draws use the stream of the event particle `st`
+// (:2212-2225, :2331-2342, :2606-2621, :2800-2813, :2921-2931); draws use the stream `st`: the event particle's, or
+// (pairs created by the ion, see shi_emit) the new particle's own stream, which it then continues
 template <class C>
 TRK_HD void emit_electron(C &c, Rec &st, uint64_t id, double Ee, double t, double X, double Y, double Z, double theta, double phi, int err_code) {
     const DevP &p = c.p;
@@ -455,7 +456,7 @@ TRK_HD void emit_electron(C &c, Rec &st, uint64_t id, double Ee, double t, doubl
     e.tn = next_time(t, vel_electron(Ee), MFP_tot);
     if (e.E < p.cut_off) e.tn = 1.0e20;
     if (e.E < -1.0e-9 || trk_isnan(e.E)) c.error(err_code);
-    e.id = id; e.ctr = 0; e.iter = st.iter; e.shell = -1;
+    e.id = id; e.ctr = (st.id == id) ? st.ctr : 0; e.iter = st.iter; e.shell = -1;
     push_new_electron(c, e);
 }
 // a new hole in `shell` with total energy Eh and random direction (:2236-2240 and the identical blocks)
@@ -466,8 +467,9 @@ TRK_HD void emit_hole(C &c, Rec &st, uint64_t id, int shell, double Eh, double t
     double htheta, hphi;
     random_angles(p, st, htheta, hphi);
     h.E = 0.0; h.Ehkin = 0.0; h.Mass = 1.0e30; h.t0 = t; h.tn = 1.0e21; h.X = X; h.Y = Y; h.Z = Z; h.L = 1.0e30; h.theta = htheta; h.phi = hphi;
-    h.shell = shell; h.id = id; h.ctr = 0; h.iter = st.iter;
+    h.shell = shell; h.id = id; h.iter = st.iter;
     hole_parameters(p, st, h, Eh, 0.0);
+    h.ctr = (st.id == id) ? st.ctr : 0;
     if (h.Ehkin < -1.0e-9 || trk_isnan(h.Ehkin)) c.error(err_code);
     c.push(shell == p.vb_shell ? SP_VBHOLE : SP_COREHOLE, h);
 }
@@ -618,22 +620,23 @@ TRK_HD void deposit_lattice(C &c, const Rec &r, int iv, double X, double Y, doub
 // ------------------------------------------------------------------------------------------------
 
 // Electron_Monte_Carlo, Monte_Carlo.f90:2253-2474.
-// COLD = true is the instantiation for electrons below the lowest ionisation threshold (DevP::e_cold): the impact-
-// ionisation branch is not compiled in; in the (probability ~1e-16) case that the channel roulette still selects it,
-// the draw is given back and false is returned so that the caller re-queues the electron for the full handler.
-template <bool COLD, class C>
-TRK_HD bool electron_event_t(C &c, Rec &e, int iv, Cache &k) {
+// RN is the first draw of the collision (the channel roulette, :2301), made by the caller.
+// MODE selects what is compiled in: EV_ANY = both channels (run-time roulette), EV_ELASTIC / EV_INELASTIC = one
+// channel only, for kernels whose warps are uniform in the event type (the caller has evaluated the roulette with
+// electron_roulette_inelastic).
+enum EventMode { EV_ANY = 0, EV_ELASTIC = 1, EV_INELASTIC = 2 };
+TRK_HD bool electron_roulette_inelastic(const Cache &k, double RN) { return RN * (1.0 / k.imfp + 1.0 / k.emfp) < 1.0 / k.imfp; }
+template <int MODE, class C>
+TRK_HD void electron_event_t(C &c, Rec &e, int iv, Cache &k, double RN) {
     const DevP &p = c.p;
     const double Eel = e.E;
     double IMFP = k.imfp, EMFP = k.emfp;                          // :2298-2299, already looked up for this energy
-    double RN = rn(p, e);
-    if (COLD) { if (RN * (1.0 / IMFP + 1.0 / EMFP) < 1.0 / IMFP) { e.ctr--; return false; } }
     const double L = e.L, theta0 = e.theta, phi0 = e.phi;
     const double st0 = sin(theta0);
     const double X = e.X + L * st0 * sin(phi0), Y = e.Y + L * st0 * cos(phi0), Z = e.Z + L * cos(theta0);
     const double t_ev = e.tn;
     double dE, theta, phi;
-    if (!COLD && RN * (1.0 / IMFP + 1.0 / EMFP) < 1.0 / IMFP) { // inelastic: impact ionisation
+    if (MODE == EV_INELASTIC || (MODE == EV_ANY && electron_roulette_inelastic(k, RN))) {     // inelastic: impact ionisation
         c.event(TRK3_EV_EL_INEL);
         int shell = which_shell(p, e, p.ei_E, p.lei_E, p.ei_L, p.lei_L, p.n_ei, Eel, k.lE);
         uint64_t id_e = child_id(p, e, 1), id_h = child_id(p, e, 2);
@@ -685,10 +688,7 @@ TRK_HD bool electron_event_t(C &c, Rec &e, int iv, Cache &k) {
         }
     }
     if (e.E < -1.0e-9 || trk_isnan(e.E)) c.error(TRK3_ERR_22);
-    return true;
 }
-template <class C>
-TRK_HD void electron_event(C &c, Rec &e, int iv, Cache &k) { electron_event_t<false>(c, e, iv, k); }
 
 // check_hole_parameters, Monte_Carlo.f90:682-721: snap the scattered hole to a populated DOS level
 TRK_HD void check_hole_level(const DevP &p, double Eel, double &dE, double &Ehole, double *E_new_electron) {
@@ -709,20 +709,20 @@ TRK_HD void check_hole_level(const DevP &p, double Eel, double &dE, double &Ehol
     }
 }
 
-// Hole_Monte_Carlo, valence-band branch, Monte_Carlo.f90:2560-2738.  COLD: holes below DevP::h_cold, whose total
-// inelastic MFP is >= 1e16, can never take the impact-ionisation branch (it requires HIMFP < 1e15): not compiled in.
-template <bool COLD, class C>
-TRK_HD void vbhole_event_t(C &c, Rec &h, int iv, Cache &k) {
+// Hole_Monte_Carlo, valence-band branch, Monte_Carlo.f90:2560-2738.  RN = first draw (channel roulette, :2582); MODE as
+// for electrons.  Holes below DevP::h_cold have a total inelastic MFP >= 1e16 and can never ionise (needs HIMFP < 1e15).
+TRK_HD bool vbhole_roulette_inelastic(const Cache &k, double RN) { return RN * (1.0 / k.imfp + 1.0 / k.emfp) < 1.0 / k.imfp && k.imfp < 1e15; }
+template <int MODE, class C>
+TRK_HD void vbhole_event_t(C &c, Rec &h, int iv, Cache &k, double RN) {
     const DevP &p = c.p;
     const double Eel = h.Ehkin;
     double HIMFP = k.imfp, HEMFP = k.emfp;                        // :2579-2580
-    double RN = rn(p, h);
     const double L = h.L, theta0 = h.theta, phi0 = h.phi;
     const double st0 = sin(theta0);
     const double X = h.X + L * st0 * sin(phi0), Y = h.Y + L * st0 * cos(phi0), Z = h.Z + L * cos(theta0);
     const double t_ev = h.tn;
     double dE, Ehole, htheta1, hphi1;
-    if (!COLD && RN * (1.0 / HIMFP + 1.0 / HEMFP) < 1.0 / HIMFP && HIMFP < 1e15) {
+    if (MODE == EV_INELASTIC || (MODE == EV_ANY && vbhole_roulette_inelastic(k, RN))) {
         c.event(TRK3_EV_VBH_INEL);
         int shell = which_shell(p, h, p.hi_E, p.lhi_E, p.hi_L, p.lhi_L, p.n_hi, Eel, k.lE);
         uint64_t id_e = child_id(p, h, 1), id_h = child_id(p, h, 2);
@@ -769,8 +769,7 @@ TRK_HD void vbhole_event_t(C &c, Rec &h, int iv, Cache &k) {
     hole_parameters(p, h, h, Ehole + p.Egap, Eel, &k);
     if (h.Ehkin < -1.0e-9 || trk_isnan(h.Ehkin)) c.error(TRK3_ERR_20);
 }
-template <class C>
-TRK_HD void vbhole_event(C &c, Rec &h, int iv, Cache &k) { vbhole_event_t<false>(c, h, iv, k); }
+
 
 // count_for_Auger_shells / Choose_for_Auger_shell, Monte_Carlo.f90:1576-1647
 TRK_HD double auger_count(const DevP &p, double NRG, bool second_e) {
@@ -901,47 +900,77 @@ TRK_HD void photon_event(C &c, Rec &ph) {
     ph.E = 0.0; ph.t0 = 1.0e27; ph.tn = 1.0e27;
 }
 
-// SHI_Monte_Carlo + the ion part of Monte_Carlo_modelling (:548-570, :593-597, :2153-2249):
-// the whole trajectory of the ion of one iteration; emits an (electron, hole) pair per collision.
-template <class C>
-TRK_HD void shi_history(C &c, uint32_t iter) {
-    const DevP &p = c.p;
-    Rec s;      // E, t0, tn, X, Y, Z, L as the Ion; Mass/Zeff in locals
+// SHI_Monte_Carlo + the ion part of Monte_Carlo_modelling (:548-570, :593-597, :2153-2249).
+// The trajectory of an ion is one serial chain of collisions; everything that does not feed back into the chain (the
+// creation of the electron-hole pair of a collision) is split off so that it can run in parallel over all collisions
+// of all ions:  shi_begin / shi_step = the ion's own part, producing one ShiEvent per collision;  shi_emit = the pair.
+// Stream convention: the ion's stream gives the ion's draws and the children's ids; the draws that create the
+// electron (level in the band, azimuth, first free path) come from the new electron's own stream and those that
+// create the hole (direction, first free path / decay time) from the new hole's own stream.
+struct ShiEvent {
+    double dE;          // transferred energy
+    double E_after;     // ion energy after the collision (Update_electron_angles_SHI uses the updated ion)
+    double Zeff;        // equilibrium charge after the collision (Impact_parameter)
+    double t0, Z;       // time and depth of the collision
+    int32_t shell;
+    uint32_t ctr0;      // position of the ion's stream at the creation of the pair (children's ids)
+    uint32_t iter;
+};
+TRK_HD void shi_begin(const DevP &p, Rec &s, uint32_t iter) {
     s.E = p.ion_E; s.t0 = 0.0; s.tn = 0.0; s.X = 0.0; s.Y = 0.0; s.Z = 0.0; s.L = 0.0; s.theta = 0.0; s.phi = 0.0; s.Ehkin = 0.0; s.Mass = p.ion_mass;
     s.id = 0; s.ctr = 0; s.iter = iter; s.shell = -1;
     const double MSHI = p.ion_mass * TRK_MP;
-    double Zeff = p.ion_Zeff0;
-    {
-        double lam = nfp_2d(tab_shi_tot(p), s.E, log(s.E));
-        double RN = rn(p, s);
-        s.L = -lam * log(RN);
-        s.tn = next_time(s.t0, sqrt(2.0 * s.E * TRK_GE / MSHI), s.L);
-    }
-    while (s.tn < p.Tim) {
-        c.event(TRK3_EV_SHI);
-        const double lEs = log(s.E);
-        int shell = which_shell(p, s, p.shi_E, p.lshi_E, p.shi_L, p.lshi_L, p.n_shi, s.E, lEs);
-        double dE = shi_energy_transfer(p, s, shell);
-        double lam = nfp_2d(tab_shi_tot(p), s.E, lEs);
-        double RN = rn(p, s);
-        double SHI_IMFP = -lam * log(RN);
-        double Z = s.Z + s.L;
-        s.E = s.E - dE; s.t0 = s.tn; s.Z = Z; s.L = SHI_IMFP;
-        s.tn = next_time(s.t0, sqrt(2.0 * s.E * TRK_GE / MSHI), SHI_IMFP);
-        Zeff = shi_zeff(p, s.E);
-        uint64_t id_e = child_id(p, s, 1), id_h = child_id(p, s, 2);
-        double dE_cur = electron_receives_E(c, s, dE, shell);
-        // Update_electron_angles_SHI (:1170-1187) with the UPDATED ion energy
-        double theta = (s.E <= 0.0) ? TRK_PI / 2.0 : acos(sqrt((MSHI + TRK_ME) * (MSHI + TRK_ME) / (4.0 * MSHI * TRK_ME) * dE / s.E));
-        double phi; { double r2 = rn(p, s); phi = 2.0 * TRK_PI * r2; }
-        // Impact_parameter (:1113-1126) is evaluated after the electron's free path is sampled (:2212-2218)
-        double A = 1.0 + MSHI / TRK_ME;
-        double b = TRK_A0 * Zeff * TRK_RY / s.E * sqrt(4.0 * s.E / dE * MSHI / TRK_ME - A * A);
-        double X = s.X + b * sin(phi), Y = s.Y + b * cos(phi);
-        emit_electron(c, s, id_e, dE_cur, s.t0, X, Y, Z, theta, phi, TRK3_ERR_20);
-        emit_hole(c, s, id_h, shell, dE - dE_cur, s.t0, X, Y, Z, TRK3_ERR_20);
-        if (s.Z >= p.layer) s.tn = 1e16;                          // :597 the ion has left the layer
-    }
+    double lam = nfp_2d(tab_shi_tot(p), s.E, log(s.E));
+    double RN = rn(p, s);
+    s.L = -lam * log(RN);
+    s.tn = next_time(s.t0, sqrt(2.0 * s.E * TRK_GE / MSHI), s.L);
+}
+// one collision of the ion at s.tn (< Tim); leaves the ion in flight towards its next collision
+template <class C>
+TRK_HD void shi_step(C &c, Rec &s, ShiEvent &ev) {
+    const DevP &p = c.p;
+    const double MSHI = p.ion_mass * TRK_MP;
+    c.event(TRK3_EV_SHI);
+    const double lEs = log(s.E);
+    int shell = which_shell(p, s, p.shi_E, p.lshi_E, p.shi_L, p.lshi_L, p.n_shi, s.E, lEs);
+    double dE = shi_energy_transfer(p, s, shell);
+    double lam = nfp_2d(tab_shi_tot(p), s.E, lEs);
+    double RN = rn(p, s);
+    double SHI_IMFP = -lam * log(RN);
+    double Z = s.Z + s.L;
+    s.E = s.E - dE; s.t0 = s.tn; s.Z = Z; s.L = SHI_IMFP;
+    s.tn = next_time(s.t0, sqrt(2.0 * s.E * TRK_GE / MSHI), SHI_IMFP);
+    ev.dE = dE; ev.E_after = s.E; ev.Zeff = shi_zeff(p, s.E); ev.t0 = s.t0; ev.Z = Z; ev.shell = shell; ev.ctr0 = s.ctr; ev.iter = s.iter;
+    s.ctr += 2;                                                   // the two child ids
+    if (s.Z >= p.layer) s.tn = 1e16;                              // :597 the ion has left the layer
+}
+// the (electron, hole) pair of one ion collision, :2198-2247
+template <class C>
+TRK_HD void shi_emit(C &c, const ShiEvent &ev) {
+    const DevP &p = c.p;
+    const double MSHI = p.ion_mass * TRK_MP;
+    Rec ion; ion.id = 0; ion.ctr = ev.ctr0; ion.iter = ev.iter;
+    const uint64_t id_e = child_id(p, ion, 1), id_h = child_id(p, ion, 2);
+    Rec se; se.id = id_e; se.ctr = 0; se.iter = ev.iter;          // the new electron's stream
+    Rec sh; sh.id = id_h; sh.ctr = 0; sh.iter = ev.iter;          // the new hole's stream
+    const double dE = ev.dE;
+    double dE_cur = electron_receives_E(c, se, dE, ev.shell);
+    // Update_electron_angles_SHI (:1170-1187) with the UPDATED ion energy
+    double theta = (ev.E_after <= 0.0) ? TRK_PI / 2.0 : acos(sqrt((MSHI + TRK_ME) * (MSHI + TRK_ME) / (4.0 * MSHI * TRK_ME) * dE / ev.E_after));
+    double phi; { double r2 = rn(p, se); phi = 2.0 * TRK_PI * r2; }
+    // Impact_parameter (:1113-1126); the ion moves along the Z axis (X = Y = 0)
+    double A = 1.0 + MSHI / TRK_ME;
+    double b = TRK_A0 * ev.Zeff * TRK_RY / ev.E_after * sqrt(4.0 * ev.E_after / dE * MSHI / TRK_ME - A * A);
+    double X = b * sin(phi), Y = b * cos(phi);
+    emit_electron(c, se, id_e, dE_cur, ev.t0, X, Y, ev.Z, theta, phi, TRK3_ERR_20);
+    emit_hole(c, sh, id_h, ev.shell, dE - dE_cur, ev.t0, X, Y, ev.Z, TRK3_ERR_20);
+}
+// the whole trajectory of the ion of one iteration (serial form, used by the CPU emulation)
+template <class C>
+TRK_HD void shi_history(C &c, uint32_t iter) {
+    Rec s;
+    shi_begin(c.p, s, iter);
+    while (s.tn < c.p.Tim) { ShiEvent ev; shi_step(c, s, ev); shi_emit(c, ev); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -954,6 +983,9 @@ TRK_HD void shi_history(C &c, uint32_t iter) {
 TRK_HD bool electron_is_cold(const DevP &p, const Rec &e) { return e.E < p.e_cold || !(e.tn < p.Tim); }
 TRK_HD bool vbhole_is_cold(const DevP &p, const Rec &h) { return h.Ehkin < p.h_cold || !(h.tn < p.Tim); }
 
+TRK_HD bool electron_leaves_hot(const DevP &p, const Rec &e) { return e.E < p.e_cold && e.tn < p.Tim; }
+TRK_HD bool vbhole_leaves_hot(const DevP &p, const Rec &h) { return h.Ehkin < p.h_cold && h.tn < p.Tim; }
+
 enum StepStatus { ST_DONE = 0, ST_CONT = 1, ST_MOVE = 2, ST_MOVE_HOT = 3 };
 // ST_DONE: history finished.  ST_CONT: call again.  ST_MOVE: hand the record to push() (it now belongs to the other
 // temperature class or another species).  ST_MOVE_HOT: hand it to push_hot() (full handler required, see electron_event_t).
@@ -962,17 +994,22 @@ TRK_HD void begin_electron(const DevP &p, const Rec &e, int &ig, Cache &k) {
     cache_electron(p, e.E, k);
     ig = interval_of(p, e.t0);
 }
-// one step = snapshots spanned by the current free flight, then the collision at tn
+// one step = snapshots spanned by the current free flight, then the collision at tn.  A record may only change
+// queue in a state where the snapshots of (t0, tn] are still all to be taken: the consumer restarts from t0.
 template <bool COLD, class C>
 TRK_HD int step_electron(C &c, Rec &e, int &ig, Cache &k) {
     const DevP &p = c.p;
+    double RN = 0.0;
+    if (COLD && e.tn < p.tg[p.Nt - 1]) {                          // a collision is pending: is it really an elastic one?
+        if (!(e.E < p.e_cold)) return ST_MOVE;
+        RN = rn(p, e);
+        if (electron_roulette_inelastic(k, RN)) { e.ctr--; return ST_MOVE_HOT; }      // probability ~1e-16 (IMFP >= 1e16)
+    }
     while (ig <= p.Nt && p.tg[ig - 1] <= e.tn) { snapshot_electron(c, e, ig); ++ig; }
     if (ig > p.Nt) return ST_DONE;
-    if (COLD) {
-        if (!(e.E < p.e_cold)) return ST_MOVE;
-        return electron_event_t<true>(c, e, ig, k) ? ST_CONT : ST_MOVE_HOT;
-    }
-    electron_event_t<false>(c, e, ig, k);
+    if (COLD) { electron_event_t<EV_ELASTIC>(c, e, ig, k, RN); return ST_CONT; }
+    RN = rn(p, e);
+    electron_event_t<EV_ANY>(c, e, ig, k, RN);
     return (e.E < p.e_cold && e.tn < p.Tim) ? ST_MOVE : ST_CONT;
 }
 // a valence hole taken from a queue: the lookups of its kinetic energy (only mobile holes ever collide)
@@ -983,14 +1020,14 @@ TRK_HD void begin_vbhole(const DevP &p, const Rec &h, int &ig, Cache &k) {
 template <bool COLD, class C>
 TRK_HD int step_vbhole(C &c, Rec &h, int &ig, Cache &k) {
     const DevP &p = c.p;
+    if (COLD && h.tn < p.tg[p.Nt - 1] && !(h.Ehkin < p.h_cold)) return ST_MOVE;
     while (ig <= p.Nt && p.tg[ig - 1] <= h.tn) { snapshot_hole(c, h, ig); ++ig; }
     if (ig > p.Nt) return ST_DONE;
     if (COLD) {
-        if (!(h.Ehkin < p.h_cold)) return ST_MOVE;
-        vbhole_event_t<true>(c, h, ig, k);
+        vbhole_event_t<EV_ELASTIC>(c, h, ig, k, rn(p, h));
         return (h.Ehkin < p.h_cold) ? ST_CONT : ST_MOVE;
     }
-    vbhole_event_t<false>(c, h, ig, k);
+    vbhole_event_t<EV_ANY>(c, h, ig, k, rn(p, h));
     return (h.Ehkin < p.h_cold && h.tn < p.Tim) ? ST_MOVE : ST_CONT;
 }
 // core hole: after a decay the hole may have hopped into the valence band -> continue as a VB hole (other queue)
