@@ -71,6 +71,12 @@ extern "C" int trk3_emul_run(const trk3_config *cfg, const trk3_tables *tab, int
 #define X(dst, src, n, op) { comp.emplace_back((size_t)(n)); std::vector<double> &v = comp.back(); for (size_t i = 0; i < v.size(); ++i) v[i] = companion_value((src)[i], op); p.dst = v.data(); }
     TRK3_COMPANIONS(X, p, T, NS)
 #undef X
+    std::vector<uint16_t> luts[N_LUT];
+#define X(id, E, n) { build_lut(E, n, luts[id], p.lut[id].l0, p.lut[id].scale); p.lut[id].lut = luts[id].data(); }
+    TRK3_LUT_GRIDS(X, T)
+#undef X
+    p.dos_inv_step = uniform_inv_step(T.dos_E, T.n_dos);
+    for (int sh = 0; sh < T.n_shells; ++sh) shi_threshold(T.dshi_E + T.dshi_off[sh], T.dshi_L + T.dshi_off[sh], (int)(T.dshi_off[sh + 1] - T.dshi_off[sh]), T.shell_Ip[sh], p.shi_Mtemp[sh], p.shi_dL[sh]);
     cold_range(p.ei_E, p.ei_tot, p.n_ei, p.e_cold, p.e_imfp_cold);
     cold_range(p.hi_E, p.hi_tot, p.n_hi, p.h_cold, p.h_imfp_cold);
     p.tally = tallies;

@@ -566,6 +566,12 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
 #undef X
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(eng->stream));
+        std::vector<uint16_t> lut;
+#define X(id, E, n) { build_lut(E, n, lut, p.lut[id].l0, p.lut[id].scale); rc = dev_upload(eng, &p.lut[id].lut, lut.data(), lut.size()); if (rc) return rc; }
+        TRK3_LUT_GRIDS(X, T)
+#undef X
+        p.dos_inv_step = uniform_inv_step(T.dos_E, T.n_dos);
+    for (int sh = 0; sh < T.n_shells; ++sh) shi_threshold(T.dshi_E + T.dshi_off[sh], T.dshi_L + T.dshi_off[sh], (int)(T.dshi_off[sh + 1] - T.dshi_off[sh]), T.shell_Ip[sh], p.shi_Mtemp[sh], p.shi_dL[sh]);
         cold_range(tab->ei_E, tot.ei_tot.data(), tab->n_ei, p.e_cold, p.e_imfp_cold);
         cold_range(tab->hi_E, tot.hi_tot.data(), tab->n_hi, p.h_cold, p.h_imfp_cold);
     }

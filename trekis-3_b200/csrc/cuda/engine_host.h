@@ -41,6 +41,32 @@ inline bool cold_range(const double *E, const double *L, int N, double &e_cold, 
     return true;
 }
 
+// Search accelerator of one energy grid (GridLut): bin b covers log(E) in [l0 + b/scale, l0 + (b+1)/scale)
+inline void build_lut(const double *E, int N, std::vector<uint16_t> &lut, double &l0, double &scale) {
+    lut.assign(TRK_NLUT, 1);
+    l0 = 0.0; scale = 0.0;
+    if (N < 2 || !(E[0] > 0.0) || N > 65535) return;               // scale = 0: every query starts its scan at index 1
+    l0 = std::log(E[0]);
+    const double l1 = std::log(E[N - 1]);
+    if (!(l1 > l0)) return;
+    scale = (double)TRK_NLUT / (l1 - l0);
+    int j = 1;
+    for (int b = 0; b < TRK_NLUT; ++b) {
+        const double edge = l0 + (double)b / scale;                  // lower edge of the bin
+        while (j < N - 1 && std::log(E[j]) <= edge) ++j;            // j = number of grid points <= edge (clamped to [1, N-1])
+        lut[b] = (uint16_t)j;
+    }
+}
+inline double uniform_inv_step(const double *E, int N) {
+    if (N < 3) return 0.0;
+    const double step = (E[N - 1] - E[0]) / (double)(N - 1);
+    if (!(step > 0.0) || E[0] != 0.0) return 0.0;
+    for (int i = 0; i < N; ++i) if (std::fabs(E[i] - step * i) > 1e-6 * step) return 0.0;
+    return 1.0 / step;
+}
+#define TRK3_LUT_GRIDS(X, T) X(LUT_EI, T.ei_E, T.n_ei) X(LUT_EE, T.ee_E, T.n_ee) X(LUT_HI, T.hi_E, T.n_hi) X(LUT_HE, T.he_E, T.n_he) \
+    X(LUT_PH, T.ph_E, T.n_ph) X(LUT_SHI, T.shi_E, T.n_shi)
+
 // Companion arrays of the tables (natural logarithms, reciprocals): X(dst, src, n, op) with op 0 = log(src),
 // 1 = 1/src, 2 = log(1/src).  The CUDA engine evaluates them on the device, the emulation on the host.
 #define TRK3_COMPANIONS(X, p, T, NS)                                                                              \

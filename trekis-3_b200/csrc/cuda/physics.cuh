@@ -134,8 +134,22 @@ TRK_HD double interp1(double E1, double E2, double S1, double S2, double En) {
     return S1 + (S2 - S1) / (E2 - E1) * (En - E1);
 }
 
-// A 1-D mean-free-path table with its log companion
-struct Tab { const double *E, *L, *lE, *lL; int N; };
+// Find_in_monotonous_1D_array through the direct-index accelerator: lv = log(v).  A strictly increasing array has
+// exactly one index n with A[n-2] <= v < A[n-1]; the scan from the looked-up start finds it, as the bisection does.
+TRK_HD int find_lut(const double *A, int N, const GridLut &g, double v, double lv) {
+    if (v < A[0]) return 1;
+    if (v >= A[N - 1]) return N;
+    int b = (int)((lv - g.l0) * g.scale);
+    b = (b < 0) ? 0 : ((b >= TRK_NLUT) ? TRK_NLUT - 1 : b);
+    int j = g.lut[b];                          // in [1, N-1]
+    while (j < N - 1 && A[j] <= v) ++j;
+    while (j > 1 && A[j - 1] > v) --j;
+    return j + 1;
+}
+
+// A 1-D mean-free-path table with its log companion and the accelerator of its energy grid
+struct Tab { const double *E, *L, *lE, *lL; int N; const GridLut *g; };
+TRK_HD int tab_find(const Tab &t, double E, double lE) { return find_lut(t.E, t.N, *t.g, E, lE); }
 
 // Find_in_monotonous_2D_array gives the same index as the 1D variant unless the value sits exactly on the lower
 // bracketing grid point, where the result depends on the bisection path: only then is the 2D search really run.
@@ -155,18 +169,21 @@ TRK_HD double nfp_at(const Tab &t, int n, bool two_d, double E, double lE) {
     if (Ll >= 1.0e16) return Ll;
     return interp5t(t.E[n - 2], t.E[n - 1], Ll, t.L[n - 1], t.lE[n - 2], t.lE[n - 1], t.lL[n - 2], t.lL[n - 1], E, lE);
 }
-TRK_HD double nfp_1d(const Tab &t, double E, double lE) { return nfp_at(t, find_1d(t.E, t.N, E), false, E, lE); }
-TRK_HD double nfp_2d(const Tab &t, double E, double lE) { return nfp_at(t, find_2d(t.E, t.N, E), true, E, lE); }
+TRK_HD double nfp_1d(const Tab &t, double E, double lE) { return nfp_at(t, tab_find(t, E, lE), false, E, lE); }
+TRK_HD double nfp_2d(const Tab &t, double E, double lE) { return nfp_at(t, find_2d_from_1d(t.E, t.N, E, tab_find(t, E, lE)), true, E, lE); }
 
-TRK_HD Tab tab_ei_tot(const DevP &p) { return Tab{p.ei_E, p.ei_tot, p.lei_E, p.lei_tot, p.n_ei}; }
-TRK_HD Tab tab_ee(const DevP &p) { return Tab{p.ee_E, p.ee_L, p.lee_E, p.lee_L, p.n_ee}; }
-TRK_HD Tab tab_hi_tot(const DevP &p) { return Tab{p.hi_E, p.hi_tot, p.lhi_E, p.lhi_tot, p.n_hi}; }
-TRK_HD Tab tab_he(const DevP &p) { return Tab{p.he_E, p.he_L, p.lhe_E, p.lhe_L, p.n_he}; }
-TRK_HD Tab tab_ph_tot(const DevP &p) { return Tab{p.ph_E, p.ph_tot, p.lph_E, p.lph_tot, p.n_ph}; }
-TRK_HD Tab tab_shi_tot(const DevP &p) { return Tab{p.shi_E, p.shi_tot, p.lshi_E, p.lshi_tot, p.n_shi}; }
-TRK_HD Tab tab_shell(const double *E, const double *lE, const double *Lmat, const double *lLmat, int N, int shell) {
-    return Tab{E, Lmat + (size_t)shell * N, lE, lLmat + (size_t)shell * N, N};
-}
+TRK_HD Tab tab_ei_tot(const DevP &p) { return Tab{p.ei_E, p.ei_tot, p.lei_E, p.lei_tot, p.n_ei, &p.lut[LUT_EI]}; }
+TRK_HD Tab tab_ee(const DevP &p) { return Tab{p.ee_E, p.ee_L, p.lee_E, p.lee_L, p.n_ee, &p.lut[LUT_EE]}; }
+TRK_HD Tab tab_hi_tot(const DevP &p) { return Tab{p.hi_E, p.hi_tot, p.lhi_E, p.lhi_tot, p.n_hi, &p.lut[LUT_HI]}; }
+TRK_HD Tab tab_he(const DevP &p) { return Tab{p.he_E, p.he_L, p.lhe_E, p.lhe_L, p.n_he, &p.lut[LUT_HE]}; }
+TRK_HD Tab tab_ph_tot(const DevP &p) { return Tab{p.ph_E, p.ph_tot, p.lph_E, p.lph_tot, p.n_ph, &p.lut[LUT_PH]}; }
+TRK_HD Tab tab_shi_tot(const DevP &p) { return Tab{p.shi_E, p.shi_tot, p.lshi_E, p.lshi_tot, p.n_shi, &p.lut[LUT_SHI]}; }
+// per-shell matrices of a family (rows [shell][energy] on the family's grid); tab_shell = one row
+TRK_HD Tab tab_ei_L(const DevP &p) { return Tab{p.ei_E, p.ei_L, p.lei_E, p.lei_L, p.n_ei, &p.lut[LUT_EI]}; }
+TRK_HD Tab tab_hi_L(const DevP &p) { return Tab{p.hi_E, p.hi_L, p.lhi_E, p.lhi_L, p.n_hi, &p.lut[LUT_HI]}; }
+TRK_HD Tab tab_ph_L(const DevP &p) { return Tab{p.ph_E, p.ph_L, p.lph_E, p.lph_L, p.n_ph, &p.lut[LUT_PH]}; }
+TRK_HD Tab tab_shi_L(const DevP &p) { return Tab{p.shi_E, p.shi_L, p.lshi_E, p.lshi_L, p.n_shi, &p.lut[LUT_SHI]}; }
+TRK_HD Tab tab_shell(const Tab &m, int shell) { return Tab{m.E, m.L + (size_t)shell * m.N, m.lE, m.lL + (size_t)shell * m.N, m.N, m.g}; }
 
 // total inelastic / elastic MFP of an electron (El_IMFP, El_EMFP of How_many_electrons, both searched with the 2D routine)
 TRK_HD double electron_imfp(const DevP &p, double E, double lE) {
@@ -188,7 +205,7 @@ struct Cache {
 };
 TRK_HD void cache_fill(const Tab &el, double E, Cache &k) {
     k.lE = log(E);
-    k.n1 = find_1d(el.E, el.N, E);
+    k.n1 = tab_find(el, E, k.lE);
     k.n2 = find_2d_from_1d(el.E, el.N, E, k.n1);
     k.emfp = nfp_at(el, k.n2, true, E, k.lE);
     k.imfp = 0.0;
@@ -205,10 +222,14 @@ TRK_HD void cache_electron(const DevP &p, double E, Cache &k) { cache_fill(tab_e
 TRK_HD void cache_vbhole(const DevP &p, double E, Cache &k) { cache_fill(tab_he(p), E, k); k.imfp = hole_imfp(p, E, k.lE); }
 
 // Which_shell, Monte_Carlo.f90:1786-1832: shell roulette on 1/lambda_shell(E); returns the flat shell
-TRK_HD int which_shell(const DevP &p, Rec &r, const double *Ea, const double *lEa, const double *Lmat, const double *lLmat, int N, double E, double lE) {
+// `m` = the family's per-shell matrix; n_out receives the search index of E in the family's grid (reused by the caller)
+TRK_HD int which_shell(const DevP &p, Rec &r, const Tab &m, double E, double lE, int &n_out) {
     double Temp[TRK3_MAX_SHELLS];
     double MFP_tot = 0.0;
-    const int n = find_1d(Ea, N, E);            // all shells share the grid (MAIN.f90:234-236)
+    const double *Ea = m.E, *lEa = m.lE, *Lmat = m.L, *lLmat = m.lL;
+    const int N = m.N;
+    const int n = tab_find(m, E, lE);           // all shells share the grid (MAIN.f90:234-236)
+    n_out = n;
     for (int s = 0; s < p.n_shells; ++s) {
         const double *La = Lmat + (size_t)s * N;
         double MFP;
@@ -252,6 +273,30 @@ TRK_HD int interval_of(const DevP &p, double t) {
 // interpolate_transferred_energy, Cross_sections.f90:1968-2045, on a CSR differential table with log companions.
 // i_E is the 1D search index of Ele in the table's energy grid (shared with the MFP lookup: same grid).
 struct Csr { const double *Eg, *lEg; int NE; const int64_t *off; const double *hw, *L, *lhw, *lL; };
+// Find_in_monoton_array_decreasing in two rows at once: the two bisections are independent chains of dependent loads,
+// interleaving them hides half of the latency.  Each follows exactly the path of find_dec.
+TRK_HD void find_dec2(const double *A, int NA, const double *B, int NB, double v, int &ia, int &ib) {
+    int a1 = 1, a2 = NA, ac = (1 + NA) >> 1, b1 = 1, b2 = NB, bc = (1 + NB) >> 1;
+    bool adone = false, bdone = false;
+    if (v < A[NA - 1]) { ac = NA; adone = true; } else if (v > A[0]) { ac = 1; adone = true; }
+    if (v < B[NB - 1]) { bc = NB; bdone = true; } else if (v > B[0]) { bc = 1; bdone = true; }
+    double ta = A[ac - 1], tb = B[bc - 1];
+    for (int coun = 0; coun <= 1000; ++coun) {
+        const bool ago = !adone && (a2 - a1 > 1 || a1 - a2 > 1), bgo = !bdone && (b2 - b1 > 1 || b1 - b2 > 1);
+        if (!ago && !bgo) break;
+        if (ago) { if (ta > v) a1 = ac; else a2 = ac; ac = (a1 + a2) >> 1; }
+        if (bgo) { if (tb > v) b1 = bc; else b2 = bc; bc = (b1 + b2) >> 1; }
+        if (ago) ta = A[ac - 1];
+        if (bgo) tb = B[bc - 1];
+    }
+    ia = ac; ib = bc;
+}
+TRK_HD double sample_row_at(const Csr &t, int64_t o, int n, int i_hw, double L_need, double lLn) {
+    const double *L = t.L + o, *hw = t.hw + o;
+    if (i_hw == 1 || i_hw == n) return hw[i_hw - 1];
+    const double *lL = t.lL + o, *lhw = t.lhw + o;
+    return interp5t(L[i_hw - 1], L[i_hw], hw[i_hw - 1], hw[i_hw], lL[i_hw - 1], lL[i_hw], lhw[i_hw - 1], lhw[i_hw], L_need, lLn);
+}
 TRK_HD double sample_row(const Csr &t, int64_t o, int n, double L_need, double lLn) {
     const double *L = t.L + o, *hw = t.hw + o;
     int i_hw = find_dec(L, n, L_need);
@@ -263,11 +308,14 @@ TRK_HD double transferred_energy(const Csr &t, double Ele, double lE, int i_E, d
     if (i_E > 1) { if (fabs(t.Eg[i_E - 2] - Ele) < 1.0e-6) i_E = i_E - 1; }
     const double lLn = log(L_need);
     int64_t o = t.off[i_E - 1];
-    double hw_1 = sample_row(t, o, (int)(t.off[i_E] - o), L_need, lLn);
-    if (i_E <= 1) return hw_1;
+    if (i_E <= 1) return sample_row(t, o, (int)(t.off[i_E] - o), L_need, lLn);
+    const int64_t o2 = t.off[i_E - 2];
+    const int n1 = (int)(t.off[i_E] - o), n2 = (int)(o - o2);
+    int i1, i2;
+    find_dec2(t.L + o, n1, t.L + o2, n2, L_need, i1, i2);
+    double hw_1 = sample_row_at(t, o, n1, i1, L_need, lLn);
     i_E = i_E - 1;
-    o = t.off[i_E - 1];
-    double hw_2 = sample_row(t, o, (int)(t.off[i_E] - o), L_need, lLn);
+    double hw_2 = sample_row_at(t, o2, n2, i2, L_need, lLn);
     if (hw_1 < 1.0e-10 || hw_2 < 1.0e-10) return interp1(t.Eg[i_E - 1], t.Eg[i_E], hw_1, hw_2, Ele);
     return interp5t(t.Eg[i_E - 1], t.Eg[i_E], hw_1, hw_2, t.lEg[i_E - 1], t.lEg[i_E], log(hw_1), log(hw_2), Ele, lE);
 }
@@ -277,10 +325,22 @@ TRK_HD Csr csr_hid(const DevP &p) { return Csr{p.hi_E, p.lhi_E, p.n_hi, p.hid_of
 TRK_HD Csr csr_hed(const DevP &p) { return Csr{p.he_E, p.lhe_E, p.n_he, p.hed_off, p.hed_hw, p.hed_L, p.lhed_hw, p.lhed_L}; }
 
 // effective hole mass from the DOS, e.g. Cross_sections.f90:1820-1825
-TRK_HD double hole_mass_dos(const DevP &p, double E) { int m = find_1d(p.dos_E, p.n_dos, E); return p.dos_effm[m - 1]; }
+// search in the DOS energy grid: direct index when the grid is uniform (reading_material_DOS resamples to 0.1 eV)
+TRK_HD int find_dos(const DevP &p, double E) {
+    const double *A = p.dos_E; const int N = p.n_dos;
+    if (!(p.dos_inv_step > 0.0)) return find_1d(A, N, E);
+    if (E < A[0]) return 1;
+    if (E >= A[N - 1]) return N;
+    int j = (int)(E * p.dos_inv_step) + 1;
+    j = (j < 1) ? 1 : ((j > N - 1) ? N - 1 : j);
+    while (j < N - 1 && A[j] <= E) ++j;
+    while (j > 1 && A[j - 1] > E) --j;
+    return j + 1;
+}
+TRK_HD double hole_mass_dos(const DevP &p, double E) { int m = find_dos(p, E); return p.dos_effm[m - 1]; }
 
 // Electron_energy_transfer_inelastic (CS_method = 1), Cross_sections.f90:1793-1871
-TRK_HD double inelastic_dE(const DevP &p, Rec &r, double Ele, double lE, int shell, double L_tot, bool hole) {
+TRK_HD double inelastic_dE(const DevP &p, Rec &r, double Ele, double lE, int n_E, int shell, double L_tot, bool hole) {
     double RN = rn(p, r);
     double L_need = L_tot / RN;
     double Emin = p.shell_Ip[shell];
@@ -288,11 +348,11 @@ TRK_HD double inelastic_dE(const DevP &p, Rec &r, double Ele, double lE, int she
     double Emax, E;
     if (!hole) {
         Emax = (Ele + Emin) / 2.0;
-        E = transferred_energy(csr_eid(p, shell), Ele, lE, find_1d(p.ei_E, p.n_ei, Ele), L_need);
+        E = transferred_energy(csr_eid(p, shell), Ele, lE, n_E, L_need);
     } else {
         double Mass = (p.hole_mass >= 0) ? p.hole_mass : hole_mass_dos(p, Ele);
         Emax = 4.0 * Ele * Mass / ((Mass + 1.0) * (Mass + 1.0));
-        E = transferred_energy(csr_hid(p), Ele, lE, find_1d(p.hi_E, p.n_hi, Ele), L_need);
+        E = transferred_energy(csr_hid(p), Ele, lE, n_E, L_need);
     }
     if (E < Emin) E = Emin;
     if (E > Emax) E = Emax;
@@ -385,7 +445,7 @@ TRK_HD double electron_receives_E(C &c, Rec &r, double dE, int shell) {
     double E = dE - p.shell_Ip[shell], dE_cur = E;
     if (shell == p.vb_shell && !(dE <= p.shell_Ip[shell])) {
         int N = p.n_dos;
-        int M_temp = (E < p.dos_E[N - 1]) ? find_1d(p.dos_E, N, E) : N + 1;
+        int M_temp = (E < p.dos_E[N - 1]) ? find_dos(p, E) : N + 1;
         if (M_temp > 1) dE_cur = E - vb_level(p, r, M_temp);
     }
     if (dE_cur < 0.0) c.error(TRK3_ERR_10);
@@ -395,7 +455,7 @@ TRK_HD double electron_receives_E(C &c, Rec &r, double dE, int shell) {
 TRK_HD double from_where_in_VB(const DevP &p, Rec &r, bool haveE, double E) {
     int N = p.n_dos;
     if (!haveE) return vb_level(p, r, N + 1);
-    int M_temp = (E < p.dos_E[N - 1]) ? find_1d(p.dos_E, N, E) : N + 1;
+    int M_temp = (E < p.dos_E[N - 1]) ? find_dos(p, E) : N + 1;
     if (M_temp > 1) return vb_level(p, r, M_temp);
     return 0.0;
 }
@@ -496,17 +556,23 @@ TRK_HD double shi_zeff(const DevP &p, double E) {
 }
 // SHI_energy_transfer (CDF shells), Monte_Carlo.f90:1719-1780.  The reference's linear search over 1/L
 // (Find_in_1D_array) is kept as a forward scan from the threshold row: same first index with 1/L >= Tot_N.
+// the part of SHI_energy_transfer that only depends on the shell (:1735-1747): the cumulative MFP at the ionisation
+// potential.  Evaluated once per shell when the tables are bound (DevP::shi_Mtemp, shi_dL).
+TRK_HD void shi_threshold(const double *Ea, const double *La, int N, double E_cur, int &M_temp, double &dL) {
+    if (N < 1) { M_temp = 1; dL = 0.0; return; }
+    M_temp = find_1d(Ea, N, E_cur);
+    if (M_temp > 1) {
+        if (La[M_temp - 2] > 1.0e-10) dL = interp5(Ea[M_temp - 2], Ea[M_temp - 1], La[M_temp - 2], La[M_temp - 1], E_cur);
+        else dL = interp1(Ea[M_temp - 2], Ea[M_temp - 1], La[M_temp - 2], La[M_temp - 1], E_cur);
+    } else dL = La[0];
+}
 TRK_HD double shi_energy_transfer(const DevP &p, Rec &r, int shell) {
     const int64_t o = p.dshi_off[shell];
     const double *Ea = p.dshi_E + o, *La = p.dshi_L + o, *lEa = p.ldshi_E + o, *iLa = p.dshi_iL + o, *liLa = p.ldshi_iL + o;
     int N = (int)(p.dshi_off[shell + 1] - o);
     double RN = rn(p, r);
-    double E_cur = p.shell_Ip[shell], dL;
-    int M_temp = find_1d(Ea, N, E_cur);
-    if (M_temp > 1) {
-        if (La[M_temp - 2] > 1.0e-10) dL = interp5(Ea[M_temp - 2], Ea[M_temp - 1], La[M_temp - 2], La[M_temp - 1], E_cur);
-        else dL = interp1(Ea[M_temp - 2], Ea[M_temp - 1], La[M_temp - 2], La[M_temp - 1], E_cur);
-    } else dL = La[0];
+    const int M_temp = p.shi_Mtemp[shell];
+    const double dL = p.shi_dL[shell];
     double Tot_N = (dL > 0.0 && La[N - 1] > 0.0) ? 1.0 / dL + RN * (1.0 / La[N - 1] - 1.0 / dL) : 1.5e21;
     int N_temmp;
     if (Tot_N < 1e20) {
@@ -556,7 +622,7 @@ TRK_HD void snapshot_hole(C &c, const Rec &h, int i) {
     const bool vb = (h.shell == p.vb_shell);
     if (vb) {
         c.add_u32(p.it.nvb, base);
-        int j = find_1d(p.dos_E, p.n_dos, h.Ehkin);
+        int j = find_dos(p, h.Ehkin);
         c.add_u32(p.it.spec_h, base * p.n_dos + (j - 1));
     }
     double Xh = h.X, Yh = h.Y;
@@ -638,10 +704,11 @@ TRK_HD void electron_event_t(C &c, Rec &e, int iv, Cache &k, double RN) {
     double dE, theta, phi;
     if (MODE == EV_INELASTIC || (MODE == EV_ANY && electron_roulette_inelastic(k, RN))) {     // inelastic: impact ionisation
         c.event(TRK3_EV_EL_INEL);
-        int shell = which_shell(p, e, p.ei_E, p.lei_E, p.ei_L, p.lei_L, p.n_ei, Eel, k.lE);
+        int n_E;
+        int shell = which_shell(p, e, tab_ei_L(p), Eel, k.lE, n_E);
         uint64_t id_e = child_id(p, e, 1), id_h = child_id(p, e, 2);
-        IMFP = nfp_1d(tab_shell(p.ei_E, p.lei_E, p.ei_L, p.lei_L, p.n_ei, shell), Eel, k.lE);
-        dE = inelastic_dE(p, e, Eel, k.lE, shell, IMFP, false);
+        IMFP = nfp_at(tab_shell(tab_ei_L(p), shell), n_E, false, Eel, k.lE);      // Next_free_path_1d, same grid => same index
+        dE = inelastic_dE(p, e, Eel, k.lE, n_E, shell, IMFP, false);
         theta = acos((Eel - dE) / sqrt(Eel * (Eel - dE)));       // Update_electron_angles_El :1189
         if (trk_isnan(theta)) { double r2 = rn(p, e); theta = r2 * TRK_PI; }
         { double r2 = rn(p, e); phi = 2.0 * TRK_PI * r2; }
@@ -693,7 +760,7 @@ TRK_HD void electron_event_t(C &c, Rec &e, int iv, Cache &k, double RN) {
 // check_hole_parameters, Monte_Carlo.f90:682-721: snap the scattered hole to a populated DOS level
 TRK_HD void check_hole_level(const DevP &p, double Eel, double &dE, double &Ehole, double *E_new_electron) {
     Ehole = Eel - dE;
-    int mhole = find_1d(p.dos_E, p.n_dos, Ehole);
+    int mhole = find_dos(p, Ehole);
     if (p.dos_DOS[mhole - 1] < 1.0e-4) {
         if (E_new_electron) {
             while (mhole > 1 && p.dos_DOS[mhole - 1] < 1.0e-4) mhole = mhole - 1;
@@ -724,10 +791,11 @@ TRK_HD void vbhole_event_t(C &c, Rec &h, int iv, Cache &k, double RN) {
     double dE, Ehole, htheta1, hphi1;
     if (MODE == EV_INELASTIC || (MODE == EV_ANY && vbhole_roulette_inelastic(k, RN))) {
         c.event(TRK3_EV_VBH_INEL);
-        int shell = which_shell(p, h, p.hi_E, p.lhi_E, p.hi_L, p.lhi_L, p.n_hi, Eel, k.lE);
+        int n_E;
+        int shell = which_shell(p, h, tab_hi_L(p), Eel, k.lE, n_E);
         uint64_t id_e = child_id(p, h, 1), id_h = child_id(p, h, 2);
-        HIMFP = nfp_1d(tab_shell(p.hi_E, p.lhi_E, p.hi_L, p.lhi_L, p.n_hi, shell), Eel, k.lE);
-        dE = inelastic_dE(p, h, Eel, k.lE, shell, HIMFP, true);
+        HIMFP = nfp_at(tab_shell(tab_hi_L(p), shell), n_E, false, Eel, k.lE);
+        dE = inelastic_dE(p, h, Eel, k.lE, n_E, shell, HIMFP, true);
         // Update_holes_angles_el, :1142-1168
         double E11 = Eel - dE, Mh = h.Mass * TRK_ME;
         double htheta = acos(sqrt((Mh + TRK_ME) * (Mh + TRK_ME) / (4.0 * Mh * TRK_ME) * dE / Eel));
@@ -890,7 +958,8 @@ TRK_HD void photon_event(C &c, Rec &ph) {
     const double Eel = ph.E, L = ph.L, theta0 = ph.theta, phi0 = ph.phi, t_ev = ph.tn;
     const double st0 = sin(theta0);
     const double X = ph.X + L * st0 * sin(phi0), Y = ph.Y + L * st0 * cos(phi0), Z = ph.Z + L * cos(theta0);
-    int shell = which_shell(p, ph, p.ph_E, p.lph_E, p.ph_L, p.lph_L, p.n_ph, Eel, log(Eel));
+    int n_E;
+    int shell = which_shell(p, ph, tab_ph_L(p), Eel, log(Eel), n_E);
     uint64_t id_e = child_id(p, ph, 1), id_h = child_id(p, ph, 2);
     double dE_cur = electron_receives_E(c, ph, Eel, shell);
     double phi1, theta1;
@@ -932,9 +1001,11 @@ TRK_HD void shi_step(C &c, Rec &s, ShiEvent &ev) {
     const double MSHI = p.ion_mass * TRK_MP;
     c.event(TRK3_EV_SHI);
     const double lEs = log(s.E);
-    int shell = which_shell(p, s, p.shi_E, p.lshi_E, p.shi_L, p.lshi_L, p.n_shi, s.E, lEs);
+    int n_E;
+    int shell = which_shell(p, s, tab_shi_L(p), s.E, lEs, n_E);
     double dE = shi_energy_transfer(p, s, shell);
-    double lam = nfp_2d(tab_shi_tot(p), s.E, lEs);
+    const Tab tt = tab_shi_tot(p);
+    double lam = nfp_at(tt, find_2d_from_1d(tt.E, tt.N, s.E, n_E), true, s.E, lEs);
     double RN = rn(p, s);
     double SHI_IMFP = -lam * log(RN);
     double Z = s.Z + s.L;
