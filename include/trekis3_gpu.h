@@ -179,6 +179,7 @@ typedef struct trk3_stats {
     double   device_ms;         /* CUDA-event time of the MC section */
     double   algorithmic_bytes; /* sum_class events*bytes */
     double   max_energy_drift;  /* max_it max_i |tot_E(it,i)-tot_E(it,Nt)|/tot_E(it,Nt), i >= first grid time after the ion left */
+    uint64_t cold_events[2];    /* elastic collisions of electrons / valence holes handled by the cold (elastic-only) kernels */
 } trk3_stats;
 
 /* Return codes */
@@ -198,6 +199,12 @@ int trk3_tally_layout_init(const trk3_config *cfg, const trk3_tables *tab, trk3_
 /* Validate + upload tables once (replaces the per-iteration How_many_electrons
  * table flattening, Monte_Carlo.f90:1902-2057).  device < 0 => current device. */
 int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, trk3_engine **out);
+
+/* Copy configuration + tables into an existing engine again (same shapes as at creation): what a persistent plugin
+ * handle does at every do_Monte_Carlo call -- the inputs go host->device, queues and scratch stay allocated.
+ * trk3_mc_table_bytes = bytes copied host->device by the last binding. */
+int trk3_mc_reload_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab);
+uint64_t trk3_mc_table_bytes(const trk3_engine *eng);
 
 /* Run iterations [it_begin, it_end) (global 0-based iteration indices; RNG streams are keyed
  * by the global index so the union over ranks is independent of the split) and ADD their

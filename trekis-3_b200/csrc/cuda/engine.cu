@@ -101,7 +101,7 @@ __device__ inline void block_prologue(double *s_tally, unsigned int *s_cnt, int 
     if (threadIdx.x < S_NCNT) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
 }
-__device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned int *s_cnt) {
+__device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned int *s_cnt, int cold_species = -1) {
     __syncthreads();
     if (s_tally) {
         // flush the private copy once per block (non-zero bins only)
@@ -117,6 +117,9 @@ __device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned i
     }
     if (threadIdx.x < TRK3_N_EVENT_CLASSES) { unsigned v = s_cnt[S_EV + threadIdx.x]; if (v) atomicAdd(&p.events[threadIdx.x], (unsigned long long)v); }
     if (threadIdx.x == 0) {
+        // collisions handled by the cold kernels (per species), for the per-kernel roofline
+        if (cold_species == SP_ELECTRON && s_cnt[S_EV + TRK3_EV_EL_ELAST]) atomicAdd(p.cnt_el + 2, (unsigned long long)s_cnt[S_EV + TRK3_EV_EL_ELAST]);
+        if (cold_species == SP_VBHOLE && s_cnt[S_EV + TRK3_EV_VBH_ELAST]) atomicAdd(p.cnt_el + 3, (unsigned long long)s_cnt[S_EV + TRK3_EV_VBH_ELAST]);
         if (s_cnt[S_NEL]) atomicAdd(p.cnt_el, (unsigned long long)s_cnt[S_NEL]);
         if (s_cnt[S_NPH]) atomicAdd(p.cnt_ph, (unsigned long long)s_cnt[S_NPH]);
     }
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
             }
         }
     }
-    block_epilogue(c_p, s_tally, s_cnt);
+    block_epilogue(c_p, s_tally, s_cnt, COLD ? SP : -1);
 }
 
 // k_hot<SP>: one generation of carriers that can still ionise (SP = electron or valence hole).  The two collision
@@ -320,6 +323,9 @@ struct trk3_engine {
     trk3_tally_layout lay{};
     DevP hp{};                         // host image of c_p (device pointers inside)
     std::vector<void *> allocs;
+    std::vector<std::pair<void *, size_t>> tab_allocs;   // table arrays in binding order (re-used by trk3_mc_reload_tables)
+    size_t tab_cursor = 0;
+    uint64_t h2d_bytes = 0;                 // bytes of the last table binding
     double nel_est = 1000.0;
     // options
     int opt_batch = 1024, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
@@ -390,13 +396,29 @@ int dev_alloc(trk3_engine *eng, T **p, size_t n) {
     eng->allocs.push_back((void *)*p);
     return TRK3_OK;
 }
+// table arrays: allocated by the first bind_tables(), re-used (same order, same sizes) by trk3_mc_reload_tables()
+template <class T>
+int tab_alloc(trk3_engine *eng, T **p, size_t n) {
+    const size_t bytes = (n ? n : 1) * sizeof(T);
+    if (eng->tab_cursor < eng->tab_allocs.size()) {
+        auto &a = eng->tab_allocs[eng->tab_cursor++];
+        if (a.second != bytes) { eng->err = "table shapes differ from those the engine was created with"; return TRK3_E_INVALID; }
+        *p = (T *)a.first;
+        return TRK3_OK;
+    }
+    int rc = dev_alloc(eng, p, n);
+    if (rc) return rc;
+    eng->tab_allocs.push_back({(void *)*p, bytes}); eng->tab_cursor++;
+    return TRK3_OK;
+}
 template <class T>
 int dev_upload(trk3_engine *eng, const T **dst, const T *src, size_t n) {
     T *d = nullptr;
-    int rc = dev_alloc(eng, &d, n);
+    int rc = tab_alloc(eng, &d, n);
     if (rc) return rc;
-    if (n && src) CK(cudaMemcpy(d, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    if (n && src) CK(cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, eng->stream));
     *dst = d;
+    eng->h2d_bytes += n * sizeof(T);
     return TRK3_OK;
 }
 void dev_free(trk3_engine *eng, void *p) {
@@ -512,33 +534,16 @@ int launch_hot(trk3_engine *eng, const Queue &qin, uint32_t n, uint32_t *head, c
     eng->launches++;
     return TRK3_OK;
 }
-}  // namespace
-
-extern "C" {
-
-const char *trk3_gpu_version(void) { return "trekis3_gpu 0.1 (sm_100a wavefront Monte-Carlo engine)"; }
-
-int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, trk3_engine **out) {
-    if (!cfg || !tab || !out) return TRK3_E_INVALID;
-    *out = nullptr;
-    trk3_engine *eng = new trk3_engine();
-    *out = eng;                                   // returned even on failure so that the caller can read last_error
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { eng->err = "no CUDA device: the engine has no CPU fallback"; return TRK3_E_CUDA; }
-    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
-    eng->device = device;
-    CK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    eng->n_sm = prop.multiProcessorCount;
-    eng->smem_optin = (int)prop.sharedMemPerBlockOptin;
+// Flattened tables -> device (first call allocates, later calls re-use the arrays): the inputs of do_Monte_Carlo.
+int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab) {
+    // everything of the previous DevP that does not come from the tables survives a reload
+    const DevP old = eng->hp;
+    eng->tab_cursor = 0; eng->h2d_bytes = 0;
     eng->cfg = *cfg;
     int rc = trk3_tally_layout_init(cfg, tab, &eng->lay);
     if (rc != TRK3_OK) { eng->err = "invalid time grid / layout"; return rc; }
     rc = fill_devp_scalars(*cfg, *tab, eng->lay, eng->hp);
     if (rc != TRK3_OK) { eng->err = (rc == TRK3_E_UNSUPPORTED) ? "unsupported option (DSF elastic scattering)" : "invalid tables"; return rc; }
-    CK(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&eng->ev0)); CK(cudaEventCreate(&eng->ev1));
     DevP &p = eng->hp;
     HostTotals tot; compute_totals(*tab, tot);
     const size_t NS = tab->n_shells;
@@ -560,14 +565,14 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
 #undef UP
     {   // log / reciprocal companions (one exp() per log-log interpolation instead of five log() + exp())
         const trk3_tables &T = *tab;
-#define X(dst, src, n, op) { double *d_ = nullptr; const size_t n_ = (size_t)(n); if ((rc = dev_alloc(eng, &d_, n_))) return rc; \
+#define X(dst, src, n, op) { double *d_ = nullptr; const size_t n_ = (size_t)(n); if ((rc = tab_alloc(eng, &d_, n_))) return rc; \
         if (n_) k_companion<<<(unsigned)((n_ + 255) / 256), 256, 0, eng->stream>>>(d_, src, n_, op); p.dst = d_; }
         TRK3_COMPANIONS(X, p, T, NS)
 #undef X
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(eng->stream));
         std::vector<uint16_t> lut;
-#define X(id, E, n) { build_lut(E, n, lut, p.lut[id].l0, p.lut[id].scale); rc = dev_upload(eng, &p.lut[id].lut, lut.data(), lut.size()); if (rc) return rc; }
+#define X(id, E, n) { build_lut(E, n, lut, p.lut[id].l0, p.lut[id].scale); rc = dev_upload(eng, &p.lut[id].lut, lut.data(), lut.size()); if (rc) return rc; CK(cudaStreamSynchronize(eng->stream)); }
         TRK3_LUT_GRIDS(X, T)
 #undef X
         p.dos_inv_step = uniform_inv_step(T.dos_E, T.n_dos);
@@ -575,19 +580,64 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
         cold_range(tab->ei_E, tot.ei_tot.data(), tab->n_ei, p.e_cold, p.e_imfp_cold);
         cold_range(tab->hi_E, tot.hi_tot.data(), tab->n_hi, p.h_cold, p.h_imfp_cold);
     }
+    CK(cudaStreamSynchronize(eng->stream));
+    p.tally = old.tally; p.events = old.events; p.errors = old.errors; p.cnt_el = old.cnt_el; p.cnt_ph = old.cnt_ph; p.it = old.it;
+    eng->nel_est = estimate_nel(*cfg, *tab);
+    return TRK3_OK;
+}
+}  // namespace
+
+extern "C" {
+
+const char *trk3_gpu_version(void) { return "trekis3_gpu 0.1 (sm_100a wavefront Monte-Carlo engine)"; }
+
+int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, trk3_engine **out) {
+    if (!cfg || !tab || !out) return TRK3_E_INVALID;
+    *out = nullptr;
+    trk3_engine *eng = new trk3_engine();
+    *out = eng;                                   // returned even on failure so that the caller can read last_error
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { eng->err = "no CUDA device: the engine has no CPU fallback"; return TRK3_E_CUDA; }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    eng->device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    eng->n_sm = prop.multiProcessorCount;
+    eng->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CK(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&eng->ev0)); CK(cudaEventCreate(&eng->ev1));
+    int rc = bind_tables(eng, cfg, tab);
+    if (rc) return rc;
+    DevP &p = eng->hp;
     if ((rc = dev_alloc(eng, &eng->d_tally, (size_t)eng->lay.total))) return rc;
     CK(cudaMemset(eng->d_tally, 0, (size_t)eng->lay.total * sizeof(double)));
     if ((rc = dev_alloc(eng, &eng->d_tally_bak, (size_t)eng->lay.total))) return rc;
     if ((rc = dev_alloc(eng, &eng->d_small, (size_t)TRK3_MAX_NT))) return rc;
-    if ((rc = dev_alloc(eng, &eng->d_counters, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 2)))) return rc;
-    if ((rc = dev_alloc(eng, &eng->d_counters_bak, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 2)))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_counters, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 4)))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_counters_bak, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 4)))) return rc;
     if ((rc = dev_alloc(eng, &eng->d_qcount, (size_t)QC_TOTAL))) return rc;
     p.tally = eng->d_tally;
     p.events = eng->d_counters; p.errors = eng->d_counters + TRK3_N_EVENT_CLASSES;
     p.cnt_el = eng->d_counters + TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS; p.cnt_ph = p.cnt_el + 1;
-    eng->nel_est = estimate_nel(*cfg, *tab);
     return TRK3_OK;
 }
+
+// Re-upload configuration + tables into an existing engine (same shapes): the per-call input copy of a persistent
+// plugin handle; queues and scratch stay allocated.
+int trk3_mc_reload_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab) {
+    if (!eng || !cfg || !tab) return TRK3_E_INVALID;
+    CK(cudaSetDevice(eng->device));
+    const trk3_tally_layout lay0 = eng->lay;
+    const double nel0 = eng->nel_est;
+    int rc = bind_tables(eng, cfg, tab);
+    if (rc) return rc;
+    if (eng->lay.total != lay0.total || eng->lay.Nt != lay0.Nt) { eng->err = "tally layout differs from the one the engine was created with"; return TRK3_E_INVALID; }
+    if (eng->nel_est > nel0) eng->nb_alloc = 0;          // larger cascades expected: re-size the queues at the next run
+    if (eng->nb_alloc) bind_scratch(eng->hp, eng->sl, eng->d_u32, eng->d_f64);
+    return TRK3_OK;
+}
+uint64_t trk3_mc_table_bytes(const trk3_engine *eng) { return eng ? eng->h2d_bytes : 0; }
 
 int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     if (!eng || !name) return TRK3_E_INVALID;
@@ -641,7 +691,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
     nb_max = std::min<int64_t>(nb_max, std::max<int64_t>(n_it, 1));
     int rc = ensure_batch(eng, (uint32_t)nb_max);
     if (rc) return rc;
-    const size_t n_counters = TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 2;
+    const size_t n_counters = TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 4;
     CK(cudaMemsetAsync(eng->d_counters, 0, n_counters * sizeof(unsigned long long), eng->stream));
     uint64_t waves = 0; const uint64_t launches0 = eng->launches;
     std::vector<double> h_diffS, h_totE; std::vector<uint32_t> h_diffN;
@@ -748,6 +798,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
     for (int q = 0; q < TRK3_N_EVENT_CLASSES; ++q) st.events[q] = h_c[q];
     for (int q = 0; q < TRK3_N_ERRORS; ++q) st.errors[q] = h_c[TRK3_N_EVENT_CLASSES + q];
     st.n_electrons = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS]; st.n_photons = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 1];
+    st.cold_events[0] = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 2]; st.cold_events[1] = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 3];
     st.n_waves = waves; st.kernel_launches = eng->launches - launches0; st.device_ms = ms;
     static const double ev_bytes[TRK3_N_EVENT_CLASSES] = {176, 320, 144, 384, 208, 384, 280, 208, 248};
     for (int q = 0; q < TRK3_N_EVENT_CLASSES; ++q) st.algorithmic_bytes += ev_bytes[q] * (double)st.events[q];

@@ -37,6 +37,9 @@ def _gpu():
         lib.trk3_mc_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         lib.trk3_mc_set_device_tallies.argtypes = [C.c_void_p, C.c_void_p]
         lib.trk3_mc_kernel_times.argtypes = [C.c_void_p, PD, C.POINTER(C.c_uint64), C.c_int]
+        lib.trk3_mc_reload_tables.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Tables)]
+        lib.trk3_mc_table_bytes.restype = C.c_uint64
+        lib.trk3_mc_table_bytes.argtypes = [C.c_void_p]
         lib.trk3_gpu_version.restype = C.c_char_p
         _lib = lib
     return _lib
@@ -66,6 +69,19 @@ class Engine:
         self.layout = lib.trk3_mc_layout(h).contents
         for k, v in options.items():
             self.set_option(k, v)
+
+    def reload_tables(self, case, seed=None):
+        """Copy the case's configuration and tables to the device again (same shapes): the per-call input transfer."""
+        cfg = Config.from_buffer_copy(case.config)
+        if seed is not None:
+            cfg.seed = int(seed)
+        self._cfg = cfg
+        self.case = case
+        self._check(_gpu().trk3_mc_reload_tables(self._h, C.byref(cfg), C.byref(case.tables)), "trk3_mc_reload_tables")
+
+    def table_bytes(self):
+        """Bytes copied host->device by the last table binding."""
+        return int(_gpu().trk3_mc_table_bytes(self._h))
 
     def set_option(self, name, value):
         rc = _gpu().trk3_mc_set_option(self._h, name.encode(), float(value))
@@ -137,13 +153,44 @@ class Engine:
             pass
 
 
-def do_Monte_Carlo(case, NMC=None, device=-1, seed=None, it_begin=0, **options):
+_handles = {}        # persistent plugin handles: (device, table shapes) -> Engine
+
+
+def _shape_key(case, device):
+    t = case.tables
+    lay = case.layout()
+    return (int(device), int(lay.total), int(lay.Nt), int(t.n_shells), int(t.n_ei), int(t.n_ee), int(t.n_hi), int(t.n_he),
+            int(t.n_ph), int(t.n_shi), int(t.n_dos), int(t.n_r), int(t.eid_off[t.n_shells * t.n_ei]),
+            int(t.eed_off[t.n_ee]), int(t.hid_off[t.n_hi]), int(t.hed_off[t.n_he]), int(t.dshi_off[t.n_shells]))
+
+
+def release_handles():
+    """Destroy the persistent engines kept by do_Monte_Carlo."""
+    for e in _handles.values():
+        e.close()
+    _handles.clear()
+
+
+def do_Monte_Carlo(case, NMC=None, device=-1, seed=None, it_begin=0, persistent=True, **options):
     """Replacement of `call do_Monte_Carlo(NMC, SHI, ...)` (Monte_Carlo.f90:39): returns the summed
-    Out_* tallies (not yet divided by NMC, as in the reference) and the run statistics."""
+    Out_* tallies (not yet divided by NMC, as in the reference) and the run statistics.
+
+    Every call copies its inputs (configuration + tables) host->device and the tallies device->host.  With
+    `persistent` (default) the engine handle -- device queues and scratch -- is kept between calls with the same table
+    shapes, as a plugin linked into the Fortran host would do; `persistent=False` creates and destroys an engine."""
     n = int(NMC if NMC is not None else case.get("NMC"))
-    eng = Engine(case, device=device, seed=seed, **options)
-    try:
-        tallies, stats = eng.run(it_begin, it_begin + n)
-    finally:
-        eng.close()
-    return tallies, stats
+    if not persistent:
+        eng = Engine(case, device=device, seed=seed, **options)
+        try:
+            return eng.run(it_begin, it_begin + n)
+        finally:
+            eng.close()
+    key = _shape_key(case, device)
+    eng = _handles.get(key)
+    if eng is None:
+        eng = _handles[key] = Engine(case, device=device, seed=seed)
+    else:
+        eng.reload_tables(case, seed=seed)
+    for k, v in options.items():
+        eng.set_option(k, v)
+    return eng.run(it_begin, it_begin + n)
