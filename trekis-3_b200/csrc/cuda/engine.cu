@@ -318,6 +318,8 @@ __global__ void k_axpy(double *dst, const double *src, int n) {
 struct trk3_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_c = nullptr;       // second stream: the cold kernels run beside the hot cascade
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     trk3_config cfg{};
     trk3_tally_layout lay{};
@@ -329,12 +331,13 @@ struct trk3_engine {
     double nel_est = 1000.0;
     // options
     int opt_batch = 1024, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
-    int opt_hot_slice = 1 << 30, opt_inel_min = 12;
+    int opt_hot_slice = 1 << 30, opt_inel_min = 8, opt_overlap = 0, opt_cold_min = 16384;
     double opt_cap_factor = 2.0;
     size_t opt_queue_bytes_max = (size_t)24 << 30;
     // per-batch resources
     uint32_t nb_alloc = 0;
     QueueSet qs[2]{};
+    QueueSet qs_x{};                   // output set of the cold kernels (small hot queues + the shared cold queues)
     uint32_t *d_qcount = nullptr;      // QC_* layout below: hot counts of both generations, cold counts, heads
     uint32_t *d_u32 = nullptr; double *d_f64 = nullptr; ScratchLayout sl{};
     FoldAux fa{};
@@ -355,17 +358,19 @@ struct trk3_engine {
 };
 
 // d_qcount layout (uint32): [0..3] hot counts generation A, [4..7] generation B, [8..9] cold counts,
-// [10..13] hot heads, [14..15] cold heads
+// [10..13] hot counts of set X (particles handed back by the cold kernels), [14..17] hot heads, [18..19] cold heads
 #define QC_HOT(b) ((b) * N_SPECIES)
 #define QC_COLD (2 * N_SPECIES)
-#define QC_HEAD (2 * N_SPECIES + 2)
-#define QC_TOTAL (3 * N_SPECIES + 4)
+#define QC_X (2 * N_SPECIES + 2)
+#define QC_HEAD (3 * N_SPECIES + 2)
+#define QC_TOTAL (4 * N_SPECIES + 4)
 
 namespace {
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { eng->err = std::string(#call) + ": " + cudaGetErrorString(e_); return TRK3_E_CUDA; } } while (0)
 
 // optional per-kernel-class timing: events are recorded on the launching stream around every launch
-int prof_begin(trk3_engine *eng, int cls) {
+int prof_begin(trk3_engine *eng, int cls, cudaStream_t st = nullptr) {
+    if (!st) st = eng->stream;
     if (!eng->opt_profile) return -1;
     size_t used = eng->ev_pending.size();
     if (used >= eng->ev_pool.size()) {
@@ -373,11 +378,11 @@ int prof_begin(trk3_engine *eng, int cls) {
         if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return -1;
         eng->ev_pool.push_back({a, b});
     }
-    cudaEventRecord(eng->ev_pool[used].first, eng->stream);
+    cudaEventRecord(eng->ev_pool[used].first, st);
     eng->ev_pending.push_back({cls, (int)used});
     return (int)used;
 }
-void prof_end(trk3_engine *eng, int idx) { if (idx >= 0) cudaEventRecord(eng->ev_pool[idx].second, eng->stream); }
+void prof_end(trk3_engine *eng, int idx, cudaStream_t st = nullptr) { if (idx >= 0) cudaEventRecord(eng->ev_pool[idx].second, st ? st : eng->stream); }
 void prof_collect(trk3_engine *eng) {      // call after a stream synchronize
     for (auto &pe : eng->ev_pending) {
         float ms = 0.f;
@@ -455,6 +460,7 @@ double queue_bytes_per_iteration(const trk3_engine *eng) {
     double b = 0;
     for (int s = 0; s < N_SPECIES; ++s) b += 2.0 * cap[s] * (TRK_NCOL * 8 + 20);
     for (int s = N_SPECIES; s < N_QUEUES; ++s) b += cap[s] * (TRK_NCOL * 8 + 20);
+    for (int s = 0; s < N_SPECIES; ++s) b += cap[s] / 16.0 * (TRK_NCOL * 8 + 20);
     return b;
 }
 
@@ -462,7 +468,8 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
     if (nb <= eng->nb_alloc) return TRK3_OK;
     // release the previous batch resources
     for (int b = 0; b < 2; ++b) for (int s = 0; s < N_SPECIES; ++s) free_queue(eng, eng->qs[b].q[s]);
-    for (int s = N_SPECIES; s < N_QUEUES; ++s) { free_queue(eng, eng->qs[0].q[s]); eng->qs[1].q[s] = Queue{}; }
+    for (int s = N_SPECIES; s < N_QUEUES; ++s) { free_queue(eng, eng->qs[0].q[s]); eng->qs[1].q[s] = Queue{}; eng->qs_x.q[s] = Queue{}; }
+    for (int s = 0; s < N_SPECIES; ++s) free_queue(eng, eng->qs_x.q[s]);
     dev_free(eng, eng->d_u32); dev_free(eng, eng->d_f64);
     dev_free(eng, eng->fa.totnel); dev_free(eng, eng->fa.totE); dev_free(eng, eng->fa.latcum); dev_free(eng, eng->fa.emcnt); dev_free(eng, eng->fa.emE);
     eng->d_u32 = nullptr; eng->d_f64 = nullptr; eng->fa = FoldAux{};
@@ -475,7 +482,11 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
     for (int s = N_SPECIES; s < N_QUEUES; ++s) {      // the cold queues are shared by both generations
         int rc = alloc_queue(eng, eng->qs[0].q[s], (uint32_t)(cap[s] * (double)nb), eng->d_qcount + QC_COLD + (s - N_SPECIES));
         if (rc) return rc;
-        eng->qs[1].q[s] = eng->qs[0].q[s];
+        eng->qs[1].q[s] = eng->qs[0].q[s]; eng->qs_x.q[s] = eng->qs[0].q[s];
+    }
+    for (int s = 0; s < N_SPECIES; ++s) {             // handed back by the cold kernels: a rarity
+        int rc = alloc_queue(eng, eng->qs_x.q[s], (uint32_t)(cap[s] * (double)nb / 16.0) + 4096u, eng->d_qcount + QC_X + s);
+        if (rc) return rc;
     }
     eng->sl = scratch_layout(eng->hp, nb);
     int rc;
@@ -493,8 +504,9 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
 }
 
 template <int SP, bool COLD>
-int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_in, uint32_t *head, const QueueSet &qout) {
+int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_in, uint32_t *head, const QueueSet &qout, cudaStream_t st = nullptr) {
     const uint32_t n = n_in - first;
+    if (!st) st = eng->stream;
     size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
     int use_smem = eng->opt_use_smem;
     const size_t smem_max = (size_t)eng->smem_optin - 1024;             // static shared memory + driver reserve
@@ -507,9 +519,9 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_i
     uint32_t want = (n + block - 1) / block;
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (grid < 1) grid = 1;
-    const int pi = prof_begin(eng, COLD ? N_SPECIES + 2 + SP : SP);
-    k_wave<SP, COLD><<<grid, block, smem, eng->stream>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice);
-    prof_end(eng, pi);
+    const int pi = prof_begin(eng, COLD ? N_SPECIES + 2 + SP : SP, st);
+    k_wave<SP, COLD><<<grid, block, smem, st>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice);
+    prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
     return TRK3_OK;
@@ -605,8 +617,14 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
     CK(cudaGetDeviceProperties(&prop, device));
     eng->n_sm = prop.multiProcessorCount;
     eng->smem_optin = (int)prop.sharedMemPerBlockOptin;
-    CK(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    {   // the hot cascade is the critical path: its stream gets the higher priority
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&eng->stream, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&eng->stream_c, cudaStreamNonBlocking, lo));
+    }
     CK(cudaEventCreate(&eng->ev0)); CK(cudaEventCreate(&eng->ev1));
+    CK(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&eng->ev_join, cudaEventDisableTiming));
     int rc = bind_tables(eng, cfg, tab);
     if (rc) return rc;
     DevP &p = eng->hp;
@@ -650,6 +668,8 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "queue_gib") eng->opt_queue_bytes_max = (size_t)(v * (double)(1ull << 30));
     else if (k == "block") eng->opt_block = std::min(TRK_BLOCK_MAX, std::max(32, ((int)v / 32) * 32));
     else if (k == "hot_slice") eng->opt_hot_slice = std::max(1, (int)v);
+    else if (k == "overlap") eng->opt_overlap = (v != 0.0);
+    else if (k == "cold_min") eng->opt_cold_min = std::max(1, (int)v);
     else if (k == "inel_min") eng->opt_inel_min = std::min(32, std::max(1, (int)v));
     else if (k == "max_generations") eng->opt_max_generations = std::max(1, (int)v);
     else if (k == "profile") { eng->opt_profile = (v != 0.0); for (auto &x : eng->class_ms) x = 0; for (auto &x : eng->class_launches) x = 0; }
@@ -719,8 +739,10 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         int cur = 0;
         bool overflow = false;
         uint32_t cold_done[2] = {0, 0};
+        cudaStream_t sc = eng->opt_overlap ? eng->stream_c : eng->stream;       // stream of the cold kernels
+        if (eng->opt_overlap) { CK(cudaEventRecord(eng->ev_fork, eng->stream)); CK(cudaStreamWaitEvent(sc, eng->ev_fork, 0)); }
         for (int gen = 0; gen < eng->opt_max_generations; ++gen) {
-            uint32_t h_cnt[QC_COLD + 2];       // hot counts of both generations + cold counts
+            uint32_t h_cnt[QC_X];              // hot counts of both generations + cold counts
             CK(cudaMemcpyAsync(h_cnt, eng->d_qcount, sizeof h_cnt, cudaMemcpyDeviceToHost, eng->stream));
             CK(cudaStreamSynchronize(eng->stream));
             uint32_t *hot = h_cnt + QC_HOT(cur), *cold = h_cnt + QC_COLD;
@@ -729,24 +751,43 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             for (int s = 0; s < N_SPECIES; ++s) { if (hot[s] > eng->qs[cur].q[s].cap) { overflow = true; hot[s] = eng->qs[cur].q[s].cap; } total += hot[s]; }
             for (int s = 0; s < 2; ++s) if (cold[s] > eng->qs[0].q[N_SPECIES + s].cap) { overflow = true; cold[s] = eng->qs[0].q[N_SPECIES + s].cap; }
             if (overflow) break;
-            const bool cold_pending = cold[0] > cold_done[0] || cold[1] > cold_done[1];
-            if (!total && !cold_pending) break;
+            const uint64_t cold_pending = (uint64_t)(cold[0] - cold_done[0]) + (cold[1] - cold_done[1]);
             ++waves;
             const int nxt = cur ^ 1;
-            CK(cudaMemsetAsync(eng->d_qcount + QC_HOT(nxt), 0, N_SPECIES * sizeof(uint32_t), eng->stream));
-            CK(cudaMemsetAsync(heads, 0, N_QUEUES * sizeof(uint32_t), eng->stream));
-            if (total) {        // one generation of the hot cascade
+            if (total) {        // one generation of the hot cascade (time-sliced, see k_hot)
+                CK(cudaMemsetAsync(eng->d_qcount + QC_HOT(nxt), 0, N_SPECIES * sizeof(uint32_t), eng->stream));
+                CK(cudaMemsetAsync(heads, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
                 if (hot[SP_ELECTRON]) { rc = launch_hot<SP_ELECTRON>(eng, eng->qs[cur].q[SP_ELECTRON], hot[SP_ELECTRON], heads + SP_ELECTRON, eng->qs[nxt]); if (rc) return rc; }
                 if (hot[SP_VBHOLE]) { rc = launch_hot<SP_VBHOLE>(eng, eng->qs[cur].q[SP_VBHOLE], hot[SP_VBHOLE], heads + SP_VBHOLE, eng->qs[nxt]); if (rc) return rc; }
                 if (hot[SP_COREHOLE]) { rc = launch_wave<SP_COREHOLE, false>(eng, eng->qs[cur].q[SP_COREHOLE], 0, hot[SP_COREHOLE], heads + SP_COREHOLE, eng->qs[nxt]); if (rc) return rc; }
                 if (hot[SP_PHOTON]) { rc = launch_wave<SP_PHOTON, false>(eng, eng->qs[cur].q[SP_PHOTON], 0, hot[SP_PHOTON], heads + SP_PHOTON, eng->qs[nxt]); if (rc) return rc; }
-            } else {            // the hot cascade has died out: drain the cold queues (they may hand particles back)
-                if (cold[0] > cold_done[0]) { rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[0].q[Q_EL_COLD], cold_done[0], cold[0], heads + Q_EL_COLD, eng->qs[nxt]); if (rc) return rc; }
-                if (cold[1] > cold_done[1]) { rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[0].q[Q_VB_COLD], cold_done[1], cold[1], heads + Q_VB_COLD, eng->qs[nxt]); if (rc) return rc; }
+                cur = nxt;
+            }
+            // cold kernels: on the second stream, beside the next hot generation, as soon as enough records have gathered
+            // (the records [cold_done, cold) were written by kernels that have completed: the stream was just synchronised)
+            if (cold_pending && (!total || (eng->opt_overlap && cold_pending >= (uint64_t)eng->opt_cold_min))) {
+                CK(cudaMemsetAsync(heads + N_SPECIES, 0, 2 * sizeof(uint32_t), sc));
+                if (cold[0] > cold_done[0]) { rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[0].q[Q_EL_COLD], cold_done[0], cold[0], heads + Q_EL_COLD, eng->qs_x, sc); if (rc) return rc; }
+                if (cold[1] > cold_done[1]) { rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[0].q[Q_VB_COLD], cold_done[1], cold[1], heads + Q_VB_COLD, eng->qs_x, sc); if (rc) return rc; }
                 cold_done[0] = cold[0]; cold_done[1] = cold[1];
             }
+            if (total) continue;
+            // the hot cascade has died out and the cold queues are drained: did the cold kernels hand anything back?
+            uint32_t h_x[N_SPECIES];
+            CK(cudaMemcpyAsync(h_x, eng->d_qcount + QC_X, sizeof h_x, cudaMemcpyDeviceToHost, sc));
+            CK(cudaStreamSynchronize(sc));
+            uint64_t nx = 0;
+            for (int s = 0; s < N_SPECIES; ++s) { if (h_x[s] > eng->qs_x.q[s].cap) overflow = true; nx += h_x[s]; }
+            if (overflow) break;
+            if (!nx) break;                                        // cold kernels create no cold records: everything is done
+            CK(cudaMemsetAsync(eng->d_qcount + QC_HOT(nxt), 0, N_SPECIES * sizeof(uint32_t), eng->stream));
+            CK(cudaMemsetAsync(heads, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
+            if (h_x[SP_ELECTRON]) { rc = launch_hot<SP_ELECTRON>(eng, eng->qs_x.q[SP_ELECTRON], h_x[SP_ELECTRON], heads + SP_ELECTRON, eng->qs[nxt]); if (rc) return rc; }
+            if (h_x[SP_VBHOLE]) { rc = launch_hot<SP_VBHOLE>(eng, eng->qs_x.q[SP_VBHOLE], h_x[SP_VBHOLE], heads + SP_VBHOLE, eng->qs[nxt]); if (rc) return rc; }
+            CK(cudaMemsetAsync(eng->d_qcount + QC_X, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
             cur = nxt;
         }
+        if (eng->opt_overlap) { CK(cudaEventRecord(eng->ev_join, sc)); CK(cudaStreamWaitEvent(eng->stream, eng->ev_join, 0)); }
         if (overflow) {
             if (++retries > 6) { eng->err = "particle queue overflow persists after 6 capacity doublings"; return TRK3_E_OVERFLOW; }
             CK(cudaMemcpyAsync(eng->d_tally, eng->d_tally_bak, (size_t)eng->lay.total * sizeof(double), cudaMemcpyDeviceToDevice, eng->stream));
@@ -868,6 +909,9 @@ void trk3_mc_destroy(trk3_engine *eng) {
     if (eng->ev1) cudaEventDestroy(eng->ev1);
     for (auto &e : eng->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (eng->own_stream && eng->stream) cudaStreamDestroy(eng->stream);
+    if (eng->stream_c) cudaStreamDestroy(eng->stream_c);
+    if (eng->ev_fork) cudaEventDestroy(eng->ev_fork);
+    if (eng->ev_join) cudaEventDestroy(eng->ev_join);
     delete eng;
 }
 

@@ -46,7 +46,7 @@ TRK_HD uint32_t trk_mulhi(uint32_t a, uint32_t b) {
     return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
-TRK_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1) {
+TRK_HDN void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t h0 = trk_mulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
@@ -203,7 +203,7 @@ struct Cache {
     double imfp;    // total inelastic MFP (El_IMFP / Hole_IMFP)
     int n1, n2;     // 1D / 2D search indices of E in the elastic grid
 };
-TRK_HD void cache_fill(const Tab &el, double E, Cache &k) {
+TRK_HDN void cache_fill(const Tab &el, double E, Cache &k) {
     k.lE = log(E);
     k.n1 = tab_find(el, E, k.lE);
     k.n2 = find_2d_from_1d(el.E, el.N, E, k.n1);
@@ -223,7 +223,7 @@ TRK_HD void cache_vbhole(const DevP &p, double E, Cache &k) { cache_fill(tab_he(
 
 // Which_shell, Monte_Carlo.f90:1786-1832: shell roulette on 1/lambda_shell(E); returns the flat shell
 // `m` = the family's per-shell matrix; n_out receives the search index of E in the family's grid (reused by the caller)
-TRK_HD int which_shell(const DevP &p, Rec &r, const Tab &m, double E, double lE, int &n_out) {
+TRK_HDN int which_shell(const DevP &p, Rec &r, const Tab &m, double E, double lE, int &n_out) {
     double Temp[TRK3_MAX_SHELLS];
     double MFP_tot = 0.0;
     const double *Ea = m.E, *lEa = m.lE, *Lmat = m.L, *lLmat = m.lL;
@@ -304,7 +304,7 @@ TRK_HD double sample_row(const Csr &t, int64_t o, int n, double L_need, double l
     const double *lL = t.lL + o, *lhw = t.lhw + o;
     return interp5t(L[i_hw - 1], L[i_hw], hw[i_hw - 1], hw[i_hw], lL[i_hw - 1], lL[i_hw], lhw[i_hw - 1], lhw[i_hw], L_need, lLn);
 }
-TRK_HD double transferred_energy(const Csr &t, double Ele, double lE, int i_E, double L_need) {
+TRK_HDN double transferred_energy(const Csr &t, double Ele, double lE, int i_E, double L_need) {
     if (i_E > 1) { if (fabs(t.Eg[i_E - 2] - Ele) < 1.0e-6) i_E = i_E - 1; }
     const double lLn = log(L_need);
     int64_t o = t.off[i_E - 1];
@@ -364,7 +364,7 @@ TRK_HD double inelastic_dE(const DevP &p, Rec &r, double Ele, double lE, int n_E
 TRK_HD double rest_energy(double M0) { return M0 * TRK_CVEL * TRK_CVEL / TRK_GE; }
 
 // NRG_transfer_elastic_atomic (Mott), Cross_sections.f90:3517-3613
-TRK_HD double mott_dE(const DevP &p, Rec &r, double Mat, double Zat, double Ee, double M_eff) {
+TRK_HDN double mott_dE(const DevP &p, Rec &r, double Mat, double Zat, double Ee, double M_eff) {
     double RN = rn(p, r);
     double theta;
     double Erest = rest_energy(TRK_ME);
@@ -415,7 +415,7 @@ TRK_HD void angles_lattice(const DevP &p, Rec &r, double E, double W, double M_e
     phi = 2.0 * TRK_PI * RN2;
 }
 // New_Angles_both, Monte_Carlo.f90:1328-1360 (not a rotation; kept as is)
-TRK_HD void new_angles(double phi0, double theta0, double theta, double psi, double &phi1, double &theta1) {
+TRK_HDN void new_angles(double phi0, double theta0, double theta, double psi, double &phi1, double &theta1) {
     phi1 = phi0 + theta * cos(theta0) * sin(psi);
     theta1 = theta0 + theta * cos(psi);
     while (theta1 < 0.0) { theta1 = fabs(theta1); phi1 = phi1 + TRK_PI; }
@@ -463,7 +463,7 @@ TRK_HD double from_where_in_VB(const DevP &p, Rec &r, bool haveE, double E) {
 // Hole_parameters (+Assign_holes_mass), Monte_Carlo.f90:724-792.  `Ehkin_prev` is the hole's kinetic energy
 // before the update (0 for a newly created hole: How_many_electrons initialises Ehkin = 0).
 // `kout` (optional) receives the lookups of the new kinetic energy for the hole's next collision.
-TRK_HD void hole_parameters(const DevP &p, Rec &st, Rec &h, double Eh, double Ehkin_prev, Cache *kout = nullptr) {
+TRK_HDN void hole_parameters(const DevP &p, Rec &st, Rec &h, double Eh, double Ehkin_prev, Cache *kout = nullptr) {
     if (h.shell == p.vb_shell) {
         h.Ehkin = Eh - p.Egap;
         h.E = p.Egap;
