@@ -688,10 +688,13 @@ struct MC {
             IMFP = Next_free_path_1d(Eel, T.ei_E, T.ei_L + (size_t)f * T.n_ei, T.n_ei);
             dE = Electron_energy_transfer_inelastic(Eel, Nat_cur, Nshl_cur, IMFP, false, st);
             Update_electron_angles_El(Eel, dE, theta, phi, st);
-            double dE_cur = Electron_recieves_E(dE, Nat_cur, Nshl_cur, st);
+            // stream convention of the engine (physics.cuh, electron_ion_emit): the draws that create the pair come from
+            // the new electron's / the new hole's own streams (the primary's history does not depend on them)
+            Stream &se = en.rng, &sh = hn.rng;
+            double dE_cur = Electron_recieves_E(dE, Nat_cur, Nshl_cur, se);
             IMFP = Next_free_path_2d(dE_cur, T.ei_E, El_IMFP.data(), T.n_ei);
             EMFP = Next_free_path_2d(dE_cur, T.ee_E, T.ee_L, T.n_ee);
-            RN = rng.rn(st);
+            RN = rng.rn(se);
             double MFP_tot = -std::log(RN) / (1.0 / IMFP + 1.0 / EMFP);
             double theta2 = g_Pi / 2.0 - theta, phi2 = phi + g_Pi, phi1, theta1;
             New_Angles_both(phi0, theta0, theta2, phi2, phi1, theta1);
@@ -701,9 +704,9 @@ struct MC {
             cut_off_e(en);
             if (en.E < -1.0e-9 || std::isnan(en.E)) er[TRK3_ERR_21]++;
             double htheta, hphi;
-            Update_holes_angles_SHI(htheta, hphi, st);
+            Update_holes_angles_SHI(htheta, hphi, sh);
             hn.t0 = t_ev; hn.X = X; hn.Y = Y; hn.Z = Z; hn.KOA = Nat_cur; hn.Shl = Nshl_cur; hn.theta = htheta; hn.phi = hphi;
-            Hole_parameters(hn, dE - dE_cur, st);
+            Hole_parameters(hn, dE - dE_cur, sh);
             cut_off_h(hn);
             if (hn.Ehkin < -1.0e-9 || std::isnan(hn.Ehkin)) er[TRK3_ERR_20]++;
         } else {

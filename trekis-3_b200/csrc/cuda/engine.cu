@@ -32,7 +32,8 @@ __constant__ DevP c_p;
 // queue ids: 0..3 = next hot generation per species, 4 / 5 = cold electrons / cold valence holes
 #define Q_EL_COLD N_SPECIES
 #define Q_VB_COLD (N_SPECIES + 1)
-#define N_QUEUES (N_SPECIES + 2)
+#define Q_ION (N_SPECIES + 2)         // impact ionisations of the current generation (IonEvent records, see k_ion_emit)
+#define N_QUEUES (N_SPECIES + 3)
 struct QueueSet { Queue q[N_QUEUES]; };
 #define N_CLASSES (N_SPECIES + 4)     // timing classes: hot waves per species, k_shi, finalize, cold electrons, cold holes
 
@@ -61,6 +62,12 @@ struct DevCtx {
         push_q(qi, r);
     }
     __device__ void push_hot(int sp, const Rec &r) { push_q(sp, r); }
+    __device__ void push_ion(const IonEvent &ev) {       // an IonEvent travels in the columns of an ordinary record
+        Rec r;
+        r.E = ev.dE; r.Ehkin = ev.t; r.Mass = ev.X; r.t0 = ev.Y; r.tn = ev.Z; r.X = ev.theta0; r.Y = ev.phi0; r.Z = ev.theta; r.L = ev.phi;
+        r.theta = 0.0; r.phi = 0.0; r.id = ev.pid; r.ctr = ev.ctr0; r.iter = ev.iter; r.shell = ev.shell;
+        push_q(Q_ION, r);
+    }
     __device__ void push_q(int qi, const Rec &r) {
         // warp-aggregated append: lanes pushing to the same queue share one atomicAdd
         const unsigned am = __activemask();
@@ -76,10 +83,6 @@ struct DevCtx {
         q.col[0][slot] = r.E; q.col[1][slot] = r.Ehkin; q.col[2][slot] = r.Mass; q.col[3][slot] = r.t0; q.col[4][slot] = r.tn;
         q.col[5][slot] = r.X; q.col[6][slot] = r.Y; q.col[7][slot] = r.Z; q.col[8][slot] = r.L; q.col[9][slot] = r.theta; q.col[10][slot] = r.phi;
         q.id[slot] = r.id; q.ctr[slot] = r.ctr; q.iter[slot] = r.iter; q.shell[slot] = r.shell;
-        if (qi < N_SPECIES) {       // hot queues are consumed while they grow (k_hot_all): publish the finished record
-            __threadfence();
-            *(volatile uint32_t *)(q.ready + slot) = p.epoch;
-        }
     }
     __device__ void tally(int id, int64_t idx, double v) {
         const int so = p.s_off[id];
@@ -98,14 +101,6 @@ __device__ inline void load_rec(const Queue &q, uint32_t i, Rec &r) {
     r.E = q.col[0][i]; r.Ehkin = q.col[1][i]; r.Mass = q.col[2][i]; r.t0 = q.col[3][i]; r.tn = q.col[4][i];
     r.X = q.col[5][i]; r.Y = q.col[6][i]; r.Z = q.col[7][i]; r.L = q.col[8][i]; r.theta = q.col[9][i]; r.phi = q.col[10][i];
     r.id = q.id[i]; r.ctr = q.ctr[i]; r.iter = q.iter[i]; r.shell = q.shell[i];
-}
-
-// a record of a queue that other blocks are still appending to: the loads must not be served by this SM's L1
-// (a line fetched for a neighbouring slot may hold the slot's bytes from before it was written)
-__device__ inline void load_rec_cg(const Queue &q, uint32_t i, Rec &r) {
-    r.E = __ldcg(q.col[0] + i); r.Ehkin = __ldcg(q.col[1] + i); r.Mass = __ldcg(q.col[2] + i); r.t0 = __ldcg(q.col[3] + i); r.tn = __ldcg(q.col[4] + i);
-    r.X = __ldcg(q.col[5] + i); r.Y = __ldcg(q.col[6] + i); r.Z = __ldcg(q.col[7] + i); r.L = __ldcg(q.col[8] + i); r.theta = __ldcg(q.col[9] + i); r.phi = __ldcg(q.col[10] + i);
-    r.id = __ldcg((const unsigned long long *)q.id + i); r.ctr = __ldcg(q.ctr + i); r.iter = __ldcg(q.iter + i); r.shell = __ldcg(q.shell + i);
 }
 
 __device__ inline void block_prologue(double *s_tally, unsigned int *s_cnt, int s_total) {
@@ -180,6 +175,24 @@ __global__ void __launch_bounds__(256) k_shi_emit(Queue stage, QueueSet qout) {
     block_epilogue(c_p, nullptr, s_cnt);
 }
 
+// k_ion_emit: the electron-hole pairs of the impact ionisations of a generation (electron_ion_emit), one thread per
+// ionisation; launched right after the hot kernels of the generation, it fills the same next-generation queues.
+__global__ void __launch_bounds__(256) k_ion_emit(Queue ionq, QueueSet qout) {
+    __shared__ unsigned int s_cnt[S_NCNT];
+    block_prologue(nullptr, s_cnt, 0);
+    DevCtx c{c_p, qout, nullptr, s_cnt};
+    const uint32_t n = min(*ionq.count, ionq.cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Rec r;
+        load_rec(ionq, i, r);
+        IonEvent ev;
+        ev.dE = r.E; ev.t = r.Ehkin; ev.X = r.Mass; ev.Y = r.t0; ev.Z = r.tn; ev.theta0 = r.X; ev.phi0 = r.Y; ev.theta = r.Z; ev.phi = r.L;
+        ev.pid = r.id; ev.ctr0 = r.ctr; ev.iter = r.iter; ev.shell = r.shell;
+        electron_ion_emit(c, ev);
+    }
+    block_epilogue(c_p, nullptr, s_cnt);
+}
+
 // k_wave<SP, COLD>: records [first, n_in) of queue qin, histories followed with lane refill until they end or
 // have to change queue (hot -> cold when the particle can no longer ionise, core hole -> valence hole, ...).
 template <int SP, bool COLD>
@@ -245,7 +258,7 @@ template <int SP, int MODE> __device__ inline void hot_event(DevCtx &c, Rec &r, 
 template <int SP> __device__ inline bool hot_leaves(const Rec &r) { return SP == SP_ELECTRON ? electron_leaves_hot(c_p, r) : vbhole_leaves_hot(c_p, r); }
 
 template <int SP>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(Queue qin, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int inel_min) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(Queue qin, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int inel_min, int quota) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
@@ -257,17 +270,21 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(Queue qin, uint32_t n_
     Cache k{};
     double RN = 0.0;
     int ig = 0, nev = 0;
+    // `quota` = how many histories a warp follows at once.  32 while there is plenty of work; in the small generations
+    // of the cascade's tail the host spreads the records over all warps (down to one per warp): histories that share a
+    // warp serialise each other whenever they disagree on the collision channel, and the tail is the critical path.
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
-        if (idle && !exhausted && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
-            const int nidle = __popc(idle);
+        const int room = quota - (32 - __popc(idle));
+        if (room > 0 && !exhausted && (room >= min(refill_min, quota) || idle == 0xffffffffu)) {
             uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(head, (uint32_t)nidle);
+            if (lane == 0) base = atomicAdd(head, (uint32_t)room);
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + (uint32_t)nidle >= n_in) exhausted = true;
+            if (base + (uint32_t)room >= n_in) exhausted = true;
             if (!active) {
-                const uint32_t my = base + __popc(idle & ((1u << lane) - 1u));
-                if (my < n_in) {
+                const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+                const uint32_t my = base + rank;
+                if (rank < (uint32_t)room && my < n_in) {
                     load_rec(qin, my, r);
                     active = true; nev = 0; have_rn = false;
                     if (SP == SP_ELECTRON) begin_electron(c_p, r, ig, k); else begin_vbhole(c_p, r, ig, k);
@@ -301,148 +318,6 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(Queue qin, uint32_t n_
     block_epilogue(c_p, s_tally, s_cnt);
 }
 
-// k_hot_all: the whole hot cascade of a batch in ONE persistent launch.  The hot queues are consumed while they grow:
-// a secondary created by a collision is picked up by any idle lane of the grid right away, instead of waiting for the
-// next generation, so that the duration of the cascade is the longest single lineage, not the sum of the longest
-// histories of all generations.  Protocol:
-//   producer (DevCtx::push_q): slot = atomicAdd(count) -> write the record -> __threadfence -> ready[slot] = epoch;
-//   consumer: lane 0 of a warp claims [h, h+n) with one compare-and-swap on the queue head, never beyond `count`; a
-//     claimed slot is reserved but possibly not yet written: the lane waits for ready[slot] (the writer is a lane of
-//     ANOTHER warp-round that is past its atomicAdd and needs no one to finish);
-//   termination: `hot_finished` counts claimed records whose processing ended; the cascade is over when it equals the
-//     sum of the hot queue counts (finished is read first: both only grow and finished <= sum at any time).
-// Warps are uniform in species (the round bodies differ); a warp changes species only when all its lanes are idle.
-// A watchdog bounds every wait: on expiry the kernel reports TRK3_ERR_QUEUE_OVERFLOW-class failure instead of hanging.
-__device__ inline uint32_t ld_volatile(const uint32_t *p) { return *(const volatile uint32_t *)p; }
-
-template <int SP>
-__device__ inline void hot_round(DevCtx &c, Rec &r, Cache &k, int &ig, double &RN, bool &have_rn, bool &active, int inel_min) {
-    if (SP == SP_ELECTRON || SP == SP_VBHOLE) {
-        int want = 0;       // 1 elastic, 2 inelastic
-        if (active) {
-            while (ig <= c_p.Nt && c_p.tg[ig - 1] <= r.tn) { if (SP == SP_ELECTRON) snapshot_electron(c, r, ig); else snapshot_hole(c, r, ig); ++ig; }
-            if (ig > c_p.Nt) active = false;
-            else {
-                if (!have_rn) { RN = rn(c_p, r); have_rn = true; }
-                want = hot_roulette<SP == SP_VBHOLE ? SP_VBHOLE : SP_ELECTRON>(k, RN) ? 2 : 1;
-            }
-        }
-        const unsigned m_in = __ballot_sync(0xffffffffu, want == 2), m_el = __ballot_sync(0xffffffffu, want == 1);
-        bool done_event = false;
-        if (m_in && (__popc(m_in) >= inel_min || !m_el)) {
-            if (want == 2) { hot_event<SP == SP_VBHOLE ? SP_VBHOLE : SP_ELECTRON, EV_INELASTIC>(c, r, ig, k, RN); done_event = true; }
-        }
-        if (want == 1) { hot_event<SP == SP_VBHOLE ? SP_VBHOLE : SP_ELECTRON, EV_ELASTIC>(c, r, ig, k, RN); done_event = true; }
-        if (done_event) {
-            have_rn = false;
-            if (hot_leaves<SP == SP_VBHOLE ? SP_VBHOLE : SP_ELECTRON>(r)) { c.push(SP, r); active = false; }      // to the cold queue
-        }
-    } else if (active) {
-        const int st = (SP == SP_COREHOLE) ? step_corehole(c, r, ig) : step_photon(c, r, ig);
-        if (st != ST_CONT) active = false;
-    }
-}
-
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot_all(QueueSet qs, uint32_t *heads, int use_smem, int refill_min, int inel_min, unsigned int spin_limit, int max_idle) {
-    extern __shared__ double s_dyn[];
-    __shared__ unsigned int s_cnt[S_NCNT];
-    double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
-    block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? c_p.s_total : 0);
-    DevCtx c{c_p, qs, s_tally, s_cnt};
-    const int lane = threadIdx.x & 31;
-    const unsigned warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    // preferred species of the warp: most warps serve electrons first; some start with the rarer species so that those
-    // (core holes whose decay releases energetic Auger electrons) are not left to the very end
-    const int pref = ((warp_id & 7u) < 6u) ? SP_ELECTRON : (((warp_id & 7u) == 6u) ? SP_VBHOLE : SP_COREHOLE);
-    int sp = pref;
-    bool active = false, have_rn = false;
-    Rec r;
-    Cache k{};
-    double RN = 0.0;
-    int ig = 0;
-    unsigned int spins = 0, idle_polls = 0, backoff = 64;
-    unsigned long long seen = ~0ull;
-    // Idle warps poll the queue counters; thousands of pollers would slow the atomics of the working lanes, so they back
-    // off exponentially and all but one warp per block retire for good after `max_idle` fruitless polls (always safe: a
-    // record is only ever produced by a warp that is still running and that refills its own idle lanes).
-    const bool keeper = (threadIdx.x >> 5) == 0;
-    for (;;) {
-        const unsigned idle = __ballot_sync(0xffffffffu, !active);
-        const int nidle = __popc(idle);
-        if (nidle >= refill_min || nidle == 32) {
-            // ---- claim records (lane 0), species-uniform per warp
-            uint32_t base = 0; int got = 0, s_new = sp;
-            if (lane == 0) {
-                bool hold = false;      // a warp that is away from its preferred species drains instead of refilling when that species has work
-                if (nidle < 32 && sp != pref) { uint32_t a = ld_volatile(qs.q[pref].count); if (a > qs.q[pref].cap) a = qs.q[pref].cap; hold = ld_volatile(heads + pref) < a; }
-                for (int t = 0; t < (nidle == 32 ? N_SPECIES + 1 : 1) && !got && !hold; ++t) {
-                    // order: current/preferred species first, then the others
-                    const int s = (nidle == 32) ? (t == 0 ? pref : t - 1) : sp;
-                    if (nidle == 32 && t > 0 && s == pref) continue;
-                    const Queue &q = qs.q[s];
-                    for (int tries = 0; tries < 4 && !got; ++tries) {
-                        const uint32_t h = ld_volatile(heads + s);
-                        uint32_t avail = ld_volatile(q.count); if (avail > q.cap) avail = q.cap;
-                        if (h >= avail) break;
-                        const uint32_t n = min((uint32_t)nidle, avail - h);
-                        if (atomicCAS(heads + s, h, h + n) == h) { base = h; got = (int)n; s_new = s; }
-                    }
-                }
-            }
-            got = __shfl_sync(0xffffffffu, got, 0);
-            if (got) {
-                base = __shfl_sync(0xffffffffu, base, 0);
-                sp = __shfl_sync(0xffffffffu, s_new, 0);
-                const int rank = __popc(idle & ((1u << lane) - 1u));
-                if (!active && rank < got) {
-                    const Queue &q = qs.q[sp];
-                    const uint32_t slot = base + (uint32_t)rank;
-                    unsigned int w = 0;
-                    while (ld_volatile(q.ready + slot) != c_p.epoch) { if (++w > spin_limit) { c.error(TRK3_ERR_QUEUE_OVERFLOW); break; } __nanosleep(20); }
-                    __threadfence();
-                    load_rec_cg(q, slot, r);
-                    active = true; have_rn = false;
-                    if (sp == SP_ELECTRON) begin_electron(c_p, r, ig, k);
-                    else if (sp == SP_VBHOLE) begin_vbhole(c_p, r, ig, k);
-                    else ig = interval_of(c_p, r.t0);
-                }
-            }
-        }
-        if (__ballot_sync(0xffffffffu, active) == 0u) {
-            // ---- nothing to do: is the cascade over?
-            int done = 0;
-            if (lane == 0) {
-                const unsigned long long F = *(volatile unsigned long long *)c_p.hot_finished;       // read BEFORE the counts
-                __threadfence();
-                unsigned long long R = 0;
-                for (int s = 0; s < N_SPECIES; ++s) { uint32_t n = ld_volatile(qs.q[s].count); if (n > qs.q[s].cap) n = qs.q[s].cap; R += n; }
-                done = (F == R) ? 1 : 0;
-                if (F + R != seen) { seen = F + R; spins = 0; }                                          // the cascade is making progress
-                if (!done && ++spins > spin_limit) { c.error(TRK3_ERR_QUEUE_OVERFLOW); done = 1; }      // watchdog: never hang the GPU
-            }
-            done = __shfl_sync(0xffffffffu, done, 0);
-            if (done) break;
-            if (!keeper && ++idle_polls > (unsigned)max_idle) break;
-            __nanosleep(backoff);
-            if (backoff < 8192u) backoff <<= 1;
-            continue;
-        }
-        spins = 0; idle_polls = 0; backoff = 64;
-        // ---- one round of the warp's species
-        const bool before = active;
-        switch (sp) {
-        case SP_ELECTRON: hot_round<SP_ELECTRON>(c, r, k, ig, RN, have_rn, active, inel_min); break;
-        case SP_VBHOLE: hot_round<SP_VBHOLE>(c, r, k, ig, RN, have_rn, active, inel_min); break;
-        case SP_COREHOLE: hot_round<SP_COREHOLE>(c, r, k, ig, RN, have_rn, active, inel_min); break;
-        default: hot_round<SP_PHOTON>(c, r, k, ig, RN, have_rn, active, inel_min); break;
-        }
-        // records whose processing ended in this round (their children, if any, are already counted in the queue counts)
-        const unsigned fin = __ballot_sync(0xffffffffu, before && !active);
-        if (fin && lane == 0) atomicAdd(c_p.hot_finished, (unsigned long long)__popc(fin));
-    }
-    block_epilogue(c_p, s_tally, s_cnt);
-}
-
 __global__ void k_iter_prefix(FoldAux a) {
     const uint32_t il = blockIdx.x * blockDim.x + threadIdx.x;
     if (il < c_p.batch_n) iter_prefix(c_p, a, il);
@@ -461,6 +336,8 @@ __global__ void k_companion(double *dst, const double *src, size_t n, int op) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = companion_value(src[i], op);
 }
+// end of a generation: remember the fill of the ionisation queue (overflow check on the host) and empty it
+__global__ void k_ion_reset(uint32_t *cnt) { if (threadIdx.x == 0) { if (cnt[0] > cnt[1]) cnt[1] = cnt[0]; cnt[0] = 0; } }
 __global__ void k_axpy(double *dst, const double *src, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] += src[i];
@@ -485,11 +362,9 @@ struct trk3_engine {
     double nel_est = 1000.0;
     // options
     int opt_batch = 1024, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
-    int opt_hot_slice = 1 << 30, opt_inel_min = 8, opt_overlap = 0, opt_cold_min = 16384, opt_persistent = 0;
-    unsigned int opt_spin_limit = 4000000u;
-    int opt_max_idle = 32;
-    uint32_t epoch = 0;
-    unsigned long long *d_hotfin = nullptr;
+    int opt_hot_slice = 32, opt_inel_min = 8, opt_overlap = 0, opt_cold_min = 16384;
+    int opt_spread = 1, opt_quota_min = 1;
+
     double opt_cap_factor = 2.0;
     size_t opt_queue_bytes_max = (size_t)24 << 30;
     // per-batch resources
@@ -516,12 +391,14 @@ struct trk3_engine {
 };
 
 // d_qcount layout (uint32): [0..3] hot counts generation A, [4..7] generation B, [8..9] cold counts,
-// [10..13] hot counts of set X (particles handed back by the cold kernels), [14..17] hot heads, [18..19] cold heads
+// [10..13] hot counts of set X (particles handed back by the cold kernels), [14] ionisations of the generation,
+// [15] their high-water mark, [16..19] hot heads, [20..21] cold heads
 #define QC_HOT(b) ((b) * N_SPECIES)
 #define QC_COLD (2 * N_SPECIES)
 #define QC_X (2 * N_SPECIES + 2)
-#define QC_HEAD (3 * N_SPECIES + 2)
-#define QC_TOTAL (4 * N_SPECIES + 4)
+#define QC_ION (3 * N_SPECIES + 2)
+#define QC_HEAD (3 * N_SPECIES + 4)
+#define QC_TOTAL (4 * N_SPECIES + 6)
 
 namespace {
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { eng->err = std::string(#call) + ": " + cudaGetErrorString(e_); return TRK3_E_CUDA; } } while (0)
@@ -598,14 +475,12 @@ int alloc_queue(trk3_engine *eng, Queue &q, uint32_t cap, uint32_t *count) {
     if ((rc = dev_alloc(eng, &q.ctr, cap))) return rc;
     if ((rc = dev_alloc(eng, &q.iter, cap))) return rc;
     if ((rc = dev_alloc(eng, &q.shell, cap))) return rc;
-    if ((rc = dev_alloc(eng, &q.ready, cap))) return rc;
-    CK(cudaMemsetAsync(q.ready, 0, (size_t)cap * sizeof(uint32_t), eng->stream));
     return TRK3_OK;
 }
 void free_queue(trk3_engine *eng, Queue &q) {
     for (int k = 0; k < TRK_NCOL; ++k) { dev_free(eng, q.col[k]); q.col[k] = nullptr; }
-    dev_free(eng, q.id); dev_free(eng, q.ctr); dev_free(eng, q.iter); dev_free(eng, q.shell); dev_free(eng, q.ready);
-    q.id = nullptr; q.ctr = nullptr; q.iter = nullptr; q.shell = nullptr; q.ready = nullptr; q.cap = 0;
+    dev_free(eng, q.id); dev_free(eng, q.ctr); dev_free(eng, q.iter); dev_free(eng, q.shell);
+    q.id = nullptr; q.ctr = nullptr; q.iter = nullptr; q.shell = nullptr; q.cap = 0;
 }
 
 // per-iteration capacities of the species queues (records of ONE generation)
@@ -614,6 +489,7 @@ void queue_caps(const trk3_engine *eng, double cap[N_QUEUES]) {
     cap[SP_ELECTRON] = n; cap[SP_VBHOLE] = n; cap[SP_COREHOLE] = 0.5 * n + 256.0;
     cap[SP_PHOTON] = eng->cfg.include_photons ? 0.25 * n + 64.0 : 1.0;
     cap[Q_EL_COLD] = n; cap[Q_VB_COLD] = n;       // every carrier of an iteration ends up here once
+    cap[Q_ION] = n;
 }
 double queue_bytes_per_iteration(const trk3_engine *eng) {
     double cap[N_QUEUES]; queue_caps(eng, cap);
@@ -639,8 +515,8 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
         int rc = alloc_queue(eng, eng->qs[b].q[s], (uint32_t)(cap[s] * (double)nb), eng->d_qcount + QC_HOT(b) + s);
         if (rc) return rc;
     }
-    for (int s = N_SPECIES; s < N_QUEUES; ++s) {      // the cold queues are shared by both generations
-        int rc = alloc_queue(eng, eng->qs[0].q[s], (uint32_t)(cap[s] * (double)nb), eng->d_qcount + QC_COLD + (s - N_SPECIES));
+    for (int s = N_SPECIES; s < N_QUEUES; ++s) {      // the cold queues and the ionisation queue are shared by both generations
+        int rc = alloc_queue(eng, eng->qs[0].q[s], (uint32_t)(cap[s] * (double)nb), eng->d_qcount + (s == Q_ION ? QC_ION : QC_COLD + (s - N_SPECIES)));
         if (rc) return rc;
         eng->qs[1].q[s] = eng->qs[0].q[s]; eng->qs_x.q[s] = eng->qs[0].q[s];
     }
@@ -696,11 +572,16 @@ int launch_hot(trk3_engine *eng, const Queue &qin, uint32_t n, uint32_t *head, c
     int bps = eng->opt_blocks_per_sm;
     const int block = eng->opt_block;
     if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_hot<SP>, block, smem)); if (bps < 1) bps = 1; }
-    uint32_t want = (n + block - 1) / block;
+    // records per warp: spread a small generation over all the warps the GPU can hold (see k_hot)
+    const uint32_t wpb = (uint32_t)block / 32u, max_warps = (uint32_t)(eng->n_sm * bps) * wpb;
+    uint32_t quota = eng->opt_spread ? (n + max_warps - 1) / max_warps : 32u;
+    if (quota > 32u) quota = 32u;
+    if (quota < (uint32_t)eng->opt_quota_min) quota = (uint32_t)eng->opt_quota_min;
+    uint32_t want = (n + quota * wpb - 1) / (quota * wpb);
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (grid < 1) grid = 1;
     const int pi = prof_begin(eng, SP);
-    k_hot<SP><<<grid, block, smem, eng->stream>>>(qin, n, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice, eng->opt_inel_min);
+    k_hot<SP><<<grid, block, smem, eng->stream>>>(qin, n, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice, eng->opt_inel_min, (int)quota);
     prof_end(eng, pi);
     CK(cudaGetLastError());
     eng->launches++;
@@ -754,7 +635,7 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
     }
     CK(cudaStreamSynchronize(eng->stream));
     p.tally = old.tally; p.events = old.events; p.errors = old.errors; p.cnt_el = old.cnt_el; p.cnt_ph = old.cnt_ph; p.it = old.it;
-    p.hot_finished = old.hot_finished;
+
     eng->nel_est = estimate_nel(*cfg, *tab);
     return TRK3_OK;
 }
@@ -796,8 +677,7 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
     if ((rc = dev_alloc(eng, &eng->d_counters, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 4)))) return rc;
     if ((rc = dev_alloc(eng, &eng->d_counters_bak, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 4)))) return rc;
     if ((rc = dev_alloc(eng, &eng->d_qcount, (size_t)QC_TOTAL))) return rc;
-    if ((rc = dev_alloc(eng, &eng->d_hotfin, (size_t)1))) return rc;
-    eng->hp.hot_finished = eng->d_hotfin;
+
     p.tally = eng->d_tally;
     p.events = eng->d_counters; p.errors = eng->d_counters + TRK3_N_EVENT_CLASSES;
     p.cnt_el = eng->d_counters + TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS; p.cnt_ph = p.cnt_el + 1;
@@ -831,10 +711,9 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "queue_gib") eng->opt_queue_bytes_max = (size_t)(v * (double)(1ull << 30));
     else if (k == "block") eng->opt_block = std::min(TRK_BLOCK_MAX, std::max(32, ((int)v / 32) * 32));
     else if (k == "hot_slice") eng->opt_hot_slice = std::max(1, (int)v);
+    else if (k == "spread") eng->opt_spread = (v != 0.0);
+    else if (k == "quota_min") eng->opt_quota_min = std::min(32, std::max(1, (int)v));
     else if (k == "overlap") eng->opt_overlap = (v != 0.0);
-    else if (k == "max_idle") eng->opt_max_idle = std::max(0, (int)v);
-    else if (k == "persistent") eng->opt_persistent = (v != 0.0);
-    else if (k == "spin_limit") eng->opt_spin_limit = (unsigned int)std::max(1000.0, v);
     else if (k == "cold_min") eng->opt_cold_min = std::max(1, (int)v);
     else if (k == "inel_min") eng->opt_inel_min = std::min(32, std::max(1, (int)v));
     else if (k == "max_generations") eng->opt_max_generations = std::max(1, (int)v);
@@ -890,9 +769,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         CK(cudaMemcpyAsync(eng->d_tally_bak, eng->d_tally, (size_t)eng->lay.total * sizeof(double), cudaMemcpyDeviceToDevice, eng->stream));
         CK(cudaMemcpyAsync(eng->d_counters_bak, eng->d_counters, n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, eng->stream));
         eng->hp.batch_begin = (uint32_t)b0; eng->hp.batch_n = nb;
-        if (++eng->epoch == 0) eng->epoch = 1;
-        eng->hp.epoch = eng->epoch;
-        CK(cudaMemsetAsync(eng->d_hotfin, 0, sizeof(unsigned long long), eng->stream));
+
         CK(cudaMemcpyToSymbolAsync(c_p, &eng->hp, sizeof(DevP), 0, cudaMemcpyHostToDevice, eng->stream));
         CK(cudaMemsetAsync(eng->d_u32, 0, eng->sl.u32_total * sizeof(uint32_t), eng->stream));
         CK(cudaMemsetAsync(eng->d_f64, 0, eng->sl.f64_total * sizeof(double), eng->stream));
@@ -908,51 +785,10 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         int cur = 0;
         bool overflow = false;
         uint32_t cold_done[2] = {0, 0};
-        if (eng->opt_persistent) {
-            // ---- the hot cascade in one persistent launch (k_hot_all), then the cold queues; repeated in the rare case
-            //      that a cold kernel hands a particle back to the hot queues
-            size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
-            int use_smem = eng->opt_use_smem;
-            if (smem > (size_t)eng->smem_optin - 1024) { smem = 8; use_smem = 0; }
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_hot_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int bps = eng->opt_blocks_per_sm;
-            const int block = eng->opt_block;
-            if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_hot_all, block, smem)); if (bps < 1) bps = 1; }
-            uint64_t hot_seen = 0;
-            for (int round = 0; round < eng->opt_max_generations; ++round) {
-                ++waves;
-                { const int pi = prof_begin(eng, SP_ELECTRON);
-                  k_hot_all<<<eng->n_sm * bps, block, smem, eng->stream>>>(eng->qs[0], heads, use_smem, eng->opt_refill_min, eng->opt_inel_min, eng->opt_spin_limit, eng->opt_max_idle);
-                  prof_end(eng, pi); }
-                CK(cudaGetLastError());
-                eng->launches++;
-                uint32_t h_cnt[QC_X];
-                CK(cudaMemcpyAsync(h_cnt, eng->d_qcount, sizeof h_cnt, cudaMemcpyDeviceToHost, eng->stream));
-                CK(cudaStreamSynchronize(eng->stream));
-                uint32_t *hot = h_cnt + QC_HOT(0), *cold = h_cnt + QC_COLD;
-                if (h_cnt[QC_HOT(1) + SP_ELECTRON] > eng->qs[1].q[SP_ELECTRON].cap) overflow = true;     // staged ion collisions
-                hot_seen = 0;
-                for (int s = 0; s < N_SPECIES; ++s) { if (hot[s] > eng->qs[0].q[s].cap) overflow = true; hot_seen += hot[s]; }
-                for (int s = 0; s < 2; ++s) if (cold[s] > eng->qs[0].q[N_SPECIES + s].cap) overflow = true;
-                if (overflow) break;
-                if (cold[0] == cold_done[0] && cold[1] == cold_done[1]) break;
-                ++waves;
-                CK(cudaMemsetAsync(heads + N_SPECIES, 0, 2 * sizeof(uint32_t), eng->stream));
-                if (cold[0] > cold_done[0]) { rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[0].q[Q_EL_COLD], cold_done[0], cold[0], heads + Q_EL_COLD, eng->qs[0]); if (rc) return rc; }
-                if (cold[1] > cold_done[1]) { rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[0].q[Q_VB_COLD], cold_done[1], cold[1], heads + Q_VB_COLD, eng->qs[0]); if (rc) return rc; }
-                cold_done[0] = cold[0]; cold_done[1] = cold[1];
-                uint32_t h_hot[N_SPECIES];
-                CK(cudaMemcpyAsync(h_hot, eng->d_qcount + QC_HOT(0), sizeof h_hot, cudaMemcpyDeviceToHost, eng->stream));
-                CK(cudaStreamSynchronize(eng->stream));
-                uint64_t now = 0;
-                for (int s = 0; s < N_SPECIES; ++s) { if (h_hot[s] > eng->qs[0].q[s].cap) overflow = true; now += h_hot[s]; }
-                if (overflow || now == hot_seen) break;      // nothing was handed back: done
-            }
-        }
         cudaStream_t sc = eng->opt_overlap ? eng->stream_c : eng->stream;       // stream of the cold kernels
         if (eng->opt_overlap) { CK(cudaEventRecord(eng->ev_fork, eng->stream)); CK(cudaStreamWaitEvent(sc, eng->ev_fork, 0)); }
-        for (int gen = 0; gen < eng->opt_max_generations && !eng->opt_persistent; ++gen) {
-            uint32_t h_cnt[QC_X];              // hot counts of both generations + cold counts
+        for (int gen = 0; gen < eng->opt_max_generations; ++gen) {
+            uint32_t h_cnt[QC_HEAD];           // hot counts of both generations, cold counts, set X, ionisation queue
             CK(cudaMemcpyAsync(h_cnt, eng->d_qcount, sizeof h_cnt, cudaMemcpyDeviceToHost, eng->stream));
             CK(cudaStreamSynchronize(eng->stream));
             uint32_t *hot = h_cnt + QC_HOT(cur), *cold = h_cnt + QC_COLD;
@@ -960,6 +796,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             if (gen == 0 && h_cnt[QC_HOT(1) + SP_ELECTRON] > eng->qs[1].q[SP_ELECTRON].cap) overflow = true;     // staged ion collisions
             for (int s = 0; s < N_SPECIES; ++s) { if (hot[s] > eng->qs[cur].q[s].cap) { overflow = true; hot[s] = eng->qs[cur].q[s].cap; } total += hot[s]; }
             for (int s = 0; s < 2; ++s) if (cold[s] > eng->qs[0].q[N_SPECIES + s].cap) { overflow = true; cold[s] = eng->qs[0].q[N_SPECIES + s].cap; }
+            if (h_cnt[QC_ION + 1] > eng->qs[0].q[Q_ION].cap) overflow = true;
             if (overflow) break;
             const uint64_t cold_pending = (uint64_t)(cold[0] - cold_done[0]) + (cold[1] - cold_done[1]);
             ++waves;
@@ -971,6 +808,14 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
                 if (hot[SP_VBHOLE]) { rc = launch_hot<SP_VBHOLE>(eng, eng->qs[cur].q[SP_VBHOLE], hot[SP_VBHOLE], heads + SP_VBHOLE, eng->qs[nxt]); if (rc) return rc; }
                 if (hot[SP_COREHOLE]) { rc = launch_wave<SP_COREHOLE, false>(eng, eng->qs[cur].q[SP_COREHOLE], 0, hot[SP_COREHOLE], heads + SP_COREHOLE, eng->qs[nxt]); if (rc) return rc; }
                 if (hot[SP_PHOTON]) { rc = launch_wave<SP_PHOTON, false>(eng, eng->qs[cur].q[SP_PHOTON], 0, hot[SP_PHOTON], heads + SP_PHOTON, eng->qs[nxt]); if (rc) return rc; }
+                if (hot[SP_ELECTRON]) {     // the pairs of this generation's impact ionisations join the next generation
+                    const int pi = prof_begin(eng, SP_ELECTRON);
+                    k_ion_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(eng->qs[0].q[Q_ION], eng->qs[nxt]);
+                    k_ion_reset<<<1, 32, 0, eng->stream>>>(eng->d_qcount + QC_ION);
+                    prof_end(eng, pi);
+                    CK(cudaGetLastError());
+                    eng->launches += 2;
+                }
                 cur = nxt;
             }
             // cold kernels: on the second stream, beside the next hot generation, as soon as enough records have gathered
@@ -994,6 +839,12 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             CK(cudaMemsetAsync(heads, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
             if (h_x[SP_ELECTRON]) { rc = launch_hot<SP_ELECTRON>(eng, eng->qs_x.q[SP_ELECTRON], h_x[SP_ELECTRON], heads + SP_ELECTRON, eng->qs[nxt]); if (rc) return rc; }
             if (h_x[SP_VBHOLE]) { rc = launch_hot<SP_VBHOLE>(eng, eng->qs_x.q[SP_VBHOLE], h_x[SP_VBHOLE], heads + SP_VBHOLE, eng->qs[nxt]); if (rc) return rc; }
+            if (h_x[SP_ELECTRON]) {
+                k_ion_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(eng->qs[0].q[Q_ION], eng->qs[nxt]);
+                k_ion_reset<<<1, 32, 0, eng->stream>>>(eng->d_qcount + QC_ION);
+                CK(cudaGetLastError());
+                eng->launches += 2;
+            }
             CK(cudaMemsetAsync(eng->d_qcount + QC_X, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
             cur = nxt;
         }

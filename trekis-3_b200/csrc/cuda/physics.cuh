@@ -10,6 +10,7 @@
 //   c.p                      const DevP&  (tables, switches, time grid)
 //   c.push(species, rec)     append a particle to a queue (the context routes it: hot/cold, see electron_is_cold)
 //   c.push_hot(species, rec) append to the queue of the full handlers regardless of the routing rule
+//   c.push_ion(ev)           hand an impact ionisation over: its electron-hole pair is created by electron_ion_emit
 //   c.tally(id, idx, v)      add v to element idx of Out_* array `id` (block-private or global)
 //   c.add_u32(base, idx)     atomic ++ on a per-iteration integer histogram
 //   c.add_f64(base, idx, v)  atomic += on a per-iteration double array
@@ -685,6 +686,33 @@ TRK_HD void deposit_lattice(C &c, const Rec &r, int iv, double X, double Y, doub
 // in its post-collision state with a new tn.  `iv` is the time interval of the event.
 // ------------------------------------------------------------------------------------------------
 
+// An impact ionisation by an electron, as far as the creation of its electron-hole pair needs it (:2321-2371).
+// The pair does not feed back into the history of the primary, so its creation is split off (electron_ion_emit) and
+// runs as parallel work instead of lengthening the serial chain of a delta-electron, which is the critical path of a
+// batch.  Stream convention as for the ion (shi_emit): the primary's stream gives the primary's draws and the
+// children's ids; the draws that create the electron / the hole come from the new particle's own stream.
+struct IonEvent {
+    double dE, t, X, Y, Z;          // transferred energy, time and place of the collision
+    double theta0, phi0;            // direction of the primary before the collision
+    double theta, phi;              // its scattering angles (Update_electron_angles_El)
+    int32_t shell;
+    uint64_t pid; uint32_t ctr0;    // primary's stream at the creation of the pair (children's ids)
+    uint32_t iter;
+};
+template <class C>
+TRK_HD void electron_ion_emit(C &c, const IonEvent &ev) {
+    const DevP &p = c.p;
+    Rec par; par.id = ev.pid; par.ctr = ev.ctr0; par.iter = ev.iter;
+    const uint64_t id_e = child_id(p, par, 1), id_h = child_id(p, par, 2);
+    Rec se; se.id = id_e; se.ctr = 0; se.iter = ev.iter;
+    Rec sh; sh.id = id_h; sh.ctr = 0; sh.iter = ev.iter;
+    double dE_cur = electron_receives_E(c, se, ev.dE, ev.shell);
+    double phi1, theta1;
+    new_angles(ev.phi0, ev.theta0, TRK_PI / 2.0 - ev.theta, ev.phi + TRK_PI, phi1, theta1);
+    emit_electron(c, se, id_e, dE_cur, ev.t, ev.X, ev.Y, ev.Z, theta1, phi1, TRK3_ERR_21);
+    emit_hole(c, sh, id_h, ev.shell, ev.dE - dE_cur, ev.t, ev.X, ev.Y, ev.Z, TRK3_ERR_20);
+}
+
 // Electron_Monte_Carlo, Monte_Carlo.f90:2253-2474.
 // RN is the first draw of the collision (the channel roulette, :2301), made by the caller.
 // MODE selects what is compiled in: EV_ANY = both channels (run-time roulette), EV_ELASTIC / EV_INELASTIC = one
@@ -706,17 +734,16 @@ TRK_HD void electron_event_t(C &c, Rec &e, int iv, Cache &k, double RN) {
         c.event(TRK3_EV_EL_INEL);
         int n_E;
         int shell = which_shell(p, e, tab_ei_L(p), Eel, k.lE, n_E);
-        uint64_t id_e = child_id(p, e, 1), id_h = child_id(p, e, 2);
+        IonEvent ev;
+        ev.pid = e.id; ev.ctr0 = e.ctr; ev.iter = e.iter;
+        e.ctr += 2;                                              // the two child ids
         IMFP = nfp_at(tab_shell(tab_ei_L(p), shell), n_E, false, Eel, k.lE);      // Next_free_path_1d, same grid => same index
         dE = inelastic_dE(p, e, Eel, k.lE, n_E, shell, IMFP, false);
         theta = acos((Eel - dE) / sqrt(Eel * (Eel - dE)));       // Update_electron_angles_El :1189
         if (trk_isnan(theta)) { double r2 = rn(p, e); theta = r2 * TRK_PI; }
         { double r2 = rn(p, e); phi = 2.0 * TRK_PI * r2; }
-        double dE_cur = electron_receives_E(c, e, dE, shell);
-        double phi1, theta1;
-        new_angles(phi0, theta0, TRK_PI / 2.0 - theta, phi + TRK_PI, phi1, theta1);
-        emit_electron(c, e, id_e, dE_cur, t_ev, X, Y, Z, theta1, phi1, TRK3_ERR_21);
-        emit_hole(c, e, id_h, shell, dE - dE_cur, t_ev, X, Y, Z, TRK3_ERR_20);
+        ev.dE = dE; ev.t = t_ev; ev.X = X; ev.Y = Y; ev.Z = Z; ev.theta0 = theta0; ev.phi0 = phi0; ev.theta = theta; ev.phi = phi; ev.shell = shell;
+        c.push_ion(ev);                                          // the pair: electron_ion_emit
     } else {                                                     // elastic: energy to the lattice
         c.event(TRK3_EV_EL_ELAST);
         EMFP = elastic_total(tab_ee(p), Eel, k);
