@@ -362,7 +362,7 @@ struct trk3_engine {
     double nel_est = 1000.0;
     // options
     int opt_batch = 1024, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
-    int opt_hot_slice = 32, opt_inel_min = 8, opt_overlap = 0, opt_cold_min = 16384;
+    int opt_hot_slice = 64, opt_inel_min = 1, opt_overlap = 0, opt_cold_min = 16384;
     int opt_spread = 1, opt_quota_min = 1;
 
     double opt_cap_factor = 2.0;

@@ -20,10 +20,14 @@
 // (Keeping the large helpers -- Philox rounds, table sampling -- out of line was measured on B200: 36.3 ms instead of
 // 31.0 ms per 1000 iterations of config C2; the call/stack traffic costs more than the smaller code gains.)
 #define TRK_HDN __host__ __device__ inline
+// (the same holds for the code of switches that are off in a run -- Mott scattering, electron emission: out of line it made
+// the cold kernels 7-10 % slower)
+#define TRK_HD_RARE __host__ __device__ inline
 #else
 #define TRK_HD inline
 #define TRK_D inline
 #define TRK_HDN inline
+#define TRK_HD_RARE inline
 #endif
 
 namespace trk3 {

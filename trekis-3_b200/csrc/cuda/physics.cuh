@@ -386,6 +386,15 @@ TRK_HDN double mott_dE(const DevP &p, Rec &r, double Mat, double Zat, double Ee,
     double W2 = Ee * E2mc / (EmcMc * EmcMc - Ee * E2mc * ct2);
     return W1 * W2;
 }
+// kind_of_EMFP = 0: stoichiometric average of the atomic (Mott) energy transfers, Monte_Carlo.f90:2393-2401
+TRK_HD_RARE double mott_elastic_dE(const DevP &p, Rec &r, double Eel, double M_eff) {
+    double dE = 0.0;
+    for (int ii = 0; ii < p.n_atoms; ++ii) {
+        double dE_loc = mott_dE(p, r, p.atom_mass[ii] * TRK_MP, (double)p.atom_Z[ii], Eel, M_eff);
+        dE = dE + dE_loc * p.atom_pers[ii];
+    }
+    return dE / p.sum_pers;
+}
 // elastic energy transfer: the kind_of_EMFP switch of Monte_Carlo.f90:2387-2407 / :2668-2692
 TRK_HD double elastic_dE(const DevP &p, Rec &r, double Eel, const Cache &k, double EMFP, bool hole, double M_eff) {
     if (p.kind_of_EMFP == 1) {      // Electron_energy_transfer_elastic, Cross_sections.f90:2403-2413
@@ -395,12 +404,7 @@ TRK_HD double elastic_dE(const DevP &p, Rec &r, double Eel, const Cache &k, doub
         if (hw >= Eel) hw = Eel;
         return hw;
     }
-    double dE = 0.0;
-    for (int ii = 0; ii < p.n_atoms; ++ii) {
-        double dE_loc = mott_dE(p, r, p.atom_mass[ii] * TRK_MP, (double)p.atom_Z[ii], Eel, hole ? M_eff : 1.0);
-        dE = dE + dE_loc * p.atom_pers[ii];
-    }
-    return dE / p.sum_pers;
+    return mott_elastic_dE(p, r, Eel, hole ? M_eff : 1.0);
 }
 
 // cos_theta_from_W + Update_particle_angles_lat, Monte_Carlo.f90:1252-1299
@@ -686,6 +690,29 @@ TRK_HD void deposit_lattice(C &c, const Rec &r, int iv, double X, double Y, doub
 // in its post-collision state with a new tn.  `iv` is the time interval of the event.
 // ------------------------------------------------------------------------------------------------
 
+// calculate_emission, Monte_Carlo.f90:2477-2513: an electron that has crossed the surface (Z < 0) is emitted or reflected
+template <class C>
+TRK_HD_RARE void electron_emission(C &c, Rec &e, int iv) {
+    const DevP &p = c.p;
+    bool emitted = false; double Ekin = 0.0;
+    if (e.E >= 1.5 * p.bar_height) { emitted = true; Ekin = e.E - p.work_function; }
+    else {
+        double r2 = rn(p, e);
+        double Em_Penetr = 1.0 / (1.0 + exp(p.Em_gamma * (p.Em_E1 - e.E)));
+        Ekin = e.E - p.work_function;
+        if (Ekin > 0.0 && r2 < Em_Penetr) emitted = true;
+        else if (cos(e.theta) < 0) e.theta = TRK_PI - e.theta;
+    }
+    if (emitted) {
+        e.tn = 1.0e30; e.L = 1.0e30;
+        const size_t b = (size_t)(e.iter - p.batch_begin) * (p.Nt + 2) + iv;
+        c.add_u32(p.it.em_cnt, b);
+        c.add_f64(p.it.em_E, b, Ekin);
+        const int j = find_1d(p.out_R, p.n_r, Ekin * 10.0);      // Out_E = Out_R/10 (:940-941)
+        c.add_u32(p.it.em_spec, b * p.n_r + (j - 1));
+    }
+}
+
 // An impact ionisation by an electron, as far as the creation of its electron-hole pair needs it (:2321-2371).
 // The pair does not feed back into the history of the primary, so its creation is split off (electron_ion_emit) and
 // runs as parallel work instead of lengthening the serial chain of a delta-electron, which is the critical path of a
@@ -761,26 +788,7 @@ TRK_HD void electron_event_t(C &c, Rec &e, int iv, Cache &k, double RN) {
     e.E = Eel - dE; e.t0 = t_ev; e.X = X; e.Y = Y; e.Z = Z; e.L = MFP_tot; e.theta = theta1; e.phi = phi1;
     e.tn = next_time(e.t0, vel_electron(e.E), MFP_tot);
     if (e.E < p.cut_off) e.tn = 1.0e20;
-    if (p.work_function > 0 && e.Z < 0.0) {                      // calculate_emission, :2477-2513
-        bool emitted = false; double Ekin = 0.0;
-        if (e.E >= 1.5 * p.bar_height) { emitted = true; Ekin = e.E - p.work_function; }
-        else {
-            double r2 = rn(p, e);
-            double Em_Penetr = 1.0 / (1.0 + exp(p.Em_gamma * (p.Em_E1 - e.E)));
-            Ekin = e.E - p.work_function;
-            if (Ekin > 0.0 && r2 < Em_Penetr) emitted = true;
-            else if (cos(e.theta) < 0) e.theta = TRK_PI - e.theta;
-        }
-        if (emitted) {
-            e.tn = 1.0e30; e.L = 1.0e30;
-            const size_t b = (size_t)(e.iter - p.batch_begin) * (p.Nt + 2) + iv;
-            c.add_u32(p.it.em_cnt, b);
-            c.add_f64(p.it.em_E, b, Ekin);
-            // Out_E = Out_R/10 (:940-941)
-            int j = 1; { double v = Ekin * 10.0; j = find_1d(p.out_R, p.n_r, v); }
-            c.add_u32(p.it.em_spec, b * p.n_r + (j - 1));
-        }
-    }
+    if (p.work_function > 0 && e.Z < 0.0) electron_emission(c, e, iv);
     if (e.E < -1.0e-9 || trk_isnan(e.E)) c.error(TRK3_ERR_22);
 }
 
