@@ -172,3 +172,77 @@ def test_high_multiplicity_gold(case_c4):
     assert not s["errors"] and s["max_energy_drift"] < 1e-9
     assert abs(s["total_events"] - se["total_events"]) <= 2e-3 * se["total_events"]
     assert np.isclose(t.sum(), te.sum(), rtol=1e-3)
+
+
+# ---- BASELINE.json configurations at their full sizes: size-independent properties ------------------------------------
+def _invariants(case, t, s, n, Se_expected=None):
+    assert not s["errors"] and s["max_energy_drift"] < 1e-9
+    lay = case.layout()
+    T = split_tallies(lay, t)
+    A = case.table_arrays()
+    V = A["out_V"]
+    # every electron sits in exactly one radial bin at every grid time; one hole per electron
+    assert np.allclose((T["Out_ne"] / V[None, :]).sum(axis=1), T["Out_tot_Ne"], rtol=1e-9)
+    assert np.allclose((T["Out_nh"] / V[None, :, None, None]).sum(axis=(1, 2, 3)), T["Out_tot_Ne"], rtol=1e-9)
+    assert np.all(np.diff(T["Out_tot_Ne"]) >= 0) and T["Out_tot_Ne"][-1] == s["n_electrons"]
+    # spectra are normalised per iteration
+    dR = np.diff(np.concatenate([[0.0], A["out_R"]]))
+    assert np.allclose((T["Out_Ee_vs_E"] * dR[None, :]).sum(axis=1), n, rtol=1e-9)
+    # energy bookkeeping at every grid time
+    tot = T["Out_E_e"] + T["Out_E_h"].sum(axis=(1, 2)) + T["Out_E_at"] + T["Out_E_phot"]
+    assert np.allclose(T["Out_tot_E"], tot, rtol=1e-9)
+    assert np.allclose(np.cumsum((T["Out_Elat"] / V[None, :]).sum(axis=1)), T["Out_E_at"], rtol=1e-9)
+    assert np.all(np.diff(T["Out_E_at"]) >= 0)
+    if Se_expected:
+        assert T["Out_tot_E"][-1] / n == pytest.approx(Se_expected, rel=0.05)
+    return T
+
+
+def test_full_size_c2_photons_and_decays():
+    """BASELINE config 2 (Au 2187 MeV in SiO2, photons + Auger/radiative decays, 1000 iterations): the bench workload."""
+    case = tk.Case.load(tk.make_run_dir("/tmp/trk3_full_c2", "C2"))
+    case.build_tables(shi_window_only=True, cache_dir=CACHE)
+    n = 1000
+    eng = tk.Engine(case)
+    t, s = eng.run(0, n)
+    T = _invariants(case, t, s, n)
+    assert s["total_events"] > 3e7 and s["events"]["auger"] > 1e4 and s["cold_events"]["electron"] > 0.9 * s["events"]["el_elastic"]
+    # the same 1000 iterations in four batches of 250 with other kernel options: identical histories
+    t2, s2 = tk.Engine(case, batch=250, hot_slice=16, inel_min=8).run(0, n)
+    assert s2["events"] == s["events"]
+    i = tk.TALLY_NAMES.index("Out_diff_coeff")
+    lay = case.layout()
+    m = np.ones(lay.total, bool); m[lay.off[i]: lay.off[i] + lay.len[i]] = False
+    assert rel_close(t2[m], t[m], 1e-9)
+
+
+def test_full_size_c3_diamond(case_c3):
+    """BASELINE config 3 (Xe 167 MeV in diamond, valence-hole impact ionisation, single-pole phonons), 100 iterations."""
+    n = 100
+    t, s = tk.Engine(case_c3).run(0, n)
+    _invariants(case_c3, t, s, n)
+    assert s["events"]["vbh_inelastic"] > 1e4
+
+
+def test_c4_gold_many_iterations(case_c4):
+    """BASELINE config 4 (U 2600 MeV in Au: >1e5 carriers per iteration, no cold range above 0.1 eV), 64 iterations."""
+    n = 64
+    t, s = tk.Engine(case_c4).run(0, n)
+    _invariants(case_c4, t, s, n)
+    assert s["n_electrons"] > 5e4 * n
+
+
+def test_c5_high_statistics_sweep_composes(case_c1):
+    """BASELINE config 5 (Xe 167 MeV in Al2O3, high-statistics sweep): 10 000 iterations in several batches; the two halves
+    (what two GPUs would run) add up to the whole."""
+    n = 10000
+    eng = tk.Engine(case_c1, batch=4096)
+    whole, sw = eng.run(0, n)
+    _invariants(case_c1, whole, sw, n, Se_expected=26188.0)
+    a, sa = eng.run(0, n // 2)
+    b, sb = eng.run(n // 2, n)
+    lay = case_c1.layout()
+    i = tk.TALLY_NAMES.index("Out_diff_coeff")
+    m = np.ones(lay.total, bool); m[lay.off[i]: lay.off[i] + lay.len[i]] = False
+    assert sw["total_events"] == sa["total_events"] + sb["total_events"]
+    assert rel_close((a + b)[m], whole[m], 1e-9)
