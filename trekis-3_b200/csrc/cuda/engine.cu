@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) k_ion_emit(Queue ionq, QueueSet qout) {
 // k_wave<SP, COLD>: records [first, n_in) of queue qin, histories followed with lane refill until they end or
 // have to change queue (hot -> cold when the particle can no longer ionise, core hole -> valence hole, ...).
 template <int SP, bool COLD>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int lockstep) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
@@ -226,7 +226,11 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
                 }
             }
         }
-        if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; continue; }
+        // The kernels are bound by instruction fetch (ncu: gcc__cache_requests_type_instruction at 98 % of peak, the loop
+        // body is several times the SM's instruction cache).  With `lockstep` the warps of a block start every round
+        // together, so that the lines one warp fetches are still cached when the others need them.
+        if (lockstep) { if (!__syncthreads_or((active || !exhausted) ? 1 : 0)) break; }
+        else if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; continue; }
         if (active) {
             int st;
             if (SP == SP_ELECTRON) st = step_electron<COLD>(c, r, ig, k);
@@ -258,7 +262,7 @@ template <int SP, int MODE> __device__ inline void hot_event(DevCtx &c, Rec &r, 
 template <int SP> __device__ inline bool hot_leaves(const Rec &r) { return SP == SP_ELECTRON ? electron_leaves_hot(c_p, r) : vbhole_leaves_hot(c_p, r); }
 
 template <int SP>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(Queue qin, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int inel_min, int quota) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(Queue qin, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int inel_min, int quota, int lockstep) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
@@ -291,7 +295,8 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(Queue qin, uint32_t n_
                 }
             }
         }
-        if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; continue; }
+        if (lockstep) { if (!__syncthreads_or((active || !exhausted) ? 1 : 0)) break; }
+        else if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; continue; }
         // snapshots of the current free flight, then the channel roulette of the collision that ends it
         int want = 0;       // 1 elastic, 2 inelastic
         if (active) {
@@ -363,7 +368,7 @@ struct trk3_engine {
     // options
     int opt_batch = 1024, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
     int opt_hot_slice = 64, opt_inel_min = 1, opt_overlap = 0, opt_cold_min = 16384;
-    int opt_spread = 1, opt_quota_min = 1;
+    int opt_spread = 1, opt_quota_min = 1, opt_lockstep = 1;
 
     double opt_cap_factor = 2.0;
     size_t opt_queue_bytes_max = (size_t)24 << 30;
@@ -556,7 +561,7 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_i
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (grid < 1) grid = 1;
     const int pi = prof_begin(eng, COLD ? N_SPECIES + 2 + SP : SP, st);
-    k_wave<SP, COLD><<<grid, block, smem, st>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice);
+    k_wave<SP, COLD><<<grid, block, smem, st>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice, eng->opt_lockstep);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
@@ -581,7 +586,7 @@ int launch_hot(trk3_engine *eng, const Queue &qin, uint32_t n, uint32_t *head, c
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (grid < 1) grid = 1;
     const int pi = prof_begin(eng, SP);
-    k_hot<SP><<<grid, block, smem, eng->stream>>>(qin, n, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice, eng->opt_inel_min, (int)quota);
+    k_hot<SP><<<grid, block, smem, eng->stream>>>(qin, n, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice, eng->opt_inel_min, (int)quota, eng->opt_lockstep);
     prof_end(eng, pi);
     CK(cudaGetLastError());
     eng->launches++;
@@ -711,6 +716,7 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "queue_gib") eng->opt_queue_bytes_max = (size_t)(v * (double)(1ull << 30));
     else if (k == "block") eng->opt_block = std::min(TRK_BLOCK_MAX, std::max(32, ((int)v / 32) * 32));
     else if (k == "hot_slice") eng->opt_hot_slice = std::max(1, (int)v);
+    else if (k == "lockstep") eng->opt_lockstep = (v != 0.0);
     else if (k == "spread") eng->opt_spread = (v != 0.0);
     else if (k == "quota_min") eng->opt_quota_min = std::min(32, std::max(1, (int)v));
     else if (k == "overlap") eng->opt_overlap = (v != 0.0);

@@ -36,6 +36,22 @@ namespace trk3 {
 
 TRK_HD bool trk_isnan(double x) { return x != x; }
 
+// Elementary functions.  With TRK_MATH_OUTLINE the device code calls ONE out-of-line copy of each instead of expanding
+// the 40-80 instruction sequence at every use (55 uses): the kernels are bound by instruction fetch, see philox4x32_10.
+#if defined(TRK_MATH_OUTLINE) && defined(__CUDA_ARCH__)
+#define TRK_MATH __device__ __noinline__
+#else
+#define TRK_MATH TRK_HD
+#endif
+TRK_MATH double m_exp(double x) { return exp(x); }
+TRK_MATH double m_log(double x) { return log(x); }
+TRK_MATH double m_sin(double x) { return sin(x); }
+TRK_MATH double m_cos(double x) { return cos(x); }
+TRK_MATH double m_acos(double x) { return acos(x); }
+// (divisions and square roots out of line were measured too: 21.4 ms instead of 20.9 ms per step -- they stay inline)
+TRK_HD double m_div(double a, double b) { return a / b; }
+TRK_HD double m_sqrt(double a) { return sqrt(a); }
+
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG (Salmon et al., SC'11).  Stream = (particle id, draw index,
 // iteration); key = user seed.  Replaces the unseeded compiler random_number of the reference.
@@ -47,8 +63,15 @@ TRK_HD uint32_t trk_mulhi(uint32_t a, uint32_t b) {
     return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
+// The wave kernels are bound by instruction FETCH (ncu: gcc__cache_requests_type_instruction at 98 % of peak, SM
+// instruction-cache hit rate 58 %): what counts is the number of distinct instruction lines a collision streams through,
+// not the number of instructions it executes.  TRK_PHILOX_ROLLED keeps the ten rounds as a loop (one round of code).
 TRK_HDN void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1) {
+#if defined(TRK_PHILOX_ROLLED) && defined(__CUDA_ARCH__)
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int r = 0; r < 10; ++r) {
         uint32_t h0 = trk_mulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
         uint32_t h1 = trk_mulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
@@ -58,7 +81,7 @@ TRK_HDN void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
     }
     o0 = c0; o1 = c1;
 }
-// uniform in (0,1]: the reference can draw RN = 0 (log(RN), L/RN -> inf); we exclude it
+// uniform in (0,1]: the reference can draw RN = 0 (m_log(RN), L/RN -> inf); we exclude it
 TRK_HD double rn(const DevP &p, Rec &r) {
     uint32_t a, b;
     philox4x32_10((uint32_t)r.id, (uint32_t)(r.id >> 32), r.ctr++, r.iter, p.seed_lo, p.seed_hi, a, b);
@@ -120,22 +143,22 @@ TRK_HD int find_dec(const double *A, int N, double v) {                // Find_i
 TRK_HD double interp5(double E1, double E2, double S1, double S2, double En) {
     if (fabs(E2 - E1) < 1.0e-6) return (S1 > S2) ? S1 : S2;
     if (En == E1) return S1;
-    double E2l = log(E2), E1l = log(E1), El = log(En), S1l = log(S1), S2l = log(S2);
-    return exp(S1l + (S2l - S1l) / (E2l - E1l) * (El - E1l));
+    double E2l = m_log(E2), E1l = m_log(E1), El = m_log(En), S1l = m_log(S1), S2l = m_log(S2);
+    return m_exp(S1l + (S2l - S1l) / (E2l - E1l) * (El - E1l));
 }
 // same with the logarithms of the table entries precomputed (identical arithmetic, identical result)
 TRK_HD double interp5t(double E1, double E2, double S1, double S2, double lE1, double lE2, double lS1, double lS2, double En, double lEn) {
     if (fabs(E2 - E1) < 1.0e-6) return (S1 > S2) ? S1 : S2;
     if (En == E1) return S1;
-    return exp(lS1 + (lS2 - lS1) / (lE2 - lE1) * (lEn - lE1));
+    return m_exp(lS1 + m_div(lS2 - lS1, lE2 - lE1) * (lEn - lE1));
 }
 TRK_HD double interp1(double E1, double E2, double S1, double S2, double En) {
     if (fabs(E2 - E1) < 1.0e-6) return (S1 > S2) ? S1 : S2;
     if (En == E1) return S1;
-    return S1 + (S2 - S1) / (E2 - E1) * (En - E1);
+    return S1 + m_div(S2 - S1, E2 - E1) * (En - E1);
 }
 
-// Find_in_monotonous_1D_array through the direct-index accelerator: lv = log(v).  A strictly increasing array has
+// Find_in_monotonous_1D_array through the direct-index accelerator: lv = m_log(v).  A strictly increasing array has
 // exactly one index n with A[n-2] <= v < A[n-1]; the scan from the looked-up start finds it, as the bisection does.
 TRK_HD int find_lut(const double *A, int N, const GridLut &g, double v, double lv) {
     if (v < A[0]) return 1;
@@ -199,13 +222,13 @@ TRK_HD double hole_imfp(const DevP &p, double E, double lE) {
 // Lookups of a particle's current energy that the next collision needs again: carried in registers between events
 // (the reference recomputes them at the start of every event: Monte_Carlo.f90:2298-2299 == :2449-2450 of the previous one)
 struct Cache {
-    double lE;      // log(E)
+    double lE;      // m_log(E)
     double emfp;    // elastic MFP from the 2D-searched table (El_EMFP / Hole_EMFP)
     double imfp;    // total inelastic MFP (El_IMFP / Hole_IMFP)
     int n1, n2;     // 1D / 2D search indices of E in the elastic grid
 };
 TRK_HDN void cache_fill(const Tab &el, double E, Cache &k) {
-    k.lE = log(E);
+    k.lE = m_log(E);
     k.n1 = tab_find(el, E, k.lE);
     k.n2 = find_2d_from_1d(el.E, el.N, E, k.n1);
     k.emfp = nfp_at(el, k.n2, true, E, k.lE);
@@ -252,17 +275,17 @@ TRK_HDN int which_shell(const DevP &p, Rec &r, const Tab &m, double E, double lE
 }
 
 // Get_velosity, Monte_Carlo.f90:850-878 (non-relativistic for massive particles)
-TRK_HD double vel_electron(double E) { return sqrt(2.0 * E * TRK_GE / TRK_ME); }
+TRK_HD double vel_electron(double E) { return m_sqrt(2.0 * E * TRK_GE / TRK_ME); }
 TRK_HD double vel_hole(const Rec &h) {
     if (h.Mass < 1.0e6) {
         if (h.Ehkin < -1.0e-6 || h.Mass < 1.0e-10) return 0.0;
         if (fabs(h.Ehkin) < 1.0e-6) return 0.0;
-        return sqrt(2.0 * h.Ehkin * TRK_GE / (h.Mass * TRK_ME));
+        return m_sqrt(m_div(2.0 * h.Ehkin * TRK_GE, h.Mass * TRK_ME));
     }
     return 0.0;
 }
 // Get_time_of_next_event, :795-848
-TRK_HD double next_time(double t0, double V, double MFP) { return (V > 1.0e-10) ? t0 + MFP / V * 1e5 : 1.0e25; }
+TRK_HD double next_time(double t0, double V, double MFP) { return (V > 1.0e-10) ? t0 + m_div(MFP, V) * 1e5 : 1.0e25; }
 
 // time-interval index of an event/creation time: smallest i (1-based) with t < tg(i); Nt+1 if t >= Tim
 TRK_HD int interval_of(const DevP &p, double t) {
@@ -307,7 +330,7 @@ TRK_HD double sample_row(const Csr &t, int64_t o, int n, double L_need, double l
 }
 TRK_HDN double transferred_energy(const Csr &t, double Ele, double lE, int i_E, double L_need) {
     if (i_E > 1) { if (fabs(t.Eg[i_E - 2] - Ele) < 1.0e-6) i_E = i_E - 1; }
-    const double lLn = log(L_need);
+    const double lLn = m_log(L_need);
     int64_t o = t.off[i_E - 1];
     if (i_E <= 1) return sample_row(t, o, (int)(t.off[i_E] - o), L_need, lLn);
     const int64_t o2 = t.off[i_E - 2];
@@ -318,7 +341,7 @@ TRK_HDN double transferred_energy(const Csr &t, double Ele, double lE, int i_E, 
     i_E = i_E - 1;
     double hw_2 = sample_row_at(t, o2, n2, i2, L_need, lLn);
     if (hw_1 < 1.0e-10 || hw_2 < 1.0e-10) return interp1(t.Eg[i_E - 1], t.Eg[i_E], hw_1, hw_2, Ele);
-    return interp5t(t.Eg[i_E - 1], t.Eg[i_E], hw_1, hw_2, t.lEg[i_E - 1], t.lEg[i_E], log(hw_1), log(hw_2), Ele, lE);
+    return interp5t(t.Eg[i_E - 1], t.Eg[i_E], hw_1, hw_2, t.lEg[i_E - 1], t.lEg[i_E], m_log(hw_1), m_log(hw_2), Ele, lE);
 }
 TRK_HD Csr csr_eid(const DevP &p, int shell) { return Csr{p.ei_E, p.lei_E, p.n_ei, p.eid_off + (size_t)shell * p.n_ei, p.eid_hw, p.eid_L, p.leid_hw, p.leid_L}; }
 TRK_HD Csr csr_eed(const DevP &p) { return Csr{p.ee_E, p.lee_E, p.n_ee, p.eed_off, p.eed_hw, p.eed_L, p.leed_hw, p.leed_L}; }
@@ -343,7 +366,7 @@ TRK_HD double hole_mass_dos(const DevP &p, double E) { int m = find_dos(p, E); r
 // Electron_energy_transfer_inelastic (CS_method = 1), Cross_sections.f90:1793-1871
 TRK_HD double inelastic_dE(const DevP &p, Rec &r, double Ele, double lE, int n_E, int shell, double L_tot, bool hole) {
     double RN = rn(p, r);
-    double L_need = L_tot / RN;
+    double L_need = m_div(L_tot, RN);
     double Emin = p.shell_Ip[shell];
     if (Emin <= 1.0e-3) Emin = 1.0e-3;
     double Emax, E;
@@ -377,10 +400,10 @@ TRK_HDN double mott_dE(const DevP &p, Rec &r, double Mat, double Zat, double Ee,
         double alpha = TRK_GE * TRK_GE / (TRK_HBAR * TRK_CVEL * 4.0 * TRK_PI * TRK_E0);
         double nu = 1.7e-5 * pow(Zat, 2.0 / 3.0) * (1.0 - beta2) / beta2 * (1.13 + 3.76 * alpha * alpha / beta2 * Zat * Zat * sqrt(tau / (1.0 + tau)));
         double mu = (RN * (2.0 * nu + 1.0) - nu) / (RN + nu);
-        theta = acos(mu);
+        theta = m_acos(mu);
     }
     double mc2 = rest_energy(TRK_ME * M_eff), Mct2 = rest_energy(Mat);
-    double ct = cos(theta), ct2 = ct * ct, st2 = 1.0 - ct2;
+    double ct = m_cos(theta), ct2 = ct * ct, st2 = 1.0 - ct2;
     double Emc = Ee + mc2, E2mc = Ee + 2.0 * mc2, EmcMc = Emc + Mct2;
     double W1 = Emc * st2 + Mct2 - ct * sqrt(Mct2 * Mct2 - mc2 * mc2 * st2);
     double W2 = Ee * E2mc / (EmcMc * EmcMc - Ee * E2mc * ct2);
@@ -399,7 +422,7 @@ TRK_HD_RARE double mott_elastic_dE(const DevP &p, Rec &r, double Eel, double M_e
 TRK_HD double elastic_dE(const DevP &p, Rec &r, double Eel, const Cache &k, double EMFP, bool hole, double M_eff) {
     if (p.kind_of_EMFP == 1) {      // Electron_energy_transfer_elastic, Cross_sections.f90:2403-2413
         double RN = rn(p, r);
-        double L_need = EMFP / RN;
+        double L_need = m_div(EMFP, RN);
         double hw = transferred_energy(hole ? csr_hed(p) : csr_eed(p), Eel, k.lE, k.n1, L_need);
         if (hw >= Eel) hw = Eel;
         return hw;
@@ -413,16 +436,16 @@ TRK_HD void angles_lattice(const DevP &p, Rec &r, double E, double W, double M_e
     double E2mc = E + 2.0 * Erest_in, EmW = E - W;
     double W1 = E * E2mc - W * (E + Erest_in + Erest_t);
     double W2 = E * E2mc * EmW * (E2mc - W);
-    double mu = (W2 > 0.0) ? W1 / sqrt(W2) : 0.0;
-    if (fabs(mu) > 1.0) { double RN = rn(p, r); mu = cos(TRK_PI * RN); }
-    theta = acos(mu);
+    double mu = (W2 > 0.0) ? m_div(W1, m_sqrt(W2)) : 0.0;
+    if (fabs(mu) > 1.0) { double RN = rn(p, r); mu = m_cos(TRK_PI * RN); }
+    theta = m_acos(mu);
     double RN2 = rn(p, r);
     phi = 2.0 * TRK_PI * RN2;
 }
 // New_Angles_both, Monte_Carlo.f90:1328-1360 (not a rotation; kept as is)
 TRK_HDN void new_angles(double phi0, double theta0, double theta, double psi, double &phi1, double &theta1) {
-    phi1 = phi0 + theta * cos(theta0) * sin(psi);
-    theta1 = theta0 + theta * cos(psi);
+    phi1 = phi0 + theta * m_cos(theta0) * m_sin(psi);
+    theta1 = theta0 + theta * m_cos(psi);
     while (theta1 < 0.0) { theta1 = fabs(theta1); phi1 = phi1 + TRK_PI; }
     while (theta1 > TRK_PI) { theta1 = 2.0 * TRK_PI - theta1; phi1 = phi1 - TRK_PI; }
     if (phi1 > 2.0 * TRK_PI) phi1 = phi1 - floor(phi1 / (2.0 * TRK_PI)) * 2.0 * TRK_PI;
@@ -480,7 +503,7 @@ TRK_HDN void hole_parameters(const DevP &p, Rec &st, Rec &h, double Eh, double E
             double HIMFP = k.imfp;
             double HEMFP = (Ehkin_prev == (Eh - p.Egap)) ? 1.0e30 : k.emfp;
             double RN = rn(p, st);
-            double MFP_tot = -log(RN) / (1.0 / HIMFP + 1.0 / HEMFP);
+            double MFP_tot = m_div(-m_log(RN), m_div(1.0, HIMFP) + m_div(1.0, HEMFP));
             h.tn = next_time(h.t0, vel_hole(h), MFP_tot);
             h.L = MFP_tot;
         } else { h.L = 1.0e30; h.tn = 1.0e30; }
@@ -488,7 +511,7 @@ TRK_HDN void hole_parameters(const DevP &p, Rec &st, Rec &h, double Eh, double E
         h.Mass = 1.0e29;
         double RN = rn(p, st);
         double nu = 1.0 / p.shell_auger[h.shell] + 1.0 / p.shell_radiat[h.shell];
-        h.tn = h.t0 - log(RN) / nu;
+        h.tn = h.t0 - m_log(RN) / nu;
         h.L = 1.0e30; h.E = Eh; h.Ehkin = 0.0;
     }
     // cut_off, :3008-3012
@@ -512,11 +535,11 @@ template <class C>
 TRK_HD void emit_electron(C &c, Rec &st, uint64_t id, double Ee, double t, double X, double Y, double Z, double theta, double phi, int err_code) {
     const DevP &p = c.p;
     Rec e;
-    const double lE = log(Ee);
+    const double lE = m_log(Ee);
     double IMFP = electron_imfp(p, Ee, lE);
     double EMFP = nfp_2d(tab_ee(p), Ee, lE);
     double RN = rn(p, st);
-    double MFP_tot = -log(RN) / (1.0 / IMFP + 1.0 / EMFP);
+    double MFP_tot = m_div(-m_log(RN), m_div(1.0, IMFP) + m_div(1.0, EMFP));
     e.E = Ee; e.Ehkin = 0.0; e.Mass = 1.0; e.t0 = t; e.X = X; e.Y = Y; e.Z = Z; e.L = MFP_tot; e.theta = theta; e.phi = phi;
     e.tn = next_time(t, vel_electron(Ee), MFP_tot);
     if (e.E < p.cut_off) e.tn = 1.0e20;
@@ -545,18 +568,18 @@ TRK_HD double shi_zeff(const DevP &p, double E) {
     double Zp = (double)p.ion_Z;
     const double g_v0 = sqrt(2.0 * TRK_RY * TRK_GE / TRK_ME);
     switch (p.ion_kind_Zeff) {
-    case 1: return Zp * (1.0 - exp(-(vp / g_v0 / pow(Zp, 0.66666666))));
+    case 1: return Zp * (1.0 - m_exp(-(vp / g_v0 / pow(Zp, 0.66666666))));
     case 2: { double c1 = 0.6, c2 = 0.45; return Zp * pow(1.0 + pow(vp / (pow(Zp, c2) * g_v0 * 4.0 / 3.0), -1.0 / c1), -c1); }
     case 3: {
         double sz = 0; for (int a = 0; a < p.n_atoms; ++a) sz += p.atom_Z[a] * p.atom_pers[a];
         double Zt = sz / p.sum_pers;
-        double c1 = 1.0 - 0.26 * exp(-Zt / 11.0 - (Zt - Zp) * (Zt - Zp) / 9.0);
+        double c1 = 1.0 - 0.26 * m_exp(-Zt / 11.0 - (Zt - Zp) * (Zt - Zp) / 9.0);
         double vpvo = pow(Zp, -0.543) * vp / g_v0;
-        double c2 = 1.0 + 0.03 * vpvo * log(Zt);
+        double c2 = 1.0 + 0.03 * vpvo * m_log(Zt);
         double x = c1 * pow(vpvo / c2 / 1.54, 1.0 + 1.83 / Zp), x2 = x * x, x4 = x2 * x2;
         return Zp * (8.29 * x + x4) / (0.06 / x + 4.0 + 7.4 * x + x4); }
     case 4: return p.ion_fixed_Zeff;
-    default: return Zp * (1.0 - exp(-(vp * 125.0 / TRK_CVEL / pow(Zp, 0.66666666))));
+    default: return Zp * (1.0 - m_exp(-(vp * 125.0 / TRK_CVEL / pow(Zp, 0.66666666))));
     }
 }
 // SHI_energy_transfer (CDF shells), Monte_Carlo.f90:1719-1780.  The reference's linear search over 1/L
@@ -586,7 +609,7 @@ TRK_HD double shi_energy_transfer(const DevP &p, Rec &r, int shell) {
         while (lo < hi) { int mid = (lo + hi) >> 1; if (iLa[mid - 1] < Tot_N) lo = mid + 1; else hi = mid; }
         N_temmp = lo;
     } else N_temmp = M_temp;
-    if (N_temmp > M_temp) return interp5t(iLa[N_temmp - 2], iLa[N_temmp - 1], Ea[N_temmp - 2], Ea[N_temmp - 1], liLa[N_temmp - 2], liLa[N_temmp - 1], lEa[N_temmp - 2], lEa[N_temmp - 1], Tot_N, log(Tot_N));
+    if (N_temmp > M_temp) return interp5t(iLa[N_temmp - 2], iLa[N_temmp - 1], Ea[N_temmp - 2], Ea[N_temmp - 1], liLa[N_temmp - 2], liLa[N_temmp - 1], lEa[N_temmp - 2], lEa[N_temmp - 1], Tot_N, m_log(Tot_N));
     return p.shell_Ip[shell];
 }
 
@@ -601,8 +624,8 @@ TRK_HD void snapshot_electron(C &c, const Rec &e, int i) {
     const double cut = (p.cut_off > 0.0) ? p.cut_off : 0.0;
     double L0 = 0.0, theta0 = 0.0, phi0 = 0.0;
     if (e.E > cut) { L0 = vel_electron(e.E) * (tim - e.t0) * 1.0e-5; if (L0 < 0.0) L0 = 0.0; theta0 = e.theta; phi0 = e.phi; }
-    double st = sin(theta0);
-    double X = e.X + L0 * st * sin(phi0), Y = e.Y + L0 * st * cos(phi0);
+    double st = m_sin(theta0);
+    double X = e.X + L0 * st * m_sin(phi0), Y = e.Y + L0 * st * m_cos(phi0);
     double R = sqrt(X * X + Y * Y);
     int j = find_1d(p.out_R, p.n_r, R);
     c.tally(TRK3_OUT_NE, (i - 1) + (int64_t)p.Nt * (j - 1), p.out_V[j - 1]);
@@ -633,8 +656,8 @@ TRK_HD void snapshot_hole(C &c, const Rec &h, int i) {
     double Xh = h.X, Yh = h.Y;
     if (h.Mass < 1.0e3 && h.Ehkin > cut) {
         double L0 = vel_hole(h) * (tim - h.t0) * 1.0e-5; if (L0 < 0.0) L0 = 0.0;
-        double st = sin(h.theta);
-        Xh = h.X + L0 * st * sin(h.phi); Yh = h.Y + L0 * st * cos(h.phi);
+        double st = m_sin(h.theta);
+        Xh = h.X + L0 * st * m_sin(h.phi); Yh = h.Y + L0 * st * m_cos(h.phi);
         double xx = h.theta / TRK_PI * 180.0;
         int jt = (xx < 1.0) ? 1 : ((xx >= 180.0) ? 180 : (int)floor(xx) + 1);
         c.add_u32(p.it.th_h, base * TRK3_NTHETA + (jt - 1));
@@ -663,8 +686,8 @@ TRK_HD void snapshot_photon(C &c, const Rec &ph, int i) {
     const uint32_t il = ph.iter - p.batch_begin;
     const size_t base = (size_t)il * p.Nt + (i - 1);
     double L0 = TRK_CVEL * (tim - ph.t0) * 1.0e-5; if (L0 < 0.0) L0 = 0.0;
-    double st = sin(ph.theta);
-    double X = ph.X + L0 * st * sin(ph.phi), Y = ph.Y + L0 * st * cos(ph.phi);
+    double st = m_sin(ph.theta);
+    double X = ph.X + L0 * st * m_sin(ph.phi), Y = ph.Y + L0 * st * m_cos(ph.phi);
     double R = sqrt(X * X + Y * Y);
     int j = find_1d(p.out_R, p.n_r, R);
     c.tally(TRK3_OUT_NPHOT, (i - 1) + (int64_t)p.Nt * (j - 1), p.out_V[j - 1]);
@@ -698,10 +721,10 @@ TRK_HD_RARE void electron_emission(C &c, Rec &e, int iv) {
     if (e.E >= 1.5 * p.bar_height) { emitted = true; Ekin = e.E - p.work_function; }
     else {
         double r2 = rn(p, e);
-        double Em_Penetr = 1.0 / (1.0 + exp(p.Em_gamma * (p.Em_E1 - e.E)));
+        double Em_Penetr = 1.0 / (1.0 + m_exp(p.Em_gamma * (p.Em_E1 - e.E)));
         Ekin = e.E - p.work_function;
         if (Ekin > 0.0 && r2 < Em_Penetr) emitted = true;
-        else if (cos(e.theta) < 0) e.theta = TRK_PI - e.theta;
+        else if (m_cos(e.theta) < 0) e.theta = TRK_PI - e.theta;
     }
     if (emitted) {
         e.tn = 1.0e30; e.L = 1.0e30;
@@ -746,15 +769,15 @@ TRK_HD void electron_ion_emit(C &c, const IonEvent &ev) {
 // channel only, for kernels whose warps are uniform in the event type (the caller has evaluated the roulette with
 // electron_roulette_inelastic).
 enum EventMode { EV_ANY = 0, EV_ELASTIC = 1, EV_INELASTIC = 2 };
-TRK_HD bool electron_roulette_inelastic(const Cache &k, double RN) { return RN * (1.0 / k.imfp + 1.0 / k.emfp) < 1.0 / k.imfp; }
+TRK_HD bool electron_roulette_inelastic(const Cache &k, double RN) { const double ii = m_div(1.0, k.imfp); return RN * (ii + m_div(1.0, k.emfp)) < ii; }
 template <int MODE, class C>
 TRK_HD void electron_event_t(C &c, Rec &e, int iv, Cache &k, double RN) {
     const DevP &p = c.p;
     const double Eel = e.E;
     double IMFP = k.imfp, EMFP = k.emfp;                          // :2298-2299, already looked up for this energy
     const double L = e.L, theta0 = e.theta, phi0 = e.phi;
-    const double st0 = sin(theta0);
-    const double X = e.X + L * st0 * sin(phi0), Y = e.Y + L * st0 * cos(phi0), Z = e.Z + L * cos(theta0);
+    const double st0 = m_sin(theta0);
+    const double X = e.X + L * st0 * m_sin(phi0), Y = e.Y + L * st0 * m_cos(phi0), Z = e.Z + L * m_cos(theta0);
     const double t_ev = e.tn;
     double dE, theta, phi;
     if (MODE == EV_INELASTIC || (MODE == EV_ANY && electron_roulette_inelastic(k, RN))) {     // inelastic: impact ionisation
@@ -766,7 +789,7 @@ TRK_HD void electron_event_t(C &c, Rec &e, int iv, Cache &k, double RN) {
         e.ctr += 2;                                              // the two child ids
         IMFP = nfp_at(tab_shell(tab_ei_L(p), shell), n_E, false, Eel, k.lE);      // Next_free_path_1d, same grid => same index
         dE = inelastic_dE(p, e, Eel, k.lE, n_E, shell, IMFP, false);
-        theta = acos((Eel - dE) / sqrt(Eel * (Eel - dE)));       // Update_electron_angles_El :1189
+        theta = m_acos((Eel - dE) / sqrt(Eel * (Eel - dE)));       // Update_electron_angles_El :1189
         if (trk_isnan(theta)) { double r2 = rn(p, e); theta = r2 * TRK_PI; }
         { double r2 = rn(p, e); phi = 2.0 * TRK_PI * r2; }
         ev.dE = dE; ev.t = t_ev; ev.X = X; ev.Y = Y; ev.Z = Z; ev.theta0 = theta0; ev.phi0 = phi0; ev.theta = theta; ev.phi = phi; ev.shell = shell;
@@ -782,7 +805,7 @@ TRK_HD void electron_event_t(C &c, Rec &e, int iv, Cache &k, double RN) {
     cache_electron(p, Eel - dE, k);                               // :2449-2450, kept for the next collision
     IMFP = k.imfp; EMFP = k.emfp;
     RN = rn(p, e);
-    double MFP_tot = -log(RN) / (1.0 / IMFP + 1.0 / EMFP);
+    double MFP_tot = m_div(-m_log(RN), m_div(1.0, IMFP) + m_div(1.0, EMFP));
     double phi1, theta1;
     new_angles(phi0, theta0, theta, phi, phi1, theta1);
     e.E = Eel - dE; e.t0 = t_ev; e.X = X; e.Y = Y; e.Z = Z; e.L = MFP_tot; e.theta = theta1; e.phi = phi1;
@@ -813,15 +836,15 @@ TRK_HD void check_hole_level(const DevP &p, double Eel, double &dE, double &Ehol
 
 // Hole_Monte_Carlo, valence-band branch, Monte_Carlo.f90:2560-2738.  RN = first draw (channel roulette, :2582); MODE as
 // for electrons.  Holes below DevP::h_cold have a total inelastic MFP >= 1e16 and can never ionise (needs HIMFP < 1e15).
-TRK_HD bool vbhole_roulette_inelastic(const Cache &k, double RN) { return RN * (1.0 / k.imfp + 1.0 / k.emfp) < 1.0 / k.imfp && k.imfp < 1e15; }
+TRK_HD bool vbhole_roulette_inelastic(const Cache &k, double RN) { const double ii = m_div(1.0, k.imfp); return RN * (ii + m_div(1.0, k.emfp)) < ii && k.imfp < 1e15; }
 template <int MODE, class C>
 TRK_HD void vbhole_event_t(C &c, Rec &h, int iv, Cache &k, double RN) {
     const DevP &p = c.p;
     const double Eel = h.Ehkin;
     double HIMFP = k.imfp, HEMFP = k.emfp;                        // :2579-2580
     const double L = h.L, theta0 = h.theta, phi0 = h.phi;
-    const double st0 = sin(theta0);
-    const double X = h.X + L * st0 * sin(phi0), Y = h.Y + L * st0 * cos(phi0), Z = h.Z + L * cos(theta0);
+    const double st0 = m_sin(theta0);
+    const double X = h.X + L * st0 * m_sin(phi0), Y = h.Y + L * st0 * m_cos(phi0), Z = h.Z + L * m_cos(theta0);
     const double t_ev = h.tn;
     double dE, Ehole, htheta1, hphi1;
     if (MODE == EV_INELASTIC || (MODE == EV_ANY && vbhole_roulette_inelastic(k, RN))) {
@@ -833,19 +856,19 @@ TRK_HD void vbhole_event_t(C &c, Rec &h, int iv, Cache &k, double RN) {
         dE = inelastic_dE(p, h, Eel, k.lE, n_E, shell, HIMFP, true);
         // Update_holes_angles_el, :1142-1168
         double E11 = Eel - dE, Mh = h.Mass * TRK_ME;
-        double htheta = acos(sqrt((Mh + TRK_ME) * (Mh + TRK_ME) / (4.0 * Mh * TRK_ME) * dE / Eel));
+        double htheta = m_acos(sqrt((Mh + TRK_ME) * (Mh + TRK_ME) / (4.0 * Mh * TRK_ME) * dE / Eel));
         double hphi; { double r2 = rn(p, h); hphi = 2.0 * TRK_PI * r2; }
         if (trk_isnan(htheta)) { double r2 = rn(p, h); htheta = TRK_PI * r2; }
-        htheta1 = acos((Eel * (Mh - TRK_ME) + E11 * (Mh + TRK_ME)) / (2 * Mh * sqrt(Eel * E11)));
+        htheta1 = m_acos((Eel * (Mh - TRK_ME) + E11 * (Mh + TRK_ME)) / (2 * Mh * sqrt(Eel * E11)));
         hphi1 = hphi + TRK_PI;
         if (trk_isnan(htheta1)) { double r2 = rn(p, h); htheta1 = TRK_PI * r2; }
         double dE_cur = electron_receives_E(c, h, dE, shell);
         // the new electron is fully sampled first (:2606-2621), then the level check may add the surplus to it (:2660)
-        const double lEn = log(dE_cur);
+        const double lEn = m_log(dE_cur);
         double IMFP = electron_imfp(p, dE_cur, lEn);
         double EMFP = nfp_2d(tab_ee(p), dE_cur, lEn);
         RN = rn(p, h);
-        double MFP_tot = -log(RN) / (1.0 / IMFP + 1.0 / EMFP);
+        double MFP_tot = m_div(-m_log(RN), m_div(1.0, IMFP) + m_div(1.0, EMFP));
         RN = rn(p, h);                                           // sic (:2611): drawn and discarded
         double phi1, theta1;
         new_angles(phi0, theta0, htheta, hphi, phi1, theta1);
@@ -937,11 +960,11 @@ TRK_HD void corehole_event(C &c, Rec &h) {
             uint64_t id_e = child_id(p, h, 1), id_h = child_id(p, h, 2);
             emit_hole(c, h, id_h, s2, E_new2, t_ev, h.X, h.Y, h.Z, TRK3_ERR_20);
             // Auger electron: isotropic in angle (:2800-2813); phi is drawn before theta
-            const double lEn = log(Ee);
+            const double lEn = m_log(Ee);
             double IMFP = electron_imfp(p, Ee, lEn);
             double EMFP = nfp_2d(tab_ee(p), Ee, lEn);
             RN = rn(p, h);
-            double MFP_tot = -log(RN) / (1.0 / IMFP + 1.0 / EMFP);
+            double MFP_tot = m_div(-m_log(RN), m_div(1.0, IMFP) + m_div(1.0, EMFP));
             RN = rn(p, h); double phi1 = 2.0 * TRK_PI * RN;
             RN = rn(p, h); double theta1 = TRK_PI * RN;
             Rec e;
@@ -970,9 +993,9 @@ TRK_HD void corehole_event(C &c, Rec &h) {
         hole_parameters(p, h, h, E_new1, Ehk_prev);
         // photon (:2843-2866); the reference's slot-reuse bug (:2844 vs :2963) does not exist here
         uint64_t id_p = child_id(p, h, 3);
-        double IMFP = nfp_2d(tab_ph_tot(p), dE, log(dE));
+        double IMFP = nfp_2d(tab_ph_tot(p), dE, m_log(dE));
         RN = rn(p, h);
-        double MFP_tot = -log(RN) * IMFP;
+        double MFP_tot = -m_log(RN) * IMFP;
         RN = rn(p, h); double phi1 = 2.0 * TRK_PI * RN;
         RN = rn(p, h); double theta1 = TRK_PI * RN;
         Rec ph;
@@ -991,10 +1014,10 @@ TRK_HD void photon_event(C &c, Rec &ph) {
     const DevP &p = c.p;
     c.event(TRK3_EV_PHOTON);
     const double Eel = ph.E, L = ph.L, theta0 = ph.theta, phi0 = ph.phi, t_ev = ph.tn;
-    const double st0 = sin(theta0);
-    const double X = ph.X + L * st0 * sin(phi0), Y = ph.Y + L * st0 * cos(phi0), Z = ph.Z + L * cos(theta0);
+    const double st0 = m_sin(theta0);
+    const double X = ph.X + L * st0 * m_sin(phi0), Y = ph.Y + L * st0 * m_cos(phi0), Z = ph.Z + L * m_cos(theta0);
     int n_E;
-    int shell = which_shell(p, ph, tab_ph_L(p), Eel, log(Eel), n_E);
+    int shell = which_shell(p, ph, tab_ph_L(p), Eel, m_log(Eel), n_E);
     uint64_t id_e = child_id(p, ph, 1), id_h = child_id(p, ph, 2);
     double dE_cur = electron_receives_E(c, ph, Eel, shell);
     double phi1, theta1;
@@ -1024,9 +1047,9 @@ TRK_HD void shi_begin(const DevP &p, Rec &s, uint32_t iter) {
     s.E = p.ion_E; s.t0 = 0.0; s.tn = 0.0; s.X = 0.0; s.Y = 0.0; s.Z = 0.0; s.L = 0.0; s.theta = 0.0; s.phi = 0.0; s.Ehkin = 0.0; s.Mass = p.ion_mass;
     s.id = 0; s.ctr = 0; s.iter = iter; s.shell = -1;
     const double MSHI = p.ion_mass * TRK_MP;
-    double lam = nfp_2d(tab_shi_tot(p), s.E, log(s.E));
+    double lam = nfp_2d(tab_shi_tot(p), s.E, m_log(s.E));
     double RN = rn(p, s);
-    s.L = -lam * log(RN);
+    s.L = -lam * m_log(RN);
     s.tn = next_time(s.t0, sqrt(2.0 * s.E * TRK_GE / MSHI), s.L);
 }
 // one collision of the ion at s.tn (< Tim); leaves the ion in flight towards its next collision
@@ -1035,14 +1058,14 @@ TRK_HD void shi_step(C &c, Rec &s, ShiEvent &ev) {
     const DevP &p = c.p;
     const double MSHI = p.ion_mass * TRK_MP;
     c.event(TRK3_EV_SHI);
-    const double lEs = log(s.E);
+    const double lEs = m_log(s.E);
     int n_E;
     int shell = which_shell(p, s, tab_shi_L(p), s.E, lEs, n_E);
     double dE = shi_energy_transfer(p, s, shell);
     const Tab tt = tab_shi_tot(p);
     double lam = nfp_at(tt, find_2d_from_1d(tt.E, tt.N, s.E, n_E), true, s.E, lEs);
     double RN = rn(p, s);
-    double SHI_IMFP = -lam * log(RN);
+    double SHI_IMFP = -lam * m_log(RN);
     double Z = s.Z + s.L;
     s.E = s.E - dE; s.t0 = s.tn; s.Z = Z; s.L = SHI_IMFP;
     s.tn = next_time(s.t0, sqrt(2.0 * s.E * TRK_GE / MSHI), SHI_IMFP);
@@ -1062,12 +1085,12 @@ TRK_HD void shi_emit(C &c, const ShiEvent &ev) {
     const double dE = ev.dE;
     double dE_cur = electron_receives_E(c, se, dE, ev.shell);
     // Update_electron_angles_SHI (:1170-1187) with the UPDATED ion energy
-    double theta = (ev.E_after <= 0.0) ? TRK_PI / 2.0 : acos(sqrt((MSHI + TRK_ME) * (MSHI + TRK_ME) / (4.0 * MSHI * TRK_ME) * dE / ev.E_after));
+    double theta = (ev.E_after <= 0.0) ? TRK_PI / 2.0 : m_acos(sqrt((MSHI + TRK_ME) * (MSHI + TRK_ME) / (4.0 * MSHI * TRK_ME) * dE / ev.E_after));
     double phi; { double r2 = rn(p, se); phi = 2.0 * TRK_PI * r2; }
     // Impact_parameter (:1113-1126); the ion moves along the Z axis (X = Y = 0)
     double A = 1.0 + MSHI / TRK_ME;
     double b = TRK_A0 * ev.Zeff * TRK_RY / ev.E_after * sqrt(4.0 * ev.E_after / dE * MSHI / TRK_ME - A * A);
-    double X = b * sin(phi), Y = b * cos(phi);
+    double X = b * m_sin(phi), Y = b * m_cos(phi);
     emit_electron(c, se, id_e, dE_cur, ev.t0, X, Y, ev.Z, theta, phi, TRK3_ERR_20);
     emit_hole(c, sh, id_h, ev.shell, dE - dE_cur, ev.t0, X, Y, ev.Z, TRK3_ERR_20);
 }
