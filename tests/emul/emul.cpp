@@ -77,6 +77,13 @@ extern "C" int trk3_emul_run(const trk3_config *cfg, const trk3_tables *tab, int
     TRK3_LUT_GRIDS(X, T)
 #undef X
     p.dos_inv_step = uniform_inv_step(T.dos_E, T.n_dos);
+    std::vector<uint16_t> dluts[TRK3_MAX_SHELLS];
+    for (int sh = 0; sh < T.n_shells; ++sh) {
+        int Mt; double dl; const int Nsh = (int)(T.dshi_off[sh + 1] - T.dshi_off[sh]);
+        shi_threshold(T.dshi_E + T.dshi_off[sh], T.dshi_L + T.dshi_off[sh], Nsh, T.shell_Ip[sh], Mt, dl);
+        build_inverse_lut(T.dshi_L + T.dshi_off[sh], Nsh, Mt, dluts[sh], p.dshi_lut[sh].l0, p.dshi_lut[sh].scale);
+        p.dshi_lut[sh].lut = dluts[sh].data();
+    }
     for (int sh = 0; sh < T.n_shells; ++sh) shi_threshold(T.dshi_E + T.dshi_off[sh], T.dshi_L + T.dshi_off[sh], (int)(T.dshi_off[sh + 1] - T.dshi_off[sh]), T.shell_Ip[sh], p.shi_Mtemp[sh], p.shi_dL[sh]);
     cold_range(p.ei_E, p.ei_tot, p.n_ei, p.e_cold, p.e_imfp_cold);
     cold_range(p.hi_E, p.hi_tot, p.n_hi, p.h_cold, p.h_imfp_cold);

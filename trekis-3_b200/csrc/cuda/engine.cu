@@ -356,6 +356,8 @@ struct trk3_engine {
     cudaStream_t stream = nullptr;
     cudaStream_t stream_c = nullptr;       // second stream: the cold kernels run beside the hot cascade
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream_sp[3] = {nullptr, nullptr, nullptr};      // the rarer species of a generation run beside the electrons
+    cudaEvent_t ev_gen = nullptr, ev_sp[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     trk3_config cfg{};
     trk3_tally_layout lay{};
@@ -368,7 +370,7 @@ struct trk3_engine {
     // options
     int opt_batch = 1024, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
     int opt_hot_slice = 64, opt_inel_min = 1, opt_overlap = 0, opt_cold_min = 16384;
-    int opt_spread = 1, opt_quota_min = 1, opt_lockstep = 1;
+    int opt_spread = 1, opt_quota_min = 1, opt_lockstep = 0, opt_species_streams = 1;
 
     double opt_cap_factor = 2.0;
     size_t opt_queue_bytes_max = (size_t)24 << 30;
@@ -568,7 +570,8 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_i
     return TRK3_OK;
 }
 template <int SP>
-int launch_hot(trk3_engine *eng, const Queue &qin, uint32_t n, uint32_t *head, const QueueSet &qout) {
+int launch_hot(trk3_engine *eng, const Queue &qin, uint32_t n, uint32_t *head, const QueueSet &qout, cudaStream_t st = nullptr) {
+    if (!st) st = eng->stream;
     size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
     int use_smem = eng->opt_use_smem;
     const size_t smem_max = (size_t)eng->smem_optin - 1024;
@@ -585,9 +588,9 @@ int launch_hot(trk3_engine *eng, const Queue &qin, uint32_t n, uint32_t *head, c
     uint32_t want = (n + quota * wpb - 1) / (quota * wpb);
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (grid < 1) grid = 1;
-    const int pi = prof_begin(eng, SP);
-    k_hot<SP><<<grid, block, smem, eng->stream>>>(qin, n, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice, eng->opt_inel_min, (int)quota, eng->opt_lockstep);
-    prof_end(eng, pi);
+    const int pi = prof_begin(eng, SP, st);
+    k_hot<SP><<<grid, block, smem, st>>>(qin, n, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice, eng->opt_inel_min, (int)quota, eng->opt_lockstep);
+    prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
     return TRK3_OK;
@@ -634,6 +637,13 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
         TRK3_LUT_GRIDS(X, T)
 #undef X
         p.dos_inv_step = uniform_inv_step(T.dos_E, T.n_dos);
+        for (int sh = 0; sh < T.n_shells; ++sh) {
+            int Mt; double dl; const int Nsh = (int)(T.dshi_off[sh + 1] - T.dshi_off[sh]);
+            shi_threshold(T.dshi_E + T.dshi_off[sh], T.dshi_L + T.dshi_off[sh], Nsh, T.shell_Ip[sh], Mt, dl);
+            build_inverse_lut(T.dshi_L + T.dshi_off[sh], Nsh, Mt, lut, p.dshi_lut[sh].l0, p.dshi_lut[sh].scale);
+            rc = dev_upload(eng, &p.dshi_lut[sh].lut, lut.data(), lut.size()); if (rc) return rc;
+            CK(cudaStreamSynchronize(eng->stream));
+        }
     for (int sh = 0; sh < T.n_shells; ++sh) shi_threshold(T.dshi_E + T.dshi_off[sh], T.dshi_L + T.dshi_off[sh], (int)(T.dshi_off[sh + 1] - T.dshi_off[sh]), T.shell_Ip[sh], p.shi_Mtemp[sh], p.shi_dL[sh]);
         cold_range(tab->ei_E, tot.ei_tot.data(), tab->n_ei, p.e_cold, p.e_imfp_cold);
         cold_range(tab->hi_E, tot.hi_tot.data(), tab->n_hi, p.h_cold, p.h_imfp_cold);
@@ -669,6 +679,8 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CK(cudaStreamCreateWithPriority(&eng->stream, cudaStreamNonBlocking, hi));
         CK(cudaStreamCreateWithPriority(&eng->stream_c, cudaStreamNonBlocking, lo));
+        for (int i = 0; i < 3; ++i) { CK(cudaStreamCreateWithPriority(&eng->stream_sp[i], cudaStreamNonBlocking, hi)); CK(cudaEventCreateWithFlags(&eng->ev_sp[i], cudaEventDisableTiming)); }
+        CK(cudaEventCreateWithFlags(&eng->ev_gen, cudaEventDisableTiming));
     }
     CK(cudaEventCreate(&eng->ev0)); CK(cudaEventCreate(&eng->ev1));
     CK(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&eng->ev_join, cudaEventDisableTiming));
@@ -716,6 +728,7 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "queue_gib") eng->opt_queue_bytes_max = (size_t)(v * (double)(1ull << 30));
     else if (k == "block") eng->opt_block = std::min(TRK_BLOCK_MAX, std::max(32, ((int)v / 32) * 32));
     else if (k == "hot_slice") eng->opt_hot_slice = std::max(1, (int)v);
+    else if (k == "species_streams") eng->opt_species_streams = (v != 0.0);
     else if (k == "lockstep") eng->opt_lockstep = (v != 0.0);
     else if (k == "spread") eng->opt_spread = (v != 0.0);
     else if (k == "quota_min") eng->opt_quota_min = std::min(32, std::max(1, (int)v));
@@ -810,10 +823,20 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             if (total) {        // one generation of the hot cascade (time-sliced, see k_hot)
                 CK(cudaMemsetAsync(eng->d_qcount + QC_HOT(nxt), 0, N_SPECIES * sizeof(uint32_t), eng->stream));
                 CK(cudaMemsetAsync(heads, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
+                // the species of a generation are independent of each other: the (few) valence holes, core holes and photons run
+                // on their own streams beside the electrons instead of lengthening the generation one after the other
+                const bool par = eng->opt_species_streams != 0;
+                cudaStream_t s1 = par ? eng->stream_sp[0] : eng->stream, s2 = par ? eng->stream_sp[1] : eng->stream, s3 = par ? eng->stream_sp[2] : eng->stream;
+                if (par) { CK(cudaEventRecord(eng->ev_gen, eng->stream)); }
                 if (hot[SP_ELECTRON]) { rc = launch_hot<SP_ELECTRON>(eng, eng->qs[cur].q[SP_ELECTRON], hot[SP_ELECTRON], heads + SP_ELECTRON, eng->qs[nxt]); if (rc) return rc; }
-                if (hot[SP_VBHOLE]) { rc = launch_hot<SP_VBHOLE>(eng, eng->qs[cur].q[SP_VBHOLE], hot[SP_VBHOLE], heads + SP_VBHOLE, eng->qs[nxt]); if (rc) return rc; }
-                if (hot[SP_COREHOLE]) { rc = launch_wave<SP_COREHOLE, false>(eng, eng->qs[cur].q[SP_COREHOLE], 0, hot[SP_COREHOLE], heads + SP_COREHOLE, eng->qs[nxt]); if (rc) return rc; }
-                if (hot[SP_PHOTON]) { rc = launch_wave<SP_PHOTON, false>(eng, eng->qs[cur].q[SP_PHOTON], 0, hot[SP_PHOTON], heads + SP_PHOTON, eng->qs[nxt]); if (rc) return rc; }
+                if (hot[SP_VBHOLE]) { if (par) CK(cudaStreamWaitEvent(s1, eng->ev_gen, 0)); rc = launch_hot<SP_VBHOLE>(eng, eng->qs[cur].q[SP_VBHOLE], hot[SP_VBHOLE], heads + SP_VBHOLE, eng->qs[nxt], s1); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[0], s1)); }
+                if (hot[SP_COREHOLE]) { if (par) CK(cudaStreamWaitEvent(s2, eng->ev_gen, 0)); rc = launch_wave<SP_COREHOLE, false>(eng, eng->qs[cur].q[SP_COREHOLE], 0, hot[SP_COREHOLE], heads + SP_COREHOLE, eng->qs[nxt], s2); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[1], s2)); }
+                if (hot[SP_PHOTON]) { if (par) CK(cudaStreamWaitEvent(s3, eng->ev_gen, 0)); rc = launch_wave<SP_PHOTON, false>(eng, eng->qs[cur].q[SP_PHOTON], 0, hot[SP_PHOTON], heads + SP_PHOTON, eng->qs[nxt], s3); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[2], s3)); }
+                if (par) {
+                    if (hot[SP_VBHOLE]) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[0], 0));
+                    if (hot[SP_COREHOLE]) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[1], 0));
+                    if (hot[SP_PHOTON]) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[2], 0));
+                }
                 if (hot[SP_ELECTRON]) {     // the pairs of this generation's impact ionisations join the next generation
                     const int pi = prof_begin(eng, SP_ELECTRON);
                     k_ion_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(eng->qs[0].q[Q_ION], eng->qs[nxt]);
@@ -977,6 +1000,8 @@ void trk3_mc_destroy(trk3_engine *eng) {
     for (auto &e : eng->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (eng->own_stream && eng->stream) cudaStreamDestroy(eng->stream);
     if (eng->stream_c) cudaStreamDestroy(eng->stream_c);
+    for (int i = 0; i < 3; ++i) { if (eng->stream_sp[i]) cudaStreamDestroy(eng->stream_sp[i]); if (eng->ev_sp[i]) cudaEventDestroy(eng->ev_sp[i]); }
+    if (eng->ev_gen) cudaEventDestroy(eng->ev_gen);
     if (eng->ev_fork) cudaEventDestroy(eng->ev_fork);
     if (eng->ev_join) cudaEventDestroy(eng->ev_join);
     delete eng;

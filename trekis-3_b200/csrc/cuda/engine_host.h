@@ -57,6 +57,25 @@ inline void build_lut(const double *E, int N, std::vector<uint16_t> &lut, double
         lut[b] = (uint16_t)j;
     }
 }
+// Accelerator of the search "first index with 1/L >= x" in a cumulative table of the ion (SHI_energy_transfer): bins in log x
+inline void build_inverse_lut(const double *L, int N, int M_temp, std::vector<uint16_t> &lut, double &l0, double &scale) {
+    lut.assign(TRK_NLUT, 1);
+    l0 = 0.0; scale = 0.0;
+    if (N < 2 || N > 65535) return;
+    int first = (M_temp >= 2) ? M_temp - 2 : 0;
+    while (first < N - 1 && !(L[first] > 0.0 && 1.0 / L[first] > 0.0 && std::isfinite(std::log(1.0 / L[first])))) ++first;
+    if (!(L[N - 1] > 0.0)) return;
+    l0 = std::log(1.0 / L[first]);
+    const double l1 = std::log(1.0 / L[N - 1]);
+    if (!(l1 > l0) || !std::isfinite(l0) || !std::isfinite(l1)) { l0 = 0.0; return; }
+    scale = (double)TRK_NLUT / (l1 - l0);
+    int j = first + 1;                                                  // 1-based
+    for (int b = 0; b < TRK_NLUT; ++b) {
+        const double edge = l0 + (double)b / scale;
+        while (j < N && !(L[j - 1] > 0.0 && std::log(1.0 / L[j - 1]) >= edge)) ++j;
+        lut[b] = (uint16_t)j;
+    }
+}
 inline double uniform_inv_step(const double *E, int N) {
     if (N < 3) return 0.0;
     const double step = (E[N - 1] - E[0]) / (double)(N - 1);
@@ -113,6 +132,7 @@ inline int fill_devp_scalars(const trk3_config &c, const trk3_tables &T, const t
     const double g_me = 9.1093821545e-31, g_Mp = 1836.1526724780 * g_me, g_e = 1.602176487e-19, g_h = 1.05457162853e-34, g_Pi = 3.1415926535897932384626433832795;
     p.ion_E = c.shi_E; p.ion_mass = c.shi_mass; p.ion_fixed_Zeff = c.shi_fixed_Zeff; p.ion_Z = c.shi_Z; p.ion_kind_Zeff = c.shi_kind_Zeff;
     p.ion_Zeff0 = host_shi_zeff(c, T);
+    p.ion_pow23 = std::pow((double)c.shi_Z, 0.66666666);
     p.Tim = c.Tim; p.cut_off = c.cut_off; p.layer = c.layer; p.hole_mass = c.hole_mass;
     p.work_function = c.work_function; p.bar_height = c.bar_height;
     p.include_photons = c.include_photons; p.kind_of_EMFP = c.kind_of_EMFP;

@@ -106,6 +106,8 @@ struct DevP {
     const double *leid_hw, *leid_L, *leed_hw, *leed_L, *lhid_hw, *lhid_L, *lhed_hw, *lhed_L;
     const double *dos_E, *dos_DOS, *dos_int, *dos_effm, *out_R, *out_V;
     int32_t shi_Mtemp[TRK3_MAX_SHELLS]; double shi_dL[TRK3_MAX_SHELLS];      // per-shell constants of SHI_energy_transfer
+    GridLut dshi_lut[TRK3_MAX_SHELLS];                   // accelerators of the inverse-CDF search of SHI_energy_transfer (in log 1/L)
+    double ion_pow23;                                    // Zion^0.66666666 (Equilibrium_charge_SHI, evaluated once)
     GridLut lut[N_LUT];                                  // search accelerators of the six energy grids
     double dos_inv_step;                                 // 1/step of the DOS energy grid if it is uniform, else 0
     // below these energies the total inelastic MFP is one constant >= 1e16 (no ionisation possible): lookup skipped

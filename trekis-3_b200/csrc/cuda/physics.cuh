@@ -568,7 +568,7 @@ TRK_HD double shi_zeff(const DevP &p, double E) {
     double Zp = (double)p.ion_Z;
     const double g_v0 = sqrt(2.0 * TRK_RY * TRK_GE / TRK_ME);
     switch (p.ion_kind_Zeff) {
-    case 1: return Zp * (1.0 - m_exp(-(vp / g_v0 / pow(Zp, 0.66666666))));
+    case 1: return Zp * (1.0 - m_exp(-(vp / g_v0 / p.ion_pow23)));
     case 2: { double c1 = 0.6, c2 = 0.45; return Zp * pow(1.0 + pow(vp / (pow(Zp, c2) * g_v0 * 4.0 / 3.0), -1.0 / c1), -c1); }
     case 3: {
         double sz = 0; for (int a = 0; a < p.n_atoms; ++a) sz += p.atom_Z[a] * p.atom_pers[a];
@@ -579,7 +579,7 @@ TRK_HD double shi_zeff(const DevP &p, double E) {
         double x = c1 * pow(vpvo / c2 / 1.54, 1.0 + 1.83 / Zp), x2 = x * x, x4 = x2 * x2;
         return Zp * (8.29 * x + x4) / (0.06 / x + 4.0 + 7.4 * x + x4); }
     case 4: return p.ion_fixed_Zeff;
-    default: return Zp * (1.0 - m_exp(-(vp * 125.0 / TRK_CVEL / pow(Zp, 0.66666666))));
+    default: return Zp * (1.0 - m_exp(-(vp * 125.0 / TRK_CVEL / p.ion_pow23)));
     }
 }
 // SHI_energy_transfer (CDF shells), Monte_Carlo.f90:1719-1780.  The reference's linear search over 1/L
@@ -603,13 +603,26 @@ TRK_HD double shi_energy_transfer(const DevP &p, Rec &r, int shell) {
     const double dL = p.shi_dL[shell];
     double Tot_N = (dL > 0.0 && La[N - 1] > 0.0) ? 1.0 / dL + RN * (1.0 / La[N - 1] - 1.0 / dL) : 1.5e21;
     int N_temmp;
+    const double lTot = m_log(Tot_N);
     if (Tot_N < 1e20) {
-        // 1/L is non-decreasing (cumulative cross section): bisection for the first index with 1/L >= Tot_N
-        int lo = 1, hi = N;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (iLa[mid - 1] < Tot_N) lo = mid + 1; else hi = mid; }
-        N_temmp = lo;
+        // 1/L is non-decreasing (cumulative cross section): the first index with 1/L >= Tot_N, clamped to N.  The tables have
+        // thousands of rows: a direct index in log(1/L) + local scan instead of 13 dependent loads of a bisection.
+        const GridLut &g = p.dshi_lut[shell];
+        int j;
+        if (g.scale > 0.0) {
+            int b = (int)((lTot - g.l0) * g.scale);
+            b = (b < 0) ? 0 : ((b >= TRK_NLUT) ? TRK_NLUT - 1 : b);
+            j = g.lut[b];
+            while (j < N && iLa[j - 1] < Tot_N) ++j;
+            while (j > 1 && !(iLa[j - 2] < Tot_N)) --j;
+        } else {
+            int lo = 1, hi = N;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (iLa[mid - 1] < Tot_N) lo = mid + 1; else hi = mid; }
+            j = lo;
+        }
+        N_temmp = j;
     } else N_temmp = M_temp;
-    if (N_temmp > M_temp) return interp5t(iLa[N_temmp - 2], iLa[N_temmp - 1], Ea[N_temmp - 2], Ea[N_temmp - 1], liLa[N_temmp - 2], liLa[N_temmp - 1], lEa[N_temmp - 2], lEa[N_temmp - 1], Tot_N, m_log(Tot_N));
+    if (N_temmp > M_temp) return interp5t(iLa[N_temmp - 2], iLa[N_temmp - 1], Ea[N_temmp - 2], Ea[N_temmp - 1], liLa[N_temmp - 2], liLa[N_temmp - 1], lEa[N_temmp - 2], lEa[N_temmp - 1], Tot_N, lTot);
     return p.shell_Ip[shell];
 }
 
