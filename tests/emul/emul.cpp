@@ -26,6 +26,7 @@ struct EmuCtx {
         else if (sp == SP_VBHOLE && vbhole_is_cold(p, r)) cold[1].push_back(r);
         else next[sp].push_back(r);
     }
+    void snap(int sp, const Rec &r, int i) { snapshot_any(*this, sp, r, i); }                 // the engine may defer this to k_snapshot
     void push_ion(const IonEvent &ev) { electron_ion_emit(*this, ev); }     // the engine defers this to k_ion_emit
     void tally(int id, int64_t idx, double v) { p.tally[p.g_off[id] + idx] += v; }
     void add_u32(uint32_t *b, size_t i) { b[i] += 1u; }

@@ -33,7 +33,8 @@ __constant__ DevP c_p;
 #define Q_EL_COLD N_SPECIES
 #define Q_VB_COLD (N_SPECIES + 1)
 #define Q_ION (N_SPECIES + 2)         // impact ionisations of the current generation (IonEvent records, see k_ion_emit)
-#define N_QUEUES (N_SPECIES + 3)
+#define Q_SNAP (N_SPECIES + 3)        // snapshot records of the whole batch (see k_snapshot)
+#define N_QUEUES (N_SPECIES + 4)
 struct QueueSet { Queue q[N_QUEUES]; };
 #define N_CLASSES (N_SPECIES + 4)     // timing classes: hot waves per species, k_shi, finalize, cold electrons, cold holes
 
@@ -62,6 +63,25 @@ struct DevCtx {
         push_q(qi, r);
     }
     __device__ void push_hot(int sp, const Rec &r) { push_q(sp, r); }
+    // A snapshot is ~450 instructions that only a few lanes of a warp need in any given round, and the kernels are bound by
+    // instruction fetch: the lanes just append the particle's state (what snapshot_* reads: 9 numbers) to a queue, and
+    // k_snapshot turns the records into tallies with full warps.  `defer` = 0: tally right here (k_snapshot itself).
+    int defer;
+    __device__ void snap(int sp, const Rec &r, int i) {
+        if (!defer) { snapshot_any(*this, sp, r, i); return; }
+        const unsigned am = __activemask();
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(am) - 1;
+        const Queue &q = out.q[Q_SNAP];
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(q.count, (unsigned)__popc(am));
+        base = __shfl_sync(am, base, leader);
+        const unsigned slot = base + __popc(am & ((1u << lane) - 1u));
+        if (slot >= q.cap) { atomicAdd(&p.errors[TRK3_ERR_QUEUE_OVERFLOW], 1ull); return; }
+        q.col[0][slot] = r.E; q.col[3][slot] = r.t0; q.col[5][slot] = r.X; q.col[6][slot] = r.Y; q.col[9][slot] = r.theta; q.col[10][slot] = r.phi;
+        if (sp != SP_ELECTRON && sp != SP_PHOTON) { q.col[1][slot] = r.Ehkin; q.col[2][slot] = r.Mass; q.col[8][slot] = r.L; }
+        q.iter[slot] = r.iter; q.shell[slot] = r.shell; q.ctr[slot] = (uint32_t)i | ((uint32_t)sp << 16);
+    }
     __device__ void push_ion(const IonEvent &ev) {       // an IonEvent travels in the columns of an ordinary record
         Rec r;
         r.E = ev.dE; r.Ehkin = ev.t; r.Mass = ev.X; r.t0 = ev.Y; r.tn = ev.Z; r.X = ev.theta0; r.Y = ev.phi0; r.Z = ev.theta; r.L = ev.phi;
@@ -144,7 +164,7 @@ __device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned i
 __global__ void __launch_bounds__(32 * SHI_WARPS) k_shi(Queue stage, QueueSet qout) {
     __shared__ unsigned int s_cnt[S_NCNT];
     block_prologue(nullptr, s_cnt, 0);
-    DevCtx c{c_p, qout, nullptr, s_cnt};
+    DevCtx c{c_p, qout, nullptr, s_cnt, c_p.defer_snap};
     const uint32_t k = blockIdx.x * SHI_WARPS + (threadIdx.x >> 5);
     if ((threadIdx.x & 31) == 0 && k < c_p.batch_n) {
         Rec s;
@@ -164,7 +184,7 @@ __global__ void __launch_bounds__(32 * SHI_WARPS) k_shi(Queue stage, QueueSet qo
 __global__ void __launch_bounds__(256) k_shi_emit(Queue stage, QueueSet qout) {
     __shared__ unsigned int s_cnt[S_NCNT];
     block_prologue(nullptr, s_cnt, 0);
-    DevCtx c{c_p, qout, nullptr, s_cnt};
+    DevCtx c{c_p, qout, nullptr, s_cnt, c_p.defer_snap};
     const uint32_t n = min(*stage.count, stage.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         ShiEvent ev;
@@ -180,7 +200,7 @@ __global__ void __launch_bounds__(256) k_shi_emit(Queue stage, QueueSet qout) {
 __global__ void __launch_bounds__(256) k_ion_emit(Queue ionq, QueueSet qout) {
     __shared__ unsigned int s_cnt[S_NCNT];
     block_prologue(nullptr, s_cnt, 0);
-    DevCtx c{c_p, qout, nullptr, s_cnt};
+    DevCtx c{c_p, qout, nullptr, s_cnt, c_p.defer_snap};
     const uint32_t n = min(*ionq.count, ionq.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Rec r;
@@ -193,6 +213,27 @@ __global__ void __launch_bounds__(256) k_ion_emit(Queue ionq, QueueSet qout) {
     block_epilogue(c_p, nullptr, s_cnt);
 }
 
+// k_snapshot: the snapshot records of a batch -> tallies (Calculated_statistics, Monte_Carlo.f90:881-1110), one thread per record
+__global__ void __launch_bounds__(256) k_snapshot(Queue sq, QueueSet qout, int use_smem) {
+    extern __shared__ double s_dyn[];
+    __shared__ unsigned int s_cnt[S_NCNT];
+    double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
+    block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? c_p.s_total : 0);
+    DevCtx c{c_p, qout, s_tally, s_cnt, 0};
+    const uint32_t n = min(*sq.count, sq.cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Rec r;
+        const uint32_t tag = sq.ctr[i];
+        const int sp = (int)(tag >> 16), ig = (int)(tag & 0xffffu);
+        r.E = sq.col[0][i]; r.t0 = sq.col[3][i]; r.X = sq.col[5][i]; r.Y = sq.col[6][i]; r.theta = sq.col[9][i]; r.phi = sq.col[10][i];
+        r.Ehkin = 0.0; r.Mass = 1.0; r.L = 0.0;
+        if (sp != SP_ELECTRON && sp != SP_PHOTON) { r.Ehkin = sq.col[1][i]; r.Mass = sq.col[2][i]; r.L = sq.col[8][i]; }
+        r.iter = sq.iter[i]; r.shell = sq.shell[i];
+        snapshot_any(c, sp, r, ig);
+    }
+    block_epilogue(c_p, s_tally, s_cnt);
+}
+
 // k_wave<SP, COLD>: records [first, n_in) of queue qin, histories followed with lane refill until they end or
 // have to change queue (hot -> cold when the particle can no longer ionise, core hole -> valence hole, ...).
 template <int SP, bool COLD>
@@ -201,7 +242,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
     block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? c_p.s_total : 0);
-    DevCtx c{c_p, qout, s_tally, s_cnt};
+    DevCtx c{c_p, qout, s_tally, s_cnt, c_p.defer_snap};
     const int lane = threadIdx.x & 31;
     bool active = false, exhausted = false;
     Rec r;
@@ -267,7 +308,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(Queue qin, uint32_t n_
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
     block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? c_p.s_total : 0);
-    DevCtx c{c_p, qout, s_tally, s_cnt};
+    DevCtx c{c_p, qout, s_tally, s_cnt, c_p.defer_snap};
     const int lane = threadIdx.x & 31;
     bool active = false, exhausted = false, have_rn = false;
     Rec r;
@@ -300,7 +341,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(Queue qin, uint32_t n_
         // snapshots of the current free flight, then the channel roulette of the collision that ends it
         int want = 0;       // 1 elastic, 2 inelastic
         if (active) {
-            while (ig <= c_p.Nt && c_p.tg[ig - 1] <= r.tn) { if (SP == SP_ELECTRON) snapshot_electron(c, r, ig); else snapshot_hole(c, r, ig); ++ig; }
+            while (ig <= c_p.Nt && c_p.tg[ig - 1] <= r.tn) { c.snap(SP, r, ig); ++ig; }
             if (ig > c_p.Nt) active = false;
             else {
                 if (!have_rn) { RN = rn(c_p, r); have_rn = true; }
@@ -370,10 +411,10 @@ struct trk3_engine {
     // options
     int opt_batch = 1024, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
     int opt_hot_slice = 64, opt_inel_min = 1, opt_overlap = 0, opt_cold_min = 16384;
-    int opt_spread = 1, opt_quota_min = 1, opt_lockstep = 0, opt_species_streams = 1;
+    int opt_spread = 1, opt_quota_min = 1, opt_lockstep = 0, opt_species_streams = 1, opt_defer_snap = 1;
 
     double opt_cap_factor = 2.0;
-    size_t opt_queue_bytes_max = (size_t)24 << 30;
+    size_t opt_queue_bytes_max = (size_t)64 << 30;       // of the 180 GB of a B200
     // per-batch resources
     uint32_t nb_alloc = 0;
     QueueSet qs[2]{};
@@ -399,13 +440,14 @@ struct trk3_engine {
 
 // d_qcount layout (uint32): [0..3] hot counts generation A, [4..7] generation B, [8..9] cold counts,
 // [10..13] hot counts of set X (particles handed back by the cold kernels), [14] ionisations of the generation,
-// [15] their high-water mark, [16..19] hot heads, [20..21] cold heads
+// [15] their high-water mark, [16] snapshot records of the batch, [17..20] hot heads, [21..22] cold heads
 #define QC_HOT(b) ((b) * N_SPECIES)
 #define QC_COLD (2 * N_SPECIES)
 #define QC_X (2 * N_SPECIES + 2)
 #define QC_ION (3 * N_SPECIES + 2)
-#define QC_HEAD (3 * N_SPECIES + 4)
-#define QC_TOTAL (4 * N_SPECIES + 6)
+#define QC_SNAP (3 * N_SPECIES + 4)
+#define QC_HEAD (3 * N_SPECIES + 5)
+#define QC_TOTAL (4 * N_SPECIES + 7)
 
 namespace {
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { eng->err = std::string(#call) + ": " + cudaGetErrorString(e_); return TRK3_E_CUDA; } } while (0)
@@ -497,6 +539,7 @@ void queue_caps(const trk3_engine *eng, double cap[N_QUEUES]) {
     cap[SP_PHOTON] = eng->cfg.include_photons ? 0.25 * n + 64.0 : 1.0;
     cap[Q_EL_COLD] = n; cap[Q_VB_COLD] = n;       // every carrier of an iteration ends up here once
     cap[Q_ION] = n;
+    cap[Q_SNAP] = eng->opt_defer_snap ? 1.25 * n * (double)eng->lay.Nt : 1.0;     // every carrier at every grid time it lives to see
 }
 double queue_bytes_per_iteration(const trk3_engine *eng) {
     double cap[N_QUEUES]; queue_caps(eng, cap);
@@ -523,7 +566,7 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
         if (rc) return rc;
     }
     for (int s = N_SPECIES; s < N_QUEUES; ++s) {      // the cold queues and the ionisation queue are shared by both generations
-        int rc = alloc_queue(eng, eng->qs[0].q[s], (uint32_t)(cap[s] * (double)nb), eng->d_qcount + (s == Q_ION ? QC_ION : QC_COLD + (s - N_SPECIES)));
+        int rc = alloc_queue(eng, eng->qs[0].q[s], (uint32_t)(cap[s] * (double)nb), eng->d_qcount + (s == Q_ION ? QC_ION : (s == Q_SNAP ? QC_SNAP : QC_COLD + (s - N_SPECIES))));
         if (rc) return rc;
         eng->qs[1].q[s] = eng->qs[0].q[s]; eng->qs_x.q[s] = eng->qs[0].q[s];
     }
@@ -728,6 +771,7 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "queue_gib") eng->opt_queue_bytes_max = (size_t)(v * (double)(1ull << 30));
     else if (k == "block") eng->opt_block = std::min(TRK_BLOCK_MAX, std::max(32, ((int)v / 32) * 32));
     else if (k == "hot_slice") eng->opt_hot_slice = std::max(1, (int)v);
+    else if (k == "defer_snap") { eng->opt_defer_snap = (v != 0.0); eng->nb_alloc = 0; }
     else if (k == "species_streams") eng->opt_species_streams = (v != 0.0);
     else if (k == "lockstep") eng->opt_lockstep = (v != 0.0);
     else if (k == "spread") eng->opt_spread = (v != 0.0);
@@ -788,6 +832,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         CK(cudaMemcpyAsync(eng->d_tally_bak, eng->d_tally, (size_t)eng->lay.total * sizeof(double), cudaMemcpyDeviceToDevice, eng->stream));
         CK(cudaMemcpyAsync(eng->d_counters_bak, eng->d_counters, n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, eng->stream));
         eng->hp.batch_begin = (uint32_t)b0; eng->hp.batch_n = nb;
+        eng->hp.defer_snap = eng->opt_defer_snap;
 
         CK(cudaMemcpyToSymbolAsync(c_p, &eng->hp, sizeof(DevP), 0, cudaMemcpyHostToDevice, eng->stream));
         CK(cudaMemsetAsync(eng->d_u32, 0, eng->sl.u32_total * sizeof(uint32_t), eng->stream));
@@ -816,6 +861,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             for (int s = 0; s < N_SPECIES; ++s) { if (hot[s] > eng->qs[cur].q[s].cap) { overflow = true; hot[s] = eng->qs[cur].q[s].cap; } total += hot[s]; }
             for (int s = 0; s < 2; ++s) if (cold[s] > eng->qs[0].q[N_SPECIES + s].cap) { overflow = true; cold[s] = eng->qs[0].q[N_SPECIES + s].cap; }
             if (h_cnt[QC_ION + 1] > eng->qs[0].q[Q_ION].cap) overflow = true;
+            if (h_cnt[QC_SNAP] > eng->qs[0].q[Q_SNAP].cap) overflow = true;
             if (overflow) break;
             const uint64_t cold_pending = (uint64_t)(cold[0] - cold_done[0]) + (cold[1] - cold_done[1]);
             ++waves;
@@ -878,6 +924,27 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             cur = nxt;
         }
         if (eng->opt_overlap) { CK(cudaEventRecord(eng->ev_join, sc)); CK(cudaStreamWaitEvent(eng->stream, eng->ev_join, 0)); }
+        if (eng->opt_defer_snap && !overflow) {
+            // all histories of the batch have ended: turn the queued snapshot records into tallies
+            uint32_t n_snap = 0;
+            CK(cudaMemcpyAsync(&n_snap, eng->d_qcount + QC_SNAP, sizeof n_snap, cudaMemcpyDeviceToHost, eng->stream));
+            CK(cudaStreamSynchronize(eng->stream));
+            if (n_snap > eng->qs[0].q[Q_SNAP].cap) overflow = true;
+            else if (n_snap) {
+                size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
+                int use_smem = eng->opt_use_smem;
+                if (smem > (size_t)eng->smem_optin - 1024) { smem = 8; use_smem = 0; }
+                if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_snapshot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int bps = 0;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_snapshot, 256, smem)); if (bps < 1) bps = 1;
+                const uint32_t grid = std::min<uint32_t>((n_snap + 255u) / 256u, (uint32_t)(eng->n_sm * bps));
+                const int pi = prof_begin(eng, N_SPECIES + 1);
+                k_snapshot<<<grid, 256, smem, eng->stream>>>(eng->qs[0].q[Q_SNAP], eng->qs[0], use_smem);
+                prof_end(eng, pi);
+                CK(cudaGetLastError());
+                eng->launches++;
+            }
+        }
         if (overflow) {
             if (++retries > 6) { eng->err = "particle queue overflow persists after 6 capacity doublings"; return TRK3_E_OVERFLOW; }
             CK(cudaMemcpyAsync(eng->d_tally, eng->d_tally_bak, (size_t)eng->lay.total * sizeof(double), cudaMemcpyDeviceToDevice, eng->stream));

@@ -50,7 +50,6 @@ struct Queue {        // SoA particle queue in global memory
     double *col[TRK_NCOL];
     uint64_t *id; uint32_t *ctr; uint32_t *iter; int32_t *shell;
     uint32_t *count;  // number of records pushed (may exceed capacity on overflow; clamp when reading)
-    uint32_t *ready;  // per slot: == DevP::epoch once the record is completely written (queues consumed while they grow)
     uint32_t cap;
 };
 
@@ -124,8 +123,7 @@ struct DevP {
     // ---- per-iteration scratch
     IterArrays it;
     uint32_t batch_begin, batch_n;       // global index of the first iteration of the batch, iterations in it
-    uint32_t epoch;                      // serial number of the batch (never 0): value of Queue::ready of its records
-    unsigned long long *hot_finished;    // records of the hot queues whose processing has ended (termination of k_hot_all)
+    int32_t defer_snap;                  // 1: the wave kernels queue their snapshots for k_snapshot instead of tallying them
     // ---- counters
     unsigned long long *events;          // [TRK3_N_EVENT_CLASSES]
     unsigned long long *errors;          // [TRK3_N_ERRORS]

@@ -11,6 +11,8 @@
 //   c.push(species, rec)     append a particle to a queue (the context routes it: hot/cold, see electron_is_cold)
 //   c.push_hot(species, rec) append to the queue of the full handlers regardless of the routing rule
 //   c.push_ion(ev)           hand an impact ionisation over: its electron-hole pair is created by electron_ion_emit
+//   c.snap(species, rec, i)  the particle's contribution to the tallies of grid time i: snapshot_electron/hole/photon,
+//                            now or (CUDA engine) from a queue of snapshot records by a kernel of its own
 //   c.tally(id, idx, v)      add v to element idx of Out_* array `id` (block-private or global)
 //   c.add_u32(base, idx)     atomic ++ on a per-iteration integer histogram
 //   c.add_f64(base, idx, v)  atomic += on a per-iteration double array
@@ -710,6 +712,14 @@ TRK_HD void snapshot_photon(C &c, const Rec &ph, int i) {
     c.add_f64(p.it.esnap, base, ph.E);
 }
 
+// the snapshot of a particle of species `sp` (valence and core holes share snapshot_hole)
+template <class C>
+TRK_HD void snapshot_any(C &c, int sp, const Rec &r, int i) {
+    if (sp == SP_ELECTRON) snapshot_electron(c, r, i);
+    else if (sp == SP_PHOTON) snapshot_photon(c, r, i);
+    else snapshot_hole(c, r, i);
+}
+
 // lattice energy of an elastic event in time interval iv at radius R (Monte_Carlo.f90:2414-2436, :2702-2719)
 template <class C>
 TRK_HD void deposit_lattice(C &c, const Rec &r, int iv, double X, double Y, double dE) {
@@ -1147,7 +1157,7 @@ TRK_HD int step_electron(C &c, Rec &e, int &ig, Cache &k) {
         RN = rn(p, e);
         if (electron_roulette_inelastic(k, RN)) { e.ctr--; return ST_MOVE_HOT; }      // probability ~1e-16 (IMFP >= 1e16)
     }
-    while (ig <= p.Nt && p.tg[ig - 1] <= e.tn) { snapshot_electron(c, e, ig); ++ig; }
+    while (ig <= p.Nt && p.tg[ig - 1] <= e.tn) { c.snap(SP_ELECTRON, e, ig); ++ig; }
     if (ig > p.Nt) return ST_DONE;
     if (COLD) { electron_event_t<EV_ELASTIC>(c, e, ig, k, RN); return ST_CONT; }
     RN = rn(p, e);
@@ -1163,7 +1173,7 @@ template <bool COLD, class C>
 TRK_HD int step_vbhole(C &c, Rec &h, int &ig, Cache &k) {
     const DevP &p = c.p;
     if (COLD && h.tn < p.tg[p.Nt - 1] && !(h.Ehkin < p.h_cold)) return ST_MOVE;
-    while (ig <= p.Nt && p.tg[ig - 1] <= h.tn) { snapshot_hole(c, h, ig); ++ig; }
+    while (ig <= p.Nt && p.tg[ig - 1] <= h.tn) { c.snap(SP_VBHOLE, h, ig); ++ig; }
     if (ig > p.Nt) return ST_DONE;
     if (COLD) {
         vbhole_event_t<EV_ELASTIC>(c, h, ig, k, rn(p, h));
@@ -1176,7 +1186,7 @@ TRK_HD int step_vbhole(C &c, Rec &h, int &ig, Cache &k) {
 template <class C>
 TRK_HD int step_corehole(C &c, Rec &h, int &ig) {
     const DevP &p = c.p;
-    while (ig <= p.Nt && p.tg[ig - 1] <= h.tn) { snapshot_hole(c, h, ig); ++ig; }
+    while (ig <= p.Nt && p.tg[ig - 1] <= h.tn) { c.snap(SP_VBHOLE, h, ig); ++ig; }
     if (ig > p.Nt) return ST_DONE;
     corehole_event(c, h);
     if (h.shell == p.vb_shell) { c.push(SP_VBHOLE, h); return ST_DONE; }
@@ -1185,7 +1195,7 @@ TRK_HD int step_corehole(C &c, Rec &h, int &ig) {
 template <class C>
 TRK_HD int step_photon(C &c, Rec &ph, int &ig) {
     const DevP &p = c.p;
-    while (ig <= p.Nt && p.tg[ig - 1] <= ph.tn) { snapshot_photon(c, ph, ig); ++ig; }
+    while (ig <= p.Nt && p.tg[ig - 1] <= ph.tn) { c.snap(SP_PHOTON, ph, ig); ++ig; }
     if (ig > p.Nt) return ST_DONE;
     photon_event(c, ph);
     return ST_DONE;
