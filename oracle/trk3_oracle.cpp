@@ -67,9 +67,15 @@ struct Rng {
     double rn(Stream &st) {
         uint64_t bits;
         if (mode == 0) bits = next64();
-        else { uint32_t o[4]; philox4x32_10((uint32_t)st.id, (uint32_t)(st.id >> 32), st.ctr++, it, (uint32_t)seed, (uint32_t)(seed >> 32), o); bits = (uint64_t)o[0] | ((uint64_t)o[1] << 32); }
+        else {      // draw k of a stream = half (k & 1) of Philox block k >> 1 (one block yields two 64-bit draws)
+            uint32_t o[4]; const uint32_t k = st.ctr++;
+            philox4x32_10((uint32_t)st.id, (uint32_t)(st.id >> 32), k >> 1, it, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+            bits = (k & 1u) ? ((uint64_t)o[2] | ((uint64_t)o[3] << 32)) : ((uint64_t)o[0] | ((uint64_t)o[1] << 32));
+        }
         return (double)((bits >> 11) + 1) * (1.0 / 9007199254740992.0);
     }
+    // every collision starts at an even draw index, so that its draws pair up in Philox blocks (engine: event_begin)
+    void align(Stream &st) { if (mode != 0) st.ctr = (st.ctr + 1u) & ~1u; }
     Stream child(Stream &parent, uint32_t tag) {      // id of a newly created particle
         Stream c; c.ctr = 0;
         if (mode == 0) { c.id = 0; return c; }
@@ -625,6 +631,7 @@ struct MC {
     // ---- SHI_Monte_Carlo, Monte_Carlo.f90:2153-2249
     void SHI_Monte_Carlo() {
         Stream &st = SHI_loc.rng;
+        rng.align(st);
         ev[TRK3_EV_SHI]++;
         int Nat_cur, Nshl_cur;
         Which_shell(T.shi_E, T.shi_L, T.n_shi, SHI_loc.E, st, Nat_cur, Nshl_cur);
@@ -667,6 +674,7 @@ struct MC {
     // ---- Electron_Monte_Carlo, Monte_Carlo.f90:2253-2474
     void Electron_Monte_Carlo(int NOP, int i, Tally &out) {
         Stream st = All_electrons[NOP - 1].rng;      // copy: All_electrons may be reallocated by Check_size
+        rng.align(st);
         double Eel = All_electrons[NOP - 1].E;
         double IMFP = Next_free_path_2d(Eel, T.ei_E, El_IMFP.data(), T.n_ei);
         double EMFP = Next_free_path_2d(Eel, T.ee_E, T.ee_L, T.n_ee);
@@ -738,6 +746,7 @@ struct MC {
     // ---- Hole_Monte_Carlo, Monte_Carlo.f90:2517-2869
     void Hole_Monte_Carlo(int NOP, int i, double t_cur, Tally &out) {
         Stream st = All_holes[NOP - 1].rng;
+        rng.align(st);
         double Egap = Egap_;
         if (isVB(All_holes[NOP - 1].KOA, All_holes[NOP - 1].Shl)) {
             double Eel = All_holes[NOP - 1].Ehkin;
@@ -875,6 +884,7 @@ struct MC {
         ev[TRK3_EV_PHOTON]++;
         Photon &p = All_photons[NOP - 1];
         Stream st = p.rng;
+        rng.align(st);
         double Eel = p.E, L = p.L, theta0 = p.theta, phi0 = p.phi;
         double X = p.X + L * std::sin(theta0) * std::sin(phi0), Y = p.Y + L * std::sin(theta0) * std::cos(phi0), Z = p.Z + L * std::cos(theta0);
         int Nat_cur, Nshl_cur;

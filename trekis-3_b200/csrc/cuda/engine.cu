@@ -121,6 +121,7 @@ __device__ inline void load_rec(const Queue &q, uint32_t i, Rec &r) {
     r.E = q.col[0][i]; r.Ehkin = q.col[1][i]; r.Mass = q.col[2][i]; r.t0 = q.col[3][i]; r.tn = q.col[4][i];
     r.X = q.col[5][i]; r.Y = q.col[6][i]; r.Z = q.col[7][i]; r.L = q.col[8][i]; r.theta = q.col[9][i]; r.phi = q.col[10][i];
     r.id = q.id[i]; r.ctr = q.ctr[i]; r.iter = q.iter[i]; r.shell = q.shell[i];
+    r.rc_blk = 0xffffffffu;
 }
 
 __device__ inline void block_prologue(double *s_tally, unsigned int *s_cnt, int s_total) {
@@ -161,12 +162,13 @@ __device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned i
 // different ions never serialise each other through divergence.  Only the ion's own part of a collision runs here; the
 // collision is written to a staging queue and its electron-hole pair is created by k_shi_emit, one thread per collision.
 #define SHI_WARPS 4
-__global__ void __launch_bounds__(32 * SHI_WARPS) k_shi(Queue stage, QueueSet qout) {
+__global__ void __launch_bounds__(32 * SHI_WARPS) k_shi(Queue stage, QueueSet qout, int lanes) {
     __shared__ unsigned int s_cnt[S_NCNT];
     block_prologue(nullptr, s_cnt, 0);
     DevCtx c{c_p, qout, nullptr, s_cnt, c_p.defer_snap};
-    const uint32_t k = blockIdx.x * SHI_WARPS + (threadIdx.x >> 5);
-    if ((threadIdx.x & 31) == 0 && k < c_p.batch_n) {
+    // `lanes` ions per warp: 1 = no divergence between ions at all, more = fewer instruction streams to fetch
+    const uint32_t k = (blockIdx.x * SHI_WARPS + (threadIdx.x >> 5)) * (uint32_t)lanes + (threadIdx.x & 31);
+    if ((int)(threadIdx.x & 31) < lanes && k < c_p.batch_n) {
         Rec s;
         shi_begin(c_p, s, c_p.batch_begin + k);
         while (s.tn < c_p.Tim) {
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(Queue qin, uint32_t n_
             while (ig <= c_p.Nt && c_p.tg[ig - 1] <= r.tn) { c.snap(SP, r, ig); ++ig; }
             if (ig > c_p.Nt) active = false;
             else {
-                if (!have_rn) { RN = rn(c_p, r); have_rn = true; }
+                if (!have_rn) { event_begin(r); RN = rn(c_p, r); have_rn = true; }
                 want = hot_roulette<SP>(k, RN) ? 2 : 1;
             }
         }
@@ -411,6 +413,7 @@ struct trk3_engine {
     // options
     int opt_batch = 1024, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
     int opt_hot_slice = 64, opt_inel_min = 1, opt_overlap = 0, opt_cold_min = 16384;
+    int opt_shi_lanes = 1;
     int opt_spread = 1, opt_quota_min = 1, opt_lockstep = 0, opt_species_streams = 1, opt_defer_snap = 1;
 
     double opt_cap_factor = 2.0;
@@ -771,6 +774,7 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "queue_gib") eng->opt_queue_bytes_max = (size_t)(v * (double)(1ull << 30));
     else if (k == "block") eng->opt_block = std::min(TRK_BLOCK_MAX, std::max(32, ((int)v / 32) * 32));
     else if (k == "hot_slice") eng->opt_hot_slice = std::max(1, (int)v);
+    else if (k == "shi_lanes") eng->opt_shi_lanes = std::min(32, std::max(1, (int)v));
     else if (k == "defer_snap") { eng->opt_defer_snap = (v != 0.0); eng->nb_alloc = 0; }
     else if (k == "species_streams") eng->opt_species_streams = (v != 0.0);
     else if (k == "lockstep") eng->opt_lockstep = (v != 0.0);
@@ -841,7 +845,8 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         { const int pi = prof_begin(eng, N_SPECIES);
           // collisions are staged in the (still unused) electron queue of the other generation
           const Queue &stage = eng->qs[1].q[SP_ELECTRON];
-          k_shi<<<(nb + SHI_WARPS - 1) / SHI_WARPS, 32 * SHI_WARPS, 0, eng->stream>>>(stage, eng->qs[0]);
+          const uint32_t shi_warps = (nb + eng->opt_shi_lanes - 1) / eng->opt_shi_lanes;
+          k_shi<<<(shi_warps + SHI_WARPS - 1) / SHI_WARPS, 32 * SHI_WARPS, 0, eng->stream>>>(stage, eng->qs[0], eng->opt_shi_lanes);
           k_shi_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(stage, eng->qs[0]);
           prof_end(eng, pi); }
         CK(cudaGetLastError());

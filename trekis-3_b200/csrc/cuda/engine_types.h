@@ -42,6 +42,8 @@ struct Rec {
     uint32_t ctr;     // next draw index of the stream
     uint32_t iter;    // global iteration index (4th Philox counter word)
     int32_t shell;    // flat shell of a hole (unused for electrons/photons)
+    // second half of the Philox block of the last even draw (registers only, never stored in a queue)
+    uint32_t rc_a, rc_b, rc_blk = 0xffffffffu;
 };
 
 #define TRK_NCOL 11   // double columns of a queue

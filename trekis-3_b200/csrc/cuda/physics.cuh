@@ -68,7 +68,7 @@ TRK_HD uint32_t trk_mulhi(uint32_t a, uint32_t b) {
 // The wave kernels are bound by instruction FETCH (ncu: gcc__cache_requests_type_instruction at 98 % of peak, SM
 // instruction-cache hit rate 58 %): what counts is the number of distinct instruction lines a collision streams through,
 // not the number of instructions it executes.  TRK_PHILOX_ROLLED keeps the ten rounds as a loop (one round of code).
-TRK_HDN void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1) {
+TRK_HDN void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3) {
 #if defined(TRK_PHILOX_ROLLED) && defined(__CUDA_ARCH__)
 #pragma unroll 1
 #else
@@ -81,19 +81,30 @@ TRK_HDN void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
         c0 = n0; c1 = l1; c2 = n2; c3 = l0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    o0 = c0; o1 = c1;
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 // uniform in (0,1]: the reference can draw RN = 0 (m_log(RN), L/RN -> inf); we exclude it
+// Draw k of a stream is half (k & 1) of Philox block k >> 1: one Philox evaluation serves two consecutive draws (the
+// second half waits in the record's registers).  Collisions start at even draw indices (event_begin), so that the usual
+// sequence of a collision -- channel roulette, transferred energy | azimuth, next free path -- costs two evaluations.
 TRK_HD double rn(const DevP &p, Rec &r) {
+    const uint32_t k = r.ctr++, blk = k >> 1;
     uint32_t a, b;
-    philox4x32_10((uint32_t)r.id, (uint32_t)(r.id >> 32), r.ctr++, r.iter, p.seed_lo, p.seed_hi, a, b);
+    if ((k & 1u) && r.rc_blk == blk) { a = r.rc_a; b = r.rc_b; }
+    else {
+        uint32_t o0, o1, o2, o3;
+        philox4x32_10((uint32_t)r.id, (uint32_t)(r.id >> 32), blk, r.iter, p.seed_lo, p.seed_hi, o0, o1, o2, o3);
+        if (k & 1u) { a = o2; b = o3; }
+        else { a = o0; b = o1; r.rc_a = o2; r.rc_b = o3; r.rc_blk = blk; }
+    }
     uint64_t bits = (uint64_t)a | ((uint64_t)b << 32);
     return (double)((bits >> 11) + 1) * (1.0 / 9007199254740992.0);
 }
+TRK_HD void event_begin(Rec &r) { r.ctr = (r.ctr + 1u) & ~1u; }
 // id of a particle created by `parent` (tag 1 electron, 2 hole, 3 photon)
 TRK_HD uint64_t child_id(const DevP &p, Rec &parent, uint32_t tag) {
-    uint32_t a, b;
-    philox4x32_10((uint32_t)parent.id, (uint32_t)(parent.id >> 32), parent.ctr++, parent.iter, p.seed_lo, p.seed_hi ^ (0x80000000u | tag), a, b);
+    uint32_t a, b, c, d;
+    philox4x32_10((uint32_t)parent.id, (uint32_t)(parent.id >> 32), parent.ctr++, parent.iter, p.seed_lo, p.seed_hi ^ (0x80000000u | tag), a, b, c, d);
     return (uint64_t)a | ((uint64_t)b << 32);
 }
 
@@ -950,6 +961,7 @@ TRK_HD void corehole_event(C &c, Rec &h) {
     const DevP &p = c.p;
     const double t_ev = h.tn;
     const int sh0 = h.shell;
+    event_begin(h);
     double RN = rn(p, h);
     const double t_Auger = p.shell_auger[sh0], t_Radiat = p.shell_radiat[sh0];
     const double Ip0 = p.shell_Ip[sh0];
@@ -1036,6 +1048,7 @@ template <class C>
 TRK_HD void photon_event(C &c, Rec &ph) {
     const DevP &p = c.p;
     c.event(TRK3_EV_PHOTON);
+    event_begin(ph);
     const double Eel = ph.E, L = ph.L, theta0 = ph.theta, phi0 = ph.phi, t_ev = ph.tn;
     const double st0 = m_sin(theta0);
     const double X = ph.X + L * st0 * m_sin(phi0), Y = ph.Y + L * st0 * m_cos(phi0), Z = ph.Z + L * m_cos(theta0);
@@ -1081,6 +1094,7 @@ TRK_HD void shi_step(C &c, Rec &s, ShiEvent &ev) {
     const DevP &p = c.p;
     const double MSHI = p.ion_mass * TRK_MP;
     c.event(TRK3_EV_SHI);
+    event_begin(s);
     const double lEs = m_log(s.E);
     int n_E;
     int shell = which_shell(p, s, tab_shi_L(p), s.E, lEs, n_E);
@@ -1154,12 +1168,14 @@ TRK_HD int step_electron(C &c, Rec &e, int &ig, Cache &k) {
     double RN = 0.0;
     if (COLD && e.tn < p.tg[p.Nt - 1]) {                          // a collision is pending: is it really an elastic one?
         if (!(e.E < p.e_cold)) return ST_MOVE;
+        event_begin(e);
         RN = rn(p, e);
         if (electron_roulette_inelastic(k, RN)) { e.ctr--; return ST_MOVE_HOT; }      // probability ~1e-16 (IMFP >= 1e16)
     }
     while (ig <= p.Nt && p.tg[ig - 1] <= e.tn) { c.snap(SP_ELECTRON, e, ig); ++ig; }
     if (ig > p.Nt) return ST_DONE;
     if (COLD) { electron_event_t<EV_ELASTIC>(c, e, ig, k, RN); return ST_CONT; }
+    event_begin(e);
     RN = rn(p, e);
     electron_event_t<EV_ANY>(c, e, ig, k, RN);
     return (e.E < p.e_cold && e.tn < p.Tim) ? ST_MOVE : ST_CONT;
@@ -1176,9 +1192,11 @@ TRK_HD int step_vbhole(C &c, Rec &h, int &ig, Cache &k) {
     while (ig <= p.Nt && p.tg[ig - 1] <= h.tn) { c.snap(SP_VBHOLE, h, ig); ++ig; }
     if (ig > p.Nt) return ST_DONE;
     if (COLD) {
+        event_begin(h);
         vbhole_event_t<EV_ELASTIC>(c, h, ig, k, rn(p, h));
         return (h.Ehkin < p.h_cold) ? ST_CONT : ST_MOVE;
     }
+    event_begin(h);
     vbhole_event_t<EV_ANY>(c, h, ig, k, rn(p, h));
     return (h.Ehkin < p.h_cold && h.tn < p.Tim) ? ST_MOVE : ST_CONT;
 }
