@@ -34,7 +34,9 @@ __constant__ DevP c_p;
 #define Q_VB_COLD (N_SPECIES + 1)
 #define Q_ION (N_SPECIES + 2)         // impact ionisations of the current generation (IonEvent records, see k_ion_emit)
 #define Q_SNAP (N_SPECIES + 3)        // snapshot records of the whole batch (see k_snapshot)
-#define N_QUEUES (N_SPECIES + 4)
+#define N_ECLASS 4                    // energy classes of the hot electrons (class 0 lives in queue SP_ELECTRON)
+#define Q_ELC (N_SPECIES + 4)         // classes 1..N_ECLASS-1: Q_ELC + (class - 1)
+#define N_QUEUES (N_SPECIES + 4 + N_ECLASS - 1)
 struct QueueSet { Queue q[N_QUEUES]; };
 #define N_CLASSES (N_SPECIES + 4)     // timing classes: hot waves per species, k_shi, finalize, cold electrons, cold holes
 
@@ -56,13 +58,21 @@ struct DevCtx {
     double *s_tally;        // block-private tallies (nullptr: straight to global)
     unsigned int *s_cnt;
 
+    // hot electrons are queued by energy class (DevP::e_class); a queue set without class queues takes them all in class 0
+    __device__ int hot_queue(int sp, const Rec &r) const {
+        if (sp != SP_ELECTRON) return sp;
+        const int c = (r.E >= p.e_class[0]) + (r.E >= p.e_class[1]) + (r.E >= p.e_class[2]);
+        if (c == 0 || out.q[Q_ELC + c - 1].cap == 0u) return SP_ELECTRON;
+        return Q_ELC + c - 1;
+    }
     __device__ void push(int sp, const Rec &r) {
-        int qi = sp;
-        if (sp == SP_ELECTRON) { if (electron_is_cold(p, r)) qi = Q_EL_COLD; }
-        else if (sp == SP_VBHOLE) { if (vbhole_is_cold(p, r)) qi = Q_VB_COLD; }
+        int qi;
+        if (sp == SP_ELECTRON && electron_is_cold(p, r)) qi = Q_EL_COLD;
+        else if (sp == SP_VBHOLE && vbhole_is_cold(p, r)) qi = Q_VB_COLD;
+        else qi = hot_queue(sp, r);
         push_q(qi, r);
     }
-    __device__ void push_hot(int sp, const Rec &r) { push_q(sp, r); }
+    __device__ void push_hot(int sp, const Rec &r) { push_q(hot_queue(sp, r), r); }
     // A snapshot is ~450 instructions that only a few lanes of a warp need in any given round, and the kernels are bound by
     // instruction fetch: the lanes just append the particle's state (what snapshot_* reads: 9 numbers) to a queue, and
     // k_snapshot turns the records into tallies with full warps.  `defer` = 0: tally right here (k_snapshot itself).
@@ -239,7 +249,7 @@ __global__ void __launch_bounds__(256) k_snapshot(Queue sq, QueueSet qout, int u
 // k_wave<SP, COLD>: records [first, n_in) of queue qin, histories followed with lane refill until they end or
 // have to change queue (hot -> cold when the particle can no longer ionise, core hole -> valence hole, ...).
 template <int SP, bool COLD>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int lockstep) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int lockstep, int budget) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
@@ -250,17 +260,23 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
     Rec r;
     Cache k{};
     int ig = 0, nev = 0;
+    // `budget` > 0: a warp claims at most that many records and then lets its block end, so that the grid is a stream of
+    // short-lived blocks (the launch sizes the grid to cover the queue).  Cold kernels that run beside the hot cascade are
+    // launched this way: the blocks of the next hot generation (higher stream priority) find room within one block lifetime.
+    int left = budget > 0 ? budget : 0x7fffffff;
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
         if (idle && !exhausted && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
-            const int nidle = __popc(idle);
+            const int nidle = min(__popc(idle), left);
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(head, (uint32_t)nidle);
             base = __shfl_sync(0xffffffffu, base, 0) + first;
-            if (base + (uint32_t)nidle >= n_in) exhausted = true;
+            left -= nidle;
+            if (base + (uint32_t)nidle >= n_in || left <= 0) exhausted = true;
             if (!active) {
-                const uint32_t my = base + __popc(idle & ((1u << lane) - 1u));
-                if (my < n_in) {
+                const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+                const uint32_t my = base + rank;
+                if (rank < (uint32_t)nidle && my < n_in) {
                     load_rec(qin, my, r);
                     active = true; nev = 0;
                     if (SP == SP_ELECTRON) begin_electron(c_p, r, ig, k);
@@ -304,8 +320,24 @@ template <int SP, int MODE> __device__ inline void hot_event(DevCtx &c, Rec &r, 
 }
 template <int SP> __device__ inline bool hot_leaves(const Rec &r) { return SP == SP_ELECTRON ? electron_leaves_hot(c_p, r) : vbhole_leaves_hot(c_p, r); }
 
+// The input of k_hot: the records of one generation by energy class (class 0 = all of them for the valence holes).
+// A history's remaining number of collisions grows with its energy and a warp advances at the pace of its slowest
+// lane: one collision of a lone history takes ~4 us, one round of a warp whose 32 lanes disagree on the channel and are
+// refilled all the time ~25 us (measured).  So the long histories get warps of their own: `quota[c]` = how
+// many histories of class c a warp follows at once, `wend` = the warps that start on class c (highest class first, i.e.
+// in the blocks that are scheduled first).  A warp whose class is used up goes on with the highest class that has
+// records left.
+struct HotIn {
+    Queue q[N_ECLASS];
+    uint32_t n[N_ECLASS];
+    uint32_t *head[N_ECLASS];
+    int quota[N_ECLASS];
+    uint32_t wend[N_ECLASS];       // warps [wend[c+1], wend[c]) start on class c (wend[ncls] = 0)
+    int ncls;
+};
+
 template <int SP>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(Queue qin, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int inel_min, int quota, int lockstep) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(HotIn in, QueueSet qout, int use_smem, int refill_min, int slice, int inel_min, int lockstep) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
@@ -317,22 +349,31 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(Queue qin, uint32_t n_
     Cache k{};
     double RN = 0.0;
     int ig = 0, nev = 0;
-    // `quota` = how many histories a warp follows at once.  32 while there is plenty of work; in the small generations
-    // of the cascade's tail the host spreads the records over all warps (down to one per warp): histories that share a
-    // warp serialise each other whenever they disagree on the collision channel, and the tail is the critical path.
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int cls = 0;
+    unsigned exh = 0u;              // classes whose queue is used up (warp-uniform)
+    for (int q = in.ncls - 1; q >= 0; --q) { if (in.n[q] == 0u) exh |= 1u << q; }
+    for (int q = in.ncls - 1; q > 0; --q) { if (gw < in.wend[q]) { cls = q; break; } }
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && ((exh >> cls) & 1u)) {
+            int q = in.ncls - 1;
+            while (q >= 0 && ((exh >> q) & 1u)) --q;
+            if (q < 0) exhausted = true; else cls = q;
+        }
+        const int quota = in.quota[cls];
         const int room = quota - (32 - __popc(idle));
         if (room > 0 && !exhausted && (room >= min(refill_min, quota) || idle == 0xffffffffu)) {
+            const uint32_t n_in = in.n[cls];
             uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(head, (uint32_t)room);
+            if (lane == 0) base = atomicAdd(in.head[cls], (uint32_t)room);
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + (uint32_t)room >= n_in) exhausted = true;
+            if (base + (uint32_t)room >= n_in) exh |= 1u << cls;
             if (!active) {
                 const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
                 const uint32_t my = base + rank;
                 if (rank < (uint32_t)room && my < n_in) {
-                    load_rec(qin, my, r);
+                    load_rec(in.q[cls], my, r);
                     active = true; nev = 0; have_rn = false;
                     if (SP == SP_ELECTRON) begin_electron(c_p, r, ig, k); else begin_vbhole(c_p, r, ig, k);
                 }
@@ -414,6 +455,11 @@ struct trk3_engine {
     int opt_batch = 1024, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
     int opt_hot_slice = 64, opt_inel_min = 1, opt_overlap = 0, opt_cold_min = 16384;
     int opt_shi_lanes = 1;
+    int opt_cold_budget = 0, opt_cold_smem_kb = 0, opt_hot_block = 0;      // see the `overlap` schedule in trk3_mc_run_device
+    // energy classes of the hot electrons: lower edges [eV] of classes 1..3 and the most histories a warp follows at once
+    int opt_hot_classes = N_ECLASS;
+    double opt_class_E[N_ECLASS - 1] = {200.0, 500.0, 1300.0};
+    int opt_class_quota[N_ECLASS] = {32, 8, 3, 1};
     int opt_spread = 1, opt_quota_min = 1, opt_lockstep = 0, opt_species_streams = 1, opt_defer_snap = 1;
 
     double opt_cap_factor = 2.0;
@@ -434,6 +480,8 @@ struct trk3_engine {
     uint64_t class_launches[N_CLASSES] = {0};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     std::vector<std::pair<int, int>> ev_pending;   // (class, pool index)
+    std::vector<std::pair<int, uint32_t>> ev_info; // (generation, records) of the same launches: option "profile" = 2 prints them
+    int cur_gen = -1;
     // results
     std::vector<double> iter_totE;
     std::vector<double> Dcoef;
@@ -450,13 +498,15 @@ struct trk3_engine {
 #define QC_ION (3 * N_SPECIES + 2)
 #define QC_SNAP (3 * N_SPECIES + 4)
 #define QC_HEAD (3 * N_SPECIES + 5)
-#define QC_TOTAL (4 * N_SPECIES + 7)
+#define QC_ELC(b) (4 * N_SPECIES + 7 + (b) * (N_ECLASS - 1))      // counts of the electron class queues 1.. of generation set b
+#define QC_HEADC (4 * N_SPECIES + 7 + 2 * (N_ECLASS - 1))          // their heads
+#define QC_TOTAL (4 * N_SPECIES + 7 + 3 * (N_ECLASS - 1))
 
 namespace {
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { eng->err = std::string(#call) + ": " + cudaGetErrorString(e_); return TRK3_E_CUDA; } } while (0)
 
 // optional per-kernel-class timing: events are recorded on the launching stream around every launch
-int prof_begin(trk3_engine *eng, int cls, cudaStream_t st = nullptr) {
+int prof_begin(trk3_engine *eng, int cls, cudaStream_t st = nullptr, uint32_t n = 0) {
     if (!st) st = eng->stream;
     if (!eng->opt_profile) return -1;
     size_t used = eng->ev_pending.size();
@@ -467,17 +517,23 @@ int prof_begin(trk3_engine *eng, int cls, cudaStream_t st = nullptr) {
     }
     cudaEventRecord(eng->ev_pool[used].first, st);
     eng->ev_pending.push_back({cls, (int)used});
+    eng->ev_info.push_back({eng->cur_gen, n});
     return (int)used;
 }
 void prof_end(trk3_engine *eng, int idx, cudaStream_t st = nullptr) { if (idx >= 0) cudaEventRecord(eng->ev_pool[idx].second, st ? st : eng->stream); }
 void prof_collect(trk3_engine *eng) {      // call after a stream synchronize
-    for (auto &pe : eng->ev_pending) {
+    for (size_t i = 0; i < eng->ev_pending.size(); ++i) {
+        const auto &pe = eng->ev_pending[i];
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, eng->ev_pool[pe.second].first, eng->ev_pool[pe.second].second) == cudaSuccess) {
             eng->class_ms[pe.first] += ms; eng->class_launches[pe.first]++;
+            if (eng->opt_profile >= 2) {
+                float t0 = 0.f; cudaEventElapsedTime(&t0, eng->ev0, eng->ev_pool[pe.second].first);
+                fprintf(stderr, "trace gen %3d class %d records %9u start %8.3f ms dur %8.3f ms\n", eng->ev_info[i].first, pe.first, eng->ev_info[i].second, t0, ms);
+            }
         }
     }
-    eng->ev_pending.clear();
+    eng->ev_pending.clear(); eng->ev_info.clear();
 }
 
 template <class T>
@@ -543,12 +599,15 @@ void queue_caps(const trk3_engine *eng, double cap[N_QUEUES]) {
     cap[Q_EL_COLD] = n; cap[Q_VB_COLD] = n;       // every carrier of an iteration ends up here once
     cap[Q_ION] = n;
     cap[Q_SNAP] = eng->opt_defer_snap ? 1.25 * n * (double)eng->lay.Nt : 1.0;     // every carrier at every grid time it lives to see
+    // the higher energy classes of the hot electrons hold a few per cent of them (the spectrum falls like 1/E^2)
+    for (int c = 1; c < N_ECLASS; ++c) cap[Q_ELC + c - 1] = (c < eng->opt_hot_classes) ? 0.25 * n + 64.0 : 0.0;
 }
 double queue_bytes_per_iteration(const trk3_engine *eng) {
     double cap[N_QUEUES]; queue_caps(eng, cap);
     double b = 0;
     for (int s = 0; s < N_SPECIES; ++s) b += 2.0 * cap[s] * (TRK_NCOL * 8 + 20);
-    for (int s = N_SPECIES; s < N_QUEUES; ++s) b += cap[s] * (TRK_NCOL * 8 + 20);
+    for (int s = N_SPECIES; s < Q_ELC; ++s) b += cap[s] * (TRK_NCOL * 8 + 20);
+    for (int s = Q_ELC; s < N_QUEUES; ++s) b += 2.0 * cap[s] * (TRK_NCOL * 8 + 20);
     for (int s = 0; s < N_SPECIES; ++s) b += cap[s] / 16.0 * (TRK_NCOL * 8 + 20);
     return b;
 }
@@ -557,7 +616,8 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
     if (nb <= eng->nb_alloc) return TRK3_OK;
     // release the previous batch resources
     for (int b = 0; b < 2; ++b) for (int s = 0; s < N_SPECIES; ++s) free_queue(eng, eng->qs[b].q[s]);
-    for (int s = N_SPECIES; s < N_QUEUES; ++s) { free_queue(eng, eng->qs[0].q[s]); eng->qs[1].q[s] = Queue{}; eng->qs_x.q[s] = Queue{}; }
+    for (int b = 0; b < 2; ++b) for (int s = Q_ELC; s < N_QUEUES; ++s) free_queue(eng, eng->qs[b].q[s]);
+    for (int s = N_SPECIES; s < Q_ELC; ++s) { free_queue(eng, eng->qs[0].q[s]); eng->qs[1].q[s] = Queue{}; eng->qs_x.q[s] = Queue{}; }
     for (int s = 0; s < N_SPECIES; ++s) free_queue(eng, eng->qs_x.q[s]);
     dev_free(eng, eng->d_u32); dev_free(eng, eng->d_f64);
     dev_free(eng, eng->fa.totnel); dev_free(eng, eng->fa.totE); dev_free(eng, eng->fa.latcum); dev_free(eng, eng->fa.emcnt); dev_free(eng, eng->fa.emE);
@@ -568,10 +628,17 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
         int rc = alloc_queue(eng, eng->qs[b].q[s], (uint32_t)(cap[s] * (double)nb), eng->d_qcount + QC_HOT(b) + s);
         if (rc) return rc;
     }
-    for (int s = N_SPECIES; s < N_QUEUES; ++s) {      // the cold queues and the ionisation queue are shared by both generations
+    for (int s = N_SPECIES; s < Q_ELC; ++s) {      // the cold queues and the ionisation queue are shared by both generations
         int rc = alloc_queue(eng, eng->qs[0].q[s], (uint32_t)(cap[s] * (double)nb), eng->d_qcount + (s == Q_ION ? QC_ION : (s == Q_SNAP ? QC_SNAP : QC_COLD + (s - N_SPECIES))));
         if (rc) return rc;
         eng->qs[1].q[s] = eng->qs[0].q[s]; eng->qs_x.q[s] = eng->qs[0].q[s];
+    }
+    for (int b = 0; b < 2; ++b) for (int c = 1; c < N_ECLASS; ++c) {       // energy classes of the hot electrons (set X has none: cap 0)
+        Queue &q = eng->qs[b].q[Q_ELC + c - 1];
+        q = Queue{};
+        if (cap[Q_ELC + c - 1] <= 0.0) continue;
+        int rc = alloc_queue(eng, q, (uint32_t)(cap[Q_ELC + c - 1] * (double)nb), eng->d_qcount + QC_ELC(b) + (c - 1));
+        if (rc) return rc;
     }
     for (int s = 0; s < N_SPECIES; ++s) {             // handed back by the cold kernels: a rarity
         int rc = alloc_queue(eng, eng->qs_x.q[s], (uint32_t)(cap[s] * (double)nb / 16.0) + 4096u, eng->d_qcount + QC_X + s);
@@ -593,13 +660,14 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
 }
 
 template <int SP, bool COLD>
-int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_in, uint32_t *head, const QueueSet &qout, cudaStream_t st = nullptr) {
+int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_in, uint32_t *head, const QueueSet &qout, cudaStream_t st = nullptr, int budget = 0, size_t smem_floor = 0) {
     const uint32_t n = n_in - first;
     if (!st) st = eng->stream;
     size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
     int use_smem = eng->opt_use_smem;
     const size_t smem_max = (size_t)eng->smem_optin - 1024;             // static shared memory + driver reserve
     if (smem > smem_max) { smem = 8; use_smem = 0; }                    // too many output times for shared memory: global atomics
+    if (smem < smem_floor && smem_floor <= smem_max) smem = smem_floor; // occupancy limiter: leaves room on every SM for the blocks of another kernel
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_wave<SP, COLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = eng->opt_blocks_per_sm;
     const int block = eng->opt_block;
@@ -607,16 +675,18 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_i
     // persistent-style grid: a multiple of the SM count, never more blocks than there is work for
     uint32_t want = (n + block - 1) / block;
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
+    if (budget > 0) { const uint32_t per_block = (uint32_t)budget * (uint32_t)(block / 32); grid = (n + per_block - 1) / per_block; }
     if (grid < 1) grid = 1;
-    const int pi = prof_begin(eng, COLD ? N_SPECIES + 2 + SP : SP, st);
-    k_wave<SP, COLD><<<grid, block, smem, st>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice, eng->opt_lockstep);
+    const int pi = prof_begin(eng, COLD ? N_SPECIES + 2 + SP : SP, st, n);
+    k_wave<SP, COLD><<<grid, block, smem, st>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice, eng->opt_lockstep, budget);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
     return TRK3_OK;
 }
+// One generation of hot carriers of species SP: `nq` class queues (valence holes: 1), see HotIn.
 template <int SP>
-int launch_hot(trk3_engine *eng, const Queue &qin, uint32_t n, uint32_t *head, const QueueSet &qout, cudaStream_t st = nullptr) {
+int launch_hot(trk3_engine *eng, const Queue *const *qin, const uint32_t *n_in, uint32_t *const *head, int ncls, const QueueSet &qout, cudaStream_t st = nullptr) {
     if (!st) st = eng->stream;
     size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
     int use_smem = eng->opt_use_smem;
@@ -624,22 +694,63 @@ int launch_hot(trk3_engine *eng, const Queue &qin, uint32_t n, uint32_t *head, c
     if (smem > smem_max) { smem = 8; use_smem = 0; }
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_hot<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = eng->opt_blocks_per_sm;
-    const int block = eng->opt_block;
+    const int block = eng->opt_hot_block ? eng->opt_hot_block : eng->opt_block;
     if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_hot<SP>, block, smem)); if (bps < 1) bps = 1; }
-    // records per warp: spread a small generation over all the warps the GPU can hold (see k_hot)
-    const uint32_t wpb = (uint32_t)block / 32u, max_warps = (uint32_t)(eng->n_sm * bps) * wpb;
-    uint32_t quota = eng->opt_spread ? (n + max_warps - 1) / max_warps : 32u;
-    if (quota > 32u) quota = 32u;
-    if (quota < (uint32_t)eng->opt_quota_min) quota = (uint32_t)eng->opt_quota_min;
-    uint32_t want = (n + quota * wpb - 1) / (quota * wpb);
-    uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
+    const uint32_t wpb = (uint32_t)block / 32u, W = (uint32_t)(eng->n_sm * bps) * wpb;       // warps the GPU holds at once
+    HotIn in{};
+    in.ncls = ncls;
+    // warps per class.  Least: n / (the class's largest quota).  If that fills the GPU, the warps are shared out in
+    // proportion (quota = largest).  Otherwise the spare warps go to the classes from the top down, until every history of
+    // a class has a warp of its own: a small generation spreads over all warps, the long histories first.
+    uint32_t need[N_ECLASS] = {0}, w[N_ECLASS] = {0}, total_need = 0, n_tot = 0;
+    for (int c = 0; c < ncls; ++c) {
+        in.q[c] = *qin[c]; in.n[c] = n_in[c]; in.head[c] = head[c];
+        const uint32_t qmax = (uint32_t)(ncls > 1 ? eng->opt_class_quota[c] : 32);
+        need[c] = (n_in[c] + qmax - 1) / qmax; total_need += need[c]; n_tot += n_in[c];
+        in.quota[c] = (int)qmax;
+    }
+    if (total_need >= W || !eng->opt_spread) {
+        for (int c = 0; c < ncls; ++c) w[c] = need[c] ? std::max<uint32_t>(1u, (uint32_t)((uint64_t)need[c] * W / std::max(total_need, 1u))) : 0u;
+        if (total_need < W) for (int c = 0; c < ncls; ++c) w[c] = need[c];
+    } else {
+        uint32_t spare = W - total_need;
+        for (int c = ncls - 1; c >= 0; --c) {
+            const uint32_t extra = std::min(spare, n_in[c] - need[c]);
+            w[c] = need[c] + extra; spare -= extra;
+            if (w[c]) in.quota[c] = (int)std::max<uint32_t>((n_in[c] + w[c] - 1) / w[c], (uint32_t)eng->opt_quota_min);
+        }
+    }
+    uint32_t wsum = 0;
+    for (int c = ncls - 1; c >= 0; --c) { wsum += w[c]; in.wend[c] = wsum; }
+    uint32_t grid = std::min<uint32_t>((wsum + wpb - 1) / wpb, (uint32_t)(eng->n_sm * bps));
     if (grid < 1) grid = 1;
-    const int pi = prof_begin(eng, SP, st);
-    k_hot<SP><<<grid, block, smem, st>>>(qin, n, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice, eng->opt_inel_min, (int)quota, eng->opt_lockstep);
+    if (eng->opt_profile >= 2) {
+        fprintf(stderr, "hot<%d> gen %d grid %u W %u:", SP, eng->cur_gen, grid, W);
+        for (int c = 0; c < ncls; ++c) fprintf(stderr, "  c%d n %u w %u q %d", c, in.n[c], w[c], in.quota[c]);
+        fprintf(stderr, "\n");
+    }
+    const int pi = prof_begin(eng, SP, st, n_tot);
+    k_hot<SP><<<grid, block, smem, st>>>(in, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice, eng->opt_inel_min, eng->opt_lockstep);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
     return TRK3_OK;
+}
+// the hot electrons of generation set `b`: all energy classes in one launch
+int launch_hot_electrons(trk3_engine *eng, const QueueSet &qs, const uint32_t *cnt, const uint32_t *cnt_cls, const QueueSet &qout) {
+    const Queue *q[N_ECLASS]; uint32_t n[N_ECLASS]; uint32_t *head[N_ECLASS];
+    uint32_t *heads = eng->d_qcount + QC_HEAD, *headc = eng->d_qcount + QC_HEADC;
+    q[0] = &qs.q[SP_ELECTRON]; n[0] = cnt[SP_ELECTRON]; head[0] = heads + SP_ELECTRON;
+    int ncls = 1;
+    for (int c = 1; c < N_ECLASS; ++c) {
+        q[c] = &qs.q[Q_ELC + c - 1]; n[c] = cnt_cls ? cnt_cls[c - 1] : 0u; head[c] = headc + (c - 1);
+        if (q[c]->cap) ncls = c + 1; else n[c] = 0u;
+    }
+    return launch_hot<SP_ELECTRON>(eng, q, n, head, ncls, qout);
+}
+int launch_hot_vbholes(trk3_engine *eng, const Queue &qin, uint32_t n_in, const QueueSet &qout, cudaStream_t st = nullptr) {
+    const Queue *q[1] = {&qin}; uint32_t n[1] = {n_in}; uint32_t *head[1] = {eng->d_qcount + QC_HEAD + SP_VBHOLE};
+    return launch_hot<SP_VBHOLE>(eng, q, n, head, 1, qout, st);
 }
 // Flattened tables -> device (first call allocates, later calls re-use the arrays): the inputs of do_Monte_Carlo.
 int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab) {
@@ -782,9 +893,20 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "quota_min") eng->opt_quota_min = std::min(32, std::max(1, (int)v));
     else if (k == "overlap") eng->opt_overlap = (v != 0.0);
     else if (k == "cold_min") eng->opt_cold_min = std::max(1, (int)v);
+    else if (k == "hot_classes") { eng->opt_hot_classes = std::min(N_ECLASS, std::max(1, (int)v)); eng->nb_alloc = 0; }
+    else if (k == "class_E1") eng->opt_class_E[0] = v;
+    else if (k == "class_E2") eng->opt_class_E[1] = v;
+    else if (k == "class_E3") eng->opt_class_E[2] = v;
+    else if (k == "class_q0") eng->opt_class_quota[0] = std::min(32, std::max(1, (int)v));
+    else if (k == "class_q1") eng->opt_class_quota[1] = std::min(32, std::max(1, (int)v));
+    else if (k == "class_q2") eng->opt_class_quota[2] = std::min(32, std::max(1, (int)v));
+    else if (k == "class_q3") eng->opt_class_quota[3] = std::min(32, std::max(1, (int)v));
+    else if (k == "cold_budget") eng->opt_cold_budget = std::max(0, (int)v);
+    else if (k == "cold_smem_kb") eng->opt_cold_smem_kb = std::max(0, (int)v);
+    else if (k == "hot_block") eng->opt_hot_block = std::min(TRK_BLOCK_MAX, std::max(0, ((int)v / 32) * 32));
     else if (k == "inel_min") eng->opt_inel_min = std::min(32, std::max(1, (int)v));
     else if (k == "max_generations") eng->opt_max_generations = std::max(1, (int)v);
-    else if (k == "profile") { eng->opt_profile = (v != 0.0); for (auto &x : eng->class_ms) x = 0; for (auto &x : eng->class_launches) x = 0; }
+    else if (k == "profile") { eng->opt_profile = (int)v; for (auto &x : eng->class_ms) x = 0; for (auto &x : eng->class_launches) x = 0; }
     else return TRK3_E_INVALID;
     return TRK3_OK;
 }
@@ -837,6 +959,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         CK(cudaMemcpyAsync(eng->d_counters_bak, eng->d_counters, n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, eng->stream));
         eng->hp.batch_begin = (uint32_t)b0; eng->hp.batch_n = nb;
         eng->hp.defer_snap = eng->opt_defer_snap;
+        for (int c = 1; c < N_ECLASS; ++c) eng->hp.e_class[c - 1] = (c < eng->opt_hot_classes) ? eng->opt_class_E[c - 1] : 1.0e300;
 
         CK(cudaMemcpyToSymbolAsync(c_p, &eng->hp, sizeof(DevP), 0, cudaMemcpyHostToDevice, eng->stream));
         CK(cudaMemsetAsync(eng->d_u32, 0, eng->sl.u32_total * sizeof(uint32_t), eng->stream));
@@ -857,13 +980,16 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         cudaStream_t sc = eng->opt_overlap ? eng->stream_c : eng->stream;       // stream of the cold kernels
         if (eng->opt_overlap) { CK(cudaEventRecord(eng->ev_fork, eng->stream)); CK(cudaStreamWaitEvent(sc, eng->ev_fork, 0)); }
         for (int gen = 0; gen < eng->opt_max_generations; ++gen) {
-            uint32_t h_cnt[QC_HEAD];           // hot counts of both generations, cold counts, set X, ionisation queue
+            eng->cur_gen = gen;
+            uint32_t h_cnt[QC_TOTAL];          // hot counts of both generations, cold counts, set X, ionisation queue, ..., class queues
             CK(cudaMemcpyAsync(h_cnt, eng->d_qcount, sizeof h_cnt, cudaMemcpyDeviceToHost, eng->stream));
             CK(cudaStreamSynchronize(eng->stream));
-            uint32_t *hot = h_cnt + QC_HOT(cur), *cold = h_cnt + QC_COLD;
+            uint32_t *hot = h_cnt + QC_HOT(cur), *cold = h_cnt + QC_COLD, *hotc = h_cnt + QC_ELC(cur);
             uint64_t total = 0;
             if (gen == 0 && h_cnt[QC_HOT(1) + SP_ELECTRON] > eng->qs[1].q[SP_ELECTRON].cap) overflow = true;     // staged ion collisions
             for (int s = 0; s < N_SPECIES; ++s) { if (hot[s] > eng->qs[cur].q[s].cap) { overflow = true; hot[s] = eng->qs[cur].q[s].cap; } total += hot[s]; }
+            uint32_t n_hot_el = hot[SP_ELECTRON];
+            for (int c = 1; c < N_ECLASS; ++c) { const uint32_t cp = eng->qs[cur].q[Q_ELC + c - 1].cap; if (hotc[c - 1] > cp) { overflow = true; hotc[c - 1] = cp; } total += hotc[c - 1]; n_hot_el += hotc[c - 1]; }
             for (int s = 0; s < 2; ++s) if (cold[s] > eng->qs[0].q[N_SPECIES + s].cap) { overflow = true; cold[s] = eng->qs[0].q[N_SPECIES + s].cap; }
             if (h_cnt[QC_ION + 1] > eng->qs[0].q[Q_ION].cap) overflow = true;
             if (h_cnt[QC_SNAP] > eng->qs[0].q[Q_SNAP].cap) overflow = true;
@@ -873,14 +999,16 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             const int nxt = cur ^ 1;
             if (total) {        // one generation of the hot cascade (time-sliced, see k_hot)
                 CK(cudaMemsetAsync(eng->d_qcount + QC_HOT(nxt), 0, N_SPECIES * sizeof(uint32_t), eng->stream));
+                CK(cudaMemsetAsync(eng->d_qcount + QC_ELC(nxt), 0, (N_ECLASS - 1) * sizeof(uint32_t), eng->stream));
+                CK(cudaMemsetAsync(eng->d_qcount + QC_HEADC, 0, (N_ECLASS - 1) * sizeof(uint32_t), eng->stream));
                 CK(cudaMemsetAsync(heads, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
                 // the species of a generation are independent of each other: the (few) valence holes, core holes and photons run
                 // on their own streams beside the electrons instead of lengthening the generation one after the other
                 const bool par = eng->opt_species_streams != 0;
                 cudaStream_t s1 = par ? eng->stream_sp[0] : eng->stream, s2 = par ? eng->stream_sp[1] : eng->stream, s3 = par ? eng->stream_sp[2] : eng->stream;
                 if (par) { CK(cudaEventRecord(eng->ev_gen, eng->stream)); }
-                if (hot[SP_ELECTRON]) { rc = launch_hot<SP_ELECTRON>(eng, eng->qs[cur].q[SP_ELECTRON], hot[SP_ELECTRON], heads + SP_ELECTRON, eng->qs[nxt]); if (rc) return rc; }
-                if (hot[SP_VBHOLE]) { if (par) CK(cudaStreamWaitEvent(s1, eng->ev_gen, 0)); rc = launch_hot<SP_VBHOLE>(eng, eng->qs[cur].q[SP_VBHOLE], hot[SP_VBHOLE], heads + SP_VBHOLE, eng->qs[nxt], s1); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[0], s1)); }
+                if (n_hot_el) { rc = launch_hot_electrons(eng, eng->qs[cur], hot, hotc, eng->qs[nxt]); if (rc) return rc; }
+                if (hot[SP_VBHOLE]) { if (par) CK(cudaStreamWaitEvent(s1, eng->ev_gen, 0)); rc = launch_hot_vbholes(eng, eng->qs[cur].q[SP_VBHOLE], hot[SP_VBHOLE], eng->qs[nxt], s1); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[0], s1)); }
                 if (hot[SP_COREHOLE]) { if (par) CK(cudaStreamWaitEvent(s2, eng->ev_gen, 0)); rc = launch_wave<SP_COREHOLE, false>(eng, eng->qs[cur].q[SP_COREHOLE], 0, hot[SP_COREHOLE], heads + SP_COREHOLE, eng->qs[nxt], s2); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[1], s2)); }
                 if (hot[SP_PHOTON]) { if (par) CK(cudaStreamWaitEvent(s3, eng->ev_gen, 0)); rc = launch_wave<SP_PHOTON, false>(eng, eng->qs[cur].q[SP_PHOTON], 0, hot[SP_PHOTON], heads + SP_PHOTON, eng->qs[nxt], s3); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[2], s3)); }
                 if (par) {
@@ -888,7 +1016,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
                     if (hot[SP_COREHOLE]) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[1], 0));
                     if (hot[SP_PHOTON]) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[2], 0));
                 }
-                if (hot[SP_ELECTRON]) {     // the pairs of this generation's impact ionisations join the next generation
+                if (n_hot_el) {             // the pairs of this generation's impact ionisations join the next generation
                     const int pi = prof_begin(eng, SP_ELECTRON);
                     k_ion_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(eng->qs[0].q[Q_ION], eng->qs[nxt]);
                     k_ion_reset<<<1, 32, 0, eng->stream>>>(eng->d_qcount + QC_ION);
@@ -902,8 +1030,11 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             // (the records [cold_done, cold) were written by kernels that have completed: the stream was just synchronised)
             if (cold_pending && (!total || (eng->opt_overlap && cold_pending >= (uint64_t)eng->opt_cold_min))) {
                 CK(cudaMemsetAsync(heads + N_SPECIES, 0, 2 * sizeof(uint32_t), sc));
-                if (cold[0] > cold_done[0]) { rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[0].q[Q_EL_COLD], cold_done[0], cold[0], heads + Q_EL_COLD, eng->qs_x, sc); if (rc) return rc; }
-                if (cold[1] > cold_done[1]) { rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[0].q[Q_VB_COLD], cold_done[1], cold[1], heads + Q_VB_COLD, eng->qs_x, sc); if (rc) return rc; }
+                // beside a running hot cascade: short-lived blocks (and optionally fewer of them per SM), see k_wave `budget`
+                const int bud = (eng->opt_overlap && total) ? eng->opt_cold_budget : 0;
+                const size_t sfl = (eng->opt_overlap && total) ? (size_t)eng->opt_cold_smem_kb * 1024 : 0;
+                if (cold[0] > cold_done[0]) { rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[0].q[Q_EL_COLD], cold_done[0], cold[0], heads + Q_EL_COLD, eng->qs_x, sc, bud, sfl); if (rc) return rc; }
+                if (cold[1] > cold_done[1]) { rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[0].q[Q_VB_COLD], cold_done[1], cold[1], heads + Q_VB_COLD, eng->qs_x, sc, bud, sfl); if (rc) return rc; }
                 cold_done[0] = cold[0]; cold_done[1] = cold[1];
             }
             if (total) continue;
@@ -916,9 +1047,11 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             if (overflow) break;
             if (!nx) break;                                        // cold kernels create no cold records: everything is done
             CK(cudaMemsetAsync(eng->d_qcount + QC_HOT(nxt), 0, N_SPECIES * sizeof(uint32_t), eng->stream));
+            CK(cudaMemsetAsync(eng->d_qcount + QC_ELC(nxt), 0, (N_ECLASS - 1) * sizeof(uint32_t), eng->stream));
+            CK(cudaMemsetAsync(eng->d_qcount + QC_HEADC, 0, (N_ECLASS - 1) * sizeof(uint32_t), eng->stream));
             CK(cudaMemsetAsync(heads, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
-            if (h_x[SP_ELECTRON]) { rc = launch_hot<SP_ELECTRON>(eng, eng->qs_x.q[SP_ELECTRON], h_x[SP_ELECTRON], heads + SP_ELECTRON, eng->qs[nxt]); if (rc) return rc; }
-            if (h_x[SP_VBHOLE]) { rc = launch_hot<SP_VBHOLE>(eng, eng->qs_x.q[SP_VBHOLE], h_x[SP_VBHOLE], heads + SP_VBHOLE, eng->qs[nxt]); if (rc) return rc; }
+            if (h_x[SP_ELECTRON]) { rc = launch_hot_electrons(eng, eng->qs_x, h_x, nullptr, eng->qs[nxt]); if (rc) return rc; }
+            if (h_x[SP_VBHOLE]) { rc = launch_hot_vbholes(eng, eng->qs_x.q[SP_VBHOLE], h_x[SP_VBHOLE], eng->qs[nxt]); if (rc) return rc; }
             if (h_x[SP_ELECTRON]) {
                 k_ion_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(eng->qs[0].q[Q_ION], eng->qs[nxt]);
                 k_ion_reset<<<1, 32, 0, eng->stream>>>(eng->d_qcount + QC_ION);
