@@ -14,6 +14,6 @@ case = tk.Case.load(tk.make_run_dir(f"/tmp/run_{cfg}", cfg))
 case.build_tables(shi_window_only=True, cache_dir=os.path.join(ROOT, ".table_cache"))
 eng = tk.Engine(case, **opts)
 eng.run_device(0, nit); eng.run_device(0, nit)
-eng.set_option("profile", 2)
+eng.set_option("profile", float(os.environ.get("TRK_PROFILE", "2")))
 st = eng.run_device(0, nit)
 print("device_ms", st["device_ms"], "events", st["events"] if "events" in st else st["total_events"])

@@ -87,6 +87,7 @@ extern "C" int trk3_emul_run(const trk3_config *cfg, const trk3_tables *tab, int
     }
     for (int sh = 0; sh < T.n_shells; ++sh) shi_threshold(T.dshi_E + T.dshi_off[sh], T.dshi_L + T.dshi_off[sh], (int)(T.dshi_off[sh + 1] - T.dshi_off[sh]), T.shell_Ip[sh], p.shi_Mtemp[sh], p.shi_dL[sh]);
     cold_range(p.ei_E, p.ei_tot, p.n_ei, p.e_cold, p.e_imfp_cold);
+    p.e_warm = p.e_cold; p.e_class[0] = p.e_class[1] = p.e_class[2] = 1.0e300;      // scheduling classes of the CUDA engine: not used here
     cold_range(p.hi_E, p.hi_tot, p.n_hi, p.h_cold, p.h_imfp_cold);
     p.tally = tallies;
     unsigned long long ev[TRK3_N_EVENT_CLASSES] = {0}, er[TRK3_N_ERRORS] = {0}, nel = 0, nph = 0;

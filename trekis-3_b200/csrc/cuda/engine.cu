@@ -36,13 +36,17 @@ __constant__ DevP c_p;
 #define Q_SNAP (N_SPECIES + 3)        // snapshot records of the whole batch (see k_snapshot)
 #define N_ECLASS 4                    // energy classes of the hot electrons (class 0 lives in queue SP_ELECTRON)
 #define Q_ELC (N_SPECIES + 4)         // classes 1..N_ECLASS-1: Q_ELC + (class - 1)
-#define N_QUEUES (N_SPECIES + 4 + N_ECLASS - 1)
+#define Q_ELW (N_SPECIES + 4 + N_ECLASS - 1)      // warm electrons of the next generation (see DevP::e_warm)
+#define N_QUEUES (N_SPECIES + 5 + N_ECLASS - 1)
 struct QueueSet { Queue q[N_QUEUES]; };
-#define N_CLASSES (N_SPECIES + 4)     // timing classes: hot waves per species, k_shi, finalize, cold electrons, cold holes
+#define N_CLASSES (N_SPECIES + 4)     // timing classes: hot waves per species, k_shi, finalize, cold electrons (+ warm: same kernel), cold holes
 
 #define TRK_BLOCK_MAX 256          // compile-time upper bound of the wave-kernel block size (launch bounds)
 #ifndef TRK_MIN_BLOCKS
 #define TRK_MIN_BLOCKS 3
+#endif
+#ifndef TRK_HOT_MIN_BLOCKS
+#define TRK_HOT_MIN_BLOCKS 2
 #endif
 #define S_EV 0                      // s_cnt layout: events[TRK3_N_EVENT_CLASSES], n_el, n_ph
 #define S_NEL TRK3_N_EVENT_CLASSES
@@ -59,15 +63,18 @@ struct DevCtx {
     unsigned int *s_cnt;
 
     // hot electrons are queued by energy class (DevP::e_class); a queue set without class queues takes them all in class 0
+    // An electron that used up the time slice of its class without turning cold has proved to be a long history: it is
+    // promoted (the tag travels in the otherwise unused `shell` of an electron record: -1 - class).
     __device__ int hot_queue(int sp, const Rec &r) const {
         if (sp != SP_ELECTRON) return sp;
-        const int c = (r.E >= p.e_class[0]) + (r.E >= p.e_class[1]) + (r.E >= p.e_class[2]);
+        const int c = max((r.E >= p.e_class[0]) + (r.E >= p.e_class[1]) + (r.E >= p.e_class[2]), min(-1 - r.shell, N_ECLASS - 1));
         if (c == 0 || out.q[Q_ELC + c - 1].cap == 0u) return SP_ELECTRON;
         return Q_ELC + c - 1;
     }
     __device__ void push(int sp, const Rec &r) {
         int qi;
         if (sp == SP_ELECTRON && electron_is_cold(p, r)) qi = Q_EL_COLD;
+        else if (sp == SP_ELECTRON && r.E < p.e_warm && out.q[Q_ELW].cap != 0u) qi = Q_ELW;
         else if (sp == SP_VBHOLE && vbhole_is_cold(p, r)) qi = Q_VB_COLD;
         else qi = hot_queue(sp, r);
         push_q(qi, r);
@@ -172,11 +179,108 @@ __device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned i
 // different ions never serialise each other through divergence.  Only the ion's own part of a collision runs here; the
 // collision is written to a staging queue and its electron-hole pair is created by k_shi_emit, one thread per collision.
 #define SHI_WARPS 4
+// An ion track is one serial chain of a few hundred collisions, so k_shi is bound by the latency of ONE collision.  A warp
+// follows one ion and its 32 lanes share the work of a collision instead of 31 of them idling:
+//   * lane j keeps Philox block (base + j) of the ion's stream: one evaluation serves ~10 collisions;
+//   * the mean free paths of all shells and the total one (which_shell + Next_free_path_2d: one log-log interpolation each)
+//     are evaluated by lanes 0..n_shells in one pass; log(E) and log(RN) share one call of the logarithm.
+// Every value is computed by the same expressions as in shi_step (physics.cuh): the result is bit-identical.
+struct PhiloxWarp {
+    uint32_t o0, o1, o2, o3, base;
+    bool valid;
+    __device__ double draw(const DevP &p, uint32_t iter, uint32_t k) {       // draw k of the ion's stream (id 0), see rn()
+        const uint32_t blk = k >> 1;
+        if (!valid || blk - base >= 32u) {
+            base = blk; valid = true;
+            philox4x32_10(0u, 0u, base + (threadIdx.x & 31), iter, p.seed_lo, p.seed_hi, o0, o1, o2, o3);
+        }
+        const int src = (int)(blk - base);
+        const uint32_t a = __shfl_sync(0xffffffffu, (k & 1u) ? o2 : o0, src), b = __shfl_sync(0xffffffffu, (k & 1u) ? o3 : o1, src);
+        const uint64_t bits = (uint64_t)a | ((uint64_t)b << 32);
+        return (double)((bits >> 11) + 1) * (1.0 / 9007199254740992.0);
+    }
+};
+// one collision of the ion (shi_step), all lanes hold the same `s`
+__device__ inline void shi_step_warp(DevCtx &c, Rec &s, ShiEvent &ev, PhiloxWarp &pw) {
+    const DevP &p = c.p;
+    const int lane = threadIdx.x & 31, NS = p.n_shells;
+    const double MSHI = p.ion_mass * TRK_MP;
+    if (lane == 0) c.event(TRK3_EV_SHI);
+    event_begin(s);
+    const uint32_t c0 = s.ctr;
+    const double RN1 = pw.draw(p, s.iter, c0), RN2 = pw.draw(p, s.iter, c0 + 1u), RN3 = pw.draw(p, s.iter, c0 + 2u);
+    s.ctr = c0 + 3u;
+    // log(E) [lane 0] and log(RN3) [lane 1] in one call
+    const double lg = m_log(lane == 1 ? RN3 : s.E);
+    const double lEs = __shfl_sync(0xffffffffu, lg, 0), lRN3 = __shfl_sync(0xffffffffu, lg, 1);
+    // lanes 0..NS-1: MFP of shell `lane` (Which_shell :1786-1832); lane NS: total MFP (Next_free_path_2d)
+    const Tab m = tab_shi_L(p), tt = tab_shi_tot(p);
+    const int n = tab_find(m, s.E, lEs);
+    double val = 1.0e20;
+    bool need = false;
+    double E1 = 1.0, E2 = 2.0, S1 = 1.0, S2 = 1.0, lE1 = 0.0, lE2 = 1.0, lS1 = 0.0, lS2 = 0.0;
+    if (lane < NS) {
+        if (n > 1) {
+            const double *La = m.L + (size_t)lane * m.N;
+            const double a = La[n - 2], b = La[n - 1];
+            if (a == b || a > 1e20) val = a;
+            else { const double *lLa = m.lL + (size_t)lane * m.N; need = true; E1 = m.E[n - 2]; E2 = m.E[n - 1]; S1 = a; S2 = b; lE1 = m.lE[n - 2]; lE2 = m.lE[n - 1]; lS1 = lLa[n - 2]; lS2 = lLa[n - 1]; }
+        }
+    } else if (lane == NS) {
+        const int n2 = find_2d_from_1d(tt.E, tt.N, s.E, n);
+        if (n2 == 1) val = nfp_at(tt, n2, true, s.E, lEs);
+        else {
+            const double Ll = tt.L[n2 - 2];
+            if (Ll >= 1.0e16) val = Ll;
+            else { need = true; E1 = tt.E[n2 - 2]; E2 = tt.E[n2 - 1]; S1 = Ll; S2 = tt.L[n2 - 1]; lE1 = tt.lE[n2 - 2]; lE2 = tt.lE[n2 - 1]; lS1 = tt.lL[n2 - 2]; lS2 = tt.lL[n2 - 1]; }
+        }
+    }
+    if (need) val = interp5t(E1, E2, S1, S2, lE1, lE2, lS1, lS2, s.E, lEs);
+    const double inv = 1.0 / val;
+    double MFP_tot = 0.0;
+    for (int q = 0; q < NS; ++q) MFP_tot = MFP_tot + __shfl_sync(0xffffffffu, inv, q);
+    MFP_tot = RN1 * MFP_tot;
+    double MFP_sum = 0.0;
+    int shell = NS - 1;
+    for (int q = 0; q < NS; ++q) { MFP_sum = MFP_sum + __shfl_sync(0xffffffffu, inv, q); if (MFP_sum >= MFP_tot) { shell = q; break; } }
+    const double lam = __shfl_sync(0xffffffffu, val, NS);
+    // SHI_energy_transfer :1719-1780
+    const double Tot_N = shi_transfer_target(p, shell, RN2);
+    const double dE = shi_transfer_energy(p, shell, Tot_N, m_log(Tot_N));
+    const double SHI_IMFP = -lam * lRN3;
+    const double Z = s.Z + s.L;
+    s.E = s.E - dE; s.t0 = s.tn; s.Z = Z; s.L = SHI_IMFP;
+    s.tn = next_time(s.t0, sqrt(2.0 * s.E * TRK_GE / MSHI), SHI_IMFP);
+    ev.dE = dE; ev.E_after = s.E; ev.t0 = s.t0; ev.Z = Z; ev.shell = shell; ev.ctr0 = s.ctr; ev.iter = s.iter;
+    s.ctr += 2;
+    if (s.Z >= p.layer) s.tn = 1e16;
+}
 __global__ void __launch_bounds__(32 * SHI_WARPS) k_shi(Queue stage, QueueSet qout, int lanes) {
     __shared__ unsigned int s_cnt[S_NCNT];
     block_prologue(nullptr, s_cnt, 0);
     DevCtx c{c_p, qout, nullptr, s_cnt, c_p.defer_snap};
-    // `lanes` ions per warp: 1 = no divergence between ions at all, more = fewer instruction streams to fetch
+    if (lanes <= 0) {       // one ion per warp, the lanes cooperate (n_shells + 1 <= 32 lanes are needed)
+        const uint32_t k = blockIdx.x * SHI_WARPS + (threadIdx.x >> 5);
+        if (k < c_p.batch_n) {
+            Rec s;
+            shi_begin(c_p, s, c_p.batch_begin + k);
+            PhiloxWarp pw; pw.valid = false; pw.base = 0u;
+            while (s.tn < c_p.Tim) {
+                ShiEvent ev;
+                shi_step_warp(c, s, ev, pw);
+                if ((threadIdx.x & 31) == 0) {
+                    const unsigned slot = atomicAdd(stage.count, 1u);
+                    if (slot < stage.cap) {
+                        stage.col[0][slot] = ev.dE; stage.col[1][slot] = ev.E_after; stage.col[3][slot] = ev.t0; stage.col[4][slot] = ev.Z;
+                        stage.shell[slot] = ev.shell; stage.ctr[slot] = ev.ctr0; stage.iter[slot] = ev.iter;
+                    }
+                }
+            }
+        }
+        block_epilogue(c_p, nullptr, s_cnt);
+        return;
+    }
+    // `lanes` ions per warp, each lane on its own: 1 = no divergence between ions at all, more = fewer instruction streams
     const uint32_t k = (blockIdx.x * SHI_WARPS + (threadIdx.x >> 5)) * (uint32_t)lanes + (threadIdx.x & 31);
     if ((int)(threadIdx.x & 31) < lanes && k < c_p.batch_n) {
         Rec s;
@@ -186,7 +290,7 @@ __global__ void __launch_bounds__(32 * SHI_WARPS) k_shi(Queue stage, QueueSet qo
             shi_step(c, s, ev);
             const unsigned slot = atomicAdd(stage.count, 1u);
             if (slot < stage.cap) {
-                stage.col[0][slot] = ev.dE; stage.col[1][slot] = ev.E_after; stage.col[2][slot] = ev.Zeff; stage.col[3][slot] = ev.t0; stage.col[4][slot] = ev.Z;
+                stage.col[0][slot] = ev.dE; stage.col[1][slot] = ev.E_after; stage.col[3][slot] = ev.t0; stage.col[4][slot] = ev.Z;
                 stage.shell[slot] = ev.shell; stage.ctr[slot] = ev.ctr0; stage.iter[slot] = ev.iter;
             }
         }
@@ -200,7 +304,7 @@ __global__ void __launch_bounds__(256) k_shi_emit(Queue stage, QueueSet qout) {
     const uint32_t n = min(*stage.count, stage.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         ShiEvent ev;
-        ev.dE = stage.col[0][i]; ev.E_after = stage.col[1][i]; ev.Zeff = stage.col[2][i]; ev.t0 = stage.col[3][i]; ev.Z = stage.col[4][i];
+        ev.dE = stage.col[0][i]; ev.E_after = stage.col[1][i]; ev.t0 = stage.col[3][i]; ev.Z = stage.col[4][i];
         ev.shell = stage.shell[i]; ev.ctr0 = stage.ctr[i]; ev.iter = stage.iter[i];
         shi_emit(c, ev);
     }
@@ -249,7 +353,7 @@ __global__ void __launch_bounds__(256) k_snapshot(Queue sq, QueueSet qout, int u
 // k_wave<SP, COLD>: records [first, n_in) of queue qin, histories followed with lane refill until they end or
 // have to change queue (hot -> cold when the particle can no longer ionise, core hole -> valence hole, ...).
 template <int SP, bool COLD>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int lockstep, int budget) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int lockstep, int budget, int warm) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
@@ -292,13 +396,14 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
         else if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; continue; }
         if (active) {
             int st;
-            if (SP == SP_ELECTRON) st = step_electron<COLD>(c, r, ig, k);
+            if (SP == SP_ELECTRON) st = step_electron<COLD>(c, r, ig, k, COLD && warm);
             else if (SP == SP_VBHOLE) st = step_vbhole<COLD>(c, r, ig, k);
             else if (SP == SP_COREHOLE) st = step_corehole(c, r, ig);
             else st = step_photon(c, r, ig);
             // time slicing of the hot cascade: after `slice` collisions the record goes back to the queue, so that the
             // duration of a generation is bounded and the work of long histories spreads over many lanes
             if (!COLD && st == ST_CONT && ++nev >= slice) st = ST_MOVE_HOT;
+            if (COLD && warm && st == ST_CONT && ++nev >= slice) st = ST_MOVE;      // a warm electron: on to the next generation
             if (st != ST_CONT) {
                 if (st == ST_MOVE) c.push(SP, r);
                 else if (st == ST_MOVE_HOT) c.push_hot(SP, r);
@@ -332,12 +437,16 @@ struct HotIn {
     uint32_t n[N_ECLASS];
     uint32_t *head[N_ECLASS];
     int quota[N_ECLASS];
+    int slice[N_ECLASS];           // collisions after which a history of class c goes back to the queue (promoted by one class)
     uint32_t wend[N_ECLASS];       // warps [wend[c+1], wend[c]) start on class c (wend[ncls] = 0)
     int ncls;
+    int hist;                      // debugging: fill g_hot_hist
 };
 
+// debugging aid (option "profile" >= 3): collisions per history and energy class of the last k_hot<electron> launch
+__device__ unsigned int g_hot_hist[N_ECLASS][66];
 template <int SP>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(HotIn in, QueueSet qout, int use_smem, int refill_min, int slice, int inel_min, int lockstep) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn in, QueueSet qout, int use_smem, int refill_min, int inel_min, int lockstep) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
@@ -348,7 +457,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(HotIn in, QueueSet qou
     Rec r;
     Cache k{};
     double RN = 0.0;
-    int ig = 0, nev = 0;
+    int ig = 0, nev = 0, my_slice = 0, my_next = 0;
     const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int cls = 0;
     unsigned exh = 0u;              // classes whose queue is used up (warp-uniform)
@@ -375,6 +484,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(HotIn in, QueueSet qou
                 if (rank < (uint32_t)room && my < n_in) {
                     load_rec(in.q[cls], my, r);
                     active = true; nev = 0; have_rn = false;
+                    my_slice = in.slice[cls]; my_next = min(cls + 1, in.ncls - 1);
                     if (SP == SP_ELECTRON) begin_electron(c_p, r, ig, k); else begin_vbhole(c_p, r, ig, k);
                 }
             }
@@ -400,8 +510,16 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, 2) k_hot(HotIn in, QueueSet qou
         if (done_event) {
             have_rn = false;
             // leave when the carrier can no longer ionise (cold queue) or, after `slice` collisions, back to the hot queue
+            ++nev;
             if (hot_leaves<SP>(r)) { c.push(SP, r); active = false; }
-            else if (++nev >= slice && r.tn < c_p.Tim) { c.push_hot(SP, r); active = false; }
+            else if (nev >= my_slice && r.tn < c_p.Tim) {
+                if (SP == SP_ELECTRON) r.shell = -1 - my_next;
+                c.push_hot(SP, r); active = false;
+            }
+            if (in.hist && SP == SP_ELECTRON && (!active || !(r.tn < c_p.Tim))) {
+                const int cc = (r.E >= c_p.e_class[0]) + (r.E >= c_p.e_class[1]) + (r.E >= c_p.e_class[2]);
+                atomicAdd(&g_hot_hist[cc][min(nev, 65)], 1u);
+            }
         }
     }
     block_epilogue(c_p, s_tally, s_cnt);
@@ -440,6 +558,7 @@ struct trk3_engine {
     cudaStream_t stream = nullptr;
     cudaStream_t stream_c = nullptr;       // second stream: the cold kernels run beside the hot cascade
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream_w = nullptr; cudaEvent_t ev_w = nullptr;   // warm electrons of a generation
     cudaStream_t stream_sp[3] = {nullptr, nullptr, nullptr};      // the rarer species of a generation run beside the electrons
     cudaEvent_t ev_gen = nullptr, ev_sp[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -454,12 +573,17 @@ struct trk3_engine {
     // options
     int opt_batch = 1024, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
     int opt_hot_slice = 64, opt_inel_min = 1, opt_overlap = 0, opt_cold_min = 16384;
-    int opt_shi_lanes = 1;
+    int opt_shi_lanes = 0;                 // 0: one ion per warp, the lanes share the work of a collision (k_shi)
     int opt_cold_budget = 0, opt_cold_smem_kb = 0, opt_hot_block = 0;      // see the `overlap` schedule in trk3_mc_run_device
     // energy classes of the hot electrons: lower edges [eV] of classes 1..3 and the most histories a warp follows at once
+    double opt_warm_pinel = 0.2;           // electrons are "warm" below the energy where the ionisation probability per collision reaches this (0: off)
+    int opt_warm_slice = 64;
+    double e_warm_auto = -1.0;             // from warm_P and opt_warm_pinel (< 0: to be evaluated)
+    std::vector<double> warm_E, warm_P;    // ionisation probability per collision on the inelastic energy grid
     int opt_hot_classes = N_ECLASS;
     double opt_class_E[N_ECLASS - 1] = {200.0, 500.0, 1300.0};
     int opt_class_quota[N_ECLASS] = {32, 8, 3, 1};
+    int opt_class_slice[N_ECLASS] = {8, 16, 32, 64};
     int opt_spread = 1, opt_quota_min = 1, opt_lockstep = 0, opt_species_streams = 1, opt_defer_snap = 1;
 
     double opt_cap_factor = 2.0;
@@ -500,7 +624,9 @@ struct trk3_engine {
 #define QC_HEAD (3 * N_SPECIES + 5)
 #define QC_ELC(b) (4 * N_SPECIES + 7 + (b) * (N_ECLASS - 1))      // counts of the electron class queues 1.. of generation set b
 #define QC_HEADC (4 * N_SPECIES + 7 + 2 * (N_ECLASS - 1))          // their heads
-#define QC_TOTAL (4 * N_SPECIES + 7 + 3 * (N_ECLASS - 1))
+#define QC_ELW(b) (4 * N_SPECIES + 7 + 3 * (N_ECLASS - 1) + (b))   // warm electrons of generation set b
+#define QC_HEADW (4 * N_SPECIES + 9 + 3 * (N_ECLASS - 1))
+#define QC_TOTAL (4 * N_SPECIES + 10 + 3 * (N_ECLASS - 1))
 
 namespace {
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { eng->err = std::string(#call) + ": " + cudaGetErrorString(e_); return TRK3_E_CUDA; } } while (0)
@@ -601,6 +727,7 @@ void queue_caps(const trk3_engine *eng, double cap[N_QUEUES]) {
     cap[Q_SNAP] = eng->opt_defer_snap ? 1.25 * n * (double)eng->lay.Nt : 1.0;     // every carrier at every grid time it lives to see
     // the higher energy classes of the hot electrons hold a few per cent of them (the spectrum falls like 1/E^2)
     for (int c = 1; c < N_ECLASS; ++c) cap[Q_ELC + c - 1] = (c < eng->opt_hot_classes) ? 0.25 * n + 64.0 : 0.0;
+    cap[Q_ELW] = (eng->opt_warm_pinel > 0.0) ? n : 0.0;
 }
 double queue_bytes_per_iteration(const trk3_engine *eng) {
     double cap[N_QUEUES]; queue_caps(eng, cap);
@@ -633,11 +760,11 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
         if (rc) return rc;
         eng->qs[1].q[s] = eng->qs[0].q[s]; eng->qs_x.q[s] = eng->qs[0].q[s];
     }
-    for (int b = 0; b < 2; ++b) for (int c = 1; c < N_ECLASS; ++c) {       // energy classes of the hot electrons (set X has none: cap 0)
-        Queue &q = eng->qs[b].q[Q_ELC + c - 1];
+    for (int b = 0; b < 2; ++b) for (int s = Q_ELC; s < N_QUEUES; ++s) {   // energy classes of the hot electrons, warm electrons (set X has none: cap 0)
+        Queue &q = eng->qs[b].q[s];
         q = Queue{};
-        if (cap[Q_ELC + c - 1] <= 0.0) continue;
-        int rc = alloc_queue(eng, q, (uint32_t)(cap[Q_ELC + c - 1] * (double)nb), eng->d_qcount + QC_ELC(b) + (c - 1));
+        if (cap[s] <= 0.0) continue;
+        int rc = alloc_queue(eng, q, (uint32_t)(cap[s] * (double)nb), eng->d_qcount + (s == Q_ELW ? QC_ELW(b) : QC_ELC(b) + (s - Q_ELC)));
         if (rc) return rc;
     }
     for (int s = 0; s < N_SPECIES; ++s) {             // handed back by the cold kernels: a rarity
@@ -660,7 +787,7 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
 }
 
 template <int SP, bool COLD>
-int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_in, uint32_t *head, const QueueSet &qout, cudaStream_t st = nullptr, int budget = 0, size_t smem_floor = 0) {
+int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_in, uint32_t *head, const QueueSet &qout, cudaStream_t st = nullptr, int budget = 0, size_t smem_floor = 0, int warm = 0) {
     const uint32_t n = n_in - first;
     if (!st) st = eng->stream;
     size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
@@ -678,7 +805,7 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_i
     if (budget > 0) { const uint32_t per_block = (uint32_t)budget * (uint32_t)(block / 32); grid = (n + per_block - 1) / per_block; }
     if (grid < 1) grid = 1;
     const int pi = prof_begin(eng, COLD ? N_SPECIES + 2 + SP : SP, st, n);
-    k_wave<SP, COLD><<<grid, block, smem, st>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice, eng->opt_lockstep, budget);
+    k_wave<SP, COLD><<<grid, block, smem, st>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, warm ? eng->opt_warm_slice : eng->opt_hot_slice, eng->opt_lockstep, budget, warm);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
@@ -708,6 +835,7 @@ int launch_hot(trk3_engine *eng, const Queue *const *qin, const uint32_t *n_in, 
         const uint32_t qmax = (uint32_t)(ncls > 1 ? eng->opt_class_quota[c] : 32);
         need[c] = (n_in[c] + qmax - 1) / qmax; total_need += need[c]; n_tot += n_in[c];
         in.quota[c] = (int)qmax;
+        in.slice[c] = (ncls > 1) ? eng->opt_class_slice[c] : eng->opt_hot_slice;
     }
     if (total_need >= W || !eng->opt_spread) {
         for (int c = 0; c < ncls; ++c) w[c] = need[c] ? std::max<uint32_t>(1u, (uint32_t)((uint64_t)need[c] * W / std::max(total_need, 1u))) : 0u;
@@ -729,8 +857,10 @@ int launch_hot(trk3_engine *eng, const Queue *const *qin, const uint32_t *n_in, 
         for (int c = 0; c < ncls; ++c) fprintf(stderr, "  c%d n %u w %u q %d", c, in.n[c], w[c], in.quota[c]);
         fprintf(stderr, "\n");
     }
+    in.hist = (eng->opt_profile >= 3);
+    if (in.hist && SP == SP_ELECTRON) { static unsigned int zero[N_ECLASS][66]; cudaMemcpyToSymbolAsync(g_hot_hist, zero, sizeof zero, 0, cudaMemcpyHostToDevice, st); }
     const int pi = prof_begin(eng, SP, st, n_tot);
-    k_hot<SP><<<grid, block, smem, st>>>(in, qout, use_smem, eng->opt_refill_min, eng->opt_hot_slice, eng->opt_inel_min, eng->opt_lockstep);
+    k_hot<SP><<<grid, block, smem, st>>>(in, qout, use_smem, eng->opt_refill_min, eng->opt_inel_min, eng->opt_lockstep);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
@@ -805,6 +935,17 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
         cold_range(tab->ei_E, tot.ei_tot.data(), tab->n_ei, p.e_cold, p.e_imfp_cold);
         cold_range(tab->hi_E, tot.hi_tot.data(), tab->n_hi, p.h_cold, p.h_imfp_cold);
     }
+    eng->warm_E.assign(tab->ei_E, tab->ei_E + tab->n_ei); eng->warm_P.assign(tab->n_ei, 1.0);
+    for (int i = 0; i < tab->n_ei; ++i) {       // ionisation probability per collision on the inelastic grid (scheduling only)
+        const double E = tab->ei_E[i], li = tot.ei_tot[i];
+        int j = (int)(std::upper_bound(tab->ee_E, tab->ee_E + tab->n_ee, E) - tab->ee_E);
+        j = std::min(std::max(j, 1), tab->n_ee - 1);
+        const double f = (E - tab->ee_E[j - 1]) / (tab->ee_E[j] - tab->ee_E[j - 1]);
+        const double le = tab->ee_L[j - 1] + std::min(1.0, std::max(0.0, f)) * (tab->ee_L[j] - tab->ee_L[j - 1]);
+        const double ii = (li > 0.0 && li < 1e15) ? 1.0 / li : 0.0, ie = (le > 0.0 && le < 1e15) ? 1.0 / le : 0.0;
+        eng->warm_P[i] = (ii + ie > 0.0) ? ii / (ii + ie) : 0.0;
+    }
+    eng->e_warm_auto = -1.0;
     CK(cudaStreamSynchronize(eng->stream));
     p.tally = old.tally; p.events = old.events; p.errors = old.errors; p.cnt_el = old.cnt_el; p.cnt_ph = old.cnt_ph; p.it = old.it;
 
@@ -838,6 +979,7 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
         CK(cudaStreamCreateWithPriority(&eng->stream_c, cudaStreamNonBlocking, lo));
         for (int i = 0; i < 3; ++i) { CK(cudaStreamCreateWithPriority(&eng->stream_sp[i], cudaStreamNonBlocking, hi)); CK(cudaEventCreateWithFlags(&eng->ev_sp[i], cudaEventDisableTiming)); }
         CK(cudaEventCreateWithFlags(&eng->ev_gen, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithPriority(&eng->stream_w, cudaStreamNonBlocking, hi)); CK(cudaEventCreateWithFlags(&eng->ev_w, cudaEventDisableTiming));
     }
     CK(cudaEventCreate(&eng->ev0)); CK(cudaEventCreate(&eng->ev1));
     CK(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&eng->ev_join, cudaEventDisableTiming));
@@ -885,7 +1027,7 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "queue_gib") eng->opt_queue_bytes_max = (size_t)(v * (double)(1ull << 30));
     else if (k == "block") eng->opt_block = std::min(TRK_BLOCK_MAX, std::max(32, ((int)v / 32) * 32));
     else if (k == "hot_slice") eng->opt_hot_slice = std::max(1, (int)v);
-    else if (k == "shi_lanes") eng->opt_shi_lanes = std::min(32, std::max(1, (int)v));
+    else if (k == "shi_lanes") eng->opt_shi_lanes = std::min(32, std::max(0, (int)v));
     else if (k == "defer_snap") { eng->opt_defer_snap = (v != 0.0); eng->nb_alloc = 0; }
     else if (k == "species_streams") eng->opt_species_streams = (v != 0.0);
     else if (k == "lockstep") eng->opt_lockstep = (v != 0.0);
@@ -893,10 +1035,16 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "quota_min") eng->opt_quota_min = std::min(32, std::max(1, (int)v));
     else if (k == "overlap") eng->opt_overlap = (v != 0.0);
     else if (k == "cold_min") eng->opt_cold_min = std::max(1, (int)v);
+    else if (k == "warm_pinel") { eng->opt_warm_pinel = std::min(0.99, std::max(0.0, v)); eng->nb_alloc = 0; eng->e_warm_auto = -1.0; }
+    else if (k == "warm_slice") eng->opt_warm_slice = std::max(1, (int)v);
     else if (k == "hot_classes") { eng->opt_hot_classes = std::min(N_ECLASS, std::max(1, (int)v)); eng->nb_alloc = 0; }
     else if (k == "class_E1") eng->opt_class_E[0] = v;
     else if (k == "class_E2") eng->opt_class_E[1] = v;
     else if (k == "class_E3") eng->opt_class_E[2] = v;
+    else if (k == "class_s0") eng->opt_class_slice[0] = std::max(1, (int)v);
+    else if (k == "class_s1") eng->opt_class_slice[1] = std::max(1, (int)v);
+    else if (k == "class_s2") eng->opt_class_slice[2] = std::max(1, (int)v);
+    else if (k == "class_s3") eng->opt_class_slice[3] = std::max(1, (int)v);
     else if (k == "class_q0") eng->opt_class_quota[0] = std::min(32, std::max(1, (int)v));
     else if (k == "class_q1") eng->opt_class_quota[1] = std::min(32, std::max(1, (int)v));
     else if (k == "class_q2") eng->opt_class_quota[2] = std::min(32, std::max(1, (int)v));
@@ -959,6 +1107,12 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         CK(cudaMemcpyAsync(eng->d_counters_bak, eng->d_counters, n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, eng->stream));
         eng->hp.batch_begin = (uint32_t)b0; eng->hp.batch_n = nb;
         eng->hp.defer_snap = eng->opt_defer_snap;
+        if (eng->e_warm_auto < 0.0) {        // the lowest grid energy at which an ionisation is at least as likely as `warm_pinel`
+            eng->e_warm_auto = eng->warm_E.empty() ? 0.0 : eng->warm_E.back();
+            for (size_t i = 0; i < eng->warm_E.size(); ++i) if (eng->warm_E[i] >= eng->hp.e_cold && eng->warm_P[i] >= eng->opt_warm_pinel) { eng->e_warm_auto = eng->warm_E[i]; break; }
+        }
+        eng->hp.e_warm = (eng->opt_warm_pinel > 0.0) ? std::max(eng->e_warm_auto, eng->hp.e_cold) : eng->hp.e_cold;
+        if (eng->opt_profile >= 2) fprintf(stderr, "e_cold %.3f e_warm %.3f eV\n", eng->hp.e_cold, eng->hp.e_warm);
         for (int c = 1; c < N_ECLASS; ++c) eng->hp.e_class[c - 1] = (c < eng->opt_hot_classes) ? eng->opt_class_E[c - 1] : 1.0e300;
 
         CK(cudaMemcpyToSymbolAsync(c_p, &eng->hp, sizeof(DevP), 0, cudaMemcpyHostToDevice, eng->stream));
@@ -968,8 +1122,9 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         { const int pi = prof_begin(eng, N_SPECIES);
           // collisions are staged in the (still unused) electron queue of the other generation
           const Queue &stage = eng->qs[1].q[SP_ELECTRON];
-          const uint32_t shi_warps = (nb + eng->opt_shi_lanes - 1) / eng->opt_shi_lanes;
-          k_shi<<<(shi_warps + SHI_WARPS - 1) / SHI_WARPS, 32 * SHI_WARPS, 0, eng->stream>>>(stage, eng->qs[0], eng->opt_shi_lanes);
+          const int shi_lanes = (eng->opt_shi_lanes > 0 || eng->hp.n_shells + 1 > 32) ? std::max(1, eng->opt_shi_lanes) : 0;
+          const uint32_t shi_warps = shi_lanes ? (nb + shi_lanes - 1) / shi_lanes : nb;
+          k_shi<<<(shi_warps + SHI_WARPS - 1) / SHI_WARPS, 32 * SHI_WARPS, 0, eng->stream>>>(stage, eng->qs[0], shi_lanes);
           k_shi_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(stage, eng->qs[0]);
           prof_end(eng, pi); }
         CK(cudaGetLastError());
@@ -984,12 +1139,25 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             uint32_t h_cnt[QC_TOTAL];          // hot counts of both generations, cold counts, set X, ionisation queue, ..., class queues
             CK(cudaMemcpyAsync(h_cnt, eng->d_qcount, sizeof h_cnt, cudaMemcpyDeviceToHost, eng->stream));
             CK(cudaStreamSynchronize(eng->stream));
+            if (eng->opt_profile >= 3 && gen > 0) {
+                unsigned int hh[N_ECLASS][66];
+                cudaMemcpyFromSymbol(hh, g_hot_hist, sizeof hh);
+                for (int c = 0; c < N_ECLASS; ++c) {
+                    fprintf(stderr, "hist gen %d final class %d:", gen - 1, c);
+                    const int edges[] = {1, 2, 3, 5, 9, 17, 33, 64, 65, 66};
+                    for (int b = 0; b + 1 < 10; ++b) { unsigned long long sum = 0; for (int i = edges[b]; i < edges[b + 1]; ++i) sum += hh[c][i]; fprintf(stderr, " [%d,%d) %llu", edges[b], edges[b + 1], sum); }
+                    fprintf(stderr, "\n");
+                }
+            }
             uint32_t *hot = h_cnt + QC_HOT(cur), *cold = h_cnt + QC_COLD, *hotc = h_cnt + QC_ELC(cur);
             uint64_t total = 0;
             if (gen == 0 && h_cnt[QC_HOT(1) + SP_ELECTRON] > eng->qs[1].q[SP_ELECTRON].cap) overflow = true;     // staged ion collisions
             for (int s = 0; s < N_SPECIES; ++s) { if (hot[s] > eng->qs[cur].q[s].cap) { overflow = true; hot[s] = eng->qs[cur].q[s].cap; } total += hot[s]; }
             uint32_t n_hot_el = hot[SP_ELECTRON];
             for (int c = 1; c < N_ECLASS; ++c) { const uint32_t cp = eng->qs[cur].q[Q_ELC + c - 1].cap; if (hotc[c - 1] > cp) { overflow = true; hotc[c - 1] = cp; } total += hotc[c - 1]; n_hot_el += hotc[c - 1]; }
+            uint32_t n_warm = h_cnt[QC_ELW(cur)];
+            if (n_warm > eng->qs[cur].q[Q_ELW].cap) { overflow = true; n_warm = eng->qs[cur].q[Q_ELW].cap; }
+            total += n_warm;
             for (int s = 0; s < 2; ++s) if (cold[s] > eng->qs[0].q[N_SPECIES + s].cap) { overflow = true; cold[s] = eng->qs[0].q[N_SPECIES + s].cap; }
             if (h_cnt[QC_ION + 1] > eng->qs[0].q[Q_ION].cap) overflow = true;
             if (h_cnt[QC_SNAP] > eng->qs[0].q[Q_SNAP].cap) overflow = true;
@@ -1001,6 +1169,8 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
                 CK(cudaMemsetAsync(eng->d_qcount + QC_HOT(nxt), 0, N_SPECIES * sizeof(uint32_t), eng->stream));
                 CK(cudaMemsetAsync(eng->d_qcount + QC_ELC(nxt), 0, (N_ECLASS - 1) * sizeof(uint32_t), eng->stream));
                 CK(cudaMemsetAsync(eng->d_qcount + QC_HEADC, 0, (N_ECLASS - 1) * sizeof(uint32_t), eng->stream));
+                CK(cudaMemsetAsync(eng->d_qcount + QC_ELW(nxt), 0, sizeof(uint32_t), eng->stream));
+                CK(cudaMemsetAsync(eng->d_qcount + QC_HEADW, 0, sizeof(uint32_t), eng->stream));
                 CK(cudaMemsetAsync(heads, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
                 // the species of a generation are independent of each other: the (few) valence holes, core holes and photons run
                 // on their own streams beside the electrons instead of lengthening the generation one after the other
@@ -1010,11 +1180,18 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
                 if (n_hot_el) { rc = launch_hot_electrons(eng, eng->qs[cur], hot, hotc, eng->qs[nxt]); if (rc) return rc; }
                 if (hot[SP_VBHOLE]) { if (par) CK(cudaStreamWaitEvent(s1, eng->ev_gen, 0)); rc = launch_hot_vbholes(eng, eng->qs[cur].q[SP_VBHOLE], hot[SP_VBHOLE], eng->qs[nxt], s1); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[0], s1)); }
                 if (hot[SP_COREHOLE]) { if (par) CK(cudaStreamWaitEvent(s2, eng->ev_gen, 0)); rc = launch_wave<SP_COREHOLE, false>(eng, eng->qs[cur].q[SP_COREHOLE], 0, hot[SP_COREHOLE], heads + SP_COREHOLE, eng->qs[nxt], s2); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[1], s2)); }
+                if (n_warm) {       // warm electrons: the elastic-only kernel, one time slice per generation
+                    cudaStream_t s4 = par ? eng->stream_w : eng->stream;
+                    if (par) CK(cudaStreamWaitEvent(s4, eng->ev_gen, 0));
+                    rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[cur].q[Q_ELW], 0, n_warm, eng->d_qcount + QC_HEADW, eng->qs[nxt], s4, 0, 0, 1); if (rc) return rc;
+                    if (par) CK(cudaEventRecord(eng->ev_w, s4));
+                }
                 if (hot[SP_PHOTON]) { if (par) CK(cudaStreamWaitEvent(s3, eng->ev_gen, 0)); rc = launch_wave<SP_PHOTON, false>(eng, eng->qs[cur].q[SP_PHOTON], 0, hot[SP_PHOTON], heads + SP_PHOTON, eng->qs[nxt], s3); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[2], s3)); }
                 if (par) {
                     if (hot[SP_VBHOLE]) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[0], 0));
                     if (hot[SP_COREHOLE]) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[1], 0));
                     if (hot[SP_PHOTON]) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[2], 0));
+                    if (n_warm) CK(cudaStreamWaitEvent(eng->stream, eng->ev_w, 0));
                 }
                 if (n_hot_el) {             // the pairs of this generation's impact ionisations join the next generation
                     const int pi = prof_begin(eng, SP_ELECTRON);
@@ -1049,6 +1226,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             CK(cudaMemsetAsync(eng->d_qcount + QC_HOT(nxt), 0, N_SPECIES * sizeof(uint32_t), eng->stream));
             CK(cudaMemsetAsync(eng->d_qcount + QC_ELC(nxt), 0, (N_ECLASS - 1) * sizeof(uint32_t), eng->stream));
             CK(cudaMemsetAsync(eng->d_qcount + QC_HEADC, 0, (N_ECLASS - 1) * sizeof(uint32_t), eng->stream));
+            CK(cudaMemsetAsync(eng->d_qcount + QC_ELW(nxt), 0, sizeof(uint32_t), eng->stream));
             CK(cudaMemsetAsync(heads, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
             if (h_x[SP_ELECTRON]) { rc = launch_hot_electrons(eng, eng->qs_x, h_x, nullptr, eng->qs[nxt]); if (rc) return rc; }
             if (h_x[SP_VBHOLE]) { rc = launch_hot_vbholes(eng, eng->qs_x.q[SP_VBHOLE], h_x[SP_VBHOLE], eng->qs[nxt]); if (rc) return rc; }
@@ -1207,6 +1385,8 @@ void trk3_mc_destroy(trk3_engine *eng) {
     if (eng->stream_c) cudaStreamDestroy(eng->stream_c);
     for (int i = 0; i < 3; ++i) { if (eng->stream_sp[i]) cudaStreamDestroy(eng->stream_sp[i]); if (eng->ev_sp[i]) cudaEventDestroy(eng->ev_sp[i]); }
     if (eng->ev_gen) cudaEventDestroy(eng->ev_gen);
+    if (eng->stream_w) cudaStreamDestroy(eng->stream_w);
+    if (eng->ev_w) cudaEventDestroy(eng->ev_w);
     if (eng->ev_fork) cudaEventDestroy(eng->ev_fork);
     if (eng->ev_join) cudaEventDestroy(eng->ev_join);
     delete eng;

@@ -57,22 +57,24 @@ inline void build_lut(const double *E, int N, std::vector<uint16_t> &lut, double
         lut[b] = (uint16_t)j;
     }
 }
-// Accelerator of the search "first index with 1/L >= x" in a cumulative table of the ion (SHI_energy_transfer): bins in log x
+// Accelerator of the search "first index with 1/L >= x" in a cumulative table of the ion (SHI_energy_transfer).  The bins
+// are uniform in x = 1/L itself: that is the measure the collisions sample x with (x = x0 + RN (x1 - x0), :1748), so every
+// bin is hit equally often and the local scan that follows the lookup is N / TRK_NLUT steps long on average.
 inline void build_inverse_lut(const double *L, int N, int M_temp, std::vector<uint16_t> &lut, double &l0, double &scale) {
     lut.assign(TRK_NLUT, 1);
     l0 = 0.0; scale = 0.0;
     if (N < 2 || N > 65535) return;
     int first = (M_temp >= 2) ? M_temp - 2 : 0;
-    while (first < N - 1 && !(L[first] > 0.0 && 1.0 / L[first] > 0.0 && std::isfinite(std::log(1.0 / L[first])))) ++first;
+    while (first < N - 1 && !(L[first] > 0.0 && std::isfinite(1.0 / L[first]))) ++first;
     if (!(L[N - 1] > 0.0)) return;
-    l0 = std::log(1.0 / L[first]);
-    const double l1 = std::log(1.0 / L[N - 1]);
+    l0 = 1.0 / L[first];
+    const double l1 = 1.0 / L[N - 1];
     if (!(l1 > l0) || !std::isfinite(l0) || !std::isfinite(l1)) { l0 = 0.0; return; }
     scale = (double)TRK_NLUT / (l1 - l0);
     int j = first + 1;                                                  // 1-based
     for (int b = 0; b < TRK_NLUT; ++b) {
         const double edge = l0 + (double)b / scale;
-        while (j < N && !(L[j - 1] > 0.0 && std::log(1.0 / L[j - 1]) >= edge)) ++j;
+        while (j < N && !(L[j - 1] > 0.0 && 1.0 / L[j - 1] >= edge)) ++j;
         lut[b] = (uint16_t)j;
     }
 }

@@ -117,6 +117,9 @@ struct DevP {
     // of collisions an electron still has before it turns cold grows with its energy, and the engine gives the long
     // histories warps of their own (engine.cu, k_hot)
     double e_class[3];
+    // "warm" electrons, e_cold <= E < e_warm, can still ionise but rarely do; the engine follows them with the elastic-only
+    // kernel, generation by generation (e_warm = e_cold: no such class)
+    double e_warm;
     // ---- time grid: tg[i-1] = min(time_grid(i), Tim), i = 1..Nt
     int32_t Nt;
     double tg[TRK3_MAX_NT];

@@ -607,23 +607,29 @@ TRK_HD void shi_threshold(const double *Ea, const double *La, int N, double E_cu
         else dL = interp1(Ea[M_temp - 2], Ea[M_temp - 1], La[M_temp - 2], La[M_temp - 1], E_cur);
     } else dL = La[0];
 }
-TRK_HD double shi_energy_transfer(const DevP &p, Rec &r, int shell) {
+// Two halves, so that a caller can evaluate the logarithm between them together with others (k_shi, engine.cu):
+// shi_transfer_target = the sampled cumulative inverse MFP, shi_transfer_energy = its inverse lookup.
+TRK_HD double shi_transfer_target(const DevP &p, int shell, double RN) {
     const int64_t o = p.dshi_off[shell];
-    const double *Ea = p.dshi_E + o, *La = p.dshi_L + o, *lEa = p.ldshi_E + o, *iLa = p.dshi_iL + o, *liLa = p.ldshi_iL + o;
-    int N = (int)(p.dshi_off[shell + 1] - o);
-    double RN = rn(p, r);
-    const int M_temp = p.shi_Mtemp[shell];
+    const double *La = p.dshi_L + o;
+    const int N = (int)(p.dshi_off[shell + 1] - o);
     const double dL = p.shi_dL[shell];
-    double Tot_N = (dL > 0.0 && La[N - 1] > 0.0) ? 1.0 / dL + RN * (1.0 / La[N - 1] - 1.0 / dL) : 1.5e21;
+    return (dL > 0.0 && La[N - 1] > 0.0) ? 1.0 / dL + RN * (1.0 / La[N - 1] - 1.0 / dL) : 1.5e21;
+}
+TRK_HD double shi_transfer_energy(const DevP &p, int shell, double Tot_N, double lTot) {
+    const int64_t o = p.dshi_off[shell];
+    const double *Ea = p.dshi_E + o, *lEa = p.ldshi_E + o, *iLa = p.dshi_iL + o, *liLa = p.ldshi_iL + o;
+    int N = (int)(p.dshi_off[shell + 1] - o);
+    const int M_temp = p.shi_Mtemp[shell];
     int N_temmp;
-    const double lTot = m_log(Tot_N);
     if (Tot_N < 1e20) {
         // 1/L is non-decreasing (cumulative cross section): the first index with 1/L >= Tot_N, clamped to N.  The tables have
-        // thousands of rows: a direct index in log(1/L) + local scan instead of 13 dependent loads of a bisection.
+        // thousands of rows: a direct index (bins uniform in 1/L, the measure Tot_N is sampled with) + local scan instead of
+        // 13 dependent loads of a bisection.
         const GridLut &g = p.dshi_lut[shell];
         int j;
         if (g.scale > 0.0) {
-            int b = (int)((lTot - g.l0) * g.scale);
+            int b = (int)((Tot_N - g.l0) * g.scale);
             b = (b < 0) ? 0 : ((b >= TRK_NLUT) ? TRK_NLUT - 1 : b);
             j = g.lut[b];
             while (j < N && iLa[j - 1] < Tot_N) ++j;
@@ -637,6 +643,10 @@ TRK_HD double shi_energy_transfer(const DevP &p, Rec &r, int shell) {
     } else N_temmp = M_temp;
     if (N_temmp > M_temp) return interp5t(iLa[N_temmp - 2], iLa[N_temmp - 1], Ea[N_temmp - 2], Ea[N_temmp - 1], liLa[N_temmp - 2], liLa[N_temmp - 1], lEa[N_temmp - 2], lEa[N_temmp - 1], Tot_N, lTot);
     return p.shell_Ip[shell];
+}
+TRK_HD double shi_energy_transfer(const DevP &p, Rec &r, int shell) {
+    const double Tot_N = shi_transfer_target(p, shell, rn(p, r));
+    return shi_transfer_energy(p, shell, Tot_N, m_log(Tot_N));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1073,7 +1083,6 @@ TRK_HD void photon_event(C &c, Rec &ph) {
 struct ShiEvent {
     double dE;          // transferred energy
     double E_after;     // ion energy after the collision (Update_electron_angles_SHI uses the updated ion)
-    double Zeff;        // equilibrium charge after the collision (Impact_parameter)
     double t0, Z;       // time and depth of the collision
     int32_t shell;
     uint32_t ctr0;      // position of the ion's stream at the creation of the pair (children's ids)
@@ -1106,7 +1115,7 @@ TRK_HD void shi_step(C &c, Rec &s, ShiEvent &ev) {
     double Z = s.Z + s.L;
     s.E = s.E - dE; s.t0 = s.tn; s.Z = Z; s.L = SHI_IMFP;
     s.tn = next_time(s.t0, sqrt(2.0 * s.E * TRK_GE / MSHI), SHI_IMFP);
-    ev.dE = dE; ev.E_after = s.E; ev.Zeff = shi_zeff(p, s.E); ev.t0 = s.t0; ev.Z = Z; ev.shell = shell; ev.ctr0 = s.ctr; ev.iter = s.iter;
+    ev.dE = dE; ev.E_after = s.E; ev.t0 = s.t0; ev.Z = Z; ev.shell = shell; ev.ctr0 = s.ctr; ev.iter = s.iter;
     s.ctr += 2;                                                   // the two child ids
     if (s.Z >= p.layer) s.tn = 1e16;                              // :597 the ion has left the layer
 }
@@ -1126,7 +1135,8 @@ TRK_HD void shi_emit(C &c, const ShiEvent &ev) {
     double phi; { double r2 = rn(p, se); phi = 2.0 * TRK_PI * r2; }
     // Impact_parameter (:1113-1126); the ion moves along the Z axis (X = Y = 0)
     double A = 1.0 + MSHI / TRK_ME;
-    double b = TRK_A0 * ev.Zeff * TRK_RY / ev.E_after * sqrt(4.0 * ev.E_after / dE * MSHI / TRK_ME - A * A);
+    const double Zeff = shi_zeff(p, ev.E_after);                  // the equilibrium charge after the collision (:2196)
+    double b = TRK_A0 * Zeff * TRK_RY / ev.E_after * sqrt(4.0 * ev.E_after / dE * MSHI / TRK_ME - A * A);
     double X = b * m_sin(phi), Y = b * m_cos(phi);
     emit_electron(c, se, id_e, dE_cur, ev.t0, X, Y, ev.Z, theta, phi, TRK3_ERR_20);
     emit_hole(c, sh, id_h, ev.shell, dE - dE_cur, ev.t0, X, Y, ev.Z, TRK3_ERR_20);
@@ -1149,7 +1159,7 @@ TRK_HD void shi_history(C &c, uint32_t iter) {
 TRK_HD bool electron_is_cold(const DevP &p, const Rec &e) { return e.E < p.e_cold || !(e.tn < p.Tim); }
 TRK_HD bool vbhole_is_cold(const DevP &p, const Rec &h) { return h.Ehkin < p.h_cold || !(h.tn < p.Tim); }
 
-TRK_HD bool electron_leaves_hot(const DevP &p, const Rec &e) { return e.E < p.e_cold && e.tn < p.Tim; }
+TRK_HD bool electron_leaves_hot(const DevP &p, const Rec &e) { return e.E < p.e_warm && e.tn < p.Tim; }      // e_warm >= e_cold
 TRK_HD bool vbhole_leaves_hot(const DevP &p, const Rec &h) { return h.Ehkin < p.h_cold && h.tn < p.Tim; }
 
 enum StepStatus { ST_DONE = 0, ST_CONT = 1, ST_MOVE = 2, ST_MOVE_HOT = 3 };
@@ -1162,19 +1172,26 @@ TRK_HD void begin_electron(const DevP &p, const Rec &e, int &ig, Cache &k) {
 }
 // one step = snapshots spanned by the current free flight, then the collision at tn.  A record may only change
 // queue in a state where the snapshots of (t0, tn] are still all to be taken: the consumer restarts from t0.
+// `warm` (COLD only): the elastic-only handler also serves the "warm" electrons, which can still ionise but rarely do
+// (E < DevP::e_warm: the channel roulette selects the ionisation with a small probability).  A warm electron whose
+// roulette does select it is handed to the full handler with its stream rewound by that draw (ST_MOVE_HOT), so the
+// result does not depend on which kernel followed it; one that has fallen below e_cold moves on to the cold queue.
 template <bool COLD, class C>
-TRK_HD int step_electron(C &c, Rec &e, int &ig, Cache &k) {
+TRK_HD int step_electron(C &c, Rec &e, int &ig, Cache &k, bool warm = false) {
     const DevP &p = c.p;
     double RN = 0.0;
     if (COLD && e.tn < p.tg[p.Nt - 1]) {                          // a collision is pending: is it really an elastic one?
-        if (!(e.E < p.e_cold)) return ST_MOVE;
+        if (!(e.E < (warm ? p.e_warm : p.e_cold))) return ST_MOVE;
         event_begin(e);
         RN = rn(p, e);
-        if (electron_roulette_inelastic(k, RN)) { e.ctr--; return ST_MOVE_HOT; }      // probability ~1e-16 (IMFP >= 1e16)
+        if (electron_roulette_inelastic(k, RN)) { e.ctr--; return ST_MOVE_HOT; }      // cold: probability ~1e-16 (IMFP >= 1e16)
     }
     while (ig <= p.Nt && p.tg[ig - 1] <= e.tn) { c.snap(SP_ELECTRON, e, ig); ++ig; }
     if (ig > p.Nt) return ST_DONE;
-    if (COLD) { electron_event_t<EV_ELASTIC>(c, e, ig, k, RN); return ST_CONT; }
+    if (COLD) {
+        electron_event_t<EV_ELASTIC>(c, e, ig, k, RN);
+        return (warm && (e.E < p.e_cold || !(e.tn < p.Tim))) ? ST_MOVE : ST_CONT;
+    }
     event_begin(e);
     RN = rn(p, e);
     electron_event_t<EV_ANY>(c, e, ig, k, RN);
