@@ -934,6 +934,7 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
     for (int sh = 0; sh < T.n_shells; ++sh) shi_threshold(T.dshi_E + T.dshi_off[sh], T.dshi_L + T.dshi_off[sh], (int)(T.dshi_off[sh + 1] - T.dshi_off[sh]), T.shell_Ip[sh], p.shi_Mtemp[sh], p.shi_dL[sh]);
         cold_range(tab->ei_E, tot.ei_tot.data(), tab->n_ei, p.e_cold, p.e_imfp_cold);
         cold_range(tab->hi_E, tot.hi_tot.data(), tab->n_hi, p.h_cold, p.h_imfp_cold);
+        p.e_iimfp_cold = (p.e_imfp_cold > 0.0) ? 1.0 / p.e_imfp_cold : 0.0; p.h_iimfp_cold = (p.h_imfp_cold > 0.0) ? 1.0 / p.h_imfp_cold : 0.0;
     }
     eng->warm_E.assign(tab->ei_E, tab->ei_E + tab->n_ei); eng->warm_P.assign(tab->n_ei, 1.0);
     for (int i = 0; i < tab->n_ei; ++i) {       // ionisation probability per collision on the inelastic grid (scheduling only)

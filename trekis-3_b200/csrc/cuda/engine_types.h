@@ -113,6 +113,7 @@ struct DevP {
     double dos_inv_step;                                 // 1/step of the DOS energy grid if it is uniform, else 0
     // below these energies the total inelastic MFP is one constant >= 1e16 (no ionisation possible): lookup skipped
     double e_cold, e_imfp_cold, h_cold, h_imfp_cold;
+    double e_iimfp_cold, h_iimfp_cold;                   // 1 / the two constants
     // hot electrons are queued by energy class (class c: e_class[c-1] <= E < e_class[c]; +inf = class not used): the number
     // of collisions an electron still has before it turns cold grows with its energy, and the engine gives the long
     // histories warps of their own (engine.cu, k_hot)

@@ -50,6 +50,9 @@ TRK_MATH double m_log(double x) { return log(x); }
 TRK_MATH double m_sin(double x) { return sin(x); }
 TRK_MATH double m_cos(double x) { return cos(x); }
 TRK_MATH double m_acos(double x) { return acos(x); }
+// sine and cosine of one angle share the argument reduction (same values as m_sin / m_cos)
+struct SinCos { double s, c; };
+TRK_MATH SinCos m_sincos(double x) { SinCos r; sincos(x, &r.s, &r.c); return r; }
 // (divisions and square roots out of line were measured too: 21.4 ms instead of 20.9 ms per step -- they stay inline)
 TRK_HD double m_div(double a, double b) { return a / b; }
 TRK_HD double m_sqrt(double a) { return sqrt(a); }
@@ -165,6 +168,15 @@ TRK_HD double interp5t(double E1, double E2, double S1, double S2, double lE1, d
     if (En == E1) return S1;
     return m_exp(lS1 + m_div(lS2 - lS1, lE2 - lE1) * (lEn - lE1));
 }
+// interp5t that also returns the logarithm of its result: the exponent it evaluated, or the tabulated logarithm of the
+// table entry it returns.  (log(exp(x)) = x up to rounding: callers that interpolate the result again in log space
+// use it instead of a second logarithm -- interpolate_transferred_energy does so twice per sampled energy.)
+TRK_HD double interp5t_l(double E1, double E2, double S1, double S2, double lE1, double lE2, double lS1, double lS2, double En, double lEn, double &lres) {
+    if (fabs(E2 - E1) < 1.0e-6) { if (S1 > S2) { lres = lS1; return S1; } lres = lS2; return S2; }
+    if (En == E1) { lres = lS1; return S1; }
+    lres = lS1 + m_div(lS2 - lS1, lE2 - lE1) * (lEn - lE1);
+    return m_exp(lres);
+}
 TRK_HD double interp1(double E1, double E2, double S1, double S2, double En) {
     if (fabs(E2 - E1) < 1.0e-6) return (S1 > S2) ? S1 : S2;
     if (En == E1) return S1;
@@ -238,6 +250,8 @@ struct Cache {
     double lE;      // m_log(E)
     double emfp;    // elastic MFP from the 2D-searched table (El_EMFP / Hole_EMFP)
     double imfp;    // total inelastic MFP (El_IMFP / Hole_IMFP)
+    double iemfp, iimfp;   // their reciprocals: the channel roulette of the next collision (:2301) and the free path sampled
+                           // at the end of this one (:2451) divide 1 by the same two numbers
     int n1, n2;     // 1D / 2D search indices of E in the elastic grid
 };
 TRK_HDN void cache_fill(const Tab &el, double E, Cache &k) {
@@ -245,7 +259,8 @@ TRK_HDN void cache_fill(const Tab &el, double E, Cache &k) {
     k.n1 = tab_find(el, E, k.lE);
     k.n2 = find_2d_from_1d(el.E, el.N, E, k.n1);
     k.emfp = nfp_at(el, k.n2, true, E, k.lE);
-    k.imfp = 0.0;
+    k.iemfp = m_div(1.0, k.emfp);
+    k.imfp = 0.0; k.iimfp = 0.0;
 }
 // Elastic_MFP%Total searched with the 1D routine (:2385, :2664): same table as El_EMFP, so the value is shared
 // whenever both searches agree and the energy is inside the grid
@@ -255,8 +270,16 @@ TRK_HD double elastic_total(const Tab &el, double E, const Cache &k) {
 }
 
 // all lookups of an electron / valence hole of kinetic energy E (what :2298-2299 / :2579-2580 evaluate at the start of an event)
-TRK_HD void cache_electron(const DevP &p, double E, Cache &k) { cache_fill(tab_ee(p), E, k); k.imfp = electron_imfp(p, E, k.lE); }
-TRK_HD void cache_vbhole(const DevP &p, double E, Cache &k) { cache_fill(tab_he(p), E, k); k.imfp = hole_imfp(p, E, k.lE); }
+TRK_HD void cache_electron(const DevP &p, double E, Cache &k) {
+    cache_fill(tab_ee(p), E, k);
+    if (E < p.e_cold) { k.imfp = p.e_imfp_cold; k.iimfp = p.e_iimfp_cold; }
+    else { k.imfp = electron_imfp(p, E, k.lE); k.iimfp = m_div(1.0, k.imfp); }
+}
+TRK_HD void cache_vbhole(const DevP &p, double E, Cache &k) {
+    cache_fill(tab_he(p), E, k);
+    if (E < p.h_cold) { k.imfp = p.h_imfp_cold; k.iimfp = p.h_iimfp_cold; }
+    else { k.imfp = hole_imfp(p, E, k.lE); k.iimfp = m_div(1.0, k.imfp); }
+}
 
 // Which_shell, Monte_Carlo.f90:1786-1832: shell roulette on 1/lambda_shell(E); returns the flat shell
 // `m` = the family's per-shell matrix; n_out receives the search index of E in the family's grid (reused by the caller)
@@ -328,11 +351,11 @@ TRK_HD void find_dec2(const double *A, int NA, const double *B, int NB, double v
     }
     ia = ac; ib = bc;
 }
-TRK_HD double sample_row_at(const Csr &t, int64_t o, int n, int i_hw, double L_need, double lLn) {
-    const double *L = t.L + o, *hw = t.hw + o;
-    if (i_hw == 1 || i_hw == n) return hw[i_hw - 1];
-    const double *lL = t.lL + o, *lhw = t.lhw + o;
-    return interp5t(L[i_hw - 1], L[i_hw], hw[i_hw - 1], hw[i_hw], lL[i_hw - 1], lL[i_hw], lhw[i_hw - 1], lhw[i_hw], L_need, lLn);
+TRK_HD double sample_row_at(const Csr &t, int64_t o, int n, int i_hw, double L_need, double lLn, double &lres) {
+    const double *L = t.L + o, *hw = t.hw + o, *lhw = t.lhw + o;
+    if (i_hw == 1 || i_hw == n) { lres = lhw[i_hw - 1]; return hw[i_hw - 1]; }
+    const double *lL = t.lL + o;
+    return interp5t_l(L[i_hw - 1], L[i_hw], hw[i_hw - 1], hw[i_hw], lL[i_hw - 1], lL[i_hw], lhw[i_hw - 1], lhw[i_hw], L_need, lLn, lres);
 }
 TRK_HD double sample_row(const Csr &t, int64_t o, int n, double L_need, double lLn) {
     const double *L = t.L + o, *hw = t.hw + o;
@@ -350,11 +373,12 @@ TRK_HDN double transferred_energy(const Csr &t, double Ele, double lE, int i_E, 
     const int n1 = (int)(t.off[i_E] - o), n2 = (int)(o - o2);
     int i1, i2;
     find_dec2(t.L + o, n1, t.L + o2, n2, L_need, i1, i2);
-    double hw_1 = sample_row_at(t, o, n1, i1, L_need, lLn);
+    double lhw_1, lhw_2;
+    double hw_1 = sample_row_at(t, o, n1, i1, L_need, lLn, lhw_1);
     i_E = i_E - 1;
-    double hw_2 = sample_row_at(t, o2, n2, i2, L_need, lLn);
+    double hw_2 = sample_row_at(t, o2, n2, i2, L_need, lLn, lhw_2);
     if (hw_1 < 1.0e-10 || hw_2 < 1.0e-10) return interp1(t.Eg[i_E - 1], t.Eg[i_E], hw_1, hw_2, Ele);
-    return interp5t(t.Eg[i_E - 1], t.Eg[i_E], hw_1, hw_2, t.lEg[i_E - 1], t.lEg[i_E], m_log(hw_1), m_log(hw_2), Ele, lE);
+    return interp5t(t.Eg[i_E - 1], t.Eg[i_E], hw_1, hw_2, t.lEg[i_E - 1], t.lEg[i_E], lhw_1, lhw_2, Ele, lE);
 }
 TRK_HD Csr csr_eid(const DevP &p, int shell) { return Csr{p.ei_E, p.lei_E, p.n_ei, p.eid_off + (size_t)shell * p.n_ei, p.eid_hw, p.eid_L, p.leid_hw, p.leid_L}; }
 TRK_HD Csr csr_eed(const DevP &p) { return Csr{p.ee_E, p.lee_E, p.n_ee, p.eed_off, p.eed_hw, p.eed_L, p.leed_hw, p.leed_L}; }
@@ -456,14 +480,17 @@ TRK_HD void angles_lattice(const DevP &p, Rec &r, double E, double W, double M_e
     phi = 2.0 * TRK_PI * RN2;
 }
 // New_Angles_both, Monte_Carlo.f90:1328-1360 (not a rotation; kept as is)
-TRK_HDN void new_angles(double phi0, double theta0, double theta, double psi, double &phi1, double &theta1) {
-    phi1 = phi0 + theta * m_cos(theta0) * m_sin(psi);
-    theta1 = theta0 + theta * m_cos(psi);
+// (cos_theta0 = m_cos(theta0): the event handlers have it already from the position update)
+TRK_HDN void new_angles_c(double phi0, double theta0, double cos_theta0, double theta, double psi, double &phi1, double &theta1) {
+    const SinCos ps = m_sincos(psi);
+    phi1 = phi0 + theta * cos_theta0 * ps.s;
+    theta1 = theta0 + theta * ps.c;
     while (theta1 < 0.0) { theta1 = fabs(theta1); phi1 = phi1 + TRK_PI; }
     while (theta1 > TRK_PI) { theta1 = 2.0 * TRK_PI - theta1; phi1 = phi1 - TRK_PI; }
     if (phi1 > 2.0 * TRK_PI) phi1 = phi1 - floor(phi1 / (2.0 * TRK_PI)) * 2.0 * TRK_PI;
     if (phi1 < 0.0) phi1 = phi1 + ceil(fabs(phi1) / (2.0 * TRK_PI)) * 2.0 * TRK_PI;
 }
+TRK_HD void new_angles(double phi0, double theta0, double theta, double psi, double &phi1, double &theta1) { new_angles_c(phi0, theta0, m_cos(theta0), theta, psi, phi1, theta1); }
 // Update_holes_angles_SHI, :1132-1140: isotropic in ANGLE (theta uniform), as the reference
 TRK_HD void random_angles(const DevP &p, Rec &r, double &theta, double &phi) {
     double RN = rn(p, r); theta = TRK_PI * RN;
@@ -513,10 +540,10 @@ TRK_HDN void hole_parameters(const DevP &p, Rec &st, Rec &h, double Eh, double E
             Cache k;
             cache_vbhole(p, h.Ehkin, k);
             if (kout) *kout = k;
-            double HIMFP = k.imfp;
-            double HEMFP = (Ehkin_prev == (Eh - p.Egap)) ? 1.0e30 : k.emfp;
+            // 1/HIMFP + 1/HEMFP with HEMFP = 1e30 if the hole's energy did not change (:746-747)
+            const double iHEMFP = (Ehkin_prev == (Eh - p.Egap)) ? (1.0 / 1.0e30) : k.iemfp;
             double RN = rn(p, st);
-            double MFP_tot = m_div(-m_log(RN), m_div(1.0, HIMFP) + m_div(1.0, HEMFP));
+            double MFP_tot = m_div(-m_log(RN), k.iimfp + iHEMFP);
             h.tn = next_time(h.t0, vel_hole(h), MFP_tot);
             h.L = MFP_tot;
         } else { h.L = 1.0e30; h.tn = 1.0e30; }
@@ -661,7 +688,8 @@ TRK_HD void snapshot_electron(C &c, const Rec &e, int i) {
     double L0 = 0.0, theta0 = 0.0, phi0 = 0.0;
     if (e.E > cut) { L0 = vel_electron(e.E) * (tim - e.t0) * 1.0e-5; if (L0 < 0.0) L0 = 0.0; theta0 = e.theta; phi0 = e.phi; }
     double st = m_sin(theta0);
-    double X = e.X + L0 * st * m_sin(phi0), Y = e.Y + L0 * st * m_cos(phi0);
+    const SinCos sp = m_sincos(phi0);
+    double X = e.X + L0 * st * sp.s, Y = e.Y + L0 * st * sp.c;
     double R = sqrt(X * X + Y * Y);
     int j = find_1d(p.out_R, p.n_r, R);
     c.tally(TRK3_OUT_NE, (i - 1) + (int64_t)p.Nt * (j - 1), p.out_V[j - 1]);
@@ -693,7 +721,8 @@ TRK_HD void snapshot_hole(C &c, const Rec &h, int i) {
     if (h.Mass < 1.0e3 && h.Ehkin > cut) {
         double L0 = vel_hole(h) * (tim - h.t0) * 1.0e-5; if (L0 < 0.0) L0 = 0.0;
         double st = m_sin(h.theta);
-        Xh = h.X + L0 * st * m_sin(h.phi); Yh = h.Y + L0 * st * m_cos(h.phi);
+        const SinCos sp = m_sincos(h.phi);
+        Xh = h.X + L0 * st * sp.s; Yh = h.Y + L0 * st * sp.c;
         double xx = h.theta / TRK_PI * 180.0;
         int jt = (xx < 1.0) ? 1 : ((xx >= 180.0) ? 180 : (int)floor(xx) + 1);
         c.add_u32(p.it.th_h, base * TRK3_NTHETA + (jt - 1));
@@ -723,7 +752,8 @@ TRK_HD void snapshot_photon(C &c, const Rec &ph, int i) {
     const size_t base = (size_t)il * p.Nt + (i - 1);
     double L0 = TRK_CVEL * (tim - ph.t0) * 1.0e-5; if (L0 < 0.0) L0 = 0.0;
     double st = m_sin(ph.theta);
-    double X = ph.X + L0 * st * m_sin(ph.phi), Y = ph.Y + L0 * st * m_cos(ph.phi);
+    const SinCos sp = m_sincos(ph.phi);
+    double X = ph.X + L0 * st * sp.s, Y = ph.Y + L0 * st * sp.c;
     double R = sqrt(X * X + Y * Y);
     int j = find_1d(p.out_R, p.n_r, R);
     c.tally(TRK3_OUT_NPHOT, (i - 1) + (int64_t)p.Nt * (j - 1), p.out_V[j - 1]);
@@ -813,15 +843,16 @@ TRK_HD void electron_ion_emit(C &c, const IonEvent &ev) {
 // channel only, for kernels whose warps are uniform in the event type (the caller has evaluated the roulette with
 // electron_roulette_inelastic).
 enum EventMode { EV_ANY = 0, EV_ELASTIC = 1, EV_INELASTIC = 2 };
-TRK_HD bool electron_roulette_inelastic(const Cache &k, double RN) { const double ii = m_div(1.0, k.imfp); return RN * (ii + m_div(1.0, k.emfp)) < ii; }
+TRK_HD bool electron_roulette_inelastic(const Cache &k, double RN) { const double ii = k.iimfp; return RN * (ii + k.iemfp) < ii; }
 template <int MODE, class C>
 TRK_HD void electron_event_t(C &c, Rec &e, int iv, Cache &k, double RN) {
     const DevP &p = c.p;
     const double Eel = e.E;
     double IMFP = k.imfp, EMFP = k.emfp;                          // :2298-2299, already looked up for this energy
     const double L = e.L, theta0 = e.theta, phi0 = e.phi;
-    const double st0 = m_sin(theta0);
-    const double X = e.X + L * st0 * m_sin(phi0), Y = e.Y + L * st0 * m_cos(phi0), Z = e.Z + L * m_cos(theta0);
+    const SinCos sc_t = m_sincos(theta0), sc_p = m_sincos(phi0);
+    const double st0 = sc_t.s;
+    const double X = e.X + L * st0 * sc_p.s, Y = e.Y + L * st0 * sc_p.c, Z = e.Z + L * sc_t.c;
     const double t_ev = e.tn;
     double dE, theta, phi;
     if (MODE == EV_INELASTIC || (MODE == EV_ANY && electron_roulette_inelastic(k, RN))) {     // inelastic: impact ionisation
@@ -847,11 +878,10 @@ TRK_HD void electron_event_t(C &c, Rec &e, int iv, Cache &k, double RN) {
         deposit_lattice(c, e, iv, X, Y, dE);
     }
     cache_electron(p, Eel - dE, k);                               // :2449-2450, kept for the next collision
-    IMFP = k.imfp; EMFP = k.emfp;
     RN = rn(p, e);
-    double MFP_tot = m_div(-m_log(RN), m_div(1.0, IMFP) + m_div(1.0, EMFP));
+    double MFP_tot = m_div(-m_log(RN), k.iimfp + k.iemfp);
     double phi1, theta1;
-    new_angles(phi0, theta0, theta, phi, phi1, theta1);
+    new_angles_c(phi0, theta0, sc_t.c, theta, phi, phi1, theta1);
     e.E = Eel - dE; e.t0 = t_ev; e.X = X; e.Y = Y; e.Z = Z; e.L = MFP_tot; e.theta = theta1; e.phi = phi1;
     e.tn = next_time(e.t0, vel_electron(e.E), MFP_tot);
     if (e.E < p.cut_off) e.tn = 1.0e20;
@@ -880,15 +910,16 @@ TRK_HD void check_hole_level(const DevP &p, double Eel, double &dE, double &Ehol
 
 // Hole_Monte_Carlo, valence-band branch, Monte_Carlo.f90:2560-2738.  RN = first draw (channel roulette, :2582); MODE as
 // for electrons.  Holes below DevP::h_cold have a total inelastic MFP >= 1e16 and can never ionise (needs HIMFP < 1e15).
-TRK_HD bool vbhole_roulette_inelastic(const Cache &k, double RN) { const double ii = m_div(1.0, k.imfp); return RN * (ii + m_div(1.0, k.emfp)) < ii && k.imfp < 1e15; }
+TRK_HD bool vbhole_roulette_inelastic(const Cache &k, double RN) { const double ii = k.iimfp; return RN * (ii + k.iemfp) < ii && k.imfp < 1e15; }
 template <int MODE, class C>
 TRK_HD void vbhole_event_t(C &c, Rec &h, int iv, Cache &k, double RN) {
     const DevP &p = c.p;
     const double Eel = h.Ehkin;
     double HIMFP = k.imfp, HEMFP = k.emfp;                        // :2579-2580
     const double L = h.L, theta0 = h.theta, phi0 = h.phi;
-    const double st0 = m_sin(theta0);
-    const double X = h.X + L * st0 * m_sin(phi0), Y = h.Y + L * st0 * m_cos(phi0), Z = h.Z + L * m_cos(theta0);
+    const SinCos sc_t = m_sincos(theta0), sc_p = m_sincos(phi0);
+    const double st0 = sc_t.s;
+    const double X = h.X + L * st0 * sc_p.s, Y = h.Y + L * st0 * sc_p.c, Z = h.Z + L * sc_t.c;
     const double t_ev = h.tn;
     double dE, Ehole, htheta1, hphi1;
     if (MODE == EV_INELASTIC || (MODE == EV_ANY && vbhole_roulette_inelastic(k, RN))) {
@@ -915,7 +946,7 @@ TRK_HD void vbhole_event_t(C &c, Rec &h, int iv, Cache &k, double RN) {
         double MFP_tot = m_div(-m_log(RN), m_div(1.0, IMFP) + m_div(1.0, EMFP));
         RN = rn(p, h);                                           // sic (:2611): drawn and discarded
         double phi1, theta1;
-        new_angles(phi0, theta0, htheta, hphi, phi1, theta1);
+        new_angles_c(phi0, theta0, sc_t.c, htheta, hphi, phi1, theta1);
         Rec e;
         e.E = dE_cur; e.Ehkin = 0.0; e.Mass = 1.0; e.t0 = t_ev; e.X = X; e.Y = Y; e.Z = Z; e.L = MFP_tot; e.theta = theta1; e.phi = phi1;
         e.tn = next_time(t_ev, vel_electron(dE_cur), MFP_tot);
@@ -934,7 +965,7 @@ TRK_HD void vbhole_event_t(C &c, Rec &h, int iv, Cache &k, double RN) {
         deposit_lattice(c, h, iv, X, Y, dE);
     }
     double hphi2, htheta2;
-    new_angles(phi0, theta0, htheta1, hphi1, hphi2, htheta2);
+    new_angles_c(phi0, theta0, sc_t.c, htheta1, hphi1, hphi2, htheta2);
     h.t0 = t_ev; h.X = X; h.Y = Y; h.Z = Z; h.theta = htheta2; h.phi = hphi2;
     hole_parameters(p, h, h, Ehole + p.Egap, Eel, &k);
     if (h.Ehkin < -1.0e-9 || trk_isnan(h.Ehkin)) c.error(TRK3_ERR_20);
@@ -1060,14 +1091,15 @@ TRK_HD void photon_event(C &c, Rec &ph) {
     c.event(TRK3_EV_PHOTON);
     event_begin(ph);
     const double Eel = ph.E, L = ph.L, theta0 = ph.theta, phi0 = ph.phi, t_ev = ph.tn;
-    const double st0 = m_sin(theta0);
-    const double X = ph.X + L * st0 * m_sin(phi0), Y = ph.Y + L * st0 * m_cos(phi0), Z = ph.Z + L * m_cos(theta0);
+    const SinCos sc_t = m_sincos(theta0), sc_p = m_sincos(phi0);
+    const double st0 = sc_t.s;
+    const double X = ph.X + L * st0 * sc_p.s, Y = ph.Y + L * st0 * sc_p.c, Z = ph.Z + L * sc_t.c;
     int n_E;
     int shell = which_shell(p, ph, tab_ph_L(p), Eel, m_log(Eel), n_E);
     uint64_t id_e = child_id(p, ph, 1), id_h = child_id(p, ph, 2);
     double dE_cur = electron_receives_E(c, ph, Eel, shell);
     double phi1, theta1;
-    new_angles(phi0, theta0, TRK_PI / 2.0, 0.0, phi1, theta1);
+    new_angles_c(phi0, theta0, sc_t.c, TRK_PI / 2.0, 0.0, phi1, theta1);
     emit_electron(c, ph, id_e, dE_cur, t_ev, X, Y, Z, theta1, phi1, TRK3_ERR_50);
     emit_hole(c, ph, id_h, shell, Eel - dE_cur, t_ev, X, Y, Z, TRK3_ERR_51);
     ph.E = 0.0; ph.t0 = 1.0e27; ph.tn = 1.0e27;
