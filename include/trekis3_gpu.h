@@ -237,6 +237,40 @@ const trk3_tally_layout *trk3_mc_layout(const trk3_engine *eng);
 const char *trk3_mc_last_error(const trk3_engine *eng);
 void trk3_mc_destroy(trk3_engine *eng);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * GPU evaluator of the table builder's integrands.  The reference builds its mean-free-path and
+ * differential cross-section tables by nested Simpson integrations (TotIMFP Cross_sections.f90:881-1050, Tot_EMFP
+ * :2966-3139, SHI_TotIMFP :2452-2597): an outer loop over the transferred energy hw whose every step needs the
+ * q-integral of the loss function at two new points (Diff_cross_section :2217, SHI_Diff_cross_section :2683,
+ * Diff_cross_section_phonon :3142).  The outer loops' control flow does not depend on the integrand, so the host builder
+ * (libtrekis3_host.so) first records every (task, hw) it will ask for, has them all evaluated at once -- by this entry
+ * point, one GPU thread per request -- and then replays the outer loops with the values: same operations in the same
+ * order, identical tables.  A "task" is one outer integration: all its requests share these parameters. */
+enum { TRK3_DCS_INELASTIC = 0, TRK3_DCS_PHONON = 1, TRK3_DCS_SHI = 2 };
+typedef struct trk3_dcs_task {
+    int32_t type;          /* TRK3_DCS_* */
+    int32_t set;           /* oscillator set (CDF shell; the phonon CDF is the last set) */
+    double Ee;             /* energy of the incident particle [eV] */
+    double Mass;           /* its mass [m_e] (electrons 1, holes from the DOS) */
+    double p1, p2, p3;     /* PHONON: mean target atom mass [kg], target temperature [K], pref;  SHI: ion mass [kg], Emax [eV] */
+} trk3_dcs_task;
+typedef struct trk3_dcs_ctx {
+    const double *osc_E0, *osc_A, *osc_G;   /* oscillators of all sets, concatenated (type CDF, Objects.f90:211-217) */
+    const int32_t *osc_off;                 /* set s = [osc_off[s], osc_off[s+1]) */
+    int32_t n_sets;
+    const double *k, *effm; int32_t n_k;    /* k-vector and effective mass on the DOS grid (Objects.f90:111-123) */
+    int32_t mass_from_dos;                  /* El_eff_mass == 0: mass from the DOS (Imewq :428-434) */
+    double El_eff_mass;
+    int32_t kind_DR;                        /* dispersion relation of the oscillators */
+    double v_f, temp;
+} trk3_dcs_ctx;
+/* out[i] = the q-integral of request i = (tasks[task_of[i]], hw[i]).  All pointers are host memory.  Returns TRK3_OK or
+ * a negative error (no CUDA device: there is no CPU fallback in this library). */
+int trk3_dcs_eval(const trk3_dcs_ctx *ctx, const trk3_dcs_task *tasks, int64_t n_tasks,
+                  const double *hw, const int32_t *task_of, int64_t n, double *out);
+/* device time [ms] and number of requests of the calls since the last reset (reset != 0 clears them) */
+int trk3_dcs_stats(double *device_ms, int64_t *requests, int reset);
+
 /* Library identity, used by tests to prove the CUDA library (not a fallback) is loaded. */
 const char *trk3_gpu_version(void);
 

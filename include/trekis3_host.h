@@ -25,6 +25,14 @@ void trk3h_free(trk3h_case *c);
 /* Build all MFP / differential cross-section tables on the host (OpenMP over grid points).
  * threads<=0: all cores.  shi_window_only!=0: only the SHI-grid points the ion can visit. */
 int trk3h_build_tables(trk3h_case *c, int threads, int shi_window_only, int verbose, char *err, int errlen);
+/* Evaluator of the integrands for the NEXT trk3h_build_tables calls (see trk3_dcs_eval in trekis3_gpu.h, whose address
+ * is what a caller passes here; trk3h_dcs_eval_host is the same interface evaluated by the host threads, used by the CPU
+ * tests of the record / replay machinery).  NULL: the builder integrates directly, point by point, on the host. */
+typedef int (*trk3_dcs_eval_fn)(const trk3_dcs_ctx *ctx, const trk3_dcs_task *tasks, int64_t n_tasks,
+                                const double *hw, const int32_t *task_of, int64_t n, double *out);
+void trk3h_set_dcs_evaluator(trk3_dcs_eval_fn fn);
+int trk3h_dcs_eval_host(const trk3_dcs_ctx *ctx, const trk3_dcs_task *tasks, int64_t n_tasks,
+                        const double *hw, const int32_t *task_of, int64_t n, double *out);
 int trk3h_save_tables(trk3h_case *c, const char *path, char *err, int errlen);
 int trk3h_load_tables(trk3h_case *c, const char *path, char *err, int errlen);
 

@@ -246,3 +246,26 @@ def test_c5_high_statistics_sweep_composes(case_c1):
     m = np.ones(lay.total, bool); m[lay.off[i]: lay.off[i] + lay.len[i]] = False
     assert sw["total_events"] == sa["total_events"] + sb["total_events"]
     assert rel_close((a + b)[m], whole[m], 1e-9)
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C4"])
+def test_gpu_table_builder_gives_the_host_tables(tmp_path, cfg):
+    """all q-integrals of the table builder evaluated on the GPU (trk3_dcs_eval).  BASELINE's bar for the
+    tables is 1e-12 relative; the GPU kernel shares its integrands with the host builder and is compiled without
+    fused multiply-adds, so the tables are expected to be identical, and are checked to be."""
+    host = tk.Case.load(tk.make_run_dir(str(tmp_path / "h"), cfg)); host.build_tables(shi_window_only=True)
+    gpu = tk.Case.load(tk.make_run_dir(str(tmp_path / "g"), cfg)); gpu.build_tables(shi_window_only=True, evaluator="gpu")
+    assert tk.gpu_library_loaded()
+    th, tg = host.table_arrays(), gpu.table_arrays()
+    worst = 0.0
+    for k in th:
+        a, b = th[k], tg[k]
+        assert a.shape == b.shape, k
+        if a.dtype.kind != "f":
+            assert np.array_equal(a, b), k
+            continue
+        den = np.maximum(np.abs(a), np.abs(b)); den[den == 0] = 1.0
+        rel = float(np.max(np.abs(a - b) / den)) if a.size else 0.0
+        worst = max(worst, rel)
+        assert rel <= 1e-12, (k, rel)
+    print(f"{cfg}: worst relative difference GPU vs host tables {worst:.3e}")

@@ -235,3 +235,31 @@ def test_unsupported_inputs_are_reported_not_guessed(tmp_path):
     d = tk.make_run_dir(str(tmp_path / "r3"), ("NoSuchMaterial", 54, 167.0, 0, 10))
     with pytest.raises(RuntimeError, match="not found"):
         tk.Case.load(d)
+
+
+def _fresh_case(tmp_path, cfg):
+    return tk.Case.load(tk.make_run_dir(str(tmp_path / f"run_{cfg}"), cfg))
+
+
+def test_record_replay_builder_is_bit_identical_to_the_direct_one(tmp_path):
+    """the builder can hand all q-integrals of the loss function to an evaluator (the GPU:
+    trk3_dcs_eval).  The machinery -- record the requests, evaluate them in one go, replay the outer loops -- is tested
+    here with the host threads as the evaluator: every table must come out bit for bit as in the direct build."""
+    a = _fresh_case(tmp_path, "C1"); a.build_tables(shi_window_only=True)
+    b = _fresh_case(tmp_path, "C1"); b.build_tables(shi_window_only=True, evaluator="host")
+    ta, tb = a.table_arrays(), b.table_arrays()
+    assert ta.keys() == tb.keys()
+    n = 0
+    for k in ta:
+        assert np.array_equal(ta[k], tb[k]), k
+        n += ta[k].size
+    assert n > 100000
+
+
+def test_gpu_evaluator_fails_loudly_without_a_gpu(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    c = _fresh_case(tmp_path, "C1")
+    with pytest.raises(RuntimeError, match="evaluator|CUDA"):
+        c.build_tables(shi_window_only=True, evaluator="gpu")

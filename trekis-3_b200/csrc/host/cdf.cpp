@@ -6,6 +6,7 @@
 // Loop orders and expression shapes follow the Fortran so that a reference build and this
 // builder agree to rounding (target 1e-12 relative, BASELINE.json north_star).
 #include "trk3_host.hpp"
+#include "../common/trk3_dcs.h"
 #include <algorithm>
 #include <complex>
 #include <cstdio>
@@ -94,43 +95,42 @@ Ctx make_ctx(const Case &c) {
         if (c.atoms[0].Ip.back() < 0.2) { x.k = &c.dos.k_inv; x.effm = &c.dos.Eff_m_inv; }
         else { x.k = &c.dos.k; x.effm = &c.dos.Eff_m; }
     }
+    // flattened view for the shared integrands (csrc/common/trk3_dcs.h): oscillator sets in (atom, shell) order, phonon CDF last
+    auto flat = std::make_shared<CtxFlat>();
+    flat->off.push_back(0);
+    auto add = [&](const CDFosc &o) {
+        flat->E0.insert(flat->E0.end(), o.E0.begin(), o.E0.end());
+        flat->A.insert(flat->A.end(), o.A.begin(), o.A.end());
+        flat->G.insert(flat->G.end(), o.Gamma.begin(), o.Gamma.end());
+        flat->off.push_back((int32_t)flat->E0.size());
+    };
+    x.set0.clear();
+    int nset = 0;
+    for (auto &a : c.atoms) { x.set0.push_back(nset); for (int sh = 0; sh < a.nshl(); ++sh) { add(sh < (int)a.Ritchi.size() ? a.Ritchi[sh] : CDFosc{}); ++nset; } }
+    add(c.CDF_Phonon); x.set_phonon = nset++;
+    trk3_dcs_ctx &d = flat->d;
+    d.osc_E0 = flat->E0.data(); d.osc_A = flat->A.data(); d.osc_G = flat->G.data(); d.osc_off = flat->off.data(); d.n_sets = nset;
+    d.k = x.k ? x.k->data() : nullptr; d.effm = x.effm ? x.effm->data() : nullptr; d.n_k = x.k ? (int32_t)x.k->size() : 0;
+    d.mass_from_dos = x.mass_from_dos ? 1 : 0; d.El_eff_mass = c.Matter.El_eff_mass;
+    d.kind_DR = c.numpar.kind_of_DR; d.v_f = c.Matter.v_f; d.temp = c.Matter.temp;
+    x.flat = flat;
     return x;
 }
 
-namespace {
-const double SQRT_GE = std::sqrt(g_e);
-
-// Imewq for electrons/holes/SHI on shell `o` (Cross_sections.f90:397-486 with Extend_E0_to_finite_q :346-393).
-// The effective-mass lookup depends only on q and is hoisted out of the oscillator loop (same arithmetic).
-inline double imewq(const Ctx &x, const CDFosc &o, double hw, double dq) {
-    const Solid &M = x.c->Matter;
-    double hq2 = g_h * g_h * dq * dq;
-    double Mass;
-    if (x.mass_from_dos) {
-        double qlim = std::fabs(dq) * SQRT_GE;
-        const std::vector<double> &k = *x.k;
-        if (qlim <= k.back()) { int j = find_monoton_1d(k.data(), (int)k.size(), qlim); Mass = (*x.effm)[j - 1]; }
-        else Mass = 1.0;
-    } else if (M.El_eff_mass > 0) Mass = M.El_eff_mass;
-    else Mass = 1.0;
-    double sqq = hq2 / (2.0 * Mass * g_me);
-    int kind_DR = x.c->numpar.kind_of_DR;
-    double dE2 = hw * hw;
-    double ImE = 0.0;
-    const size_t n = o.A.size();
-    for (size_t i = 0; i < n; ++i) {
-        double E = o.E0[i], Gamma = o.Gamma[i], E0, Gamma1;
-        switch (kind_DR) {
-        case 2: E0 = std::sqrt(E * E + M.v_f * M.v_f * hq2 * 0.3333333333333 + sqq * sqq); Gamma1 = Gamma; break;
-        case 3: E0 = std::pow(std::pow(E, 0.666666666666) + std::pow(sqq, 0.666666666666), 1.5); Gamma1 = std::sqrt(Gamma * Gamma + sqq * sqq); break;
-        default: E0 = E + sqq; Gamma1 = Gamma; break;
-        }
-        double E02 = E0 * E0;
-        ImE = ImE + o.A[i] * Gamma1 * hw / ((dE2 - E02) * (dE2 - E02) + Gamma1 * Gamma1 * dE2);
+// One q-integral.  Direct mode: evaluated here.  Record mode: the request is noted and 0 returned (the outer loops never
+// branch on the value).  Replay mode: the value the evaluator produced for this request.
+double dcs_request(const Ctx &x, const trk3_dcs_task &t, double hw) {
+    DcsBatch *b = x.batch;
+    if (!b || b->mode == DcsBatch::DIRECT) return trk3dcs::eval_request(x.flat->d, t, hw);
+    if (b->mode == DcsBatch::RECORD) {
+        if (b->hw.empty()) b->task = t;
+        b->hw.push_back(hw);
+        return 0.0;
     }
-    return ImE;
+    return b->val[b->cursor++];
 }
 
+namespace {
 inline double imewq_photon(const CDFosc &o, double hw) {   // Loss_func with photon=.true.: q = 0
     double dE2 = hw * hw, ImE = 0.0;
     for (size_t i = 0; i < o.A.size(); ++i) {
@@ -139,88 +139,18 @@ inline double imewq_photon(const CDFosc &o, double hw) {   // Loss_func with pho
     }
     return ImE;
 }
-
-inline double imewq_phonon(const CDFosc &o, double hw, double hq, double Mtarget) {   // :3409-3433, Extend with Mtarget
-    double hq2 = g_h * g_h * hq * hq;
-    double dE2 = hw * hw, ImE = 0.0;
-    for (size_t i = 0; i < o.A.size(); ++i) {
-        double E0 = o.E0[i] + hq2 / (2.0 * Mtarget);
-        double G = o.Gamma[i], E02 = E0 * E0;
-        ImE = ImE + o.A[i] * G * hw / ((dE2 - E02) * (dE2 - E02) + G * G * dE2);
-    }
-    return ImE;
+// the three q-integrals (csrc/common/trk3_dcs.h) as requests of the current outer integration
+inline double diff_cross_section(const Ctx &x, int set, double Ee, double dE, double Mass) {
+    trk3_dcs_task t{TRK3_DCS_INELASTIC, set, Ee, Mass, 0.0, 0.0, 0.0};
+    return dcs_request(x, t, dE);
 }
-
-// Diff_cross_section, Cross_sections.f90:2217-2282
-double diff_cross_section(const Ctx &x, const CDFosc &o, double Ee, double dE, double Mass) {
-    double pre = std::sqrt(2.0 * Mass * g_me) / g_h;
-    double qmin, qmax;
-    if (dE > Ee) { qmin = pre * std::sqrt(Ee); qmax = pre * std::sqrt(Ee); }
-    else { qmin = pre * (std::sqrt(Ee) - std::sqrt(Ee - dE)); qmax = pre * (std::sqrt(Ee) + std::sqrt(Ee - dE)); }
-    double dLs = 0.0, hq = qmin, dLs0 = 0.0;
-    const double n = 100.0;                       // m_N_p_grid_SHI
-    while (hq < qmax) {
-        double dq = hq / n;
-        double a = hq + dq / 2.0;
-        double temp1 = imewq(x, o, dE, a);
-        double b = hq + dq;
-        double dL = imewq(x, o, dE, b);
-        dLs = dLs + dq / 6.0 * (dLs0 + 4.0 * temp1 + dL) / hq;
-        dLs0 = dL;
-        hq = hq + dq;
-    }
-    double T_fact = 1.0;
-    if (x.c->Matter.temp > 0.0) T_fact = 1.0 / (1.0 - std::exp(-dE / x.c->Matter.temp * g_kb));
-    return 1.0 / (g_Pi * g_a0 * Ee) * dLs * T_fact;
+inline double shi_diff_cross_section(const Ctx &x, int set, double Ee, double MSHI, double Emax, double hw) {
+    trk3_dcs_task t{TRK3_DCS_SHI, set, Ee, 1.0, MSHI, Emax, 0.0};
+    return dcs_request(x, t, hw);
 }
-
-// SHI_Diff_cross_section, Cross_sections.f90:2683-2744
-double shi_diff_cross_section(const Ctx &x, const CDFosc &o, double Ee, double MSHI, double Emax, double hw) {
-    double qmin = (Ee > 0.0) ? hw / g_h / std::sqrt(2.0 * Ee / MSHI) : 0.0;
-    if (!(Emax > 0.0)) return 0.0;
-    double qmax = std::sqrt(2.0 * g_me) / g_h * std::sqrt(Emax);
-    double dLs = 0.0, hq = qmin, dLs0 = 0.0;
-    const double n = 100.0;
-    while (hq < qmax) {
-        double dq = hq / n;
-        double a = hq + dq / 2.0;
-        double temp1 = imewq(x, o, hw, a);
-        double b = hq + dq;
-        double dL = imewq(x, o, hw, b);
-        dLs = dLs + dq / 6.0 * (dLs0 + 4.0 * temp1 + dL) / hq;
-        dLs0 = dL;
-        hq = hq + dq;
-    }
-    double T_fact = 1.0;
-    if (x.c->Matter.temp > 0.0) T_fact = 1.0 / (1.0 - std::exp(-hw / x.c->Matter.temp * g_kb));
-    return dLs * T_fact;
-}
-
-// Diff_cross_section_phonon, Cross_sections.f90:3142-3300 (CDF_elast_Zeff 0/1: screening = 1)
-double diff_cross_section_phonon(const Ctx &x, double Ee, double dE, double Mtarget, double Mass, double Ttarget, double pref) {
-    const double eps = 1.0e-12;
-    double pre = std::sqrt(2.0 * Mass * g_me) / g_h;
-    double qmin;
-    if (std::fabs(dE) < eps) return 1.31e30;
-    else if (dE > (Ee - eps)) qmin = pre * std::sqrt(Ee);
-    else qmin = pre * (std::sqrt(Ee) - std::sqrt(std::fabs(Ee - dE)));
-    double qmax = pref * pre * (std::sqrt(Ee) + std::sqrt(std::fabs(Ee - dE)));
-    const CDFosc &o = x.c->CDF_Phonon;
-    double dLs = 0.0, hq = qmin, dLs0 = 0.0;
-    const double n = 100.0;
-    while (std::fabs(hq) < std::fabs(qmax)) {
-        double dq = hq / n;
-        double a = hq + dq / 2.0;
-        double temp1 = imewq_phonon(o, dE, a, Mtarget);
-        double b = hq + dq;
-        double dL = imewq_phonon(o, dE, b, Mtarget);
-        double Pot = 1.0 / hq;
-        dLs = dLs + dq / 6.0 * (dLs0 + 4.0 * temp1 + dL) * Pot;
-        dLs0 = dL;
-        hq = hq + dq;
-    }
-    if (Ttarget > 1.0e-6) return 1.0 / (g_Pi * g_a0 * Ee) * dLs / (1 - std::exp(-dE / Ttarget * g_kb));
-    return 1.0 / (g_Pi * g_a0 * Ee) * dLs;
+inline double diff_cross_section_phonon(const Ctx &x, double Ee, double dE, double Mtarget, double Mass, double Ttarget, double pref) {
+    trk3_dcs_task t{TRK3_DCS_PHONON, x.set_phonon, Ee, Mass, Mtarget, Ttarget, pref};
+    return dcs_request(x, t, dE);
 }
 
 // get_diff_CS_grid_size (new grid, both bounds present), Cross_sections.f90:1278-1343
@@ -294,13 +224,14 @@ void TotIMFP(const Ctx &x, double Ele, int Nat, int Nshl, int kind, double &Sigm
 
     std::vector<double> hw, cum;
     double E = Emin, Ltot1 = 0.0, ddEdx = 0.0;
-    double Ltot0 = diff_cross_section(x, o, Ele, E, Mass);
+    const int set = x.set0[Nat] + Nshl;
+    double Ltot0 = diff_cross_section(x, set, Ele, E, Mass);
     while (E <= Emax) {
         double dE = define_dE(1, n, E, true, E_low, true, E_high, 0.001);
         double a = E + dE / 2.0;
-        double temp1 = diff_cross_section(x, o, Ele, a, Mass);
+        double temp1 = diff_cross_section(x, set, Ele, a, Mass);
         double b = E + dE;
-        double dL = diff_cross_section(x, o, Ele, b, Mass);
+        double dL = diff_cross_section(x, set, Ele, b, Mass);
         double temp2 = dE / 6.0 * (Ltot0 + 4.0 * temp1 + dL);
         Ltot1 = Ltot1 + temp2;
         ddEdx = ddEdx + E * temp2;
@@ -491,16 +422,17 @@ void SHI_TotIMFP(const Ctx &x, Ion &shi, int Nat, int Nshl, double &Sigma, doubl
         dSedE->E.assign(k0, 0.0); dSedE->L.assign(k0, 0.0); dSedE->dEdx.assign(k0, 0.0);
     }
     double E = Emin, Ltot1 = 0.0, ddEdx = 0.0;
-    double Ltot0 = shi_diff_cross_section(x, o, Ele, MSHI, Emax, E);
+    const int set = x.set0[Nat] + Nshl;
+    double Ltot0 = shi_diff_cross_section(x, set, Ele, MSHI, Emax, E);
     size_t i = 0;
     while (E <= Emax) {
         ++i;
         if (dSedE && i > cap) break;
         double dE = define_dE(1, n, E, true, E_low, true, E_high, 0.001);
         double a = E + dE / 2.0;
-        double temp1 = shi_diff_cross_section(x, o, Ele, MSHI, Emax, a);
+        double temp1 = shi_diff_cross_section(x, set, Ele, MSHI, Emax, a);
         double b = E + dE;
-        double dL = shi_diff_cross_section(x, o, Ele, MSHI, Emax, b);
+        double dL = shi_diff_cross_section(x, set, Ele, MSHI, Emax, b);
         double temp2 = dE / 6.0 * (Ltot0 + 4.0 * temp1 + dL);
         Ltot1 = Ltot1 + temp2;
         ddEdx = ddEdx + dE / 6.0 * (E * Ltot0 + a * 4.0 * temp1 + b * dL);

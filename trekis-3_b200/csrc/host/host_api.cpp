@@ -1,9 +1,14 @@
 // host_api.cpp -- extern "C" surface of libtrekis3_host.so (include/trekis3_host.h).
 #include "../../../include/trekis3_host.h"
 #include "trk3_host.hpp"
+#include "../common/trk3_dcs.h"
+#include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <thread>
+#include <vector>
 
 using namespace trk3;
 
@@ -37,9 +42,34 @@ trk3h_case *trk3h_load(const char *dir, char *err, int errlen) {
 
 void trk3h_free(trk3h_case *c) { delete c; }
 
+static trk3_dcs_eval_fn g_dcs_evaluator = nullptr;
+void trk3h_set_dcs_evaluator(trk3_dcs_eval_fn fn) { g_dcs_evaluator = fn; }
+
+// the evaluator interface on the host threads (tests of the record / replay machinery without a GPU)
+int trk3h_dcs_eval_host(const trk3_dcs_ctx *ctx, const trk3_dcs_task *tasks, int64_t n_tasks, const double *hw, const int32_t *task_of, int64_t n, double *out) {
+    if (!ctx || !tasks || !hw || !task_of || !out || n < 0) return TRK3_E_INVALID;
+    int nth = (int)std::thread::hardware_concurrency(); if (nth < 1) nth = 1;
+    std::atomic<int64_t> next(0);
+    std::atomic<int> bad(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nth; ++t) th.emplace_back([&]() {
+        for (;;) {
+            const int64_t i0 = next.fetch_add(256);
+            if (i0 >= n) break;
+            for (int64_t i = i0; i < std::min<int64_t>(n, i0 + 256); ++i) {
+                if (task_of[i] < 0 || task_of[i] >= n_tasks) { bad = 1; continue; }
+                out[i] = trk3dcs::eval_request(*ctx, tasks[task_of[i]], hw[i]);
+            }
+        }
+    });
+    for (auto &t : th) t.join();
+    return bad ? TRK3_E_INVALID : TRK3_OK;
+}
+
 int trk3h_build_tables(trk3h_case *h, int threads, int shi_window_only, int verbose, char *err, int errlen) {
     if (!h) return TRK3_E_INVALID;
     BuildOptions o; o.threads = threads; o.shi_window_only = shi_window_only != 0; o.verbose = verbose != 0;
+    o.evaluator = g_dcs_evaluator;
     std::string e;
     if (!build_tables(h->c, o, e)) { set_err(err, errlen, e); return TRK3_E_INVALID; }
     h->packed = false;

@@ -26,6 +26,44 @@ void parallel_for(int n, int nth, const std::function<void(int)> &fn) {
     for (auto &t : th) t.join();
 }
 
+// The outer integrations of a table (one per task: grid point x shell), each calling body(t, ctx).  Without an evaluator
+// they run directly on the host threads.  With one (the GPU: trk3_dcs_eval) every task is first run in RECORD mode, which
+// only walks its outer loop and notes the q-integrals it needs, then all of them are evaluated in one go, and the tasks
+// are run again in REPLAY mode with the values (see dcs_request, cdf.cpp): same operations, same order, same result.
+bool run_integrations(const Ctx &x0, int n, int nth, trk3_dcs_eval_fn ev, std::string &err, const std::function<void(int, const Ctx &)> &body) {
+    if (!ev) { parallel_for(n, nth, [&](int t) { body(t, x0); }); return true; }
+    std::vector<DcsBatch> b((size_t)n);
+    parallel_for(n, nth, [&](int t) { Ctx x = x0; b[t].mode = DcsBatch::RECORD; x.batch = &b[t]; body(t, x); });
+    const size_t chunk_max = (size_t)8 << 20;             // requests per evaluator call (bounds the staging memory)
+    std::vector<std::vector<double>> val((size_t)n);
+    std::vector<trk3_dcs_task> tasks; std::vector<double> hw, out; std::vector<int32_t> task_of;
+    for (int t0 = 0; t0 < n;) {
+        tasks.clear(); hw.clear(); task_of.clear();
+        int t1 = t0;
+        while (t1 < n && (hw.empty() || hw.size() + b[t1].hw.size() <= chunk_max)) {
+            tasks.push_back(b[t1].task);
+            hw.insert(hw.end(), b[t1].hw.begin(), b[t1].hw.end());
+            task_of.insert(task_of.end(), b[t1].hw.size(), (int32_t)(t1 - t0));
+            ++t1;
+        }
+        out.assign(hw.size(), 0.0);
+        if (!hw.empty()) {
+            const int rc = ev(&x0.flat->d, tasks.data(), (int64_t)tasks.size(), hw.data(), task_of.data(), (int64_t)hw.size(), out.data());
+            if (rc != TRK3_OK) { err = "the evaluator of the table integrands failed (code " + std::to_string(rc) + ")"; return false; }
+        }
+        size_t o = 0;
+        for (int t = t0; t < t1; ++t) { val[t].assign(out.begin() + o, out.begin() + o + b[t].hw.size()); o += b[t].hw.size(); }
+        t0 = t1;
+    }
+    parallel_for(n, nth, [&](int t) {
+        Ctx x = x0;
+        b[t].mode = DcsBatch::REPLAY; b[t].val = val[t].data(); b[t].cursor = 0;
+        std::vector<double>().swap(b[t].hw);
+        x.batch = &b[t]; body(t, x);
+    });
+    return true;
+}
+
 // find_order_of_number_real, Analytical_IMFPs.f90:3077: number of decimal digits of ceiling(num)
 int find_order_of_number(double num) {
     char buf[64];
@@ -163,7 +201,7 @@ void radius_for_distributions(Case &c) {      // Sorting_output_data.f90:1403-14
 }
 
 bool build_tables(Case &c, const BuildOptions &opt, std::string &err) {
-    (void)err;
+    const trk3_dcs_eval_fn ev = opt.evaluator;
     int nth = opt.threads > 0 ? opt.threads : (int)std::thread::hardware_concurrency();
     if (nth < 1) nth = 1;
     get_single_pole(c);                                   // MAIN.f90:146
@@ -195,7 +233,7 @@ bool build_tables(Case &c, const BuildOptions &opt, std::string &err) {
         struct Task { int j, a, s; };
         std::vector<Task> tasks;
         for (int j : todo) for (int a = 0; a < Nat; ++a) for (int s = 0; s < c.atoms[a].nshl(); ++s) tasks.push_back({j, a, s});
-        parallel_for((int)tasks.size(), nth, [&](int t) {
+        if (!run_integrations(x, (int)tasks.size(), nth, ev, err, [&](int t, const Ctx &x) {
             Ion shi1 = c.SHI;
             shi1.E = grid[tasks[t].j];
             double IMFP, dEdx;
@@ -204,7 +242,7 @@ bool build_tables(Case &c, const BuildOptions &opt, std::string &err) {
             double L = (IMFP > 1.0e-10) ? 1.0 / IMFP : 1.0e28;     // :2644-2648
             if (L > 1e30) L = 1e30;                                 // :2682
             m.L[tasks[t].j] = L; m.dEdx[tasks[t].j] = dEdx;
-        });
+        })) return false;
     }
     equilibrium_charge_SHI(c.SHI, c.atoms);               // MAIN.f90:171
 
@@ -232,7 +270,7 @@ bool build_tables(Case &c, const BuildOptions &opt, std::string &err) {
         std::vector<Task> tasks;
         for (int i = 0; i < N; ++i) for (int a = 0; a < Nat; ++a) for (int s = 0; s < c.atoms[a].nshl(); ++s) tasks.push_back({i, a, s});
         if (opt.verbose) std::fprintf(stderr, "[trk3] %s inelastic table: %d points x %d shells\n", kind ? "hole" : "electron", N, c.n_shells());
-        parallel_for((int)tasks.size(), nth, [&](int t) {
+        if (!run_integrations(x, (int)tasks.size(), nth, ev, err, [&](int t, const Ctx &x) {
             const Task &k = tasks[t];
             DiffRow *row = nullptr;
             if (kind == 0) row = &c.EIdCS[k.a][k.s].row[k.i];
@@ -240,7 +278,7 @@ bool build_tables(Case &c, const BuildOptions &opt, std::string &err) {
             double S, dEdx;
             TotIMFP(x, grid[k.i], k.a, k.s, kind, S, dEdx, row);
             T[k.a][k.s].L[k.i] = S; T[k.a][k.s].dEdx[k.i] = dEdx;
-        });
+        })) return false;
         // elastic
         MFP &El = (kind == 0) ? c.Elastic_MFP : c.Elastic_Hole_MFP;
         DiffCS &Ed = (kind == 0) ? c.EEdCS : c.HEdCS;
@@ -248,11 +286,11 @@ bool build_tables(Case &c, const BuildOptions &opt, std::string &err) {
         Ed.E = gridE; Ed.row.assign(Ne, DiffRow{});
         if (opt.verbose) std::fprintf(stderr, "[trk3] %s elastic table: %d points\n", kind ? "hole" : "electron", Ne);
         if (c.numpar.kind_of_EMFP == 1 || c.numpar.kind_of_EMFP == 0) {
-            parallel_for(Ne, nth, [&](int i) {
+            if (!run_integrations(x, Ne, nth, ev, err, [&](int i, const Ctx &x) {
                 double S, dEdx;
                 Elastic_cross_section(x, gridE[i], kind, S, dEdx, (c.numpar.kind_of_EMFP == 1) ? &Ed.row[i] : nullptr);
                 El.L[i] = S; El.dEdx[i] = dEdx;
-            });
+            })) return false;
         } else {
             // kind_of_EMFP = -1: elastic scattering disabled (Analytical_IMFPs.f90 'No_elas'): infinite MFP
             for (int i = 0; i < Ne; ++i) { El.L[i] = 1.0e30; El.dEdx[i] = 0.0; }
@@ -280,11 +318,11 @@ bool build_tables(Case &c, const BuildOptions &opt, std::string &err) {
         struct Task { int a, s; };
         std::vector<Task> tasks;
         for (int a = 0; a < Nat; ++a) for (int s = 0; s < c.atoms[a].nshl(); ++s) tasks.push_back({a, s});
-        parallel_for((int)tasks.size(), nth, [&](int t) {
+        if (!run_integrations(x, (int)tasks.size(), nth, ev, err, [&](int t, const Ctx &x) {
             Ion shi1 = c.SHI;
             double S, dEdx;
             SHI_TotIMFP(x, shi1, tasks[t].a, tasks[t].s, S, dEdx, &c.diff_SHI_MFP[tasks[t].a][tasks[t].s]);
-        });
+        })) return false;
     }
     find_VB_numbers(c);
     radius_for_distributions(c);

@@ -8,9 +8,10 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
-#include "../../../include/trekis3_gpu.h"
+#include "../../../include/trekis3_host.h"
 
 namespace trk3 {
 
@@ -123,11 +124,30 @@ void set_default_numpar(NumPar &np);
 bool read_case(const std::string &dir, Case &c, std::string &err);
 
 // ---- physics of the table builder (cdf.cpp)
+struct CtxFlat {        // storage behind the trk3_dcs_ctx handed to the shared integrands / the GPU evaluator
+    std::vector<double> E0, A, G;
+    std::vector<int32_t> off;
+    trk3_dcs_ctx d{};
+};
+// Requests of ONE outer integration (TotIMFP / Tot_EMFP / SHI_TotIMFP call): see dcs_request in cdf.cpp
+struct DcsBatch {
+    enum { DIRECT = 0, RECORD = 1, REPLAY = 2 };
+    int mode = DIRECT;
+    trk3_dcs_task task{};
+    std::vector<double> hw;        // RECORD: transferred energies asked for, in call order
+    const double *val = nullptr;   // REPLAY: their values
+    size_t cursor = 0;
+};
 struct Ctx {            // immutable view used by the integrators
     const Case *c;
     const std::vector<double> *k = nullptr, *effm = nullptr;   // DOS (or inverted DOS for metals)
     bool mass_from_dos = false;
+    std::shared_ptr<CtxFlat> flat;          // oscillator sets flattened: set0[atom] + shell, phonon CDF = set_phonon
+    std::vector<int> set0;
+    int set_phonon = 0;
+    DcsBatch *batch = nullptr;              // null: integrate directly
 };
+double dcs_request(const Ctx &x, const trk3_dcs_task &t, double hw);
 Ctx make_ctx(const Case &c);
 void get_single_pole(Case &c);                                   // Cross_sections.f90:554
 void sumrules(const CDFosc &o, double &ksum, double &fsum, double x_min, double Omega);   // :728
@@ -148,6 +168,7 @@ struct BuildOptions {
     int threads = 0;              // 0 => all
     bool shi_window_only = false; // only the SHI grid points the MC can touch (test speed-up)
     bool verbose = false;
+    trk3_dcs_eval_fn evaluator = nullptr;   // of the integrands (trk3h_set_dcs_evaluator); null: integrate directly on the host
 };
 bool build_tables(Case &c, const BuildOptions &opt, std::string &err);     // MAIN.f90:146-247
 void find_VB_numbers(Case &c);                                             // Reading_files...:3252

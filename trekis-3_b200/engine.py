@@ -40,9 +40,17 @@ def _gpu():
         lib.trk3_mc_reload_tables.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Tables)]
         lib.trk3_mc_table_bytes.restype = C.c_uint64
         lib.trk3_mc_table_bytes.argtypes = [C.c_void_p]
+        lib.trk3_dcs_stats.argtypes = [PD, C.POINTER(C.c_int64), C.c_int]
         lib.trk3_gpu_version.restype = C.c_char_p
         _lib = lib
     return _lib
+
+
+def dcs_stats(reset=False):
+    """Device time [ms] and number of q-integrals evaluated by trk3_dcs_eval (the GPU table builder) so far."""
+    ms, n = C.c_double(0.0), C.c_int64(0)
+    _gpu().trk3_dcs_stats(C.byref(ms), C.byref(n), int(reset))
+    return ms.value, n.value
 
 
 def gpu_library_loaded():

@@ -24,6 +24,8 @@ def _host():
         lib.trk3h_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
         lib.trk3h_free.argtypes = [C.c_void_p]
         lib.trk3h_build_tables.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        lib.trk3h_set_dcs_evaluator.argtypes = [C.c_void_p]
+        lib.trk3h_set_dcs_evaluator.restype = None
         lib.trk3h_save_tables.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
         lib.trk3h_load_tables.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
         lib.trk3h_config.restype = C.POINTER(Config)
@@ -158,8 +160,13 @@ class Case:
         hsh.update(b"window" if shi_window_only else b"full")
         return hsh.hexdigest()[:20]
 
-    def build_tables(self, threads=0, shi_window_only=False, verbose=False, cache_dir=None):
-        """Build (or load from the binary cache) all MFP and differential cross-section tables."""
+    def build_tables(self, threads=0, shi_window_only=False, verbose=False, cache_dir=None, evaluator=None):
+        """Build (or load from the binary cache) all MFP and differential cross-section tables.
+
+        evaluator: who evaluates the q-integrals of the loss function (>99 % of the work): None = the host threads,
+        point by point, as the reference does; "gpu" = all of them at once by trk3_dcs_eval of libtrekis3_gpu.so
+        (raises without the CUDA library); "host" = the same record / evaluate / replay path with
+        the host threads as the evaluator (tests).  The tables are identical in all three cases."""
         lib = _host()
         err = C.create_string_buffer(1024)
         cache = None
@@ -170,7 +177,19 @@ class Case:
             if os.path.exists(cache):
                 if lib.trk3h_load_tables(self._h, os.fsencode(cache), err, 1024) == 0:
                     return self
-        rc = lib.trk3h_build_tables(self._h, threads, int(shi_window_only), int(verbose), err, 1024)
+        fn = None
+        if evaluator == "gpu":
+            from .engine import _gpu
+            fn = C.cast(_gpu().trk3_dcs_eval, C.c_void_p)
+        elif evaluator == "host":
+            fn = C.cast(lib.trk3h_dcs_eval_host, C.c_void_p)
+        elif evaluator is not None:
+            raise ValueError("evaluator must be None, 'host' or 'gpu'")
+        lib.trk3h_set_dcs_evaluator(fn)
+        try:
+            rc = lib.trk3h_build_tables(self._h, threads, int(shi_window_only), int(verbose), err, 1024)
+        finally:
+            lib.trk3h_set_dcs_evaluator(None)
         if rc != 0:
             raise RuntimeError("table build failed: " + err.value.decode(errors="replace"))
         if cache:
