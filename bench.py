@@ -186,6 +186,7 @@ def run_ours(args):
     events_total, launches, drift, errors = 0, 0, 0.0, {}
     ev_by_class = {}
     cold_ev = {"electron": 0, "vbhole": 0}
+    warm_ev = 0
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                            # L2 flush between timed iterations (untimed)
@@ -203,6 +204,7 @@ def run_ours(args):
             errors[n] = errors.get(n, 0) + v
         for n, v in st["cold_events"].items():
             cold_ev[n] += v
+        warm_ev += st["warm_events"]
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -258,7 +260,8 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
     B = tk.EVENT_BYTES
     class_bytes = {
-        "k_wave<electron,hot>": ev_by_class.get("el_inelastic", 0) * B["el_inelastic"] + (ev_by_class.get("el_elastic", 0) - cold_ev["electron"]) * B["el_elastic"],
+        "k_wave<electron,hot>": ev_by_class.get("el_inelastic", 0) * B["el_inelastic"] + (ev_by_class.get("el_elastic", 0) - cold_ev["electron"] - warm_ev) * B["el_elastic"],
+        "k_wave<electron,warm>": warm_ev * B["el_elastic"],
         "k_wave<vbhole,hot>": ev_by_class.get("vbh_inelastic", 0) * B["vbh_inelastic"] + (ev_by_class.get("vbh_elastic", 0) - cold_ev["vbhole"]) * B["vbh_elastic"],
         "k_wave<electron,cold>": cold_ev["electron"] * B["el_elastic"],
         "k_wave<vbhole,cold>": cold_ev["vbhole"] * B["vbh_elastic"],
@@ -282,8 +285,10 @@ def run_ours(args):
                 "per_kernel": {k: {"GB/s": (class_bytes[k] / (ktimes[k]["ms"] * 1e-3) / 1e9 if ktimes[k]["ms"] > 0 else 0.0),
                                    "ms": ktimes[k]["ms"], "launches": ktimes[k]["launches"]} for k in class_bytes},
                 "note": "algorithmic bytes = collisions x compulsory particle-state bytes (SURVEY.md 8d); histories stay in "
-                        "registers between collisions and tables are L1/L2-resident, so the kernels are bound by FP64 issue and "
-                        "instruction/latency chains (the dominant one by the longest delta-electron cascade), not by HBM"}
+                        "registers between collisions and tables are L1/L2-resident, so the kernels are bound by instruction "
+                        "issue/fetch (fp64 libm sequences, ~120 warp instructions per collision in the cold kernels) and, in the "
+                        "hot cascade, by warp divergence (5-7 lanes per instruction), not by HBM; the hot/warm/core-hole/photon "
+                        "kernels of one generation run on concurrent streams, so their class times overlap"}
 
     # ---- CPU baseline: oracle on the host cores, bounded sample of the same workload
     cpu = None
@@ -303,7 +308,7 @@ def run_ours(args):
                    "inputs": "shipped INPUT_CDF/INPUT_DOS files; radiative widths from data/INPUT_EADL/radiative_widths.dat "
                              "(approximate, EADL2023.ALL is not redistributable)"},
         "events_per_s": events_all / (ms * 1e-3), "events_per_s_per_gpu": events_all / (ms * 1e-3) / world,
-        "events_by_class": ev_by_class, "cold_events": cold_ev, "wall_s": t_wall,
+        "events_by_class": ev_by_class, "cold_events": cold_ev, "warm_events": warm_ev, "wall_s": t_wall,
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "trekis3_b200.do_Monte_Carlo(case) with host buffers: configuration + tables host->device, MC, tallies and "

@@ -39,7 +39,7 @@ __constant__ DevP c_p;
 #define Q_ELW (N_SPECIES + 4 + N_ECLASS - 1)      // warm electrons of the next generation (see DevP::e_warm)
 #define N_QUEUES (N_SPECIES + 5 + N_ECLASS - 1)
 struct QueueSet { Queue q[N_QUEUES]; };
-#define N_CLASSES (N_SPECIES + 4)     // timing classes: hot waves per species, k_shi, finalize, cold electrons (+ warm: same kernel), cold holes
+#define N_CLASSES (N_SPECIES + 5)     // timing classes: hot waves per species, k_shi, finalize, cold electrons, cold holes, warm electrons
 
 #define TRK_BLOCK_MAX 256          // compile-time upper bound of the wave-kernel block size (launch bounds)
 #ifndef TRK_MIN_BLOCKS
@@ -146,7 +146,7 @@ __device__ inline void block_prologue(double *s_tally, unsigned int *s_cnt, int 
     if (threadIdx.x < S_NCNT) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
 }
-__device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned int *s_cnt, int cold_species = -1) {
+__device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned int *s_cnt, int cold_species = -1, int warm = 0) {
     __syncthreads();
     if (s_tally) {
         // flush the private copy once per block (non-zero bins only)
@@ -163,7 +163,7 @@ __device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned i
     if (threadIdx.x < TRK3_N_EVENT_CLASSES) { unsigned v = s_cnt[S_EV + threadIdx.x]; if (v) atomicAdd(&p.events[threadIdx.x], (unsigned long long)v); }
     if (threadIdx.x == 0) {
         // collisions handled by the cold kernels (per species), for the per-kernel roofline
-        if (cold_species == SP_ELECTRON && s_cnt[S_EV + TRK3_EV_EL_ELAST]) atomicAdd(p.cnt_el + 2, (unsigned long long)s_cnt[S_EV + TRK3_EV_EL_ELAST]);
+        if (cold_species == SP_ELECTRON && s_cnt[S_EV + TRK3_EV_EL_ELAST]) atomicAdd(p.cnt_el + (warm ? 4 : 2), (unsigned long long)s_cnt[S_EV + TRK3_EV_EL_ELAST]);
         if (cold_species == SP_VBHOLE && s_cnt[S_EV + TRK3_EV_VBH_ELAST]) atomicAdd(p.cnt_el + 3, (unsigned long long)s_cnt[S_EV + TRK3_EV_VBH_ELAST]);
         if (s_cnt[S_NEL]) atomicAdd(p.cnt_el, (unsigned long long)s_cnt[S_NEL]);
         if (s_cnt[S_NPH]) atomicAdd(p.cnt_ph, (unsigned long long)s_cnt[S_NPH]);
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
             }
         }
     }
-    block_epilogue(c_p, s_tally, s_cnt, COLD ? SP : -1);
+    block_epilogue(c_p, s_tally, s_cnt, COLD ? SP : -1, warm);
 }
 
 // k_hot<SP>: one generation of carriers that can still ionise (SP = electron or valence hole).  The two collision
@@ -804,7 +804,7 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_i
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (budget > 0) { const uint32_t per_block = (uint32_t)budget * (uint32_t)(block / 32); grid = (n + per_block - 1) / per_block; }
     if (grid < 1) grid = 1;
-    const int pi = prof_begin(eng, COLD ? N_SPECIES + 2 + SP : SP, st, n);
+    const int pi = prof_begin(eng, warm ? N_CLASSES - 1 : (COLD ? N_SPECIES + 2 + SP : SP), st, n);
     k_wave<SP, COLD><<<grid, block, smem, st>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, warm ? eng->opt_warm_slice : eng->opt_hot_slice, eng->opt_lockstep, budget, warm);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
@@ -991,8 +991,8 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
     CK(cudaMemset(eng->d_tally, 0, (size_t)eng->lay.total * sizeof(double)));
     if ((rc = dev_alloc(eng, &eng->d_tally_bak, (size_t)eng->lay.total))) return rc;
     if ((rc = dev_alloc(eng, &eng->d_small, (size_t)TRK3_MAX_NT))) return rc;
-    if ((rc = dev_alloc(eng, &eng->d_counters, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 4)))) return rc;
-    if ((rc = dev_alloc(eng, &eng->d_counters_bak, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 4)))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_counters, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 5)))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_counters_bak, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 5)))) return rc;
     if ((rc = dev_alloc(eng, &eng->d_qcount, (size_t)QC_TOTAL))) return rc;
 
     p.tally = eng->d_tally;
@@ -1094,7 +1094,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
     nb_max = std::min<int64_t>(nb_max, std::max<int64_t>(n_it, 1));
     int rc = ensure_batch(eng, (uint32_t)nb_max);
     if (rc) return rc;
-    const size_t n_counters = TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 4;
+    const size_t n_counters = TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 5;
     CK(cudaMemsetAsync(eng->d_counters, 0, n_counters * sizeof(unsigned long long), eng->stream));
     uint64_t waves = 0; const uint64_t launches0 = eng->launches;
     std::vector<double> h_diffS, h_totE; std::vector<uint32_t> h_diffN;
@@ -1314,6 +1314,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
     for (int q = 0; q < TRK3_N_ERRORS; ++q) st.errors[q] = h_c[TRK3_N_EVENT_CLASSES + q];
     st.n_electrons = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS]; st.n_photons = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 1];
     st.cold_events[0] = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 2]; st.cold_events[1] = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 3];
+    st.warm_events = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 4];
     st.n_waves = waves; st.kernel_launches = eng->launches - launches0; st.device_ms = ms;
     static const double ev_bytes[TRK3_N_EVENT_CLASSES] = {176, 320, 144, 384, 208, 384, 280, 208, 248};
     for (int q = 0; q < TRK3_N_EVENT_CLASSES; ++q) st.algorithmic_bytes += ev_bytes[q] * (double)st.events[q];

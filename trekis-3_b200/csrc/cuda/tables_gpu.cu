@@ -23,11 +23,11 @@
 namespace {
 
 #define DCS_BLOCK 128
-#define DCS_SMEM_DOUBLES 5600          // oscillators + DOS copies in shared memory (44.8 KB); larger inputs stay in global memory
+#define DCS_SMEM_DOUBLES 5600          // most oscillators + DOS entries copied to shared memory (44.8 KB); larger inputs stay in global memory
 
 __global__ void __launch_bounds__(DCS_BLOCK) k_dcs(trk3_dcs_ctx x, const trk3_dcs_task *tasks, const double *hw, const int32_t *task_of,
                                                    long long n, double *out, unsigned long long *next, int n_osc, int use_smem) {
-    __shared__ double s_tab[DCS_SMEM_DOUBLES];
+    extern __shared__ double s_tab[];      // 3 n_osc + 2 n_k doubles (typically ~4 KB: does not limit the occupancy)
     __shared__ long long s_base;
     if (use_smem) {     // constants of the integrands -> shared memory (every loss-function evaluation reads them)
         double *p = s_tab;
@@ -103,13 +103,14 @@ extern "C" int trk3_dcs_eval(const trk3_dcs_ctx *ctx, const trk3_dcs_task *tasks
         CKD(cudaGetDevice(&dev));
         CKD(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         int bps = 1;
-        CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_dcs, DCS_BLOCK, 0));
+        const int use_smem = (3 * n_osc + 2 * ctx->n_k <= DCS_SMEM_DOUBLES) ? 1 : 0;
+        const size_t smem = use_smem ? sizeof(double) * (size_t)(3 * n_osc + 2 * ctx->n_k) : 0;
+        CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_dcs, DCS_BLOCK, smem));
         // persistent grid: a multiple of the SM count, never more blocks than there are chunks of requests
         const long long chunks = (n + DCS_BLOCK - 1) / DCS_BLOCK;
         const int grid = (int)std::min<long long>(chunks, (long long)n_sm * std::max(bps, 1));
-        const int use_smem = (3 * n_osc + 2 * ctx->n_k <= DCS_SMEM_DOUBLES) ? 1 : 0;
         CKD(cudaEventRecord(e0, st));
-        k_dcs<<<grid, DCS_BLOCK, 0, st>>>(d, d_tasks, d_hw, d_task_of, (long long)n, d_out, d_next, n_osc, use_smem);
+        k_dcs<<<grid, DCS_BLOCK, smem, st>>>(d, d_tasks, d_hw, d_task_of, (long long)n, d_out, d_next, n_osc, use_smem);
         CKD(cudaGetLastError());
         CKD(cudaEventRecord(e1, st));
         CKD(cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
