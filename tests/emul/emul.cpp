@@ -16,6 +16,7 @@ using namespace trk3;
 
 namespace {
 struct EmuCtx {
+    static constexpr bool kLean = false;      // every switch compiled in (see elastic_dE, physics.cuh)
     const DevP &p;
     std::vector<Rec> *next;     // [N_SPECIES] next hot generation
     std::vector<Rec> *cold;     // [2] cold electrons / valence holes (consumed after the hot generations)

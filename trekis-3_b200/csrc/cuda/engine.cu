@@ -56,7 +56,11 @@ struct QueueSet { Queue q[N_QUEUES]; };
 // ------------------------------------------------------------------------------------------------
 // device context: the side effects of physics.cuh
 // ------------------------------------------------------------------------------------------------
-struct DevCtx {
+// LEAN: the kernel was chosen for the default switches (CDF elastic scattering, no electron emission, queued snapshots):
+// the code of the other settings is not compiled into it (physics.cuh, elastic_dE).
+template <bool LEAN>
+struct DevCtxT {
+    static constexpr bool kLean = LEAN;
     const DevP &p;
     const QueueSet &out;
     double *s_tally;        // block-private tallies (nullptr: straight to global)
@@ -85,7 +89,7 @@ struct DevCtx {
     // k_snapshot turns the records into tallies with full warps.  `defer` = 0: tally right here (k_snapshot itself).
     int defer;
     __device__ void snap(int sp, const Rec &r, int i) {
-        if (!defer) { snapshot_any(*this, sp, r, i); return; }
+        if (!LEAN && !defer) { snapshot_any(*this, sp, r, i); return; }
         const unsigned am = __activemask();
         const int lane = threadIdx.x & 31;
         const int leader = __ffs(am) - 1;
@@ -201,7 +205,7 @@ struct PhiloxWarp {
     }
 };
 // one collision of the ion (shi_step), all lanes hold the same `s`
-__device__ inline void shi_step_warp(DevCtx &c, Rec &s, ShiEvent &ev, PhiloxWarp &pw) {
+__device__ inline void shi_step_warp(DevCtxT<false> &c, Rec &s, ShiEvent &ev, PhiloxWarp &pw) {
     const DevP &p = c.p;
     const int lane = threadIdx.x & 31, NS = p.n_shells;
     const double MSHI = p.ion_mass * TRK_MP;
@@ -258,7 +262,7 @@ __device__ inline void shi_step_warp(DevCtx &c, Rec &s, ShiEvent &ev, PhiloxWarp
 __global__ void __launch_bounds__(32 * SHI_WARPS) k_shi(Queue stage, QueueSet qout, int lanes) {
     __shared__ unsigned int s_cnt[S_NCNT];
     block_prologue(nullptr, s_cnt, 0);
-    DevCtx c{c_p, qout, nullptr, s_cnt, c_p.defer_snap};
+    DevCtxT<false> c{c_p, qout, nullptr, s_cnt, c_p.defer_snap};
     if (lanes <= 0) {       // one ion per warp, the lanes cooperate (n_shells + 1 <= 32 lanes are needed)
         const uint32_t k = blockIdx.x * SHI_WARPS + (threadIdx.x >> 5);
         if (k < c_p.batch_n) {
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(32 * SHI_WARPS) k_shi(Queue stage, QueueSet qo
 __global__ void __launch_bounds__(256) k_shi_emit(Queue stage, QueueSet qout) {
     __shared__ unsigned int s_cnt[S_NCNT];
     block_prologue(nullptr, s_cnt, 0);
-    DevCtx c{c_p, qout, nullptr, s_cnt, c_p.defer_snap};
+    DevCtxT<false> c{c_p, qout, nullptr, s_cnt, c_p.defer_snap};
     const uint32_t n = min(*stage.count, stage.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         ShiEvent ev;
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(256) k_shi_emit(Queue stage, QueueSet qout) {
 __global__ void __launch_bounds__(256) k_ion_emit(Queue ionq, QueueSet qout) {
     __shared__ unsigned int s_cnt[S_NCNT];
     block_prologue(nullptr, s_cnt, 0);
-    DevCtx c{c_p, qout, nullptr, s_cnt, c_p.defer_snap};
+    DevCtxT<false> c{c_p, qout, nullptr, s_cnt, c_p.defer_snap};
     const uint32_t n = min(*ionq.count, ionq.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Rec r;
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(256) k_snapshot(Queue sq, QueueSet qout, int u
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
     block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? c_p.s_total : 0);
-    DevCtx c{c_p, qout, s_tally, s_cnt, 0};
+    DevCtxT<false> c{c_p, qout, s_tally, s_cnt, 0};
     const uint32_t n = min(*sq.count, sq.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Rec r;
@@ -352,13 +356,13 @@ __global__ void __launch_bounds__(256) k_snapshot(Queue sq, QueueSet qout, int u
 
 // k_wave<SP, COLD>: records [first, n_in) of queue qin, histories followed with lane refill until they end or
 // have to change queue (hot -> cold when the particle can no longer ionise, core hole -> valence hole, ...).
-template <int SP, bool COLD>
+template <int SP, bool COLD, bool LEAN>
 __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int lockstep, int budget, int warm) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
     block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? c_p.s_total : 0);
-    DevCtx c{c_p, qout, s_tally, s_cnt, c_p.defer_snap};
+    DevCtxT<LEAN> c{c_p, qout, s_tally, s_cnt, c_p.defer_snap};
     const int lane = threadIdx.x & 31;
     bool active = false, exhausted = false;
     Rec r;
@@ -420,7 +424,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
 // channel roulette selected the ionisation wait until `inel_min` of them have gathered (or nothing else is left to
 // do), and then take that path together; elastic collisions are never delayed.
 template <int SP> __device__ inline bool hot_roulette(const Cache &k, double RN) { return SP == SP_ELECTRON ? electron_roulette_inelastic(k, RN) : vbhole_roulette_inelastic(k, RN); }
-template <int SP, int MODE> __device__ inline void hot_event(DevCtx &c, Rec &r, int ig, Cache &k, double RN) {
+template <int SP, int MODE, class C> __device__ inline void hot_event(C &c, Rec &r, int ig, Cache &k, double RN) {
     if (SP == SP_ELECTRON) electron_event_t<MODE>(c, r, ig, k, RN); else vbhole_event_t<MODE>(c, r, ig, k, RN);
 }
 template <int SP> __device__ inline bool hot_leaves(const Rec &r) { return SP == SP_ELECTRON ? electron_leaves_hot(c_p, r) : vbhole_leaves_hot(c_p, r); }
@@ -445,13 +449,13 @@ struct HotIn {
 
 // debugging aid (option "profile" >= 3): collisions per history and energy class of the last k_hot<electron> launch
 __device__ unsigned int g_hot_hist[N_ECLASS][66];
-template <int SP>
+template <int SP, bool LEAN>
 __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn in, QueueSet qout, int use_smem, int refill_min, int inel_min, int lockstep) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
     block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? c_p.s_total : 0);
-    DevCtx c{c_p, qout, s_tally, s_cnt, c_p.defer_snap};
+    DevCtxT<LEAN> c{c_p, qout, s_tally, s_cnt, c_p.defer_snap};
     const int lane = threadIdx.x & 31;
     bool active = false, exhausted = false, have_rn = false;
     Rec r;
@@ -580,6 +584,7 @@ struct trk3_engine {
     int opt_warm_slice = 64;
     double e_warm_auto = -1.0;             // from warm_P and opt_warm_pinel (< 0: to be evaluated)
     std::vector<double> warm_E, warm_P;    // ionisation probability per collision on the inelastic energy grid
+    int opt_lean = 1;                      // 0: always the kernels with every switch compiled in
     int opt_hot_classes = N_ECLASS;
     double opt_class_E[N_ECLASS - 1] = {200.0, 500.0, 1300.0};
     int opt_class_quota[N_ECLASS] = {32, 8, 3, 1};
@@ -786,6 +791,10 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
     return TRK3_OK;
 }
 
+// The lean kernels serve the default switches (see DevCtxT); any other setting runs the kernels with everything compiled in.
+inline bool engine_is_lean(const trk3_engine *eng) {
+    return eng->opt_lean && eng->cfg.kind_of_EMFP == 1 && !(eng->cfg.work_function > 0.0) && eng->opt_defer_snap;
+}
 template <int SP, bool COLD>
 int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_in, uint32_t *head, const QueueSet &qout, cudaStream_t st = nullptr, int budget = 0, size_t smem_floor = 0, int warm = 0) {
     const uint32_t n = n_in - first;
@@ -795,17 +804,19 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_i
     const size_t smem_max = (size_t)eng->smem_optin - 1024;             // static shared memory + driver reserve
     if (smem > smem_max) { smem = 8; use_smem = 0; }                    // too many output times for shared memory: global atomics
     if (smem < smem_floor && smem_floor <= smem_max) smem = smem_floor; // occupancy limiter: leaves room on every SM for the blocks of another kernel
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_wave<SP, COLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool lean = engine_is_lean(eng);
+    auto kern = lean ? k_wave<SP, COLD, true> : k_wave<SP, COLD, false>;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = eng->opt_blocks_per_sm;
     const int block = eng->opt_block;
-    if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_wave<SP, COLD>, block, smem)); if (bps < 1) bps = 1; }
+    if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, block, smem)); if (bps < 1) bps = 1; }
     // persistent-style grid: a multiple of the SM count, never more blocks than there is work for
     uint32_t want = (n + block - 1) / block;
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (budget > 0) { const uint32_t per_block = (uint32_t)budget * (uint32_t)(block / 32); grid = (n + per_block - 1) / per_block; }
     if (grid < 1) grid = 1;
     const int pi = prof_begin(eng, warm ? N_CLASSES - 1 : (COLD ? N_SPECIES + 2 + SP : SP), st, n);
-    k_wave<SP, COLD><<<grid, block, smem, st>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, warm ? eng->opt_warm_slice : eng->opt_hot_slice, eng->opt_lockstep, budget, warm);
+    kern<<<grid, block, smem, st>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, warm ? eng->opt_warm_slice : eng->opt_hot_slice, eng->opt_lockstep, budget, warm);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
@@ -819,10 +830,12 @@ int launch_hot(trk3_engine *eng, const Queue *const *qin, const uint32_t *n_in, 
     int use_smem = eng->opt_use_smem;
     const size_t smem_max = (size_t)eng->smem_optin - 1024;
     if (smem > smem_max) { smem = 8; use_smem = 0; }
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_hot<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool lean = engine_is_lean(eng);
+    auto kern = lean ? k_hot<SP, true> : k_hot<SP, false>;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = eng->opt_blocks_per_sm;
     const int block = eng->opt_hot_block ? eng->opt_hot_block : eng->opt_block;
-    if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_hot<SP>, block, smem)); if (bps < 1) bps = 1; }
+    if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, block, smem)); if (bps < 1) bps = 1; }
     const uint32_t wpb = (uint32_t)block / 32u, W = (uint32_t)(eng->n_sm * bps) * wpb;       // warps the GPU holds at once
     HotIn in{};
     in.ncls = ncls;
@@ -860,7 +873,7 @@ int launch_hot(trk3_engine *eng, const Queue *const *qin, const uint32_t *n_in, 
     in.hist = (eng->opt_profile >= 3);
     if (in.hist && SP == SP_ELECTRON) { static unsigned int zero[N_ECLASS][66]; cudaMemcpyToSymbolAsync(g_hot_hist, zero, sizeof zero, 0, cudaMemcpyHostToDevice, st); }
     const int pi = prof_begin(eng, SP, st, n_tot);
-    k_hot<SP><<<grid, block, smem, st>>>(in, qout, use_smem, eng->opt_refill_min, eng->opt_inel_min, eng->opt_lockstep);
+    kern<<<grid, block, smem, st>>>(in, qout, use_smem, eng->opt_refill_min, eng->opt_inel_min, eng->opt_lockstep);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
@@ -1038,6 +1051,7 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "cold_min") eng->opt_cold_min = std::max(1, (int)v);
     else if (k == "warm_pinel") { eng->opt_warm_pinel = std::min(0.99, std::max(0.0, v)); eng->nb_alloc = 0; eng->e_warm_auto = -1.0; }
     else if (k == "warm_slice") eng->opt_warm_slice = std::max(1, (int)v);
+    else if (k == "lean") eng->opt_lean = (v != 0.0);
     else if (k == "hot_classes") { eng->opt_hot_classes = std::min(N_ECLASS, std::max(1, (int)v)); eng->nb_alloc = 0; }
     else if (k == "class_E1") eng->opt_class_E[0] = v;
     else if (k == "class_E2") eng->opt_class_E[1] = v;

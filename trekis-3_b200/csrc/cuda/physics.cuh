@@ -17,6 +17,7 @@
 //   c.add_u32(base, idx)     atomic ++ on a per-iteration integer histogram
 //   c.add_f64(base, idx, v)  atomic += on a per-iteration double array
 //   c.event(cls) / c.error(code) / c.count_electron() / c.count_photon()
+//   C::kLean                 compile-time promise of the default switches (see elastic_dE); false = everything compiled in
 // so that the identical code runs in the CUDA kernels (engine.cu) and in the CPU emulation used by
 // the no-GPU tests (tests/emul).  fp64 throughout (the reference is built with -real-size 64).
 #pragma once
@@ -455,9 +456,13 @@ TRK_HD_RARE double mott_elastic_dE(const DevP &p, Rec &r, double Eel, double M_e
     }
     return dE / p.sum_pers;
 }
-// elastic energy transfer: the kind_of_EMFP switch of Monte_Carlo.f90:2387-2407 / :2668-2692
+// elastic energy transfer: the kind_of_EMFP switch of Monte_Carlo.f90:2387-2407 / :2668-2692.
+// LEAN (compile time, C::kLean of the context): the caller guarantees the default switches -- CDF elastic scattering
+// (kind_of_EMFP = 1) and no electron emission (work_function <= 0) --, and the code of the other settings is not compiled
+// in.  The wave kernels are bound by instruction fetch: code that never runs still costs (measured: -6 % step time).
+template <bool LEAN>
 TRK_HD double elastic_dE(const DevP &p, Rec &r, double Eel, const Cache &k, double EMFP, bool hole, double M_eff) {
-    if (p.kind_of_EMFP == 1) {      // Electron_energy_transfer_elastic, Cross_sections.f90:2403-2413
+    if (LEAN || p.kind_of_EMFP == 1) {      // Electron_energy_transfer_elastic, Cross_sections.f90:2403-2413
         double RN = rn(p, r);
         double L_need = m_div(EMFP, RN);
         double hw = transferred_energy(hole ? csr_hed(p) : csr_eed(p), Eel, k.lE, k.n1, L_need);
@@ -872,7 +877,7 @@ TRK_HD void electron_event_t(C &c, Rec &e, int iv, Cache &k, double RN) {
     } else {                                                     // elastic: energy to the lattice
         c.event(TRK3_EV_EL_ELAST);
         EMFP = elastic_total(tab_ee(p), Eel, k);
-        dE = elastic_dE(p, e, Eel, k, EMFP, false, 1.0);
+        dE = elastic_dE<C::kLean>(p, e, Eel, k, EMFP, false, 1.0);
         angles_lattice(p, e, Eel, dE, 1.0, theta, phi);
         if (trk_isnan(theta) || trk_isnan(phi)) c.error(TRK3_ERR_NAN);
         deposit_lattice(c, e, iv, X, Y, dE);
@@ -885,7 +890,7 @@ TRK_HD void electron_event_t(C &c, Rec &e, int iv, Cache &k, double RN) {
     e.E = Eel - dE; e.t0 = t_ev; e.X = X; e.Y = Y; e.Z = Z; e.L = MFP_tot; e.theta = theta1; e.phi = phi1;
     e.tn = next_time(e.t0, vel_electron(e.E), MFP_tot);
     if (e.E < p.cut_off) e.tn = 1.0e20;
-    if (p.work_function > 0 && e.Z < 0.0) electron_emission(c, e, iv);
+    if (!C::kLean && p.work_function > 0 && e.Z < 0.0) electron_emission(c, e, iv);
     if (e.E < -1.0e-9 || trk_isnan(e.E)) c.error(TRK3_ERR_22);
 }
 
@@ -959,7 +964,7 @@ TRK_HD void vbhole_event_t(C &c, Rec &h, int iv, Cache &k, double RN) {
     } else {
         c.event(TRK3_EV_VBH_ELAST);
         HEMFP = elastic_total(tab_he(p), Eel, k);
-        dE = elastic_dE(p, h, Eel, k, HEMFP, true, h.Mass);
+        dE = elastic_dE<C::kLean>(p, h, Eel, k, HEMFP, true, h.Mass);
         angles_lattice(p, h, Eel, dE, h.Mass, htheta1, hphi1);
         check_hole_level(p, Eel, dE, Ehole, nullptr);
         deposit_lattice(c, h, iv, X, Y, dE);
