@@ -507,10 +507,20 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn
         }
         const unsigned m_in = __ballot_sync(0xffffffffu, want == 2), m_el = __ballot_sync(0xffffffffu, want == 1);
         bool done_event = false;
-        if (m_in && (__popc(m_in) >= inel_min || !m_el)) {
-            if (want == 2) { hot_event<SP, EV_INELASTIC>(c, r, ig, k, RN); done_event = true; }
+        const bool go_in = (want == 2) && (__popc(m_in) >= inel_min || !m_el);
+        if (SP == SP_ELECTRON) {
+            // head and tail of a collision are common to both channels: lanes that disagree on the channel only take the
+            // channel-specific middle part one after the other (electron_event_head / _inel / _elast / _tail, physics.cuh)
+            ElEvent s;
+            const bool ev_now = go_in || want == 1;
+            if (ev_now) electron_event_head(r, s);
+            if (go_in) electron_event_inel(c, r, k, s);
+            if (want == 1) electron_event_elast(c, r, ig, k, s);
+            if (ev_now) { electron_event_tail(c, r, ig, k, s); done_event = true; }
+        } else {
+            if (go_in) { hot_event<SP, EV_INELASTIC>(c, r, ig, k, RN); done_event = true; }
+            if (want == 1) { hot_event<SP, EV_ELASTIC>(c, r, ig, k, RN); done_event = true; }
         }
-        if (want == 1) { hot_event<SP, EV_ELASTIC>(c, r, ig, k, RN); done_event = true; }
         if (done_event) {
             have_rn = false;
             // leave when the carrier can no longer ionise (cold queue) or, after `slice` collisions, back to the hot queue

@@ -849,49 +849,71 @@ TRK_HD void electron_ion_emit(C &c, const IonEvent &ev) {
 // electron_roulette_inelastic).
 enum EventMode { EV_ANY = 0, EV_ELASTIC = 1, EV_INELASTIC = 2 };
 TRK_HD bool electron_roulette_inelastic(const Cache &k, double RN) { const double ii = k.iimfp; return RN * (ii + k.iemfp) < ii; }
-template <int MODE, class C>
-TRK_HD void electron_event_t(C &c, Rec &e, int iv, Cache &k, double RN) {
+// The collision in three parts, so that a warp whose lanes disagree on the channel runs the channel-specific middle part
+// once per channel but the common head and tail once for all of them (k_hot, engine.cu):
+//   electron_event_head   the place of the collision (:2290-2296)
+//   electron_event_inel / electron_event_elast   transferred energy and scattering angles of the channel
+//   electron_event_tail   lookups of the new energy, next free flight, new direction (:2449-2465)
+struct ElEvent { double X, Y, Z, cos_t0, dE, theta, phi; };
+TRK_HD void electron_event_head(const Rec &e, ElEvent &s) {
+    const double L = e.L;
+    const SinCos sc_t = m_sincos(e.theta), sc_p = m_sincos(e.phi);
+    const double st0 = sc_t.s;
+    s.X = e.X + L * st0 * sc_p.s; s.Y = e.Y + L * st0 * sc_p.c; s.Z = e.Z + L * sc_t.c;
+    s.cos_t0 = sc_t.c;
+}
+template <class C>
+TRK_HD void electron_event_inel(C &c, Rec &e, const Cache &k, ElEvent &s) {     // impact ionisation
     const DevP &p = c.p;
     const double Eel = e.E;
-    double IMFP = k.imfp, EMFP = k.emfp;                          // :2298-2299, already looked up for this energy
-    const double L = e.L, theta0 = e.theta, phi0 = e.phi;
-    const SinCos sc_t = m_sincos(theta0), sc_p = m_sincos(phi0);
-    const double st0 = sc_t.s;
-    const double X = e.X + L * st0 * sc_p.s, Y = e.Y + L * st0 * sc_p.c, Z = e.Z + L * sc_t.c;
-    const double t_ev = e.tn;
-    double dE, theta, phi;
-    if (MODE == EV_INELASTIC || (MODE == EV_ANY && electron_roulette_inelastic(k, RN))) {     // inelastic: impact ionisation
-        c.event(TRK3_EV_EL_INEL);
-        int n_E;
-        int shell = which_shell(p, e, tab_ei_L(p), Eel, k.lE, n_E);
-        IonEvent ev;
-        ev.pid = e.id; ev.ctr0 = e.ctr; ev.iter = e.iter;
-        e.ctr += 2;                                              // the two child ids
-        IMFP = nfp_at(tab_shell(tab_ei_L(p), shell), n_E, false, Eel, k.lE);      // Next_free_path_1d, same grid => same index
-        dE = inelastic_dE(p, e, Eel, k.lE, n_E, shell, IMFP, false);
-        theta = m_acos((Eel - dE) / sqrt(Eel * (Eel - dE)));       // Update_electron_angles_El :1189
-        if (trk_isnan(theta)) { double r2 = rn(p, e); theta = r2 * TRK_PI; }
-        { double r2 = rn(p, e); phi = 2.0 * TRK_PI * r2; }
-        ev.dE = dE; ev.t = t_ev; ev.X = X; ev.Y = Y; ev.Z = Z; ev.theta0 = theta0; ev.phi0 = phi0; ev.theta = theta; ev.phi = phi; ev.shell = shell;
-        c.push_ion(ev);                                          // the pair: electron_ion_emit
-    } else {                                                     // elastic: energy to the lattice
-        c.event(TRK3_EV_EL_ELAST);
-        EMFP = elastic_total(tab_ee(p), Eel, k);
-        dE = elastic_dE<C::kLean>(p, e, Eel, k, EMFP, false, 1.0);
-        angles_lattice(p, e, Eel, dE, 1.0, theta, phi);
-        if (trk_isnan(theta) || trk_isnan(phi)) c.error(TRK3_ERR_NAN);
-        deposit_lattice(c, e, iv, X, Y, dE);
-    }
-    cache_electron(p, Eel - dE, k);                               // :2449-2450, kept for the next collision
-    RN = rn(p, e);
+    c.event(TRK3_EV_EL_INEL);
+    int n_E;
+    int shell = which_shell(p, e, tab_ei_L(p), Eel, k.lE, n_E);
+    IonEvent ev;
+    ev.pid = e.id; ev.ctr0 = e.ctr; ev.iter = e.iter;
+    e.ctr += 2;                                              // the two child ids
+    const double IMFP = nfp_at(tab_shell(tab_ei_L(p), shell), n_E, false, Eel, k.lE);      // Next_free_path_1d, same grid => same index
+    const double dE = inelastic_dE(p, e, Eel, k.lE, n_E, shell, IMFP, false);
+    double theta = m_acos((Eel - dE) / sqrt(Eel * (Eel - dE)));       // Update_electron_angles_El :1189
+    if (trk_isnan(theta)) { double r2 = rn(p, e); theta = r2 * TRK_PI; }
+    double phi; { double r2 = rn(p, e); phi = 2.0 * TRK_PI * r2; }
+    ev.dE = dE; ev.t = e.tn; ev.X = s.X; ev.Y = s.Y; ev.Z = s.Z; ev.theta0 = e.theta; ev.phi0 = e.phi; ev.theta = theta; ev.phi = phi; ev.shell = shell;
+    c.push_ion(ev);                                          // the pair: electron_ion_emit
+    s.dE = dE; s.theta = theta; s.phi = phi;
+}
+template <class C>
+TRK_HD void electron_event_elast(C &c, Rec &e, int iv, const Cache &k, ElEvent &s) {     // elastic: energy to the lattice
+    const DevP &p = c.p;
+    const double Eel = e.E;
+    c.event(TRK3_EV_EL_ELAST);
+    const double EMFP = elastic_total(tab_ee(p), Eel, k);
+    s.dE = elastic_dE<C::kLean>(p, e, Eel, k, EMFP, false, 1.0);
+    angles_lattice(p, e, Eel, s.dE, 1.0, s.theta, s.phi);
+    if (trk_isnan(s.theta) || trk_isnan(s.phi)) c.error(TRK3_ERR_NAN);
+    deposit_lattice(c, e, iv, s.X, s.Y, s.dE);
+}
+template <class C>
+TRK_HD void electron_event_tail(C &c, Rec &e, int iv, Cache &k, const ElEvent &s) {
+    const DevP &p = c.p;
+    const double Eel = e.E, t_ev = e.tn;
+    cache_electron(p, Eel - s.dE, k);                               // :2449-2450, kept for the next collision
+    const double RN = rn(p, e);
     double MFP_tot = m_div(-m_log(RN), k.iimfp + k.iemfp);
     double phi1, theta1;
-    new_angles_c(phi0, theta0, sc_t.c, theta, phi, phi1, theta1);
-    e.E = Eel - dE; e.t0 = t_ev; e.X = X; e.Y = Y; e.Z = Z; e.L = MFP_tot; e.theta = theta1; e.phi = phi1;
+    new_angles_c(e.phi, e.theta, s.cos_t0, s.theta, s.phi, phi1, theta1);
+    e.E = Eel - s.dE; e.t0 = t_ev; e.X = s.X; e.Y = s.Y; e.Z = s.Z; e.L = MFP_tot; e.theta = theta1; e.phi = phi1;
     e.tn = next_time(e.t0, vel_electron(e.E), MFP_tot);
     if (e.E < p.cut_off) e.tn = 1.0e20;
     if (!C::kLean && p.work_function > 0 && e.Z < 0.0) electron_emission(c, e, iv);
     if (e.E < -1.0e-9 || trk_isnan(e.E)) c.error(TRK3_ERR_22);
+}
+template <int MODE, class C>
+TRK_HD void electron_event_t(C &c, Rec &e, int iv, Cache &k, double RN) {
+    ElEvent s;
+    electron_event_head(e, s);
+    if (MODE == EV_INELASTIC || (MODE == EV_ANY && electron_roulette_inelastic(k, RN))) electron_event_inel(c, e, k, s);
+    else electron_event_elast(c, e, iv, k, s);
+    electron_event_tail(c, e, iv, k, s);
 }
 
 // check_hole_parameters, Monte_Carlo.f90:682-721: snap the scattered hole to a populated DOS level
