@@ -186,7 +186,7 @@ def run_ours(args):
     events_total, launches, drift, errors = 0, 0, 0.0, {}
     ev_by_class = {}
     cold_ev = {"electron": 0, "vbhole": 0}
-    warm_ev = 0
+    warm_ev = {"electron": 0, "vbhole": 0}
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                            # L2 flush between timed iterations (untimed)
@@ -204,7 +204,8 @@ def run_ours(args):
             errors[n] = errors.get(n, 0) + v
         for n, v in st["cold_events"].items():
             cold_ev[n] += v
-        warm_ev += st["warm_events"]
+        for n, v in st["warm_events"].items():
+            warm_ev[n] += v
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -260,9 +261,10 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
     B = tk.EVENT_BYTES
     class_bytes = {
-        "k_wave<electron,hot>": ev_by_class.get("el_inelastic", 0) * B["el_inelastic"] + (ev_by_class.get("el_elastic", 0) - cold_ev["electron"] - warm_ev) * B["el_elastic"],
-        "k_wave<electron,warm>": warm_ev * B["el_elastic"],
-        "k_wave<vbhole,hot>": ev_by_class.get("vbh_inelastic", 0) * B["vbh_inelastic"] + (ev_by_class.get("vbh_elastic", 0) - cold_ev["vbhole"]) * B["vbh_elastic"],
+        "k_wave<electron,hot>": ev_by_class.get("el_inelastic", 0) * B["el_inelastic"] + (ev_by_class.get("el_elastic", 0) - cold_ev["electron"] - warm_ev["electron"]) * B["el_elastic"],
+        "k_wave<electron,warm>": warm_ev["electron"] * B["el_elastic"],
+        "k_wave<vbhole,warm>": warm_ev["vbhole"] * B["vbh_elastic"],
+        "k_wave<vbhole,hot>": ev_by_class.get("vbh_inelastic", 0) * B["vbh_inelastic"] + (ev_by_class.get("vbh_elastic", 0) - cold_ev["vbhole"] - warm_ev["vbhole"]) * B["vbh_elastic"],
         "k_wave<electron,cold>": cold_ev["electron"] * B["el_elastic"],
         "k_wave<vbhole,cold>": cold_ev["vbhole"] * B["vbh_elastic"],
         "k_wave<corehole>": ev_by_class.get("auger", 0) * B["auger"] + ev_by_class.get("radiative", 0) * B["radiative"] + ev_by_class.get("auger_frozen", 0) * B["auger_frozen"],

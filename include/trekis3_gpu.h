@@ -180,7 +180,7 @@ typedef struct trk3_stats {
     double   algorithmic_bytes; /* sum_class events*bytes */
     double   max_energy_drift;  /* max_it max_i |tot_E(it,i)-tot_E(it,Nt)|/tot_E(it,Nt), i >= first grid time after the ion left */
     uint64_t cold_events[2];    /* elastic collisions of electrons / valence holes handled by the cold (elastic-only) kernels */
-    uint64_t warm_events;       /* elastic collisions of "warm" electrons (can still ionise, rarely do) handled by the same kernel, generation by generation */
+    uint64_t warm_events[2];    /* elastic collisions of "warm" electrons / valence holes (can still ionise, rarely do) handled by the same kernels, generation by generation */
 } trk3_stats;
 
 /* Return codes */
@@ -228,7 +228,7 @@ int trk3_mc_iteration_energies(trk3_engine *eng, double *out, int64_t capacity_d
 int trk3_mc_set_stream(trk3_engine *eng, void *cuda_stream);
 int trk3_mc_set_device_tallies(trk3_engine *eng, double *device_buffer);
 /* Device time per kernel class since option "profile"=1 (0 hot electron wave, 1 hot valence-hole wave, 2 core-hole
- * wave, 3 photon wave, 4 ion tracks, 5 finalize, 6 cold electrons, 7 cold valence holes, 8 warm electrons); returns the number
+ * wave, 3 photon wave, 4 ion tracks, 5 finalize, 6 cold electrons, 7 cold valence holes, 8 warm electrons, 9 warm valence holes); returns the number
  * of classes.  Classes 0-3 and 8 of one generation run on concurrent streams: their times overlap. */
 int trk3_mc_kernel_times(trk3_engine *eng, double *ms, uint64_t *launches, int n);
 

@@ -91,6 +91,7 @@ extern "C" int trk3_emul_run(const trk3_config *cfg, const trk3_tables *tab, int
     p.e_warm = p.e_cold; p.e_class[0] = p.e_class[1] = p.e_class[2] = 1.0e300;      // scheduling classes of the CUDA engine: not used here
     cold_range(p.hi_E, p.hi_tot, p.n_hi, p.h_cold, p.h_imfp_cold);
     p.e_iimfp_cold = (p.e_imfp_cold > 0.0) ? 1.0 / p.e_imfp_cold : 0.0; p.h_iimfp_cold = (p.h_imfp_cold > 0.0) ? 1.0 / p.h_imfp_cold : 0.0;
+    p.h_warm = p.h_cold;
     p.tally = tallies;
     unsigned long long ev[TRK3_N_EVENT_CLASSES] = {0}, er[TRK3_N_ERRORS] = {0}, nel = 0, nph = 0;
     uint64_t waves = 0;

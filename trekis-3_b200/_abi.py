@@ -95,7 +95,7 @@ class Stats(C.Structure):
         ("events", C.c_uint64 * len(EVENT_NAMES)), ("errors", C.c_uint64 * len(ERROR_NAMES)),
         ("n_electrons", C.c_uint64), ("n_photons", C.c_uint64), ("n_waves", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("algorithmic_bytes", C.c_double),
-        ("max_energy_drift", C.c_double), ("cold_events", C.c_uint64 * 2), ("warm_events", C.c_uint64),
+        ("max_energy_drift", C.c_double), ("cold_events", C.c_uint64 * 2), ("warm_events", C.c_uint64 * 2),
     ]
 
     def as_dict(self):
@@ -105,7 +105,7 @@ class Stats(C.Structure):
              "kernel_launches": int(self.kernel_launches), "device_ms": float(self.device_ms),
              "algorithmic_bytes": float(self.algorithmic_bytes), "max_energy_drift": float(self.max_energy_drift),
              "cold_events": {"electron": int(self.cold_events[0]), "vbhole": int(self.cold_events[1])},
-             "warm_events": int(self.warm_events)}
+             "warm_events": {"electron": int(self.warm_events[0]), "vbhole": int(self.warm_events[1])}}
         d["total_events"] = sum(d["events"].values())
         return d
 

@@ -37,9 +37,10 @@ __constant__ DevP c_p;
 #define N_ECLASS 4                    // energy classes of the hot electrons (class 0 lives in queue SP_ELECTRON)
 #define Q_ELC (N_SPECIES + 4)         // classes 1..N_ECLASS-1: Q_ELC + (class - 1)
 #define Q_ELW (N_SPECIES + 4 + N_ECLASS - 1)      // warm electrons of the next generation (see DevP::e_warm)
-#define N_QUEUES (N_SPECIES + 5 + N_ECLASS - 1)
+#define Q_VBW (N_SPECIES + 5 + N_ECLASS - 1)      // warm valence holes of the next generation (DevP::h_warm)
+#define N_QUEUES (N_SPECIES + 6 + N_ECLASS - 1)
 struct QueueSet { Queue q[N_QUEUES]; };
-#define N_CLASSES (N_SPECIES + 5)     // timing classes: hot waves per species, k_shi, finalize, cold electrons, cold holes, warm electrons
+#define N_CLASSES (N_SPECIES + 6)     // timing classes: hot waves per species, k_shi, finalize, cold electrons, cold holes, warm electrons, warm holes
 
 #define TRK_BLOCK_MAX 256          // compile-time upper bound of the wave-kernel block size (launch bounds)
 #ifndef TRK_MIN_BLOCKS
@@ -80,6 +81,7 @@ struct DevCtxT {
         if (sp == SP_ELECTRON && electron_is_cold(p, r)) qi = Q_EL_COLD;
         else if (sp == SP_ELECTRON && r.E < p.e_warm && out.q[Q_ELW].cap != 0u) qi = Q_ELW;
         else if (sp == SP_VBHOLE && vbhole_is_cold(p, r)) qi = Q_VB_COLD;
+        else if (sp == SP_VBHOLE && r.Ehkin < p.h_warm && out.q[Q_VBW].cap != 0u) qi = Q_VBW;
         else qi = hot_queue(sp, r);
         push_q(qi, r);
     }
@@ -168,7 +170,7 @@ __device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned i
     if (threadIdx.x == 0) {
         // collisions handled by the cold kernels (per species), for the per-kernel roofline
         if (cold_species == SP_ELECTRON && s_cnt[S_EV + TRK3_EV_EL_ELAST]) atomicAdd(p.cnt_el + (warm ? 4 : 2), (unsigned long long)s_cnt[S_EV + TRK3_EV_EL_ELAST]);
-        if (cold_species == SP_VBHOLE && s_cnt[S_EV + TRK3_EV_VBH_ELAST]) atomicAdd(p.cnt_el + 3, (unsigned long long)s_cnt[S_EV + TRK3_EV_VBH_ELAST]);
+        if (cold_species == SP_VBHOLE && s_cnt[S_EV + TRK3_EV_VBH_ELAST]) atomicAdd(p.cnt_el + (warm ? 5 : 3), (unsigned long long)s_cnt[S_EV + TRK3_EV_VBH_ELAST]);
         if (s_cnt[S_NEL]) atomicAdd(p.cnt_el, (unsigned long long)s_cnt[S_NEL]);
         if (s_cnt[S_NPH]) atomicAdd(p.cnt_ph, (unsigned long long)s_cnt[S_NPH]);
     }
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
         if (active) {
             int st;
             if (SP == SP_ELECTRON) st = step_electron<COLD>(c, r, ig, k, COLD && warm);
-            else if (SP == SP_VBHOLE) st = step_vbhole<COLD>(c, r, ig, k);
+            else if (SP == SP_VBHOLE) st = step_vbhole<COLD>(c, r, ig, k, COLD && warm);
             else if (SP == SP_COREHOLE) st = step_corehole(c, r, ig);
             else st = step_photon(c, r, ig);
             // time slicing of the hot cascade: after `slice` collisions the record goes back to the queue, so that the
@@ -573,6 +575,7 @@ struct trk3_engine {
     cudaStream_t stream_c = nullptr;       // second stream: the cold kernels run beside the hot cascade
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t stream_w = nullptr; cudaEvent_t ev_w = nullptr;   // warm electrons of a generation
+    cudaStream_t stream_wh = nullptr; cudaEvent_t ev_wh = nullptr; // warm valence holes
     cudaStream_t stream_sp[3] = {nullptr, nullptr, nullptr};      // the rarer species of a generation run beside the electrons
     cudaEvent_t ev_gen = nullptr, ev_sp[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -590,10 +593,11 @@ struct trk3_engine {
     int opt_shi_lanes = 0;                 // 0: one ion per warp, the lanes share the work of a collision (k_shi)
     int opt_cold_budget = 0, opt_cold_smem_kb = 0, opt_hot_block = 0;      // see the `overlap` schedule in trk3_mc_run_device
     // energy classes of the hot electrons: lower edges [eV] of classes 1..3 and the most histories a warp follows at once
-    double opt_warm_pinel = 0.2;           // electrons are "warm" below the energy where the ionisation probability per collision reaches this (0: off)
+    double opt_warm_pinel = 0.5;           // electrons are "warm" below the energy where the ionisation probability per collision reaches this (0: off)
     int opt_warm_slice = 64;
-    double e_warm_auto = -1.0;             // from warm_P and opt_warm_pinel (< 0: to be evaluated)
-    std::vector<double> warm_E, warm_P;    // ionisation probability per collision on the inelastic energy grid
+    int opt_warm_holes = 1;                // the warm class for valence holes too
+    double e_warm_auto = -1.0, h_warm_auto = -1.0;      // from warm_P / warm_Ph and opt_warm_pinel (< 0: to be evaluated)
+    std::vector<double> warm_E, warm_P, warm_Eh, warm_Ph;    // ionisation probability per collision on the inelastic energy grids
     int opt_lean = 1;                      // 0: always the kernels with every switch compiled in
     int opt_hot_classes = N_ECLASS;
     double opt_class_E[N_ECLASS - 1] = {200.0, 500.0, 1300.0};
@@ -641,7 +645,9 @@ struct trk3_engine {
 #define QC_HEADC (4 * N_SPECIES + 7 + 2 * (N_ECLASS - 1))          // their heads
 #define QC_ELW(b) (4 * N_SPECIES + 7 + 3 * (N_ECLASS - 1) + (b))   // warm electrons of generation set b
 #define QC_HEADW (4 * N_SPECIES + 9 + 3 * (N_ECLASS - 1))
-#define QC_TOTAL (4 * N_SPECIES + 10 + 3 * (N_ECLASS - 1))
+#define QC_VBW(b) (4 * N_SPECIES + 10 + 3 * (N_ECLASS - 1) + (b))  // warm valence holes of generation set b
+#define QC_HEADWH (4 * N_SPECIES + 12 + 3 * (N_ECLASS - 1))
+#define QC_TOTAL (4 * N_SPECIES + 13 + 3 * (N_ECLASS - 1))
 
 namespace {
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { eng->err = std::string(#call) + ": " + cudaGetErrorString(e_); return TRK3_E_CUDA; } } while (0)
@@ -743,6 +749,7 @@ void queue_caps(const trk3_engine *eng, double cap[N_QUEUES]) {
     // the higher energy classes of the hot electrons hold a few per cent of them (the spectrum falls like 1/E^2)
     for (int c = 1; c < N_ECLASS; ++c) cap[Q_ELC + c - 1] = (c < eng->opt_hot_classes) ? 0.25 * n + 64.0 : 0.0;
     cap[Q_ELW] = (eng->opt_warm_pinel > 0.0) ? n : 0.0;
+    cap[Q_VBW] = (eng->opt_warm_pinel > 0.0) ? n : 0.0;
 }
 double queue_bytes_per_iteration(const trk3_engine *eng) {
     double cap[N_QUEUES]; queue_caps(eng, cap);
@@ -779,7 +786,7 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
         Queue &q = eng->qs[b].q[s];
         q = Queue{};
         if (cap[s] <= 0.0) continue;
-        int rc = alloc_queue(eng, q, (uint32_t)(cap[s] * (double)nb), eng->d_qcount + (s == Q_ELW ? QC_ELW(b) : QC_ELC(b) + (s - Q_ELC)));
+        int rc = alloc_queue(eng, q, (uint32_t)(cap[s] * (double)nb), eng->d_qcount + (s == Q_VBW ? QC_VBW(b) : (s == Q_ELW ? QC_ELW(b) : QC_ELC(b) + (s - Q_ELC))));
         if (rc) return rc;
     }
     for (int s = 0; s < N_SPECIES; ++s) {             // handed back by the cold kernels: a rarity
@@ -825,7 +832,7 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_i
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (budget > 0) { const uint32_t per_block = (uint32_t)budget * (uint32_t)(block / 32); grid = (n + per_block - 1) / per_block; }
     if (grid < 1) grid = 1;
-    const int pi = prof_begin(eng, warm ? N_CLASSES - 1 : (COLD ? N_SPECIES + 2 + SP : SP), st, n);
+    const int pi = prof_begin(eng, warm ? N_SPECIES + 4 + SP : (COLD ? N_SPECIES + 2 + SP : SP), st, n);
     kern<<<grid, block, smem, st>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, warm ? eng->opt_warm_slice : eng->opt_hot_slice, eng->opt_lockstep, budget, warm);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
@@ -970,6 +977,17 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
         eng->warm_P[i] = (ii + ie > 0.0) ? ii / (ii + ie) : 0.0;
     }
     eng->e_warm_auto = -1.0;
+    eng->warm_Eh.assign(tab->hi_E, tab->hi_E + tab->n_hi); eng->warm_Ph.assign(tab->n_hi, 1.0);
+    for (int i = 0; i < tab->n_hi; ++i) {       // the same for valence holes
+        const double E = tab->hi_E[i], li = tot.hi_tot[i];
+        int j = (int)(std::upper_bound(tab->he_E, tab->he_E + tab->n_he, E) - tab->he_E);
+        j = std::min(std::max(j, 1), tab->n_he - 1);
+        const double f = (E - tab->he_E[j - 1]) / (tab->he_E[j] - tab->he_E[j - 1]);
+        const double le = tab->he_L[j - 1] + std::min(1.0, std::max(0.0, f)) * (tab->he_L[j] - tab->he_L[j - 1]);
+        const double ii = (li > 0.0 && li < 1e15) ? 1.0 / li : 0.0, ie = (le > 0.0 && le < 1e15) ? 1.0 / le : 0.0;
+        eng->warm_Ph[i] = (ii + ie > 0.0) ? ii / (ii + ie) : 0.0;
+    }
+    eng->h_warm_auto = -1.0;
     CK(cudaStreamSynchronize(eng->stream));
     p.tally = old.tally; p.events = old.events; p.errors = old.errors; p.cnt_el = old.cnt_el; p.cnt_ph = old.cnt_ph; p.it = old.it;
 
@@ -1004,6 +1022,7 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
         for (int i = 0; i < 3; ++i) { CK(cudaStreamCreateWithPriority(&eng->stream_sp[i], cudaStreamNonBlocking, hi)); CK(cudaEventCreateWithFlags(&eng->ev_sp[i], cudaEventDisableTiming)); }
         CK(cudaEventCreateWithFlags(&eng->ev_gen, cudaEventDisableTiming));
         CK(cudaStreamCreateWithPriority(&eng->stream_w, cudaStreamNonBlocking, hi)); CK(cudaEventCreateWithFlags(&eng->ev_w, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithPriority(&eng->stream_wh, cudaStreamNonBlocking, hi)); CK(cudaEventCreateWithFlags(&eng->ev_wh, cudaEventDisableTiming));
     }
     CK(cudaEventCreate(&eng->ev0)); CK(cudaEventCreate(&eng->ev1));
     CK(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&eng->ev_join, cudaEventDisableTiming));
@@ -1014,8 +1033,8 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
     CK(cudaMemset(eng->d_tally, 0, (size_t)eng->lay.total * sizeof(double)));
     if ((rc = dev_alloc(eng, &eng->d_tally_bak, (size_t)eng->lay.total))) return rc;
     if ((rc = dev_alloc(eng, &eng->d_small, (size_t)TRK3_MAX_NT))) return rc;
-    if ((rc = dev_alloc(eng, &eng->d_counters, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 5)))) return rc;
-    if ((rc = dev_alloc(eng, &eng->d_counters_bak, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 5)))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_counters, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 6)))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_counters_bak, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 6)))) return rc;
     if ((rc = dev_alloc(eng, &eng->d_qcount, (size_t)QC_TOTAL))) return rc;
 
     p.tally = eng->d_tally;
@@ -1059,7 +1078,8 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "quota_min") eng->opt_quota_min = std::min(32, std::max(1, (int)v));
     else if (k == "overlap") eng->opt_overlap = (v != 0.0);
     else if (k == "cold_min") eng->opt_cold_min = std::max(1, (int)v);
-    else if (k == "warm_pinel") { eng->opt_warm_pinel = std::min(0.99, std::max(0.0, v)); eng->nb_alloc = 0; eng->e_warm_auto = -1.0; }
+    else if (k == "warm_pinel") { eng->opt_warm_pinel = std::min(0.99, std::max(0.0, v)); eng->nb_alloc = 0; eng->e_warm_auto = -1.0; eng->h_warm_auto = -1.0; }
+    else if (k == "warm_holes") eng->opt_warm_holes = (v != 0.0);
     else if (k == "warm_slice") eng->opt_warm_slice = std::max(1, (int)v);
     else if (k == "lean") eng->opt_lean = (v != 0.0);
     else if (k == "hot_classes") { eng->opt_hot_classes = std::min(N_ECLASS, std::max(1, (int)v)); eng->nb_alloc = 0; }
@@ -1118,7 +1138,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
     nb_max = std::min<int64_t>(nb_max, std::max<int64_t>(n_it, 1));
     int rc = ensure_batch(eng, (uint32_t)nb_max);
     if (rc) return rc;
-    const size_t n_counters = TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 5;
+    const size_t n_counters = TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 6;
     CK(cudaMemsetAsync(eng->d_counters, 0, n_counters * sizeof(unsigned long long), eng->stream));
     uint64_t waves = 0; const uint64_t launches0 = eng->launches;
     std::vector<double> h_diffS, h_totE; std::vector<uint32_t> h_diffN;
@@ -1137,7 +1157,12 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             for (size_t i = 0; i < eng->warm_E.size(); ++i) if (eng->warm_E[i] >= eng->hp.e_cold && eng->warm_P[i] >= eng->opt_warm_pinel) { eng->e_warm_auto = eng->warm_E[i]; break; }
         }
         eng->hp.e_warm = (eng->opt_warm_pinel > 0.0) ? std::max(eng->e_warm_auto, eng->hp.e_cold) : eng->hp.e_cold;
-        if (eng->opt_profile >= 2) fprintf(stderr, "e_cold %.3f e_warm %.3f eV\n", eng->hp.e_cold, eng->hp.e_warm);
+        if (eng->h_warm_auto < 0.0) {
+            eng->h_warm_auto = eng->warm_Eh.empty() ? 0.0 : eng->warm_Eh.back();
+            for (size_t i = 0; i < eng->warm_Eh.size(); ++i) if (eng->warm_Eh[i] >= eng->hp.h_cold && eng->warm_Ph[i] >= eng->opt_warm_pinel) { eng->h_warm_auto = eng->warm_Eh[i]; break; }
+        }
+        eng->hp.h_warm = (eng->opt_warm_pinel > 0.0 && eng->opt_warm_holes) ? std::max(eng->h_warm_auto, eng->hp.h_cold) : eng->hp.h_cold;
+        if (eng->opt_profile >= 2) fprintf(stderr, "e_cold %.3f e_warm %.3f eV, h_cold %.3f h_warm %.3f eV\n", eng->hp.e_cold, eng->hp.e_warm, eng->hp.h_cold, eng->hp.h_warm);
         for (int c = 1; c < N_ECLASS; ++c) eng->hp.e_class[c - 1] = (c < eng->opt_hot_classes) ? eng->opt_class_E[c - 1] : 1.0e300;
 
         CK(cudaMemcpyToSymbolAsync(c_p, &eng->hp, sizeof(DevP), 0, cudaMemcpyHostToDevice, eng->stream));
@@ -1183,6 +1208,9 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             uint32_t n_warm = h_cnt[QC_ELW(cur)];
             if (n_warm > eng->qs[cur].q[Q_ELW].cap) { overflow = true; n_warm = eng->qs[cur].q[Q_ELW].cap; }
             total += n_warm;
+            uint32_t n_warm_h = h_cnt[QC_VBW(cur)];
+            if (n_warm_h > eng->qs[cur].q[Q_VBW].cap) { overflow = true; n_warm_h = eng->qs[cur].q[Q_VBW].cap; }
+            total += n_warm_h;
             for (int s = 0; s < 2; ++s) if (cold[s] > eng->qs[0].q[N_SPECIES + s].cap) { overflow = true; cold[s] = eng->qs[0].q[N_SPECIES + s].cap; }
             if (h_cnt[QC_ION + 1] > eng->qs[0].q[Q_ION].cap) overflow = true;
             if (h_cnt[QC_SNAP] > eng->qs[0].q[Q_SNAP].cap) overflow = true;
@@ -1196,6 +1224,8 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
                 CK(cudaMemsetAsync(eng->d_qcount + QC_HEADC, 0, (N_ECLASS - 1) * sizeof(uint32_t), eng->stream));
                 CK(cudaMemsetAsync(eng->d_qcount + QC_ELW(nxt), 0, sizeof(uint32_t), eng->stream));
                 CK(cudaMemsetAsync(eng->d_qcount + QC_HEADW, 0, sizeof(uint32_t), eng->stream));
+                CK(cudaMemsetAsync(eng->d_qcount + QC_VBW(nxt), 0, sizeof(uint32_t), eng->stream));
+                CK(cudaMemsetAsync(eng->d_qcount + QC_HEADWH, 0, sizeof(uint32_t), eng->stream));
                 CK(cudaMemsetAsync(heads, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
                 // the species of a generation are independent of each other: the (few) valence holes, core holes and photons run
                 // on their own streams beside the electrons instead of lengthening the generation one after the other
@@ -1211,12 +1241,19 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
                     rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[cur].q[Q_ELW], 0, n_warm, eng->d_qcount + QC_HEADW, eng->qs[nxt], s4, 0, 0, 1); if (rc) return rc;
                     if (par) CK(cudaEventRecord(eng->ev_w, s4));
                 }
+                if (n_warm_h) {     // warm valence holes
+                    cudaStream_t s5 = par ? eng->stream_wh : eng->stream;
+                    if (par) CK(cudaStreamWaitEvent(s5, eng->ev_gen, 0));
+                    rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[cur].q[Q_VBW], 0, n_warm_h, eng->d_qcount + QC_HEADWH, eng->qs[nxt], s5, 0, 0, 1); if (rc) return rc;
+                    if (par) CK(cudaEventRecord(eng->ev_wh, s5));
+                }
                 if (hot[SP_PHOTON]) { if (par) CK(cudaStreamWaitEvent(s3, eng->ev_gen, 0)); rc = launch_wave<SP_PHOTON, false>(eng, eng->qs[cur].q[SP_PHOTON], 0, hot[SP_PHOTON], heads + SP_PHOTON, eng->qs[nxt], s3); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[2], s3)); }
                 if (par) {
                     if (hot[SP_VBHOLE]) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[0], 0));
                     if (hot[SP_COREHOLE]) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[1], 0));
                     if (hot[SP_PHOTON]) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[2], 0));
                     if (n_warm) CK(cudaStreamWaitEvent(eng->stream, eng->ev_w, 0));
+                    if (n_warm_h) CK(cudaStreamWaitEvent(eng->stream, eng->ev_wh, 0));
                 }
                 if (n_hot_el) {             // the pairs of this generation's impact ionisations join the next generation
                     const int pi = prof_begin(eng, SP_ELECTRON);
@@ -1252,6 +1289,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             CK(cudaMemsetAsync(eng->d_qcount + QC_ELC(nxt), 0, (N_ECLASS - 1) * sizeof(uint32_t), eng->stream));
             CK(cudaMemsetAsync(eng->d_qcount + QC_HEADC, 0, (N_ECLASS - 1) * sizeof(uint32_t), eng->stream));
             CK(cudaMemsetAsync(eng->d_qcount + QC_ELW(nxt), 0, sizeof(uint32_t), eng->stream));
+            CK(cudaMemsetAsync(eng->d_qcount + QC_VBW(nxt), 0, sizeof(uint32_t), eng->stream));
             CK(cudaMemsetAsync(heads, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
             if (h_x[SP_ELECTRON]) { rc = launch_hot_electrons(eng, eng->qs_x, h_x, nullptr, eng->qs[nxt]); if (rc) return rc; }
             if (h_x[SP_VBHOLE]) { rc = launch_hot_vbholes(eng, eng->qs_x.q[SP_VBHOLE], h_x[SP_VBHOLE], eng->qs[nxt]); if (rc) return rc; }
@@ -1338,7 +1376,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
     for (int q = 0; q < TRK3_N_ERRORS; ++q) st.errors[q] = h_c[TRK3_N_EVENT_CLASSES + q];
     st.n_electrons = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS]; st.n_photons = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 1];
     st.cold_events[0] = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 2]; st.cold_events[1] = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 3];
-    st.warm_events = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 4];
+    st.warm_events[0] = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 4]; st.warm_events[1] = h_c[TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 5];
     st.n_waves = waves; st.kernel_launches = eng->launches - launches0; st.device_ms = ms;
     static const double ev_bytes[TRK3_N_EVENT_CLASSES] = {176, 320, 144, 384, 208, 384, 280, 208, 248};
     for (int q = 0; q < TRK3_N_EVENT_CLASSES; ++q) st.algorithmic_bytes += ev_bytes[q] * (double)st.events[q];
@@ -1413,6 +1451,8 @@ void trk3_mc_destroy(trk3_engine *eng) {
     if (eng->ev_gen) cudaEventDestroy(eng->ev_gen);
     if (eng->stream_w) cudaStreamDestroy(eng->stream_w);
     if (eng->ev_w) cudaEventDestroy(eng->ev_w);
+    if (eng->stream_wh) cudaStreamDestroy(eng->stream_wh);
+    if (eng->ev_wh) cudaEventDestroy(eng->ev_wh);
     if (eng->ev_fork) cudaEventDestroy(eng->ev_fork);
     if (eng->ev_join) cudaEventDestroy(eng->ev_join);
     delete eng;

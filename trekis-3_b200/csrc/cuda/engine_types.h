@@ -121,6 +121,7 @@ struct DevP {
     // "warm" electrons, e_cold <= E < e_warm, can still ionise but rarely do; the engine follows them with the elastic-only
     // kernel, generation by generation (e_warm = e_cold: no such class)
     double e_warm;
+    double h_warm;                                       // the same for valence holes (kinetic energy)
     // ---- time grid: tg[i-1] = min(time_grid(i), Tim), i = 1..Nt
     int32_t Nt;
     double tg[TRK3_MAX_NT];

@@ -1219,7 +1219,7 @@ TRK_HD bool electron_is_cold(const DevP &p, const Rec &e) { return e.E < p.e_col
 TRK_HD bool vbhole_is_cold(const DevP &p, const Rec &h) { return h.Ehkin < p.h_cold || !(h.tn < p.Tim); }
 
 TRK_HD bool electron_leaves_hot(const DevP &p, const Rec &e) { return e.E < p.e_warm && e.tn < p.Tim; }      // e_warm >= e_cold
-TRK_HD bool vbhole_leaves_hot(const DevP &p, const Rec &h) { return h.Ehkin < p.h_cold && h.tn < p.Tim; }
+TRK_HD bool vbhole_leaves_hot(const DevP &p, const Rec &h) { return h.Ehkin < p.h_warm && h.tn < p.Tim; }      // h_warm >= h_cold
 
 enum StepStatus { ST_DONE = 0, ST_CONT = 1, ST_MOVE = 2, ST_MOVE_HOT = 3 };
 // ST_DONE: history finished.  ST_CONT: call again.  ST_MOVE: hand the record to push() (it now belongs to the other
@@ -1261,15 +1261,27 @@ TRK_HD void begin_vbhole(const DevP &p, const Rec &h, int &ig, Cache &k) {
     ig = interval_of(p, h.t0);
     if (h.tn < p.Tim) cache_vbhole(p, h.Ehkin, k);
 }
+// `warm` (COLD only): as for electrons (step_electron) -- valence holes with h_cold <= Ehkin < h_warm can ionise but rarely
+// do; the elastic-only handler follows them and hands one over (stream rewound by the draw) when its roulette selects the
+// ionisation.  (A cold hole never ionises: vbhole_roulette_inelastic needs HIMFP < 1e15.)
 template <bool COLD, class C>
-TRK_HD int step_vbhole(C &c, Rec &h, int &ig, Cache &k) {
+TRK_HD int step_vbhole(C &c, Rec &h, int &ig, Cache &k, bool warm = false) {
     const DevP &p = c.p;
-    if (COLD && h.tn < p.tg[p.Nt - 1] && !(h.Ehkin < p.h_cold)) return ST_MOVE;
+    double RN = 0.0;
+    if (COLD && h.tn < p.tg[p.Nt - 1]) {
+        if (!(h.Ehkin < (warm ? p.h_warm : p.h_cold))) return ST_MOVE;
+        if (warm) {
+            event_begin(h);
+            RN = rn(p, h);
+            if (vbhole_roulette_inelastic(k, RN)) { h.ctr--; return ST_MOVE_HOT; }
+        }
+    }
     while (ig <= p.Nt && p.tg[ig - 1] <= h.tn) { c.snap(SP_VBHOLE, h, ig); ++ig; }
     if (ig > p.Nt) return ST_DONE;
     if (COLD) {
-        event_begin(h);
-        vbhole_event_t<EV_ELASTIC>(c, h, ig, k, rn(p, h));
+        if (!warm) { event_begin(h); RN = rn(p, h); }
+        vbhole_event_t<EV_ELASTIC>(c, h, ig, k, RN);
+        if (warm) return (h.Ehkin < p.h_cold || !(h.tn < p.Tim) || !(h.Ehkin < p.h_warm)) ? ST_MOVE : ST_CONT;
         return (h.Ehkin < p.h_cold) ? ST_CONT : ST_MOVE;
     }
     event_begin(h);

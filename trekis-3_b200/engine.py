@@ -122,12 +122,12 @@ class Engine:
         self._check(_gpu().trk3_mc_set_device_tallies(self._h, C.c_void_p(int(device_ptr))), "set_device_tallies")
 
     KERNEL_CLASSES = ("k_wave<electron,hot>", "k_wave<vbhole,hot>", "k_wave<corehole>", "k_wave<photon>", "k_shi", "finalize",
-                      "k_wave<electron,cold>", "k_wave<vbhole,cold>", "k_wave<electron,warm>")
+                      "k_wave<electron,cold>", "k_wave<vbhole,cold>", "k_wave<electron,warm>", "k_wave<vbhole,warm>")
 
     def kernel_times(self):
-        ms = (C.c_double * 9)()
-        n = (C.c_uint64 * 9)()
-        _gpu().trk3_mc_kernel_times(self._h, ms, n, 9)
+        ms = (C.c_double * 10)()
+        n = (C.c_uint64 * 10)()
+        _gpu().trk3_mc_kernel_times(self._h, ms, n, 10)
         return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(self.KERNEL_CLASSES)}
 
     def device_tallies_ptr(self):
