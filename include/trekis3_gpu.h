@@ -228,7 +228,7 @@ int trk3_mc_iteration_energies(trk3_engine *eng, double *out, int64_t capacity_d
 int trk3_mc_set_stream(trk3_engine *eng, void *cuda_stream);
 int trk3_mc_set_device_tallies(trk3_engine *eng, double *device_buffer);
 /* Device time per kernel class since option "profile"=1 (0 hot electron wave, 1 hot valence-hole wave, 2 core-hole
- * wave, 3 photon wave, 4 ion tracks, 5 finalize, 6 cold electrons, 7 cold valence holes, 8 warm electrons, 9 warm valence holes); returns the number
+ * wave, 3 photon wave, 4 ion tracks, 5 pair creation + snapshots + folding, 6 cold electrons, 7 cold valence holes, 8 warm electrons, 9 warm valence holes); returns the number
  * of classes.  Classes 0-3 and 8 of one generation run on concurrent streams: their times overlap. */
 int trk3_mc_kernel_times(trk3_engine *eng, double *ms, uint64_t *launches, int n);
 

@@ -269,3 +269,24 @@ def test_gpu_table_builder_gives_the_host_tables(tmp_path, cfg):
         worst = max(worst, rel)
         assert rel <= 1e-12, (k, rel)
     print(f"{cfg}: worst relative difference GPU vs host tables {worst:.3e}")
+
+
+def test_two_engines_on_one_device_from_two_threads(case_c1):
+    """Engines that share a device take turns (the kernels read one __constant__ image per device): concurrent calls
+    from two host threads must give what the same calls give one after the other."""
+    import threading
+    a, b = tk.Engine(case_c1), tk.Engine(case_c1)
+    ref_a, sa = a.run(0, 6)
+    ref_b, sb = b.run(6, 12)
+    out = {}
+
+    def work(name, eng, lo, hi):
+        out[name] = eng.run(lo, hi)
+
+    for rep in range(3):
+        th = [threading.Thread(target=work, args=("a", a, 0, 6)), threading.Thread(target=work, args=("b", b, 6, 12))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert out["a"][1]["total_events"] == sa["total_events"] and out["b"][1]["total_events"] == sb["total_events"]
+        assert rel_close(out["a"][0], ref_a, 1e-9) and rel_close(out["b"][0], ref_b, 1e-9)
+        assert not out["a"][1]["errors"] and not out["b"][1]["errors"]

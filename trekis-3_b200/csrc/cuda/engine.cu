@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "physics.cuh"
@@ -588,7 +589,7 @@ struct trk3_engine {
     uint64_t h2d_bytes = 0;                 // bytes of the last table binding
     double nel_est = 1000.0;
     // options
-    int opt_batch = 1024, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
+    int opt_batch = 4096, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
     int opt_hot_slice = 64, opt_inel_min = 1, opt_overlap = 0, opt_cold_min = 16384;
     int opt_shi_lanes = 0;                 // 0: one ion per warp, the lanes share the work of a collision (k_shi)
     int opt_cold_budget = 0, opt_cold_smem_kb = 0, opt_hot_block = 0;      // see the `overlap` schedule in trk3_mc_run_device
@@ -1126,8 +1127,13 @@ int trk3_mc_download_tallies(trk3_engine *eng, double *dst) {
     return TRK3_OK;
 }
 
+// The kernels read the run's constants from ONE __constant__ image per device (c_p): engines that share a device take
+// turns (handles on different devices, one per host thread, run concurrently).
+static std::mutex g_device_mutex[64];
+
 int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_stats *stats) {
     if (!eng || it_end < it_begin || it_begin < 0 || it_end > 0xffffffffll) return TRK3_E_INVALID;
+    std::lock_guard<std::mutex> device_turn(g_device_mutex[eng->device & 63]);
     CK(cudaSetDevice(eng->device));
     const int Nt = eng->lay.Nt;
     const int64_t n_it = it_end - it_begin;
@@ -1256,7 +1262,7 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
                     if (n_warm_h) CK(cudaStreamWaitEvent(eng->stream, eng->ev_wh, 0));
                 }
                 if (n_hot_el) {             // the pairs of this generation's impact ionisations join the next generation
-                    const int pi = prof_begin(eng, SP_ELECTRON);
+                    const int pi = prof_begin(eng, N_SPECIES + 1);       // timed with the finalisation kernels
                     k_ion_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(eng->qs[0].q[Q_ION], eng->qs[nxt]);
                     k_ion_reset<<<1, 32, 0, eng->stream>>>(eng->d_qcount + QC_ION);
                     prof_end(eng, pi);
