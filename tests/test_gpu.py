@@ -208,7 +208,7 @@ def test_full_size_c2_photons_and_decays():
     T = _invariants(case, t, s, n)
     assert s["total_events"] > 3e7 and s["events"]["auger"] > 1e4 and s["cold_events"]["electron"] > 0.9 * s["events"]["el_elastic"]
     # the same 1000 iterations in four batches of 250 with other kernel options: identical histories
-    t2, s2 = tk.Engine(case, batch=250, hot_slice=16, inel_min=8).run(0, n)
+    t2, s2 = tk.Engine(case, batch=250, hot_slice=16, hot_classes=1, warm_pinel=0).run(0, n)
     assert s2["events"] == s["events"]
     i = tk.TALLY_NAMES.index("Out_diff_coeff")
     lay = case.layout()

@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(256) k_snapshot(Queue sq, QueueSet qout, int u
 // k_wave<SP, COLD>: records [first, n_in) of queue qin, histories followed with lane refill until they end or
 // have to change queue (hot -> cold when the particle can no longer ionise, core hole -> valence hole, ...).
 template <int SP, bool COLD, bool LEAN>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int lockstep, int budget, int warm) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int warm) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
@@ -371,19 +371,14 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
     Rec r;
     Cache k{};
     int ig = 0, nev = 0;
-    // `budget` > 0: a warp claims at most that many records and then lets its block end, so that the grid is a stream of
-    // short-lived blocks (the launch sizes the grid to cover the queue).  Cold kernels that run beside the hot cascade are
-    // launched this way: the blocks of the next hot generation (higher stream priority) find room within one block lifetime.
-    int left = budget > 0 ? budget : 0x7fffffff;
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
         if (idle && !exhausted && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
-            const int nidle = min(__popc(idle), left);
+            const int nidle = __popc(idle);
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(head, (uint32_t)nidle);
             base = __shfl_sync(0xffffffffu, base, 0) + first;
-            left -= nidle;
-            if (base + (uint32_t)nidle >= n_in || left <= 0) exhausted = true;
+            if (base + (uint32_t)nidle >= n_in) exhausted = true;
             if (!active) {
                 const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
                 const uint32_t my = base + rank;
@@ -396,11 +391,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
                 }
             }
         }
-        // The kernels are bound by instruction fetch (ncu: gcc__cache_requests_type_instruction at 98 % of peak, the loop
-        // body is several times the SM's instruction cache).  With `lockstep` the warps of a block start every round
-        // together, so that the lines one warp fetches are still cached when the others need them.
-        if (lockstep) { if (!__syncthreads_or((active || !exhausted) ? 1 : 0)) break; }
-        else if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; continue; }
+        if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; continue; }
         if (active) {
             int st;
             if (SP == SP_ELECTRON) st = step_electron<COLD>(c, r, ig, k, COLD && warm);
@@ -421,11 +412,10 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
     block_epilogue(c_p, s_tally, s_cnt, COLD ? SP : -1, warm);
 }
 
-// k_hot<SP>: one generation of carriers that can still ionise (SP = electron or valence hole).  The two collision
-// channels have very different code (an impact ionisation creates two particles), so letting every lane branch on its
-// own would make each warp pay for both channels in every round.  Instead the lanes of a warp vote: lanes whose
-// channel roulette selected the ionisation wait until `inel_min` of them have gathered (or nothing else is left to
-// do), and then take that path together; elastic collisions are never delayed.
+// k_hot<SP>: one generation of carriers that can still ionise (SP = electron or valence hole).  Every round a lane draws
+// the channel roulette of its collision first, so that the kernel (not the event handler) branches on the channel: the
+// handlers are instantiated for one channel each, and for electrons the head and tail of the collision are shared.
+// (Making the ionising lanes wait until several have gathered was measured: no gain once the pairs were deferred.)
 template <int SP> __device__ inline bool hot_roulette(const Cache &k, double RN) { return SP == SP_ELECTRON ? electron_roulette_inelastic(k, RN) : vbhole_roulette_inelastic(k, RN); }
 template <int SP, int MODE, class C> __device__ inline void hot_event(C &c, Rec &r, int ig, Cache &k, double RN) {
     if (SP == SP_ELECTRON) electron_event_t<MODE>(c, r, ig, k, RN); else vbhole_event_t<MODE>(c, r, ig, k, RN);
@@ -447,13 +437,10 @@ struct HotIn {
     int slice[N_ECLASS];           // collisions after which a history of class c goes back to the queue (promoted by one class)
     uint32_t wend[N_ECLASS];       // warps [wend[c+1], wend[c]) start on class c (wend[ncls] = 0)
     int ncls;
-    int hist;                      // debugging: fill g_hot_hist
 };
 
-// debugging aid (option "profile" >= 3): collisions per history and energy class of the last k_hot<electron> launch
-__device__ unsigned int g_hot_hist[N_ECLASS][66];
 template <int SP, bool LEAN>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn in, QueueSet qout, int use_smem, int refill_min, int inel_min, int lockstep) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn in, QueueSet qout, int use_smem, int refill_min) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
@@ -496,8 +483,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn
                 }
             }
         }
-        if (lockstep) { if (!__syncthreads_or((active || !exhausted) ? 1 : 0)) break; }
-        else if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; continue; }
+        if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; continue; }
         // snapshots of the current free flight, then the channel roulette of the collision that ends it
         int want = 0;       // 1 elastic, 2 inelastic
         if (active) {
@@ -508,9 +494,8 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn
                 want = hot_roulette<SP>(k, RN) ? 2 : 1;
             }
         }
-        const unsigned m_in = __ballot_sync(0xffffffffu, want == 2), m_el = __ballot_sync(0xffffffffu, want == 1);
         bool done_event = false;
-        const bool go_in = (want == 2) && (__popc(m_in) >= inel_min || !m_el);
+        const bool go_in = (want == 2);
         if (SP == SP_ELECTRON) {
             // head and tail of a collision are common to both channels: lanes that disagree on the channel only take the
             // channel-specific middle part one after the other (electron_event_head / _inel / _elast / _tail, physics.cuh)
@@ -532,10 +517,6 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn
             else if (nev >= my_slice && r.tn < c_p.Tim) {
                 if (SP == SP_ELECTRON) r.shell = -1 - my_next;
                 c.push_hot(SP, r); active = false;
-            }
-            if (in.hist && SP == SP_ELECTRON && (!active || !(r.tn < c_p.Tim))) {
-                const int cc = (r.E >= c_p.e_class[0]) + (r.E >= c_p.e_class[1]) + (r.E >= c_p.e_class[2]);
-                atomicAdd(&g_hot_hist[cc][min(nev, 65)], 1u);
             }
         }
     }
@@ -590,9 +571,9 @@ struct trk3_engine {
     double nel_est = 1000.0;
     // options
     int opt_batch = 4096, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
-    int opt_hot_slice = 64, opt_inel_min = 1, opt_overlap = 0, opt_cold_min = 16384;
+    int opt_hot_slice = 64, opt_overlap = 0, opt_cold_min = 16384;
     int opt_shi_lanes = 0;                 // 0: one ion per warp, the lanes share the work of a collision (k_shi)
-    int opt_cold_budget = 0, opt_cold_smem_kb = 0, opt_hot_block = 0;      // see the `overlap` schedule in trk3_mc_run_device
+    int opt_cold_smem_kb = 0, opt_hot_block = 0;      // see the `overlap` schedule in trk3_mc_run_device
     // energy classes of the hot electrons: lower edges [eV] of classes 1..3 and the most histories a warp follows at once
     double opt_warm_pinel = 0.5;           // electrons are "warm" below the energy where the ionisation probability per collision reaches this (0: off)
     int opt_warm_slice = 64;
@@ -604,7 +585,7 @@ struct trk3_engine {
     double opt_class_E[N_ECLASS - 1] = {200.0, 500.0, 1300.0};
     int opt_class_quota[N_ECLASS] = {32, 8, 3, 1};
     int opt_class_slice[N_ECLASS] = {8, 16, 32, 64};
-    int opt_spread = 1, opt_quota_min = 1, opt_lockstep = 0, opt_species_streams = 1, opt_defer_snap = 1;
+    int opt_spread = 1, opt_quota_min = 1, opt_species_streams = 1, opt_defer_snap = 1;
 
     double opt_cap_factor = 2.0;
     size_t opt_queue_bytes_max = (size_t)64 << 30;       // of the 180 GB of a B200
@@ -814,7 +795,7 @@ inline bool engine_is_lean(const trk3_engine *eng) {
     return eng->opt_lean && eng->cfg.kind_of_EMFP == 1 && !(eng->cfg.work_function > 0.0) && eng->opt_defer_snap;
 }
 template <int SP, bool COLD>
-int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_in, uint32_t *head, const QueueSet &qout, cudaStream_t st = nullptr, int budget = 0, size_t smem_floor = 0, int warm = 0) {
+int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_in, uint32_t *head, const QueueSet &qout, cudaStream_t st = nullptr, size_t smem_floor = 0, int warm = 0) {
     const uint32_t n = n_in - first;
     if (!st) st = eng->stream;
     size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
@@ -831,10 +812,9 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_i
     // persistent-style grid: a multiple of the SM count, never more blocks than there is work for
     uint32_t want = (n + block - 1) / block;
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
-    if (budget > 0) { const uint32_t per_block = (uint32_t)budget * (uint32_t)(block / 32); grid = (n + per_block - 1) / per_block; }
     if (grid < 1) grid = 1;
     const int pi = prof_begin(eng, warm ? N_SPECIES + 4 + SP : (COLD ? N_SPECIES + 2 + SP : SP), st, n);
-    kern<<<grid, block, smem, st>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, warm ? eng->opt_warm_slice : eng->opt_hot_slice, eng->opt_lockstep, budget, warm);
+    kern<<<grid, block, smem, st>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, warm ? eng->opt_warm_slice : eng->opt_hot_slice, warm);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
@@ -888,10 +868,8 @@ int launch_hot(trk3_engine *eng, const Queue *const *qin, const uint32_t *n_in, 
         for (int c = 0; c < ncls; ++c) fprintf(stderr, "  c%d n %u w %u q %d", c, in.n[c], w[c], in.quota[c]);
         fprintf(stderr, "\n");
     }
-    in.hist = (eng->opt_profile >= 3);
-    if (in.hist && SP == SP_ELECTRON) { static unsigned int zero[N_ECLASS][66]; cudaMemcpyToSymbolAsync(g_hot_hist, zero, sizeof zero, 0, cudaMemcpyHostToDevice, st); }
     const int pi = prof_begin(eng, SP, st, n_tot);
-    kern<<<grid, block, smem, st>>>(in, qout, use_smem, eng->opt_refill_min, eng->opt_inel_min, eng->opt_lockstep);
+    kern<<<grid, block, smem, st>>>(in, qout, use_smem, eng->opt_refill_min);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
@@ -1074,7 +1052,6 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "shi_lanes") eng->opt_shi_lanes = std::min(32, std::max(0, (int)v));
     else if (k == "defer_snap") { eng->opt_defer_snap = (v != 0.0); eng->nb_alloc = 0; }
     else if (k == "species_streams") eng->opt_species_streams = (v != 0.0);
-    else if (k == "lockstep") eng->opt_lockstep = (v != 0.0);
     else if (k == "spread") eng->opt_spread = (v != 0.0);
     else if (k == "quota_min") eng->opt_quota_min = std::min(32, std::max(1, (int)v));
     else if (k == "overlap") eng->opt_overlap = (v != 0.0);
@@ -1095,10 +1072,8 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "class_q1") eng->opt_class_quota[1] = std::min(32, std::max(1, (int)v));
     else if (k == "class_q2") eng->opt_class_quota[2] = std::min(32, std::max(1, (int)v));
     else if (k == "class_q3") eng->opt_class_quota[3] = std::min(32, std::max(1, (int)v));
-    else if (k == "cold_budget") eng->opt_cold_budget = std::max(0, (int)v);
     else if (k == "cold_smem_kb") eng->opt_cold_smem_kb = std::max(0, (int)v);
     else if (k == "hot_block") eng->opt_hot_block = std::min(TRK_BLOCK_MAX, std::max(0, ((int)v / 32) * 32));
-    else if (k == "inel_min") eng->opt_inel_min = std::min(32, std::max(1, (int)v));
     else if (k == "max_generations") eng->opt_max_generations = std::max(1, (int)v);
     else if (k == "profile") { eng->opt_profile = (int)v; for (auto &x : eng->class_ms) x = 0; for (auto &x : eng->class_launches) x = 0; }
     else return TRK3_E_INVALID;
@@ -1195,16 +1170,6 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             uint32_t h_cnt[QC_TOTAL];          // hot counts of both generations, cold counts, set X, ionisation queue, ..., class queues
             CK(cudaMemcpyAsync(h_cnt, eng->d_qcount, sizeof h_cnt, cudaMemcpyDeviceToHost, eng->stream));
             CK(cudaStreamSynchronize(eng->stream));
-            if (eng->opt_profile >= 3 && gen > 0) {
-                unsigned int hh[N_ECLASS][66];
-                cudaMemcpyFromSymbol(hh, g_hot_hist, sizeof hh);
-                for (int c = 0; c < N_ECLASS; ++c) {
-                    fprintf(stderr, "hist gen %d final class %d:", gen - 1, c);
-                    const int edges[] = {1, 2, 3, 5, 9, 17, 33, 64, 65, 66};
-                    for (int b = 0; b + 1 < 10; ++b) { unsigned long long sum = 0; for (int i = edges[b]; i < edges[b + 1]; ++i) sum += hh[c][i]; fprintf(stderr, " [%d,%d) %llu", edges[b], edges[b + 1], sum); }
-                    fprintf(stderr, "\n");
-                }
-            }
             uint32_t *hot = h_cnt + QC_HOT(cur), *cold = h_cnt + QC_COLD, *hotc = h_cnt + QC_ELC(cur);
             uint64_t total = 0;
             if (gen == 0 && h_cnt[QC_HOT(1) + SP_ELECTRON] > eng->qs[1].q[SP_ELECTRON].cap) overflow = true;     // staged ion collisions
@@ -1244,13 +1209,13 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
                 if (n_warm) {       // warm electrons: the elastic-only kernel, one time slice per generation
                     cudaStream_t s4 = par ? eng->stream_w : eng->stream;
                     if (par) CK(cudaStreamWaitEvent(s4, eng->ev_gen, 0));
-                    rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[cur].q[Q_ELW], 0, n_warm, eng->d_qcount + QC_HEADW, eng->qs[nxt], s4, 0, 0, 1); if (rc) return rc;
+                    rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[cur].q[Q_ELW], 0, n_warm, eng->d_qcount + QC_HEADW, eng->qs[nxt], s4, 0, 1); if (rc) return rc;
                     if (par) CK(cudaEventRecord(eng->ev_w, s4));
                 }
                 if (n_warm_h) {     // warm valence holes
                     cudaStream_t s5 = par ? eng->stream_wh : eng->stream;
                     if (par) CK(cudaStreamWaitEvent(s5, eng->ev_gen, 0));
-                    rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[cur].q[Q_VBW], 0, n_warm_h, eng->d_qcount + QC_HEADWH, eng->qs[nxt], s5, 0, 0, 1); if (rc) return rc;
+                    rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[cur].q[Q_VBW], 0, n_warm_h, eng->d_qcount + QC_HEADWH, eng->qs[nxt], s5, 0, 1); if (rc) return rc;
                     if (par) CK(cudaEventRecord(eng->ev_wh, s5));
                 }
                 if (hot[SP_PHOTON]) { if (par) CK(cudaStreamWaitEvent(s3, eng->ev_gen, 0)); rc = launch_wave<SP_PHOTON, false>(eng, eng->qs[cur].q[SP_PHOTON], 0, hot[SP_PHOTON], heads + SP_PHOTON, eng->qs[nxt], s3); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[2], s3)); }
@@ -1275,11 +1240,10 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             // (the records [cold_done, cold) were written by kernels that have completed: the stream was just synchronised)
             if (cold_pending && (!total || (eng->opt_overlap && cold_pending >= (uint64_t)eng->opt_cold_min))) {
                 CK(cudaMemsetAsync(heads + N_SPECIES, 0, 2 * sizeof(uint32_t), sc));
-                // beside a running hot cascade: short-lived blocks (and optionally fewer of them per SM), see k_wave `budget`
-                const int bud = (eng->opt_overlap && total) ? eng->opt_cold_budget : 0;
+                // beside a running hot cascade: optionally fewer cold blocks per SM (shared-memory floor)
                 const size_t sfl = (eng->opt_overlap && total) ? (size_t)eng->opt_cold_smem_kb * 1024 : 0;
-                if (cold[0] > cold_done[0]) { rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[0].q[Q_EL_COLD], cold_done[0], cold[0], heads + Q_EL_COLD, eng->qs_x, sc, bud, sfl); if (rc) return rc; }
-                if (cold[1] > cold_done[1]) { rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[0].q[Q_VB_COLD], cold_done[1], cold[1], heads + Q_VB_COLD, eng->qs_x, sc, bud, sfl); if (rc) return rc; }
+                if (cold[0] > cold_done[0]) { rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[0].q[Q_EL_COLD], cold_done[0], cold[0], heads + Q_EL_COLD, eng->qs_x, sc, sfl); if (rc) return rc; }
+                if (cold[1] > cold_done[1]) { rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[0].q[Q_VB_COLD], cold_done[1], cold[1], heads + Q_VB_COLD, eng->qs_x, sc, sfl); if (rc) return rc; }
                 cold_done[0] = cold[0]; cold_done[1] = cold[1];
             }
             if (total) continue;
