@@ -128,7 +128,14 @@ struct DevCtxT {
         q.col[5][slot] = r.X; q.col[6][slot] = r.Y; q.col[7][slot] = r.Z; q.col[8][slot] = r.L; q.col[9][slot] = r.theta; q.col[10][slot] = r.phi;
         q.id[slot] = r.id; q.ctr[slot] = r.ctr; q.iter[slot] = r.iter; q.shell[slot] = r.shell;
     }
+    // The lean kernels queue their snapshots, so the only tally they write is the lattice energy (deposit_lattice): their
+    // block-private copy holds Out_Elat alone (2 KB instead of ~46 KB per block: the rest of the SM's memory stays L1 cache).
     __device__ void tally(int id, int64_t idx, double v) {
+        if (LEAN) {
+            if (s_tally && id == TRK3_OUT_ELAT) atomicAdd(&s_tally[idx], v);
+            else atomicAdd(&p.tally[p.g_off[id] + idx], v);
+            return;
+        }
         const int so = p.s_off[id];
         if (s_tally && so >= 0) atomicAdd(&s_tally[so + idx], v);
         else atomicAdd(&p.tally[p.g_off[id] + idx], v);
@@ -153,9 +160,12 @@ __device__ inline void block_prologue(double *s_tally, unsigned int *s_cnt, int 
     if (threadIdx.x < S_NCNT) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
 }
-__device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned int *s_cnt, int cold_species = -1, int warm = 0) {
+__device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned int *s_cnt, int cold_species = -1, int warm = 0, bool elat_only = false) {
     __syncthreads();
-    if (s_tally) {
+    if (s_tally && elat_only) {
+        double *g = p.tally + p.g_off[TRK3_OUT_ELAT];
+        for (int i = threadIdx.x; i < p.s_len[TRK3_OUT_ELAT]; i += blockDim.x) { const double v = s_tally[i]; if (v != 0.0) atomicAdd(g + i, v); }
+    } else if (s_tally) {
         // flush the private copy once per block (non-zero bins only)
         for (int id = 0; id < TRK3_N_TALLIES; ++id) {
             const int so = p.s_off[id];
@@ -364,7 +374,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
-    block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? c_p.s_total : 0);
+    block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? (LEAN ? c_p.s_len[TRK3_OUT_ELAT] : c_p.s_total) : 0);
     DevCtxT<LEAN> c{c_p, qout, s_tally, s_cnt, c_p.defer_snap};
     const int lane = threadIdx.x & 31;
     bool active = false, exhausted = false;
@@ -409,7 +419,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qi
             }
         }
     }
-    block_epilogue(c_p, s_tally, s_cnt, COLD ? SP : -1, warm);
+    block_epilogue(c_p, s_tally, s_cnt, COLD ? SP : -1, warm, LEAN);
 }
 
 // k_hot<SP>: one generation of carriers that can still ionise (SP = electron or valence hole).  Every round a lane draws
@@ -444,7 +454,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
-    block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? c_p.s_total : 0);
+    block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? (LEAN ? c_p.s_len[TRK3_OUT_ELAT] : c_p.s_total) : 0);
     DevCtxT<LEAN> c{c_p, qout, s_tally, s_cnt, c_p.defer_snap};
     const int lane = threadIdx.x & 31;
     bool active = false, exhausted = false, have_rn = false;
@@ -520,7 +530,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn
             }
         }
     }
-    block_epilogue(c_p, s_tally, s_cnt);
+    block_epilogue(c_p, s_tally, s_cnt, -1, 0, LEAN);
 }
 
 __global__ void k_iter_prefix(FoldAux a) {
@@ -798,12 +808,12 @@ template <int SP, bool COLD>
 int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_in, uint32_t *head, const QueueSet &qout, cudaStream_t st = nullptr, size_t smem_floor = 0, int warm = 0) {
     const uint32_t n = n_in - first;
     if (!st) st = eng->stream;
-    size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
+    const bool lean = engine_is_lean(eng);
+    size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)(lean ? eng->hp.s_len[TRK3_OUT_ELAT] : eng->hp.s_total) * sizeof(double) : 8;
     int use_smem = eng->opt_use_smem;
     const size_t smem_max = (size_t)eng->smem_optin - 1024;             // static shared memory + driver reserve
     if (smem > smem_max) { smem = 8; use_smem = 0; }                    // too many output times for shared memory: global atomics
     if (smem < smem_floor && smem_floor <= smem_max) smem = smem_floor; // occupancy limiter: leaves room on every SM for the blocks of another kernel
-    const bool lean = engine_is_lean(eng);
     auto kern = lean ? k_wave<SP, COLD, true> : k_wave<SP, COLD, false>;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = eng->opt_blocks_per_sm;
@@ -824,11 +834,11 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_i
 template <int SP>
 int launch_hot(trk3_engine *eng, const Queue *const *qin, const uint32_t *n_in, uint32_t *const *head, int ncls, const QueueSet &qout, cudaStream_t st = nullptr) {
     if (!st) st = eng->stream;
-    size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
+    const bool lean = engine_is_lean(eng);
+    size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)(lean ? eng->hp.s_len[TRK3_OUT_ELAT] : eng->hp.s_total) * sizeof(double) : 8;
     int use_smem = eng->opt_use_smem;
     const size_t smem_max = (size_t)eng->smem_optin - 1024;
     if (smem > smem_max) { smem = 8; use_smem = 0; }
-    const bool lean = engine_is_lean(eng);
     auto kern = lean ? k_hot<SP, true> : k_hot<SP, false>;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = eng->opt_blocks_per_sm;
