@@ -36,6 +36,19 @@ int trk3h_dcs_eval_host(const trk3_dcs_ctx *ctx, const trk3_dcs_task *tasks, int
 int trk3h_save_tables(trk3h_case *c, const char *path, char *err, int errlen);
 int trk3h_load_tables(trk3h_case *c, const char *path, char *err, int errlen);
 
+/* The reference's own on-disk table cache (Analytical_IMFPs.f90:262-786, 917-1606, 2306-2349, 2462-2506, 2657-2707;
+ * reader of the ion files Reading_files_and_parameters.f90:2855-2903): <out_root>/OUTPUT_<material>/OUTPUT_*_IMFPs_*.dat,
+ * *_EMFPs_*.dat, diff_CS/<one file per shell and grid energy>, OUTPUT_<ion>_in_<material>/OUTPUT_<ion>_*_{IMFP,dEdx,
+ * effective_charges,Range}.dat, same names, row layout and number formats ('(f)', '(e)', '(es)' of real(8) = F25.16,
+ * E25.16, ES25.16, which the reference reads back as fixed 25-character fields).
+ * write: the built tables of the case (e.g. built on the GPU) -> files the Fortran program accepts as its cache.
+ * read:  tables cached by the reference (or by write) -> the case, instead of trk3h_build_tables; fails (and leaves the case
+ *        without tables) if a file is missing or its row count differs from the energy grid, as the reference decides to redo.
+ * name:  one component of the layout: dir_material, dir_ion, dir_diff, el_imfp, hole_imfp, photon_imfp, el_emfp, hole_emfp, shi_stem */
+int trk3h_write_reference_cache(trk3h_case *c, const char *out_root, int *n_files, char *err, int errlen);
+int trk3h_read_reference_cache(trk3h_case *c, const char *out_root, int threads, char *err, int errlen);
+int trk3h_reference_cache_name(trk3h_case *c, const char *which, char *out, int outlen);
+
 /* Flattened views; valid until the next trk3h_* call that modifies the case. */
 const trk3_config *trk3h_config(trk3h_case *c);
 const trk3_tables *trk3h_tables(trk3h_case *c);

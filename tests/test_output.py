@@ -9,7 +9,7 @@ import trekis3_b200 as tk
 from trekis3_b200.host import split_tallies
 import emul_api
 
-E_FIELD = re.compile(r"^ [ -]0\.\d{15}E[+-]\d{3}$")          # Intel default of '(e)' for real(8): E24.15E3
+E_FIELD = re.compile(r"^ +-?0\.\d{16}E[+-]\d{2}$")            # '(e)' of real(8): E25.16 (csrc/host/fortran_fmt.hpp)
 
 
 def read_table(path, skip=1):
@@ -40,18 +40,18 @@ def test_output_tree_matches_the_reference_layout(tmp_path):
     assert files == expected
     lay = case.layout()
     T = split_tallies(lay, t)
-    # Total_numbers.txt: header + Nt rows of 6 fields of 24 characters
+    # Total_numbers.txt: header + Nt rows of 6 fields of 25 characters
     lines = open(os.path.join(d, "Total_numbers.txt")).read().splitlines()
     assert lines[0] == "#Time[fs]    Ne    Ne_Emitted    Energy[eV]     Energy_Emitted[eV] N_photons"
-    assert len(lines) == 1 + lay.Nt and all(len(l) == 6 * 24 for l in lines[1:])
-    assert all(E_FIELD.match(lines[1][i:i + 24]) for i in range(0, 6 * 24, 24))
+    assert len(lines) == 1 + lay.Nt and all(len(l) == 6 * 25 for l in lines[1:])
+    assert all(E_FIELD.match(lines[1][i:i + 25]) for i in range(0, 6 * 25, 25))
     tot = read_table(os.path.join(d, "Total_numbers.txt"))
     assert np.allclose(tot[:, 0], [0.01, 0.1, 1.0, 10.0, 100.0])
     assert np.allclose(tot[:, 1], T["Out_tot_Ne"] / nmc, rtol=1e-14) and np.allclose(tot[:, 3], T["Out_tot_E"] / nmc, rtol=1e-14)
     # radial files: header '#Radius[A] ' + f10.2 times, rows f9.1 + Nt numbers
     head, *rows = open(os.path.join(d, "Radial_electron_density[1_cm^-3].txt")).read().splitlines()
     assert head.startswith("#Radius[A]       0.01[fs]   ") and len(rows) == 50
-    assert rows[0][:9] == "      1.0" and len(rows[0]) == 9 + 24 * lay.Nt + 1
+    assert rows[0][:9] == "      1.0" and len(rows[0]) == 9 + 25 * lay.Nt + 1
     ne = read_table(os.path.join(d, "Radial_electron_density[1_cm^-3].txt"))
     assert np.allclose(ne[:, 1:], (T["Out_ne"] / nmc * 1e24).T, rtol=1e-14)
     # the lattice file shows the running sum over the time intervals (:931)

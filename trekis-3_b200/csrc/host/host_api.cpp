@@ -91,6 +91,35 @@ int trk3h_load_tables(trk3h_case *h, const char *path, char *err, int errlen) {
     return TRK3_OK;
 }
 
+int trk3h_write_reference_cache(trk3h_case *h, const char *out_root, int *n_files, char *err, int errlen) {
+    std::string e;
+    if (!h || !h->c.tables_built) { set_err(err, errlen, "tables not built"); return TRK3_E_INVALID; }
+    if (!write_reference_cache(h->c, out_root ? out_root : ".", n_files, e)) { set_err(err, errlen, e); return TRK3_E_INVALID; }
+    return TRK3_OK;
+}
+
+int trk3h_read_reference_cache(trk3h_case *h, const char *out_root, int threads, char *err, int errlen) {
+    if (!h) return TRK3_E_INVALID;
+    BuildOptions o; o.threads = threads; o.evaluator = g_dcs_evaluator;
+    std::string e;
+    h->c.tables_built = false;
+    if (!read_reference_cache(h->c, out_root ? out_root : ".", o, e)) { set_err(err, errlen, e); return TRK3_E_INVALID; }
+    h->packed = false;
+    return TRK3_OK;
+}
+
+int trk3h_reference_cache_name(trk3h_case *h, const char *which, char *out, int outlen) {
+    if (!h || !which || !out || outlen < 1) return TRK3_E_INVALID;
+    const RefCacheNames n = reference_cache_names(h->c);
+    const std::string w(which);
+    const std::string *s = w == "dir_material" ? &n.dir_material : w == "dir_ion" ? &n.dir_ion : w == "dir_diff" ? &n.dir_diff
+                         : w == "el_imfp" ? &n.el_imfp : w == "hole_imfp" ? &n.hole_imfp : w == "photon_imfp" ? &n.photon_imfp
+                         : w == "el_emfp" ? &n.el_emfp : w == "hole_emfp" ? &n.hole_emfp : w == "shi_stem" ? &n.shi_stem : nullptr;
+    if (!s) return TRK3_E_INVALID;
+    std::snprintf(out, (size_t)outlen, "%s", s->c_str());
+    return TRK3_OK;
+}
+
 const trk3_config *trk3h_config(trk3h_case *h) {
     if (!h || !h->c.tables_built) return nullptr;
     if (!h->packed) repack(h);

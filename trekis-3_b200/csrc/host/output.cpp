@@ -3,43 +3,20 @@
 // Same directory name, file names, headers, column layout and number formats as the reference, so that existing
 // post-processing and gnuplot scripts keep working:
 //   <out_root>/OUTPUT_<material>/OUTPUT_<ion>_in_<material>/<ion>_E_<f8.2>_MeV_<f10.2>_fs[_n]/
-// Numbers written with the width-less descriptor '(e)' use the Intel default for real(8), E24.15E3
-// (the reference is built with ifort/ifx; gfortran needs -fdec-format-defaults).
+// Numbers written with the width-less descriptor '(e)' use the DEC/Intel default for real(8), E25.16 (fortran_fmt.hpp:
+// pinned by files shipped with the reference; gfortran needs -fdec-format-defaults).
 // '!Parameters.txt' carries the same information as print_parameters (:42-338) but is not byte-identical:
 // the title banner, the sum-rule table and the wall-clock duration are the reference program's own.
 #include <sys/stat.h>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include "fortran_fmt.hpp"
 #include "trk3_host.hpp"
 
 namespace trk3 {
 namespace {
 
-// Fortran Fw.d: right-justified, asterisks on overflow
-std::string fmt_f(double v, int w, int d) {
-    char b[64];
-    snprintf(b, sizeof b, "%*.*f", w, d, v);
-    std::string s(b);
-    if ((int)s.size() > w) s.assign((size_t)w, '*');
-    return s;
-}
-// Intel default of the width-less E descriptor for real(8): E24.15E3 ("  0.100000000000000E-001")
-std::string fmt_e(double v) {
-    char b[64];
-    if (v != v) return std::string(21, ' ') + "NaN";
-    if (std::isinf(v)) return v > 0 ? std::string(16, ' ') + "Infinity" : std::string(15, ' ') + "-Infinity";
-    if (v == 0.0) return " " + std::string(std::signbit(v) ? "-" : " ") + "0.000000000000000E+000";
-    snprintf(b, sizeof b, "%.14e", std::fabs(v));          // d.dddddddddddddde+xx : 15 significant digits
-    std::string m(b);
-    const size_t pe = m.find('e');
-    int ex = atoi(m.c_str() + pe + 1) + 1;                  // 0.ddd form: exponent + 1
-    std::string digits = m.substr(0, 1) + m.substr(2, pe - 2);
-    char e[16];
-    snprintf(e, sizeof e, "E%c%03d", ex < 0 ? '-' : '+', ex < 0 ? -ex : ex);
-    std::string s = std::string(v < 0 ? "-" : " ") + "0." + digits + e;
-    return std::string(24 - s.size(), ' ') + s;
-}
 std::string trim(const std::string &s) {
     size_t a = s.find_first_not_of(' '), b = s.find_last_not_of(' ');
     return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);

@@ -311,7 +311,17 @@ bool build_tables(Case &c, const BuildOptions &opt, std::string &err) {
         }
     } else c.Total_Photon_MFPs.clear();
 
-    // ---- differential SHI MFP for the given ion energy, MAIN.f90:231-238
+    return finish_tables(c, opt, err);
+}
+
+// What MAIN.f90 computes after the (possibly cached) tables: the differential SHI MFP for the given ion energy
+// (:231-238), the valence-band indices and the radial grid.  Shared by build_tables and read_reference_cache.
+bool finish_tables(Case &c, const BuildOptions &opt, std::string &err) {
+    const trk3_dcs_eval_fn ev = opt.evaluator;
+    int nth = opt.threads > 0 ? opt.threads : (int)std::thread::hardware_concurrency();
+    if (nth < 1) nth = 1;
+    Ctx x = make_ctx(c);
+    const int Nat = (int)c.atoms.size();
     c.diff_SHI_MFP.assign(Nat, {});
     for (int j = 0; j < Nat; ++j) c.diff_SHI_MFP[j].assign(c.atoms[j].nshl(), MFP{});
     {

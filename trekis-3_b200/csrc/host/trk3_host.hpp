@@ -171,14 +171,27 @@ struct BuildOptions {
     trk3_dcs_eval_fn evaluator = nullptr;   // of the integrands (trk3h_set_dcs_evaluator); null: integrate directly on the host
 };
 bool build_tables(Case &c, const BuildOptions &opt, std::string &err);     // MAIN.f90:146-247
+bool finish_tables(Case &c, const BuildOptions &opt, std::string &err);    // MAIN.f90:231-247 (never cached by the reference)
 void find_VB_numbers(Case &c);                                             // Reading_files...:3252
 void radius_for_distributions(Case &c);                                    // Sorting_output_data.f90:1363
 std::vector<double> set_time_grid(double Tim, double dt, int dt_flag);     // Monte_Carlo.f90:2118
 int  count_time_points(double Tim, double dt, int dt_flag);               // Sorting_output_data.f90:1375-1386
 
-// ---- binary cache of built tables (ours; the reference's text cache lives in output.cpp)
+// ---- binary cache of built tables (ours)
 bool save_tables_bin(const Case &c, const std::string &path, std::string &err);
 bool load_tables_bin(Case &c, const std::string &path, std::string &err);
+
+// ---- the reference's own on-disk table cache (refcache.cpp): OUTPUT_<material>/OUTPUT_*_IMFPs_*.dat, *_EMFPs_*.dat,
+// diff_CS/*.dat, OUTPUT_<ion>_in_<material>/OUTPUT_<ion>_*_{IMFP,dEdx,effective_charges,Range}.dat
+// (Analytical_IMFPs.f90:262-291, 385-408, 506-526, 590-786, 917-1606, 2306-2349, 2462-2506, 2657-2707)
+struct RefCacheNames {              // file names without directories, as the reference composes them
+    std::string dir_material, dir_ion, dir_diff;             // OUTPUT_<mat>, OUTPUT_<mat>/OUTPUT_<ion>_in_<mat>, OUTPUT_<mat>/diff_CS
+    std::string el_imfp, hole_imfp, photon_imfp, el_emfp, hole_emfp, shi_stem;
+};
+RefCacheNames reference_cache_names(const Case &c);
+std::string diff_cs_file_name(const std::string &table_file, const std::string &atom, const std::string &shell, double E);
+bool write_reference_cache(const Case &c, const std::string &out_root, int *n_files, std::string &err);
+bool read_reference_cache(Case &c, const std::string &out_root, const BuildOptions &opt, std::string &err);
 
 // ---- flattening into the C ABI (pack.cpp)
 struct Packed {

@@ -28,6 +28,9 @@ def _host():
         lib.trk3h_set_dcs_evaluator.restype = None
         lib.trk3h_save_tables.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
         lib.trk3h_load_tables.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+        lib.trk3h_write_reference_cache.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int), C.c_char_p, C.c_int]
+        lib.trk3h_read_reference_cache.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+        lib.trk3h_reference_cache_name.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
         lib.trk3h_config.restype = C.POINTER(Config)
         lib.trk3h_config.argtypes = [C.c_void_p]
         lib.trk3h_tables.restype = C.POINTER(Tables)
@@ -197,6 +200,32 @@ class Case:
             if lib.trk3h_save_tables(self._h, os.fsencode(tmp), err, 1024) == 0:
                 os.replace(tmp, cache)
         return self
+
+    def write_reference_cache(self, out_root):
+        """Write the built tables as the reference's own on-disk cache under <out_root>/OUTPUT_<material>/ (names, rows
+        and number formats of Analytical_IMFPs.f90:262-786, 917-1606, 2306-2707): a TREKIS-3 working directory that
+        holds these files skips its table integration.  Returns the number of files written."""
+        n = C.c_int(0)
+        err = C.create_string_buffer(1024)
+        if _host().trk3h_write_reference_cache(self._h, os.fsencode(out_root), C.byref(n), err, 1024) != 0:
+            raise RuntimeError("write_reference_cache failed: " + err.value.decode(errors="replace"))
+        return n.value
+
+    def read_reference_cache(self, out_root, threads=0):
+        """Take the tables from a reference-format cache under <out_root>/OUTPUT_<material>/ instead of building them
+        (the differential ion table of the given ion energy is always computed, as MAIN.f90:231-238 does).  Raises if a
+        file is missing or its row count differs from the energy grid -- the conditions under which the reference
+        recomputes (Analytical_IMFPs.f90:307-327)."""
+        err = C.create_string_buffer(1024)
+        if _host().trk3h_read_reference_cache(self._h, os.fsencode(out_root), int(threads), err, 1024) != 0:
+            raise RuntimeError("read_reference_cache failed: " + err.value.decode(errors="replace"))
+        return self
+
+    def reference_cache_name(self, which):
+        out = C.create_string_buffer(512)
+        if _host().trk3h_reference_cache_name(self._h, which.encode(), out, 512) != 0:
+            raise KeyError(which)
+        return out.value.decode()
 
     @property
     def config(self):
