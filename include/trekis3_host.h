@@ -57,6 +57,11 @@ const trk3_tables *trk3h_tables(trk3h_case *c);
 int trk3h_set(trk3h_case *c, const char *key, double value);
 double trk3h_get(trk3h_case *c, const char *key);
 int trk3h_get_string(trk3h_case *c, const char *key, char *out, int outlen);
+/* "atom:<j>:<k>:<field>" in trk3h_get: parameter of shell k of atom j (0-based): Nel, Ip, Ek, Auger, Radiat, Shl_num, PQN.
+ * When <dir>/INPUT_EADL/EADL2023.ALL exists, trk3h_load takes from it what the .cdf leaves out, as check_atomic_parameters
+ * does (Dealing_with_EADL.f90:312-413): Nel (I=912), Ip (913), Ek (914), radiative (921) and Auger (922) widths -> times.
+ * trk3h_eadl_lookup: one lookup with the reader's sub-shell rules (READ_EADL_TYPE_FILE_int/_real :417-684); value in eV. */
+int trk3h_eadl_lookup(const char *path, int Z, int I, int designator, double *out);
 int trk3h_num_warnings(trk3h_case *c);
 int trk3h_warning(trk3h_case *c, int i, char *out, int outlen);
 

@@ -181,6 +181,22 @@ double trk3h_get(trk3h_case *h, const char *key) {
     if (k == "phonon_E0") return c.CDF_Phonon.E0.empty() ? 0.0 : c.CDF_Phonon.E0[0];
     if (k == "phonon_A") return c.CDF_Phonon.A.empty() ? 0.0 : c.CDF_Phonon.A[0];
     if (k == "phonon_Gamma") return c.CDF_Phonon.Gamma.empty() ? 0.0 : c.CDF_Phonon.Gamma[0];
+    // "atom:<j>:<k>:<field>": a parameter of shell k of atom j (0-based), field = Nel | Ip | Ek | Auger | Radiat | Shl_num | PQN
+    if (k.rfind("atom:", 0) == 0) {
+        int j = -1, sh = -1; char fld[32] = "";
+        if (std::sscanf(key, "atom:%d:%d:%31s", &j, &sh, fld) != 3 || j < 0 || j >= (int)c.atoms.size()) return std::nan("");
+        const Atom &a = c.atoms[(size_t)j];
+        if (sh < 0 || sh >= a.nshl()) return std::nan("");
+        const std::string f(fld);
+        if (f == "Nel") return a.Nel[(size_t)sh];
+        if (f == "Ip") return a.Ip[(size_t)sh];
+        if (f == "Ek") return a.Ek[(size_t)sh];
+        if (f == "Auger") return a.Auger[(size_t)sh];
+        if (f == "Radiat") return a.Radiat[(size_t)sh];
+        if (f == "Shl_num") return a.Shl_num[(size_t)sh];
+        if (f == "PQN") return a.PQN[(size_t)sh];
+        return std::nan("");
+    }
     return 0.0;
 }
 
@@ -194,6 +210,15 @@ int trk3h_get_string(trk3h_case *h, const char *key, char *out, int outlen) {
     else return TRK3_E_INVALID;
     std::snprintf(out, (size_t)outlen, "%s", v.c_str());
     return TRK3_OK;
+}
+
+/* One lookup in an ENDL file (tests of the reader): I = 912 -> electrons of the designator, else the value in eV */
+int trk3h_eadl_lookup(const char *path, int Z, int I, int designator, double *out) {
+    if (!path || !out) return TRK3_E_INVALID;
+    Eadl db; std::string e;
+    if (!db.load(path, e)) return TRK3_E_INVALID;
+    const bool ok = (I == 912) ? db.electrons(Z, designator, *out) : db.real_value(Z, I, designator, *out);
+    return ok ? TRK3_OK : TRK3_E_INVALID;
 }
 
 int trk3h_num_warnings(trk3h_case *h) { return h ? (int)h->c.warnings.size() : 0; }

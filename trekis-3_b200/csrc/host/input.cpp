@@ -267,6 +267,17 @@ bool read_cdf(const std::string &dir, Case &c, const std::vector<PT> &pt, std::s
         f.backspace();
     }
     c.numpar.kind_of_CDF = 0;
+    // EADL2023.ALL is optional here (the reference refuses to start without it, Check_EPICS_files :867-892)
+    Eadl eadl;
+    bool have_eadl = false;
+    {
+        const std::string p = dir + "/INPUT_EADL/EADL2023.ALL";
+        if (file_exists(p)) {
+            std::string e;
+            if (!eadl.load(p, e)) return bad(e);
+            have_eadl = true;
+        }
+    }
     for (int j = 0; j < N; ++j) {
         Atom &a = c.atoms[j];
         int Shl;
@@ -281,13 +292,21 @@ bool read_cdf(const std::string &dir, Case &c, const std::vector<PT> &pt, std::s
             a.Shl_num[k] = std::abs(des);
             define_PQN(a.Shl_num[k], a.Shell_name[k], a.PQN[k]);
             if (a.Shl_num[k] >= 63) c.Matter.N_VB_el = a.Nel[k];
-            // check_atomic_parameters (Dealing_with_EADL.f90:350-370) without the EPICS files:
-            // only the decay times are decided here; Nel/Ip/Auger must come from the .cdf.
-            if (a.Nel[k] <= 0 || a.Ip[k] <= -1.0e-14) return bad("shell without Nel/Ip needs EADL2023.ALL; not supported");
-            if (a.Shl_num[k] >= 63 || !c.numpar.include_photons) a.Radiat[k] = 1.0e23;
-            else a.Radiat[k] = -1.0;                       // resolved by apply_radiative_data()
-            if (a.Shl_num[k] >= 63) a.Auger[k] = 1.0e23;
-            else if (a.Auger[k] <= 0.0 || a.Auger[k] > 1.0e30) return bad("shell without Auger time needs EADL2023.ALL; not supported");
+            if (have_eadl) {
+                // check_atomic_parameters (Dealing_with_EADL.f90:325-372): what the line left out comes from EADL2023.ALL
+                eadl_check_shell(eadl, a, k, c.numpar.include_photons, c.warnings);
+                if (a.Nel[k] <= 0 || a.Ip[k] <= -1.0e-14) return bad("shell without Nel/Ip that EADL2023.ALL does not list either");
+                if (a.Shl_num[k] < 63 && (a.Auger[k] <= 0.0 || a.Auger[k] > 1.0e30)) return bad("shell without Auger time that EADL2023.ALL does not list either");
+                if (a.Radiat[k] == 2.0e31) a.Radiat[k] = 1.0e23;  // element not in the file at all: channel closed
+            } else {
+                // the same decisions without the EPICS files: only the decay times are decided here, Nel/Ip/Auger must
+                // come from the .cdf and the radiative widths from the side-car (apply_radiative_data)
+                if (a.Nel[k] <= 0 || a.Ip[k] <= -1.0e-14) return bad("shell without Nel/Ip needs INPUT_EADL/EADL2023.ALL (absent)");
+                if (a.Shl_num[k] >= 63 || !c.numpar.include_photons) a.Radiat[k] = 1.0e23;
+                else a.Radiat[k] = -1.0;                       // resolved by apply_radiative_data()
+                if (a.Shl_num[k] >= 63) a.Auger[k] = 1.0e23;
+                else if (a.Auger[k] <= 0.0 || a.Auger[k] > 1.0e30) return bad("shell without Auger time needs INPUT_EADL/EADL2023.ALL (absent)");
+            }
             if (a.Ip[k] < 1.0e-1) a.Ip[k] = 1.0e-1;
             if (ncdf > 0) {
                 a.KOCS_SHI[k] = 1;

@@ -123,6 +123,21 @@ double interpolate(int flag, double E1, double E2, double S1, double S2, double 
 void set_default_numpar(NumPar &np);
 bool read_case(const std::string &dir, Case &c, std::string &err);
 
+// ---- EADL2023.ALL (ENDL format) for what a .cdf leaves out (eadl.cpp; Dealing_with_EADL.f90:312-742)
+struct Eadl {
+    struct Row { double des, val; };
+    struct Block { int Z = 0, C = 0, I = 0, S = 0; std::vector<Row> rows; };
+    std::vector<Block> blocks;
+    bool load(const std::string &path, std::string &err);
+    const Block *find(int Z, int I) const;
+    bool has_element(int Z) const;
+    bool real_value(int Z, int I, int designator, double &out) const;   // READ_EADL_TYPE_FILE_real, [eV]
+    bool electrons(int Z, int designator, double &out) const;           // READ_EADL_TYPE_FILE_int (I = 912)
+};
+void eadl_select_imin_imax(int designator, int &imin, int &imax);
+int eadl_next_designator(int last_designator);
+void eadl_check_shell(const Eadl &db, Atom &a, int k, bool include_photons, std::vector<std::string> &warnings);
+
 // ---- physics of the table builder (cdf.cpp)
 struct CtxFlat {        // storage behind the trk3_dcs_ctx handed to the shared integrands / the GPU evaluator
     std::vector<double> E0, A, G;
