@@ -580,6 +580,7 @@ struct trk3_engine {
     uint64_t h2d_bytes = 0;                 // bytes of the last table binding
     double nel_est = 1000.0;
     // options
+    int opt_cold_pair = 0;
     int opt_batch = 4096, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
     int opt_hot_slice = 64, opt_overlap = 0, opt_cold_min = 16384;
     int opt_shi_lanes = 0;                 // 0: one ion per warp, the lanes share the work of a collision (k_shi)
@@ -1066,6 +1067,7 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "quota_min") eng->opt_quota_min = std::min(32, std::max(1, (int)v));
     else if (k == "overlap") eng->opt_overlap = (v != 0.0);
     else if (k == "cold_min") eng->opt_cold_min = std::max(1, (int)v);
+    else if (k == "cold_pair") eng->opt_cold_pair = (v != 0.0);
     else if (k == "warm_pinel") { eng->opt_warm_pinel = std::min(0.99, std::max(0.0, v)); eng->nb_alloc = 0; eng->e_warm_auto = -1.0; eng->h_warm_auto = -1.0; }
     else if (k == "warm_holes") eng->opt_warm_holes = (v != 0.0);
     else if (k == "warm_slice") eng->opt_warm_slice = std::max(1, (int)v);
@@ -1252,8 +1254,14 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
                 CK(cudaMemsetAsync(heads + N_SPECIES, 0, 2 * sizeof(uint32_t), sc));
                 // beside a running hot cascade: optionally fewer cold blocks per SM (shared-memory floor)
                 const size_t sfl = (eng->opt_overlap && total) ? (size_t)eng->opt_cold_smem_kb * 1024 : 0;
+                // cold_pair: the two cold kernels on two streams -- the blocks of the second one move in as the blocks of the first
+                // one run out of records, so that its tail (the last, longest histories at a few lanes per warp) is not idle time
+                const bool pair = eng->opt_cold_pair && cold[0] > cold_done[0] && cold[1] > cold_done[1];
+                cudaStream_t sc2 = pair ? eng->stream_sp[0] : sc;
+                if (pair) { CK(cudaEventRecord(eng->ev_gen, sc)); CK(cudaStreamWaitEvent(sc2, eng->ev_gen, 0)); }
                 if (cold[0] > cold_done[0]) { rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[0].q[Q_EL_COLD], cold_done[0], cold[0], heads + Q_EL_COLD, eng->qs_x, sc, sfl); if (rc) return rc; }
-                if (cold[1] > cold_done[1]) { rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[0].q[Q_VB_COLD], cold_done[1], cold[1], heads + Q_VB_COLD, eng->qs_x, sc, sfl); if (rc) return rc; }
+                if (cold[1] > cold_done[1]) { rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[0].q[Q_VB_COLD], cold_done[1], cold[1], heads + Q_VB_COLD, eng->qs_x, sc2, sfl); if (rc) return rc; }
+                if (pair) { CK(cudaEventRecord(eng->ev_sp[0], sc2)); CK(cudaStreamWaitEvent(sc, eng->ev_sp[0], 0)); }
                 cold_done[0] = cold[0]; cold_done[1] = cold[1];
             }
             if (total) continue;
