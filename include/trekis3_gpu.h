@@ -248,13 +248,13 @@ void trk3_mc_destroy(trk3_engine *eng);
  * (libtrekis3_host.so) first records every (task, hw) it will ask for, has them all evaluated at once -- by this entry
  * point, one GPU thread per request -- and then replays the outer loops with the values: same operations in the same
  * order, identical tables.  A "task" is one outer integration: all its requests share these parameters. */
-enum { TRK3_DCS_INELASTIC = 0, TRK3_DCS_PHONON = 1, TRK3_DCS_SHI = 2 };
+enum { TRK3_DCS_INELASTIC = 0, TRK3_DCS_PHONON = 1, TRK3_DCS_SHI = 2, TRK3_DCS_SHI_BK = 3 };
 typedef struct trk3_dcs_task {
     int32_t type;          /* TRK3_DCS_* */
     int32_t set;           /* oscillator set (CDF shell; the phonon CDF is the last set) */
     double Ee;             /* energy of the incident particle [eV] */
-    double Mass;           /* its mass [m_e] (electrons 1, holes from the DOS) */
-    double p1, p2, p3;     /* PHONON: mean target atom mass [kg], target temperature [K], pref;  SHI: ion mass [kg], Emax [eV] */
+    double Mass;           /* its mass [m_e] (electrons 1, holes from the DOS); SHI_BK: atomic number of the ion */
+    double p1, p2, p3;     /* PHONON: mean target atom mass [kg], target temperature [K], pref;  SHI: ion mass [kg], Emax [eV] (SHI_BK: and the equilibrium charge) */
 } trk3_dcs_task;
 typedef struct trk3_dcs_ctx {
     const double *osc_E0, *osc_A, *osc_G;   /* oscillators of all sets, concatenated (type CDF, Objects.f90:211-217) */

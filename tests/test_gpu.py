@@ -248,13 +248,16 @@ def test_c5_high_statistics_sweep_composes(case_c1):
     assert rel_close((a + b)[m], whole[m], 1e-9)
 
 
-@pytest.mark.parametrize("cfg", ["C1", "C2", "C4"])
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C4", "C1-BK"])
 def test_gpu_table_builder_gives_the_host_tables(tmp_path, cfg):
     """all q-integrals of the table builder evaluated on the GPU (trk3_dcs_eval).  BASELINE's bar for the
     tables is 1e-12 relative; the GPU kernel shares its integrands with the host builder and is compiled without
     fused multiply-adds, so the tables are expected to be identical, and are checked to be."""
-    host = tk.Case.load(tk.make_run_dir(str(tmp_path / "h"), cfg)); host.build_tables(shi_window_only=True)
-    gpu = tk.Case.load(tk.make_run_dir(str(tmp_path / "g"), cfg)); gpu.build_tables(shi_window_only=True, evaluator="gpu")
+    edits = None
+    if cfg.endswith("-BK"):          # Brandt-Kitagawa ion: the form factor uses pow(), which may differ in the last bit on the device
+        cfg, edits = cfg[:-3], {11: "1   ! Brandt-Kitagawa ion"}
+    host = tk.Case.load(tk.make_run_dir(str(tmp_path / "h"), cfg, edits=edits)); host.build_tables(shi_window_only=True)
+    gpu = tk.Case.load(tk.make_run_dir(str(tmp_path / "g"), cfg, edits=edits)); gpu.build_tables(shi_window_only=True, evaluator="gpu")
     assert tk.gpu_library_loaded()
     th, tg = host.table_arrays(), gpu.table_arrays()
     worst = 0.0

@@ -204,6 +204,49 @@ def test_ion_stopping_and_effective_charge(case_c1):
     assert zeff == pytest.approx(54.0 * (1.0 - math.exp(-(v * 125.0 / g_cvel / 54.0 ** 0.66666666))), rel=1e-14)   # Barkas, :2675
 
 
+def test_brandt_kitagawa_ion(tmp_path, case_c1):
+    """Kind_ion = 1 (SHI_TotIMFP_BK / Brand_Kitagawa, Cross_sections.f90:2748-2889): the ion's charge enters through the form
+    factor rho(q) inside the q-integral instead of Zeff^2 in front of it."""
+    bk = tk.Case.load(tk.make_run_dir(str(tmp_path / "bk"), "C1", edits={11: "1   ! Brandt-Kitagawa ion"}))
+    # (i) a fully stripped ion has rho = Z_SHI at every q: the Brandt-Kitagawa MFP equals the point-charge MFP with Zeff = Z
+    full = {10: "4   54.0   ! fixed Zeff = Z"}
+    p4 = tk.Case.load(tk.make_run_dir(str(tmp_path / "p4"), "C1", edits=full))
+    b4 = tk.Case.load(tk.make_run_dir(str(tmp_path / "b4"), "C1", edits={**full, 11: "1   ! Brandt-Kitagawa ion"}))
+    for at, sh in ((0, 1), (0, 2), (1, 0)):
+        sp, dp, zp = p4.eval_SHI(167e6, at, sh)
+        sb, db, zb = b4.eval_SHI(167e6, at, sh)
+        assert zp == zb == 54.0
+        assert sb == pytest.approx(sp, rel=1e-12)
+        # the stopping power is summed differently (E x interval weight, :2817, instead of Simpson on E x f, :2580): close, not equal
+        assert db == pytest.approx(dp, rel=2e-2) and db != dp
+    # (ii) a dressed ion: small momentum transfers see the screened charge Zeff, large ones the nucleus -> between the two limits
+    s_pt, _, zeff = case_c1.eval_SHI(167e6, 0, 2)
+    s_bk, _, zeff_b = bk.eval_SHI(167e6, 0, 2)
+    assert zeff_b == zeff and 10.0 < zeff < 54.0
+    assert s_pt < s_bk < s_pt * (54.0 / zeff) ** 2
+    # (iii) the form factor itself against an independent restatement, through a one-oscillator-free route: ratio of the
+    # differential integrands is rho^2 only if rho is constant -- so check the two limits of rho in closed form
+    a = 0.2400519147
+    Z = (54.0 - zeff) / 54.0
+
+    def rho(hq):
+        kl = hq * (0.5291772085936e-10 * math.sqrt(g_e)) * 2.0 * a * Z ** (2.0 / 3.0) / (54.0 ** (2.0 / 3.0) * (1.0 - Z / 7.0))
+        return 54.0 * (1.0 - Z + kl * kl) / (1.0 + kl * kl)
+
+    assert rho(0.0) == pytest.approx(zeff, rel=1e-14) and rho(1e30) == pytest.approx(54.0, rel=1e-12)
+    # (iv) the tables: built through record / evaluate / replay they are identical to the direct build, and the file names say BK
+    bk.build_tables(shi_window_only=True)
+    bk2 = tk.Case.load(tk.make_run_dir(str(tmp_path / "bk2"), "C1", edits={11: "1   ! Brandt-Kitagawa ion"}))
+    bk2.build_tables(shi_window_only=True, evaluator="host")
+    ta, tb, tp = bk.table_arrays(), bk2.table_arrays(), case_c1.table_arrays()
+    for k in ta:
+        assert np.array_equal(ta[k], tb[k]), k
+    built = ta["shi_L"][2] < 1e20
+    assert built.any() and np.all(ta["shi_L"][2][built] < tp["shi_L"][2][built])          # shorter MFPs than the point charge
+    assert np.array_equal(ta["dshi_L"], tp["dshi_L"])             # the differential table stays the point-charge one (MAIN.f90:233)
+    assert bk.reference_cache_name("shi_stem") == "OUTPUT_Xe_CDF_Barkas_BK"
+
+
 def test_time_grid_and_layout(case_c1):
     lay = case_c1.layout()
     assert lay.Nt == 5 and list(lay.time_grid[:6]) == pytest.approx([0.01, 0.1, 1.0, 10.0, 100.0, 110.0], rel=1e-12)
@@ -226,8 +269,8 @@ def test_table_cache_round_trip(case_c1, tmp_path):
 
 
 def test_unsupported_inputs_are_reported_not_guessed(tmp_path):
-    d = tk.make_run_dir(str(tmp_path / "r1"), "C1", edits={11: "1   ! Brandt-Kitagawa"})
-    with pytest.raises(RuntimeError, match="Brandt-Kitagawa"):
+    d = tk.make_run_dir(str(tmp_path / "r1"), "C1", edits={12: "2   1   ! DSF elastic cross sections"})
+    with pytest.raises(RuntimeError, match="DSF"):
         tk.Case.load(d)
     d = tk.make_run_dir(str(tmp_path / "r2"), "C1", extra_lines=("grid 0",))
     with pytest.raises(RuntimeError, match="grid 1"):

@@ -136,6 +136,36 @@ DCS_HD double shi_diff_cross_section(const trk3_dcs_ctx &x, int s, double Ee, do
     return dLs * T_fact;
 }
 
+// Brand_Kitagawa, Cross_sections.f90:2877-2889: form factor of a partially stripped ion (Z = ionisation deficit / Z_SHI)
+DCS_HD double brandt_kitagawa(double hq, double Z_SHI, double Zeff) {
+    const double a = 0.2400519147;
+    double Z = (Z_SHI - Zeff) / Z_SHI;
+    double kl = hq * (DCS_A0 * 1e-10 * sqrt(DCS_GE)) * 2.0 * a * pow(Z, 2.0 / 3.0) / (pow(Z_SHI, 2.0 / 3.0) * (1.0 - Z / 7.0));
+    double kl2 = kl * kl;
+    return Z_SHI * (1.0 - Z + kl2) / (1.0 + kl2);
+}
+
+// SHI_Diff_cross_section_BK, Cross_sections.f90:2826-2874: the loss function weighted with the squared form factor
+DCS_HD double shi_diff_cross_section_bk(const trk3_dcs_ctx &x, int s, double Ee, double MSHI, double Emax, double hw, double Z_SHI, double Zeff) {
+    double qmin = hw / DCS_H / sqrt(2.0 * Ee / MSHI);
+    double qmax = sqrt(2.0 * DCS_ME) / DCS_H * sqrt(Emax);
+    double dLs = 0.0, hq = qmin, dLs0 = 0.0;
+    const double n = 100.0;                      // m_N_p_grid_SHI
+    while (hq < qmax) {
+        double dq = hq / n;
+        double a = hq + dq / 2.0;
+        double rho = brandt_kitagawa(a, Z_SHI, Zeff);
+        double temp1 = imewq(x, s, hw, a) * rho * rho;
+        double b = hq + dq;
+        rho = brandt_kitagawa(b, Z_SHI, Zeff);
+        double dL = imewq(x, s, hw, b) * rho * rho;
+        dLs = dLs + dq / 6.0 * (dLs0 + 4.0 * temp1 + dL) / hq;
+        dLs0 = dL;
+        hq = hq + dq;
+    }
+    return dLs / (1.0 - exp(-hw / x.temp * DCS_KB));      // :2873, at 0 K: exp(-inf) = 0
+}
+
 // Diff_cross_section_phonon, Cross_sections.f90:3142-3300 (CDF_elast_Zeff 0/1: screening = 1)
 DCS_HD double diff_cross_section_phonon(const trk3_dcs_ctx &x, int s, double Ee, double dE, double Mtarget, double Mass, double Ttarget, double pref) {
     const double eps = 1.0e-12;
@@ -167,6 +197,7 @@ DCS_HD double eval_request(const trk3_dcs_ctx &x, const trk3_dcs_task &t, double
     switch (t.type) {
     case TRK3_DCS_INELASTIC: return diff_cross_section(x, t.set, t.Ee, hw, t.Mass);
     case TRK3_DCS_PHONON: return diff_cross_section_phonon(x, t.set, t.Ee, hw, t.p1, t.Mass, t.p2, t.p3);
+    case TRK3_DCS_SHI_BK: return shi_diff_cross_section_bk(x, t.set, t.Ee, t.p1, t.p2, hw, t.Mass, t.p3);
     default: return shi_diff_cross_section(x, t.set, t.Ee, t.p1, t.p2, hw);
     }
 }

@@ -148,6 +148,10 @@ inline double shi_diff_cross_section(const Ctx &x, int set, double Ee, double MS
     trk3_dcs_task t{TRK3_DCS_SHI, set, Ee, 1.0, MSHI, Emax, 0.0};
     return dcs_request(x, t, hw);
 }
+inline double shi_diff_cross_section_bk(const Ctx &x, int set, double Ee, double MSHI, double Emax, double hw, double Z_SHI, double Zeff) {
+    trk3_dcs_task t{TRK3_DCS_SHI_BK, set, Ee, Z_SHI, MSHI, Emax, Zeff};
+    return dcs_request(x, t, hw);
+}
 inline double diff_cross_section_phonon(const Ctx &x, double Ee, double dE, double Mtarget, double Mass, double Ttarget, double pref) {
     trk3_dcs_task t{TRK3_DCS_PHONON, x.set_phonon, Ee, Mass, Mtarget, Ttarget, pref};
     return dcs_request(x, t, dE);
@@ -447,6 +451,53 @@ void SHI_TotIMFP(const Ctx &x, Ion &shi, int Nat, int Nshl, double &Sigma, doubl
     Sigma = 1.0 / (g_Pi * g_a0 * Ele) * MSHI / g_me * Zeff * Zeff * Ltot1;
     if (Sigma > 1e30) Sigma = 1e30;
     dEdx = 1.0 / (g_Pi * g_a0 * Ele) * MSHI / g_me * Zeff * Zeff * ddEdx;
+}
+
+// SHI_TotIMFP_BK, Cross_sections.f90:2748-2823: Brandt-Kitagawa ion.  The charge enters through the form factor inside the
+// q-integral (no Zeff^2 in front); the stopping power is summed as E*(Simpson weight of the interval), as the reference does
+void SHI_TotIMFP_BK(const Ctx &x, Ion &shi, int Nat, int Nshl, double &Sigma, double &dEdx) {
+    const Case &c = *x.c;
+    const Atom &at = c.atoms[Nat];
+    const CDFosc &o = at.Ritchi[Nshl];
+    equilibrium_charge_SHI(shi, c.atoms);
+    const double Ele = shi.E, MSHI = g_Mp * shi.Mass, Zeff = shi.Zeff, Z_SHI = (double)shi.Zat;
+    const double Egap = c.atoms[0].Ip.back();
+    double Emin = at.Ip[Nshl];
+    if (Emin <= 1.0e-3) Emin = 1.0e-3;
+    double Emax = 4.0 * Ele * g_me * MSHI / ((MSHI + g_me) * (MSHI + g_me));
+    if (c.numpar.plasmon_Emax && Emin == Egap) {
+        double Epl = std::sqrt(c.Matter.N_VB_el * c.Matter.At_Dens * 1e6 * g_h * g_h / (g_me * g_e0) + Egap * Egap);
+        if (Epl >= Emax) Emax = Epl;
+    }
+    const int n = 1000;                              // m_N_grid_SHI
+    double lo = 1e300, hi = -1e300;
+    for (size_t i = 0; i < o.E0.size(); ++i) { lo = std::min(lo, o.E0[i] - 5.0 * o.Gamma[i]); hi = std::max(hi, o.E0[i] + 5.0 * o.Gamma[i]); }
+    const double E_low = std::max(lo, Emin), E_high = std::min(hi, Emax);
+    const int set = x.set0[Nat] + Nshl;
+    double E = Emin, Ltot1 = 0.0, ddEdx = 0.0;
+    double Ltot0 = shi_diff_cross_section_bk(x, set, Ele, MSHI, Emax, E, Z_SHI, Zeff);
+    while (E <= Emax) {
+        double dE = define_dE(1, n, E, true, E_low, true, E_high, 0.001);
+        double a = E + dE / 2.0;
+        double temp1 = shi_diff_cross_section_bk(x, set, Ele, MSHI, Emax, a, Z_SHI, Zeff);
+        double b = E + dE;
+        double dL = shi_diff_cross_section_bk(x, set, Ele, MSHI, Emax, b, Z_SHI, Zeff);
+        double temp2 = dE / 6.0 * (Ltot0 + 4.0 * temp1 + dL);
+        Ltot1 = Ltot1 + temp2;
+        ddEdx = ddEdx + E * temp2;
+        Ltot0 = dL;
+        E = E + dE;
+    }
+    Sigma = 1.0 / (g_Pi * g_a0 * Ele) * MSHI / g_me * Ltot1;
+    if (Sigma > 1e30) Sigma = 1e30;
+    dEdx = 1.0 / (g_Pi * g_a0 * Ele) * MSHI / g_me * ddEdx;
+}
+
+// SHI_Total_IMFP, Cross_sections.f90:2431-2446: the tabulated ion MFPs follow Kind_ion; the differential table of the given
+// ion energy is always the point-charge one (MAIN.f90:233 calls SHI_TotIMFP directly)
+void SHI_Total_IMFP(const Ctx &x, Ion &shi, int Nat, int Nshl, double &Sigma, double &dEdx) {
+    if (shi.Kind_ion == 1) SHI_TotIMFP_BK(x, shi, Nat, Nshl, Sigma, dEdx);
+    else SHI_TotIMFP(x, shi, Nat, Nshl, Sigma, dEdx, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -254,7 +254,7 @@ int trk3h_eval_SHI(trk3h_case *h, double E, int atom, int shell, double *inv_L, 
     if (!shell_ok(h, atom, shell)) return TRK3_E_INVALID;
     Ctx x = make_ctx(h->c);
     Ion s = h->c.SHI; s.E = E;
-    double S, d; SHI_TotIMFP(x, s, atom, shell, S, d, nullptr);
+    double S, d; SHI_Total_IMFP(x, s, atom, shell, S, d);
     if (inv_L) *inv_L = S;
     if (dEdx) *dEdx = d;
     if (Zeff) *Zeff = s.Zeff;

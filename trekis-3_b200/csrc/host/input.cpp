@@ -454,7 +454,7 @@ bool read_case(const std::string &dir, Case &c, std::string &err) {
     if (!read_input_parameters(dir, c, pt, err)) return false;
     if (!read_cdf(dir, c, pt, err)) return false;
     apply_radiative_data(dir, c);
-    if (c.SHI.Kind_ion == 1) { err = "Brandt-Kitagawa ion (Kind_ion=1) is not supported yet"; return false; }
+    if (c.SHI.Kind_ion != 0 && c.SHI.Kind_ion != 1) c.SHI.Kind_ion = 0;       // anything but 1 is the point charge (select case default)
     if (c.numpar.kind_of_DR == 4) { err = "Delta-CDF (kind_of_DR=4) is not supported"; return false; }
     if (c.numpar.kind_of_EMFP == 2) { err = "DSF elastic cross sections (kind_of_EMFP=2) need INPUT_DSF files; not supported"; return false; }
     if (c.numpar.CDF_elast_Zeff >= 2) { err = "CDF_elast_Zeff=2/3 (form-factor / CDF screening) is not supported yet"; return false; }

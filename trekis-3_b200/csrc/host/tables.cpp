@@ -237,7 +237,7 @@ bool build_tables(Case &c, const BuildOptions &opt, std::string &err) {
             Ion shi1 = c.SHI;
             shi1.E = grid[tasks[t].j];
             double IMFP, dEdx;
-            SHI_TotIMFP(x, shi1, tasks[t].a, tasks[t].s, IMFP, dEdx, nullptr);
+            SHI_Total_IMFP(x, shi1, tasks[t].a, tasks[t].s, IMFP, dEdx);
             MFP &m = c.SHI_MFP[tasks[t].a][tasks[t].s];
             double L = (IMFP > 1.0e-10) ? 1.0 / IMFP : 1.0e28;     // :2644-2648
             if (L > 1e30) L = 1e30;                                 // :2682

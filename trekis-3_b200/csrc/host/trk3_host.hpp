@@ -176,6 +176,8 @@ void Tot_EMFP(const Ctx &x, double Ele, int kind, double Zeff, double &Sigma, do
 void Elastic_cross_section(const Ctx &x, double Ee, int kind, double &EMFP, double &dEdx, DiffRow *row);                  // :2892
 void Tot_Phot_IMFP(const Ctx &x, double Ele, int Nat, int Nshl, double &Sigma, double &dEdx);                            // :833
 void SHI_TotIMFP(const Ctx &x, Ion &shi, int Nat, int Nshl, double &Sigma, double &dEdx, MFP *dSedE);                     // :2452
+void SHI_TotIMFP_BK(const Ctx &x, Ion &shi, int Nat, int Nshl, double &Sigma, double &dEdx);                              // :2748 (Brandt-Kitagawa ion)
+void SHI_Total_IMFP(const Ctx &x, Ion &shi, int Nat, int Nshl, double &Sigma, double &dEdx);                              // :2431 (dispatch on Kind_ion)
 
 // ---- table drivers (tables.cpp)
 std::vector<double> get_grid_4CS(const std::vector<Atom> &atoms, double Emin, double Emax);   // Analytical_IMFPs.f90:2815
