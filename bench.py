@@ -44,15 +44,80 @@ def workload_name(config, nmc):
     return f"{config}: {ion} {e:g} MeV in {mat}, photons {'on' if ph else 'off'}, {nmc} MC iterations per step, T=100 fs"
 
 
+_JSON_FD = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+    version banner there): from here on fd 1 goes to stderr, and the JSON line alone goes to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled in-process every few
+    milliseconds (a `nvidia-smi -lms` child needs longer to start than a short timed region lasts); nvidia-smi is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index=0):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.nvml, self.handle, self.stop_flag, self.thread = None, None, threading.Event(), None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:        # CUDA ordinal -> NVML device through the PCI address (CUDA_VISIBLE_DEVICES may renumber)
+            import torch
+            pr = torch.cuda.get_device_properties(self.gpu)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        return pynvml, h
+
+    def _sample(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            mask = int(get(self.handle))
+            for bit, name in self.BITS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self.stop_flag.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            self.stop_flag.wait(0.004)
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.mx.append(float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -65,6 +130,18 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag.set()
+            if self.thread:
+                self.thread.join(timeout=1.0)
+            if not self.sm:                 # a timed region shorter than one polling period: one sample right at its end
+                try:
+                    self._sample()
+                except Exception:
+                    pass
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml"}
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
@@ -81,7 +158,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def cpu_reference_rate(case, seconds, threads=0):
@@ -131,7 +208,7 @@ def run_reference(args):
                                    "the Fortran reference cannot be built here (no Fortran compiler in the image)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def table_bytes(case):
@@ -321,7 +398,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "max_energy_drift": drift, "errors": errors,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -338,6 +415,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    protect_stdout()
     import trekis3_b200 as tk
     if args.nmc is None:
         args.nmc = tk.CONFIGS[args.config][4]

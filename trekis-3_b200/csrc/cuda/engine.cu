@@ -580,14 +580,6 @@ struct trk3_engine {
     uint64_t h2d_bytes = 0;                 // bytes of the last table binding
     double nel_est = 1000.0;
     // options
-    int opt_cold_pair = 0;
-    // late overlap: once a hot generation is down to `late_hot_max` records, a share `late_frac` of the pending cold electrons is
-    // launched beside the tail of the cascade (2 cold blocks per SM through a shared-memory floor, small hot blocks from then on)
-    int opt_late_overlap = 0, opt_late_hot_block = 128, opt_late_cold_smem_kb = 80;
-    uint32_t opt_late_hot_max = 12000;
-    double opt_late_frac = 0.15;
-    bool late_active = false;
-    cudaEvent_t ev_late = nullptr;
     uint32_t *h_qcount = nullptr;       // pinned mirror of d_qcount
     int opt_batch = 4096, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
     int opt_hot_slice = 64, opt_overlap = 0, opt_cold_min = 16384;
@@ -858,9 +850,7 @@ int launch_hot(trk3_engine *eng, const Queue *const *qin, const uint32_t *n_in, 
     auto kern = lean ? k_hot<SP, true> : k_hot<SP, false>;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = eng->opt_blocks_per_sm;
-    const bool late = eng->late_active && eng->opt_late_hot_block > 0;        // cold blocks hold most of every SM: one small block fits
-    const int block = late ? eng->opt_late_hot_block : (eng->opt_hot_block ? eng->opt_hot_block : eng->opt_block);
-    if (late) bps = 1;
+    const int block = eng->opt_hot_block ? eng->opt_hot_block : eng->opt_block;
     if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, block, smem)); if (bps < 1) bps = 1; }
     const uint32_t wpb = (uint32_t)block / 32u, W = (uint32_t)(eng->n_sm * bps) * wpb;       // warps the GPU holds at once
     HotIn in{};
@@ -1033,7 +1023,6 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
     }
     CK(cudaEventCreate(&eng->ev0)); CK(cudaEventCreate(&eng->ev1));
     CK(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&eng->ev_join, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&eng->ev_late, cudaEventDisableTiming));
     int rc = bind_tables(eng, cfg, tab);
     if (rc) return rc;
     DevP &p = eng->hp;
@@ -1085,12 +1074,6 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "quota_min") eng->opt_quota_min = std::min(32, std::max(1, (int)v));
     else if (k == "overlap") eng->opt_overlap = (v != 0.0);
     else if (k == "cold_min") eng->opt_cold_min = std::max(1, (int)v);
-    else if (k == "cold_pair") eng->opt_cold_pair = (v != 0.0);
-    else if (k == "late_overlap") eng->opt_late_overlap = (v != 0.0);
-    else if (k == "late_hot_max") eng->opt_late_hot_max = (uint32_t)std::max(0.0, v);
-    else if (k == "late_frac") eng->opt_late_frac = std::min(1.0, std::max(0.0, v));
-    else if (k == "late_hot_block") eng->opt_late_hot_block = std::min(TRK_BLOCK_MAX, std::max(0, ((int)v / 32) * 32));
-    else if (k == "late_cold_smem_kb") eng->opt_late_cold_smem_kb = std::max(0, (int)v);
     else if (k == "warm_pinel") { eng->opt_warm_pinel = std::min(0.99, std::max(0.0, v)); eng->nb_alloc = 0; eng->e_warm_auto = -1.0; eng->h_warm_auto = -1.0; }
     else if (k == "warm_holes") eng->opt_warm_holes = (v != 0.0);
     else if (k == "warm_slice") eng->opt_warm_slice = std::max(1, (int)v);
@@ -1198,8 +1181,6 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
         int cur = 0;
         bool overflow = false;
         uint32_t cold_done[2] = {0, 0};
-        bool late_done = false, late_pending = false;
-        eng->late_active = false;
         cudaStream_t sc = eng->opt_overlap ? eng->stream_c : eng->stream;       // stream of the cold kernels
         if (eng->opt_overlap) { CK(cudaEventRecord(eng->ev_fork, eng->stream)); CK(cudaStreamWaitEvent(sc, eng->ev_fork, 0)); }
         for (int gen = 0; gen < eng->opt_max_generations; ++gen) {
@@ -1271,34 +1252,14 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
                 }
                 cur = nxt;
             }
-            if (eng->opt_late_overlap && !late_done && total && total <= eng->opt_late_hot_max && cold[0] > cold_done[0]) {
-                late_done = true;
-                const uint32_t f0 = (uint32_t)((double)(cold[0] - cold_done[0]) * eng->opt_late_frac);
-                if (f0 >= 1024) {
-                    CK(cudaMemsetAsync(heads + Q_EL_COLD, 0, sizeof(uint32_t), eng->stream_c));
-                    rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[0].q[Q_EL_COLD], cold_done[0], cold_done[0] + f0, heads + Q_EL_COLD, eng->qs_x,
-                                                       eng->stream_c, (size_t)eng->opt_late_cold_smem_kb * 1024);
-                    if (rc) return rc;
-                    CK(cudaEventRecord(eng->ev_late, eng->stream_c));
-                    cold_done[0] += f0;
-                    eng->late_active = true; late_pending = true;
-                }
-            }
-            if (!total && late_pending) { CK(cudaStreamWaitEvent(sc, eng->ev_late, 0)); late_pending = false; eng->late_active = false; }
             // cold kernels: on the second stream, beside the next hot generation, as soon as enough records have gathered
             // (the records [cold_done, cold) were written by kernels that have completed: the stream was just synchronised)
             if (cold_pending && (!total || (eng->opt_overlap && cold_pending >= (uint64_t)eng->opt_cold_min))) {
                 CK(cudaMemsetAsync(heads + N_SPECIES, 0, 2 * sizeof(uint32_t), sc));
                 // beside a running hot cascade: optionally fewer cold blocks per SM (shared-memory floor)
                 const size_t sfl = (eng->opt_overlap && total) ? (size_t)eng->opt_cold_smem_kb * 1024 : 0;
-                // cold_pair: the two cold kernels on two streams -- the blocks of the second one move in as the blocks of the first
-                // one run out of records, so that its tail (the last, longest histories at a few lanes per warp) is not idle time
-                const bool pair = eng->opt_cold_pair && cold[0] > cold_done[0] && cold[1] > cold_done[1];
-                cudaStream_t sc2 = pair ? eng->stream_sp[0] : sc;
-                if (pair) { CK(cudaEventRecord(eng->ev_gen, sc)); CK(cudaStreamWaitEvent(sc2, eng->ev_gen, 0)); }
                 if (cold[0] > cold_done[0]) { rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[0].q[Q_EL_COLD], cold_done[0], cold[0], heads + Q_EL_COLD, eng->qs_x, sc, sfl); if (rc) return rc; }
-                if (cold[1] > cold_done[1]) { rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[0].q[Q_VB_COLD], cold_done[1], cold[1], heads + Q_VB_COLD, eng->qs_x, sc2, sfl); if (rc) return rc; }
-                if (pair) { CK(cudaEventRecord(eng->ev_sp[0], sc2)); CK(cudaStreamWaitEvent(sc, eng->ev_sp[0], 0)); }
+                if (cold[1] > cold_done[1]) { rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[0].q[Q_VB_COLD], cold_done[1], cold[1], heads + Q_VB_COLD, eng->qs_x, sc, sfl); if (rc) return rc; }
                 cold_done[0] = cold[0]; cold_done[1] = cold[1];
             }
             if (total) continue;
@@ -1327,8 +1288,6 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
             CK(cudaMemsetAsync(eng->d_qcount + QC_X, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
             cur = nxt;
         }
-        if (late_pending) { CK(cudaStreamWaitEvent(eng->stream, eng->ev_late, 0)); CK(cudaStreamWaitEvent(sc, eng->ev_late, 0)); late_pending = false; }
-        eng->late_active = false;
         if (eng->opt_overlap) { CK(cudaEventRecord(eng->ev_join, sc)); CK(cudaStreamWaitEvent(eng->stream, eng->ev_join, 0)); }
         if (eng->opt_defer_snap && !overflow) {
             // all histories of the batch have ended: turn the queued snapshot records into tallies
@@ -1482,7 +1441,6 @@ void trk3_mc_destroy(trk3_engine *eng) {
     if (eng->ev_wh) cudaEventDestroy(eng->ev_wh);
     if (eng->ev_fork) cudaEventDestroy(eng->ev_fork);
     if (eng->ev_join) cudaEventDestroy(eng->ev_join);
-    if (eng->ev_late) cudaEventDestroy(eng->ev_late);
     if (eng->h_qcount) cudaFreeHost(eng->h_qcount);
     delete eng;
 }
