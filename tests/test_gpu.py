@@ -66,6 +66,13 @@ def test_sio2_photons_radiative_and_hole_ionisation(tmp_path):
     assert sg["events"]["radiative"] > 10 and sg["events"]["photon"] > 10 and sg["n_photons"] > 10
 
 
+def test_water_an_atom_without_shells(tmp_path):
+    """H2O.cdf: hydrogen has no shells of its own (all its electrons sit in the valence band of the first atom)."""
+    case = tk.Case.load(tk.make_run_dir(str(tmp_path / "w"), ("H2O", 54, 167.0, 0, 10)))
+    case.build_tables(shi_window_only=True, cache_dir=CACHE)
+    check_against_oracle(case, 6)
+
+
 def test_diamond_single_pole_phonons(case_c3):
     sg, so = check_against_oracle(case_c3, 4)
     assert sg["events"]["vbh_inelastic"] > 100

@@ -52,6 +52,21 @@ def test_wavefront_equals_time_ordered_loop_al2o3(case_c1):
     assert se["n_waves"] >= 3
 
 
+def test_atom_without_shells_of_its_own_water(tmp_path):
+    """H2O.cdf (shipped with the reference) gives hydrogen ZERO shells: its electron is counted in the valence band of the
+    first atom (Reading_files_and_parameters.f90:1496-1503 allocates arrays of length 0 and loops over nothing)."""
+    case = tk.Case.load(tk.make_run_dir(str(tmp_path / "w"), ("H2O", 54, 167.0, 0, 10)))
+    case.build_tables(shi_window_only=True, cache_dir=CACHE)
+    assert case.get("n_atoms") == 2 and case.tables.n_shells == 2
+    to, so, eo, no = oracle_api.run(case, 0, 4, rng_mode=1)
+    te, se, ee, ne = emul_api.run(case, 0, 4, batch=3)
+    assert not so["errors"] and so["events"]["shi"] > 100 and so["events"]["el_elastic"] > 1000
+    assert_same(case, to, te, so, se)
+    assert np.array_equal(no, ne) and np.allclose(eo, ee, rtol=1e-12)
+    drift = np.abs(eo[:, 1:] - eo[:, -1:]) / eo[:, -1:]
+    assert drift.max() < 1e-9
+
+
 def test_wavefront_equals_time_ordered_loop_photons_and_radiative_decay(tmp_path):
     d = tk.make_run_dir(str(tmp_path / "c2"), "C2")
     case = tk.Case.load(d)

@@ -281,7 +281,7 @@ bool read_cdf(const std::string &dir, Case &c, const std::vector<PT> &pt, std::s
     for (int j = 0; j < N; ++j) {
         Atom &a = c.atoms[j];
         int Shl;
-        if (read_list(f, 1, t) != 0 || !parse_int(t[0], Shl) || Shl < 1) return bad("number of shells");
+        if (read_list(f, 1, t) != 0 || !parse_int(t[0], Shl) || Shl < 0) return bad("number of shells");   // 0: an atom without shells of its own (H in H2O.cdf: its electron sits in the valence band of atom 1)
         a.Shell_name.assign(Shl, ""); a.Shl_num.assign(Shl, 0); a.Nel.assign(Shl, 0.0); a.Ip.assign(Shl, -1.0e15);
         a.Ek.assign(Shl, -1.0e-15); a.Auger.assign(Shl, 1.0e31); a.Radiat.assign(Shl, 2.0e31); a.PQN.assign(Shl, 0);
         a.KOCS.assign(Shl, 0); a.KOCS_SHI.assign(Shl, 0); a.Ritchi.assign(Shl, CDFosc{});
