@@ -113,6 +113,8 @@ class ClockSampler:
         try:
             self.nvml, self.handle = self._nvml_handle()
             self.mx.append(float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+            self._sample()                      # the first NVML queries of a process can take tens of milliseconds: not in the timed region
+            self.sm.clear(); self.reasons.clear()
             self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
             return

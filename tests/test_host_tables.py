@@ -3,6 +3,7 @@
 The reference ships no golden tables (parity unpinned), so the checks are: an independent numpy
 restatement of the integrators at a few points (1e-12), closed-form limits, sum rules, and structural invariants."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -306,3 +307,44 @@ def test_gpu_evaluator_fails_loudly_without_a_gpu(tmp_path):
     c = _fresh_case(tmp_path, "C1")
     with pytest.raises(RuntimeError, match="evaluator|CUDA"):
         c.build_tables(shi_window_only=True, evaluator="gpu")
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "INPUT_CDF")), reason="the reference tree is only mounted in the build container")
+def test_every_shipped_material_file_loads_or_is_refused_for_a_stated_reason(tmp_path):
+    """Coverage of the input contract over ALL 51 .cdf files the reference ships (read in place, nothing copied): which ones
+    the host half accepts, and why it refuses the others -- never silently."""
+    dd = tmp_path / "data"
+    os.makedirs(dd)
+    os.symlink(os.path.join(REF, "INPUT_CDF"), dd / "INPUT_CDF")
+    os.symlink(os.path.join(REF, "INPUT_DOS"), dd / "INPUT_DOS")
+    os.symlink(os.path.join(tk._abi.REPO, "data", "INPUT_EADL"), dd / "INPUT_EADL")
+    import shutil
+    shutil.copy(os.path.join(tk._abi.REPO, "data", "INPUT_PARAMETERS.default.txt"), dd)
+    loaded, refused = [], {}
+    for f in sorted(os.listdir(os.path.join(REF, "INPUT_CDF"))):
+        if not f.endswith(".cdf"):
+            continue
+        m = f[:-4]
+        try:
+            tk.Case.load(tk.make_run_dir(str(tmp_path / "run" / m), (m, 54, 167.0, 0, 10), data_dir=str(dd)))
+            loaded.append(m)
+        except RuntimeError as e:
+            refused[m] = str(e)
+    assert len(loaded) + len(refused) == 51
+    # complete files (every shell with its CDF oscillators, Ip, Nel and Auger time), incl. atoms without shells (H2O, C2H4)
+    assert len(loaded) == 25 and {"Al2O3", "SiO2_cryst", "Diamond", "Au", "H2O", "C2H4", "LiF", "yag", "Olivine"} <= set(loaded)
+
+    def why(m, text):
+        assert text in refused[m], (m, refused[m])
+
+    for m in ("GaN", "MgO", "ZnO", "Y2O3_test"):                    # need EADL2023.ALL for what the file leaves out (tests/test_eadl.py)
+        why(m, "EADL2023.ALL")
+    for m in ("CdS_sp", "Si_sp", "Fe", "PbS_sp"):                   # chemical formula instead of an element list: Decompose_compound + all-shells EADL branch
+        why(m, "chemical-formula")
+    for m in ("Al2O3_phonons", "Graphite1", "Si1", "TiO2"):         # pre-3.x format: the reference's reader refuses them too (SURVEY 8, caveat i)
+        why(m, "old-format")
+    why("Ru", "BEB")
+    assert sum("chemical-formula" in v for v in refused.values()) == 14
