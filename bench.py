@@ -353,16 +353,29 @@ def run_ours(args):
     dom = max((k for k in ktimes if k in class_bytes), key=lambda k: ktimes[k]["ms"])
     dom_ms, dom_n = ktimes[dom]["ms"], max(1, ktimes[dom]["launches"])
     achieved = class_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    traffic = None
+    traffic, ipc = None, {}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(dom)
+            nj = json.load(f)
+        traffic = nj.get(dom)
+        ipc = {k: v for k, v in nj.get("warp_inst_per_collision", {}).items() if not k.startswith("_")}
     except Exception:
         pass
+    # the bound that does hold the throughput kernels: instruction issue.  Warp instructions per collision come from the ncu
+    # capture of the same workload (profiles/), collisions and time are measured live; peak = SMs x 4 schedulers x SM clock
+    sm_clock_hz = float((clk or {}).get("sm_mhz") or 1965.0) * 1e6
+    issue_peak = torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * sm_clock_hz
+    cold_n = {"k_wave<electron,cold>": cold_ev["electron"], "k_wave<vbhole,cold>": cold_ev["vbhole"]}
+    issue = {k: {"warp_inst_per_collision": ipc[k], "achieved_Gwarp_inst_s": cold_n[k] * ipc[k] / (ktimes[k]["ms"] * 1e-3) / 1e9,
+                 "frac": cold_n[k] * ipc[k] / (ktimes[k]["ms"] * 1e-3) / issue_peak}
+             for k in cold_n if k in ipc and k in ktimes and ktimes[k]["ms"] > 0}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "launches": dom_n, "avg_launch_ms": dom_ms / dom_n,
                 "algorithmic_bytes_per_launch": class_bytes[dom] / dom_n,
                 "kernel_share_of_step": dom_ms / ms if ms > 0 else None,
+                "instruction_issue": {"peak_Gwarp_inst_s": issue_peak / 1e9, "kernels": issue,
+                                      "note": "secondary roofline of the throughput (cold) kernels: warp instructions issued / "
+                                              "(SMs x 4 schedulers x SM clock); instructions per collision from profiles/ncu_traffic.json"},
                 "per_kernel": {k: {"GB/s": (class_bytes[k] / (ktimes[k]["ms"] * 1e-3) / 1e9 if ktimes[k]["ms"] > 0 else 0.0),
                                    "ms": ktimes[k]["ms"], "launches": ktimes[k]["launches"]} for k in class_bytes},
                 "note": "algorithmic bytes = collisions x compulsory particle-state bytes (SURVEY.md 8d); histories stay in "
