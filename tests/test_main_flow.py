@@ -1,0 +1,68 @@
+"""Program flow of Universal_MC_for_SHI_MAIN.f90 around the engine (trekis-3_b200/main.py): run directory in, table cache and
+output tree out.  The table half runs without a GPU; the whole run is a GPU test."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import trekis3_b200 as tk
+from trekis3_b200 import main as flow
+
+ROOT = tk._abi.REPO
+
+
+def test_tables_are_built_once_and_then_taken_from_the_reference_cache(tmp_path):
+    d = tk.make_run_dir(str(tmp_path / "run"), "C3")
+    first = flow.run(d, tables_only=True, evaluator=None, shi_window_only=True)
+    assert first["tables"] == "built:host-direct"
+    out = os.path.join(d, "OUTPUT_Diamond")
+    assert os.path.isfile(os.path.join(out, "OUTPUT_Electron_IMFPs_Free_CDF_DOS_0.00_K.dat"))
+    assert os.path.isdir(os.path.join(out, "diff_CS")) and os.path.isdir(os.path.join(out, "OUTPUT_Xe_in_Diamond"))
+    second = flow.run(d, tables_only=True, evaluator=None, shi_window_only=True)
+    assert second["tables"] == "cache" and second["t_tables_s"] < first["t_tables_s"]
+    # a stale cache (grid mismatch) is rebuilt, as the reference decides (Analytical_IMFPs.f90:317-323)
+    p = os.path.join(out, "OUTPUT_Hole_IMFPs_CDF_CDF_0.00_K.dat")
+    lines = open(p).read().splitlines(True)
+    open(p, "w").writelines(lines[:-2])
+    third = flow.run(d, tables_only=True, evaluator=None, shi_window_only=True)
+    assert third["tables"] == "built:host-direct" and len(open(p).read().splitlines()) == len(lines)
+    # and --redo-tables ignores a valid cache (the reference's redo_MFP keywords)
+    assert flow.run(d, tables_only=True, evaluator=None, redo_tables=True, shi_window_only=True)["tables"] == "built:host-direct"
+
+
+def test_command_line_tables_only(tmp_path):
+    d = tk.make_run_dir(str(tmp_path / "run"), "C3")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "trekis3_run.py"), d, "--tables-only", "--evaluator", "host", "--quiet"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.startswith("tables: built:host-direct")
+    assert os.path.isdir(os.path.join(d, "OUTPUT_Diamond", "diff_CS"))
+
+
+def test_monte_carlo_needs_the_gpu(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    d = tk.make_run_dir(str(tmp_path / "run"), "C1", nmc=2)
+    flow.run(d, tables_only=True, evaluator=None, shi_window_only=True)
+    with pytest.raises(RuntimeError):
+        flow.run(d)
+
+
+@pytest.mark.gpu
+def test_whole_run_writes_the_reference_output_tree(tmp_path):
+    d = tk.make_run_dir(str(tmp_path / "run"), "C1", nmc=20)
+    info = flow.run(d, verbose=False, shi_window_only=True)
+    assert info["tables"] == "built:gpu" and tk.gpu_library_loaded()
+    assert not info["stats"]["errors"] and info["stats"]["max_energy_drift"] < 1e-9
+    od = info["out_dir"]
+    assert od.startswith(os.path.join(d, "OUTPUT_Al2O3", "OUTPUT_Xe_in_Al2O3")) and os.path.isfile(os.path.join(od, "Total_numbers.txt"))
+    tot = np.loadtxt(os.path.join(od, "Total_numbers.txt"), skiprows=1)
+    assert tot.shape[0] == 5 and 15e3 < tot[-1, 3] < 40e3                  # deposited energy per ion ~ S_e x layer
+    assert np.allclose(tot[1:, 3], tot[-1, 3], rtol=1e-9)                  # conserved once the ion has left
+    # second run: tables from the cache it wrote, same result (streams are keyed by the global iteration index)
+    info2 = flow.run(d, verbose=False)
+    assert info2["tables"] == "cache" and info2["out_dir"] != od            # the reference numbers repeated output directories
+    assert np.allclose(info2["tallies"], info["tallies"], rtol=1e-6, atol=1e-12)
