@@ -66,13 +66,17 @@ def run(run_dir, nmc=None, evaluator="auto", threads=0, redo_tables=False, table
     _stamp(verbose, "Input files read:", t0)
     info = {"rank": rank, "world": world}
     # tables: rank 0 prepares (and writes) the cache, the other ranks read it afterwards -- the reference broadcasts instead
-    dist = None
+    dist, own_group = None, False
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        if not dist.is_initialized():
-            dist.init_process_group("nccl" if not tables_only else "gloo")
+        own_group = not dist.is_initialized()
+        if own_group:
+            if tables_only:
+                dist.init_process_group("gloo")
+            else:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if rank == 0:
         info["tables"] = prepare_tables(case, run_dir, evaluator, threads, redo_tables, True, verbose, shi_window_only)
     if dist is not None:
@@ -82,6 +86,8 @@ def run(run_dir, nmc=None, evaluator="auto", threads=0, redo_tables=False, table
     _stamp(verbose, "Mean free paths and differential tables ready:", t0)
     info["t_tables_s"] = time.perf_counter() - t0
     if tables_only:
+        if own_group:
+            dist.destroy_process_group()
         return info
 
     import torch
@@ -111,6 +117,8 @@ def run(run_dir, nmc=None, evaluator="auto", threads=0, redo_tables=False, table
     eng.close()
     if dist is not None:
         dist.barrier()
+        if own_group:
+            dist.destroy_process_group()
     _stamp(verbose, "Done:", t0)
     info["t_total_s"] = time.perf_counter() - t0
     return info
