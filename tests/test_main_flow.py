@@ -41,6 +41,19 @@ def test_command_line_tables_only(tmp_path):
     assert os.path.isdir(os.path.join(d, "OUTPUT_Diamond", "diff_CS"))
 
 
+def test_two_ranks_share_one_table_cache(tmp_path):
+    """Under torchrun rank 0 builds the tables and writes the cache, the other ranks read it (the reference broadcasts)."""
+    d = tk.make_run_dir(str(tmp_path / "run"), "C3")
+    prog = ("import sys; sys.path.insert(0, %r); import trekis3_b200; from trekis3_b200 import main as flow; import os; "
+            "i = flow.run(%r, tables_only=True, evaluator=None, shi_window_only=True); "
+            "print('RANK', os.environ['RANK'], i['tables'], flush=True)") % (ROOT, d)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", "--no-python", sys.executable, "-c", prog], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = r.stdout
+    assert "RANK 0 built:host-direct" in out and "RANK 1 cache" in out
+
+
 def test_monte_carlo_needs_the_gpu(tmp_path):
     import torch
     if torch.cuda.is_available():

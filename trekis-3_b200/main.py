@@ -70,7 +70,8 @@ def run(run_dir, nmc=None, evaluator="auto", threads=0, redo_tables=False, table
     if world > 1:
         import torch
         import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
+        if not tables_only:
+            torch.cuda.set_device(local_rank)
         own_group = not dist.is_initialized()
         if own_group:
             if tables_only:
