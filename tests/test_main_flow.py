@@ -79,3 +79,19 @@ def test_whole_run_writes_the_reference_output_tree(tmp_path):
     info2 = flow.run(d, verbose=False)
     assert info2["tables"] == "cache" and info2["out_dir"] != od            # the reference numbers repeated output directories
     assert np.allclose(info2["tallies"], info["tallies"], rtol=1e-6, atol=1e-12)
+
+
+def test_bench_reference_arm_prints_one_json_line(tmp_path):
+    """`bench.py --impl reference`: the CPU restatement timed on the host cores; exactly one JSON line on stdout with the keys
+    the driver reads (the GPU arm shares the printing path and cannot run here)."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--config", "C1", "--nmc", "10"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1
+    b = json.loads(lines[0])
+    assert b["impl"] == "reference" and b["unit"] == "iterations/s" and b["higher_is_better"] is True and b["value"] > 0
+    assert b["cpu_baseline"]["kind"] == "port" and b["cpu_baseline"]["cores"] >= 1
+    assert b["e2e"] == {"value": b["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert b["config"]["workload"].startswith("C1: Xe 167 MeV in Al2O3")
