@@ -85,6 +85,15 @@ def test_variants_cutoff_linear_grid_emission(tmp_path):
     check_against_oracle(case, 4)
 
 
+@pytest.mark.parametrize("name", ["target_at_300K", "plasmon_pole_dispersion", "hole_mass_1", "elastic_scattering_off",
+                                  "plasmon_integration_limit"])
+def test_more_input_switches(tmp_path, name):
+    from test_oracle import SWITCHES
+    case = tk.Case.load(tk.make_run_dir(str(tmp_path / "r"), "C1", edits=SWITCHES[name]))
+    case.build_tables(shi_window_only=True, evaluator="gpu")
+    check_against_oracle(case, 4)
+
+
 def test_mott_elastic_scattering(tmp_path):
     d = tk.make_run_dir(str(tmp_path / "v2"), "C1", edits={12: "0   1"})
     case = tk.Case.load(d)

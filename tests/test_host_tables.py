@@ -348,3 +348,33 @@ def test_every_shipped_material_file_loads_or_is_refused_for_a_stated_reason(tmp
         why(m, "old-format")
     why("Ru", "BEB")
     assert sum("chemical-formula" in v for v in refused.values()) == 14
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3, 4])
+def test_equilibrium_charge_models(tmp_path, kind):
+    """Equilibrium_charge_SHI (Cross_sections.f90:2641-2680): Barkas, Bohr, Nikolaev-Dmitriev, Schiwietz-Grande, fixed --
+    restated here from the published formulas, against the host library (the Monte-Carlo kernels use the same routine per
+    ion collision: tests/test_oracle.py::test_charge_models_in_the_monte_carlo)."""
+    c = tk.Case.load(tk.make_run_dir(str(tmp_path / "r"), "C1", edits={10: "%d   23.5   ! kind of Zeff; fixed value" % kind}))
+    E = 167e6
+    _, _, zeff = c.eval_SHI(E, 0, 0)
+    Zp, M = 54.0, 131.293
+    vp = math.sqrt(2.0 * E * g_e / (M * g_Mp))
+    v0 = math.sqrt(2.0 * 13.6056981 * g_e / g_me)
+    Zt = (13 * 2 + 8 * 3) / 5.0                                   # Al2O3
+    if kind == 1:
+        want = Zp * (1.0 - math.exp(-(vp / v0 / Zp ** 0.66666666)))
+    elif kind == 2:
+        want = Zp * (1.0 + (vp / (Zp ** 0.45 * v0 * 4.0 / 3.0)) ** (-1.0 / 0.6)) ** (-0.6)
+    elif kind == 3:
+        c1 = 1.0 - 0.26 * math.exp(-Zt / 11.0 - (Zt - Zp) ** 2 / 9.0)
+        vpvo = Zp ** (-0.543) * vp / v0
+        c2 = 1.0 + 0.03 * vpvo * math.log(Zt)
+        x = c1 * (vpvo / c2 / 1.54) ** (1.0 + 1.83 / Zp)
+        want = Zp * (8.29 * x + x ** 4) / (0.06 / x + 4.0 + 7.4 * x + x ** 4)
+    elif kind == 4:
+        want = 23.5
+    else:
+        want = Zp * (1.0 - math.exp(-(vp * 125.0 / g_cvel / Zp ** 0.66666666)))
+    assert zeff == pytest.approx(want, rel=1e-13)
+    assert 10.0 < zeff < 54.0

@@ -67,6 +67,50 @@ def test_atom_without_shells_of_its_own_water(tmp_path):
     assert drift.max() < 1e-9
 
 
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+def test_charge_models_in_the_monte_carlo(tmp_path, kind):
+    """The ion's equilibrium charge is recomputed at every ion collision (Monte_Carlo.f90:2196) with the model of input line 10:
+    the device code (CUDA physics header, emulated on the CPU) and the oracle agree for every model, and the models differ."""
+    case = tk.Case.load(tk.make_run_dir(str(tmp_path / "r"), "C1", edits={10: "%d   23.5   ! kind of Zeff; fixed value" % kind}))
+    case.build_tables(shi_window_only=True, cache_dir=CACHE)
+    to, so, eo, no = oracle_api.run(case, 0, 3, rng_mode=1)
+    te, se, ee, ne = emul_api.run(case, 0, 3, batch=3)
+    assert not so["errors"]
+    assert_same(case, to, te, so, se)
+    assert np.allclose(eo, ee, rtol=1e-12)
+
+
+SWITCHES = {                                  # INPUT_PARAMETERS.txt line -> text (Reading_files_and_parameters.f90:300-400)
+    "target_at_300K": {9: "300.0"},                   # phonon absorption / emission weights
+    "elastic_scattering_off": {12: "-1   1"},
+    "elastic_Zeff_Barkas_like": {12: "1   0"},
+    "plasmon_pole_dispersion": {13: "2   0"},
+    "ritchie_dispersion": {13: "3   0"},
+    "free_electron_mass": {13: "1   -1"},
+    "effective_mass_0.5": {13: "1   0.5"},
+    "plasmon_integration_limit": {14: "1"},
+    "hole_mass_1": {15: "1.0"},
+    "heavy_holes": {15: "1.0d10"},
+}
+
+
+@pytest.mark.parametrize("name", sorted(SWITCHES))
+def test_input_switches_through_oracle_and_device_code(tmp_path, name):
+    """Every switch of INPUT_PARAMETERS.txt that the path supports, beyond the defaults: tables are rebuilt with it and the
+    device code (emulated) gives the oracle's events and tallies with the same Philox streams."""
+    case = tk.Case.load(tk.make_run_dir(str(tmp_path / "r"), "C1", edits=SWITCHES[name]))
+    case.build_tables(shi_window_only=True)
+    to, so, eo, no = oracle_api.run(case, 0, 2, rng_mode=1)
+    te, se, ee, ne = emul_api.run(case, 0, 2, batch=2)
+    assert not so["errors"] and so["events"]["shi"] > 100
+    assert_same(case, to, te, so, se)
+    assert np.array_equal(no, ne) and np.allclose(eo, ee, rtol=1e-12)
+    drift = np.abs(eo[:, 1:] - eo[:, -1:]) / eo[:, -1:]
+    assert drift.max() < 1e-9
+    if name == "elastic_scattering_off":
+        assert so["events"]["el_elastic"] == 0 and so["events"]["vbh_elastic"] == 0
+
+
 def test_wavefront_equals_time_ordered_loop_photons_and_radiative_decay(tmp_path):
     d = tk.make_run_dir(str(tmp_path / "c2"), "C2")
     case = tk.Case.load(d)
