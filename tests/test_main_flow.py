@@ -34,7 +34,7 @@ def test_tables_are_built_once_and_then_taken_from_the_reference_cache(tmp_path)
 
 def test_command_line_tables_only(tmp_path):
     d = tk.make_run_dir(str(tmp_path / "run"), "C3")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "trekis3_run.py"), d, "--tables-only", "--evaluator", "host", "--quiet"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "trekis3_run.py"), d, "--tables-only", "--evaluator", "host", "--quiet", "--shi-window-only"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     assert r.stdout.startswith("tables: built:host-direct")

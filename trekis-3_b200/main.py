@@ -136,9 +136,11 @@ def main(argv=None):
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--out-root", default=None, help="where OUTPUT_<material>/ is written (default: the run directory)")
     ap.add_argument("--quiet", action="store_true")
+    ap.add_argument("--shi-window-only", action="store_true", help="(tests) tabulate the ion only around its own energy")
     a = ap.parse_args(argv)
     info = run(a.run_dir, nmc=a.nmc, evaluator=None if a.evaluator == "host" else a.evaluator, threads=a.threads,
-               redo_tables=a.redo_tables, tables_only=a.tables_only, out_root=a.out_root, verbose=not a.quiet)
+               redo_tables=a.redo_tables, tables_only=a.tables_only, out_root=a.out_root, verbose=not a.quiet,
+               shi_window_only=a.shi_window_only)
     if info["rank"] == 0:
         if "out_dir" in info:
             st = info["stats"] or {}
