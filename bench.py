@@ -4,8 +4,13 @@
 Metric (BASELINE.json): MC iterations/s (whole job, all GPUs); events/s reported beside it.
 Workload at N=1: BASELINE.json configs[1] -- Au 2187 MeV in SiO2_cryst, photon transport and Auger/radiative
 decays on, 1000 MC iterations per step.  A step is one do_Monte_Carlo call (1000 ion impacts + full cascades
-to 100 fs).  N>1: weak scaling -- every rank runs its own 1000 iterations (disjoint global iteration ranges,
-Philox streams keyed by the global index) followed by ONE NCCL all-reduce of the packed tally buffer.
+to 100 fs).  N>1, two modes:
+  --scaling weak   (default for C1-C4) every rank runs its own NMC iterations per step (disjoint global ranges);
+  --scaling strong (default for --config C5, BASELINE.json configs[4]) the NMC = 1e5 iterations of a step are split
+                   contiguously over the ranks, value = NMC / max-rank time.
+Either way a step ends with ONE ncclAllReduce of the packed tally buffer issued by the library itself on its own stream
+(trk3_mc_comm_init: the all-reduce sits behind the C ABI, replacing the 26 MPI_Reduce of Monte_Carlo.f90:131-389);
+torch.distributed only carries the 128-byte NCCL id and the barrier / max-over-ranks of the timing.
 
   python bench.py --gpus N --steps K --warmup W            our CUDA engine
   python bench.py --impl reference ...                      the CPU restatement of the reference on the host cores
@@ -33,7 +38,9 @@ def load_case(config, nmc):
     run_dir = os.path.join(ROOT, ".bench_run", f"{config}_{os.getpid()}")
     tk.make_run_dir(run_dir, config, nmc=nmc)
     case = tk.Case.load(run_dir)
-    case.build_tables(shi_window_only=True, cache_dir=os.path.join(ROOT, ".table_cache"))
+    # the tables the reference main builds: the ion over its whole energy grid (Analytical_IMFPs.f90:2242-2510).  Built once
+    # (host threads: a few seconds; excluded from every timing, as the reference caches them too) and kept in .table_cache
+    case.build_tables(shi_window_only=False, cache_dir=os.path.join(ROOT, ".table_cache"))
     return case
 
 
@@ -190,6 +197,8 @@ def run_reference(args):
     if rank != 0:
         return
     case = load_case(args.config, args.nmc)
+    import oracle_api
+    flags = oracle_api.use_native_build()       # compiled on THIS machine: -O3 -march=native
     per_step = max(2.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         cpu_reference_rate(case, min(per_step, 2.0))
@@ -200,14 +209,15 @@ def run_reference(args):
     value = n_tot / t_tot
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.config, args.nmc), "sample": f"{n_tot} iterations in {t_tot:.1f} s"},
         "events_per_s": sum(ev_rates) / len(ev_rates),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"oracle/trk3_oracle.cpp (reference algorithm incl. O(N) next-event search), "
+                         "sample": f"oracle/trk3_oracle.cpp (reference algorithm incl. O(N) next-event search, {flags}), "
                                    f"{n_tot} iterations of the same workload in {t_tot:.1f} s on {os.cpu_count()} threads; "
-                                   "the Fortran reference cannot be built here (no Fortran compiler in the image)"},
+                                   "the Fortran reference cannot be built: no Fortran compiler in the image or on the box "
+                                   "(profiles/r2_probe_fortran.txt; recipe: oracle/build_ref.sh)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -233,7 +243,12 @@ def run_ours(args):
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # rank 0 builds the tables (or finds them in .table_cache), the other ranks then load them from the cache
+    if dist is not None and rank != 0:
+        dist.barrier()
     case = load_case(args.config, args.nmc)
+    if dist is not None and rank == 0:
+        dist.barrier()
     nmc = args.nmc
     lay = case.layout()
     stream = torch.cuda.Stream()
@@ -241,16 +256,24 @@ def run_ours(args):
     eng = tk.Engine(case, device=local_rank, batch=args.batch)
     eng.set_stream(stream.cuda_stream)
     eng.set_device_tallies(tally.data_ptr())
+    if dist is not None:
+        eng.comm_init_torch(local_rank)         # from here on run_device() is collective: the library all-reduces the tallies
+    strong = args.scaling == "strong"
+
+    def my_range(k):
+        """global iteration range of this rank in step k"""
+        if strong:          # the NMC iterations of the step split contiguously over the ranks
+            return k * nmc + rank * nmc // world, k * nmc + (rank + 1) * nmc // world
+        first = ((k * world) + rank) * nmc      # weak: every rank its own NMC iterations
+        return first, first + nmc
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")     # > 126 MB L2
 
     def step(k):
         # iterations of this rank for step k: disjoint global ranges -> independent Philox streams
-        first = ((k * world) + rank) * nmc
+        lo, hi = my_range(k)
         with torch.cuda.stream(stream):
             tally.zero_()
-            st = eng.run_device(first, first + nmc)
-            if dist is not None:
-                dist.all_reduce(tally)          # the single collective of the path (MPI_Reduce x26 in the reference)
+            st = eng.run_device(lo, hi)         # ends with the single collective of the path, issued by the library (N > 1)
         return st
 
     for k in range(args.warmup):
@@ -298,30 +321,37 @@ def run_ours(args):
         ms, events_all = float(tmax[0]), float(tsum[1])
     else:
         events_all = float(events_total)
-    value = world * nmc * args.steps / (ms * 1e-3)
+    job_iterations = nmc if strong else world * nmc          # iterations of one step, all ranks
+    value = job_iterations * args.steps / (ms * 1e-3)
     ktimes = eng.kernel_times()
 
     # ---- end-to-end through the public API with HOST buffers (tables H2D + tallies D2H inside the timed region)
     e2e_steps = max(1, min(args.steps, 3))
     host_tally = np.zeros(lay.total)
-    tk.do_Monte_Carlo(case, NMC=nmc, device=local_rank, batch=args.batch)            # warm-up of the public path (creates the handle)
+    e2e_comm = None
+    if dist is not None:
+        id_t = torch.zeros(tk.engine.NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            id_t = torch.frombuffer(bytearray(tk.nccl_unique_id()), dtype=torch.uint8).clone().cuda()
+        dist.broadcast(id_t, src=0)
+        e2e_comm = (world, rank, bytes(id_t.cpu().numpy().tobytes()))
+    lo, hi = my_range(0)
+    tk.do_Monte_Carlo(case, NMC=hi - lo, device=local_rank, batch=args.batch, comm=e2e_comm)   # warm-up of the public path (creates the handle)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        first = ((k * world) + rank) * nmc
-        tl, _ = tk.do_Monte_Carlo(case, NMC=nmc, device=local_rank, it_begin=first, batch=args.batch)
-        if dist is not None:
-            g = torch.from_numpy(tl).cuda(); dist.all_reduce(g); tl = g.cpu().numpy()
+        lo, hi = my_range(k)
+        tl, _ = tk.do_Monte_Carlo(case, NMC=hi - lo, device=local_rank, it_begin=lo, batch=args.batch, comm=e2e_comm)   # collective for N > 1
         host_tally += tl
     torch.cuda.synchronize()
     e2e_t = time.perf_counter() - t0
     if dist is not None:
         tt = torch.tensor([e2e_t], dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); e2e_t = float(tt[0])
-    e2e_value = world * nmc * e2e_steps / e2e_t
+    e2e_value = job_iterations * e2e_steps / e2e_t
     h2d = int(tk.engine._handles[tk.engine._shape_key(case, local_rank)].table_bytes()) + 4096     # tables + configuration block
-    d2h = int(lay.total * 8 + nmc * lay.Nt * 20)
+    d2h = int(lay.total * 8 + (my_range(0)[1] - my_range(0)[0]) * lay.Nt * 20)
     tk.release_handles()
 
     if rank != 0:
@@ -394,11 +424,13 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.config, nmc), "iterations_in_flight": args.batch,
                    "l2": "256 MiB buffer written between timed steps (L2 flush); queues stream through HBM",
-                   "parallelism": f"iterations sharded over {world} GPU(s), one NCCL all-reduce of {lay.total} doubles per step",
+                   "parallelism": (f"{nmc} iterations per step split contiguously over {world} GPU(s) (strong scaling)" if strong else
+                                   f"every one of {world} GPU(s) runs its own {nmc} iterations per step (weak scaling)") +
+                                  f"; one ncclAllReduce of {lay.total} doubles per step, issued by libtrekis3_gpu.so on its own stream",
                    "inputs": "shipped INPUT_CDF/INPUT_DOS files; radiative widths from data/INPUT_EADL/radiative_widths.dat "
                              "(approximate, EADL2023.ALL is not redistributable)"},
         "events_per_s": events_all / (ms * 1e-3), "events_per_s_per_gpu": events_all / (ms * 1e-3) / world,
@@ -429,7 +461,12 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="iterations in flight on the GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="N > 1: weak = NMC iterations per rank and step (default), strong = NMC iterations per step split over the "
+                         "ranks (default for --config C5, the configuration BASELINE.json names for 1/2/4/8 GPUs)")
     args = ap.parse_args()
+    if args.scaling is None:
+        args.scaling = "strong" if args.config == "C5" else "weak"
     protect_stdout()
     import trekis3_b200 as tk
     if args.nmc is None:

@@ -232,6 +232,30 @@ int trk3_mc_set_device_tallies(trk3_engine *eng, double *device_buffer);
  * of classes.  Classes 0-3 and 8 of one generation run on concurrent streams: their times overlap. */
 int trk3_mc_kernel_times(trk3_engine *eng, double *ms, uint64_t *launches, int n);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: the role of MPI_subroutines.f90 on this path.  The reference splits the iterations over the MPI ranks
+ * (Monte_Carlo.f90:111-129) and then sums the 26 Out_* arrays with 26 MPI_Reduce calls (:131-389).  Here every rank
+ * (one process per GPU) runs its own range of GLOBAL iteration indices, and -- once a communicator is attached -- every
+ * trk3_mc_run / trk3_mc_run_device call is COLLECTIVE: it ends with ONE ncclAllReduce(ncclDouble, ncclSum) of the packed
+ * tally buffer, issued on the engine's own stream right behind the folding kernels, and every rank returns the reduced
+ * tallies (the reference leaves them on rank 0 only).  The per-rank statistics (trk3_stats) stay local.
+ *   trk3_nccl_unique_id   rank 0 creates the 128-byte NCCL id; the caller distributes it (MPI_Bcast, a file, torch ...)
+ *   trk3_mc_comm_init     ncclCommInitRank on the engine's device; the engine owns (and destroys) the communicator
+ *   trk3_mc_set_comm      attach a caller-owned ncclComm_t instead (NULL detaches)
+ * NCCL is loaded at run time (dlopen "libnccl.so.2": the copy already mapped into the process, e.g. PyTorch's, or the
+ * system's), so the library itself has no link-time dependency on it.  If a rank fails before its all-reduce the other
+ * ranks block in theirs: the caller aborts the job, as the reference's MPI_Abort does (MPI_subroutines.f90:177-188). */
+#define TRK3_NCCL_UNIQUE_ID_BYTES 128
+int trk3_nccl_unique_id(void *id_out_128_bytes);
+int trk3_mc_comm_init(trk3_engine *eng, int nranks, int rank, const void *id_128_bytes);
+int trk3_mc_set_comm(trk3_engine *eng, void *nccl_comm, int nranks);
+int trk3_mc_comm_size(const trk3_engine *eng);          /* ranks of the attached communicator, 1 if none */
+
+/* Bring an engine back to a defined state after a failed run (CUDA error, persistent overflow): waits for its streams,
+ * clears the device queues, counters and tallies and the error text.  Tables and options stay.  Returns TRK3_E_CUDA if the
+ * device itself is lost (sticky CUDA error): then only trk3_mc_destroy is left. */
+int trk3_mc_reset(trk3_engine *eng);
+
 /* Tunables: "batch" iterations in flight, "cap_factor" queue capacity, "use_smem", "refill_min", "profile" ... */
 int trk3_mc_set_option(trk3_engine *eng, const char *name, double value);
 

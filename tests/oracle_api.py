@@ -9,17 +9,29 @@ import trekis3_b200 as tk
 from trekis3_b200 import _abi
 
 _lib = None
+_native = False
 
 
-def build():
-    subprocess.run(["make", "-C", os.path.join(_abi.REPO, "oracle")], check=True, capture_output=True)
+def build(native=False):
+    subprocess.run(["make", "-C", os.path.join(_abi.REPO, "oracle")] + (["native"] if native else []), check=True, capture_output=True)
+
+
+def use_native_build():
+    """The CPU arm of bench.py: compile the oracle ON THIS MACHINE with -O3 -march=native and use that
+    library from now on.  Returns the compiler flags for the report."""
+    global _lib, _native
+    build(native=True)
+    _lib, _native = None, True
+    return "g++ -O3 -march=native -ffp-contract=off"
 
 
 def lib():
     global _lib
     if _lib is None:
         path = _abi.lib_path("oracle")
-        if not os.path.exists(path):
+        if _native:
+            path = os.path.join(os.path.dirname(path), "libtrk3_oracle_native.so")
+        elif not os.path.exists(path):
             build()
         l = C.CDLL(path)
         PD = C.POINTER(C.c_double)

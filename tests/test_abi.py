@@ -77,3 +77,19 @@ def test_product_code_never_touches_the_oracle():
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert "trk3_oracle_run" not in txt and "trk3_emul_run" not in txt, os.path.join(dp, f)
                 assert "oracle_api" not in txt and "emul_api" not in txt, os.path.join(dp, f)
+
+
+def test_nccl_entry_points_fail_cleanly_without_an_engine():
+    """The collective half of the ABI (trk3_mc_comm_init / trk3_mc_set_comm / trk3_mc_reset) validates its arguments before it
+    touches NCCL or CUDA: callable in the GPU-less container."""
+    lib = C.CDLL(_abi.lib_path("gpu"))
+    lib.trk3_mc_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.trk3_mc_set_comm.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.trk3_mc_reset.argtypes = [C.c_void_p]
+    lib.trk3_mc_comm_size.argtypes = [C.c_void_p]
+    buf = C.create_string_buffer(128)
+    assert lib.trk3_mc_comm_init(None, 2, 0, buf) == -1
+    assert lib.trk3_mc_set_comm(None, None, 1) == -1
+    assert lib.trk3_mc_reset(None) == -1
+    assert lib.trk3_mc_comm_size(None) == 1
+    assert lib.trk3_nccl_unique_id(None) == -1

@@ -17,7 +17,9 @@ def test_tables_are_built_once_and_then_taken_from_the_reference_cache(tmp_path)
     d = tk.make_run_dir(str(tmp_path / "run"), "C3")
     first = flow.run(d, tables_only=True, evaluator=None, shi_window_only=True)
     assert first["tables"] == "built:host-direct"
-    out = os.path.join(d, "OUTPUT_Diamond")
+    # window-only tables (test shortcut) must never land where the reference looks for its cache
+    assert not os.path.exists(os.path.join(d, "OUTPUT_Diamond"))
+    out = os.path.join(d, "TEST_ONLY_window_tables", "OUTPUT_Diamond")
     assert os.path.isfile(os.path.join(out, "OUTPUT_Electron_IMFPs_Free_CDF_DOS_0.00_K.dat"))
     assert os.path.isdir(os.path.join(out, "diff_CS")) and os.path.isdir(os.path.join(out, "OUTPUT_Xe_in_Diamond"))
     second = flow.run(d, tables_only=True, evaluator=None, shi_window_only=True)
@@ -28,8 +30,24 @@ def test_tables_are_built_once_and_then_taken_from_the_reference_cache(tmp_path)
     open(p, "w").writelines(lines[:-2])
     third = flow.run(d, tables_only=True, evaluator=None, shi_window_only=True)
     assert third["tables"] == "built:host-direct" and len(open(p).read().splitlines()) == len(lines)
-    # and --redo-tables ignores a valid cache (the reference's redo_MFP keywords)
+    # and --redo-tables ignores a valid cache
     assert flow.run(d, tables_only=True, evaluator=None, redo_tables=True, shi_window_only=True)["tables"] == "built:host-direct"
+    assert flow.run(d, tables_only=True, evaluator=None, shi_window_only=True)["tables"] == "cache"
+    # the reference's own conditions (Analytical_IMFPs.f90:307-327): a redo_* keyword in INPUT_PARAMETERS.txt ...
+    ip = os.path.join(d, "INPUT_PARAMETERS.txt")
+    text = open(ip).read()
+    open(ip, "w").write(text + "redo_IMFP\n")
+    assert flow.run(d, tables_only=True, evaluator=None, shi_window_only=True)["tables"] == "built:host-direct"
+    open(ip, "w").write(text)
+    assert flow.run(d, tables_only=True, evaluator=None, shi_window_only=True)["tables"] == "cache"
+    # ... or a .cdf file that is newer than the cached tables
+    import shutil
+    cdf_dir = os.path.join(d, "INPUT_CDF")
+    real = os.path.realpath(cdf_dir)
+    os.unlink(cdf_dir); shutil.copytree(real, cdf_dir)
+    os.utime(os.path.join(cdf_dir, "Diamond.cdf"), None)            # touched: now newer than the tables
+    assert flow.run(d, tables_only=True, evaluator=None, shi_window_only=True)["tables"] == "built:host-direct"
+    assert flow.run(d, tables_only=True, evaluator=None, shi_window_only=True)["tables"] == "cache"
 
 
 def test_command_line_tables_only(tmp_path):
@@ -38,7 +56,7 @@ def test_command_line_tables_only(tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     assert r.stdout.startswith("tables: built:host-direct")
-    assert os.path.isdir(os.path.join(d, "OUTPUT_Diamond", "diff_CS"))
+    assert os.path.isdir(os.path.join(d, "TEST_ONLY_window_tables", "OUTPUT_Diamond", "diff_CS"))
 
 
 def test_two_ranks_share_one_table_cache(tmp_path):

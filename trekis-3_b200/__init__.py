@@ -9,6 +9,6 @@ The CUDA engine has no CPU fallback: do_Monte_Carlo raises if libtrekis3_gpu.so 
 """
 from ._abi import Config, Tables, TallyLayout, Stats, TALLY_NAMES, EVENT_NAMES, EVENT_BYTES, lib_path  # noqa: F401
 from .host import Case, make_run_dir, CONFIGS  # noqa: F401
-from .engine import Engine, do_Monte_Carlo, gpu_library_loaded, release_handles  # noqa: F401
+from .engine import Engine, do_Monte_Carlo, gpu_library_loaded, release_handles, nccl_unique_id  # noqa: F401
 
 __version__ = "0.1.0"

@@ -16,6 +16,7 @@
 //   * the tally sums stay in one packed device buffer so that multi-GPU runs need a single all-reduce.
 // No tensor cores: nothing here is a dense contraction.  No CPU fallback: every entry point fails if CUDA does.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -559,6 +560,38 @@ __global__ void k_axpy(double *dst, const double *src, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// NCCL, bound at run time (see include/trekis3_gpu.h "Multi-GPU"): the handful of entry points the path needs
+// ------------------------------------------------------------------------------------------------
+namespace nccl_rt {
+typedef struct { char internal[TRK3_NCCL_UNIQUE_ID_BYTES]; } UniqueId;      // ncclUniqueId (nccl.h: 128 bytes)
+typedef void *Comm;
+enum { kSuccess = 0, kFloat64 = 8, kSum = 0 };                               // ncclSuccess, ncclDouble, ncclSum
+struct Api {
+    void *handle = nullptr;
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    int (*CommAbort)(Comm) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string err;
+};
+static Api &api() {
+    static Api a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) { a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (a.handle) break; }
+        if (!a.handle) { a.err = std::string("NCCL not found: ") + dlerror(); return; }
+#define SYM(field, name) a.field = (decltype(a.field))dlsym(a.handle, name); if (!a.field) { a.err = std::string("NCCL symbol missing: ") + name; return; }
+        SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(AllReduce, "ncclAllReduce")
+        SYM(CommDestroy, "ncclCommDestroy") SYM(CommAbort, "ncclCommAbort") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    });
+    return a;
+}
+}  // namespace nccl_rt
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 struct trk3_engine {
@@ -602,6 +635,7 @@ struct trk3_engine {
     size_t opt_queue_bytes_max = (size_t)64 << 30;       // of the 180 GB of a B200
     // per-batch resources
     uint32_t nb_alloc = 0;
+    std::vector<double> batch_sig;     // what the per-batch resources were sized for (batch_signature)
     QueueSet qs[2]{};
     QueueSet qs_x{};                   // output set of the cold kernels (small hot queues + the shared cold queues)
     uint32_t *d_qcount = nullptr;      // QC_* layout below: hot counts of both generations, cold counts, heads
@@ -618,6 +652,10 @@ struct trk3_engine {
     std::vector<std::pair<int, int>> ev_pending;   // (class, pool index)
     std::vector<std::pair<int, uint32_t>> ev_info; // (generation, records) of the same launches: option "profile" = 2 prints them
     int cur_gen = -1;
+    // multi-GPU: with a communicator attached every run ends with one all-reduce of the tally buffer
+    nccl_rt::Comm comm = nullptr; int comm_size = 1; bool own_comm = false;
+    double allreduce_ms = 0.0;
+    bool failed = false;               // a run ended with an error: device state undefined until trk3_mc_reset
     // results
     std::vector<double> iter_totE;
     std::vector<double> Dcoef;
@@ -761,6 +799,18 @@ double queue_bytes_per_iteration(const trk3_engine *eng) {
     return b;
 }
 
+// Everything the per-batch resources (queues, per-iteration scratch) are sized from, besides the batch size itself: a
+// reload of configuration + tables that changes any of it (electron emission switched on -> em_spec, photons switched on
+// -> photon queue, a longer time grid, larger cascades ...) must re-allocate them.
+std::vector<double> batch_signature(const trk3_engine *eng) {
+    double cap[N_QUEUES]; queue_caps(eng, cap);
+    std::vector<double> sig(cap, cap + N_QUEUES);
+    const ScratchLayout sl = scratch_layout(eng->hp, 1);
+    sig.push_back((double)sl.u32_total); sig.push_back((double)sl.f64_total); sig.push_back((double)sl.em_spec);
+    sig.push_back((double)eng->lay.Nt); sig.push_back((double)eng->hp.n_r); sig.push_back((double)eng->hp.n_dos);
+    return sig;
+}
+
 int ensure_batch(trk3_engine *eng, uint32_t nb) {
     if (nb <= eng->nb_alloc) return TRK3_OK;
     // release the previous batch resources
@@ -805,6 +855,7 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
     if ((rc = dev_alloc(eng, &eng->fa.emE, n))) return rc;
     bind_scratch(eng->hp, eng->sl, eng->d_u32, eng->d_f64);
     eng->nb_alloc = nb;
+    eng->batch_sig = batch_signature(eng);
     return TRK3_OK;
 }
 
@@ -1051,6 +1102,9 @@ int trk3_mc_reload_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_t
     if (rc) return rc;
     if (eng->lay.total != lay0.total || eng->lay.Nt != lay0.Nt) { eng->err = "tally layout differs from the one the engine was created with"; return TRK3_E_INVALID; }
     if (eng->nel_est > nel0) eng->nb_alloc = 0;          // larger cascades expected: re-size the queues at the next run
+    // the scratch layout and the queue capacities follow the configuration (work_function > 0 -> emission spectrum,
+    // include_photons -> photon queue): if the new inputs need other sizes, the next run re-allocates
+    if (eng->nb_alloc && batch_signature(eng) != eng->batch_sig) eng->nb_alloc = 0;
     if (eng->nb_alloc) bind_scratch(eng->hp, eng->sl, eng->d_u32, eng->d_f64);
     return TRK3_OK;
 }
@@ -1124,9 +1178,16 @@ int trk3_mc_download_tallies(trk3_engine *eng, double *dst) {
 // turns (handles on different devices, one per host thread, run concurrently).
 static std::mutex g_device_mutex[64];
 
+static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_stats *stats);
 int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_stats *stats) {
     if (!eng || it_end < it_begin || it_begin < 0 || it_end > 0xffffffffll) return TRK3_E_INVALID;
-    std::lock_guard<std::mutex> device_turn(g_device_mutex[eng->device & 63]);
+    if (eng->failed) { eng->err = "the previous run failed (" + eng->err + "): call trk3_mc_reset first"; return TRK3_E_INVALID; }
+    const int rc = run_device_impl(eng, it_begin, it_end, stats);
+    if (rc != TRK3_OK) eng->failed = true;          // queues / counters / tallies are in an undefined state now
+    return rc;
+}
+static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_stats *stats) {
+    std::lock_guard<std::mutex> device_turn(g_device_mutex[eng->device % 64]);
     CK(cudaSetDevice(eng->device));
     const int Nt = eng->lay.Nt;
     const int64_t n_it = it_end - it_begin;
@@ -1350,6 +1411,12 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
     k_axpy<<<1, 256, 0, eng->stream>>>(eng->d_tally + eng->lay.off[TRK3_OUT_DIFF_COEFF], eng->d_small, Nt);
     CK(cudaGetLastError());
     eng->launches++;
+    if (eng->comm && eng->comm_size > 1) {
+        // the single collective of the path (26 x MPI_Reduce in the reference, Monte_Carlo.f90:131-389): in place, on the
+        // engine's stream, right behind the folding kernels -- no host synchronisation in between
+        const int nrc = nccl_rt::api().AllReduce(eng->d_tally, eng->d_tally, (size_t)eng->lay.total, nccl_rt::kFloat64, nccl_rt::kSum, eng->comm, eng->stream);
+        if (nrc != nccl_rt::kSuccess) { eng->err = std::string("ncclAllReduce: ") + nccl_rt::api().GetErrorString(nrc); return TRK3_E_CUDA; }
+    }
     CK(cudaEventRecord(eng->ev1, eng->stream));
     std::vector<unsigned long long> h_c(n_counters);
     CK(cudaMemcpyAsync(h_c.data(), eng->d_counters, n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToHost, eng->stream));
@@ -1424,9 +1491,58 @@ int trk3_mc_kernel_times(trk3_engine *eng, double *ms, uint64_t *launches, int n
     return N_CLASSES;
 }
 
+int trk3_nccl_unique_id(void *id) {
+    if (!id) return TRK3_E_INVALID;
+    nccl_rt::Api &a = nccl_rt::api();
+    if (!a.err.empty()) return TRK3_E_UNSUPPORTED;
+    return a.GetUniqueId((nccl_rt::UniqueId *)id) == nccl_rt::kSuccess ? TRK3_OK : TRK3_E_CUDA;
+}
+int trk3_mc_comm_init(trk3_engine *eng, int nranks, int rank, const void *id) {
+    if (!eng || !id || nranks < 1 || rank < 0 || rank >= nranks) return TRK3_E_INVALID;
+    nccl_rt::Api &a = nccl_rt::api();
+    if (!a.err.empty()) { eng->err = a.err; return TRK3_E_UNSUPPORTED; }
+    CK(cudaSetDevice(eng->device));
+    if (eng->comm && eng->own_comm) a.CommDestroy(eng->comm);
+    eng->comm = nullptr; eng->own_comm = false; eng->comm_size = 1;
+    nccl_rt::UniqueId uid; std::memcpy(&uid, id, sizeof uid);
+    const int nrc = a.CommInitRank(&eng->comm, nranks, uid, rank);
+    if (nrc != nccl_rt::kSuccess) { eng->err = std::string("ncclCommInitRank: ") + a.GetErrorString(nrc); eng->comm = nullptr; return TRK3_E_CUDA; }
+    eng->own_comm = true; eng->comm_size = nranks;
+    return TRK3_OK;
+}
+int trk3_mc_set_comm(trk3_engine *eng, void *comm, int nranks) {
+    if (!eng || (comm && nranks < 1)) return TRK3_E_INVALID;
+    nccl_rt::Api &a = nccl_rt::api();
+    if (comm && !a.err.empty()) { eng->err = a.err; return TRK3_E_UNSUPPORTED; }
+    if (eng->comm && eng->own_comm) a.CommDestroy(eng->comm);
+    eng->comm = comm; eng->own_comm = false; eng->comm_size = comm ? nranks : 1;
+    return TRK3_OK;
+}
+int trk3_mc_comm_size(const trk3_engine *eng) { return eng ? eng->comm_size : 1; }
+
+int trk3_mc_reset(trk3_engine *eng) {
+    if (!eng) return TRK3_E_INVALID;
+    if (cudaSetDevice(eng->device) != cudaSuccess) { eng->err = "device lost"; return TRK3_E_CUDA; }
+    // wait for everything the failed run left in flight; a sticky error (illegal address ...) cannot be cleared
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess && cudaDeviceSynchronize() != cudaSuccess) { eng->err = std::string("device lost: ") + cudaGetErrorString(e); return TRK3_E_CUDA; }
+    const size_t n_counters = TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 6;
+    if (eng->d_counters) CK(cudaMemsetAsync(eng->d_counters, 0, n_counters * sizeof(unsigned long long), eng->stream));
+    if (eng->d_qcount) CK(cudaMemsetAsync(eng->d_qcount, 0, QC_TOTAL * sizeof(uint32_t), eng->stream));
+    if (eng->d_tally) CK(cudaMemsetAsync(eng->d_tally, 0, (size_t)eng->lay.total * sizeof(double), eng->stream));
+    if (eng->nb_alloc) { CK(cudaMemsetAsync(eng->d_u32, 0, eng->sl.u32_total * sizeof(uint32_t), eng->stream)); CK(cudaMemsetAsync(eng->d_f64, 0, eng->sl.f64_total * sizeof(double), eng->stream)); }
+    CK(cudaStreamSynchronize(eng->stream));
+    eng->ev_pending.clear(); eng->ev_info.clear();
+    eng->iter_totE.clear(); eng->Dcoef.clear();
+    eng->failed = false; eng->err.clear();
+    return TRK3_OK;
+}
+
 void trk3_mc_destroy(trk3_engine *eng) {
     if (!eng) return;
     cudaSetDevice(eng->device);
+    if (eng->comm && eng->own_comm) { if (eng->failed) nccl_rt::api().CommAbort(eng->comm); else nccl_rt::api().CommDestroy(eng->comm); }
     for (void *p : eng->allocs) cudaFree(p);
     if (eng->ev0) cudaEventDestroy(eng->ev0);
     if (eng->ev1) cudaEventDestroy(eng->ev1);

@@ -16,8 +16,11 @@
 //     OUTPUT_<ion>_in_<material>/OUTPUT_<ion>_<CDF|spCDF>_<Barkas|Bohr|ND|SG|fixed>_<P|BK>_{IMFP,dEdx,effective_charges,Range}.dat
 //         '(e)' E [MeV], per-shell values, total (:2657-2707); Range: two header lines + '(es,es,es)' E [eV], dE/dx, range (:2462-2506)
 //
-// Validity as in the reference (:307-327): a table file counts if it has as many rows as the energy grid.  The reference also
-// compares modification times with the .cdf file; callers that want that can touch the files.
+// Validity as in the reference (:307-327, 422-437, 540-555, 966-981, 2364-2372): a table file counts if it has as many rows
+// as the energy grid, is not older than the .cdf file it was computed from (get_file_stat, Last_mod_time_CDF), and no
+// redo_MFP / redo_IMFP / redo_EMFP / redo_MFP_SHI keyword asks for a recalculation.  The cache is read all-or-nothing here:
+// where the reference would recompute one table family, read_reference_cache declines and the caller rebuilds them all
+// (the tables are deterministic, so the untouched families come out as they were).
 #include <sys/stat.h>
 #include <algorithm>
 #include <cstdio>
@@ -33,6 +36,8 @@ std::string trim_s(const std::string &s) {
     return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
 }
 bool exists(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0; }
+// modification time [s]; -1 if the file cannot be examined
+double mtime_of(const std::string &p) { struct stat st; if (stat(p.c_str(), &st) != 0) return -1.0; return (double)st.st_mtim.tv_sec + 1.0e-9 * (double)st.st_mtim.tv_nsec; }
 bool make_dirs(const std::string &p) {
     std::string cur;
     for (size_t i = 0; i <= p.size(); ++i) {
@@ -263,6 +268,22 @@ bool read_reference_cache(Case &c, const std::string &out_root, const BuildOptio
     const std::string dm = out_root + "/" + n.dir_material, di = out_root + "/" + n.dir_ion, dd = out_root + "/" + n.dir_diff;
     const Grids g = make_grids(c);
     const size_t ns = (size_t)c.n_shells();
+    // ---- validity beyond existence and row count: recalculation keywords and the age of the files
+    if (c.numpar.redo_IMFP || c.numpar.redo_EMFP || c.numpar.redo_IMFP_SHI) {
+        err = std::string("recalculation requested by keyword (") + (c.numpar.redo_IMFP ? "redo_IMFP " : "") + (c.numpar.redo_EMFP ? "redo_EMFP " : "") +
+              (c.numpar.redo_IMFP_SHI ? "redo_MFP_SHI" : "") + ")";
+        return false;
+    }
+    {
+        const double t_cdf = mtime_of(c.dir + "/" + c.numpar.CDF_file);
+        std::vector<std::string> files = {dm + "/" + n.el_imfp, dm + "/" + n.hole_imfp, di + "/" + n.shi_stem + "_IMFP.dat"};
+        if (c.numpar.kind_of_EMFP == 0 || c.numpar.kind_of_EMFP == 1) { files.push_back(dm + "/" + n.el_emfp); files.push_back(dm + "/" + n.hole_emfp); }
+        if (c.numpar.include_photons) files.push_back(dm + "/" + n.photon_imfp);
+        for (const auto &f : files) {
+            const double t = mtime_of(f);
+            if (t >= 0.0 && t_cdf >= 0.0 && t < t_cdf) { err = "the CDF file was modified more recently than " + f; return false; }
+        }
+    }
     // ---- ion: read_SHI_MFP (Reading_files_and_parameters.f90:2855-2903); all four files must exist (:2357-2365)
     for (const char *sfx : {"_IMFP.dat", "_dEdx.dat", "_effective_charges.dat", "_Range.dat"})
         if (!exists(di + "/" + n.shi_stem + sfx)) { err = "missing " + di + "/" + n.shi_stem + sfx; return false; }

@@ -40,6 +40,11 @@ def _gpu():
         lib.trk3_mc_reload_tables.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Tables)]
         lib.trk3_mc_table_bytes.restype = C.c_uint64
         lib.trk3_mc_table_bytes.argtypes = [C.c_void_p]
+        lib.trk3_nccl_unique_id.argtypes = [C.c_void_p]
+        lib.trk3_mc_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.trk3_mc_set_comm.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib.trk3_mc_comm_size.argtypes = [C.c_void_p]
+        lib.trk3_mc_reset.argtypes = [C.c_void_p]
         lib.trk3_dcs_stats.argtypes = [PD, C.POINTER(C.c_int64), C.c_int]
         lib.trk3_gpu_version.restype = C.c_char_p
         _lib = lib
@@ -51,6 +56,18 @@ def dcs_stats(reset=False):
     ms, n = C.c_double(0.0), C.c_int64(0)
     _gpu().trk3_dcs_stats(C.byref(ms), C.byref(n), int(reset))
     return ms.value, n.value
+
+
+NCCL_UNIQUE_ID_BYTES = 128
+
+
+def nccl_unique_id():
+    """128-byte NCCL id (rank 0 creates it, every rank passes it to Engine.comm_init)."""
+    buf = C.create_string_buffer(NCCL_UNIQUE_ID_BYTES)
+    rc = _gpu().trk3_nccl_unique_id(buf)
+    if rc != 0:
+        raise RuntimeError(f"trk3_nccl_unique_id failed ({rc}): NCCL not available")
+    return buf.raw
 
 
 def gpu_library_loaded():
@@ -114,6 +131,34 @@ class Engine:
         self._check(_gpu().trk3_mc_run_device(self._h, int(it_begin), int(it_end), C.byref(st)), "trk3_mc_run_device")
         return st.as_dict()
 
+    def comm_init(self, nranks, rank, unique_id):
+        """Attach this engine to an NCCL communicator of `nranks` engines (one per GPU/process): from now on run() and
+        run_device() are collective and end with ONE all-reduce of the tally buffer, issued by the library on its own
+        stream (replaces the 26 MPI_Reduce of Monte_Carlo.f90:131-389)."""
+        buf = C.create_string_buffer(bytes(unique_id), NCCL_UNIQUE_ID_BYTES)
+        self._check(_gpu().trk3_mc_comm_init(self._h, int(nranks), int(rank), buf), "trk3_mc_comm_init")
+
+    def comm_init_torch(self, device=None):
+        """comm_init with the id distributed through an initialised torch.distributed process group (plumbing only)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        on_gpu = dist.get_backend() == "nccl"
+        t = torch.zeros(NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8).clone()
+        if on_gpu:
+            t = t.cuda(device)
+        dist.broadcast(t, src=0)
+        self.comm_init(world, rank, bytes(t.cpu().numpy().tobytes()))
+
+    def comm_size(self):
+        return int(_gpu().trk3_mc_comm_size(self._h))
+
+    def reset(self):
+        """Back to a defined state after a failed run (see trk3_mc_reset)."""
+        self._check(_gpu().trk3_mc_reset(self._h), "trk3_mc_reset")
+
     def set_stream(self, cuda_stream_handle):
         self._check(_gpu().trk3_mc_set_stream(self._h, C.c_void_p(int(cuda_stream_handle))), "set_stream")
 
@@ -169,7 +214,8 @@ def _shape_key(case, device):
     lay = case.layout()
     return (int(device), int(lay.total), int(lay.Nt), int(t.n_shells), int(t.n_ei), int(t.n_ee), int(t.n_hi), int(t.n_he),
             int(t.n_ph), int(t.n_shi), int(t.n_dos), int(t.n_r), int(t.eid_off[t.n_shells * t.n_ei]),
-            int(t.eed_off[t.n_ee]), int(t.hid_off[t.n_hi]), int(t.hed_off[t.n_he]), int(t.dshi_off[t.n_shells]))
+            int(t.eed_off[t.n_ee]), int(t.hid_off[t.n_hi]), int(t.hed_off[t.n_he]), int(t.dshi_off[t.n_shells]),
+            bool(case.config.work_function > 0), bool(case.config.include_photons))
 
 
 def release_handles():
@@ -179,17 +225,24 @@ def release_handles():
     _handles.clear()
 
 
-def do_Monte_Carlo(case, NMC=None, device=-1, seed=None, it_begin=0, persistent=True, **options):
+def do_Monte_Carlo(case, NMC=None, device=-1, seed=None, it_begin=0, persistent=True, comm=None, **options):
     """Replacement of `call do_Monte_Carlo(NMC, SHI, ...)` (Monte_Carlo.f90:39): returns the summed
     Out_* tallies (not yet divided by NMC, as in the reference) and the run statistics.
 
     Every call copies its inputs (configuration + tables) host->device and the tallies device->host.  With
     `persistent` (default) the engine handle -- device queues and scratch -- is kept between calls with the same table
-    shapes, as a plugin linked into the Fortran host would do; `persistent=False` creates and destroys an engine."""
+    shapes, as a plugin linked into the Fortran host would do; `persistent=False` creates and destroys an engine.
+
+    comm = (nranks, rank, nccl_unique_id) makes the call collective over `nranks` processes, one GPU each, every rank passing its
+    own share of the global iterations [it_begin, it_begin + NMC): the library sums the tallies of all ranks with one NCCL
+    all-reduce before they are copied back, and every rank returns the reduced arrays (the MPI build of the reference:
+    Monte_Carlo.f90:111-129 + :131-389).  The communicator is created once per persistent handle."""
     n = int(NMC if NMC is not None else case.get("NMC"))
     if not persistent:
         eng = Engine(case, device=device, seed=seed, **options)
         try:
+            if comm is not None:
+                eng.comm_init(*comm)
             return eng.run(it_begin, it_begin + n)
         finally:
             eng.close()
@@ -197,8 +250,12 @@ def do_Monte_Carlo(case, NMC=None, device=-1, seed=None, it_begin=0, persistent=
     eng = _handles.get(key)
     if eng is None:
         eng = _handles[key] = Engine(case, device=device, seed=seed)
+        if comm is not None:
+            eng.comm_init(*comm)
     else:
         eng.reload_tables(case, seed=seed)
+        if comm is not None and eng.comm_size() != comm[0]:
+            eng.comm_init(*comm)
     for k, v in options.items():
         eng.set_option(k, v)
     return eng.run(it_begin, it_begin + n)

@@ -29,10 +29,14 @@ def _stamp(verbose, text, t0):
 
 def prepare_tables(case, run_dir, evaluator="auto", threads=0, redo=False, write_cache=True, verbose=False, shi_window_only=False):
     """Tables of a loaded case: from the reference-format cache in run_dir if it is valid, else built (and cached).
-    Returns "cache" or "built:<evaluator>"."""
+    Returns "cache" or "built:<evaluator>".
+    Tables built with shi_window_only (a test shortcut: ion rows outside [0.5 E, E] are placeholders) never go into the
+    reference's cache directory, where a later run with another ion energy -- or the Fortran program itself -- would accept
+    them: they are cached under <run_dir>/TEST_ONLY_window_tables/ instead."""
+    cache_root = os.path.join(run_dir, "TEST_ONLY_window_tables") if shi_window_only else run_dir
     if not redo:
         try:
-            case.read_reference_cache(run_dir, threads=threads)
+            case.read_reference_cache(cache_root, threads=threads)
             return "cache"
         except RuntimeError as e:          # missing file / grid mismatch: the conditions under which the reference recomputes
             if verbose:
@@ -49,7 +53,8 @@ def prepare_tables(case, run_dir, evaluator="auto", threads=0, redo=False, write
             ev = None
     case.build_tables(threads=threads, verbose=verbose, evaluator=ev, shi_window_only=shi_window_only)
     if write_cache:
-        case.write_reference_cache(run_dir)
+        os.makedirs(cache_root, exist_ok=True)
+        case.write_reference_cache(cache_root)
     return "built:" + (ev or "host-direct")
 
 
@@ -83,7 +88,7 @@ def run(run_dir, nmc=None, evaluator="auto", threads=0, redo_tables=False, table
     if dist is not None:
         dist.barrier()
         if rank != 0:
-            info["tables"] = prepare_tables(case, run_dir, None, threads, False, False, False)
+            info["tables"] = prepare_tables(case, run_dir, None, threads, False, False, False, shi_window_only)
     _stamp(verbose, "Mean free paths and differential tables ready:", t0)
     info["t_tables_s"] = time.perf_counter() - t0
     if tables_only:
