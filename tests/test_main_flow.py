@@ -85,7 +85,7 @@ def test_monte_carlo_needs_the_gpu(tmp_path):
 @pytest.mark.gpu
 def test_whole_run_writes_the_reference_output_tree(tmp_path):
     d = tk.make_run_dir(str(tmp_path / "run"), "C1", nmc=20)
-    info = flow.run(d, verbose=False, shi_window_only=True)
+    info = flow.run(d, verbose=False)            # full tables (the ion over its whole grid), q-integrals on the GPU
     assert info["tables"] == "built:gpu" and tk.gpu_library_loaded()
     assert not info["stats"]["errors"] and info["stats"]["max_energy_drift"] < 1e-9
     od = info["out_dir"]

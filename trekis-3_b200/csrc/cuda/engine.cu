@@ -206,11 +206,11 @@ __device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned i
 struct PhiloxWarp {
     uint32_t o0, o1, o2, o3, base;
     bool valid;
-    __device__ double draw(const DevP &p, uint32_t iter, uint32_t k) {       // draw k of the ion's stream (id 0), see rn()
+    __device__ double draw(const DevP &p, uint32_t iter, uint32_t k, uint64_t id = 0ull) {       // draw k of stream `id` (the ion: 0), see rn()
         const uint32_t blk = k >> 1;
         if (!valid || blk - base >= 32u) {
             base = blk; valid = true;
-            philox4x32_10(0u, 0u, base + (threadIdx.x & 31), iter, p.seed_lo, p.seed_hi, o0, o1, o2, o3);
+            philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), base + (threadIdx.x & 31), iter, p.seed_lo, p.seed_hi, o0, o1, o2, o3);
         }
         const int src = (int)(blk - base);
         const uint32_t a = __shfl_sync(0xffffffffu, (k & 1u) ? o2 : o0, src), b = __shfl_sync(0xffffffffu, (k & 1u) ? o3 : o1, src);
@@ -273,6 +273,166 @@ __device__ inline void shi_step_warp(DevCtxT<false> &c, Rec &s, ShiEvent &ev, Ph
     s.ctr += 2;
     if (s.Z >= p.layer) s.tn = 1e16;
 }
+// ------------------------------------------------------------------------------------------------
+// One hot electron per warp (the classes whose quota is one history per warp: the long delta-electron lineages that are
+// the critical path of a batch, and every class of a late, small generation).  A lone history advances one collision per
+// ~12 us when a single lane follows it (3 500 dependent instructions, ~25 dependent table loads, 4-5 Philox evaluations);
+// here the 32 lanes of its warp share the collision, as in k_shi:
+//   * lane j keeps Philox block (base + j) of the electron's stream: one evaluation serves ~8 collisions;
+//   * evaluations of the SAME elementary function on independent arguments go through ONE call, one argument per lane:
+//     sincos(theta) | sincos(phi);  the shell MFPs of Which_shell and the Next_free_path_1d of every shell;
+//     log(E') | log(RN);  elastic MFP | total inelastic MFP of the new energy;  the two row interpolations of
+//     interpolate_transferred_energy;
+//   * the two inverse-CDF row searches of interpolate_transferred_energy (Find_in_monoton_array_decreasing: ~2 x 7
+//     dependent loads) become ONE pass: the lanes count the entries above the sampled value (the rows are stored back to
+//     back), which for a non-increasing row is exactly the index the reference's bisection ends on; rows that are not
+//     monotone (a handful per table, flagged at upload) take the bisection.
+// All lanes hold the same record and the same lookups; every value is computed by the same expressions as in physics.cuh.
+// ------------------------------------------------------------------------------------------------
+__device__ inline double transferred_energy_warp(const Csr &t, const uint8_t *mono, double Ele, double lE, int i_E, double L_need) {
+    const int lane = threadIdx.x & 31;
+    if (i_E > 1) { if (fabs(t.Eg[i_E - 2] - Ele) < 1.0e-6) i_E = i_E - 1; }
+    const double lLn = m_log(L_need);
+    const int64_t o = t.off[i_E - 1];
+    if (i_E <= 1) return sample_row(t, o, (int)(t.off[i_E] - o), L_need, lLn);
+    const int64_t o2 = t.off[i_E - 2];
+    const int n1 = (int)(t.off[i_E] - o), n2 = (int)(o - o2);
+    int i1, i2;
+    if (mono[i_E - 1] && mono[i_E - 2]) {
+        // entries above L_need in rows [o2, o) and [o, o + n1): clamp(count, 1, n) is where Find_in_monoton_array_decreasing ends
+        unsigned cnt = 0u;
+        const double *La = t.L + o2;
+        const int ntot = n1 + n2;
+        for (int j = lane; j < ntot; j += 32) { if (La[j] > L_need) cnt += (j < n2) ? 0x10000u : 1u; }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+        i1 = (int)(cnt & 0xffffu); i2 = (int)(cnt >> 16);
+        i1 = min(max(i1, 1), n1); i2 = min(max(i2, 1), n2);
+    } else find_dec2(t.L + o, n1, t.L + o2, n2, L_need, i1, i2);
+    // the two row interpolations in one call: lane 0 row i_E, lane 1 row i_E - 1
+    double lres = 0.0;
+    const double hw = (lane & 1) ? sample_row_at(t, o2, n2, i2, L_need, lLn, lres) : sample_row_at(t, o, n1, i1, L_need, lLn, lres);
+    const double hw_1 = __shfl_sync(0xffffffffu, hw, 0), hw_2 = __shfl_sync(0xffffffffu, hw, 1);
+    const double lhw_1 = __shfl_sync(0xffffffffu, lres, 0), lhw_2 = __shfl_sync(0xffffffffu, lres, 1);
+    i_E = i_E - 1;
+    if (hw_1 < 1.0e-10 || hw_2 < 1.0e-10) return interp1(t.Eg[i_E - 1], t.Eg[i_E], hw_1, hw_2, Ele);
+    return interp5t(t.Eg[i_E - 1], t.Eg[i_E], hw_1, hw_2, t.lEg[i_E - 1], t.lEg[i_E], lhw_1, lhw_2, Ele, lE);
+}
+// One collision of the electron `e` (Electron_Monte_Carlo, Monte_Carlo.f90:2253-2474; electron_event_head / _inel / _elast /
+// _tail of physics.cuh) shared by the lanes of a warp.  RN of the channel roulette has been drawn: `inel` is its outcome.
+template <class C>
+__device__ inline void electron_collision_warp(C &c, Rec &e, int iv, Cache &k, PhiloxWarp &pw, bool inel) {
+    const DevP &p = c.p;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const double Eel = e.E, t_ev = e.tn, L = e.L;
+    // head: the place of the collision (:2290-2296)
+    const SinCos sc = m_sincos(lane == 1 ? e.phi : e.theta);
+    const double st0 = __shfl_sync(FULL, sc.s, 0), ct0 = __shfl_sync(FULL, sc.c, 0), sp0 = __shfl_sync(FULL, sc.s, 1), cp0 = __shfl_sync(FULL, sc.c, 1);
+    const double X = e.X + L * st0 * sp0, Y = e.Y + L * st0 * cp0, Z = e.Z + L * ct0;
+    double dE, theta, phi;
+    if (inel) {                                                  // impact ionisation (electron_event_inel)
+        if (lane == 0) c.event(TRK3_EV_EL_INEL);
+        const Tab m = tab_ei_L(p);
+        const int NS = p.n_shells;
+        const int n = tab_find(m, Eel, k.lE);
+        // lanes 0..NS-1: shell MFP of Which_shell (:1786-1832); lanes NS..2NS-1: Next_free_path_1d of the same shells (:2312)
+        double val = 1.0e20, E1 = 1.0, E2 = 2.0, S1 = 1.0, S2 = 1.0, lE1 = 0.0, lE2 = 1.0, lS1 = 0.0, lS2 = 0.0;
+        bool need = false;
+        if (lane < 2 * NS) {
+            const int sh = (lane < NS) ? lane : lane - NS;
+            const double *La = m.L + (size_t)sh * m.N, *lLa = m.lL + (size_t)sh * m.N;
+            if (n > 1) {
+                const double a = La[n - 2], b = La[n - 1];
+                const bool flat = (lane < NS) ? (a == b || a > 1e20) : (a >= 1.0e16);
+                if (flat) val = a;
+                else { need = true; E1 = m.E[n - 2]; E2 = m.E[n - 1]; S1 = a; S2 = b; lE1 = m.lE[n - 2]; lE2 = m.lE[n - 1]; lS1 = lLa[n - 2]; lS2 = lLa[n - 1]; }
+            } else if (lane >= NS) val = nfp_at(tab_shell(m, sh), 1, false, Eel, k.lE);
+        }
+        if (need) val = interp5t(E1, E2, S1, S2, lE1, lE2, lS1, lS2, Eel, k.lE);
+        const double inv = 1.0 / val;
+        double MFP_tot = 0.0;
+        for (int q = 0; q < NS; ++q) MFP_tot = MFP_tot + __shfl_sync(FULL, inv, q);
+        const double RN2 = pw.draw(p, e.iter, e.ctr++, e.id);
+        MFP_tot = RN2 * MFP_tot;
+        double MFP_sum = 0.0;
+        int shell = NS - 1;
+        for (int q = 0; q < NS; ++q) { MFP_sum = MFP_sum + __shfl_sync(FULL, inv, q); if (MFP_sum >= MFP_tot) { shell = q; break; } }
+        IonEvent ev;
+        ev.pid = e.id; ev.ctr0 = e.ctr; ev.iter = e.iter;
+        e.ctr += 2;                                              // the two child ids
+        const double IMFP = __shfl_sync(FULL, val, NS + shell);
+        // Electron_energy_transfer_inelastic (inelastic_dE)
+        const double RN3 = pw.draw(p, e.iter, e.ctr++, e.id);
+        const double L_need = m_div(IMFP, RN3);
+        double Emin = p.shell_Ip[shell];
+        if (Emin <= 1.0e-3) Emin = 1.0e-3;
+        const double Emax = (Eel + Emin) / 2.0;
+        double E = transferred_energy_warp(csr_eid(p, shell), p.eid_mono + (size_t)shell * p.n_ei, Eel, k.lE, n, L_need);
+        if (E < Emin) E = Emin;
+        if (E > Emax) E = Emax;
+        if (trk_isnan(E)) E = Emin;
+        dE = E;
+        theta = m_acos((Eel - dE) / sqrt(Eel * (Eel - dE)));       // Update_electron_angles_El :1189
+        if (trk_isnan(theta)) { const double r2 = pw.draw(p, e.iter, e.ctr++, e.id); theta = r2 * TRK_PI; }
+        { const double r2 = pw.draw(p, e.iter, e.ctr++, e.id); phi = 2.0 * TRK_PI * r2; }
+        if (lane == 0) {
+            ev.dE = dE; ev.t = t_ev; ev.X = X; ev.Y = Y; ev.Z = Z; ev.theta0 = e.theta; ev.phi0 = e.phi; ev.theta = theta; ev.phi = phi; ev.shell = shell;
+            c.push_ion(ev);                                      // the pair: electron_ion_emit
+        }
+    } else {                                                     // elastic: energy to the lattice (electron_event_elast, LEAN: CDF scattering)
+        if (lane == 0) c.event(TRK3_EV_EL_ELAST);
+        const double EMFP = elastic_total(tab_ee(p), Eel, k);
+        const double RN = pw.draw(p, e.iter, e.ctr++, e.id);
+        const double L_need = m_div(EMFP, RN);
+        double hw = transferred_energy_warp(csr_eed(p), p.eed_mono, Eel, k.lE, k.n1, L_need);
+        if (hw >= Eel) hw = Eel;
+        dE = hw;
+        // cos_theta_from_W + Update_particle_angles_lat (angles_lattice, M_eff = 1)
+        const double Erest_in = rest_energy(1.0 * TRK_ME), Erest_t = rest_energy(p.Mtarget);
+        const double E2mc = Eel + 2.0 * Erest_in, EmW = Eel - dE;
+        const double W1 = Eel * E2mc - dE * (Eel + Erest_in + Erest_t);
+        const double W2 = Eel * E2mc * EmW * (E2mc - dE);
+        double mu = (W2 > 0.0) ? m_div(W1, m_sqrt(W2)) : 0.0;
+        if (fabs(mu) > 1.0) { const double RNm = pw.draw(p, e.iter, e.ctr++, e.id); mu = m_cos(TRK_PI * RNm); }
+        theta = m_acos(mu);
+        const double RN2 = pw.draw(p, e.iter, e.ctr++, e.id);
+        phi = 2.0 * TRK_PI * RN2;
+        if (lane == 0) {
+            if (trk_isnan(theta) || trk_isnan(phi)) c.error(TRK3_ERR_NAN);
+            deposit_lattice(c, e, iv, X, Y, dE);
+        }
+    }
+    // tail: lookups of the new energy, next free flight, new direction (:2449-2465)
+    const double En = Eel - dE;
+    const double RN4 = pw.draw(p, e.iter, e.ctr++, e.id);
+    const double lg = m_log(lane == 1 ? RN4 : En);
+    const double lEn = __shfl_sync(FULL, lg, 0), lRN4 = __shfl_sync(FULL, lg, 1);
+    {   // cache_electron(p, En, k): lane 0 the elastic MFP, lane 1 the total inelastic MFP, one call
+        const Tab el = tab_ee(p);
+        k.lE = lEn;
+        k.n1 = tab_find(el, En, lEn);
+        k.n2 = find_2d_from_1d(el.E, el.N, En, k.n1);
+        const bool cold = En < p.e_cold;
+        const Tab ti = tab_ei_tot(p);
+        int ni = 1;
+        if (!cold) ni = find_2d_from_1d(ti.E, ti.N, En, tab_find(ti, En, lEn));
+        double v = 0.0;
+        if (lane == 0 || (lane == 1 && !cold)) v = nfp_at(lane == 0 ? el : ti, lane == 0 ? k.n2 : ni, true, En, lEn);
+        k.emfp = __shfl_sync(FULL, v, 0);
+        k.iemfp = m_div(1.0, k.emfp);
+        if (cold) { k.imfp = p.e_imfp_cold; k.iimfp = p.e_iimfp_cold; }
+        else { k.imfp = __shfl_sync(FULL, v, 1); k.iimfp = m_div(1.0, k.imfp); }
+    }
+    const double MFP_tot = m_div(-lRN4, k.iimfp + k.iemfp);
+    double phi1, theta1;
+    new_angles_c(e.phi, e.theta, ct0, theta, phi, phi1, theta1);
+    e.E = En; e.t0 = t_ev; e.X = X; e.Y = Y; e.Z = Z; e.L = MFP_tot; e.theta = theta1; e.phi = phi1;
+    e.tn = next_time(e.t0, vel_electron(e.E), MFP_tot);
+    if (e.E < p.cut_off) e.tn = 1.0e20;
+    if (lane == 0 && (e.E < -1.0e-9 || trk_isnan(e.E))) c.error(TRK3_ERR_22);
+}
+
 __global__ void __launch_bounds__(32 * SHI_WARPS) k_shi(Queue stage, QueueSet qout, int lanes) {
     __shared__ unsigned int s_cnt[S_NCNT];
     block_prologue(nullptr, s_cnt, 0);
@@ -370,10 +530,14 @@ __global__ void __launch_bounds__(256) k_snapshot(Queue sq, QueueSet qout, int u
 
 // k_wave<SP, COLD>: records [first, n_in) of queue qin, histories followed with lane refill until they end or
 // have to change queue (hot -> cold when the particle can no longer ionise, core hole -> valence hole, ...).
+// The number of records is read from the queue's device counter: the host enqueues the launches of a generation without
+// knowing how many records the previous one produced (no host round trip per generation); blocks without work leave at once.
 template <int SP, bool COLD, bool LEAN>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t n_in, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int warm) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int warm) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
+    const uint32_t n_in = min(*qin.count, qin.cap);       // records [first, n_in)
+    if (first + blockIdx.x * blockDim.x >= n_in) return;          // nothing left for this block (uniform per block, before any barrier)
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
     block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? (LEAN ? c_p.s_len[TRK3_OUT_ELAT] : c_p.s_total) : 0);
     DevCtxT<LEAN> c{c_p, qout, s_tally, s_cnt, c_p.defer_snap};
@@ -442,32 +606,70 @@ template <int SP> __device__ inline bool hot_leaves(const Rec &r) { return SP ==
 // records left.
 struct HotIn {
     Queue q[N_ECLASS];
-    uint32_t n[N_ECLASS];
     uint32_t *head[N_ECLASS];
-    int quota[N_ECLASS];
+    int qmax[N_ECLASS];            // most histories of class c a warp follows at once
     int slice[N_ECLASS];           // collisions after which a history of class c goes back to the queue (promoted by one class)
-    uint32_t wend[N_ECLASS];       // warps [wend[c+1], wend[c]) start on class c (wend[ncls] = 0)
-    int ncls;
+    int ncls, spread, quota_min;
 };
+// What the launch works with, derived ON THE DEVICE from the queue counters (the host does not know them when it enqueues
+// the launch): records per class, histories per warp, and the warps that start on each class.
+struct HotPlan {
+    uint32_t n[N_ECLASS];
+    int quota[N_ECLASS];
+    uint32_t wend[N_ECLASS];       // warps [wend[c+1], wend[c]) start on class c (wend[ncls] = 0); warps >= wend[0] have nothing to do
+};
+// warps per class.  Least: n / (the class's largest quota).  If that fills the GPU, the warps are shared out in proportion
+// (quota = largest).  Otherwise the spare warps go to the classes from the top down, until every history of a class has a
+// warp of its own: a small generation spreads over all warps, the long histories first.  W = warps of the grid.
+__device__ inline void hot_plan(const HotIn &in, uint32_t W, HotPlan &pl) {
+    uint32_t need[N_ECLASS], w[N_ECLASS], total_need = 0;
+    for (int c = 0; c < N_ECLASS; ++c) { pl.n[c] = 0; pl.quota[c] = 1; pl.wend[c] = 0; need[c] = 0; w[c] = 0; }
+    for (int c = 0; c < in.ncls; ++c) {
+        pl.n[c] = min(*in.q[c].count, in.q[c].cap);
+        const uint32_t qmax = (uint32_t)in.qmax[c];
+        need[c] = (pl.n[c] + qmax - 1) / qmax; total_need += need[c];
+        pl.quota[c] = (int)qmax;
+    }
+    if (total_need >= W || !in.spread) {
+        for (int c = 0; c < in.ncls; ++c) w[c] = need[c] ? max(1u, (uint32_t)((unsigned long long)need[c] * W / max(total_need, 1u))) : 0u;
+        if (total_need < W) for (int c = 0; c < in.ncls; ++c) w[c] = need[c];
+    } else {
+        uint32_t spare = W - total_need;
+        for (int c = in.ncls - 1; c >= 0; --c) {
+            const uint32_t extra = min(spare, pl.n[c] - need[c]);
+            w[c] = need[c] + extra; spare -= extra;
+            if (w[c]) pl.quota[c] = (int)max((pl.n[c] + w[c] - 1) / w[c], (uint32_t)in.quota_min);
+        }
+    }
+    uint32_t wsum = 0;
+    for (int c = in.ncls - 1; c >= 0; --c) { wsum += w[c]; pl.wend[c] = wsum; }
+}
 
 template <int SP, bool LEAN>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn in, QueueSet qout, int use_smem, int refill_min) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn in, QueueSet qout, int use_smem, int refill_min, int coop) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
+    __shared__ HotPlan pl;
+    if (threadIdx.x == 0) hot_plan(in, gridDim.x * (blockDim.x >> 5), pl);
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
     block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? (LEAN ? c_p.s_len[TRK3_OUT_ELAT] : c_p.s_total) : 0);
+    if (blockIdx.x * (blockDim.x >> 5) >= pl.wend[0]) return;          // no warp of this block has work (uniform per block)
     DevCtxT<LEAN> c{c_p, qout, s_tally, s_cnt, c_p.defer_snap};
     const int lane = threadIdx.x & 31;
-    bool active = false, exhausted = false, have_rn = false;
+    bool active = false, have_rn = false;
     Rec r;
     Cache k{};
     double RN = 0.0;
     int ig = 0, nev = 0, my_slice = 0, my_next = 0;
     const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    bool exhausted = gw >= pl.wend[0];       // a warp beyond the planned ones: nothing to do (it still joins the block's epilogue)
     int cls = 0;
     unsigned exh = 0u;              // classes whose queue is used up (warp-uniform)
-    for (int q = in.ncls - 1; q >= 0; --q) { if (in.n[q] == 0u) exh |= 1u << q; }
-    for (int q = in.ncls - 1; q > 0; --q) { if (gw < in.wend[q]) { cls = q; break; } }
+    for (int q = in.ncls - 1; q >= 0; --q) { if (pl.n[q] == 0u) exh |= 1u << q; }
+    for (int q = in.ncls - 1; q > 0; --q) { if (gw < pl.wend[q]) { cls = q; break; } }
+    // classes whose quota is ONE history per warp are followed by the whole warp (electron_collision_warp)
+    const bool coop_ok = LEAN && SP == SP_ELECTRON && coop && 2 * c_p.n_shells <= 32;
+    PhiloxWarp pw; pw.valid = false; pw.base = 0u;
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
         if (!exhausted && ((exh >> cls) & 1u)) {
@@ -475,10 +677,32 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn
             while (q >= 0 && ((exh >> q) & 1u)) --q;
             if (q < 0) exhausted = true; else cls = q;
         }
-        const int quota = in.quota[cls];
+        if (coop_ok && !exhausted && pl.quota[cls] == 1 && idle == 0xffffffffu) {
+            // one record of class `cls`, all lanes hold it
+            uint32_t my = 0;
+            if (lane == 0) my = atomicAdd(in.head[cls], 1u);
+            my = __shfl_sync(0xffffffffu, my, 0);
+            if (my >= pl.n[cls]) { exh |= 1u << cls; continue; }
+            load_rec(in.q[cls], my, r);
+            begin_electron(c_p, r, ig, k);
+            pw.valid = false;
+            const int slice_c = in.slice[cls], next_c = min(cls + 1, in.ncls - 1);
+            for (int n_coll = 0;;) {
+                while (ig <= c_p.Nt && c_p.tg[ig - 1] <= r.tn) { if (lane == 0) c.snap(SP, r, ig); ++ig; }
+                if (ig > c_p.Nt) break;
+                event_begin(r);
+                const double RN1 = pw.draw(c_p, r.iter, r.ctr++, r.id);
+                electron_collision_warp(c, r, ig, k, pw, electron_roulette_inelastic(k, RN1));
+                ++n_coll;
+                if (electron_leaves_hot(c_p, r)) { if (lane == 0) c.push(SP, r); break; }
+                if (n_coll >= slice_c && r.tn < c_p.Tim) { r.shell = -1 - next_c; if (lane == 0) c.push_hot(SP, r); break; }
+            }
+            continue;
+        }
+        const int quota = pl.quota[cls];
         const int room = quota - (32 - __popc(idle));
         if (room > 0 && !exhausted && (room >= min(refill_min, quota) || idle == 0xffffffffu)) {
-            const uint32_t n_in = in.n[cls];
+            const uint32_t n_in = pl.n[cls];
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(in.head[cls], (uint32_t)room);
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -613,11 +837,14 @@ struct trk3_engine {
     uint64_t h2d_bytes = 0;                 // bytes of the last table binding
     double nel_est = 1000.0;
     // options
-    uint32_t *h_qcount = nullptr;       // pinned mirror of d_qcount
+    uint32_t *h_qcount = nullptr;       // pinned ring of counter snapshots (run-ahead generation loop)
+    std::vector<cudaEvent_t> ring_ev;   // one event per ring slot
+    int opt_coop = 1;                   // hot electrons that have a warp of their own: the lanes share the collision
+    int opt_run_ahead = 1;              // generations the host may enqueue beyond the last counter snapshot it has seen
     int opt_batch = 4096, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
-    int opt_hot_slice = 64, opt_overlap = 0, opt_cold_min = 16384;
+    int opt_hot_slice = 64;
     int opt_shi_lanes = 0;                 // 0: one ion per warp, the lanes share the work of a collision (k_shi)
-    int opt_cold_smem_kb = 0, opt_hot_block = 0;      // see the `overlap` schedule in trk3_mc_run_device
+    int opt_hot_block = 0;
     // energy classes of the hot electrons: lower edges [eV] of classes 1..3 and the most histories a warp follows at once
     double opt_warm_pinel = 0.5;           // electrons are "warm" below the energy where the ionisation probability per collision reaches this (0: off)
     int opt_warm_slice = 64;
@@ -679,9 +906,21 @@ struct trk3_engine {
 #define QC_VBW(b) (4 * N_SPECIES + 10 + 3 * (N_ECLASS - 1) + (b))  // warm valence holes of generation set b
 #define QC_HEADWH (4 * N_SPECIES + 12 + 3 * (N_ECLASS - 1))
 #define QC_TOTAL (4 * N_SPECIES + 13 + 3 * (N_ECLASS - 1))
-// the counters of the generation set that is about to be filled and all queue heads of a hot generation: one launch instead of eight memsets
-__global__ void k_gen_reset(uint32_t *qc, int nxt) {
+#define QC_OVERFLOW QC_TOTAL                                         // sticky flag: some queue of a generation ran over its capacity
+#define QC_WORDS (QC_TOTAL + 1)
+// capacities of the per-generation queues, in the order the overflow check of k_gen_reset reads them
+struct GenCaps { uint32_t hot[N_SPECIES], cls[N_ECLASS - 1], warm_e, warm_h; };
+// Start of a generation (input set `cur`, output set `nxt`): the fill of the input set is final now -> a counter beyond its
+// queue's capacity raises the sticky overflow flag (the host looks at it when it next reads the counters; records beyond
+// the capacity were dropped, the batch is then rolled back and re-run with larger queues).  Then the counters of the set
+// that is about to be filled and all queue heads are cleared: one launch instead of eight memsets.
+__global__ void k_gen_reset(uint32_t *qc, int cur, int nxt, GenCaps caps) {
     const int t = threadIdx.x;
+    bool over = false;
+    if (t < N_SPECIES) over |= qc[QC_HOT(cur) + t] > caps.hot[t];
+    if (t < N_ECLASS - 1) over |= qc[QC_ELC(cur) + t] > caps.cls[t];
+    if (t == 0) over |= qc[QC_ELW(cur)] > caps.warm_e || qc[QC_VBW(cur)] > caps.warm_h;
+    if (over) qc[QC_OVERFLOW] = 1u;
     if (t < N_SPECIES) { qc[QC_HOT(nxt) + t] = 0; qc[QC_HEAD + t] = 0; }
     if (t < N_ECLASS - 1) { qc[QC_ELC(nxt) + t] = 0; qc[QC_HEADC + t] = 0; }
     if (t == 0) { qc[QC_ELW(nxt)] = 0; qc[QC_HEADW] = 0; qc[QC_VBW(nxt)] = 0; qc[QC_HEADWH] = 0; }
@@ -863,35 +1102,35 @@ int ensure_batch(trk3_engine *eng, uint32_t nb) {
 inline bool engine_is_lean(const trk3_engine *eng) {
     return eng->opt_lean && eng->cfg.kind_of_EMFP == 1 && !(eng->cfg.work_function > 0.0) && eng->opt_defer_snap;
 }
+// Grids are persistent-style and sized for the device, not for the work: the number of records is only known on the device
+// (queue counters) when the host enqueues the launch; blocks without work leave at once.
 template <int SP, bool COLD>
-int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t first, uint32_t n_in, uint32_t *head, const QueueSet &qout, cudaStream_t st = nullptr, size_t smem_floor = 0, int warm = 0) {
-    const uint32_t n = n_in - first;
+int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t *head, const QueueSet &qout, cudaStream_t st = nullptr, int warm = 0, uint32_t n_hint = 0, uint32_t first = 0) {
     if (!st) st = eng->stream;
     const bool lean = engine_is_lean(eng);
     size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)(lean ? eng->hp.s_len[TRK3_OUT_ELAT] : eng->hp.s_total) * sizeof(double) : 8;
     int use_smem = eng->opt_use_smem;
     const size_t smem_max = (size_t)eng->smem_optin - 1024;             // static shared memory + driver reserve
     if (smem > smem_max) { smem = 8; use_smem = 0; }                    // too many output times for shared memory: global atomics
-    if (smem < smem_floor && smem_floor <= smem_max) smem = smem_floor; // occupancy limiter: leaves room on every SM for the blocks of another kernel
     auto kern = lean ? k_wave<SP, COLD, true> : k_wave<SP, COLD, false>;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = eng->opt_blocks_per_sm;
     const int block = eng->opt_block;
     if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, block, smem)); if (bps < 1) bps = 1; }
-    // persistent-style grid: a multiple of the SM count, never more blocks than there is work for
-    uint32_t want = (n + block - 1) / block;
+    // one resident wave of blocks, never more than the queue could hold records for
+    const uint32_t want = (qin.cap + block - 1) / block;
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (grid < 1) grid = 1;
-    const int pi = prof_begin(eng, warm ? N_SPECIES + 4 + SP : (COLD ? N_SPECIES + 2 + SP : SP), st, n);
-    kern<<<grid, block, smem, st>>>(qin, first, n_in, head, qout, use_smem, eng->opt_refill_min, warm ? eng->opt_warm_slice : eng->opt_hot_slice, warm);
+    const int pi = prof_begin(eng, warm ? N_SPECIES + 4 + SP : (COLD ? N_SPECIES + 2 + SP : SP), st, n_hint);
+    kern<<<grid, block, smem, st>>>(qin, first, head, qout, use_smem, eng->opt_refill_min, warm ? eng->opt_warm_slice : eng->opt_hot_slice, warm);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
     return TRK3_OK;
 }
-// One generation of hot carriers of species SP: `nq` class queues (valence holes: 1), see HotIn.
+// One generation of hot carriers of species SP: `ncls` class queues (valence holes: 1), see HotIn / hot_plan.
 template <int SP>
-int launch_hot(trk3_engine *eng, const Queue *const *qin, const uint32_t *n_in, uint32_t *const *head, int ncls, const QueueSet &qout, cudaStream_t st = nullptr) {
+int launch_hot(trk3_engine *eng, const Queue *const *qin, uint32_t *const *head, int ncls, const QueueSet &qout, cudaStream_t st = nullptr, uint32_t n_hint = 0) {
     if (!st) st = eng->stream;
     const bool lean = engine_is_lean(eng);
     size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)(lean ? eng->hp.s_len[TRK3_OUT_ELAT] : eng->hp.s_total) * sizeof(double) : 8;
@@ -903,62 +1142,36 @@ int launch_hot(trk3_engine *eng, const Queue *const *qin, const uint32_t *n_in, 
     int bps = eng->opt_blocks_per_sm;
     const int block = eng->opt_hot_block ? eng->opt_hot_block : eng->opt_block;
     if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, block, smem)); if (bps < 1) bps = 1; }
-    const uint32_t wpb = (uint32_t)block / 32u, W = (uint32_t)(eng->n_sm * bps) * wpb;       // warps the GPU holds at once
     HotIn in{};
-    in.ncls = ncls;
-    // warps per class.  Least: n / (the class's largest quota).  If that fills the GPU, the warps are shared out in
-    // proportion (quota = largest).  Otherwise the spare warps go to the classes from the top down, until every history of
-    // a class has a warp of its own: a small generation spreads over all warps, the long histories first.
-    uint32_t need[N_ECLASS] = {0}, w[N_ECLASS] = {0}, total_need = 0, n_tot = 0;
+    in.ncls = ncls; in.spread = eng->opt_spread; in.quota_min = eng->opt_quota_min;
     for (int c = 0; c < ncls; ++c) {
-        in.q[c] = *qin[c]; in.n[c] = n_in[c]; in.head[c] = head[c];
-        const uint32_t qmax = (uint32_t)(ncls > 1 ? eng->opt_class_quota[c] : 32);
-        need[c] = (n_in[c] + qmax - 1) / qmax; total_need += need[c]; n_tot += n_in[c];
-        in.quota[c] = (int)qmax;
+        in.q[c] = *qin[c]; in.head[c] = head[c];
+        in.qmax[c] = (ncls > 1) ? eng->opt_class_quota[c] : 32;
         in.slice[c] = (ncls > 1) ? eng->opt_class_slice[c] : eng->opt_hot_slice;
     }
-    if (total_need >= W || !eng->opt_spread) {
-        for (int c = 0; c < ncls; ++c) w[c] = need[c] ? std::max<uint32_t>(1u, (uint32_t)((uint64_t)need[c] * W / std::max(total_need, 1u))) : 0u;
-        if (total_need < W) for (int c = 0; c < ncls; ++c) w[c] = need[c];
-    } else {
-        uint32_t spare = W - total_need;
-        for (int c = ncls - 1; c >= 0; --c) {
-            const uint32_t extra = std::min(spare, n_in[c] - need[c]);
-            w[c] = need[c] + extra; spare -= extra;
-            if (w[c]) in.quota[c] = (int)std::max<uint32_t>((n_in[c] + w[c] - 1) / w[c], (uint32_t)eng->opt_quota_min);
-        }
-    }
-    uint32_t wsum = 0;
-    for (int c = ncls - 1; c >= 0; --c) { wsum += w[c]; in.wend[c] = wsum; }
-    uint32_t grid = std::min<uint32_t>((wsum + wpb - 1) / wpb, (uint32_t)(eng->n_sm * bps));
-    if (grid < 1) grid = 1;
-    if (eng->opt_profile >= 2) {
-        fprintf(stderr, "hot<%d> gen %d grid %u W %u:", SP, eng->cur_gen, grid, W);
-        for (int c = 0; c < ncls; ++c) fprintf(stderr, "  c%d n %u w %u q %d", c, in.n[c], w[c], in.quota[c]);
-        fprintf(stderr, "\n");
-    }
-    const int pi = prof_begin(eng, SP, st, n_tot);
-    kern<<<grid, block, smem, st>>>(in, qout, use_smem, eng->opt_refill_min);
+    const uint32_t grid = (uint32_t)(eng->n_sm * bps);               // the warps the GPU holds at once: hot_plan shares them out
+    const int pi = prof_begin(eng, SP, st, n_hint);
+    kern<<<grid, block, smem, st>>>(in, qout, use_smem, eng->opt_refill_min, eng->opt_coop);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
     return TRK3_OK;
 }
-// the hot electrons of generation set `b`: all energy classes in one launch
-int launch_hot_electrons(trk3_engine *eng, const QueueSet &qs, const uint32_t *cnt, const uint32_t *cnt_cls, const QueueSet &qout) {
-    const Queue *q[N_ECLASS]; uint32_t n[N_ECLASS]; uint32_t *head[N_ECLASS];
+// the hot electrons of generation set `qs`: all energy classes in one launch
+int launch_hot_electrons(trk3_engine *eng, const QueueSet &qs, const QueueSet &qout, uint32_t n_hint = 0) {
+    const Queue *q[N_ECLASS]; uint32_t *head[N_ECLASS];
     uint32_t *heads = eng->d_qcount + QC_HEAD, *headc = eng->d_qcount + QC_HEADC;
-    q[0] = &qs.q[SP_ELECTRON]; n[0] = cnt[SP_ELECTRON]; head[0] = heads + SP_ELECTRON;
+    q[0] = &qs.q[SP_ELECTRON]; head[0] = heads + SP_ELECTRON;
     int ncls = 1;
     for (int c = 1; c < N_ECLASS; ++c) {
-        q[c] = &qs.q[Q_ELC + c - 1]; n[c] = cnt_cls ? cnt_cls[c - 1] : 0u; head[c] = headc + (c - 1);
-        if (q[c]->cap) ncls = c + 1; else n[c] = 0u;
+        q[c] = &qs.q[Q_ELC + c - 1]; head[c] = headc + (c - 1);
+        if (q[c]->cap) ncls = c + 1; else break;
     }
-    return launch_hot<SP_ELECTRON>(eng, q, n, head, ncls, qout);
+    return launch_hot<SP_ELECTRON>(eng, q, head, ncls, qout, nullptr, n_hint);
 }
-int launch_hot_vbholes(trk3_engine *eng, const Queue &qin, uint32_t n_in, const QueueSet &qout, cudaStream_t st = nullptr) {
-    const Queue *q[1] = {&qin}; uint32_t n[1] = {n_in}; uint32_t *head[1] = {eng->d_qcount + QC_HEAD + SP_VBHOLE};
-    return launch_hot<SP_VBHOLE>(eng, q, n, head, 1, qout, st);
+int launch_hot_vbholes(trk3_engine *eng, const Queue &qin, const QueueSet &qout, cudaStream_t st = nullptr, uint32_t n_hint = 0) {
+    const Queue *q[1] = {&qin}; uint32_t *head[1] = {eng->d_qcount + QC_HEAD + SP_VBHOLE};
+    return launch_hot<SP_VBHOLE>(eng, q, head, 1, qout, st, n_hint);
 }
 // Flattened tables -> device (first call allocates, later calls re-use the arrays): the inputs of do_Monte_Carlo.
 int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab) {
@@ -986,6 +1199,17 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
     UP(eed_off, tab->eed_off, tab->n_ee + 1); UP(eed_hw, tab->eed_hw, tab->eed_off[tab->n_ee]); UP(eed_L, tab->eed_L, tab->eed_off[tab->n_ee]);
     UP(hid_off, tab->hid_off, tab->n_hi + 1); UP(hid_hw, tab->hid_hw, tab->hid_off[tab->n_hi]); UP(hid_L, tab->hid_L, tab->hid_off[tab->n_hi]);
     UP(hed_off, tab->hed_off, tab->n_he + 1); UP(hed_hw, tab->hed_hw, tab->hed_off[tab->n_he]); UP(hed_L, tab->hed_L, tab->hed_off[tab->n_he]);
+    {   // rows of the electron differential tables that are non-increasing (see DevP::eid_mono)
+        auto mono_flags = [](const int64_t *off, const double *L, size_t nrows) {
+            std::vector<uint8_t> f(nrows, 1);
+            for (size_t r = 0; r < nrows; ++r)
+                for (int64_t j = off[r]; j + 1 < off[r + 1]; ++j) if (!(L[j + 1] <= L[j])) { f[r] = 0; break; }
+            return f;
+        };
+        const std::vector<uint8_t> fe = mono_flags(tab->eid_off, tab->eid_L, n_eid), fl = mono_flags(tab->eed_off, tab->eed_L, (size_t)tab->n_ee);
+        UP(eid_mono, fe.data(), fe.size()); UP(eed_mono, fl.data(), fl.size());
+        CK(cudaStreamSynchronize(eng->stream));          // the vectors go out of scope
+    }
     UP(dos_E, tab->dos_E, tab->n_dos); UP(dos_DOS, tab->dos_DOS, tab->n_dos); UP(dos_int, tab->dos_int, tab->n_dos); UP(dos_effm, tab->dos_effm, tab->n_dos);
     UP(out_R, tab->out_R, tab->n_r); UP(out_V, tab->out_V, tab->n_r);
 #undef UP
@@ -1083,7 +1307,7 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
     if ((rc = dev_alloc(eng, &eng->d_small, (size_t)TRK3_MAX_NT))) return rc;
     if ((rc = dev_alloc(eng, &eng->d_counters, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 6)))) return rc;
     if ((rc = dev_alloc(eng, &eng->d_counters_bak, (size_t)(TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 6)))) return rc;
-    if ((rc = dev_alloc(eng, &eng->d_qcount, (size_t)QC_TOTAL))) return rc;
+    if ((rc = dev_alloc(eng, &eng->d_qcount, (size_t)QC_WORDS))) return rc;
 
     p.tally = eng->d_tally;
     p.events = eng->d_counters; p.errors = eng->d_counters + TRK3_N_EVENT_CLASSES;
@@ -1126,8 +1350,8 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "species_streams") eng->opt_species_streams = (v != 0.0);
     else if (k == "spread") eng->opt_spread = (v != 0.0);
     else if (k == "quota_min") eng->opt_quota_min = std::min(32, std::max(1, (int)v));
-    else if (k == "overlap") eng->opt_overlap = (v != 0.0);
-    else if (k == "cold_min") eng->opt_cold_min = std::max(1, (int)v);
+    else if (k == "coop") eng->opt_coop = (v != 0.0);
+    else if (k == "run_ahead") eng->opt_run_ahead = std::min(6, std::max(0, (int)v));
     else if (k == "warm_pinel") { eng->opt_warm_pinel = std::min(0.99, std::max(0.0, v)); eng->nb_alloc = 0; eng->e_warm_auto = -1.0; eng->h_warm_auto = -1.0; }
     else if (k == "warm_holes") eng->opt_warm_holes = (v != 0.0);
     else if (k == "warm_slice") eng->opt_warm_slice = std::max(1, (int)v);
@@ -1144,7 +1368,6 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "class_q1") eng->opt_class_quota[1] = std::min(32, std::max(1, (int)v));
     else if (k == "class_q2") eng->opt_class_quota[2] = std::min(32, std::max(1, (int)v));
     else if (k == "class_q3") eng->opt_class_quota[3] = std::min(32, std::max(1, (int)v));
-    else if (k == "cold_smem_kb") eng->opt_cold_smem_kb = std::max(0, (int)v);
     else if (k == "hot_block") eng->opt_hot_block = std::min(TRK_BLOCK_MAX, std::max(0, ((int)v / 32) * 32));
     else if (k == "max_generations") eng->opt_max_generations = std::max(1, (int)v);
     else if (k == "profile") { eng->opt_profile = (int)v; for (auto &x : eng->class_ms) x = 0; for (auto &x : eng->class_launches) x = 0; }
@@ -1228,7 +1451,7 @@ static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, t
         CK(cudaMemcpyToSymbolAsync(c_p, &eng->hp, sizeof(DevP), 0, cudaMemcpyHostToDevice, eng->stream));
         CK(cudaMemsetAsync(eng->d_u32, 0, eng->sl.u32_total * sizeof(uint32_t), eng->stream));
         CK(cudaMemsetAsync(eng->d_f64, 0, eng->sl.f64_total * sizeof(double), eng->stream));
-        CK(cudaMemsetAsync(eng->d_qcount, 0, QC_TOTAL * sizeof(uint32_t), eng->stream));
+        CK(cudaMemsetAsync(eng->d_qcount, 0, QC_WORDS * sizeof(uint32_t), eng->stream));
         { const int pi = prof_begin(eng, N_SPECIES);
           // collisions are staged in the (still unused) electron queue of the other generation
           const Queue &stage = eng->qs[1].q[SP_ELECTRON];
@@ -1239,130 +1462,187 @@ static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, t
           prof_end(eng, pi); }
         CK(cudaGetLastError());
         eng->launches += 2;
-        int cur = 0;
         bool overflow = false;
-        uint32_t cold_done[2] = {0, 0};
-        cudaStream_t sc = eng->opt_overlap ? eng->stream_c : eng->stream;       // stream of the cold kernels
-        if (eng->opt_overlap) { CK(cudaEventRecord(eng->ev_fork, eng->stream)); CK(cudaStreamWaitEvent(sc, eng->ev_fork, 0)); }
-        for (int gen = 0; gen < eng->opt_max_generations; ++gen) {
-            eng->cur_gen = gen;
-            // hot counts of both generations, cold counts, set X, ionisation queue, ..., class queues -- read into pinned memory
-            // (a pageable destination goes through a staging copy: ~15 us more per generation)
-            if (!eng->h_qcount) CK(cudaHostAlloc((void **)&eng->h_qcount, QC_TOTAL * sizeof(uint32_t), cudaHostAllocDefault));
-            uint32_t *h_cnt = eng->h_qcount;
-            CK(cudaMemcpyAsync(h_cnt, eng->d_qcount, QC_TOTAL * sizeof(uint32_t), cudaMemcpyDeviceToHost, eng->stream));
-            CK(cudaStreamSynchronize(eng->stream));
-            uint32_t *hot = h_cnt + QC_HOT(cur), *cold = h_cnt + QC_COLD, *hotc = h_cnt + QC_ELC(cur);
+        // ---- the hot cascade, generation by generation, WITHOUT the host in the loop.  Every kernel of a generation reads the
+        // number of its records from the device counters, so the host enqueues generation after generation and only LOOKS at
+        // the counters: after each generation an asynchronous copy lands in a pinned ring slot, the host examines the slots
+        // that have arrived (never blocking unless it is `run_ahead` generations ahead of what it has seen) and stops
+        // enqueuing when a slot shows an empty input set.  At most `run_ahead` + 1 empty generations are launched (a few tens
+        // of microseconds of empty kernels) in exchange for ~12 host round trips per batch.
+        const int depth = (eng->opt_profile >= 2) ? 0 : std::max(0, eng->opt_run_ahead);     // profile 2 prints the records per launch: synchronous
+        const int R = depth + 2;
+        if ((int)eng->ring_ev.size() < R || !eng->h_qcount) {
+            if (eng->h_qcount) cudaFreeHost(eng->h_qcount);
+            eng->h_qcount = nullptr;
+            CK(cudaHostAlloc((void **)&eng->h_qcount, (size_t)R * QC_WORDS * sizeof(uint32_t), cudaHostAllocDefault));
+            while ((int)eng->ring_ev.size() < R) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); eng->ring_ev.push_back(e); }
+        }
+        auto slot_of = [&](int g) { return eng->h_qcount + (size_t)(g % R) * QC_WORDS; };
+        auto post_counts = [&](int g) -> int {      // the counters as they are before generation g runs
+            CK(cudaMemcpyAsync(slot_of(g), eng->d_qcount, QC_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, eng->stream));
+            CK(cudaEventRecord(eng->ring_ev[g % R], eng->stream));
+            return TRK3_OK;
+        };
+        GenCaps caps{};
+        auto set_caps = [&]() {
+            for (int sp = 0; sp < N_SPECIES; ++sp) caps.hot[sp] = eng->qs[0].q[sp].cap;
+            for (int c = 1; c < N_ECLASS; ++c) caps.cls[c - 1] = eng->qs[0].q[Q_ELC + c - 1].cap ? eng->qs[0].q[Q_ELC + c - 1].cap : 0xffffffffu;
+            caps.warm_e = eng->qs[0].q[Q_ELW].cap ? eng->qs[0].q[Q_ELW].cap : 0xffffffffu;
+            caps.warm_h = eng->qs[0].q[Q_VBW].cap ? eng->qs[0].q[Q_VBW].cap : 0xffffffffu;
+        };
+        set_caps();
+        // total records of input set `cur` in a counter snapshot (0: the cascade has died out); sets the overflow flag
+        auto hot_total = [&](const uint32_t *h, int cur, uint32_t n[6]) -> uint64_t {
             uint64_t total = 0;
-            if (gen == 0 && h_cnt[QC_HOT(1) + SP_ELECTRON] > eng->qs[1].q[SP_ELECTRON].cap) overflow = true;     // staged ion collisions
-            for (int s = 0; s < N_SPECIES; ++s) { if (hot[s] > eng->qs[cur].q[s].cap) { overflow = true; hot[s] = eng->qs[cur].q[s].cap; } total += hot[s]; }
-            uint32_t n_hot_el = hot[SP_ELECTRON];
-            for (int c = 1; c < N_ECLASS; ++c) { const uint32_t cp = eng->qs[cur].q[Q_ELC + c - 1].cap; if (hotc[c - 1] > cp) { overflow = true; hotc[c - 1] = cp; } total += hotc[c - 1]; n_hot_el += hotc[c - 1]; }
-            uint32_t n_warm = h_cnt[QC_ELW(cur)];
-            if (n_warm > eng->qs[cur].q[Q_ELW].cap) { overflow = true; n_warm = eng->qs[cur].q[Q_ELW].cap; }
-            total += n_warm;
-            uint32_t n_warm_h = h_cnt[QC_VBW(cur)];
-            if (n_warm_h > eng->qs[cur].q[Q_VBW].cap) { overflow = true; n_warm_h = eng->qs[cur].q[Q_VBW].cap; }
-            total += n_warm_h;
-            for (int s = 0; s < 2; ++s) if (cold[s] > eng->qs[0].q[N_SPECIES + s].cap) { overflow = true; cold[s] = eng->qs[0].q[N_SPECIES + s].cap; }
-            if (h_cnt[QC_ION + 1] > eng->qs[0].q[Q_ION].cap) overflow = true;
-            if (h_cnt[QC_SNAP] > eng->qs[0].q[Q_SNAP].cap) overflow = true;
-            if (overflow) break;
-            const uint64_t cold_pending = (uint64_t)(cold[0] - cold_done[0]) + (cold[1] - cold_done[1]);
-            ++waves;
+            n[0] = h[QC_HOT(cur) + SP_ELECTRON];
+            for (int c = 1; c < N_ECLASS; ++c) n[0] += h[QC_ELC(cur) + c - 1];
+            n[1] = h[QC_HOT(cur) + SP_VBHOLE]; n[2] = h[QC_HOT(cur) + SP_COREHOLE]; n[3] = h[QC_HOT(cur) + SP_PHOTON];
+            n[4] = h[QC_ELW(cur)]; n[5] = h[QC_VBW(cur)];
+            for (int q = 0; q < 6; ++q) total += n[q];
+            return total;
+        };
+        auto counters_overflow = [&](const uint32_t *h, int cur) {
+            bool o = h[QC_OVERFLOW] != 0u;
+            for (int sp = 0; sp < N_SPECIES; ++sp) o |= h[QC_HOT(cur) + sp] > eng->qs[cur].q[sp].cap;
+            for (int c = 1; c < N_ECLASS; ++c) o |= eng->qs[cur].q[Q_ELC + c - 1].cap && h[QC_ELC(cur) + c - 1] > eng->qs[cur].q[Q_ELC + c - 1].cap;
+            o |= eng->qs[cur].q[Q_ELW].cap && h[QC_ELW(cur)] > eng->qs[cur].q[Q_ELW].cap;
+            o |= eng->qs[cur].q[Q_VBW].cap && h[QC_VBW(cur)] > eng->qs[cur].q[Q_VBW].cap;
+            for (int q = 0; q < 2; ++q) o |= h[QC_COLD + q] > eng->qs[0].q[N_SPECIES + q].cap;
+            o |= std::max(h[QC_ION], h[QC_ION + 1]) > eng->qs[0].q[Q_ION].cap;
+            o |= h[QC_SNAP] > eng->qs[0].q[Q_SNAP].cap;
+            for (int sp = 0; sp < N_SPECIES; ++sp) o |= h[QC_X + sp] > eng->qs_x.q[sp].cap;
+            return o;
+        };
+        // one generation of the hot cascade: input set `cur`, output set `cur ^ 1` (time-sliced, see k_hot).  `n` = records per
+        // kernel if the host happens to know them (profile trace only).
+        auto enqueue_generation = [&](int cur, const uint32_t *n) -> int {
             const int nxt = cur ^ 1;
-            if (total) {        // one generation of the hot cascade (time-sliced, see k_hot)
-                static_assert(N_SPECIES <= 32 && N_ECLASS <= 32, "k_gen_reset uses one warp");
-                k_gen_reset<<<1, 32, 0, eng->stream>>>(eng->d_qcount, nxt);
-                eng->launches++;
-                // the species of a generation are independent of each other: the (few) valence holes, core holes and photons run
-                // on their own streams beside the electrons instead of lengthening the generation one after the other
-                const bool par = eng->opt_species_streams != 0;
-                cudaStream_t s1 = par ? eng->stream_sp[0] : eng->stream, s2 = par ? eng->stream_sp[1] : eng->stream, s3 = par ? eng->stream_sp[2] : eng->stream;
-                if (par) { CK(cudaEventRecord(eng->ev_gen, eng->stream)); }
-                if (n_hot_el) { rc = launch_hot_electrons(eng, eng->qs[cur], hot, hotc, eng->qs[nxt]); if (rc) return rc; }
-                if (hot[SP_VBHOLE]) { if (par) CK(cudaStreamWaitEvent(s1, eng->ev_gen, 0)); rc = launch_hot_vbholes(eng, eng->qs[cur].q[SP_VBHOLE], hot[SP_VBHOLE], eng->qs[nxt], s1); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[0], s1)); }
-                if (hot[SP_COREHOLE]) { if (par) CK(cudaStreamWaitEvent(s2, eng->ev_gen, 0)); rc = launch_wave<SP_COREHOLE, false>(eng, eng->qs[cur].q[SP_COREHOLE], 0, hot[SP_COREHOLE], heads + SP_COREHOLE, eng->qs[nxt], s2); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[1], s2)); }
-                if (n_warm) {       // warm electrons: the elastic-only kernel, one time slice per generation
-                    cudaStream_t s4 = par ? eng->stream_w : eng->stream;
-                    if (par) CK(cudaStreamWaitEvent(s4, eng->ev_gen, 0));
-                    rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[cur].q[Q_ELW], 0, n_warm, eng->d_qcount + QC_HEADW, eng->qs[nxt], s4, 0, 1); if (rc) return rc;
-                    if (par) CK(cudaEventRecord(eng->ev_w, s4));
-                }
-                if (n_warm_h) {     // warm valence holes
-                    cudaStream_t s5 = par ? eng->stream_wh : eng->stream;
-                    if (par) CK(cudaStreamWaitEvent(s5, eng->ev_gen, 0));
-                    rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[cur].q[Q_VBW], 0, n_warm_h, eng->d_qcount + QC_HEADWH, eng->qs[nxt], s5, 0, 1); if (rc) return rc;
-                    if (par) CK(cudaEventRecord(eng->ev_wh, s5));
-                }
-                if (hot[SP_PHOTON]) { if (par) CK(cudaStreamWaitEvent(s3, eng->ev_gen, 0)); rc = launch_wave<SP_PHOTON, false>(eng, eng->qs[cur].q[SP_PHOTON], 0, hot[SP_PHOTON], heads + SP_PHOTON, eng->qs[nxt], s3); if (rc) return rc; if (par) CK(cudaEventRecord(eng->ev_sp[2], s3)); }
-                if (par) {
-                    if (hot[SP_VBHOLE]) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[0], 0));
-                    if (hot[SP_COREHOLE]) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[1], 0));
-                    if (hot[SP_PHOTON]) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[2], 0));
-                    if (n_warm) CK(cudaStreamWaitEvent(eng->stream, eng->ev_w, 0));
-                    if (n_warm_h) CK(cudaStreamWaitEvent(eng->stream, eng->ev_wh, 0));
-                }
-                if (n_hot_el) {             // the pairs of this generation's impact ionisations join the next generation
-                    const int pi = prof_begin(eng, N_SPECIES + 1);       // timed with the finalisation kernels
-                    k_ion_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(eng->qs[0].q[Q_ION], eng->qs[nxt]);
-                    k_ion_reset<<<1, 32, 0, eng->stream>>>(eng->d_qcount + QC_ION);
-                    prof_end(eng, pi);
-                    CK(cudaGetLastError());
-                    eng->launches += 2;
-                }
-                cur = nxt;
+            static_assert(N_SPECIES <= 32 && N_ECLASS <= 32, "k_gen_reset uses one warp");
+            k_gen_reset<<<1, 32, 0, eng->stream>>>(eng->d_qcount, cur, nxt, caps);
+            eng->launches++;
+            // the species of a generation are independent of each other: the (few) valence holes, core holes and photons run
+            // on their own streams beside the electrons instead of lengthening the generation one after the other
+            const bool par = eng->opt_species_streams != 0;
+            cudaStream_t s1 = par ? eng->stream_sp[0] : eng->stream, s2 = par ? eng->stream_sp[1] : eng->stream, s3 = par ? eng->stream_sp[2] : eng->stream;
+            cudaStream_t s4 = par ? eng->stream_w : eng->stream, s5 = par ? eng->stream_wh : eng->stream;
+            const bool warm_e = eng->qs[cur].q[Q_ELW].cap != 0u, warm_h = eng->qs[cur].q[Q_VBW].cap != 0u && eng->hp.h_warm > eng->hp.h_cold;
+            const bool photons = eng->cfg.include_photons != 0;
+            if (par) { CK(cudaEventRecord(eng->ev_gen, eng->stream)); }
+            int rc;
+            if ((rc = launch_hot_electrons(eng, eng->qs[cur], eng->qs[nxt], n ? n[0] : 0))) return rc;
+            if (par) CK(cudaStreamWaitEvent(s1, eng->ev_gen, 0));
+            if ((rc = launch_hot_vbholes(eng, eng->qs[cur].q[SP_VBHOLE], eng->qs[nxt], s1, n ? n[1] : 0))) return rc;
+            if (par) CK(cudaEventRecord(eng->ev_sp[0], s1));
+            if (par) CK(cudaStreamWaitEvent(s2, eng->ev_gen, 0));
+            if ((rc = launch_wave<SP_COREHOLE, false>(eng, eng->qs[cur].q[SP_COREHOLE], heads + SP_COREHOLE, eng->qs[nxt], s2, 0, n ? n[2] : 0))) return rc;
+            if (par) CK(cudaEventRecord(eng->ev_sp[1], s2));
+            if (warm_e) {       // warm electrons: the elastic-only kernel, one time slice per generation
+                if (par) CK(cudaStreamWaitEvent(s4, eng->ev_gen, 0));
+                if ((rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[cur].q[Q_ELW], eng->d_qcount + QC_HEADW, eng->qs[nxt], s4, 1, n ? n[4] : 0))) return rc;
+                if (par) CK(cudaEventRecord(eng->ev_w, s4));
             }
-            // cold kernels: on the second stream, beside the next hot generation, as soon as enough records have gathered
-            // (the records [cold_done, cold) were written by kernels that have completed: the stream was just synchronised)
-            if (cold_pending && (!total || (eng->opt_overlap && cold_pending >= (uint64_t)eng->opt_cold_min))) {
-                CK(cudaMemsetAsync(heads + N_SPECIES, 0, 2 * sizeof(uint32_t), sc));
-                // beside a running hot cascade: optionally fewer cold blocks per SM (shared-memory floor)
-                const size_t sfl = (eng->opt_overlap && total) ? (size_t)eng->opt_cold_smem_kb * 1024 : 0;
-                if (cold[0] > cold_done[0]) { rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[0].q[Q_EL_COLD], cold_done[0], cold[0], heads + Q_EL_COLD, eng->qs_x, sc, sfl); if (rc) return rc; }
-                if (cold[1] > cold_done[1]) { rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[0].q[Q_VB_COLD], cold_done[1], cold[1], heads + Q_VB_COLD, eng->qs_x, sc, sfl); if (rc) return rc; }
-                cold_done[0] = cold[0]; cold_done[1] = cold[1];
+            if (warm_h) {       // warm valence holes
+                if (par) CK(cudaStreamWaitEvent(s5, eng->ev_gen, 0));
+                if ((rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[cur].q[Q_VBW], eng->d_qcount + QC_HEADWH, eng->qs[nxt], s5, 1, n ? n[5] : 0))) return rc;
+                if (par) CK(cudaEventRecord(eng->ev_wh, s5));
             }
-            if (total) continue;
-            // the hot cascade has died out and the cold queues are drained: did the cold kernels hand anything back?
-            uint32_t h_x[N_SPECIES];
-            CK(cudaMemcpyAsync(h_x, eng->d_qcount + QC_X, sizeof h_x, cudaMemcpyDeviceToHost, sc));
-            CK(cudaStreamSynchronize(sc));
-            uint64_t nx = 0;
-            for (int s = 0; s < N_SPECIES; ++s) { if (h_x[s] > eng->qs_x.q[s].cap) overflow = true; nx += h_x[s]; }
-            if (overflow) break;
-            if (!nx) break;                                        // cold kernels create no cold records: everything is done
-            CK(cudaMemsetAsync(eng->d_qcount + QC_HOT(nxt), 0, N_SPECIES * sizeof(uint32_t), eng->stream));
-            CK(cudaMemsetAsync(eng->d_qcount + QC_ELC(nxt), 0, (N_ECLASS - 1) * sizeof(uint32_t), eng->stream));
-            CK(cudaMemsetAsync(eng->d_qcount + QC_HEADC, 0, (N_ECLASS - 1) * sizeof(uint32_t), eng->stream));
-            CK(cudaMemsetAsync(eng->d_qcount + QC_ELW(nxt), 0, sizeof(uint32_t), eng->stream));
-            CK(cudaMemsetAsync(eng->d_qcount + QC_VBW(nxt), 0, sizeof(uint32_t), eng->stream));
-            CK(cudaMemsetAsync(heads, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
-            if (h_x[SP_ELECTRON]) { rc = launch_hot_electrons(eng, eng->qs_x, h_x, nullptr, eng->qs[nxt]); if (rc) return rc; }
-            if (h_x[SP_VBHOLE]) { rc = launch_hot_vbholes(eng, eng->qs_x.q[SP_VBHOLE], h_x[SP_VBHOLE], eng->qs[nxt]); if (rc) return rc; }
-            if (h_x[SP_ELECTRON]) {
+            if (photons) {
+                if (par) CK(cudaStreamWaitEvent(s3, eng->ev_gen, 0));
+                if ((rc = launch_wave<SP_PHOTON, false>(eng, eng->qs[cur].q[SP_PHOTON], heads + SP_PHOTON, eng->qs[nxt], s3, 0, n ? n[3] : 0))) return rc;
+                if (par) CK(cudaEventRecord(eng->ev_sp[2], s3));
+            }
+            if (par) {
+                CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[0], 0));
+                CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[1], 0));
+                if (photons) CK(cudaStreamWaitEvent(eng->stream, eng->ev_sp[2], 0));
+                if (warm_e) CK(cudaStreamWaitEvent(eng->stream, eng->ev_w, 0));
+                if (warm_h) CK(cudaStreamWaitEvent(eng->stream, eng->ev_wh, 0));
+            }
+            {   // the pairs of this generation's impact ionisations join the next generation
+                const int pi = prof_begin(eng, N_SPECIES + 1);       // timed with the finalisation kernels
                 k_ion_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(eng->qs[0].q[Q_ION], eng->qs[nxt]);
                 k_ion_reset<<<1, 32, 0, eng->stream>>>(eng->d_qcount + QC_ION);
+                prof_end(eng, pi);
                 CK(cudaGetLastError());
                 eng->launches += 2;
             }
-            CK(cudaMemsetAsync(eng->d_qcount + QC_X, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
-            cur = nxt;
-        }
-        if (eng->opt_overlap) { CK(cudaEventRecord(eng->ev_join, sc)); CK(cudaStreamWaitEvent(eng->stream, eng->ev_join, 0)); }
-        if (eng->opt_defer_snap && !overflow) {
-            // all histories of the batch have ended: turn the queued snapshot records into tallies
-            uint32_t n_snap = 0;
-            CK(cudaMemcpyAsync(&n_snap, eng->d_qcount + QC_SNAP, sizeof n_snap, cudaMemcpyDeviceToHost, eng->stream));
+            return TRK3_OK;
+        };
+        // run the cascade from input set `cur0` until it has died out; returns the set that is empty at the end
+        auto run_cascade = [&](int cur0, int &cur_out) -> int {
+            int enq = 0, seen = 0;          // generations enqueued / counter snapshots examined
+            bool dead = false;
+            int rc = post_counts(0);
+            if (rc) return rc;
+            while (!dead && !overflow && enq < eng->opt_max_generations) {
+                uint32_t n[6]; bool have_n = false;
+                while (seen <= enq) {
+                    if (seen <= enq - depth) CK(cudaEventSynchronize(eng->ring_ev[seen % R]));
+                    else if (cudaEventQuery(eng->ring_ev[seen % R]) != cudaSuccess) break;
+                    const uint32_t *h = slot_of(seen);
+                    const int cur = cur0 ^ (seen & 1);
+                    if (counters_overflow(h, cur)) { overflow = true; break; }
+                    const uint64_t total = hot_total(h, cur, n);
+                    have_n = (seen == enq);
+                    if (seen == 0 && h[QC_HOT(1) + SP_ELECTRON] > eng->qs[1].q[SP_ELECTRON].cap && cur0 == 0) { overflow = true; break; }     // staged ion collisions
+                    if (total == 0) { dead = true; break; }
+                    ++waves; ++seen;
+                }
+                if (dead || overflow) break;
+                eng->cur_gen = enq;
+                rc = enqueue_generation(cur0 ^ (enq & 1), have_n ? n : nullptr);
+                if (rc) return rc;
+                ++enq;
+                if ((rc = post_counts(enq))) return rc;
+            }
+            cur_out = cur0 ^ (enq & 1);
+            return TRK3_OK;
+        };
+        int cur = 0;
+        rc = run_cascade(0, cur);
+        if (rc) return rc;
+        // ---- the cold kernels: launched once, after the hot cascade has died out, over ALL cold records of the batch
+        uint32_t cold_done[2] = {0, 0};
+        uint32_t *h_fin = slot_of(0);
+        for (int round = 0; !overflow; ++round) {
+            eng->cur_gen = 1000 + round;
+            CK(cudaMemsetAsync(heads + N_SPECIES, 0, 2 * sizeof(uint32_t), eng->stream));
+            rc = launch_wave<SP_ELECTRON, true>(eng, eng->qs[0].q[Q_EL_COLD], heads + Q_EL_COLD, eng->qs_x, nullptr, 0, 0, cold_done[0]); if (rc) return rc;
+            rc = launch_wave<SP_VBHOLE, true>(eng, eng->qs[0].q[Q_VB_COLD], heads + Q_VB_COLD, eng->qs_x, nullptr, 0, 0, cold_done[1]); if (rc) return rc;
+            // the one host round trip of a batch: did anything overflow, and did the cold kernels hand anything back?
+            CK(cudaMemcpyAsync(h_fin, eng->d_qcount, QC_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, eng->stream));
             CK(cudaStreamSynchronize(eng->stream));
-            if (n_snap > eng->qs[0].q[Q_SNAP].cap) overflow = true;
-            else if (n_snap) {
-                size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
-                int use_smem = eng->opt_use_smem;
-                if (smem > (size_t)eng->smem_optin - 1024) { smem = 8; use_smem = 0; }
-                if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_snapshot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int bps = 0;
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_snapshot, 256, smem)); if (bps < 1) bps = 1;
+            if (counters_overflow(h_fin, cur)) { overflow = true; break; }
+            uint64_t nx = 0;
+            for (int sp = 0; sp < N_SPECIES; ++sp) nx += h_fin[QC_X + sp];
+            if (!nx) break;                                        // cold kernels create no cold records: everything is done
+            // a carrier that a cold kernel handed back (a valence hole lifted above the cold range by the level snapping):
+            // one generation from set X into `nxt`, then the cascade goes on from there; the next cold round starts behind
+            // the records that are done
+            cold_done[0] = std::min(h_fin[QC_COLD], eng->qs[0].q[Q_EL_COLD].cap); cold_done[1] = std::min(h_fin[QC_COLD + 1], eng->qs[0].q[Q_VB_COLD].cap);
+            const int nxt = cur ^ 1;
+            k_gen_reset<<<1, 32, 0, eng->stream>>>(eng->d_qcount, cur, nxt, caps);
+            eng->launches++;
+            rc = launch_hot_electrons(eng, eng->qs_x, eng->qs[nxt]); if (rc) return rc;
+            rc = launch_hot_vbholes(eng, eng->qs_x.q[SP_VBHOLE], eng->qs[nxt]); if (rc) return rc;
+            k_ion_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(eng->qs[0].q[Q_ION], eng->qs[nxt]);
+            k_ion_reset<<<1, 32, 0, eng->stream>>>(eng->d_qcount + QC_ION);
+            CK(cudaGetLastError());
+            eng->launches += 2;
+            CK(cudaMemsetAsync(eng->d_qcount + QC_X, 0, N_SPECIES * sizeof(uint32_t), eng->stream));
+            rc = run_cascade(nxt, cur);
+            if (rc) return rc;
+        }
+        if (eng->opt_defer_snap && !overflow) {
+            // all histories of the batch have ended: turn the queued snapshot records into tallies (the kernel reads their number)
+            size_t smem = (eng->opt_use_smem && eng->hp.s_total > 0) ? (size_t)eng->hp.s_total * sizeof(double) : 8;
+            int use_smem = eng->opt_use_smem;
+            if (smem > (size_t)eng->smem_optin - 1024) { smem = 8; use_smem = 0; }
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_snapshot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int bps = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_snapshot, 256, smem)); if (bps < 1) bps = 1;
+            const uint32_t n_snap = h_fin[QC_SNAP];
+            if (n_snap) {
                 const uint32_t grid = std::min<uint32_t>((n_snap + 255u) / 256u, (uint32_t)(eng->n_sm * bps));
                 const int pi = prof_begin(eng, N_SPECIES + 1);
                 k_snapshot<<<grid, 256, smem, eng->stream>>>(eng->qs[0].q[Q_SNAP], eng->qs[0], use_smem);
@@ -1529,7 +1809,7 @@ int trk3_mc_reset(trk3_engine *eng) {
     if (e != cudaSuccess && cudaDeviceSynchronize() != cudaSuccess) { eng->err = std::string("device lost: ") + cudaGetErrorString(e); return TRK3_E_CUDA; }
     const size_t n_counters = TRK3_N_EVENT_CLASSES + TRK3_N_ERRORS + 6;
     if (eng->d_counters) CK(cudaMemsetAsync(eng->d_counters, 0, n_counters * sizeof(unsigned long long), eng->stream));
-    if (eng->d_qcount) CK(cudaMemsetAsync(eng->d_qcount, 0, QC_TOTAL * sizeof(uint32_t), eng->stream));
+    if (eng->d_qcount) CK(cudaMemsetAsync(eng->d_qcount, 0, QC_WORDS * sizeof(uint32_t), eng->stream));
     if (eng->d_tally) CK(cudaMemsetAsync(eng->d_tally, 0, (size_t)eng->lay.total * sizeof(double), eng->stream));
     if (eng->nb_alloc) { CK(cudaMemsetAsync(eng->d_u32, 0, eng->sl.u32_total * sizeof(uint32_t), eng->stream)); CK(cudaMemsetAsync(eng->d_f64, 0, eng->sl.f64_total * sizeof(double), eng->stream)); }
     CK(cudaStreamSynchronize(eng->stream));
@@ -1558,6 +1838,7 @@ void trk3_mc_destroy(trk3_engine *eng) {
     if (eng->ev_fork) cudaEventDestroy(eng->ev_fork);
     if (eng->ev_join) cudaEventDestroy(eng->ev_join);
     if (eng->h_qcount) cudaFreeHost(eng->h_qcount);
+    for (auto e : eng->ring_ev) cudaEventDestroy(e);
     delete eng;
 }
 

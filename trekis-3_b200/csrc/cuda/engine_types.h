@@ -105,6 +105,9 @@ struct DevP {
     const double *dshi_E, *dshi_L, *eid_hw, *eid_L, *eed_hw, *eed_L, *hid_hw, *hid_L, *hed_hw, *hed_L;
     const double *ldshi_E, *dshi_iL, *ldshi_iL;          // log(E), 1/L and log(1/L) of the SHI cumulative tables
     const double *leid_hw, *leid_L, *leed_hw, *leed_L, *lhid_hw, *lhid_L, *lhed_hw, *lhed_L;
+    // per row of the electron differential tables: 1 = the cumulative MFPs of the row are non-increasing, so that the index
+    // Find_in_monoton_array_decreasing ends on is clamp(#entries above the value, 1, n) (engine.cu, transferred_energy_warp)
+    const uint8_t *eid_mono, *eed_mono;
     const double *dos_E, *dos_DOS, *dos_int, *dos_effm, *out_R, *out_V;
     int32_t shi_Mtemp[TRK3_MAX_SHELLS]; double shi_dL[TRK3_MAX_SHELLS];      // per-shell constants of SHI_energy_transfer
     GridLut dshi_lut[TRK3_MAX_SHELLS];                   // accelerators of the inverse-CDF search of SHI_energy_transfer (in log 1/L)
