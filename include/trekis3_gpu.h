@@ -289,6 +289,14 @@ typedef struct trk3_dcs_ctx {
     double El_eff_mass;
     int32_t kind_DR;                        /* dispersion relation of the oscillators */
     double v_f, temp;
+    /* Dynamical screening of the nucleus in the elastic (phonon-CDF) cross section, CDF_elast_Zeff = 2 / 3
+     * (Diff_cross_section_phonon, Cross_sections.f90:3216-3276): 0 = none (CDF_elast_Zeff 0 / 1), 2 = atomic form factors for
+     * the core + CDF of the valence band, 3 = CDF of every shell.  `scr` packs what get_screening_ff / get_screening_all
+     * read: [0] n_atoms, then per atom 10 doubles {Zat, Pers, electrons outside the valence band, first oscillator set,
+     * number of shells, form-factor coefficients a1..a5 (INPUT_EADL/Atomic_form_factors.dat)}, then per oscillator set
+     * (shell) 2 doubles {Nel, Ip}.  vb_set = oscillator set of the valence band (last shell of the first atom). */
+    int32_t screening, vb_set;
+    const double *scr; int32_t n_scr;
 } trk3_dcs_ctx;
 /* out[i] = the q-integral of request i = (tasks[task_of[i]], hw[i]).  All pointers are host memory.  Returns TRK3_OK or
  * a negative error (no CUDA device: there is no CPU fallback in this library). */

@@ -68,6 +68,8 @@ int trk3h_warning(trk3h_case *c, int i, char *out, int outlen);
 /* Single-point evaluations of the table builder (parity tests of Cross_sections.f90 routines). */
 int trk3h_eval_TotIMFP(trk3h_case *c, double E, int atom, int shell, int kind, double *L, double *dEdx);
 int trk3h_eval_EMFP(trk3h_case *c, double E, int kind, double *L, double *dEdx);
+/* one value of Diff_cross_section_phonon (Cross_sections.f90:3142) for an electron, with the screening of the case's CDF_elast_Zeff */
+int trk3h_eval_dcs_phonon(trk3h_case *c, double Ee, double hw, double *value, double *phonon_A0);
 int trk3h_eval_SHI(trk3h_case *c, double E, int atom, int shell, double *inv_L, double *dEdx, double *Zeff);
 int trk3h_eval_photon(trk3h_case *c, double E, int atom, int shell, double *L);
 int trk3h_sumrules(trk3h_case *c, int atom, int shell, double *ksum, double *fsum);   /* atom<0: phonon CDF */

@@ -123,6 +123,17 @@ def test_charge_models_on_the_gpu(tmp_path, kind):
     check_against_oracle(case, 4)
 
 
+@pytest.mark.parametrize("mode", [2, 3])
+def test_screened_elastic_scattering_on_the_gpu(tmp_path, mode):
+    """CDF_elast_Zeff = 2 / 3: elastic tables with the dynamically screened nucleus (built on the GPU), then the
+    Monte-Carlo on them -- CUDA engine vs oracle.  The screened cross section is larger than the unit-charge one by the square
+    of a charge of several units, so elastic collisions dominate even more."""
+    case = tk.Case.load(tk.make_run_dir(str(tmp_path / "z"), "C1", edits={12: "1   %d   ! CDF elastic scattering, screened nucleus" % mode}))
+    case.build_tables(cache_dir=CACHE, **FULL)
+    sg, so = check_against_oracle(case, 3)
+    assert sg["events"]["el_elastic"] > 5e4
+
+
 def test_mott_elastic_scattering(tmp_path):
     d = tk.make_run_dir(str(tmp_path / "v2"), "C1", edits={12: "0   1"})
     case = tk.Case.load(d)
@@ -405,7 +416,7 @@ def test_c5_high_statistics_sweep_composes(case_c1):
     assert rel_close((a + b)[m], whole[m], 1e-9)
 
 
-@pytest.mark.parametrize("cfg", ["C1", "C2", "C4", "C1-BK"])
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C4", "C1-BK", "C1-Z2", "C1-Z3"])
 def test_gpu_table_builder_gives_the_host_tables(tmp_path, cfg):
     """all q-integrals of the table builder evaluated on the GPU (trk3_dcs_eval).  BASELINE's bar for the
     tables is 1e-12 relative; the GPU kernel shares its integrands with the host builder and is compiled without
@@ -413,6 +424,8 @@ def test_gpu_table_builder_gives_the_host_tables(tmp_path, cfg):
     edits = None
     if cfg.endswith("-BK"):          # Brandt-Kitagawa ion: the form factor uses pow(), which may differ in the last bit on the device
         cfg, edits = cfg[:-3], {11: "1   ! Brandt-Kitagawa ion"}
+    elif cfg.endswith(("-Z2", "-Z3")):   # dynamically screened nucleus in the elastic cross section (form factors: sin, atan, pow)
+        cfg, edits = cfg[:-3], {12: "1   %s   ! CDF elastic scattering, CDF_elast_Zeff" % cfg[-1]}
     window = not (cfg == "C1" and edits is None)             # C1: the ion over its whole energy grid (what the reference main builds), host side ~1 min
     host = tk.Case.load(tk.make_run_dir(str(tmp_path / "h"), cfg, edits=edits)); host.build_tables(shi_window_only=window)
     gpu = tk.Case.load(tk.make_run_dir(str(tmp_path / "g"), cfg, edits=edits)); gpu.build_tables(shi_window_only=window, evaluator="gpu")

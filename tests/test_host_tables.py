@@ -248,6 +248,115 @@ def test_brandt_kitagawa_ion(tmp_path, case_c1):
     assert bk.reference_cache_name("shi_stem") == "OUTPUT_Xe_CDF_Barkas_BK"
 
 
+def _al2o3_screening_inputs(case):
+    """What the screened elastic cross section reads, parsed here from the shipped files (not through the library)."""
+    ff = np.loadtxt(os.path.join(case.dir, "INPUT_EADL", "Atomic_form_factors.dat"), skiprows=1)
+    atoms = [dict(Z=13, pers=2, Nel=[2, 8, 24], Ip=[1559.1, 89.0, 8.8], mass=26.9815386,
+                  osc=[[(1565.0, 178.0, 1200.0)], [(80.0, 620.0, 160.0)], AL2O3["vb_osc"]]),
+             dict(Z=8, pers=3, Nel=[2], Ip=[538.0], mass=15.9992, osc=[[(545.0, 270.0, 380.0)]])]
+    for a in atoms:
+        a["ff"] = ff[a["Z"] - 1]
+    return atoms
+
+
+def numpy_dcs_phonon_screened(case, mode, Ee, hw, phonon_osc, dos_k, dos_effm):
+    """Independent restatement of Diff_cross_section_phonon with dynamical screening (Cross_sections.f90:3142-3300,
+    get_screening_ff :3303, get_screening_all :3372, construct_CDF :184, One_Reewq :303, form_factor :61) for an electron in
+    Al2O3, free-electron dispersion, effective mass from the DOS, T = 0."""
+    atoms = _al2o3_screening_inputs(case)
+    sq_ge = math.sqrt(g_e)
+    Mt = sum(a["pers"] * a["mass"] for a in atoms) * g_Mp / sum(a["pers"] for a in atoms)
+    alpha = g_e * g_e / (g_h * g_cvel * 4.0 * g_Pi * 8.854187817620e-12)
+
+    def mass_at(q):
+        qlim = abs(q) * sq_ge
+        if qlim <= dos_k[-1]:
+            j = min(max(int(np.searchsorted(dos_k, qlim, side="right")), 0), len(dos_k) - 1)
+            return dos_effm[j]
+        return 1.0
+
+    def shell_abs_cdf(osc, Ip, is_vb, w, q):
+        if not is_vb and w + (g_h * q) ** 2 / (2.0 * g_me) <= Ip:
+            return 1.0
+        sqq = g_h * g_h * q * q / (2.0 * mass_at(q) * g_me)
+        im = sum(A * G * w / ((w * w - (E0 + sqq) ** 2) ** 2 + G * G * w * w) for E0, A, G in osc)
+        re = -(1.0 - sum(A * ((E0 + sqq) ** 2 - w * w) / ((w * w - (E0 + sqq) ** 2) ** 2 + G * G * w * w) for E0, A, G in osc))
+        den = re * re + im * im
+        return abs(complex(-re / den, im / den)) if abs(den) > 1e-12 else 1.0
+
+    def form_factor(q, a, Z):
+        mc = g_me * g_cvel
+        x = q / mc * 20.6074224164
+        f = Z * (1.0 + a[0] * x ** 2 + a[1] * x ** 3 + a[2] * x ** 4) / (1.0 + a[3] * x ** 2 + a[4] * x ** 4) ** 2
+        if Z > 10.0 and f < 2.0:
+            al = alpha * (Z - 5.0 / 16.0); b = math.sqrt(1.0 - al * al); Q = q / (2.0 * mc * al)
+            f = max(f, math.sin(2.0 * b * math.atan(Q)) / (b * Q * (1.0 + Q * Q) ** b))
+        return f
+
+    Zmol = sum(a["Z"] * a["pers"] for a in atoms); pers = sum(a["pers"] for a in atoms)
+    vb = atoms[0]
+
+    def screening(q):
+        c = 0.0
+        if mode == 2:
+            p_e = 0.5 * (math.sqrt(2.0 * g_me * Ee * g_e) + q * g_h * sq_ge)
+            p_prime = 0.5 * (math.sqrt(2.0 * g_me * Ee) / g_h + q)
+            acdf = shell_abs_cdf(vb["osc"][-1], vb["Ip"][-1], True, hw, p_prime)
+            for i, a in enumerate(atoms):
+                core = sum(a["Nel"][:-1]) if i == 0 else sum(a["Nel"])
+                c -= min(form_factor(p_e, a["ff"], float(a["Z"])), core) * a["pers"]
+            c += vb["Nel"][-1] * (1.0 / acdf - 1.0)
+        else:
+            for i, a in enumerate(atoms):
+                nsh = len(a["Ip"])                      # sic: shell number nsh of the FIRST atom stands for all shells of atom i
+                acdf = shell_abs_cdf(vb["osc"][nsh - 1], vb["Ip"][nsh - 1], nsh == len(vb["Ip"]), hw, q)
+                for j in range(nsh):
+                    is_vb = (i == 0 and j == nsh - 1)
+                    c += (a["Nel"][j] if is_vb else a["Nel"][j] * a["pers"]) * (1.0 / acdf - 1.0)
+        return ((Zmol + c) / pers) ** 2
+
+    def im_phonon(w, q):
+        sqq = g_h * g_h * q * q / (2.0 * Mt)
+        return sum(A * G * w / ((w * w - (E0 + sqq) ** 2) ** 2 + G * G * w * w) for E0, A, G in phonon_osc)
+
+    pre = math.sqrt(2.0 * g_me) / g_h
+    qmin = pre * (math.sqrt(Ee) - math.sqrt(abs(Ee - hw))) if hw <= Ee - 1e-12 else pre * math.sqrt(Ee)
+    qmax = pre * (math.sqrt(Ee) + math.sqrt(abs(Ee - hw)))
+    s, q, prev = 0.0, qmin, 0.0
+    while abs(q) < abs(qmax):
+        dq = q / 100.0
+        a = im_phonon(hw, q + dq / 2.0); b = im_phonon(hw, q + dq)
+        s = s + dq / 6.0 * (prev + 4.0 * a + b) * (screening(q) / q)
+        prev = b; q = q + dq
+    return 1.0 / (g_Pi * g_a0 * Ee) * s
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+def test_screened_elastic_cross_section_against_independent_numpy_restatement(tmp_path, mode, case_c1):
+    """CDF_elast_Zeff = 2 (atomic form factors for the core + CDF of the valence band) and 3 (CDF of every shell): the nucleus
+    is screened dynamically inside the q-integral of the elastic cross section (Cross_sections.f90:3216-3276)."""
+    case = tk.Case.load(tk.make_run_dir(str(tmp_path / "z"), "C1", edits={12: f"1   {mode}   ! CDF elastic scattering, screened nucleus"}))
+    a = case_c1.table_arrays()
+    at_dens = case_c1.get("At_Dens")
+    k = (3.0 * 2.0 * g_Pi * g_Pi / 2.0 * np.cumsum(a["dos_DOS"]) * at_dens / 5.0 * 1e6) ** (1.0 / 3.0)
+    # the user's phonon CDF is renormalised to the number of atoms per molecule (:641-655): k-sum rule = N_at_mol = 5
+    ks, _ = case.sumrules(-1, 0)
+    _, A0 = case.eval_dcs_phonon(10.0, 0.05)
+    ks, _ = case.sumrules(-1, 0)
+    assert ks == pytest.approx(5.0, rel=1e-10)
+    scale = A0 / 0.003
+    phonon = [(0.1125, 0.003 * scale, 0.005), (0.061, 0.000045 * scale, 0.002)]
+    for Ee, hw in ((10.0, 0.05), (100.0, 0.11), (1000.0, 0.2), (3.0, 0.061)):
+        v, _ = case.eval_dcs_phonon(Ee, hw)
+        ref = numpy_dcs_phonon_screened(case, mode, Ee, hw, phonon, k, a["dos_effm"])
+        assert v == pytest.approx(ref, rel=1e-10), (mode, Ee, hw)
+    # and it differs from the unscreened unit charge by the square of a charge of a few units
+    v1, _ = case_c1.eval_dcs_phonon(100.0, 0.11)
+    v2, _ = case.eval_dcs_phonon(100.0, 0.11)
+    assert v2 / scale > 2.0 * v1
+    assert case.reference_cache_name("el_emfp") == ("OUTPUT_Electron_EMFPs_CDF_Z_CDFe_FF_0.00_K.dat" if mode == 2 else "OUTPUT_Electron_EMFPs_CDF_Z_CDFe_0.00_K.dat")
+
+
 def test_time_grid_and_layout(case_c1):
     lay = case_c1.layout()
     assert lay.Nt == 5 and list(lay.time_grid[:6]) == pytest.approx([0.01, 0.1, 1.0, 10.0, 100.0, 110.0], rel=1e-12)

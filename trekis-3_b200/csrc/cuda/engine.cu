@@ -29,7 +29,58 @@
 
 using namespace trk3;
 
+// The run's constants (DevP: switches, table pointers, time grid ...): ONE __constant__ image per device, copied at the start of
+// every batch; engines that share a device take turns (trk3_mc_run_device holds a per-device lock for the length of a run).
+//
+// -DTRK_PARAM_CONSTANTS passes DevP as a __grid_constant__ kernel parameter instead (8 KB of parameters per launch; the constants
+// then belong to the launch and engines on one device need no lock).  Measured in round 2 and NOT the default: with the
+// parameter the pair-creation kernels (k_shi_emit / k_ion_emit) give a handful of particles per iteration another first
+// free flight than the oracle (same event counts and energies, 36 of 86 Out_Elat bins off by up to 3 % on C1, 8 iterations),
+// while the symbol build agrees with the oracle in every bin; kernel group by kernel group (-DTRK_HYBRID=mask keeps both and lets
+// group g read the symbol if bit g is set) the difference follows those two kernels alone.  Not understood, so not shipped.
+#ifdef TRK_PARAM_CONSTANTS
+#define TRK_P const __grid_constant__ DevP c_p
+#define TRK_PA(eng) (eng)->hp
+#else
+#define TRK_CONST_SYMBOL 1
 __constant__ DevP c_p;
+#define TRK_P int
+#define TRK_PA(eng) 0
+#endif
+#ifdef TRK_HYBRID
+#undef TRK_P
+#undef TRK_PA
+#ifndef TRK_CONST_SYMBOL
+__constant__ DevP c_p;
+#endif
+#define TRK_PA(eng) (eng)->hp
+#define TRK_PSEL(g) const __grid_constant__ DevP TRK_CAT(c_, TRK_NAME(g))
+#define TRK_CAT(a, b) TRK_CAT2(a, b)
+#define TRK_CAT2(a, b) a##b
+#if TRK_HYBRID & 1
+#define TRK_NAME_0 unused
+#else
+#define TRK_NAME_0 p
+#endif
+#if TRK_HYBRID & 2
+#define TRK_NAME_1 unused
+#else
+#define TRK_NAME_1 p
+#endif
+#if TRK_HYBRID & 4
+#define TRK_NAME_2 unused
+#else
+#define TRK_NAME_2 p
+#endif
+#define TRK_NAME(g) TRK_NAME_##g
+#define TRK_P0 TRK_PSEL(0)
+#define TRK_P1 TRK_PSEL(1)
+#define TRK_P2 TRK_PSEL(2)
+#else
+#define TRK_P0 TRK_P
+#define TRK_P1 TRK_P
+#define TRK_P2 TRK_P
+#endif
 
 // queue ids: 0..3 = next hot generation per species, 4 / 5 = cold electrons / cold valence holes
 #define Q_EL_COLD N_SPECIES
@@ -433,7 +484,7 @@ __device__ inline void electron_collision_warp(C &c, Rec &e, int iv, Cache &k, P
     if (lane == 0 && (e.E < -1.0e-9 || trk_isnan(e.E))) c.error(TRK3_ERR_22);
 }
 
-__global__ void __launch_bounds__(32 * SHI_WARPS) k_shi(Queue stage, QueueSet qout, int lanes) {
+__global__ void __launch_bounds__(32 * SHI_WARPS) k_shi(TRK_P0, Queue stage, QueueSet qout, int lanes) {
     __shared__ unsigned int s_cnt[S_NCNT];
     block_prologue(nullptr, s_cnt, 0);
     DevCtxT<false> c{c_p, qout, nullptr, s_cnt, c_p.defer_snap};
@@ -475,7 +526,7 @@ __global__ void __launch_bounds__(32 * SHI_WARPS) k_shi(Queue stage, QueueSet qo
     }
     block_epilogue(c_p, nullptr, s_cnt);
 }
-__global__ void __launch_bounds__(256) k_shi_emit(Queue stage, QueueSet qout) {
+__global__ void __launch_bounds__(256) k_shi_emit(TRK_P0, Queue stage, QueueSet qout) {
     __shared__ unsigned int s_cnt[S_NCNT];
     block_prologue(nullptr, s_cnt, 0);
     DevCtxT<false> c{c_p, qout, nullptr, s_cnt, c_p.defer_snap};
@@ -491,7 +542,7 @@ __global__ void __launch_bounds__(256) k_shi_emit(Queue stage, QueueSet qout) {
 
 // k_ion_emit: the electron-hole pairs of the impact ionisations of a generation (electron_ion_emit), one thread per
 // ionisation; launched right after the hot kernels of the generation, it fills the same next-generation queues.
-__global__ void __launch_bounds__(256) k_ion_emit(Queue ionq, QueueSet qout) {
+__global__ void __launch_bounds__(256) k_ion_emit(TRK_P0, Queue ionq, QueueSet qout) {
     __shared__ unsigned int s_cnt[S_NCNT];
     block_prologue(nullptr, s_cnt, 0);
     DevCtxT<false> c{c_p, qout, nullptr, s_cnt, c_p.defer_snap};
@@ -508,7 +559,7 @@ __global__ void __launch_bounds__(256) k_ion_emit(Queue ionq, QueueSet qout) {
 }
 
 // k_snapshot: the snapshot records of a batch -> tallies (Calculated_statistics, Monte_Carlo.f90:881-1110), one thread per record
-__global__ void __launch_bounds__(256) k_snapshot(Queue sq, QueueSet qout, int use_smem) {
+__global__ void __launch_bounds__(256) k_snapshot(TRK_P2, Queue sq, QueueSet qout, int use_smem) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
@@ -533,7 +584,7 @@ __global__ void __launch_bounds__(256) k_snapshot(Queue sq, QueueSet qout, int u
 // The number of records is read from the queue's device counter: the host enqueues the launches of a generation without
 // knowing how many records the previous one produced (no host round trip per generation); blocks without work leave at once.
 template <int SP, bool COLD, bool LEAN>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(Queue qin, uint32_t first, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int warm) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(TRK_P1, Queue qin, uint32_t first, uint32_t *head, QueueSet qout, int use_smem, int refill_min, int slice, int warm) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     const uint32_t n_in = min(*qin.count, qin.cap);       // records [first, n_in)
@@ -595,7 +646,7 @@ template <int SP> __device__ inline bool hot_roulette(const Cache &k, double RN)
 template <int SP, int MODE, class C> __device__ inline void hot_event(C &c, Rec &r, int ig, Cache &k, double RN) {
     if (SP == SP_ELECTRON) electron_event_t<MODE>(c, r, ig, k, RN); else vbhole_event_t<MODE>(c, r, ig, k, RN);
 }
-template <int SP> __device__ inline bool hot_leaves(const Rec &r) { return SP == SP_ELECTRON ? electron_leaves_hot(c_p, r) : vbhole_leaves_hot(c_p, r); }
+template <int SP> __device__ inline bool hot_leaves(const DevP &p, const Rec &r) { return SP == SP_ELECTRON ? electron_leaves_hot(p, r) : vbhole_leaves_hot(p, r); }
 
 // The input of k_hot: the records of one generation by energy class (class 0 = all of them for the valence holes).
 // A history's remaining number of collisions grows with its energy and a warp advances at the pace of its slowest
@@ -609,7 +660,7 @@ struct HotIn {
     uint32_t *head[N_ECLASS];
     int qmax[N_ECLASS];            // most histories of class c a warp follows at once
     int slice[N_ECLASS];           // collisions after which a history of class c goes back to the queue (promoted by one class)
-    int ncls, spread, quota_min;
+    int ncls, spread, quota_min, coop, weighted;
 };
 // What the launch works with, derived ON THE DEVICE from the queue counters (the host does not know them when it enqueues
 // the launch): records per class, histories per warp, and the warps that start on each class.
@@ -631,7 +682,18 @@ __device__ inline void hot_plan(const HotIn &in, uint32_t W, HotPlan &pl) {
         pl.quota[c] = (int)qmax;
     }
     if (total_need >= W || !in.spread) {
-        for (int c = 0; c < in.ncls; ++c) w[c] = need[c] ? max(1u, (uint32_t)((unsigned long long)need[c] * W / max(total_need, 1u))) : 0u;
+        // more warp-loads than warps: the generation is bound by throughput, and a warp-load of class c keeps its warp busy
+        // for slice[c] rounds of a duration that grows with the histories per warp (measured: ~12 us for a lone lane, ~6 us
+        // when the lanes share it, ~25 us for 32 lanes that disagree on the channel).  The warps are shared out in
+        // proportion to that WORK, so that all classes end together (in proportion to the warp-loads alone, the long
+        // time slices of the upper classes were the tail of the early generations).
+        float cost[N_ECLASS], total = 0.f;
+        for (int c = 0; c < in.ncls; ++c) {
+            const float tau = (in.qmax[c] == 1 && in.coop ? 6.f : 12.f) + 0.42f * (float)(in.qmax[c] - 1);
+            cost[c] = in.weighted ? (float)need[c] * (float)in.slice[c] * tau : (float)need[c];
+            total += cost[c];
+        }
+        for (int c = 0; c < in.ncls; ++c) w[c] = need[c] ? max(1u, (uint32_t)(cost[c] * (float)W / fmaxf(total, 1.f))) : 0u;
         if (total_need < W) for (int c = 0; c < in.ncls; ++c) w[c] = need[c];
     } else {
         uint32_t spare = W - total_need;
@@ -644,9 +706,8 @@ __device__ inline void hot_plan(const HotIn &in, uint32_t W, HotPlan &pl) {
     uint32_t wsum = 0;
     for (int c = in.ncls - 1; c >= 0; --c) { wsum += w[c]; pl.wend[c] = wsum; }
 }
-
 template <int SP, bool LEAN>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn in, QueueSet qout, int use_smem, int refill_min, int coop) {
+__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(TRK_P1, HotIn in, QueueSet qout, int use_smem, int refill_min, int coop) {
     extern __shared__ double s_dyn[];
     __shared__ unsigned int s_cnt[S_NCNT];
     __shared__ HotPlan pl;
@@ -748,7 +809,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn
             have_rn = false;
             // leave when the carrier can no longer ionise (cold queue) or, after `slice` collisions, back to the hot queue
             ++nev;
-            if (hot_leaves<SP>(r)) { c.push(SP, r); active = false; }
+            if (hot_leaves<SP>(c_p, r)) { c.push(SP, r); active = false; }
             else if (nev >= my_slice && r.tn < c_p.Tim) {
                 if (SP == SP_ELECTRON) r.shell = -1 - my_next;
                 c.push_hot(SP, r); active = false;
@@ -758,11 +819,11 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(HotIn
     block_epilogue(c_p, s_tally, s_cnt, -1, 0, LEAN);
 }
 
-__global__ void k_iter_prefix(FoldAux a) {
+__global__ void k_iter_prefix(TRK_P2, FoldAux a) {
     const uint32_t il = blockIdx.x * blockDim.x + threadIdx.x;
     if (il < c_p.batch_n) iter_prefix(c_p, a, il);
 }
-__global__ void k_fold(FoldAux a, int64_t njobs) {      // one warp per output element
+__global__ void k_fold(TRK_P2, FoldAux a, int64_t njobs) {      // one warp per output element
     const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (j >= njobs) return;
     double *dst;
@@ -830,7 +891,7 @@ struct trk3_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     trk3_config cfg{};
     trk3_tally_layout lay{};
-    DevP hp{};                         // host image of c_p (device pointers inside)
+    DevP hp{};                         // the run's constants (device pointers inside): passed to every launch by value
     std::vector<void *> allocs;
     std::vector<std::pair<void *, size_t>> tab_allocs;   // table arrays in binding order (re-used by trk3_mc_reload_tables)
     size_t tab_cursor = 0;
@@ -839,6 +900,7 @@ struct trk3_engine {
     // options
     uint32_t *h_qcount = nullptr;       // pinned ring of counter snapshots (run-ahead generation loop)
     std::vector<cudaEvent_t> ring_ev;   // one event per ring slot
+    int opt_weighted = 0;               // warps per energy class in proportion to the class's work, not its warp-loads
     int opt_coop = 1;                   // hot electrons that have a warp of their own: the lanes share the collision
     int opt_run_ahead = 1;              // generations the host may enqueue beyond the last counter snapshot it has seen
     int opt_batch = 4096, opt_use_smem = 1, opt_refill_min = 8, opt_blocks_per_sm = 0, opt_max_generations = 1 << 20, opt_block = 256;
@@ -1122,7 +1184,7 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t *head, const QueueS
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (grid < 1) grid = 1;
     const int pi = prof_begin(eng, warm ? N_SPECIES + 4 + SP : (COLD ? N_SPECIES + 2 + SP : SP), st, n_hint);
-    kern<<<grid, block, smem, st>>>(qin, first, head, qout, use_smem, eng->opt_refill_min, warm ? eng->opt_warm_slice : eng->opt_hot_slice, warm);
+    kern<<<grid, block, smem, st>>>(TRK_PA(eng), qin, first, head, qout, use_smem, eng->opt_refill_min, warm ? eng->opt_warm_slice : eng->opt_hot_slice, warm);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
@@ -1143,7 +1205,7 @@ int launch_hot(trk3_engine *eng, const Queue *const *qin, uint32_t *const *head,
     const int block = eng->opt_hot_block ? eng->opt_hot_block : eng->opt_block;
     if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, block, smem)); if (bps < 1) bps = 1; }
     HotIn in{};
-    in.ncls = ncls; in.spread = eng->opt_spread; in.quota_min = eng->opt_quota_min;
+    in.ncls = ncls; in.spread = eng->opt_spread; in.quota_min = eng->opt_quota_min; in.coop = eng->opt_coop; in.weighted = eng->opt_weighted;
     for (int c = 0; c < ncls; ++c) {
         in.q[c] = *qin[c]; in.head[c] = head[c];
         in.qmax[c] = (ncls > 1) ? eng->opt_class_quota[c] : 32;
@@ -1151,7 +1213,7 @@ int launch_hot(trk3_engine *eng, const Queue *const *qin, uint32_t *const *head,
     }
     const uint32_t grid = (uint32_t)(eng->n_sm * bps);               // the warps the GPU holds at once: hot_plan shares them out
     const int pi = prof_begin(eng, SP, st, n_hint);
-    kern<<<grid, block, smem, st>>>(in, qout, use_smem, eng->opt_refill_min, eng->opt_coop);
+    kern<<<grid, block, smem, st>>>(TRK_PA(eng), in, qout, use_smem, eng->opt_refill_min, eng->opt_coop);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
@@ -1351,6 +1413,7 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "spread") eng->opt_spread = (v != 0.0);
     else if (k == "quota_min") eng->opt_quota_min = std::min(32, std::max(1, (int)v));
     else if (k == "coop") eng->opt_coop = (v != 0.0);
+    else if (k == "weighted") eng->opt_weighted = (v != 0.0);
     else if (k == "run_ahead") eng->opt_run_ahead = std::min(6, std::max(0, (int)v));
     else if (k == "warm_pinel") { eng->opt_warm_pinel = std::min(0.99, std::max(0.0, v)); eng->nb_alloc = 0; eng->e_warm_auto = -1.0; eng->h_warm_auto = -1.0; }
     else if (k == "warm_holes") eng->opt_warm_holes = (v != 0.0);
@@ -1397,9 +1460,6 @@ int trk3_mc_download_tallies(trk3_engine *eng, double *dst) {
     return TRK3_OK;
 }
 
-// The kernels read the run's constants from ONE __constant__ image per device (c_p): engines that share a device take
-// turns (handles on different devices, one per host thread, run concurrently).
-static std::mutex g_device_mutex[64];
 
 static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_stats *stats);
 int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_stats *stats) {
@@ -1410,7 +1470,10 @@ int trk3_mc_run_device(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_
     return rc;
 }
 static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, trk3_stats *stats) {
+#ifdef TRK_CONST_SYMBOL
+    static std::mutex g_device_mutex[64];
     std::lock_guard<std::mutex> device_turn(g_device_mutex[eng->device % 64]);
+#endif
     CK(cudaSetDevice(eng->device));
     const int Nt = eng->lay.Nt;
     const int64_t n_it = it_end - it_begin;
@@ -1448,7 +1511,9 @@ static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, t
         if (eng->opt_profile >= 2) fprintf(stderr, "e_cold %.3f e_warm %.3f eV, h_cold %.3f h_warm %.3f eV\n", eng->hp.e_cold, eng->hp.e_warm, eng->hp.h_cold, eng->hp.h_warm);
         for (int c = 1; c < N_ECLASS; ++c) eng->hp.e_class[c - 1] = (c < eng->opt_hot_classes) ? eng->opt_class_E[c - 1] : 1.0e300;
 
+#if defined(TRK_CONST_SYMBOL) || defined(TRK_HYBRID)
         CK(cudaMemcpyToSymbolAsync(c_p, &eng->hp, sizeof(DevP), 0, cudaMemcpyHostToDevice, eng->stream));
+#endif
         CK(cudaMemsetAsync(eng->d_u32, 0, eng->sl.u32_total * sizeof(uint32_t), eng->stream));
         CK(cudaMemsetAsync(eng->d_f64, 0, eng->sl.f64_total * sizeof(double), eng->stream));
         CK(cudaMemsetAsync(eng->d_qcount, 0, QC_WORDS * sizeof(uint32_t), eng->stream));
@@ -1457,8 +1522,8 @@ static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, t
           const Queue &stage = eng->qs[1].q[SP_ELECTRON];
           const int shi_lanes = (eng->opt_shi_lanes > 0 || eng->hp.n_shells + 1 > 32) ? std::max(1, eng->opt_shi_lanes) : 0;
           const uint32_t shi_warps = shi_lanes ? (nb + shi_lanes - 1) / shi_lanes : nb;
-          k_shi<<<(shi_warps + SHI_WARPS - 1) / SHI_WARPS, 32 * SHI_WARPS, 0, eng->stream>>>(stage, eng->qs[0], shi_lanes);
-          k_shi_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(stage, eng->qs[0]);
+          k_shi<<<(shi_warps + SHI_WARPS - 1) / SHI_WARPS, 32 * SHI_WARPS, 0, eng->stream>>>(TRK_PA(eng), stage, eng->qs[0], shi_lanes);
+          k_shi_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(TRK_PA(eng), stage, eng->qs[0]);
           prof_end(eng, pi); }
         CK(cudaGetLastError());
         eng->launches += 2;
@@ -1560,7 +1625,7 @@ static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, t
             }
             {   // the pairs of this generation's impact ionisations join the next generation
                 const int pi = prof_begin(eng, N_SPECIES + 1);       // timed with the finalisation kernels
-                k_ion_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(eng->qs[0].q[Q_ION], eng->qs[nxt]);
+                k_ion_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(TRK_PA(eng), eng->qs[0].q[Q_ION], eng->qs[nxt]);
                 k_ion_reset<<<1, 32, 0, eng->stream>>>(eng->d_qcount + QC_ION);
                 prof_end(eng, pi);
                 CK(cudaGetLastError());
@@ -1625,7 +1690,7 @@ static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, t
             eng->launches++;
             rc = launch_hot_electrons(eng, eng->qs_x, eng->qs[nxt]); if (rc) return rc;
             rc = launch_hot_vbholes(eng, eng->qs_x.q[SP_VBHOLE], eng->qs[nxt]); if (rc) return rc;
-            k_ion_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(eng->qs[0].q[Q_ION], eng->qs[nxt]);
+            k_ion_emit<<<eng->n_sm * 4, 256, 0, eng->stream>>>(TRK_PA(eng), eng->qs[0].q[Q_ION], eng->qs[nxt]);
             k_ion_reset<<<1, 32, 0, eng->stream>>>(eng->d_qcount + QC_ION);
             CK(cudaGetLastError());
             eng->launches += 2;
@@ -1645,7 +1710,7 @@ static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, t
             if (n_snap) {
                 const uint32_t grid = std::min<uint32_t>((n_snap + 255u) / 256u, (uint32_t)(eng->n_sm * bps));
                 const int pi = prof_begin(eng, N_SPECIES + 1);
-                k_snapshot<<<grid, 256, smem, eng->stream>>>(eng->qs[0].q[Q_SNAP], eng->qs[0], use_smem);
+                k_snapshot<<<grid, 256, smem, eng->stream>>>(TRK_PA(eng), eng->qs[0].q[Q_SNAP], eng->qs[0], use_smem);
                 prof_end(eng, pi);
                 CK(cudaGetLastError());
                 eng->launches++;
@@ -1664,10 +1729,10 @@ static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, t
             continue;                // re-run from the same b0 (histories are keyed by the global iteration index: same result)
         }
         const int pf = prof_begin(eng, N_SPECIES + 1);
-        k_iter_prefix<<<(nb + 127) / 128, 128, 0, eng->stream>>>(eng->fa);
+        k_iter_prefix<<<(nb + 127) / 128, 128, 0, eng->stream>>>(TRK_PA(eng), eng->fa);
         CK(cudaGetLastError());
         const int64_t njobs = fold_num_jobs(eng->hp);
-        k_fold<<<(unsigned)((njobs * 32 + 255) / 256), 256, 0, eng->stream>>>(eng->fa, njobs);
+        k_fold<<<(unsigned)((njobs * 32 + 255) / 256), 256, 0, eng->stream>>>(TRK_PA(eng), eng->fa, njobs);
         prof_end(eng, pf);
         CK(cudaGetLastError());
         eng->launches += 2;

@@ -66,7 +66,7 @@ extern "C" int trk3_dcs_eval(const trk3_dcs_ctx *ctx, const trk3_dcs_task *tasks
     int rc = TRK3_OK;
     const int n_osc = ctx->osc_off[ctx->n_sets];
     trk3_dcs_ctx d = *ctx;
-    double *d_osc = nullptr, *d_dos = nullptr, *d_hw = nullptr, *d_out = nullptr;
+    double *d_osc = nullptr, *d_dos = nullptr, *d_hw = nullptr, *d_out = nullptr, *d_scr = nullptr;
     int32_t *d_off = nullptr, *d_task_of = nullptr;
     trk3_dcs_task *d_tasks = nullptr;
     unsigned long long *d_next = nullptr;
@@ -91,6 +91,12 @@ extern "C" int trk3_dcs_eval(const trk3_dcs_ctx *ctx, const trk3_dcs_task *tasks
         if (ctx->n_k > 0) {
             CKD(cudaMemcpyAsync(d_dos, ctx->k, sizeof(double) * ctx->n_k, cudaMemcpyHostToDevice, st));
             CKD(cudaMemcpyAsync(d_dos + ctx->n_k, ctx->effm, sizeof(double) * ctx->n_k, cudaMemcpyHostToDevice, st));
+        }
+        if (ctx->screening >= 2) {       // what the screening of the elastic cross section reads (trk3_dcs_ctx::scr)
+            if (!ctx->scr || ctx->n_scr < 1) { rc = TRK3_E_INVALID; goto done; }
+            CKD(cudaMalloc(&d_scr, sizeof(double) * ctx->n_scr));
+            CKD(cudaMemcpyAsync(d_scr, ctx->scr, sizeof(double) * ctx->n_scr, cudaMemcpyHostToDevice, st));
+            d.scr = d_scr;
         }
         CKD(cudaMemcpyAsync(d_off, ctx->osc_off, sizeof(int32_t) * (ctx->n_sets + 1), cudaMemcpyHostToDevice, st));
         CKD(cudaMemcpyAsync(d_tasks, tasks, sizeof(trk3_dcs_task) * n_tasks, cudaMemcpyHostToDevice, st));
@@ -120,7 +126,7 @@ extern "C" int trk3_dcs_eval(const trk3_dcs_ctx *ctx, const trk3_dcs_task *tasks
         g_state.device_ms += ms; g_state.requests += n;
     }
 done:
-    cudaFree(d_osc); cudaFree(d_dos); cudaFree(d_off); cudaFree(d_tasks); cudaFree(d_hw); cudaFree(d_out); cudaFree(d_task_of); cudaFree(d_next);
+    cudaFree(d_scr); cudaFree(d_osc); cudaFree(d_dos); cudaFree(d_off); cudaFree(d_tasks); cudaFree(d_hw); cudaFree(d_out); cudaFree(d_task_of); cudaFree(d_next);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (st) cudaStreamDestroy(st);

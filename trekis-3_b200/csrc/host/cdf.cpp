@@ -113,6 +113,21 @@ Ctx make_ctx(const Case &c) {
     d.k = x.k ? x.k->data() : nullptr; d.effm = x.effm ? x.effm->data() : nullptr; d.n_k = x.k ? (int32_t)x.k->size() : 0;
     d.mass_from_dos = x.mass_from_dos ? 1 : 0; d.El_eff_mass = c.Matter.El_eff_mass;
     d.kind_DR = c.numpar.kind_of_DR; d.v_f = c.Matter.v_f; d.temp = c.Matter.temp;
+    // dynamical screening of the elastic cross section (CDF_elast_Zeff = 2 / 3): what get_screening_ff / get_screening_all read
+    d.screening = (c.numpar.kind_of_EMFP == 1 && c.numpar.CDF_elast_Zeff >= 2) ? c.numpar.CDF_elast_Zeff : 0;
+    d.vb_set = x.set0[0] + c.atoms[0].nshl() - 1;
+    flat->scr.assign(1, (double)c.atoms.size());
+    for (size_t i = 0; i < c.atoms.size(); ++i) {
+        const Atom &a = c.atoms[i];
+        double core = 0.0;
+        for (int sh = 0; sh < a.nshl() - (i == 0 ? 1 : 0); ++sh) core += a.Nel[(size_t)sh];
+        flat->scr.insert(flat->scr.end(), {(double)a.Zat, a.Pers, core, (double)x.set0[i], (double)a.nshl()});
+        std::array<double, 5> ff{};
+        if (a.Zat >= 1 && a.Zat <= (int)c.form_factor.size()) ff = c.form_factor[(size_t)a.Zat - 1];
+        flat->scr.insert(flat->scr.end(), ff.begin(), ff.end());
+    }
+    for (auto &a : c.atoms) for (int sh = 0; sh < a.nshl(); ++sh) { flat->scr.push_back(a.Nel[(size_t)sh]); flat->scr.push_back(a.Ip[(size_t)sh]); }
+    d.scr = flat->scr.data(); d.n_scr = (int32_t)flat->scr.size();
     x.flat = flat;
     return x;
 }
@@ -569,6 +584,20 @@ void get_single_pole(Case &c) {
         double ksum, fsum;
         sumrules(p, ksum, fsum, 1.0e-8, Omega);
         p.A[0] = N_at_mol / ksum;
+    } else if (c.numpar.CDF_elast_Zeff == 2 || c.numpar.CDF_elast_Zeff == 3) {
+        // user-provided phonon CDF with dynamical screening (:641-655): renormalised to the number of atoms per molecule -- the
+        // optical charge it was fitted with is replaced by the screened nuclear charge inside the cross section.  Done once:
+        // the tables may be built (or read from the cache) several times for one case
+        if (!c.phonon_renormalised) {
+            CDFosc &p = c.CDF_Phonon;
+            double sm = 0; for (auto &a : c.atoms) sm += a.Pers * a.Mass;
+            double Mean_Mass = sm * g_Mp / N_at_mol;
+            double Omega = w_plasma(1e6 * c.Matter.At_Dens / N_at_mol, Mean_Mass);
+            double ksum, fsum;
+            sumrules(p, ksum, fsum, 1.0e-8, Omega);
+            for (auto &A : p.A) A = A * N_at_mol / ksum;
+            c.phonon_renormalised = true;
+        }
     }
 }
 

@@ -234,7 +234,7 @@ static bool shell_ok(trk3h_case *h, int atom, int shell) {
 
 int trk3h_eval_TotIMFP(trk3h_case *h, double E, int atom, int shell, int kind, double *L, double *dEdx) {
     if (!shell_ok(h, atom, shell)) return TRK3_E_INVALID;
-    if (h->c.numpar.kind_of_CDF_ph == 1 && h->c.CDF_Phonon.A[0] == 0.0) get_single_pole(h->c);
+    if ((h->c.numpar.kind_of_CDF_ph == 1 && h->c.CDF_Phonon.A[0] == 0.0) || (h->c.numpar.CDF_elast_Zeff >= 2 && !h->c.phonon_renormalised)) get_single_pole(h->c);
     Ctx x = make_ctx(h->c);
     double S, d; TotIMFP(x, E, atom, shell, kind, S, d, nullptr);
     if (L) *L = S;
@@ -243,11 +243,23 @@ int trk3h_eval_TotIMFP(trk3h_case *h, double E, int atom, int shell, int kind, d
 }
 int trk3h_eval_EMFP(trk3h_case *h, double E, int kind, double *L, double *dEdx) {
     if (!h) return TRK3_E_INVALID;
-    if (h->c.numpar.kind_of_CDF_ph == 1 && h->c.CDF_Phonon.A[0] == 0.0) get_single_pole(h->c);
+    if ((h->c.numpar.kind_of_CDF_ph == 1 && h->c.CDF_Phonon.A[0] == 0.0) || (h->c.numpar.CDF_elast_Zeff >= 2 && !h->c.phonon_renormalised)) get_single_pole(h->c);
     Ctx x = make_ctx(h->c);
     double S, d; Elastic_cross_section(x, E, kind, S, d, nullptr);
     if (L) *L = S;
     if (dEdx) *dEdx = d;
+    return TRK3_OK;
+}
+// one value of Diff_cross_section_phonon (Cross_sections.f90:3142-3300) for an electron: the integrand of Tot_EMFP, with the
+// screening the case's CDF_elast_Zeff asks for; *phonon_A0 receives the (possibly renormalised) amplitude of the first phonon oscillator
+int trk3h_eval_dcs_phonon(trk3h_case *h, double Ee, double hw, double *value, double *phonon_A0) {
+    if (!h || !value) return TRK3_E_INVALID;
+    if ((h->c.numpar.kind_of_CDF_ph == 1 && h->c.CDF_Phonon.A[0] == 0.0) || (h->c.numpar.CDF_elast_Zeff >= 2 && !h->c.phonon_renormalised)) get_single_pole(h->c);
+    Ctx x = make_ctx(h->c);
+    double sm = 0, sp = 0; for (auto &a : h->c.atoms) { sm += a.Pers * a.Mass; sp += a.Pers; }
+    trk3_dcs_task t{TRK3_DCS_PHONON, x.set_phonon, Ee, 1.0, sm * g_Mp / sp, h->c.Matter.temp, 1.0};
+    *value = trk3dcs::eval_request(x.flat->d, t, hw);
+    if (phonon_A0) *phonon_A0 = h->c.CDF_Phonon.A[0];
     return TRK3_OK;
 }
 int trk3h_eval_SHI(trk3h_case *h, double E, int atom, int shell, double *inv_L, double *dEdx, double *Zeff) {

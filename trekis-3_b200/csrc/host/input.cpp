@@ -457,7 +457,27 @@ bool read_case(const std::string &dir, Case &c, std::string &err) {
     if (c.SHI.Kind_ion != 0 && c.SHI.Kind_ion != 1) c.SHI.Kind_ion = 0;       // anything but 1 is the point charge (select case default)
     if (c.numpar.kind_of_DR == 4) { err = "Delta-CDF (kind_of_DR=4) is not supported"; return false; }
     if (c.numpar.kind_of_EMFP == 2) { err = "DSF elastic cross sections (kind_of_EMFP=2) need INPUT_DSF files; not supported"; return false; }
-    if (c.numpar.CDF_elast_Zeff >= 2) { err = "CDF_elast_Zeff=2/3 (form-factor / CDF screening) is not supported yet"; return false; }
+    if (c.numpar.CDF_elast_Zeff == 2) {
+        // read_form_factors, Reading_files_and_parameters.f90:605-615, 867-907: one header line, then row Z = a1..a5 of element Z
+        const std::string p = dir + "/INPUT_EADL/Atomic_form_factors.dat";
+        std::ifstream f(p);
+        if (!f) { err = "CDF_elast_Zeff=2 needs " + p; return false; }
+        std::string line;
+        std::getline(f, line);
+        while (std::getline(f, line)) {
+            std::istringstream is(line);
+            std::array<double, 5> a{};
+            if (!(is >> a[0] >> a[1] >> a[2] >> a[3] >> a[4])) { if (line.find_first_not_of(" \t\r") == std::string::npos) continue; err = "could not read a line of " + p; return false; }
+            c.form_factor.push_back(a);
+        }
+        for (auto &a : c.atoms) if (a.Zat < 1 || a.Zat > (int)c.form_factor.size()) { err = "no form factor for Z=" + std::to_string(a.Zat) + " in " + p; return false; }
+    }
+    if (c.numpar.CDF_elast_Zeff == 3) {
+        // get_screening via construct_CDF(..., 1, size(Target_atoms(i)%Ip), ...) (Cross_sections.f90:3253) addresses shell number
+        // "shells of atom i" of the FIRST atom: out of bounds in the reference when another atom has more shells than the first
+        for (auto &a : c.atoms) if (a.nshl() > c.atoms[0].nshl()) { err = "CDF_elast_Zeff=3: an atom has more shells than the first atom (the reference reads out of bounds)"; return false; }
+    }
+    if (c.numpar.CDF_elast_Zeff > 3 || c.numpar.CDF_elast_Zeff < 0) c.numpar.CDF_elast_Zeff = 0;   // select case default: Barkas-like charge
     if (c.numpar.CS_method != 1) { err = "only 'grid 1' (tabulated differential cross sections, the reference default) is supported"; return false; }
     if (c.SHI.Zat > 0) {
         // Reading_files_and_parameters.f90:509-535

@@ -8,6 +8,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <array>
 #include <memory>
 #include <string>
 #include <vector>
@@ -100,6 +101,7 @@ struct Case {                       // everything Read_input_file + MAIN.f90:120
     CDFosc CDF_Phonon;
     DOS dos;
     std::vector<std::string> input_lines;   // verbatim copy of INPUT_PARAMETERS.txt (Save_output copies it)
+    std::vector<std::array<double, 5>> form_factor;   // Matter%form_factor: row Z-1 = coefficients a1..a5 of element Z (CDF_elast_Zeff = 2)
     // tables (MAIN.f90:166-238)
     std::vector<std::vector<MFP>> SHI_MFP, diff_SHI_MFP, Total_el_MFPs, Total_Hole_MFPs, Total_Photon_MFPs;
     MFP Elastic_MFP, Elastic_Hole_MFP;
@@ -108,6 +110,7 @@ struct Case {                       // everything Read_input_file + MAIN.f90:120
     int Lowest_Ip_At = 0, Lowest_Ip_Shl = 0;  // 0-based
     std::vector<double> Out_R, Out_V;
     bool tables_built = false;
+    bool phonon_renormalised = false;       // get_single_pole has rescaled the user's phonon CDF (CDF_elast_Zeff = 2 / 3)
     std::vector<std::string> warnings;
     int n_shells() const { int n = 0; for (auto &a : atoms) n += a.nshl(); return n; }
 };
@@ -140,7 +143,7 @@ void eadl_check_shell(const Eadl &db, Atom &a, int k, bool include_photons, std:
 
 // ---- physics of the table builder (cdf.cpp)
 struct CtxFlat {        // storage behind the trk3_dcs_ctx handed to the shared integrands / the GPU evaluator
-    std::vector<double> E0, A, G;
+    std::vector<double> E0, A, G, scr;
     std::vector<int32_t> off;
     trk3_dcs_ctx d{};
 };

@@ -44,6 +44,7 @@ def _host():
         PD = C.POINTER(C.c_double)
         lib.trk3h_eval_TotIMFP.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, PD, PD]
         lib.trk3h_eval_EMFP.argtypes = [C.c_void_p, C.c_double, C.c_int, PD, PD]
+        lib.trk3h_eval_dcs_phonon.argtypes = [C.c_void_p, C.c_double, C.c_double, PD, PD]
         lib.trk3h_eval_SHI.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, PD, PD, PD]
         lib.trk3h_eval_photon.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, PD]
         lib.trk3h_sumrules.argtypes = [C.c_void_p, C.c_int, C.c_int, PD, PD]
@@ -292,6 +293,13 @@ class Case:
         L, d = C.c_double(), C.c_double()
         _host().trk3h_eval_EMFP(self._h, E, kind, C.byref(L), C.byref(d))
         return L.value, d.value
+
+    def eval_dcs_phonon(self, Ee, hw):
+        """(value of Diff_cross_section_phonon for an electron, amplitude of the first phonon oscillator as used)"""
+        v, a0 = C.c_double(), C.c_double()
+        if _host().trk3h_eval_dcs_phonon(self._h, Ee, hw, C.byref(v), C.byref(a0)) != 0:
+            raise RuntimeError("trk3h_eval_dcs_phonon failed")
+        return v.value, a0.value
 
     def eval_SHI(self, E, atom, shell):
         s, d, z = C.c_double(), C.c_double(), C.c_double()
