@@ -1,4 +1,6 @@
-"""One C2 batch through the engine (for `ncu --kernel-name ... --launch-skip ...`). Usage: ncu_target.py [CFG] [NIT] [opt=val ...]"""
+"""One batch through the engine (for `ncu --kernel-name ... --launch-skip ...`). Usage: ncu_target.py [CFG] [NIT] [opt=val ...]
+Prints: device_ms total_events n_waves kernel_launches; with NCU_STATS_OUT=<file> the run statistics go there as JSON."""
+import json
 import os
 import sys
 
@@ -16,3 +18,7 @@ case.build_tables(shi_window_only=True, cache_dir=os.path.join(ROOT, ".table_cac
 eng = tk.Engine(case, **opts)
 st = eng.run_device(0, nit)
 print(st["device_ms"], st["total_events"], st["n_waves"], st["kernel_launches"])
+if os.environ.get("NCU_STATS_OUT"):
+    with open(os.environ["NCU_STATS_OUT"], "w") as f:
+        json.dump({"config": cfg, "iterations": nit, "options": opts, "events": st["events"], "cold_events": st["cold_events"],
+                   "warm_events": st["warm_events"], "n_waves": st["n_waves"], "kernel_launches": st["kernel_launches"]}, f)
