@@ -177,3 +177,56 @@ def test_sub_shell_windows_and_next_designator():
         assert look(912, 7) == 2.0 * (5 + 6 + 7)                               # electrons: summed over the same window
         assert look(912, 1) == 2.0 and look(913, 63) == 1e22                   # valence band: 'infinite' (:662)
         assert lib.trk3h_eadl_lookup(p.encode(), 14, 913, 1, C.byref(v)) != 0  # element not in the file
+
+
+# ---- files that leave their shells to the atomic database: chemical formula, single-pole CDF, VALENCE / PHONON keywords --------
+SP_CDF = """Quartz from the atomic database
+SiO2						! chemical formula instead of an element list
+2.65	5900.0	5.0	8.9	! density [g/cm^3], speed of sound [m/s], fermi energy [eV], band gap [eV]
+"""
+
+
+def test_chemical_formula_file_is_built_from_the_atomic_database(tmp_path):
+    """Decompose_compound (Dealing_with_EADL.f90:28-198) + the all-shells branch of check_atomic_parameters (:374-392) +
+    make_valence_band (Reading_files_and_parameters.f90:1989-2137) + the electronic part of get_single_pole
+    (Cross_sections.f90:570-633): 'SiO2' -> Si (Z = 14) first, O second; every EADL sub-shell becomes a shell; the outermost ones
+    holding the valence electrons (4 of Si, 6 of O: INPUT_atomic_data.dat) are merged into ONE valence band on the first atom;
+    every shell gets one oscillator whose k-sum rule gives the electrons of the shell."""
+    d = run_dir(tmp_path, cdf_text=SP_CDF, eadl={14: SI, 8: OX}, config="C2")
+    case = tk.Case.load(d)
+    assert case.get("n_atoms") == 2 and case.get("kind_of_CDF") == 1 and case.get("kind_of_CDF_ph") == 1
+    # Si: K, L1, L2, L3 core (M1 + M2 = 2 + 2 valence electrons) + the valence band; O: K core (L1..L3 = 6 valence electrons)
+    assert case.get("nshl:0") == 5 and case.get("nshl:1") == 1
+    assert case.get("Zat:0") == 14 and case.get("Zat:1") == 8
+    n_vb = 4 * 1 + 6 * 2
+    assert case.get("atom:0:4:Nel") == pytest.approx(n_vb) and case.get("atom:0:4:Ip") == pytest.approx(8.9)
+    assert case.get("atom:0:0:Ip") == pytest.approx(1838.9) and case.get("atom:1:0:Ip") == pytest.approx(538.0)
+    assert case.get("atom:0:0:Auger") == pytest.approx(t_fs(0.4), rel=1e-12) and case.get("atom:0:4:Auger") == 1.0e26
+    assert case.get("atom:0:0:Radiat") == pytest.approx(t_fs(0.02), rel=1e-12)          # photons on in C2
+    # single-pole CDFs: E0 = Ip + 10 eV for the core shells, Gamma = E0, and A from the k-sum rule
+    case.build_tables(shi_window_only=True)
+    for at, sh, nel in ((0, 0, 2.0), (0, 1, 2.0), (0, 3, 4.0), (1, 0, 2.0 * 2)):   # k-sum per MOLECULE: electrons of the shell x atoms of the kind
+        ks, _ = case.sumrules(at, sh)
+        assert ks == pytest.approx(nel, rel=1e-9), (at, sh)
+    ks, _ = case.sumrules(0, 4)
+    assert ks == pytest.approx(n_vb, rel=1e-9)                                      # valence band, per molecule
+    assert case.reference_cache_name("el_imfp").startswith("OUTPUT_Electron_IMFPs_Free_spCDF")
+    a = case.table_arrays()
+    assert a["ei_L"].shape[0] == 6 and np.all(a["ei_L"] > 0)
+
+
+def test_valence_and_phonon_keywords(tmp_path):
+    text = SP_CDF + "VALENCE\n2 63 8.9 16.0 1.0e23\n22.0 200.0 10.0\n35.0 100.0 20.0\nPHONON\n1\n0.12 0.002 0.01\n"
+    case = tk.Case.load(run_dir(tmp_path, cdf_text=text, eadl={14: SI, 8: OX}, config="C2"))
+    assert case.get("kind_of_CDF") == 1 and case.get("kind_of_CDF_ph") == 0
+    assert case.get("phonon_E0") == pytest.approx(0.12)
+    case.build_tables(shi_window_only=True)
+    ks_user, _ = case.sumrules(0, 4)
+    assert ks_user != pytest.approx(16.0, rel=1e-3)                                 # the user's valence CDF is taken as it is
+    ks, _ = case.sumrules(0, 0)
+    assert ks == pytest.approx(2.0, rel=1e-9)                                       # the core shells are still single-pole
+
+
+def test_database_files_are_refused_without_the_database(tmp_path):
+    with pytest.raises(RuntimeError, match="EADL2023.ALL"):
+        tk.Case.load(run_dir(tmp_path, cdf_text=SP_CDF, eadl=None, config="C2"))

@@ -1488,6 +1488,7 @@ static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, t
     CK(cudaMemsetAsync(eng->d_counters, 0, n_counters * sizeof(unsigned long long), eng->stream));
     uint64_t waves = 0; const uint64_t launches0 = eng->launches;
     std::vector<double> h_diffS, h_totE; std::vector<uint32_t> h_diffN;
+    std::vector<unsigned long long> h_c(n_counters, 0ull);
     uint32_t *heads = eng->d_qcount + QC_HEAD;
     CK(cudaEventRecord(eng->ev0, eng->stream));
     int retries = 0;
@@ -1743,6 +1744,11 @@ static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, t
         CK(cudaMemcpyAsync(h_diffS.data(), eng->hp.it.diffS, n * sizeof(double), cudaMemcpyDeviceToHost, eng->stream));
         CK(cudaMemcpyAsync(h_diffN.data(), eng->hp.it.diffN, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, eng->stream));
         CK(cudaMemcpyAsync(h_totE.data(), eng->fa.totE, n * sizeof(double), cudaMemcpyDeviceToHost, eng->stream));
+        // the run's counters travel with the last batch's results: no further host round trip after this one
+        if (b0 + nb >= it_end) {
+            CK(cudaMemcpyAsync(h_c.data(), eng->d_counters, n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToHost, eng->stream));
+            CK(cudaEventRecord(eng->ev1, eng->stream));
+        }
         CK(cudaStreamSynchronize(eng->stream));
         for (uint32_t il = 0; il < nb; ++il) for (int i = 0; i < Nt; ++i) {
             const size_t o = (size_t)il * Nt + i;
@@ -1762,12 +1768,13 @@ static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, t
         const int nrc = nccl_rt::api().AllReduce(eng->d_tally, eng->d_tally, (size_t)eng->lay.total, nccl_rt::kFloat64, nccl_rt::kSum, eng->comm, eng->stream);
         if (nrc != nccl_rt::kSuccess) { eng->err = std::string("ncclAllReduce: ") + nccl_rt::api().GetErrorString(nrc); return TRK3_E_CUDA; }
     }
-    CK(cudaEventRecord(eng->ev1, eng->stream));
-    std::vector<unsigned long long> h_c(n_counters);
-    CK(cudaMemcpyAsync(h_c.data(), eng->d_counters, n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToHost, eng->stream));
-    CK(cudaStreamSynchronize(eng->stream));
+    // No synchronisation here: the last two operations (the Out_diff_coeff update and the all-reduce) stay in flight on the
+    // engine's stream when the call returns, so that a rank does not sit in cudaStreamSynchronize until the slowest rank has
+    // reached its all-reduce and the caller's next call is already queued behind them.  Whoever reads the tally buffer does so
+    // in stream order (trk3_mc_download_tallies synchronises; a framework that owns the stream is ordered by it).
+    // device_ms = the Monte-Carlo section up to the folded tallies.
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
+    if (it_end > it_begin) CK(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
     prof_collect(eng);
     trk3_stats st; std::memset(&st, 0, sizeof st);
     for (int q = 0; q < TRK3_N_EVENT_CLASSES; ++q) st.events[q] = h_c[q];

@@ -566,9 +566,38 @@ void sumrules(const CDFosc &o, double &ksum, double &fsum, double x_min, double 
 }
 
 void get_single_pole(Case &c) {
-    // Part 1 (electronic single-pole CDF) only applies to files without CDF, which need EADL data and are
-    // rejected by the reader.  Part 2: phonon CDF, Cross_sections.f90:639-686.
+    // Cross_sections.f90:554-686.  Part 1, electronic single-pole CDF: files that leave their shells to the atomic database
+    // (kind_of_CDF = 1; they need EADL2023.ALL).  Part 2: phonon CDF.
     double N_at_mol = 0; for (auto &a : c.atoms) N_at_mol += a.Pers;
+    if (c.numpar.kind_of_CDF == 1) {
+        // Part 1 (:570-633): one oscillator per shell.  Valence band: E0 = plasmon energy of the valence electrons, Gamma = E0;
+        // core shells: E0 = Ip + 10 eV, Gamma = E0; A from the k-sum rule (electrons of the shell).
+        for (size_t i = 0; i < c.atoms.size(); ++i) {
+            Atom &a = c.atoms[i];
+            const int N_shl = a.nshl();
+            for (int j = 0; j < N_shl; ++j) {
+                CDFosc &o = a.Ritchi[(size_t)j];
+                double ksum, fsum;
+                if (i == 0 && j == N_shl - 1) {
+                    if (c.numpar.VB_CDF_defined) continue;
+                    const double NVB = a.Nel[(size_t)j] / N_at_mol;
+                    double Omega = w_plasma(1e6 * c.Matter.At_Dens * NVB);
+                    o.E0.assign(1, std::sqrt((g_h / g_e) * (g_h / g_e) * Omega));
+                    o.Gamma.assign(1, o.E0[0]); o.A.assign(1, 1.0);
+                    Omega = w_plasma(1e6 * c.Matter.At_Dens);
+                    sumrules(o, ksum, fsum, a.Ip[(size_t)j], Omega);
+                    o.A[0] = NVB / ksum;
+                } else {
+                    const double NVB = a.Nel[(size_t)j], contrib = a.Pers / N_at_mol;
+                    o.E0.assign(1, a.Ip[(size_t)j] + 10.0);
+                    o.Gamma.assign(1, o.E0[0]); o.A.assign(1, 1.0);
+                    const double Omega = w_plasma(1e6 * c.Matter.At_Dens * contrib);
+                    sumrules(o, ksum, fsum, a.Ip[(size_t)j], Omega);
+                    o.A[0] = NVB / ksum;
+                }
+            }
+        }
+    }
     if (c.numpar.kind_of_CDF_ph == 1) {
         double qdebye = std::pow(6.0 * g_Pi * g_Pi * (c.Matter.At_Dens * 1e6), 0.33333333);
         double E_debye = g_h * c.Matter.Vsound * qdebye / g_e;

@@ -175,6 +175,9 @@ double trk3h_get(trk3h_case *h, const char *key) {
     if (k == "shi_Zeff") return c.SHI.Zeff;
     if (k == "include_photons") return c.numpar.include_photons ? 1 : 0;
     if (k == "kind_of_CDF_ph") return c.numpar.kind_of_CDF_ph;
+    if (k == "kind_of_CDF") return c.numpar.kind_of_CDF;
+    if (k.rfind("nshl:", 0) == 0) { int j = atoi(key + 5); return (j >= 0 && j < (int)c.atoms.size()) ? (double)c.atoms[(size_t)j].nshl() : std::nan(""); }
+    if (k.rfind("Zat:", 0) == 0) { int j = atoi(key + 4); return (j >= 0 && j < (int)c.atoms.size()) ? (double)c.atoms[(size_t)j].Zat : std::nan(""); }
     if (k == "n_atoms") return (double)c.atoms.size();
     if (k == "n_dos") return (double)c.dos.E.size();
     if (k == "Num_th") return c.Num_th;

@@ -203,8 +203,99 @@ bool read_input_parameters(const std::string &dir, Case &c, const std::vector<PT
     return true;
 }
 
-// reading_material_parameters, Reading_files_and_parameters.f90:1185-1644 (full-CDF branch;
-// the single-pole/EADL-only branch needs EADL2023.ALL and is reported as unsupported)
+// Decompose_compound + sort_elements_in_chem_formula, Dealing_with_EADL.f90:28-198: "Al2O3" -> (Al, 2), (O, 3), heaviest first.
+// A digit extends the count of the current element, an upper-case letter starts a new element, lower-case letters continue
+// its name; any other character is skipped with a warning, as the reference does.
+bool decompose_compound(const std::string &formula, const std::vector<PT> &pt, std::vector<Atom> &atoms, std::vector<std::string> &warnings, std::string &err) {
+    std::vector<std::pair<std::string, double>> el;
+    int C = 0;
+    std::string cur;
+    auto close = [&]() { if (!cur.empty()) el.push_back({cur, C <= 0 ? 1.0 : (double)C}); };
+    for (char ch : formula) {
+        if (ch >= '0' && ch <= '9') C = C * 10 + (ch - '0');
+        else if (ch >= 'A' && ch <= 'Z') { close(); C = 0; cur = std::string(1, ch); }
+        else if (ch >= 'a' && ch <= 'z') cur += ch;
+        else if (ch != ' ' && ch != '\t') warnings.push_back(std::string("Symbol ") + ch + " in the compound formula could not be identified");
+    }
+    close();
+    if (el.empty()) { err = "no element found in the chemical formula '" + formula + "'"; return false; }
+    atoms.assign(el.size(), Atom{});
+    for (size_t i = 0; i < el.size(); ++i) {
+        int Z = 0;
+        for (size_t z = 1; z < pt.size(); ++z) {
+            std::string nm = pt[z].name;
+            while (!nm.empty() && nm.back() == ' ') nm.pop_back();
+            if (!nm.empty() && nm == el[i].first) { Z = (int)z; break; }
+        }
+        if (Z == 0) { err = el[i].first + " - such an element was not found in our database..."; return false; }
+        atoms[i].Zat = Z; atoms[i].Pers = el[i].second; atoms[i].Name = el[i].first; atoms[i].Full_Name = pt[(size_t)Z].full; atoms[i].Mass = pt[(size_t)Z].mass;
+    }
+    for (int j = (int)atoms.size() - 1; j >= 1; --j) {       // bubble sort, descending atomic number (:160-193)
+        bool swapped = false;
+        for (int i = 0; i < j; ++i) if (atoms[(size_t)i].Zat < atoms[(size_t)i + 1].Zat) { std::swap(atoms[(size_t)i], atoms[(size_t)i + 1]); swapped = true; }
+        if (!swapped) break;
+    }
+    return true;
+}
+
+// check_atomic_parameters, ALL-shells branch (Dealing_with_EADL.f90:374-392) with READ_EADL_TYPE_FILE_int / _real (:506-535,
+// :661-674): every sub-shell EADL lists for the element, in the order of the file.  The real-valued blocks are copied BY
+// POSITION (the I = 921 / 922 blocks list fewer sub-shells than I = 912: the outer ones keep the 1e-24 they were allocated with,
+// which the conversion below turns into a practically infinite decay time).
+bool eadl_all_shells(const Eadl &db, Atom &a, bool include_photons, std::string &err) {
+    const Eadl::Block *b = db.find(a.Zat, 912);
+    if (!b || b->rows.empty()) { err = "element Z=" + std::to_string(a.Zat) + " is not in the EADL database"; return false; }
+    const size_t n = b->rows.size();
+    a.Shell_name.assign(n, ""); a.Shl_num.assign(n, 0); a.PQN.assign(n, 0); a.Nel.assign(n, 0.0);
+    a.Ip.assign(n, 0.0); a.Ek.assign(n, 0.0); a.Radiat.assign(n, 1.0e-24); a.Auger.assign(n, 1.0e-24);
+    a.KOCS.assign(n, 0); a.KOCS_SHI.assign(n, 0); a.Ritchi.assign(n, CDFosc{});
+    for (size_t i = 0; i < n; ++i) {
+        a.Nel[i] = b->rows[i].val; a.Shl_num[i] = (int)b->rows[i].des;
+        define_PQN(a.Shl_num[i], a.Shell_name[i], a.PQN[i]);
+    }
+    auto fill = [&](int I, std::vector<double> &arr) {
+        const Eadl::Block *r = db.find(a.Zat, I);
+        if (!r) { std::fill(arr.begin(), arr.end(), 1.0e-30); return; }          // "if the value does not exist"
+        for (size_t i = 0; i < r->rows.size() && i < arr.size(); ++i) arr[i] = r->rows[i].val * 1.0e6;
+    };
+    fill(913, a.Ip); fill(914, a.Ek); fill(921, a.Radiat); fill(922, a.Auger);
+    for (size_t j = 0; j < n; ++j) {
+        a.Auger[j] = 1.0e15 * g_h / (g_e * a.Auger[j]);
+        a.Radiat[j] = (a.Shl_num[j] >= 63 || !include_photons) ? 1.0e23 : 1.0e15 * g_h / (g_e * a.Radiat[j]);
+    }
+    return true;
+}
+
+// make_valence_band + copy_atomic_data_back, Reading_files_and_parameters.f90:1989-2137: the outermost atomic shells that hold the
+// element's valence electrons (INPUT_atomic_data.dat, column 5) are merged into ONE valence band, kept as the last shell of the
+// first element: N_e_VB electrons per molecule, ionisation potential = band gap.
+void make_valence_band(std::vector<Atom> &atoms, const std::vector<PT> &pt, Solid &Matter) {
+    std::vector<size_t> n_core(atoms.size(), 0);
+    double N_e_VB = 0.0;
+    for (size_t i = 0; i < atoms.size(); ++i) {
+        double N_el = 0.0;
+        int j = atoms[i].nshl();
+        while (N_el < pt[(size_t)atoms[i].Zat].nvb && j > 0) { N_el += atoms[i].Nel[(size_t)j - 1]; --j; }
+        n_core[i] = (size_t)j;
+        N_e_VB += N_el * atoms[i].Pers;
+    }
+    Matter.N_VB_el = N_e_VB;
+    for (size_t i = 0; i < atoms.size(); ++i) {
+        Atom &a = atoms[i];
+        const size_t Shl = n_core[i] + (i == 0 ? 1 : 0);
+        a.Shell_name.resize(Shl); a.Shl_num.resize(Shl); a.Nel.resize(Shl); a.Ip.resize(Shl); a.Ek.resize(Shl); a.Auger.resize(Shl);
+        a.Radiat.resize(Shl); a.PQN.resize(Shl); a.KOCS.resize(Shl); a.KOCS_SHI.resize(Shl);
+        a.Ritchi.assign(Shl, CDFosc{});
+        if (i == 0) {
+            const size_t v = Shl - 1;
+            a.Shell_name[v] = "Valence"; a.Shl_num[v] = 63; a.Nel[v] = N_e_VB; a.Ip[v] = Matter.Egap; a.Ek[v] = 0.0;
+            a.Auger[v] = 1.0e26; a.Radiat[v] = 1.0e27;
+        }
+    }
+}
+
+// reading_material_parameters, Reading_files_and_parameters.f90:1185-1644: full-CDF files, and (with EADL2023.ALL at hand) files
+// that give a chemical formula and / or leave the shells to the atomic database (single-pole CDF, VALENCE / PHONON keywords)
 bool read_cdf(const std::string &dir, Case &c, const std::vector<PT> &pt, std::string &err) {
     std::string name = c.numpar.CDF_file.empty() ? (c.Material_name + ".cdf") : c.numpar.CDF_file;
     std::string path = dir + "/INPUT_CDF/" + name;
@@ -227,11 +318,16 @@ bool read_cdf(const std::string &dir, Case &c, const std::vector<PT> &pt, std::s
     }
     int N = 0;
     if (read_list(f, 1, t) != 0) return bad("number of elements");
-    if (!parse_int(t[0], N)) return bad("chemical-formula .cdf files need EADL data (Decompose_compound); not supported");
+    const bool formula = !parse_int(t[0], N);
+    if (formula) {                                                   // a chemical formula instead of an element list (:1291-1308)
+        c.Matter.Chem = t[0];
+        std::string e;
+        if (!decompose_compound(t[0], pt, c.atoms, c.warnings, e)) return bad("chemical-formula line: " + e);
+        N = (int)c.atoms.size();
+    }
     if (N < 1 || N > TRK3_MAX_ATOMS) return bad("unsupported number of elements");
-    c.atoms.assign(N, Atom{});
-    c.Matter.Chem.clear();
-    for (int j = 0; j < N; ++j) {
+    if (!formula) { c.atoms.assign(N, Atom{}); c.Matter.Chem.clear(); }
+    for (int j = 0; j < N && !formula; ++j) {
         Atom &a = c.atoms[j];
         if (read_list(f, 2, t) != 0 || !parse_int(t[0], a.Zat) || !parse_real(t[1], a.Pers)) return bad("element line");
         if (a.Zat <= 0 || a.Zat >= (int)pt.size() || pt[a.Zat].mass <= 0) return bad("unknown element");
@@ -257,16 +353,6 @@ bool read_cdf(const std::string &dir, Case &c, const std::vector<PT> &pt, std::s
         c.Matter.At_Dens = 1.0e-3 * c.Matter.Dens / (g_Mp * sm / sp);
         c.Matter.v_f = std::sqrt(2.0 * c.Matter.E_F / g_me);
     }
-    // number of shells of the first element, or a keyword (single-pole mode)
-    if (!f.read_line(s)) return bad("shell block");
-    {
-        auto tk = tokens(s); int Shl;
-        if (tk.empty() || !parse_int(tk[0], Shl))
-            return bad("single-pole / VALENCE / PHONON keyword files need EADL2023.ALL (check_atomic_parameters, "
-                       "Dealing_with_EADL.f90:312) which is not available; not supported");
-        f.backspace();
-    }
-    c.numpar.kind_of_CDF = 0;
     // EADL2023.ALL is optional here (the reference refuses to start without it, Check_EPICS_files :867-892)
     Eadl eadl;
     bool have_eadl = false;
@@ -278,6 +364,62 @@ bool read_cdf(const std::string &dir, Case &c, const std::vector<PT> &pt, std::s
             have_eadl = true;
         }
     }
+    // number of shells of the first element, or no number: the shells come from the atomic database (single-pole CDF)
+    if (!f.read_line(s)) s.clear(), f.pos = f.l.size();
+    {
+        auto tk = tokens(s); int Shl;
+        if (tk.empty() || !parse_int(tk[0], Shl)) {
+            // SP_CDF branch (:1349-1488): single-pole CDFs for every shell, optionally a user-given valence-band CDF (VALENCE) and
+            // phonon CDF (PHONON)
+            c.numpar.kind_of_CDF = 1; c.numpar.kind_of_CDF_ph = 1; c.numpar.VB_CDF_defined = false;
+            CDFosc vb;
+            if (!f.eof() || !tk.empty()) f.backspace();
+            while (f.read_line(s)) {
+                size_t a0 = s.find_first_not_of(" \t");
+                if (a0 == std::string::npos) continue;
+                const std::string key = s.substr(a0, 3);
+                if (key == "VAL" || key == "Val" || key == "val") {
+                    int ncdf = 0, shl_num = 0; double r3[3];
+                    c.numpar.VB_CDF_defined = true;
+                    if (read_list(f, 5, t) == 0 && parse_int(t[0], ncdf) && parse_int(t[1], shl_num) && parse_real(t[2], r3[0]) && parse_real(t[3], r3[1]) && parse_real(t[4], r3[2]) && ncdf > 0) {
+                        vb.E0.resize((size_t)ncdf); vb.A.resize((size_t)ncdf); vb.Gamma.resize((size_t)ncdf);
+                        for (int l = 0; l < ncdf; ++l)
+                            if (read_list(f, 3, t) != 0 || !parse_real(t[0], vb.E0[(size_t)l]) || !parse_real(t[1], vb.A[(size_t)l]) || !parse_real(t[2], vb.Gamma[(size_t)l])) {
+                                c.warnings.push_back("Could not interprete VB CDF parameters. Using single-pole approximation."); c.numpar.VB_CDF_defined = false; break;
+                            }
+                    } else { c.warnings.push_back("Could not interprete VB CDF parameters. Using single-pole approximation."); c.numpar.VB_CDF_defined = false; }
+                } else if (key == "PHO" || key == "Pho" || key == "pho") {
+                    int ncdf = 0;
+                    c.numpar.kind_of_CDF_ph = 0;
+                    if (read_list(f, 1, t) != 0 || !parse_int(t[0], ncdf) || ncdf < 1) { c.numpar.kind_of_CDF_ph = 1; continue; }
+                    c.CDF_Phonon.E0.resize((size_t)ncdf); c.CDF_Phonon.A.resize((size_t)ncdf); c.CDF_Phonon.Gamma.resize((size_t)ncdf);
+                    for (int l = 0; l < ncdf; ++l)
+                        if (read_list(f, 3, t) != 0 || !parse_real(t[0], c.CDF_Phonon.E0[(size_t)l]) || !parse_real(t[1], c.CDF_Phonon.A[(size_t)l]) || !parse_real(t[2], c.CDF_Phonon.Gamma[(size_t)l])) {
+                            c.warnings.push_back("Could not interprete phonon CDF parameters. Using single-pole approximation."); c.numpar.kind_of_CDF_ph = 1; break;
+                        }
+                }
+            }
+            if (!have_eadl)
+                return bad("files that leave their shells to the atomic database (single-pole CDF; chemical-formula / VALENCE / PHONON keyword form) "
+                           "need INPUT_EADL/EADL2023.ALL (check_atomic_parameters, Dealing_with_EADL.f90:374), which is absent");
+            for (auto &a : c.atoms) { std::string e; if (!eadl_all_shells(eadl, a, c.numpar.include_photons, e)) return bad(e); }
+            make_valence_band(c.atoms, pt, c.Matter);
+            for (size_t j = 0; j < c.atoms.size(); ++j) {
+                Atom &a = c.atoms[j];
+                if (a.nshl() > TRK3_MAX_SHELLS) return bad("too many shells");
+                for (int k = 0; k < a.nshl(); ++k) {
+                    a.KOCS[(size_t)k] = 1; a.KOCS_SHI[(size_t)k] = 1;
+                    if (j == 0 && k == a.nshl() - 1 && c.numpar.VB_CDF_defined) a.Ritchi[(size_t)k] = vb;
+                    else { a.Ritchi[(size_t)k].E0.assign(1, 0.0); a.Ritchi[(size_t)k].A.assign(1, 0.0); a.Ritchi[(size_t)k].Gamma.assign(1, 0.0); }
+                    if (a.Ip[(size_t)k] < 1.0e-1 && !(j == 0 && k == a.nshl() - 1)) a.Ip[(size_t)k] = a.Ip[(size_t)k];      // (the SP branch keeps EADL's values as they are)
+                }
+            }
+            if (c.numpar.kind_of_CDF_ph == 1) { c.CDF_Phonon.E0.assign(1, 0.0); c.CDF_Phonon.A.assign(1, 0.0); c.CDF_Phonon.Gamma.assign(1, 0.0); }
+            return true;
+        }
+        f.backspace();
+    }
+    c.numpar.kind_of_CDF = 0;
     for (int j = 0; j < N; ++j) {
         Atom &a = c.atoms[j];
         int Shl;
