@@ -109,6 +109,14 @@ typedef struct trk3_tables {
     int32_t n_dos; const double *dos_E; const double *dos_DOS; const double *dos_int; const double *dos_effm;
     /* Out_R / Out_V (Sorting_output_data.f90:1403-1434) */
     int32_t n_r;   const double *out_R; const double *out_V;
+    /* BEB shells (negative shell designator in the .cdf: Target_atoms%KOCS = 2, Reading_files_and_parameters.f90:1557-1561):
+     * electrons and valence holes ionise them with the binary-encounter-Bethe cross section (Cross_sections.f90:3891-3906);
+     * the transferred energy is then sampled from its closed form by bisection (Electron_NRG_transfer_BEB, :2128-2165)
+     * instead of a differential table.  shell_kocs: 1 CDF, 2 BEB; shell_Ek = mean kinetic energy of the shell (EADL I = 914);
+     * at_dens = Matter%At_Dens [1/cm^3]. */
+    int32_t shell_kocs[TRK3_MAX_SHELLS];
+    double  shell_Ek[TRK3_MAX_SHELLS];
+    double  at_dens;
 } trk3_tables;
 
 /* ---------------------------------------------------------------------------------

@@ -442,7 +442,38 @@ struct MC {
         }
         return hw_out;
     }
-    // ---- Electron_energy_transfer_inelastic (CS_method=1, CDF shells), Cross_sections.f90:1793-1871
+    // ---- BEB shells (KOCS = 2).  dSigma_dw_int :3981-3984, dSigma_int_BEB :3958-3979, Electron_NRG_transfer_BEB :2128-2165
+    static double dSigma_dw_int(double S, double t0, double u0, double w0) {
+        return S / (t0 + u0 + 1.0) * (-(std::log(w0 + 1.0) - std::log(std::fabs(t0 - w0))) / (t0 + 1.0) + (1.0 / (t0 - w0) - 1.0 / (w0 + 1.0))
+                                      + std::log(t0) * 0.5 * (1.0 / ((t0 - w0) * (t0 - w0)) - 1.0 / ((w0 + 1.0) * (w0 + 1.0))));
+    }
+    static double dSigma_int_BEB(double Tk, double w, double B, double U, double N) {
+        const double S = 4.0 * g_Pi * g_a0 * g_a0 * N * (g_Ry / B) * (g_Ry / B);
+        const double t0 = Tk / B, u0 = U / B, w0 = w / B;
+        const double dSigma0 = dSigma_dw_int(S, t0, u0, 0.0);
+        return dSigma_dw_int(S, t0, u0, w0) - dSigma0;
+    }
+    double Electron_NRG_transfer_BEB(double Ele, int Nat_cur, int Nshl_cur, double L_need, double Mass, double Emin) {
+        const int f = flat(Nat_cur, Nshl_cur);
+        const double B = T.shell_Ip[f], U = T.shell_Ek[f], N = T.shell_Nel[f];
+        double sum_pers = 0.0;
+        for (int a = 0; a < T.n_atoms; ++a) sum_pers += T.atom_pers[a];
+        double Emin1 = Emin, Emax1 = (Ele - B) / 2.0, E = 0.0;
+        int coun = 0;
+        double Sigma_cur = dSigma_int_BEB(Ele, E, B, U, N);
+        double temp1 = T.at_dens * 1e-24 * T.atom_pers[Nat_cur - 1] / sum_pers;
+        double L_cur = 1.0 / (Mass * temp1 * Sigma_cur);
+        while (std::fabs(L_cur - L_need) / L_need > 0.001) {
+            coun = coun + 1;
+            Sigma_cur = dSigma_int_BEB(Ele, E, B, U, N);
+            L_cur = 1.0 / (Mass * temp1 * Sigma_cur);
+            if (L_cur > L_need) Emin1 = E; else Emax1 = E;
+            E = (Emax1 + Emin1) / 2.0;
+            if (coun >= 1000) break;
+        }
+        return E + B;
+    }
+    // ---- Electron_energy_transfer_inelastic (CS_method=1), Cross_sections.f90:1793-1871
     double Electron_energy_transfer_inelastic(double Ele, int Nat_cur, int Nshl_cur, double L_tot, bool hole, Stream &st) {
         double RN = rng.rn(st);
         double L_need = L_tot / RN;
@@ -452,13 +483,15 @@ struct MC {
         if (!hole) {
             Emax = (Ele + Emin) / 2.0;
             int f = flat(Nat_cur, Nshl_cur);
-            E = interpolate_transferred_energy(Ele, T.ei_E, T.n_ei, T.eid_off + (size_t)f * T.n_ei, T.eid_hw, T.eid_L, L_need);
+            if (T.shell_kocs[f] == 2) E = Electron_NRG_transfer_BEB(Ele, Nat_cur, Nshl_cur, L_need, 1.0, Emin);
+            else E = interpolate_transferred_energy(Ele, T.ei_E, T.n_ei, T.eid_off + (size_t)f * T.n_ei, T.eid_hw, T.eid_L, L_need);
         } else {
             double Mass;
             if (cfg.hole_mass >= 0) Mass = cfg.hole_mass;
             else { int m = Find_in_monotonous_1D_array(T.dos_E, T.n_dos, Ele); Mass = T.dos_effm[m - 1]; }
             Emax = 4.0 * Ele * Mass / ((Mass + 1.0) * (Mass + 1.0));
-            E = interpolate_transferred_energy(Ele, T.hi_E, T.n_hi, T.hid_off, T.hid_hw, T.hid_L, L_need);
+            if (T.shell_kocs[flat(Nat_cur, Nshl_cur)] == 2) E = Electron_NRG_transfer_BEB(Ele, Nat_cur, Nshl_cur, L_need, Mass, Emin);
+            else E = interpolate_transferred_energy(Ele, T.hi_E, T.n_hi, T.hid_off, T.hid_hw, T.hid_L, L_need);
         }
         if (E < Emin) E = Emin;
         if (E > Emax) E = Emax;

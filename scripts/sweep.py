@@ -7,6 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import trekis3_b200 as tk
 
+if os.environ.get("TRK3_GPU_LIB"):          # A/B against another build of the engine library
+    _orig = tk._abi.lib_path
+    tk._abi.lib_path = lambda name: os.environ["TRK3_GPU_LIB"] if name == "gpu" else _orig(name)
+
 cfg, nit = sys.argv[1], int(sys.argv[2])
 case = tk.Case.load(tk.make_run_dir(f"/tmp/run_{cfg}", cfg))
 case.build_tables(shi_window_only=True, cache_dir=os.path.join(ROOT, ".table_cache"))

@@ -134,6 +134,34 @@ def test_screened_elastic_scattering_on_the_gpu(tmp_path, mode):
     assert sg["events"]["el_elastic"] > 5e4
 
 
+@pytest.mark.parametrize("which", ["core", "all"])
+def test_beb_shells_on_the_gpu(tmp_path, which):
+    """BEB shells (negative shell designator; tests/test_beb.py): closed-form total cross sections in the tables,
+    transferred energy by the reference's bisection inside the hot kernels (beb_transfer, one out-of-line copy; in the
+    warp-cooperative collision every lane runs the same bisection).  'all' puts the valence band on BEB as well, where the
+    reference's own error counters 10 / 40 fire: the counts must be the oracle's."""
+    from test_beb import beb_case
+    case = beb_case(tmp_path, which)
+    case.build_tables(**FULL)
+    if which == "core":
+        sg, so = check_against_oracle(case, 4)
+    else:
+        eng = tk.Engine(case)
+        tg, sg = eng.run(0, 4)
+        eng.close()
+        to, so, _, _ = oracle_api.run(case, 0, 4, rng_mode=1)
+        for k in so["events"]:
+            assert abs(sg["events"][k] - so["events"][k]) <= max(2, 2e-3 * so["events"][k]), (k, sg["events"][k], so["events"][k])
+        assert set(sg["errors"]) <= {"err10", "err40"} and set(so["errors"]) <= {"err10", "err40"}
+        for k in so["errors"]:
+            assert abs(sg["errors"].get(k, 0) - so["errors"][k]) <= max(2, 0.05 * so["errors"][k])
+        lay = case.layout()
+        Tg, To = split_tallies(lay, tg), split_tallies(lay, to)
+        for k in To:
+            assert np.isclose(Tg[k].sum(), To[k].sum(), rtol=5e-3), k
+    assert sg["events"]["el_inelastic"] > 3000
+
+
 def test_mott_elastic_scattering(tmp_path):
     d = tk.make_run_dir(str(tmp_path / "v2"), "C1", edits={12: "0   1"})
     case = tk.Case.load(d)
@@ -143,7 +171,8 @@ def test_mott_elastic_scattering(tmp_path):
 
 def test_results_do_not_depend_on_batching_or_tally_placement(case_c1):
     ref, sref = tk.Engine(case_c1, batch=64).run(0, 12)
-    for opts in ({"batch": 5}, {"batch": 64, "use_smem": 0}, {"batch": 7, "refill_min": 1}, {"batch": 64, "refill_min": 32}):
+    for opts in ({"batch": 5}, {"batch": 64, "use_smem": 0}, {"batch": 7, "refill_min": 1}, {"batch": 64, "refill_min": 32},
+                 {"batch": 64, "cold_phased": 1}, {"batch": 64, "coop": 0}):
         t, s = tk.Engine(case_c1, **opts).run(0, 12)
         assert s["events"] == sref["events"], opts
         assert rel_close(t, ref, 1e-9), opts

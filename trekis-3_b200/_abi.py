@@ -48,6 +48,7 @@ class Tables(C.Structure):
         ("hed_off", P_I64), ("hed_hw", P_D), ("hed_L", P_D),
         ("n_dos", C.c_int32), ("dos_E", P_D), ("dos_DOS", P_D), ("dos_int", P_D), ("dos_effm", P_D),
         ("n_r", C.c_int32), ("out_R", P_D), ("out_V", P_D),
+        ("shell_kocs", C.c_int32 * MAX_SHELLS), ("shell_Ek", C.c_double * MAX_SHELLS), ("at_dens", C.c_double),
     ]
 
 

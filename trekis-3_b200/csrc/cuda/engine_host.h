@@ -150,7 +150,9 @@ inline int fill_devp_scalars(const trk3_config &c, const trk3_tables &T, const t
     for (int s = 0; s < T.n_shells; ++s) {
         p.shell_atom[s] = T.shell_atom[s]; p.shell_num[s] = T.shell_num[s]; p.shell_Ip[s] = T.shell_Ip[s];
         p.shell_Nel[s] = T.shell_Nel[s]; p.shell_auger[s] = T.shell_auger[s]; p.shell_radiat[s] = T.shell_radiat[s];
+        p.shell_kocs[s] = (T.shell_kocs[s] == 2) ? 2 : 1; p.shell_Ek[s] = T.shell_Ek[s];   // 0 from a caller that predates the fields = CDF
     }
+    p.at_dens = T.at_dens;
     p.Egap = T.shell_Ip[T.atom_first[0] + T.atom_nshl[0] - 1];            // Target_atoms(1)%Ip(size(...))
     p.n_ei = T.n_ei; p.n_ee = T.n_ee; p.n_hi = T.n_hi; p.n_he = T.n_he; p.n_ph = T.n_ph; p.n_shi = T.n_shi; p.n_dos = T.n_dos; p.n_r = T.n_r;
     p.Nt = lay.Nt;

@@ -23,11 +23,14 @@
 // (the same holds for the code of switches that are off in a run -- Mott scattering, electron emission: out of line it made
 // the cold kernels 7-10 % slower)
 #define TRK_HD_RARE __host__ __device__ inline
+// one out-of-line copy: code that only some inputs ever reach and that only the hot kernels (latency-, not fetch-bound) contain
+#define TRK_HD_OUTLINE __host__ __device__ __noinline__ inline
 #else
 #define TRK_HD inline
 #define TRK_D inline
 #define TRK_HDN inline
 #define TRK_HD_RARE inline
+#define TRK_HD_OUTLINE inline
 #endif
 
 namespace trk3 {
@@ -93,6 +96,8 @@ struct DevP {
     double atom_mass[TRK3_MAX_ATOMS], atom_pers[TRK3_MAX_ATOMS];
     int32_t shell_atom[TRK3_MAX_SHELLS], shell_num[TRK3_MAX_SHELLS];
     double shell_Ip[TRK3_MAX_SHELLS], shell_Nel[TRK3_MAX_SHELLS], shell_auger[TRK3_MAX_SHELLS], shell_radiat[TRK3_MAX_SHELLS];
+    int32_t shell_kocs[TRK3_MAX_SHELLS];                 // 1: CDF shell, 2: BEB shell (electrons and holes; beb_transfer, physics.cuh)
+    double shell_Ek[TRK3_MAX_SHELLS], at_dens;           // mean kinetic energy of the shell [eV], atomic density [1/cm^3] (BEB only)
     // ---- tables (device pointers).  Every table has a companion of natural logarithms (prefix l) computed once
     //      at upload with the same log() the kernels use, so that the log-log interpolation of the reference
     //      (Interpolate(5,...), Cross_sections.f90:4074-4081) costs one exp() instead of five log() + exp().

@@ -55,7 +55,23 @@ TRK_MATH double m_acos(double x) { return acos(x); }
 struct SinCos { double s, c; };
 TRK_MATH SinCos m_sincos(double x) { SinCos r; sincos(x, &r.s, &r.c); return r; }
 // (divisions and square roots out of line were measured too: 21.4 ms instead of 20.9 ms per step -- they stay inline)
-TRK_HD double m_div(double a, double b) { return a / b; }
+// experiment switches (A/B builds, scripts/ab_build.sh): keep ONE copy of a helper in the kernel instead of one per call site
+#if defined(__CUDA_ARCH__) && defined(TRK_OUT_DIV)
+#define TRK_XDIV __device__ __noinline__
+#else
+#define TRK_XDIV TRK_HD
+#endif
+#if defined(__CUDA_ARCH__) && defined(TRK_OUT_INTERP)
+#define TRK_XINT __device__ __noinline__
+#else
+#define TRK_XINT TRK_HD
+#endif
+#if defined(__CUDA_ARCH__) && defined(TRK_OUT_FIND)
+#define TRK_XFIND __device__ __noinline__
+#else
+#define TRK_XFIND TRK_HD
+#endif
+TRK_XDIV double m_div(double a, double b) { return a / b; }
 TRK_HD double m_sqrt(double a) { return sqrt(a); }
 
 // ------------------------------------------------------------------------------------------------
@@ -164,7 +180,7 @@ TRK_HD double interp5(double E1, double E2, double S1, double S2, double En) {
     return m_exp(S1l + (S2l - S1l) / (E2l - E1l) * (El - E1l));
 }
 // same with the logarithms of the table entries precomputed (identical arithmetic, identical result)
-TRK_HD double interp5t(double E1, double E2, double S1, double S2, double lE1, double lE2, double lS1, double lS2, double En, double lEn) {
+TRK_XINT double interp5t(double E1, double E2, double S1, double S2, double lE1, double lE2, double lS1, double lS2, double En, double lEn) {
     if (fabs(E2 - E1) < 1.0e-6) return (S1 > S2) ? S1 : S2;
     if (En == E1) return S1;
     return m_exp(lS1 + m_div(lS2 - lS1, lE2 - lE1) * (lEn - lE1));
@@ -172,7 +188,7 @@ TRK_HD double interp5t(double E1, double E2, double S1, double S2, double lE1, d
 // interp5t that also returns the logarithm of its result: the exponent it evaluated, or the tabulated logarithm of the
 // table entry it returns.  (log(exp(x)) = x up to rounding: callers that interpolate the result again in log space
 // use it instead of a second logarithm -- interpolate_transferred_energy does so twice per sampled energy.)
-TRK_HD double interp5t_l(double E1, double E2, double S1, double S2, double lE1, double lE2, double lS1, double lS2, double En, double lEn, double &lres) {
+TRK_XINT double interp5t_l(double E1, double E2, double S1, double S2, double lE1, double lE2, double lS1, double lS2, double En, double lEn, double &lres) {
     if (fabs(E2 - E1) < 1.0e-6) { if (S1 > S2) { lres = lS1; return S1; } lres = lS2; return S2; }
     if (En == E1) { lres = lS1; return S1; }
     lres = lS1 + m_div(lS2 - lS1, lE2 - lE1) * (lEn - lE1);
@@ -186,7 +202,7 @@ TRK_HD double interp1(double E1, double E2, double S1, double S2, double En) {
 
 // Find_in_monotonous_1D_array through the direct-index accelerator: lv = m_log(v).  A strictly increasing array has
 // exactly one index n with A[n-2] <= v < A[n-1]; the scan from the looked-up start finds it, as the bisection does.
-TRK_HD int find_lut(const double *A, int N, const GridLut &g, double v, double lv) {
+TRK_XFIND int find_lut(const double *A, int N, const GridLut &g, double v, double lv) {
     if (v < A[0]) return 1;
     if (v >= A[N - 1]) return N;
     int b = (int)((lv - g.l0) * g.scale);
@@ -401,6 +417,36 @@ TRK_HD int find_dos(const DevP &p, double E) {
 }
 TRK_HD double hole_mass_dos(const DevP &p, double E) { int m = find_dos(p, E); return p.dos_effm[m - 1]; }
 
+// BEB shells (Target_atoms%KOCS = 2: negative shell designator in the .cdf).  dSigma_dw_int, Cross_sections.f90:3981-3984:
+// the binary-encounter-Bethe cross section integrated over the transferred energy up to w0 (in units of the binding energy).
+TRK_HD double beb_dsigma_dw_int(double S, double t0, double u0, double w0) {
+    return S / (t0 + u0 + 1.0) * (-(m_log(w0 + 1.0) - m_log(fabs(t0 - w0))) / (t0 + 1.0) + (1.0 / (t0 - w0) - 1.0 / (w0 + 1.0))
+                                  + m_log(t0) * 0.5 * (1.0 / ((t0 - w0) * (t0 - w0)) - 1.0 / ((w0 + 1.0) * (w0 + 1.0))));
+}
+// Electron_NRG_transfer_BEB, Cross_sections.f90:2128-2165: the transferred energy whose cumulative mean free path
+// (dSigma_int_BEB :3958-3979) is L_need, by the reference's bisection (0.1 % tolerance, first probe at E = 0, where the
+// cumulative cross section is exactly zero and the path infinite); the binding energy is added at the end.
+TRK_HD_OUTLINE double beb_transfer(const DevP &p, double Ele, int shell, double L_need, double Mass, double Emin) {
+    const double B = p.shell_Ip[shell], U = p.shell_Ek[shell], N = p.shell_Nel[shell];
+    const double S = 4.0 * TRK_PI * TRK_A0 * TRK_A0 * N * (TRK_RY / B) * (TRK_RY / B);
+    const double t0 = Ele / B, u0 = U / B;
+    const double dSigma0 = beb_dsigma_dw_int(S, t0, u0, 0.0);
+    const double temp1 = p.at_dens * 1e-24 * p.atom_pers[p.shell_atom[shell]] / p.sum_pers;
+    double Emin1 = Emin, Emax1 = (Ele - B) / 2.0, E = 0.0;
+    double Sigma_cur = beb_dsigma_dw_int(S, t0, u0, E / B) - dSigma0;
+    double L_cur = 1.0 / (Mass * temp1 * Sigma_cur);
+    int coun = 0;
+    while (fabs(L_cur - L_need) / L_need > 0.001) {
+        ++coun;
+        Sigma_cur = beb_dsigma_dw_int(S, t0, u0, E / B) - dSigma0;
+        L_cur = 1.0 / (Mass * temp1 * Sigma_cur);
+        if (L_cur > L_need) Emin1 = E; else Emax1 = E;
+        E = (Emax1 + Emin1) / 2.0;
+        if (coun >= 1000) break;
+    }
+    return E + B;
+}
+
 // Electron_energy_transfer_inelastic (CS_method = 1), Cross_sections.f90:1793-1871
 TRK_HD double inelastic_dE(const DevP &p, Rec &r, double Ele, double lE, int n_E, int shell, double L_tot, bool hole) {
     double RN = rn(p, r);
@@ -410,11 +456,13 @@ TRK_HD double inelastic_dE(const DevP &p, Rec &r, double Ele, double lE, int n_E
     double Emax, E;
     if (!hole) {
         Emax = (Ele + Emin) / 2.0;
-        E = transferred_energy(csr_eid(p, shell), Ele, lE, n_E, L_need);
+        if (p.shell_kocs[shell] == 2) E = beb_transfer(p, Ele, shell, L_need, 1.0, Emin);     // :1845-1846
+        else E = transferred_energy(csr_eid(p, shell), Ele, lE, n_E, L_need);
     } else {
         double Mass = (p.hole_mass >= 0) ? p.hole_mass : hole_mass_dos(p, Ele);
         Emax = 4.0 * Ele * Mass / ((Mass + 1.0) * (Mass + 1.0));
-        E = transferred_energy(csr_hid(p), Ele, lE, n_E, L_need);
+        if (p.shell_kocs[shell] == 2) E = beb_transfer(p, Ele, shell, L_need, Mass, Emin);
+        else E = transferred_energy(csr_hid(p), Ele, lE, n_E, L_need);
     }
     if (E < Emin) E = Emin;
     if (E > Emax) E = Emax;

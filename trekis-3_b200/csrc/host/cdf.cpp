@@ -216,9 +216,43 @@ double define_dE(int CS_method, int n, double E, bool has_min, double E0_min, bo
 // ---------------------------------------------------------------------------------------------
 // TotIMFP, Cross_sections.f90:881-1050 (CS_method = 1, Ritchie CDF shells)
 // ---------------------------------------------------------------------------------------------
+// BEB cross sections, Cross_sections.f90:3891-3906 (Sigma_BEB), :4000-4040 (dSigma_w_int_BEB, dSigma_dw_w_int): closed forms of
+// Kim & Rudd, Phys. Rev. A 50 (1994) 3954.  T = energy of the incident particle, B = binding energy, U = mean kinetic energy of
+// the shell, N = its electrons; [A^2] and [A^2 eV].
+double Sigma_BEB(double T, double B, double U, double N) {
+    if (T <= B) return 0.0;
+    const double S = 4.0 * g_Pi * g_a0 * g_a0 * N * (g_Ry / B) * (g_Ry / B);
+    const double t0 = T / B, u0 = U / B;
+    return S / (t0 + u0 + 1.0) * (std::log(t0) * 0.5 * (1.0 - 1.0 / (t0 * t0)) + (1.0 - 1.0 / t0) - std::log(t0) / (t0 + 1.0));
+}
+static double dSigma_dw_w_int(double S, double t0, double u0, double w0) {
+    const double tw = 1.0 / (t0 + u0 + 1.0);
+    const double logwt = std::log((w0 + 1.0) * std::fabs(w0 - t0));
+    const double overwt = 1.0 / (w0 - t0), overw1 = 1.0 / (w0 + 1.0), overt1 = 1.0 / (t0 + 1.0);
+    const double A = tw * overt1 * overt1 * (t0 * t0 * std::log(std::fabs(w0 - t0)) + t0 * logwt + std::log(w0 + 1.0));
+    const double B = tw * (-t0 * overwt + overw1 + logwt);
+    const double C = tw * std::log(t0) * (0.5 * (overw1 * overw1 + t0 * overwt * overwt) + overwt - overw1);
+    return S * (A + B + C);
+}
+double dSigma_w_int_BEB(double T, double w, double B, double U, double N) {
+    const double S = 4.0 * g_Pi * g_a0 * g_a0 * N * (g_Ry / B) * (g_Ry / B);
+    const double t0 = T / B, u0 = U / B, w0 = w / B;
+    return B * (dSigma_dw_w_int(S, t0, u0, w0) - dSigma_dw_w_int(S, t0, u0, 0.0));
+}
+
 void TotIMFP(const Ctx &x, double Ele, int Nat, int Nshl, int kind, double &Sigma, double &dEdx, DiffRow *row) {
     const Case &c = *x.c;
     const Atom &at = c.atoms[Nat];
+    if (Nshl < (int)at.KOCS.size() && at.KOCS[Nshl] == 2) {          // BEB shell (:1041-1047): closed form, no differential table
+        const double Mass = (kind == 0) ? 1.0 : hole_mass_at(c, Ele);
+        double sp = 0; for (auto &a : c.atoms) sp += a.Pers;
+        const double temp1 = c.Matter.At_Dens * 1e-24 * at.Pers / sp;
+        const double sig = Sigma_BEB(Ele, at.Ip[Nshl], at.Ek[Nshl], at.Nel[Nshl]);
+        Sigma = 1.0 / (Mass * temp1 * sig);
+        dEdx = Mass * temp1 * dSigma_w_int_BEB(Ele, (Ele - 1.0) / 2.0, at.Ip[Nshl], at.Ek[Nshl], at.Nel[Nshl]);
+        if (row) { row->hw.clear(); row->L.clear(); }
+        return;
+    }
     const CDFosc &o = at.Ritchi[Nshl];
     double Emin = at.Ip[Nshl];
     double Egap = c.atoms[0].Ip.back();

@@ -196,6 +196,7 @@ double trk3h_get(trk3h_case *h, const char *key) {
         if (f == "Ek") return a.Ek[(size_t)sh];
         if (f == "Auger") return a.Auger[(size_t)sh];
         if (f == "Radiat") return a.Radiat[(size_t)sh];
+        if (f == "KOCS") return (double)a.KOCS[(size_t)sh];
         if (f == "Shl_num") return a.Shl_num[(size_t)sh];
         if (f == "PQN") return a.PQN[(size_t)sh];
         return std::nan("");
@@ -210,6 +211,8 @@ int trk3h_get_string(trk3h_case *h, const char *key, char *out, int outlen) {
     else if (k == "target_name") v = h->c.Matter.Target_name;
     else if (k == "chem") v = h->c.Matter.Chem;
     else if (k == "ion") v = h->c.SHI.Name;
+    else if (k == "cdf_file") v = h->c.numpar.CDF_file;          // relative to the run directory, as opened (flags 'CDF <file>' / 'DOS <file>' included)
+    else if (k == "dos_file") v = h->c.numpar.DOS_file;
     else return TRK3_E_INVALID;
     std::snprintf(out, (size_t)outlen, "%s", v.c_str());
     return TRK3_OK;

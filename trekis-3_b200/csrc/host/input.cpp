@@ -459,7 +459,11 @@ bool read_cdf(const std::string &dir, Case &c, const std::vector<PT> &pt, std::s
                     if (read_list(f, 3, t) != 0 || !parse_real(t[0], o.E0[l]) || !parse_real(t[1], o.A[l]) || !parse_real(t[2], o.Gamma[l]))
                         return bad("CDF oscillator line");
             } else { a.KOCS[k] = 2; a.KOCS_SHI[k] = 2; }
-            if (a.KOCS[k] != 1 || a.KOCS_SHI[k] != 1) return bad("BEB shells (negative designator / no CDF) are not supported yet");
+            if (a.KOCS_SHI[k] != 1)
+                return bad("a shell without CDF oscillators would need the ion's BEB branch, which the reference itself marks 'NOT WORKING FOR SHI' "
+                           "(Monte_Carlo.f90:1774), and EPDL photo-absorption: not supported (BEB shell)");
+            if (a.KOCS[k] == 2 && !(a.Ek[k] > 0.0))
+                return bad("BEB shell (negative designator): the mean kinetic energy of the shell comes from INPUT_EADL/EADL2023.ALL (I = 914), which is absent");
         }
     }
     // phonon peaks (optional)

@@ -34,9 +34,11 @@ void pack_case(const Case &c, Packed &p) {
         for (int k = 0; k < at.nshl(); ++k, ++s) {
             t.shell_atom[s] = a; t.shell_num[s] = k; t.shell_Ip[s] = at.Ip[k]; t.shell_Nel[s] = at.Nel[k];
             t.shell_auger[s] = at.Auger[k]; t.shell_radiat[s] = at.Radiat[k];
+            t.shell_kocs[s] = (k < (int)at.KOCS.size() && at.KOCS[k] == 2) ? 2 : 1; t.shell_Ek[s] = k < (int)at.Ek.size() ? at.Ek[k] : 0.0;
             if (a == c.Lowest_Ip_At && k == c.Lowest_Ip_Shl) t.vb_shell = s;
         }
     }
+    t.at_dens = c.Matter.At_Dens;
     const int NS = t.n_shells;
     auto pack_mfp = [&](const std::vector<std::vector<MFP>> &T, std::vector<double> &E, std::vector<double> &L, std::vector<double> *dEdx) {
         E = T[0][0].E;

@@ -154,10 +154,15 @@ class Case:
                 lines = f.read().splitlines()
                 keep = [lines[i] for i in (0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 14, 15) if i < len(lines)] + lines[19:]
                 hsh.update(b"\n".join(keep))
-        mat = self.get_string("material")
-        for rel in (f"INPUT_CDF/{mat}.cdf", f"INPUT_DOS/{mat}.dos", "INPUT_EADL/radiative_widths.dat"):
+        # every file the reader opened: the .cdf / .dos actually used (the optional 'CDF <file>' / 'DOS <file>' flags redirect
+        # them) and the atomic data bases that supply what a .cdf leaves out (masses, Ip, Nel, Ek, decay times, form factors)
+        rels = [self.get_string("cdf_file"), self.get_string("dos_file")]
+        rels += [f"INPUT_EADL/{n}" for n in ("INPUT_atomic_data.dat", "radiative_widths.dat", "EADL2023.ALL", "EPDL2023.ALL",
+                                              "Atomic_form_factors.dat")]
+        for rel in rels:
             p = os.path.join(self.dir, rel)
-            if os.path.exists(p):
+            if rel and os.path.isfile(p):
+                hsh.update(rel.encode())
                 with open(p, "rb") as f:
                     hsh.update(f.read())
         hsh.update(_host().trk3_host_version())
