@@ -1,9 +1,9 @@
 #!/usr/bin/env bash
 # A/B builds of the engine library: .ab/libtrekis3_gpu_<name>.so = the default build plus the given -D switches
-# (physics.cuh: TRK_OUT_DIV / TRK_OUT_INTERP / TRK_OUT_FIND keep ONE out-of-line copy of a helper in each kernel instead of one
-# per call site -- the wave kernels are bound by instruction fetch).  Compare on the GPU box with
+# (any macro the sources test; the out-of-line copies of m_div / interp5t / find_lut tried with it in round 2 were all slower,
+# profiles/r2k_sweep_outline_builds.txt, and are gone again).  Compare on the GPU box with
 #   TRK3_GPU_LIB=.ab/libtrekis3_gpu_<name>.so python scripts/sweep.py C2 1000 ""
-# Usage: scripts/ab_build.sh name "-DTRK_OUT_DIV -DTRK_OUT_INTERP" [name2 "flags2" ...]
+# Usage: scripts/ab_build.sh name "-DSOME_SWITCH" [name2 "flags2" ...]
 set -eu
 cd "$(dirname "$0")/../trekis-3_b200/csrc"
 mkdir -p ../../.ab

@@ -6,7 +6,7 @@
 #      raw page -> scripts/ncu_to_json.py -> per-kernel-class figures for exactly the launches whose algorithmic bytes bench.py
 #      counts (profiles/ncu_classes_C2.json).  A metric list instead of `--set full`: ~5 replay passes per launch instead of ~40
 #      (the first version of this script ran `--set full` over every launch of C2, C4 and C5 and did not finish in 40 minutes).
-#   3. `--set full` of a FEW launches per question: C2 hot generations 0-1, C2 cold launches (incl. the phased cold-electron kernel),
+#   3. `--set full` of a FEW launches per question: C2 hot generations 0-1, C2 cold launches,
 #      C4 generation 1, C5 cold launches; summaries by scripts/ncu_summary.py, per-instruction source page of the C2 hot kernel.
 # run_ahead=0 makes the number of launches per batch exact (no speculative empty generations), so that --launch-skip addresses
 # the cold launches.  Every stage runs under its own `timeout`.
@@ -36,14 +36,12 @@ full)
     $T $NCU -k regex:k_hot -c 3 -o $OUT/${TAG}_c2_hot -f python scripts/ncu_target.py C2 1000 run_ahead=0 > $OUT/${TAG}_c2_hot.log 2>&1
     W=$(python scripts/ncu_target.py C2 1000 run_ahead=0 | awk '{print $3}')
     $T $NCU -k regex:k_wave --launch-skip $((4 * W)) -c 2 -o $OUT/${TAG}_c2_cold -f python scripts/ncu_target.py C2 1000 run_ahead=0 > $OUT/${TAG}_c2_cold.log 2>&1
-    $T $NCU -k regex:k_cold_e -c 1 -o $OUT/${TAG}_c2_cold_phased -f python scripts/ncu_target.py C2 1000 run_ahead=0 cold_phased=1 > $OUT/${TAG}_c2_cold_phased.log 2>&1
     $T $NCU -k regex:"k_wave|k_hot" --launch-skip 5 -c 5 -o $OUT/${TAG}_c4_gen1 -f python scripts/ncu_target.py C4 100 run_ahead=0 > $OUT/${TAG}_c4_gen1.log 2>&1
-    for r in c2_hot c2_cold c2_cold_phased c4_gen1; do
+    for r in c2_hot c2_cold c4_gen1; do
         [ -f $OUT/${TAG}_$r.ncu-rep ] || continue
         python scripts/ncu_summary.py $OUT/${TAG}_$r.ncu-rep $OUT/${TAG}_ncu_full_$r.md > /dev/null 2>&1
     done
     [ -f $OUT/${TAG}_c2_hot.ncu-rep ] && ncu -i $OUT/${TAG}_c2_hot.ncu-rep --page source --csv 2>/dev/null | gzip > $OUT/${TAG}_source_c2_hot.csv.gz
-    [ -f $OUT/${TAG}_c2_cold_phased.ncu-rep ] && ncu -i $OUT/${TAG}_c2_cold_phased.ncu-rep --page source --csv 2>/dev/null | gzip > $OUT/${TAG}_source_c2_cold_phased.csv.gz
     rm -f $OUT/${TAG}_*.ncu-rep
     ;;
 esac; done

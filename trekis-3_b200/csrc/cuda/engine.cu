@@ -639,80 +639,6 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_wave(TRK_P1, 
     block_epilogue(c_p, s_tally, s_cnt, COLD ? SP : -1, warm, LEAN);
 }
 
-// k_cold_e: the cold electrons in PHASES.  The cold kernels are bound by instruction fetch: one collision streams through ~50 KB
-// of SASS, the SM's instruction cache holds 32 KB, and the warps of an SM are each somewhere else in the loop body, so every warp
-// fetches its own copy of every line (ncu: stall no_instruction 2.0 of ~9 cycles per issued instruction).  Here the collision is
-// cut into four parts with a block-wide barrier between them: the warps of a block run the same ~12 KB of code at the same
-// time, so a line fetched for one warp serves them all.  Same functions, same order of operations per history as
-// step_electron<COLD> (physics.cuh): identical results.
-template <bool LEAN>
-__global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_MIN_BLOCKS) k_cold_e(TRK_P1, Queue qin, uint32_t first, uint32_t *head, QueueSet qout, int use_smem, int refill_min) {
-    extern __shared__ double s_dyn[];
-    __shared__ unsigned int s_cnt[S_NCNT];
-    const uint32_t n_in = min(*qin.count, qin.cap);
-    if (first + blockIdx.x * blockDim.x >= n_in) return;
-    double *s_tally = (use_smem && c_p.s_total > 0) ? s_dyn : nullptr;
-    block_prologue(s_tally ? s_tally : s_dyn, s_cnt, s_tally ? (LEAN ? c_p.s_len[TRK3_OUT_ELAT] : c_p.s_total) : 0);
-    DevCtxT<LEAN> c{c_p, qout, s_tally, s_cnt, c_p.defer_snap};
-    const int lane = threadIdx.x & 31;
-    bool active = false, exhausted = false;
-    Rec r;
-    Cache k{};
-    ElEvent s;
-    int ig = 0;
-    for (;;) {
-        // ---- part 0: refill, pending-collision checks, snapshots of the current free flight, place of the collision
-        const unsigned idle = __ballot_sync(0xffffffffu, !active);
-        if (idle && !exhausted && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
-            const int nidle = __popc(idle);
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(head, (uint32_t)nidle);
-            base = __shfl_sync(0xffffffffu, base, 0) + first;
-            if (base + (uint32_t)nidle >= n_in) exhausted = true;
-            if (!active) {
-                const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
-                const uint32_t my = base + rank;
-                if (rank < (uint32_t)nidle && my < n_in) { load_rec(qin, my, r); active = true; begin_electron(c_p, r, ig, k); }
-            }
-        }
-        if (!__syncthreads_or((int)(active || !exhausted))) break;          // barrier + block-uniform end of the loop
-        bool ev = false;
-        if (active) {
-            if (r.tn < c_p.tg[c_p.Nt - 1]) {                                 // a collision is pending: is it really an elastic one?
-                if (!(r.E < c_p.e_cold)) { c.push(SP_ELECTRON, r); active = false; }
-                else {
-                    event_begin(r);
-                    const double RN = rn(c_p, r);
-                    if (electron_roulette_inelastic(k, RN)) { r.ctr--; c.push_hot(SP_ELECTRON, r); active = false; }   // probability ~1e-16
-                }
-            }
-            if (active) {
-                while (ig <= c_p.Nt && c_p.tg[ig - 1] <= r.tn) { c.snap(SP_ELECTRON, r, ig); ++ig; }
-                if (ig > c_p.Nt) active = false; else ev = true;
-            }
-            if (ev) electron_event_head(r, s);
-        }
-        __syncthreads();
-        // ---- part 1: transferred energy (Electron_energy_transfer_elastic)
-        if (ev) {
-            c.event(TRK3_EV_EL_ELAST);
-            const double EMFP = elastic_total(tab_ee(c_p), r.E, k);
-            s.dE = elastic_dE<LEAN>(c_p, r, r.E, k, EMFP, false, 1.0);
-        }
-        __syncthreads();
-        // ---- part 2: scattering angles, energy to the lattice
-        if (ev) {
-            angles_lattice(c_p, r, r.E, s.dE, 1.0, s.theta, s.phi);
-            if (trk_isnan(s.theta) || trk_isnan(s.phi)) c.error(TRK3_ERR_NAN);
-            deposit_lattice(c, r, ig, s.X, s.Y, s.dE);
-        }
-        __syncthreads();
-        // ---- part 3: lookups of the new energy, next free flight, new direction
-        if (ev) electron_event_tail(c, r, ig, k, s);
-    }
-    block_epilogue(c_p, s_tally, s_cnt, SP_ELECTRON, 0, LEAN);
-}
-
 // k_hot<SP>: one generation of carriers that can still ionise (SP = electron or valence hole).  Every round a lane draws
 // the channel roulette of its collision first, so that the kernel (not the event handler) branches on the channel: the
 // handlers are instantiated for one channel each, and for electrons the head and tail of the collision are shared.
@@ -970,12 +896,14 @@ struct trk3_engine {
     std::vector<void *> allocs;
     std::vector<std::pair<void *, size_t>> tab_allocs;   // table arrays in binding order (re-used by trk3_mc_reload_tables)
     size_t tab_cursor = 0;
+    // the table arrays live back to back in ONE arena, so that one access-policy window can pin them in L2 (option l2_persist)
+    char *tab_arena = nullptr; size_t tab_arena_cap = 0, tab_arena_used = 0;
+    int opt_l2_persist = 1, l2_persist_applied = 0;
     uint64_t h2d_bytes = 0;                 // bytes of the last table binding
     double nel_est = 1000.0;
     // options
     uint32_t *h_qcount = nullptr;       // pinned ring of counter snapshots (run-ahead generation loop)
     std::vector<cudaEvent_t> ring_ev;   // one event per ring slot
-    int opt_cold_phased = 0;            // cold electrons by k_cold_e (collision in four parts with block-wide barriers)
     int opt_weighted = 0;               // warps per energy class in proportion to the class's work, not its warp-loads
     int opt_coop = 1;                   // hot electrons that have a warp of their own: the lanes share the collision
     int opt_run_ahead = 1;              // generations the host may enqueue beyond the last counter snapshot it has seen
@@ -1116,9 +1044,37 @@ int tab_alloc(trk3_engine *eng, T **p, size_t n) {
         *p = (T *)a.first;
         return TRK3_OK;
     }
-    int rc = dev_alloc(eng, p, n);
-    if (rc) return rc;
+    if (!eng->tab_arena) {
+        eng->tab_arena_cap = (size_t)192 << 20;        // tables + companions of the largest shipped material are ~80 MB; 180 GB of HBM
+        int rc = dev_alloc(eng, &eng->tab_arena, eng->tab_arena_cap);
+        if (rc) return rc;
+    }
+    const size_t at = (eng->tab_arena_used + 255) & ~(size_t)255;
+    if (at + bytes <= eng->tab_arena_cap) { *p = (T *)(eng->tab_arena + at); eng->tab_arena_used = at + bytes; }
+    else { int rc = dev_alloc(eng, p, n); if (rc) return rc; }      // does not fit: outside the arena (and outside the L2 window)
     eng->tab_allocs.push_back({(void *)*p, bytes}); eng->tab_cursor++;
+    return TRK3_OK;
+}
+// Option l2_persist: the table arena as a persisting access-policy window on every stream of the engine.  The queues stream
+// through L2 (108 B per record, written once, read once) and evict the tables that every collision looks up; with the window
+// the table lines are kept (hitProp persisting) and everything else is treated as streaming.
+int apply_l2_policy(trk3_engine *eng) {
+    if (eng->l2_persist_applied == eng->opt_l2_persist) return TRK3_OK;
+    eng->l2_persist_applied = eng->opt_l2_persist;
+    int max_win = 0, max_persist = 0;
+    CK(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, eng->device));
+    CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, eng->device));
+    cudaStreamAttrValue v; std::memset(&v, 0, sizeof v);
+    if (eng->opt_l2_persist && eng->tab_arena && max_win > 0 && max_persist > 0) {
+        const size_t bytes = std::min<size_t>(eng->tab_arena_used, (size_t)max_win);
+        CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)max_persist)));
+        v.accessPolicyWindow.base_ptr = eng->tab_arena; v.accessPolicyWindow.num_bytes = bytes;
+        v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)bytes);
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } else { v.accessPolicyWindow.num_bytes = 0; v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal; v.accessPolicyWindow.missProp = cudaAccessPropertyNormal; }
+    cudaStream_t all[] = {eng->stream, eng->stream_c, eng->stream_w, eng->stream_wh, eng->stream_sp[0], eng->stream_sp[1], eng->stream_sp[2]};
+    for (cudaStream_t st : all) if (st) CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v));
+    if (!eng->opt_l2_persist) CK(cudaCtxResetPersistingL2Cache());
     return TRK3_OK;
 }
 template <class T>
@@ -1251,24 +1207,16 @@ int launch_wave(trk3_engine *eng, const Queue &qin, uint32_t *head, const QueueS
     const size_t smem_max = (size_t)eng->smem_optin - 1024;             // static shared memory + driver reserve
     if (smem > smem_max) { smem = 8; use_smem = 0; }                    // too many output times for shared memory: global atomics
     auto kern = lean ? k_wave<SP, COLD, true> : k_wave<SP, COLD, false>;
-    const bool phased = SP == SP_ELECTRON && COLD && !warm && eng->opt_cold_phased;
-    auto kern_p = lean ? k_cold_e<true> : k_cold_e<false>;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (phased && smem > 48 * 1024) CK(cudaFuncSetAttribute(kern_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = eng->opt_blocks_per_sm;
     const int block = eng->opt_block;
-    if (bps <= 0) {
-        if (phased) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern_p, block, smem));
-        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, block, smem));
-        if (bps < 1) bps = 1;
-    }
+    if (bps <= 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, block, smem)); if (bps < 1) bps = 1; }
     // one resident wave of blocks, never more than the queue could hold records for
     const uint32_t want = (qin.cap + block - 1) / block;
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(eng->n_sm * bps));
     if (grid < 1) grid = 1;
     const int pi = prof_begin(eng, warm ? N_SPECIES + 4 + SP : (COLD ? N_SPECIES + 2 + SP : SP), st, n_hint);
-    if (phased) kern_p<<<grid, block, smem, st>>>(TRK_PA(eng), qin, first, head, qout, use_smem, eng->opt_refill_min);
-    else kern<<<grid, block, smem, st>>>(TRK_PA(eng), qin, first, head, qout, use_smem, eng->opt_refill_min, warm ? eng->opt_warm_slice : eng->opt_hot_slice, warm);
+    kern<<<grid, block, smem, st>>>(TRK_PA(eng), qin, first, head, qout, use_smem, eng->opt_refill_min, warm ? eng->opt_warm_slice : eng->opt_hot_slice, warm);
     prof_end(eng, pi, st);
     CK(cudaGetLastError());
     eng->launches++;
@@ -1498,7 +1446,7 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "quota_min") eng->opt_quota_min = std::min(32, std::max(1, (int)v));
     else if (k == "coop") eng->opt_coop = (v != 0.0);
     else if (k == "weighted") eng->opt_weighted = (v != 0.0);
-    else if (k == "cold_phased") eng->opt_cold_phased = (int)v;
+    else if (k == "l2_persist") eng->opt_l2_persist = (v != 0.0);
     else if (k == "run_ahead") eng->opt_run_ahead = std::min(6, std::max(0, (int)v));
     else if (k == "warm_pinel") { eng->opt_warm_pinel = std::min(0.99, std::max(0.0, v)); eng->nb_alloc = 0; eng->e_warm_auto = -1.0; eng->h_warm_auto = -1.0; }
     else if (k == "warm_holes") eng->opt_warm_holes = (v != 0.0);
@@ -1560,6 +1508,7 @@ static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, t
     std::lock_guard<std::mutex> device_turn(g_device_mutex[eng->device % 64]);
 #endif
     CK(cudaSetDevice(eng->device));
+    { int rcp = apply_l2_policy(eng); if (rcp) return rcp; }
     const int Nt = eng->lay.Nt;
     const int64_t n_it = it_end - it_begin;
     eng->iter_totE.assign((size_t)n_it * Nt, 0.0);
@@ -1912,6 +1861,7 @@ int trk3_mc_set_stream(trk3_engine *eng, void *stream) {
     CK(cudaStreamSynchronize(eng->stream));
     if (eng->own_stream && eng->stream) cudaStreamDestroy(eng->stream);
     eng->stream = (cudaStream_t)stream; eng->own_stream = false;
+    eng->l2_persist_applied = 0;            // the new stream has no access-policy window yet
     return TRK3_OK;
 }
 // Accumulate into a caller-owned DEVICE buffer of lay.total doubles (e.g. a torch tensor that is then all-reduced).

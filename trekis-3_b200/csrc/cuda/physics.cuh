@@ -55,23 +55,7 @@ TRK_MATH double m_acos(double x) { return acos(x); }
 struct SinCos { double s, c; };
 TRK_MATH SinCos m_sincos(double x) { SinCos r; sincos(x, &r.s, &r.c); return r; }
 // (divisions and square roots out of line were measured too: 21.4 ms instead of 20.9 ms per step -- they stay inline)
-// experiment switches (A/B builds, scripts/ab_build.sh): keep ONE copy of a helper in the kernel instead of one per call site
-#if defined(__CUDA_ARCH__) && defined(TRK_OUT_DIV)
-#define TRK_XDIV __device__ __noinline__
-#else
-#define TRK_XDIV TRK_HD
-#endif
-#if defined(__CUDA_ARCH__) && defined(TRK_OUT_INTERP)
-#define TRK_XINT __device__ __noinline__
-#else
-#define TRK_XINT TRK_HD
-#endif
-#if defined(__CUDA_ARCH__) && defined(TRK_OUT_FIND)
-#define TRK_XFIND __device__ __noinline__
-#else
-#define TRK_XFIND TRK_HD
-#endif
-TRK_XDIV double m_div(double a, double b) { return a / b; }
+TRK_HD double m_div(double a, double b) { return a / b; }
 TRK_HD double m_sqrt(double a) { return sqrt(a); }
 
 // ------------------------------------------------------------------------------------------------
@@ -180,7 +164,7 @@ TRK_HD double interp5(double E1, double E2, double S1, double S2, double En) {
     return m_exp(S1l + (S2l - S1l) / (E2l - E1l) * (El - E1l));
 }
 // same with the logarithms of the table entries precomputed (identical arithmetic, identical result)
-TRK_XINT double interp5t(double E1, double E2, double S1, double S2, double lE1, double lE2, double lS1, double lS2, double En, double lEn) {
+TRK_HD double interp5t(double E1, double E2, double S1, double S2, double lE1, double lE2, double lS1, double lS2, double En, double lEn) {
     if (fabs(E2 - E1) < 1.0e-6) return (S1 > S2) ? S1 : S2;
     if (En == E1) return S1;
     return m_exp(lS1 + m_div(lS2 - lS1, lE2 - lE1) * (lEn - lE1));
@@ -188,7 +172,7 @@ TRK_XINT double interp5t(double E1, double E2, double S1, double S2, double lE1,
 // interp5t that also returns the logarithm of its result: the exponent it evaluated, or the tabulated logarithm of the
 // table entry it returns.  (log(exp(x)) = x up to rounding: callers that interpolate the result again in log space
 // use it instead of a second logarithm -- interpolate_transferred_energy does so twice per sampled energy.)
-TRK_XINT double interp5t_l(double E1, double E2, double S1, double S2, double lE1, double lE2, double lS1, double lS2, double En, double lEn, double &lres) {
+TRK_HD double interp5t_l(double E1, double E2, double S1, double S2, double lE1, double lE2, double lS1, double lS2, double En, double lEn, double &lres) {
     if (fabs(E2 - E1) < 1.0e-6) { if (S1 > S2) { lres = lS1; return S1; } lres = lS2; return S2; }
     if (En == E1) { lres = lS1; return S1; }
     lres = lS1 + m_div(lS2 - lS1, lE2 - lE1) * (lEn - lE1);
@@ -202,7 +186,7 @@ TRK_HD double interp1(double E1, double E2, double S1, double S2, double En) {
 
 // Find_in_monotonous_1D_array through the direct-index accelerator: lv = m_log(v).  A strictly increasing array has
 // exactly one index n with A[n-2] <= v < A[n-1]; the scan from the looked-up start finds it, as the bisection does.
-TRK_XFIND int find_lut(const double *A, int N, const GridLut &g, double v, double lv) {
+TRK_HD int find_lut(const double *A, int N, const GridLut &g, double v, double lv) {
     if (v < A[0]) return 1;
     if (v >= A[N - 1]) return N;
     int b = (int)((lv - g.l0) * g.scale);
