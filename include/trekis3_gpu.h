@@ -117,6 +117,14 @@ typedef struct trk3_tables {
     int32_t shell_kocs[TRK3_MAX_SHELLS];
     double  shell_Ek[TRK3_MAX_SHELLS];
     double  at_dens;
+    /* Delta-function CDF (kind_of_DR = 4, Cross_sections.f90:952-956, 1449-1786): the inelastic cross section of electrons and
+     * valence holes has a closed form per CDF oscillator (position E0, weight alpha = define_alpha,
+     * Reading_files_and_parameters.f90:2199-2206) and the transferred energy is sampled from it by bisection
+     * (get_inelastic_energy_transfer, :2051-2123) instead of a differential table.  delta_cdf: 0 off, 1 on; the oscillators of flat
+     * shell s are entries [osc_off[s], osc_off[s+1]) of osc_E0 / osc_alpha. */
+    int32_t delta_cdf;
+    int32_t osc_off[TRK3_MAX_SHELLS + 1];
+    const double *osc_E0; const double *osc_alpha;
 } trk3_tables;
 
 /* ---------------------------------------------------------------------------------

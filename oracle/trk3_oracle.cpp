@@ -473,6 +473,86 @@ struct MC {
         }
         return E + B;
     }
+    // ---- Delta-function CDF (kind_of_DR = 4), Cross_sections.f90:1449-1720 and get_inelastic_energy_transfer :2051-2123.
+    // The reference calls these with M = mt = g_me and identical = .true. for electrons and holes alike; the ion-electron
+    // branches of W_min / W_max / minimal_sufficient_E are therefore not restated (they cannot be reached on this path).
+    static double dl_rest_energy(double M0) { return M0 * g_cvel * g_cvel / g_e; }
+    static double dl_W_min(double Ip_, double E, double E0) {                                  // :1564-1590, |Mc2 - mtc2|/Mc2 < 1e-6
+        double Wmin = Ip_;
+        const double E0min = E0 * (1.0 - 0.25 * E0 / E);
+        return std::max(Wmin, E0min);
+    }
+    static double dl_W_max(double E, double Ip_) { return (E + Ip_) * 0.50; }                   // :1593-1616, identical
+    static double dl_Eeq(double Ip_, double E0) {                                             // find_Wmax_equal_Wmin :1619-1649, identical
+        return 5.0 / 4.0 * E0 - Ip_ / 2.0 + 0.25 * std::sqrt(17.0 * E0 * E0 - 12.0 * Ip_ * E0 + 4.0 * Ip_ * Ip_);
+    }
+    static double dl_P_prefactor(double M, double E, double nat) {                            // :1525-1556
+        const double Erest = dl_rest_energy(M), fact = E / Erest + 1.0;
+        const double v = g_cvel * std::sqrt(1.0 - 1.0 / (fact * fact));
+        const double beta = v / g_cvel;
+        const double g_me_eV = 0.51099906 * 1.0e6;
+        return 1.0e24 / (g_Pi * g_a0 * nat * g_me_eV * (beta * beta));
+    }
+    static double dl_integral_CS(double alpha, double Mc2, double mtc2, double E0, double W) { // :1706-1712
+        const double g_me_eV = 0.51099906 * 1.0e6;
+        const double Mc22 = 2.0 * Mc2;
+        return alpha / (g_me_eV * (Mc22 - E0)) * ((Mc22 - mtc2) * std::log(Mc22 + W - E0) + Mc22 * mtc2 / E0 * (std::log(W) - std::log(std::fabs(W - E0))));
+    }
+    static double dl_integrated_delta_CDF_CS(double alpha, double Mc2, double E0, double mtc2, double W, double Ip_, double E) {   // :1690-1704
+        const double Wmin = dl_W_min(Ip_, E, E0);
+        if (W < Wmin || E <= Ip_) return 0.0;
+        return dl_integral_CS(alpha, Mc2, mtc2, E0, W);
+    }
+    double Integral_CDF_delta_CS(double E, int f, double Ip_, bool have_Emax_in, double Emax_in) const {   // :1449-1522
+        const double M = g_me, Mc2 = dl_rest_energy(g_me), mtc2 = dl_rest_energy(g_me), nat = T.at_dens;
+        double CS = 0.0, P = 0.0;
+        for (int i = T.osc_off[f]; i < T.osc_off[f + 1]; ++i) {
+            const double E0 = T.osc_E0[i], alpha = T.osc_alpha[i];
+            const double Emin = dl_W_min(Ip_, E, E0);
+            const double Estart = Ip_;
+            const double Eeq = dl_Eeq(Ip_, E0);
+            if (E <= Estart) { CS = 0.0; P = 0.0; }
+            else {
+                const double dEed = Eeq / 100.0;
+                if (E <= Eeq + dEed) {                       // linear extrapolation, Find_linear_a_b :1671-1688
+                    const double Ex = Eeq + dEed;
+                    const double Wmin_lim = dl_W_min(Ip_, Ex, E0), Wmax_lim = dl_W_max(Ex, Ip_);
+                    const double Pl = dl_P_prefactor(M, Ex, nat);
+                    const double CSl = -Pl * (dl_integral_CS(alpha, Mc2, mtc2, E0, Wmax_lim) - dl_integral_CS(alpha, Mc2, mtc2, E0, Wmin_lim));
+                    const double IpMm = Ip_;
+                    const double a = CSl / (Ex - IpMm), b = -CSl * Ip_ / (Ex - IpMm);
+                    CS = a * E + b;
+                    P = 1.0;
+                } else {
+                    double Emax = dl_W_max(E, Ip_);
+                    if (have_Emax_in) {
+                        if (Emax_in < Emin) Emax = Emin;
+                        else if (Emax_in < Emax) Emax = Emax_in;
+                    }
+                    CS = CS - (dl_integrated_delta_CDF_CS(alpha, Mc2, E0, mtc2, Emax, Ip_, E) - dl_integrated_delta_CDF_CS(alpha, Mc2, E0, mtc2, Emin, Ip_, E));
+                    P = dl_P_prefactor(M, E, nat);
+                }
+            }
+        }
+        return std::fabs(CS) * P;
+    }
+    double get_inelastic_energy_transfer(double Ee, int Nat_cur, int Nshl_cur, double Ip_, Stream &st) {   // :2051-2123
+        const int f = flat(Nat_cur, Nshl_cur);
+        const double eps = 1.0e-3;
+        double E_left = Ip_, E_right = (Ip_ + Ee) * 0.5;
+        double RN = rng.rn(st);
+        const double CS_tot = Integral_CDF_delta_CS(Ee, f, Ip_, true, E_right);
+        const double CS_sampled = RN * CS_tot;
+        double E_cur = (E_left + E_right) * 0.5;
+        double CS_cur = Integral_CDF_delta_CS(Ee, f, Ip_, true, E_cur);
+        while (std::fabs(CS_cur - CS_sampled) / CS_sampled > eps) {
+            if (CS_cur > CS_sampled) E_right = E_cur; else E_left = E_cur;
+            E_cur = (E_left + E_right) / 2.0;
+            if (std::fabs(E_left - E_right) < eps) break;
+            CS_cur = Integral_CDF_delta_CS(Ee, f, Ip_, true, E_cur);
+        }
+        return E_cur;
+    }
     // ---- Electron_energy_transfer_inelastic (CS_method=1), Cross_sections.f90:1793-1871
     double Electron_energy_transfer_inelastic(double Ele, int Nat_cur, int Nshl_cur, double L_tot, bool hole, Stream &st) {
         double RN = rng.rn(st);
@@ -484,6 +564,7 @@ struct MC {
             Emax = (Ele + Emin) / 2.0;
             int f = flat(Nat_cur, Nshl_cur);
             if (T.shell_kocs[f] == 2) E = Electron_NRG_transfer_BEB(Ele, Nat_cur, Nshl_cur, L_need, 1.0, Emin);
+            else if (T.delta_cdf) E = get_inelastic_energy_transfer(Ele, Nat_cur, Nshl_cur, Emin, st);      // :1894-1895
             else E = interpolate_transferred_energy(Ele, T.ei_E, T.n_ei, T.eid_off + (size_t)f * T.n_ei, T.eid_hw, T.eid_L, L_need);
         } else {
             double Mass;
@@ -491,6 +572,7 @@ struct MC {
             else { int m = Find_in_monotonous_1D_array(T.dos_E, T.n_dos, Ele); Mass = T.dos_effm[m - 1]; }
             Emax = 4.0 * Ele * Mass / ((Mass + 1.0) * (Mass + 1.0));
             if (T.shell_kocs[flat(Nat_cur, Nshl_cur)] == 2) E = Electron_NRG_transfer_BEB(Ele, Nat_cur, Nshl_cur, L_need, Mass, Emin);
+            else if (T.delta_cdf) E = get_inelastic_energy_transfer(Ele, Nat_cur, Nshl_cur, Emin, st);
             else E = interpolate_transferred_energy(Ele, T.hi_E, T.n_hi, T.hid_off, T.hid_hw, T.hid_L, L_need);
         }
         if (E < Emin) E = Emin;

@@ -67,6 +67,7 @@ extern "C" int trk3_emul_run(const trk3_config *cfg, const trk3_tables *tab, int
     p.eid_off = tab->eid_off; p.eid_hw = tab->eid_hw; p.eid_L = tab->eid_L; p.eed_off = tab->eed_off; p.eed_hw = tab->eed_hw; p.eed_L = tab->eed_L;
     p.hid_off = tab->hid_off; p.hid_hw = tab->hid_hw; p.hid_L = tab->hid_L; p.hed_off = tab->hed_off; p.hed_hw = tab->hed_hw; p.hed_L = tab->hed_L;
     p.dos_E = tab->dos_E; p.dos_DOS = tab->dos_DOS; p.dos_int = tab->dos_int; p.dos_effm = tab->dos_effm; p.out_R = tab->out_R; p.out_V = tab->out_V;
+    p.osc_E0 = tab->osc_E0; p.osc_alpha = tab->osc_alpha;
     // companions of the tables (logs, reciprocals) and the cold ranges, as engine.cu prepares them on the device
     std::vector<std::vector<double>> comp;
     const size_t NS = tab->n_shells;

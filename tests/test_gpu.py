@@ -174,6 +174,20 @@ def test_beb_shells_on_the_gpu(tmp_path, which):
     assert sg["events"]["el_inelastic"] > 6000
 
 
+@pytest.mark.parametrize("cfg", ["C1", "C3"])
+def test_delta_function_cdf_on_the_gpu(tmp_path, cfg):
+    """kind_of_DR = 4 (tests/test_delta_cdf.py): closed-form inelastic tables, the transferred energy by bisection on
+    the closed form inside the hot kernels (delta_transfer: one out-of-line copy, csrc/common/trk3_delta.h shared with the host
+    table builder) -- CUDA engine vs the oracle's own restatement; C3 (diamond) exercises the valence-hole ionisation."""
+    case = tk.Case.load(tk.make_run_dir(str(tmp_path / "d"), cfg, edits={13: "4   0   ! delta-function CDF"}))
+    case.build_tables(**FULL)
+    assert case.tables.delta_cdf == 1
+    sg, so = check_against_oracle(case, 4)
+    assert sg["events"]["el_inelastic"] > 2000
+    if cfg == "C3":
+        assert sg["events"]["vbh_inelastic"] > 100
+
+
 def test_mott_elastic_scattering(tmp_path):
     d = tk.make_run_dir(str(tmp_path / "v2"), "C1", edits={12: "0   1"})
     case = tk.Case.load(d)

@@ -49,6 +49,7 @@ class Tables(C.Structure):
         ("n_dos", C.c_int32), ("dos_E", P_D), ("dos_DOS", P_D), ("dos_int", P_D), ("dos_effm", P_D),
         ("n_r", C.c_int32), ("out_R", P_D), ("out_V", P_D),
         ("shell_kocs", C.c_int32 * MAX_SHELLS), ("shell_Ek", C.c_double * MAX_SHELLS), ("at_dens", C.c_double),
+        ("delta_cdf", C.c_int32), ("osc_off", C.c_int32 * (MAX_SHELLS + 1)), ("osc_E0", P_D), ("osc_alpha", P_D),
     ]
 
 

@@ -419,8 +419,10 @@ __device__ inline void electron_collision_warp(C &c, Rec &e, int iv, Cache &k, P
         double Emin = p.shell_Ip[shell];
         if (Emin <= 1.0e-3) Emin = 1.0e-3;
         const double Emax = (Eel + Emin) / 2.0;
-        double E = (p.shell_kocs[shell] == 2) ? beb_transfer(p, Eel, shell, L_need, 1.0, Emin)     // BEB shell: every lane the same bisection
-                                              : transferred_energy_warp(csr_eid(p, shell), p.eid_mono + (size_t)shell * p.n_ei, Eel, k.lE, n, L_need);
+        double E;
+        if (p.shell_kocs[shell] == 2) E = beb_transfer(p, Eel, shell, L_need, 1.0, Emin);          // BEB shell: every lane the same bisection
+        else if (p.delta_cdf) { const double RNd = pw.draw(p, e.iter, e.ctr++, e.id); E = delta_transfer(p, Eel, shell, Emin, RNd); }   // delta-function CDF: likewise
+        else E = transferred_energy_warp(csr_eid(p, shell), p.eid_mono + (size_t)shell * p.n_ei, Eel, k.lE, n, L_need);
         if (E < Emin) E = Emin;
         if (E > Emax) E = Emax;
         if (trk_isnan(E)) E = Emin;
@@ -1306,6 +1308,8 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
     }
     UP(dos_E, tab->dos_E, tab->n_dos); UP(dos_DOS, tab->dos_DOS, tab->n_dos); UP(dos_int, tab->dos_int, tab->n_dos); UP(dos_effm, tab->dos_effm, tab->n_dos);
     UP(out_R, tab->out_R, tab->n_r); UP(out_V, tab->out_V, tab->n_r);
+    { const int n_osc = tab->delta_cdf ? tab->osc_off[tab->n_shells] : 0;        // delta-function CDF (kind_of_DR = 4)
+      UP(osc_E0, tab->osc_E0, n_osc); UP(osc_alpha, tab->osc_alpha, n_osc); }
 #undef UP
     {   // log / reciprocal companions (one exp() per log-log interpolation instead of five log() + exp())
         const trk3_tables &T = *tab;

@@ -153,6 +153,8 @@ inline int fill_devp_scalars(const trk3_config &c, const trk3_tables &T, const t
         p.shell_kocs[s] = (T.shell_kocs[s] == 2) ? 2 : 1; p.shell_Ek[s] = T.shell_Ek[s];   // 0 from a caller that predates the fields = CDF
     }
     p.at_dens = T.at_dens;
+    p.delta_cdf = T.delta_cdf ? 1 : 0;
+    for (int s = 0; s <= TRK3_MAX_SHELLS; ++s) p.osc_off[s] = T.delta_cdf ? T.osc_off[s] : 0;
     p.Egap = T.shell_Ip[T.atom_first[0] + T.atom_nshl[0] - 1];            // Target_atoms(1)%Ip(size(...))
     p.n_ei = T.n_ei; p.n_ee = T.n_ee; p.n_hi = T.n_hi; p.n_he = T.n_he; p.n_ph = T.n_ph; p.n_shi = T.n_shi; p.n_dos = T.n_dos; p.n_r = T.n_r;
     p.Nt = lay.Nt;

@@ -97,7 +97,9 @@ struct DevP {
     int32_t shell_atom[TRK3_MAX_SHELLS], shell_num[TRK3_MAX_SHELLS];
     double shell_Ip[TRK3_MAX_SHELLS], shell_Nel[TRK3_MAX_SHELLS], shell_auger[TRK3_MAX_SHELLS], shell_radiat[TRK3_MAX_SHELLS];
     int32_t shell_kocs[TRK3_MAX_SHELLS];                 // 1: CDF shell, 2: BEB shell (electrons and holes; beb_transfer, physics.cuh)
-    double shell_Ek[TRK3_MAX_SHELLS], at_dens;           // mean kinetic energy of the shell [eV], atomic density [1/cm^3] (BEB only)
+    double shell_Ek[TRK3_MAX_SHELLS], at_dens;           // mean kinetic energy of the shell [eV], atomic density [1/cm^3] (BEB, delta-CDF)
+    int32_t delta_cdf, osc_off[TRK3_MAX_SHELLS + 1];     // delta-function CDF (kind_of_DR = 4): oscillators [osc_off[s], osc_off[s+1]) of shell s
+    const double *osc_E0, *osc_alpha;                    // (delta_transfer, physics.cuh)
     // ---- tables (device pointers).  Every table has a companion of natural logarithms (prefix l) computed once
     //      at upload with the same log() the kernels use, so that the log-log interpolation of the reference
     //      (Interpolate(5,...), Cross_sections.f90:4074-4081) costs one exp() instead of five log() + exp().

@@ -57,6 +57,11 @@ TRK_MATH SinCos m_sincos(double x) { SinCos r; sincos(x, &r.s, &r.c); return r; 
 // (divisions and square roots out of line were measured too: 21.4 ms instead of 20.9 ms per step -- they stay inline)
 TRK_HD double m_div(double a, double b) { return a / b; }
 TRK_HD double m_sqrt(double a) { return sqrt(a); }
+}  // namespace trk3
+// the closed forms of the delta-function CDF (shared with the host table builder); their logarithms through the one copy above
+#define DLT_LOG(x) trk3::m_log(x)
+#include "../common/trk3_delta.h"
+namespace trk3 {
 
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG (Salmon et al., SC'11).  Stream = (particle id, draw index,
@@ -431,6 +436,15 @@ TRK_HD_OUTLINE double beb_transfer(const DevP &p, double Ele, int shell, double 
     return E + B;
 }
 
+// Delta-function CDF (kind_of_DR = 4): Electron_NRG_transfer_CDF hands over to get_inelastic_energy_transfer
+// (Cross_sections.f90:1894-1895, 2051-2123), which draws a random number of its own and finds the transferred energy by bisection
+// on the closed-form cross section (csrc/common/trk3_delta.h, shared with the host table builder) -- for electrons and for
+// valence holes alike with the free-electron mass.
+TRK_HD_OUTLINE double delta_transfer(const DevP &p, double Ele, int shell, double Emin, double RN) {
+    const int o = p.osc_off[shell];
+    return trk3delta::inelastic_energy_transfer(Ele, p.osc_E0 + o, p.osc_alpha + o, p.osc_off[shell + 1] - o, Emin, p.at_dens, RN);
+}
+
 // Electron_energy_transfer_inelastic (CS_method = 1), Cross_sections.f90:1793-1871
 TRK_HD double inelastic_dE(const DevP &p, Rec &r, double Ele, double lE, int n_E, int shell, double L_tot, bool hole) {
     double RN = rn(p, r);
@@ -441,11 +455,13 @@ TRK_HD double inelastic_dE(const DevP &p, Rec &r, double Ele, double lE, int n_E
     if (!hole) {
         Emax = (Ele + Emin) / 2.0;
         if (p.shell_kocs[shell] == 2) E = beb_transfer(p, Ele, shell, L_need, 1.0, Emin);     // :1845-1846
+        else if (p.delta_cdf) { const double RNd = rn(p, r); E = delta_transfer(p, Ele, shell, Emin, RNd); }
         else E = transferred_energy(csr_eid(p, shell), Ele, lE, n_E, L_need);
     } else {
         double Mass = (p.hole_mass >= 0) ? p.hole_mass : hole_mass_dos(p, Ele);
         Emax = 4.0 * Ele * Mass / ((Mass + 1.0) * (Mass + 1.0));
         if (p.shell_kocs[shell] == 2) E = beb_transfer(p, Ele, shell, L_need, Mass, Emin);
+        else if (p.delta_cdf) { const double RNd = rn(p, r); E = delta_transfer(p, Ele, shell, Emin, RNd); }
         else E = transferred_energy(csr_hid(p), Ele, lE, n_E, L_need);
     }
     if (E < Emin) E = Emin;

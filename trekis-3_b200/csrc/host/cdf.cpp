@@ -5,6 +5,7 @@
 // effective charges (:2601-2680), searches and interpolation.
 // Loop orders and expression shapes follow the Fortran so that a reference build and this
 // builder agree to rounding (target 1e-12 relative, BASELINE.json north_star).
+#include "../common/trk3_delta.h"
 #include "trk3_host.hpp"
 #include "../common/trk3_dcs.h"
 #include <algorithm>
@@ -257,6 +258,13 @@ void TotIMFP(const Ctx &x, double Ele, int Nat, int Nshl, int kind, double &Sigm
     double Emin = at.Ip[Nshl];
     double Egap = c.atoms[0].Ip.back();
     if (Emin <= 1.0e-3) Emin = 1.0e-3;
+    if (c.numpar.kind_of_DR == 4) {          // Delta-CDF (:952-956): closed form for electrons AND holes (M = mt = g_me), no differential table
+        const double sig = trk3delta::Integral_CDF_delta_CS(g_me, g_me, Ele, o.E0.data(), o.alpha.data(), (int)o.E0.size(), Emin, c.Matter.At_Dens, true, -1.0);
+        Sigma = trk3delta::MFP_from_sigma(sig, c.Matter.At_Dens);
+        dEdx = trk3delta::energy_loss_delta(Ele, g_me, 1.0, Emin, c.Matter.At_Dens, g_me, o.E0.data(), o.alpha.data(), (int)o.E0.size(), true);
+        if (row) { row->hw.clear(); row->L.clear(); }
+        return;
+    }
     double Emax, Mass;
     bool save = false;
     if (kind == 0) { Emax = (Ele + Emin) / 2.0; Mass = 1.0; save = true; }
@@ -588,6 +596,11 @@ double Int_Ritchi_p_x(double A, double E, double Gamma, double xx) {
     return In.real();
 }
 }  // namespace
+
+// define_alpha, Reading_files_and_parameters.f90:2199-2206: weight of the delta function that replaces a Ritchie oscillator
+double define_alpha(double Ai, double Gammai, double E0i, double x_min) {
+    return Int_Ritchi_x(Ai, E0i, Gammai, 1.0e30) - Int_Ritchi_x(Ai, E0i, Gammai, x_min);
+}
 
 void sumrules(const CDFosc &o, double &ksum, double &fsum, double x_min, double Omega) {
     double ne = 0.0, f = 0.0;

@@ -601,7 +601,18 @@ bool read_case(const std::string &dir, Case &c, std::string &err) {
     if (!read_cdf(dir, c, pt, err)) return false;
     apply_radiative_data(dir, c);
     if (c.SHI.Kind_ion != 0 && c.SHI.Kind_ion != 1) c.SHI.Kind_ion = 0;       // anything but 1 is the point charge (select case default)
-    if (c.numpar.kind_of_DR == 4) { err = "Delta-CDF (kind_of_DR=4) is not supported"; return false; }
+    if (c.numpar.kind_of_DR == 4) {
+        // Delta-CDF: the weights follow the oscillators as they are read (Reading_files_and_parameters.f90:1565-1575, 1608-1610)
+        if (c.numpar.kind_of_CDF == 1) { err = "Delta-CDF (kind_of_DR=4) with a .cdf that leaves its shells to the atomic database (single-pole CDFs) is not supported"; return false; }
+        for (auto &a : c.atoms) for (int k = 0; k < a.nshl(); ++k) {
+            CDFosc &o = a.Ritchi[(size_t)k];
+            o.alpha.resize(o.E0.size());
+            for (size_t l = 0; l < o.E0.size(); ++l) o.alpha[l] = define_alpha(o.A[l], o.Gamma[l], o.E0[l], a.Ip[(size_t)k]);
+        }
+        CDFosc &ph = c.CDF_Phonon;
+        ph.alpha.resize(ph.E0.size());
+        for (size_t l = 0; l < ph.E0.size(); ++l) ph.alpha[l] = define_alpha(ph.A[l], ph.Gamma[l], ph.E0[l], 0.0);
+    }
     if (c.numpar.kind_of_EMFP == 2) { err = "DSF elastic cross sections (kind_of_EMFP=2) need INPUT_DSF files; not supported"; return false; }
     if (c.numpar.CDF_elast_Zeff == 2) {
         // read_form_factors, Reading_files_and_parameters.f90:605-615, 867-907: one header line, then row Z = a1..a5 of element Z

@@ -39,6 +39,20 @@ void pack_case(const Case &c, Packed &p) {
         }
     }
     t.at_dens = c.Matter.At_Dens;
+    // oscillators of the delta-function CDF per flat shell (kind_of_DR = 4)
+    t.delta_cdf = (c.numpar.kind_of_DR == 4) ? 1 : 0;
+    p.osc_E0.clear(); p.osc_alpha.clear();
+    {
+        int sf = 0;
+        for (int a = 0; a < t.n_atoms; ++a) for (int k = 0; k < c.atoms[a].nshl(); ++k, ++sf) {
+            t.osc_off[sf] = (int32_t)p.osc_E0.size();
+            const CDFosc &o = c.atoms[a].Ritchi[k];
+            if (t.delta_cdf) for (size_t l = 0; l < o.E0.size() && l < o.alpha.size(); ++l) { p.osc_E0.push_back(o.E0[l]); p.osc_alpha.push_back(o.alpha[l]); }
+        }
+        for (; sf <= TRK3_MAX_SHELLS; ++sf) t.osc_off[sf] = (int32_t)p.osc_E0.size();
+    }
+    if (p.osc_E0.empty()) { p.osc_E0.push_back(0.0); p.osc_alpha.push_back(0.0); }
+    t.osc_E0 = p.osc_E0.data(); t.osc_alpha = p.osc_alpha.data();
     const int NS = t.n_shells;
     auto pack_mfp = [&](const std::vector<std::vector<MFP>> &T, std::vector<double> &E, std::vector<double> &L, std::vector<double> *dEdx) {
         E = T[0][0].E;

@@ -204,8 +204,18 @@ RefCacheNames reference_cache_names(const Case &c) {
     return n;
 }
 
+// Closed-form shells have no differential tables: BEB shells (KOCS = 2) and every shell under the delta-function CDF
+// (kind_of_DR = 4).  The reference still writes one diff_CS file per shell and grid energy for them -- from arrays its TotIMFP
+// never filled (Cross_sections.f90:950-956, 1041-1047) -- and reads them back: that part of the cache carries no information and is
+// not reproduced, so the reference-format cache is refused for such inputs (the binary .trk3tab cache serves them).
+static bool closed_form_shells(const Case &c) {
+    if (c.numpar.kind_of_DR == 4) return true;
+    for (const auto &a : c.atoms) for (int k : a.KOCS) if (k == 2) return true;
+    return false;
+}
 bool write_reference_cache(const Case &c, const std::string &out_root, int *n_files_out, std::string &err) {
     if (!c.tables_built) { err = "write_reference_cache: tables not built"; return false; }
+    if (closed_form_shells(c)) { err = "write_reference_cache: BEB shells / delta-function CDF have no differential tables; the reference-format cache is not written for them"; return false; }
     const RefCacheNames n = reference_cache_names(c);
     const std::string dm = out_root + "/" + n.dir_material, di = out_root + "/" + n.dir_ion, dd = out_root + "/" + n.dir_diff;
     if (!make_dirs(di) || !make_dirs(dd)) { err = "cannot create " + di; return false; }
@@ -263,6 +273,7 @@ bool write_reference_cache(const Case &c, const std::string &out_root, int *n_fi
 }
 
 bool read_reference_cache(Case &c, const std::string &out_root, const BuildOptions &opt, std::string &err) {
+    if (closed_form_shells(c)) { err = "read_reference_cache: BEB shells / delta-function CDF have no differential tables; build the tables instead"; return false; }
     get_single_pole(c);                                   // MAIN.f90:146 (before any table, cached or not)
     const RefCacheNames n = reference_cache_names(c);
     const std::string dm = out_root + "/" + n.dir_material, di = out_root + "/" + n.dir_ion, dd = out_root + "/" + n.dir_diff;

@@ -32,7 +32,7 @@ inline double g_alpha() { return g_e * g_e / (g_h * g_cvel * 4.0 * g_Pi * g_e0);
 inline double g_v0() { return std::sqrt(2.0 * g_Ry * g_e / g_me); }
 
 // ---- Objects.f90:211-217 (type CDF)
-struct CDFosc { std::vector<double> E0, A, Gamma; };
+struct CDFosc { std::vector<double> E0, A, Gamma, alpha; };   // alpha: weights of the delta-function CDF (kind_of_DR = 4)
 
 // ---- Objects.f90:257-275 (type Atom)
 struct Atom {
@@ -220,9 +220,10 @@ struct Packed {
     std::vector<double> ei_E, ei_L, ee_E, ee_L, hi_E, hi_L, he_E, he_L, ph_E, ph_L, shi_E, shi_L, shi_dEdx;
     std::vector<int64_t> dshi_off, eid_off, eed_off, hid_off, hed_off;
     std::vector<double> dshi_E, dshi_L, eid_hw, eid_L, eed_hw, eed_L, hid_hw, hid_L, hed_hw, hed_L;
-    std::vector<double> dos_E, dos_DOS, dos_int, dos_effm, out_R, out_V;
+    std::vector<double> dos_E, dos_DOS, dos_int, dos_effm, out_R, out_V, osc_E0, osc_alpha;
 };
 void pack_case(const Case &c, Packed &p);
+double define_alpha(double Ai, double Gammai, double E0i, double x_min);       // cdf.cpp
 
 // ---- output files (output.cpp): Save_output, Sorting_output_data.f90:340-1140
 bool save_output(const Case &c, const trk3_tally_layout &lay, const double *tallies_sum, int NMC,

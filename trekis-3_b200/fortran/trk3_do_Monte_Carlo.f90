@@ -50,6 +50,10 @@ module trk3_gpu_binding
      type(c_ptr) :: eid_off, eid_hw, eid_L, eed_off, eed_hw, eed_L, hid_off, hid_hw, hid_L, hed_off, hed_hw, hed_L
      integer(c_int32_t) :: n_dos; type(c_ptr) :: dos_E, dos_DOS, dos_int, dos_effm
      integer(c_int32_t) :: n_r;   type(c_ptr) :: out_R, out_V
+     integer(c_int32_t) :: shell_kocs(TRK3_MAX_SHELLS)                      ! 1 CDF shell, 2 BEB shell (Target_atoms%KOCS)
+     real(c_double) :: shell_Ek(TRK3_MAX_SHELLS), at_dens                   ! Target_atoms%Ek, Matter%At_Dens
+     integer(c_int32_t) :: delta_cdf, osc_off(TRK3_MAX_SHELLS + 1)          ! kind_of_DR = 4: oscillators of flat shell s = [osc_off(s), osc_off(s+1))
+     type(c_ptr) :: osc_E0, osc_alpha                                       ! Target_atoms%Ritchi%E0 / %alpha, flattened
   end type
 
   type, bind(C) :: trk3_tally_layout                ! include/trekis3_gpu.h: trk3_tally_layout
@@ -148,7 +152,8 @@ subroutine do_Monte_Carlo(NMC, SHI, SHI_MFP, diff_SHI_MFP, Target_atoms, Lowest_
     real(c_double), allocatable, target :: eid_hw(:), eid_L(:), eed_hw(:), eed_L(:), hid_hw(:), hid_L(:), hed_hw(:), hed_L(:)
     integer(c_int64_t), allocatable, target :: dshi_off(:), eid_off(:), eed_off(:), hid_off(:), hed_off(:)
     real(c_double), allocatable, target :: dos_E(:), dos_DOS(:), dos_int(:), dos_effm(:), R_c(:), V_c(:)
-    real(c_double), allocatable, target :: buf(:)
+    real(c_double), allocatable, target :: buf(:), osc_E0(:), osc_alpha(:)
+    integer :: n_osc, l
 
     Nat = size(Target_atoms)
     NS = 0
@@ -182,8 +187,39 @@ subroutine do_Monte_Carlo(NMC, SHI, SHI_MFP, diff_SHI_MFP, Target_atoms, Lowest_
           tab%shell_Ip(q) = Target_atoms(a)%Ip(k); tab%shell_Nel(q) = Target_atoms(a)%Nel(k)
           tab%shell_auger(q) = Target_atoms(a)%Auger(k); tab%shell_radiat(q) = Target_atoms(a)%Radiat(k)
           if (a == Lowest_Ip_At .and. k == Lowest_Ip_Shl) tab%vb_shell = q - 1
+          tab%shell_kocs(q) = Target_atoms(a)%KOCS(k)           ! 2: BEB shell (negative designator in the .cdf)
+          tab%shell_Ek(q) = Target_atoms(a)%Ek(k)
        enddo
     enddo
+    tab%at_dens = Matter%At_Dens
+    ! ---- delta-function CDF (kind_of_DR = 4): positions and weights of the oscillators, flattened in shell order
+    tab%delta_cdf = merge(1, 0, NumPar%kind_of_DR == 4)
+    n_osc = 0
+    if (tab%delta_cdf == 1) then
+       do a = 1, Nat
+          do k = 1, size(Target_atoms(a)%Ip)
+             n_osc = n_osc + size(Target_atoms(a)%Ritchi(k)%E0)
+          enddo
+       enddo
+    endif
+    allocate(osc_E0(max(n_osc, 1)), osc_alpha(max(n_osc, 1)))
+    osc_E0 = 0.0d0; osc_alpha = 0.0d0
+    tab%osc_off(:) = 0
+    q = 0; n_osc = 0
+    do a = 1, Nat
+       do k = 1, size(Target_atoms(a)%Ip)
+          q = q + 1
+          tab%osc_off(q) = n_osc
+          if (tab%delta_cdf == 1) then
+             do l = 1, size(Target_atoms(a)%Ritchi(k)%E0)
+                n_osc = n_osc + 1
+                osc_E0(n_osc) = Target_atoms(a)%Ritchi(k)%E0(l); osc_alpha(n_osc) = Target_atoms(a)%Ritchi(k)%alpha(l)
+             enddo
+          endif
+       enddo
+    enddo
+    tab%osc_off(q + 1:) = n_osc
+    tab%osc_E0 = c_loc(osc_E0); tab%osc_alpha = c_loc(osc_alpha)
 
     ! ---- mean free paths: one energy grid per family, rows [shell][energy]
     call flatten_mfp(Total_el_MFPs, ei_E, ei_L)

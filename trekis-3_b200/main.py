@@ -54,7 +54,13 @@ def prepare_tables(case, run_dir, evaluator="auto", threads=0, redo=False, write
     case.build_tables(threads=threads, verbose=verbose, evaluator=ev, shi_window_only=shi_window_only)
     if write_cache:
         os.makedirs(cache_root, exist_ok=True)
-        case.write_reference_cache(cache_root)
+        try:
+            case.write_reference_cache(cache_root)
+        except RuntimeError as e:          # closed-form shells (BEB, delta-function CDF) have no differential tables to cache
+            if "no differential tables" not in str(e):
+                raise
+            if verbose:
+                print(f"[trekis3] {e}", file=sys.stderr)
     return "built:" + (ev or "host-direct")
 
 
