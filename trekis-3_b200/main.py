@@ -89,12 +89,23 @@ def run(run_dir, nmc=None, evaluator="auto", threads=0, redo_tables=False, table
                 dist.init_process_group("gloo")
             else:
                 dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    failure = None
     if rank == 0:
-        info["tables"] = prepare_tables(case, run_dir, evaluator, threads, redo_tables, True, verbose, shi_window_only)
+        try:
+            info["tables"] = prepare_tables(case, run_dir, evaluator, threads, redo_tables, True, verbose, shi_window_only)
+        except Exception as e:             # bad input, write failure: the other ranks must not sit in a collective until it times out
+            failure = f"{type(e).__name__}: {e}"
     if dist is not None:
-        dist.barrier()
-        if rank != 0:
-            info["tables"] = prepare_tables(case, run_dir, None, threads, False, False, False, shi_window_only)
+        box = [failure]
+        dist.broadcast_object_list(box, src=0)      # doubles as the barrier behind which the cache files exist
+        if box[0] is not None:
+            if own_group:
+                dist.destroy_process_group()
+            raise RuntimeError("rank 0 could not prepare the tables: " + box[0])
+        if rank != 0:                       # a rank that cannot read the cache builds with the SAME options as rank 0 did
+            info["tables"] = prepare_tables(case, run_dir, evaluator, threads, False, False, False, shi_window_only)
+    elif failure is not None:
+        raise RuntimeError(failure)
     _stamp(verbose, "Mean free paths and differential tables ready:", t0)
     info["t_tables_s"] = time.perf_counter() - t0
     if tables_only:
