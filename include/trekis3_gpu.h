@@ -125,6 +125,14 @@ typedef struct trk3_tables {
     int32_t delta_cdf;
     int32_t osc_off[TRK3_MAX_SHELLS + 1];
     const double *osc_E0; const double *osc_alpha;
+    /* DSF elastic scattering (kind_of_EMFP = 2; DSF_DEMFP / DSF_DEMFP_H of do_Monte_Carlo, NRG_transfer_elastic_DSF,
+     * Cross_sections.f90:3652-3780).  The elastic tables ee_E / ee_L (he_E / he_L) then live on the DSF file's own particle-energy
+     * grid; per grid energy i the row [i * n_dsf_e, (i + 1) * n_dsf_e) of dsf_e_dE holds the transferred energies (ascending, from
+     * -0.2 eV: the particle absorbs energy from the lattice, to +0.2 eV: it emits) and the same row of dsf_e_emit / dsf_e_absorb the
+     * mean free paths integrated up to them; ee_emit / ee_absorb = Elastic_MFP%Emit%L / %Absorb%L (the rows' last entries,
+     * Analytical_IMFPs.f90:913-919).  n_dsf_e = 0: no DSF tables. */
+    int32_t n_dsf_e; const double *dsf_e_dE; const double *dsf_e_emit; const double *dsf_e_absorb; const double *ee_emit; const double *ee_absorb;
+    int32_t n_dsf_h; const double *dsf_h_dE; const double *dsf_h_emit; const double *dsf_h_absorb; const double *he_emit; const double *he_absorb;
 } trk3_tables;
 
 /* ---------------------------------------------------------------------------------

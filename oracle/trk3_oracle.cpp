@@ -616,7 +616,50 @@ struct MC {
         double W2 = Ee * E2mc / (EmcMc * EmcMc - Ee * E2mc * ct2);
         return W1 * W2;
     }
+    // ---- NRG_transfer_elastic_DSF, Cross_sections.f90:3652-3780, with Linear_approx_2x1d_DSF (Reading_files_and_parameters.f90:3718-3745)
+    // and linear_interpolation (:3798-3802).  The row of integrated mean free paths is interpolated as a whole between the two
+    // tabulated particle energies, as the reference does.
+    double NRG_transfer_elastic_DSF(double Eel, bool hole, Stream &st) {
+        const double *gE = hole ? T.he_E : T.ee_E, *gL = hole ? T.he_L : T.ee_L, *gEm = hole ? T.he_emit : T.ee_emit, *gAb = hole ? T.he_absorb : T.ee_absorb;
+        const int NE = hole ? T.n_he : T.n_ee, NW = hole ? T.n_dsf_h : T.n_dsf_e;
+        const double *dEt = hole ? T.dsf_h_dE : T.dsf_e_dE, *dEm = hole ? T.dsf_h_emit : T.dsf_e_emit, *dAb = hole ? T.dsf_h_absorb : T.dsf_e_absorb;
+        int NumE = Find_in_monotonous_1D_array(gE, NE, Eel);
+        if (NumE > 1) NumE = NumE - 1;
+        std::vector<double> dL(NW, 0.0), dW(NW, 0.0);
+        int i_MFP = Find_in_monotonous_1D_array(gE, NE, Eel);
+        if (i_MFP > 1) i_MFP = i_MFP - 1;
+        auto lin = [](double y1, double y2, double x1, double x2, double x) { return y1 + (y2 - y1) / (x2 - x1) * (x - x1); };
+        const double EMFP_tot = lin(gL[i_MFP - 1], gL[i_MFP], gE[i_MFP - 1], gE[i_MFP], Eel);
+        const double EMFP_emit = lin(gEm[i_MFP - 1], gEm[i_MFP], gE[i_MFP - 1], gE[i_MFP], Eel);
+        const double EMFP_absorb = lin(gAb[i_MFP - 1], gAb[i_MFP], gE[i_MFP - 1], gE[i_MFP], Eel);
+        double RN = rng.rn(st);
+        const bool it_is_emission = RN < EMFP_tot / EMFP_emit;
+        const double *src = it_is_emission ? dEm : dAb;
+        if (NumE == NE) {
+            for (int j = 0; j < NW; ++j) { dL[j] = src[(size_t)(NumE - 1) * NW + j]; dW[j] = dEt[(size_t)(NumE - 1) * NW + j]; }
+        } else {
+            const double Value1 = (Eel - gE[NumE - 1]) / (gE[NumE] - gE[NumE - 1]);
+            for (int j = 0; j < NW; ++j) {
+                dL[j] = src[(size_t)(NumE - 1) * NW + j] + (src[(size_t)NumE * NW + j] - src[(size_t)(NumE - 1) * NW + j]) * Value1;
+                dW[j] = dEt[(size_t)(NumE - 1) * NW + j] + (dEt[(size_t)NumE * NW + j] - dEt[(size_t)(NumE - 1) * NW + j]) * Value1;
+            }
+            for (int j = 0; j < NW; ++j) if (dL[j] < 0.0) dL[j] = 0.0;
+        }
+        RN = rng.rn(st);
+        const double L_need = it_is_emission ? EMFP_emit / RN : EMFP_absorb / RN;
+        std::vector<double> neg(NW);
+        for (int j = 0; j < NW; ++j) neg[j] = -dL[j];
+        const int Number = Find_in_monotonous_1D_array(neg.data(), NW, -L_need);
+        double dE;
+        if (Number == 1) dE = dW[0] + (dW[1] - dW[0]) / (dL[1] - dL[0]) * (L_need - dL[0]);
+        else if (std::fabs(dL[Number - 1] - dL[Number - 2]) < 1.0e-9) dE = dW[Number - 2];
+        else if (dL[Number - 2] > 1e20) dE = dW[Number - 2];
+        else dE = dW[Number - 2] + (dW[Number - 1] - dW[Number - 2]) / (dL[Number - 1] - dL[Number - 2]) * (L_need - dL[Number - 2]);
+        if (std::fabs(dE) > 1.0 && it_is_emission && dE > Eel) dE = Eel;
+        return dE;
+    }
     double elastic_dE(double Eel, double EMFP, bool hole, double M_eff, Stream &st) {    // the kind_of_EMFP switch, Monte_Carlo.f90:2387-2407 / :2668-2692
+        if (cfg.kind_of_EMFP == 2) return NRG_transfer_elastic_DSF(Eel, hole, st);
         if (cfg.kind_of_EMFP == 1) return Electron_energy_transfer_elastic(Eel, EMFP, hole, st);
         double dE = 0.0, sp = 0.0;
         for (int ii = 0; ii < Nat; ++ii) {
@@ -1184,7 +1227,7 @@ int trk3_oracle_run(const trk3_config *cfg, const trk3_tables *tab, int64_t it_b
     trk3_tally_layout lay;
     int rc = trk3_tally_layout_init(cfg, tab, &lay);
     if (rc != TRK3_OK) return rc;
-    if (cfg->kind_of_EMFP == 2) return TRK3_E_UNSUPPORTED;
+    if (cfg->kind_of_EMFP == 2 && (tab->n_dsf_e < 2 || tab->n_dsf_h < 2)) return TRK3_E_UNSUPPORTED;
     const int64_t n_it = it_end - it_begin;
     if (threads < 1) threads = (int)std::thread::hardware_concurrency();
     if (threads < 1) threads = 1;

@@ -68,6 +68,8 @@ extern "C" int trk3_emul_run(const trk3_config *cfg, const trk3_tables *tab, int
     p.hid_off = tab->hid_off; p.hid_hw = tab->hid_hw; p.hid_L = tab->hid_L; p.hed_off = tab->hed_off; p.hed_hw = tab->hed_hw; p.hed_L = tab->hed_L;
     p.dos_E = tab->dos_E; p.dos_DOS = tab->dos_DOS; p.dos_int = tab->dos_int; p.dos_effm = tab->dos_effm; p.out_R = tab->out_R; p.out_V = tab->out_V;
     p.osc_E0 = tab->osc_E0; p.osc_alpha = tab->osc_alpha;
+    p.dsf_e_dE = tab->dsf_e_dE; p.dsf_e_emit = tab->dsf_e_emit; p.dsf_e_absorb = tab->dsf_e_absorb; p.ee_emit = tab->ee_emit; p.ee_absorb = tab->ee_absorb;
+    p.dsf_h_dE = tab->dsf_h_dE; p.dsf_h_emit = tab->dsf_h_emit; p.dsf_h_absorb = tab->dsf_h_absorb; p.he_emit = tab->he_emit; p.he_absorb = tab->he_absorb;
     // companions of the tables (logs, reciprocals) and the cold ranges, as engine.cu prepares them on the device
     std::vector<std::vector<double>> comp;
     const size_t NS = tab->n_shells;

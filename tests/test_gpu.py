@@ -190,6 +190,18 @@ def test_delta_function_cdf_on_the_gpu(tmp_path, cfg):
         assert sg["events"]["vbh_inelastic"] > 100
 
 
+@pytest.mark.parametrize("cfg,material", [("C1", "Al2O3"), ("C3", "Diamond")])
+def test_dsf_elastic_scattering_on_the_gpu(tmp_path, cfg, material):
+    """kind_of_EMFP = 2 (tests/test_dsf.py): the arguments DSF_DEMFP / DSF_DEMFP_H of do_Monte_Carlo.  Collisions can
+    hand energy to the particle; a cold electron that is lifted above the cold range goes back to the hot queues (set X)."""
+    from test_dsf import dsf_run_dir
+    case = tk.Case.load(dsf_run_dir(tmp_path, cfg=cfg, material=material))
+    case.build_tables(**FULL)
+    assert case.config.kind_of_EMFP == 2 and case.tables.n_dsf_e > 2
+    sg, so = check_against_oracle(case, 4)
+    assert sg["events"]["el_elastic"] > 5000 and sg["events"]["vbh_elastic"] > 5000
+
+
 def test_mott_elastic_scattering(tmp_path):
     d = tk.make_run_dir(str(tmp_path / "v2"), "C1", edits={12: "0   1"})
     case = tk.Case.load(d)

@@ -50,6 +50,8 @@ class Tables(C.Structure):
         ("n_r", C.c_int32), ("out_R", P_D), ("out_V", P_D),
         ("shell_kocs", C.c_int32 * MAX_SHELLS), ("shell_Ek", C.c_double * MAX_SHELLS), ("at_dens", C.c_double),
         ("delta_cdf", C.c_int32), ("osc_off", C.c_int32 * (MAX_SHELLS + 1)), ("osc_E0", P_D), ("osc_alpha", P_D),
+        ("n_dsf_e", C.c_int32), ("dsf_e_dE", P_D), ("dsf_e_emit", P_D), ("dsf_e_absorb", P_D), ("ee_emit", P_D), ("ee_absorb", P_D),
+        ("n_dsf_h", C.c_int32), ("dsf_h_dE", P_D), ("dsf_h_emit", P_D), ("dsf_h_absorb", P_D), ("he_emit", P_D), ("he_absorb", P_D),
     ]
 
 

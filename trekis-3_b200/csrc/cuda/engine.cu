@@ -1278,7 +1278,7 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
     int rc = trk3_tally_layout_init(cfg, tab, &eng->lay);
     if (rc != TRK3_OK) { eng->err = "invalid time grid / layout"; return rc; }
     rc = fill_devp_scalars(*cfg, *tab, eng->lay, eng->hp);
-    if (rc != TRK3_OK) { eng->err = (rc == TRK3_E_UNSUPPORTED) ? "unsupported option (DSF elastic scattering)" : "invalid tables"; return rc; }
+    if (rc != TRK3_OK) { eng->err = (rc == TRK3_E_UNSUPPORTED) ? "DSF elastic scattering (kind_of_EMFP = 2) without DSF tables" : "invalid tables"; return rc; }
     DevP &p = eng->hp;
     HostTotals tot; compute_totals(*tab, tot);
     const size_t NS = tab->n_shells;
@@ -1310,6 +1310,11 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
     UP(out_R, tab->out_R, tab->n_r); UP(out_V, tab->out_V, tab->n_r);
     { const int n_osc = tab->delta_cdf ? tab->osc_off[tab->n_shells] : 0;        // delta-function CDF (kind_of_DR = 4)
       UP(osc_E0, tab->osc_E0, n_osc); UP(osc_alpha, tab->osc_alpha, n_osc); }
+    { const bool dsf = cfg->kind_of_EMFP == 2;                                     // DSF elastic scattering (kind_of_EMFP = 2)
+      const size_t ne = dsf ? (size_t)tab->n_ee : 0, nh = dsf ? (size_t)tab->n_he : 0;
+      const size_t re = ne * (size_t)tab->n_dsf_e, rh = nh * (size_t)tab->n_dsf_h;
+      UP(dsf_e_dE, tab->dsf_e_dE, re); UP(dsf_e_emit, tab->dsf_e_emit, re); UP(dsf_e_absorb, tab->dsf_e_absorb, re); UP(ee_emit, tab->ee_emit, ne); UP(ee_absorb, tab->ee_absorb, ne);
+      UP(dsf_h_dE, tab->dsf_h_dE, rh); UP(dsf_h_emit, tab->dsf_h_emit, rh); UP(dsf_h_absorb, tab->dsf_h_absorb, rh); UP(he_emit, tab->he_emit, nh); UP(he_absorb, tab->he_absorb, nh); }
 #undef UP
     {   // log / reciprocal companions (one exp() per log-log interpolation instead of five log() + exp())
         const trk3_tables &T = *tab;

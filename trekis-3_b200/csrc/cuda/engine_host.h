@@ -129,7 +129,7 @@ inline double host_shi_zeff(const trk3_config &c, const trk3_tables &T) {
 inline int fill_devp_scalars(const trk3_config &c, const trk3_tables &T, const trk3_tally_layout &lay, DevP &p) {
     std::memset(&p, 0, sizeof p);
     if (T.n_atoms < 1 || T.n_atoms > TRK3_MAX_ATOMS || T.n_shells < 1 || T.n_shells > TRK3_MAX_SHELLS) return TRK3_E_INVALID;
-    if (c.kind_of_EMFP == 2) return TRK3_E_UNSUPPORTED;
+    if (c.kind_of_EMFP == 2 && (T.n_dsf_e < 2 || T.n_dsf_h < 2 || T.n_ee < 2 || T.n_he < 2)) return TRK3_E_UNSUPPORTED;   // DSF scattering without its tables
     if (c.include_photons && T.n_ph <= 0) return TRK3_E_INVALID;
     const double g_me = 9.1093821545e-31, g_Mp = 1836.1526724780 * g_me, g_e = 1.602176487e-19, g_h = 1.05457162853e-34, g_Pi = 3.1415926535897932384626433832795;
     p.ion_E = c.shi_E; p.ion_mass = c.shi_mass; p.ion_fixed_Zeff = c.shi_fixed_Zeff; p.ion_Z = c.shi_Z; p.ion_kind_Zeff = c.shi_kind_Zeff;
@@ -153,6 +153,7 @@ inline int fill_devp_scalars(const trk3_config &c, const trk3_tables &T, const t
         p.shell_kocs[s] = (T.shell_kocs[s] == 2) ? 2 : 1; p.shell_Ek[s] = T.shell_Ek[s];   // 0 from a caller that predates the fields = CDF
     }
     p.at_dens = T.at_dens;
+    p.n_dsf_e = (c.kind_of_EMFP == 2) ? T.n_dsf_e : 0; p.n_dsf_h = (c.kind_of_EMFP == 2) ? T.n_dsf_h : 0;
     p.delta_cdf = T.delta_cdf ? 1 : 0;
     for (int s = 0; s <= TRK3_MAX_SHELLS; ++s) p.osc_off[s] = T.delta_cdf ? T.osc_off[s] : 0;
     p.Egap = T.shell_Ip[T.atom_first[0] + T.atom_nshl[0] - 1];            // Target_atoms(1)%Ip(size(...))

@@ -100,6 +100,9 @@ struct DevP {
     double shell_Ek[TRK3_MAX_SHELLS], at_dens;           // mean kinetic energy of the shell [eV], atomic density [1/cm^3] (BEB, delta-CDF)
     int32_t delta_cdf, osc_off[TRK3_MAX_SHELLS + 1];     // delta-function CDF (kind_of_DR = 4): oscillators [osc_off[s], osc_off[s+1]) of shell s
     const double *osc_E0, *osc_alpha;                    // (delta_transfer, physics.cuh)
+    // DSF elastic scattering (kind_of_EMFP = 2): rows [i * n_dsf][0..n_dsf) per energy of the elastic grid (dsf_elastic_dE, physics.cuh)
+    int32_t n_dsf_e, n_dsf_h;
+    const double *dsf_e_dE, *dsf_e_emit, *dsf_e_absorb, *ee_emit, *ee_absorb, *dsf_h_dE, *dsf_h_emit, *dsf_h_absorb, *he_emit, *he_absorb;
     // ---- tables (device pointers).  Every table has a companion of natural logarithms (prefix l) computed once
     //      at upload with the same log() the kernels use, so that the log-log interpolation of the reference
     //      (Interpolate(5,...), Cross_sections.f90:4074-4081) costs one exp() instead of five log() + exp().

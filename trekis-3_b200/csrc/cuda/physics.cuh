@@ -508,8 +508,70 @@ TRK_HD_RARE double mott_elastic_dE(const DevP &p, Rec &r, double Eel, double M_e
 // LEAN (compile time, C::kLean of the context): the caller guarantees the default switches -- CDF elastic scattering
 // (kind_of_EMFP = 1) and no electron emission (work_function <= 0) --, and the code of the other settings is not compiled
 // in.  The wave kernels are bound by instruction fetch: code that never runs still costs (measured: -6 % step time).
+// NRG_transfer_elastic_DSF, Cross_sections.f90:3652-3780 (kind_of_EMFP = 2): the energy an electron or a valence hole exchanges
+// with the lattice, sampled from tabulated dynamic-structure-factor cross sections.  Positive = emission (the particle loses
+// energy), NEGATIVE = absorption (it gains: "allowed in DSF formalism", Monte_Carlo.f90:713).  The reference interpolates the whole
+// row of integrated mean free paths between the two tabulated particle energies around Eel (clipping negative entries to zero) and
+// then searches it with Find_in_array_monoton on the NEGATED row; here the elements of the interpolated row are evaluated where the
+// bisection probes them -- the same expression per element, the same index.
+struct DsfRow {
+    const double *La, *Lb, *Wa, *Wb; double v; bool two;      // rows of the two particle energies, interpolation weight Value1
+    TRK_HD double L(int j) const { double x = two ? La[j] + (Lb[j] - La[j]) * v : La[j]; return (two && x < 0.0) ? 0.0 : x; }
+    TRK_HD double W(int j) const { return two ? Wa[j] + (Wb[j] - Wa[j]) * v : Wa[j]; }
+};
+TRK_HD_RARE double dsf_elastic_dE(const DevP &p, Rec &r, double Eel, bool hole) {
+    const double *gE = hole ? p.he_E : p.ee_E, *gL = hole ? p.he_L : p.ee_L, *gEm = hole ? p.he_emit : p.ee_emit, *gAb = hole ? p.he_absorb : p.ee_absorb;
+    const int NE = hole ? p.n_he : p.n_ee, NW = hole ? p.n_dsf_h : p.n_dsf_e;
+    const double *dE = hole ? p.dsf_h_dE : p.dsf_e_dE, *dEm = hole ? p.dsf_h_emit : p.dsf_e_emit, *dAb = hole ? p.dsf_h_absorb : p.dsf_e_absorb;
+    // 0) the DSF energy grid is the grid of the elastic tables (Analytical_IMFPs.f90:913-915): one search serves :3665 and :3682
+    int NumE = find_1d(gE, NE, Eel);
+    if (NumE > 1) NumE = NumE - 1;
+    const int i_MFP = NumE;
+    // 1) emission or absorption (:3690-3705); linear_interpolation :3798-3802
+    const double x1 = gE[i_MFP - 1], x2 = gE[i_MFP];
+    const double EMFP_tot = gL[i_MFP - 1] + (gL[i_MFP] - gL[i_MFP - 1]) / (x2 - x1) * (Eel - x1);
+    const double EMFP_emit = gEm[i_MFP - 1] + (gEm[i_MFP] - gEm[i_MFP - 1]) / (x2 - x1) * (Eel - x1);
+    const double EMFP_absorb = gAb[i_MFP - 1] + (gAb[i_MFP] - gAb[i_MFP - 1]) / (x2 - x1) * (Eel - x1);
+    double RN = rn(p, r);
+    const bool it_is_emission = RN < EMFP_tot / EMFP_emit;
+    // 2) the row between the two particle energies (:3712-3746)
+    DsfRow row;
+    row.two = (NumE != NE);
+    row.v = row.two ? (Eel - gE[NumE - 1]) / (gE[NumE] - gE[NumE - 1]) : 0.0;
+    const double *src = it_is_emission ? dEm : dAb;
+    row.La = src + (size_t)(NumE - 1) * NW; row.Lb = row.two ? src + (size_t)NumE * NW : row.La;
+    row.Wa = dE + (size_t)(NumE - 1) * NW; row.Wb = row.two ? dE + (size_t)NumE * NW : row.Wa;
+    RN = rn(p, r);
+    const double L_need = it_is_emission ? EMFP_emit / RN : EMFP_absorb / RN;
+    // Linear_approx_2x1d_DSF, Reading_files_and_parameters.f90:3718-3745: Find_in_monotonous_1D_array on (-row, -L_need)
+    int Number;
+    {
+        const double v = -L_need;
+        if (v < -row.L(0)) Number = 1;
+        else if (v >= -row.L(NW - 1)) Number = NW;
+        else {
+            int i_1 = 1, i_2 = NW, i_cur = (1 + NW) >> 1;
+            double temp_val = -row.L(i_cur - 1);
+            while (i_1 != i_2 - 1) {
+                if (temp_val <= v) i_1 = i_cur; else i_2 = i_cur;
+                i_cur = (i_1 + i_2) >> 1;
+                temp_val = -row.L(i_cur - 1);
+            }
+            Number = i_cur + 1;
+        }
+    }
+    double W;
+    if (Number == 1) W = row.W(0) + (row.W(1) - row.W(0)) / (row.L(1) - row.L(0)) * (L_need - row.L(0));
+    else if (fabs(row.L(Number - 1) - row.L(Number - 2)) < 1.0e-9) W = row.W(Number - 2);
+    else if (row.L(Number - 2) > 1e20) W = row.W(Number - 2);
+    else W = row.W(Number - 2) + (row.W(Number - 1) - row.W(Number - 2)) / (row.L(Number - 1) - row.L(Number - 2)) * (L_need - row.L(Number - 2));
+    if (fabs(W) > 1.0 && it_is_emission && W > Eel) W = Eel;        // :3758-3771 (the messages of the reference are not printed)
+    return W;
+}
+
 template <bool LEAN>
 TRK_HD double elastic_dE(const DevP &p, Rec &r, double Eel, const Cache &k, double EMFP, bool hole, double M_eff) {
+    if (!LEAN && p.kind_of_EMFP == 2) return dsf_elastic_dE(p, r, Eel, hole);
     if (LEAN || p.kind_of_EMFP == 1) {      // Electron_energy_transfer_elastic, Cross_sections.f90:2403-2413
         double RN = rn(p, r);
         double L_need = m_div(EMFP, RN);

@@ -613,7 +613,18 @@ bool read_case(const std::string &dir, Case &c, std::string &err) {
         ph.alpha.resize(ph.E0.size());
         for (size_t l = 0; l < ph.E0.size(); ++l) ph.alpha[l] = define_alpha(ph.A[l], ph.Gamma[l], ph.E0[l], 0.0);
     }
-    if (c.numpar.kind_of_EMFP == 2) { err = "DSF elastic cross sections (kind_of_EMFP=2) need INPUT_DSF files; not supported"; return false; }
+    if (c.numpar.kind_of_EMFP == 2) {
+        // Reading_files_and_parameters.f90:578-599: electrons, then holes; a missing file switches the run to Mott cross sections
+        for (int hole = 0; hole < 2 && c.numpar.kind_of_EMFP == 2; ++hole) {
+            const std::string rel = dsf_file_name(c, hole != 0);
+            bool found = false;
+            if (!read_dsf(dir + "/" + rel, hole ? c.DSF_DEMFP_H : c.DSF_DEMFP, found, err)) return false;
+            if (!found) {
+                c.warnings.push_back("File " + rel + " is not found. The calculations proceed with Mott atomic cross-sections.");
+                c.numpar.kind_of_EMFP = 0; c.DSF_DEMFP.clear(); c.DSF_DEMFP_H.clear();
+            }
+        }
+    }
     if (c.numpar.CDF_elast_Zeff == 2) {
         // read_form_factors, Reading_files_and_parameters.f90:605-615, 867-907: one header line, then row Z = a1..a5 of element Z
         const std::string p = dir + "/INPUT_EADL/Atomic_form_factors.dat";

@@ -53,6 +53,23 @@ void pack_case(const Case &c, Packed &p) {
     }
     if (p.osc_E0.empty()) { p.osc_E0.push_back(0.0); p.osc_alpha.push_back(0.0); }
     t.osc_E0 = p.osc_E0.data(); t.osc_alpha = p.osc_alpha.data();
+    // DSF elastic scattering (kind_of_EMFP = 2): rows of the two DSF files, flattened [particle energy][transferred energy]
+    auto pack_dsf = [](const std::vector<DsfPoint> &D, int32_t &n, std::vector<double> &dE, std::vector<double> &em, std::vector<double> &ab,
+                       std::vector<double> &Lem, std::vector<double> &Lab) {
+        dE.clear(); em.clear(); ab.clear(); Lem.clear(); Lab.clear();
+        n = D.empty() ? 0 : (int32_t)D[0].dE.size();
+        for (const DsfPoint &d : D) {
+            dE.insert(dE.end(), d.dE.begin(), d.dE.end()); em.insert(em.end(), d.dL_emit.begin(), d.dL_emit.end()); ab.insert(ab.end(), d.dL_absorb.begin(), d.dL_absorb.end());
+            Lem.push_back(d.dL_emit.back()); Lab.push_back(d.dL_absorb.back());
+        }
+        if (dE.empty()) { dE.push_back(0.0); em.push_back(0.0); ab.push_back(0.0); Lem.push_back(0.0); Lab.push_back(0.0); }
+    };
+    const bool dsf = c.numpar.kind_of_EMFP == 2;
+    static const std::vector<DsfPoint> none;
+    pack_dsf(dsf ? c.DSF_DEMFP : none, t.n_dsf_e, p.dsf_e_dE, p.dsf_e_emit, p.dsf_e_absorb, p.ee_emit, p.ee_absorb);
+    pack_dsf(dsf ? c.DSF_DEMFP_H : none, t.n_dsf_h, p.dsf_h_dE, p.dsf_h_emit, p.dsf_h_absorb, p.he_emit, p.he_absorb);
+    t.dsf_e_dE = p.dsf_e_dE.data(); t.dsf_e_emit = p.dsf_e_emit.data(); t.dsf_e_absorb = p.dsf_e_absorb.data(); t.ee_emit = p.ee_emit.data(); t.ee_absorb = p.ee_absorb.data();
+    t.dsf_h_dE = p.dsf_h_dE.data(); t.dsf_h_emit = p.dsf_h_emit.data(); t.dsf_h_absorb = p.dsf_h_absorb.data(); t.he_emit = p.he_emit.data(); t.he_absorb = p.he_absorb.data();
     const int NS = t.n_shells;
     auto pack_mfp = [&](const std::vector<std::vector<MFP>> &T, std::vector<double> &E, std::vector<double> &L, std::vector<double> *dEdx) {
         E = T[0][0].E;

@@ -210,12 +210,13 @@ RefCacheNames reference_cache_names(const Case &c) {
 // not reproduced, so the reference-format cache is refused for such inputs (the binary .trk3tab cache serves them).
 static bool closed_form_shells(const Case &c) {
     if (c.numpar.kind_of_DR == 4) return true;
+    if (c.numpar.kind_of_EMFP == 2) return true;        // DSF: the elastic tables are the DSF file's own, nothing to cache
     for (const auto &a : c.atoms) for (int k : a.KOCS) if (k == 2) return true;
     return false;
 }
 bool write_reference_cache(const Case &c, const std::string &out_root, int *n_files_out, std::string &err) {
     if (!c.tables_built) { err = "write_reference_cache: tables not built"; return false; }
-    if (closed_form_shells(c)) { err = "write_reference_cache: BEB shells / delta-function CDF have no differential tables; the reference-format cache is not written for them"; return false; }
+    if (closed_form_shells(c)) { err = "write_reference_cache: BEB shells / delta-function CDF / DSF scattering have no differential tables; the reference-format cache is not written for them"; return false; }
     const RefCacheNames n = reference_cache_names(c);
     const std::string dm = out_root + "/" + n.dir_material, di = out_root + "/" + n.dir_ion, dd = out_root + "/" + n.dir_diff;
     if (!make_dirs(di) || !make_dirs(dd)) { err = "cannot create " + di; return false; }
@@ -273,7 +274,7 @@ bool write_reference_cache(const Case &c, const std::string &out_root, int *n_fi
 }
 
 bool read_reference_cache(Case &c, const std::string &out_root, const BuildOptions &opt, std::string &err) {
-    if (closed_form_shells(c)) { err = "read_reference_cache: BEB shells / delta-function CDF have no differential tables; build the tables instead"; return false; }
+    if (closed_form_shells(c)) { err = "read_reference_cache: BEB shells / delta-function CDF / DSF scattering have no differential tables; build the tables instead"; return false; }
     get_single_pole(c);                                   // MAIN.f90:146 (before any table, cached or not)
     const RefCacheNames n = reference_cache_names(c);
     const std::string dm = out_root + "/" + n.dir_material, di = out_root + "/" + n.dir_ion, dd = out_root + "/" + n.dir_diff;

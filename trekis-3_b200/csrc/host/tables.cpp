@@ -291,6 +291,12 @@ bool build_tables(Case &c, const BuildOptions &opt, std::string &err) {
                 Elastic_cross_section(x, gridE[i], kind, S, dEdx, (c.numpar.kind_of_EMFP == 1) ? &Ed.row[i] : nullptr);
                 El.L[i] = S; El.dEdx[i] = dEdx;
             })) return false;
+        } else if (c.numpar.kind_of_EMFP == 2) {
+            // DSF: the elastic tables live on the DSF file's own energy grid (Analytical_IMFPs.f90:885-919); no differential rows --
+            // the transferred energy is sampled from the DSF rows themselves (NRG_transfer_elastic_DSF)
+            std::vector<double> emit, absorb;
+            dsf_elastic_tables(kind == 0 ? c.DSF_DEMFP : c.DSF_DEMFP_H, El, emit, absorb);
+            Ed.E = El.E; Ed.row.assign(El.E.size(), DiffRow{});
         } else {
             // kind_of_EMFP = -1: elastic scattering disabled (Analytical_IMFPs.f90 'No_elas'): infinite MFP
             for (int i = 0; i < Ne; ++i) { El.L[i] = 1.0e30; El.dEdx[i] = 0.0; }

@@ -32,6 +32,9 @@ inline double g_alpha() { return g_e * g_e / (g_h * g_cvel * 4.0 * g_Pi * g_e0);
 inline double g_v0() { return std::sqrt(2.0 * g_Ry * g_e / g_me); }
 
 // ---- Objects.f90:211-217 (type CDF)
+// one particle energy of a DSF table (Differential_MFP, Objects.f90:170-178): transferred-energy grid and the mean free paths
+// integrated up to each of its points (total, emission only, absorption only)
+struct DsfPoint { double E = 0; std::vector<double> dE, dL, dL_absorb, dL_emit; };
 struct CDFosc { std::vector<double> E0, A, Gamma, alpha; };   // alpha: weights of the delta-function CDF (kind_of_DR = 4)
 
 // ---- Objects.f90:257-275 (type Atom)
@@ -105,6 +108,7 @@ struct Case {                       // everything Read_input_file + MAIN.f90:120
     // tables (MAIN.f90:166-238)
     std::vector<std::vector<MFP>> SHI_MFP, diff_SHI_MFP, Total_el_MFPs, Total_Hole_MFPs, Total_Photon_MFPs;
     MFP Elastic_MFP, Elastic_Hole_MFP;
+    std::vector<DsfPoint> DSF_DEMFP, DSF_DEMFP_H;      // kind_of_EMFP = 2 (dsf.cpp)
     std::vector<std::vector<DiffCS>> EIdCS;   // [atom][shell]
     DiffCS EEdCS, HIdCS, HEdCS;
     int Lowest_Ip_At = 0, Lowest_Ip_Shl = 0;  // 0-based
@@ -121,6 +125,11 @@ int find_monoton_2d(const double *A, int stride, int N, double v);     // Find_i
 int find_monoton_decreasing(const double *A, int N, double v);         // Find_in_monoton_array_decreasing
 inline int find_monoton_1d(const std::vector<double> &A, double v) { return find_monoton_1d(A.data(), (int)A.size(), v); }
 double interpolate(int flag, double E1, double E2, double S1, double S2, double E);   // Cross_sections.f90:4051
+
+// ---- DSF elastic cross sections (dsf.cpp)
+std::string dsf_file_name(const Case &c, bool hole);
+bool read_dsf(const std::string &path, std::vector<DsfPoint> &out, bool &found, std::string &err);
+void dsf_elastic_tables(const std::vector<DsfPoint> &D, MFP &Total, std::vector<double> &Emit, std::vector<double> &Absorb);
 
 // ---- input (input.cpp)
 void set_default_numpar(NumPar &np);
@@ -221,6 +230,7 @@ struct Packed {
     std::vector<int64_t> dshi_off, eid_off, eed_off, hid_off, hed_off;
     std::vector<double> dshi_E, dshi_L, eid_hw, eid_L, eed_hw, eed_L, hid_hw, hid_L, hed_hw, hed_L;
     std::vector<double> dos_E, dos_DOS, dos_int, dos_effm, out_R, out_V, osc_E0, osc_alpha;
+    std::vector<double> dsf_e_dE, dsf_e_emit, dsf_e_absorb, ee_emit, ee_absorb, dsf_h_dE, dsf_h_emit, dsf_h_absorb, he_emit, he_absorb;
 };
 void pack_case(const Case &c, Packed &p);
 double define_alpha(double Ai, double Gammai, double E0i, double x_min);       // cdf.cpp

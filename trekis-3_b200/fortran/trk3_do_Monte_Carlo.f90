@@ -54,6 +54,8 @@ module trk3_gpu_binding
      real(c_double) :: shell_Ek(TRK3_MAX_SHELLS), at_dens                   ! Target_atoms%Ek, Matter%At_Dens
      integer(c_int32_t) :: delta_cdf, osc_off(TRK3_MAX_SHELLS + 1)          ! kind_of_DR = 4: oscillators of flat shell s = [osc_off(s), osc_off(s+1))
      type(c_ptr) :: osc_E0, osc_alpha                                       ! Target_atoms%Ritchi%E0 / %alpha, flattened
+     integer(c_int32_t) :: n_dsf_e; type(c_ptr) :: dsf_e_dE, dsf_e_emit, dsf_e_absorb, ee_emit, ee_absorb   ! DSF_DEMFP (kind_of_EMFP = 2)
+     integer(c_int32_t) :: n_dsf_h; type(c_ptr) :: dsf_h_dE, dsf_h_emit, dsf_h_absorb, he_emit, he_absorb   ! DSF_DEMFP_H
   end type
 
   type, bind(C) :: trk3_tally_layout                ! include/trekis3_gpu.h: trk3_tally_layout
@@ -153,6 +155,8 @@ subroutine do_Monte_Carlo(NMC, SHI, SHI_MFP, diff_SHI_MFP, Target_atoms, Lowest_
     integer(c_int64_t), allocatable, target :: dshi_off(:), eid_off(:), eed_off(:), hid_off(:), hed_off(:)
     real(c_double), allocatable, target :: dos_E(:), dos_DOS(:), dos_int(:), dos_effm(:), R_c(:), V_c(:)
     real(c_double), allocatable, target :: buf(:), osc_E0(:), osc_alpha(:)
+    real(c_double), allocatable, target :: dsf_e_dE(:), dsf_e_emit(:), dsf_e_absorb(:), ee_emit(:), ee_absorb(:)
+    real(c_double), allocatable, target :: dsf_h_dE(:), dsf_h_emit(:), dsf_h_absorb(:), he_emit(:), he_absorb(:)
     integer :: n_osc, l
 
     Nat = size(Target_atoms)
@@ -220,6 +224,13 @@ subroutine do_Monte_Carlo(NMC, SHI, SHI_MFP, diff_SHI_MFP, Target_atoms, Lowest_
     enddo
     tab%osc_off(q + 1:) = n_osc
     tab%osc_E0 = c_loc(osc_E0); tab%osc_alpha = c_loc(osc_alpha)
+    ! ---- DSF elastic scattering (kind_of_EMFP = 2): the rows of DSF_DEMFP / DSF_DEMFP_H, [particle energy][transferred energy]
+    call flatten_dsf(DSF_DEMFP, Elastic_MFP%Emit%L, Elastic_MFP%Absorb%L, tab%n_dsf_e, dsf_e_dE, dsf_e_emit, dsf_e_absorb, ee_emit, ee_absorb)
+    call flatten_dsf(DSF_DEMFP_H, Elastic_Hole_MFP%Emit%L, Elastic_Hole_MFP%Absorb%L, tab%n_dsf_h, dsf_h_dE, dsf_h_emit, dsf_h_absorb, he_emit, he_absorb)
+    tab%dsf_e_dE = c_loc(dsf_e_dE); tab%dsf_e_emit = c_loc(dsf_e_emit); tab%dsf_e_absorb = c_loc(dsf_e_absorb)
+    tab%ee_emit = c_loc(ee_emit); tab%ee_absorb = c_loc(ee_absorb)
+    tab%dsf_h_dE = c_loc(dsf_h_dE); tab%dsf_h_emit = c_loc(dsf_h_emit); tab%dsf_h_absorb = c_loc(dsf_h_absorb)
+    tab%he_emit = c_loc(he_emit); tab%he_absorb = c_loc(he_absorb)
 
     ! ---- mean free paths: one energy grid per family, rows [shell][energy]
     call flatten_mfp(Total_el_MFPs, ei_E, ei_L)
@@ -348,6 +359,28 @@ contains
           enddo
        enddo
     end subroutine flatten_mfp
+
+    subroutine flatten_dsf(D, Lem, Lab, nW, dE, em, ab, Lem_c, Lab_c)    ! Differential_MFP(iE)%{dE,dL_emit,dL_absorb} -> rows [iE][transfer]
+       type(Differential_MFP), dimension(:), intent(in) :: D
+       real(8), dimension(:), allocatable, intent(in) :: Lem, Lab           ! Elastic_MFP%Emit%L, %Absorb%L (allocated for kind_of_EMFP = 2 only)
+       integer(c_int32_t), intent(out) :: nW
+       real(c_double), allocatable, intent(out) :: dE(:), em(:), ab(:), Lem_c(:), Lab_c(:)
+       integer :: i1
+       nW = 0
+       if (size(D) > 0 .and. NumPar%kind_of_EMFP == 2) nW = size(D(1)%dE)
+       if (nW == 0) then
+          allocate(dE(1), em(1), ab(1), Lem_c(1), Lab_c(1))
+          dE = 0.0d0; em = 0.0d0; ab = 0.0d0; Lem_c = 0.0d0; Lab_c = 0.0d0
+          return
+       endif
+       allocate(dE(size(D) * nW), em(size(D) * nW), ab(size(D) * nW), Lem_c(size(D)), Lab_c(size(D)))
+       do i1 = 1, size(D)
+          dE((i1 - 1) * nW + 1 : i1 * nW) = D(i1)%dE
+          em((i1 - 1) * nW + 1 : i1 * nW) = D(i1)%dL_emit
+          ab((i1 - 1) * nW + 1 : i1 * nW) = D(i1)%dL_absorb
+       enddo
+       Lem_c = Lem; Lab_c = Lab
+    end subroutine flatten_dsf
 
     subroutine flatten_dcs(D, off, hw, L)    ! diff_CS%diffCS(iE)%{hw,dsdhw} -> CSR
        type(diff_CS), intent(in) :: D

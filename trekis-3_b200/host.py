@@ -88,10 +88,12 @@ def make_run_dir(path, config="C1", data_dir=None, nmc=None, extra_lines=("gnupl
     lines = lines[:19] + list(extra_lines)
     with open(os.path.join(path, "INPUT_PARAMETERS.txt"), "w") as f:
         f.write("\n".join(lines) + "\n")
-    for d in ("INPUT_CDF", "INPUT_DOS", "INPUT_EADL"):
+    for d in ("INPUT_CDF", "INPUT_DOS", "INPUT_EADL", "INPUT_DSF"):
         dst = os.path.join(path, d)
         if os.path.islink(dst) or os.path.exists(dst):
             continue
+        if d == "INPUT_DSF" and not os.path.isdir(os.path.join(data_dir, d)):
+            continue                        # DSF cross sections (kind_of_EMFP = 2) are optional inputs; the reference ships none
         os.symlink(os.path.join(data_dir, d), dst)
     return path
 
@@ -157,6 +159,9 @@ class Case:
         # every file the reader opened: the .cdf / .dos actually used (the optional 'CDF <file>' / 'DOS <file>' flags redirect
         # them) and the atomic data bases that supply what a .cdf leaves out (masses, Ip, Nel, Ek, decay times, form factors)
         rels = [self.get_string("cdf_file"), self.get_string("dos_file")]
+        mat = self.get_string("material")
+        if os.path.isdir(os.path.join(self.dir, "INPUT_DSF", mat)):
+            rels += [f"INPUT_DSF/{mat}/{n}" for n in sorted(os.listdir(os.path.join(self.dir, "INPUT_DSF", mat)))]
         rels += [f"INPUT_EADL/{n}" for n in ("INPUT_atomic_data.dat", "radiative_widths.dat", "EADL2023.ALL", "EPDL2023.ALL",
                                               "Atomic_form_factors.dat")]
         for rel in rels:
