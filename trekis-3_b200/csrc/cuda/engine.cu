@@ -105,7 +105,8 @@ struct QueueSet { Queue q[N_QUEUES]; };
 #define S_EV 0                      // s_cnt layout: events[TRK3_N_EVENT_CLASSES], n_el, n_ph
 #define S_NEL TRK3_N_EVENT_CLASSES
 #define S_NPH (TRK3_N_EVENT_CLASSES + 1)
-#define S_NCNT (TRK3_N_EVENT_CLASSES + 2)
+#define S_DONE (TRK3_N_EVENT_CLASSES + 2)     // warps of the block that have finished (block_epilogue_last_warp)
+#define S_NCNT (TRK3_N_EVENT_CLASSES + 3)
 
 // ------------------------------------------------------------------------------------------------
 // device context: the side effects of physics.cuh
@@ -236,6 +237,40 @@ __device__ inline void block_epilogue(const DevP &p, double *s_tally, unsigned i
         if (cold_species == SP_VBHOLE && s_cnt[S_EV + TRK3_EV_VBH_ELAST]) atomicAdd(p.cnt_el + (warm ? 5 : 3), (unsigned long long)s_cnt[S_EV + TRK3_EV_VBH_ELAST]);
         if (s_cnt[S_NEL]) atomicAdd(p.cnt_el, (unsigned long long)s_cnt[S_NEL]);
         if (s_cnt[S_NPH]) atomicAdd(p.cnt_ph, (unsigned long long)s_cnt[S_NPH]);
+    }
+}
+
+// The same closing WITHOUT a block-wide barrier, for the hot kernels: there a block lives as long as its longest history, and
+// with a barrier at the end every warp that has finished sits in it until then (ncu: stall `barrier` 2-6 cycles per issued
+// instruction in k_hot).  Instead a warp that is done counts itself out and leaves; the LAST warp to arrive flushes the block's
+// private tallies and counters with its 32 lanes.  (The warps' shared-memory atomics are ordered before their count-out by the
+// block-level fence; the last arriver reads after its own atomic on the same counter.)
+__device__ inline void block_epilogue_last_warp(const DevP &p, double *s_tally, unsigned int *s_cnt, bool elat_only) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    __threadfence_block();
+    unsigned last = 0u;
+    if (lane == 0) last = (atomicAdd(&s_cnt[S_DONE], 1u) == (blockDim.x >> 5) - 1u) ? 1u : 0u;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence_block();
+    const volatile double *st = s_tally;
+    const volatile unsigned int *sc = s_cnt;
+    if (s_tally && elat_only) {
+        double *g = p.tally + p.g_off[TRK3_OUT_ELAT];
+        for (int i = lane; i < p.s_len[TRK3_OUT_ELAT]; i += 32) { const double v = st[i]; if (v != 0.0) atomicAdd(g + i, v); }
+    } else if (s_tally) {
+        for (int id = 0; id < TRK3_N_TALLIES; ++id) {
+            const int so = p.s_off[id];
+            if (so < 0) continue;
+            double *g = p.tally + p.g_off[id];
+            for (int i = lane; i < p.s_len[id]; i += 32) { const double v = st[so + i]; if (v != 0.0) atomicAdd(g + i, v); }
+        }
+    }
+    if (lane < TRK3_N_EVENT_CLASSES) { const unsigned v = sc[S_EV + lane]; if (v) atomicAdd(&p.events[lane], (unsigned long long)v); }
+    if (lane == 0) {
+        if (sc[S_NEL]) atomicAdd(p.cnt_el, (unsigned long long)sc[S_NEL]);
+        if (sc[S_NPH]) atomicAdd(p.cnt_ph, (unsigned long long)sc[S_NPH]);
     }
 }
 
@@ -819,7 +854,7 @@ __global__ void __launch_bounds__(TRK_BLOCK_MAX, TRK_HOT_MIN_BLOCKS) k_hot(TRK_P
             }
         }
     }
-    block_epilogue(c_p, s_tally, s_cnt, -1, 0, LEAN);
+    block_epilogue_last_warp(c_p, s_tally, s_cnt, LEAN);
 }
 
 __global__ void k_iter_prefix(TRK_P2, FoldAux a) {
