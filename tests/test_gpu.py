@@ -198,10 +198,9 @@ def test_dsf_elastic_scattering_on_the_gpu(tmp_path, cfg, material):
     case = tk.Case.load(dsf_run_dir(tmp_path, cfg=cfg, material=material))
     case.build_tables(**FULL)
     assert case.config.kind_of_EMFP == 2 and case.tables.n_dsf_e > 2
-    # the hole spectra are normalised per grid time by the number of MOBILE holes (Ehkin > 0): with DSF a hole can sit at exactly the
-    # top of the band after a collision, and one such hole counted on the other side rescales a whole row of the 5 x 212 array
-    # (and a hole whose kinetic energy lands within rounding of zero is mobile on one side only: a few more bins may move by it)
-    sg, so = check_against_oracle(case, 4, hole_spectrum_bins=0.75, max_bad_bins=8)
+    # (diamond: a cold valence hole that ABSORBS lattice energy leaves the cold range; the case found a hole in the hand-back of
+    # such carriers -- one without a collision left before Tim was queued behind the running cold launch and lost its last snapshots)
+    sg, so = check_against_oracle(case, 4)
     assert sg["events"]["el_elastic"] > 5000 and sg["events"]["vbh_elastic"] > 5000
 
 

@@ -478,7 +478,7 @@ __device__ inline void electron_collision_warp(C &c, Rec &e, int iv, Cache &k, P
         if (hw >= Eel) hw = Eel;
         dE = hw;
         // cos_theta_from_W + Update_particle_angles_lat (angles_lattice, M_eff = 1)
-        const double Erest_in = rest_energy(1.0 * TRK_ME), Erest_t = rest_energy(p.Mtarget);
+        const double Erest_in = rest_energy(1.0 * TRK_ME), Erest_t = p.Erest_target;
         const double E2mc = Eel + 2.0 * Erest_in, EmW = Eel - dE;
         const double W1 = Eel * E2mc - dE * (Eel + Erest_in + Erest_t);
         const double W2 = Eel * E2mc * EmW * (E2mc - dE);

@@ -147,6 +147,7 @@ inline int fill_devp_scalars(const trk3_config &c, const trk3_tables &T, const t
         sm += T.atom_mass[a] * T.atom_pers[a]; sp += T.atom_pers[a];
     }
     p.Mtarget = g_Mp * sm / sp; p.sum_pers = sp;
+    p.Erest_target = p.Mtarget * 299792458.0 * 299792458.0 / 1.602176487e-19;      // rest_energy (physics.cuh), the same operations
     for (int s = 0; s < T.n_shells; ++s) {
         p.shell_atom[s] = T.shell_atom[s]; p.shell_num[s] = T.shell_num[s]; p.shell_Ip[s] = T.shell_Ip[s];
         p.shell_Nel[s] = T.shell_Nel[s]; p.shell_auger[s] = T.shell_auger[s]; p.shell_radiat[s] = T.shell_radiat[s];

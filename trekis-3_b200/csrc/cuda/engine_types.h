@@ -88,6 +88,7 @@ struct DevP {
     double ion_E, ion_mass, ion_fixed_Zeff, ion_Zeff0;
     double Tim, cut_off, layer, hole_mass, work_function, bar_height, Em_E1, Em_gamma;
     double Egap, Mtarget, sum_pers;
+    double Erest_target;                 // rest_energy(Mtarget) [eV], evaluated once (angles_lattice needs it at every elastic collision)
     int32_t ion_Z, ion_kind_Zeff, include_photons, kind_of_EMFP;
     uint32_t seed_lo, seed_hi;
     // ---- target (trk3_tables header)

@@ -363,6 +363,33 @@ TRK_HD double sample_row_at(const Csr &t, int64_t o, int n, int i_hw, double L_n
     const double *lL = t.lL + o;
     return interp5t_l(L[i_hw - 1], L[i_hw], hw[i_hw - 1], hw[i_hw], lL[i_hw - 1], lL[i_hw], lhw[i_hw - 1], lhw[i_hw], L_need, lLn, lres);
 }
+// The same sample without its final exponential: the across-energy interpolation of interpolate_transferred_energy only needs the
+// LOGARITHM of the two row samples (interp5t works in log space), so the two exponentials per sampled energy are not evaluated
+// unless a rare branch asks for the values themselves.  `direct` = the sample is a table entry (hw then holds it), else hw is
+// not set and lres is the exponent interp5t_l would have passed to m_exp.
+TRK_HD void sample_row_log(const Csr &t, int64_t o, int n, int i_hw, double L_need, double lLn, double &lres, double &hw, bool &direct) {
+    const double *L = t.L + o, *hwv = t.hw + o, *lhw = t.lhw + o;
+    if (i_hw == 1 || i_hw == n) { lres = lhw[i_hw - 1]; hw = hwv[i_hw - 1]; direct = true; return; }
+    const double E1 = L[i_hw - 1], E2 = L[i_hw];
+    if (fabs(E2 - E1) < 1.0e-6) { const double S1 = hwv[i_hw - 1], S2 = hwv[i_hw]; direct = true; if (S1 > S2) { lres = lhw[i_hw - 1]; hw = S1; } else { lres = lhw[i_hw]; hw = S2; } return; }
+    if (L_need == E1) { lres = lhw[i_hw - 1]; hw = hwv[i_hw - 1]; direct = true; return; }
+    const double *lL = t.lL + o;
+    lres = lhw[i_hw - 1] + m_div(lhw[i_hw] - lhw[i_hw - 1], lL[i_hw] - lL[i_hw - 1]) * (lLn - lL[i_hw - 1]);
+    direct = false;
+}
+#define TRK_LN_1E_10 (-23.025850929940457)        // log(1e-10): exp(x) < 1e-10 <=> x < log(1e-10)
+// the tail of interpolate_transferred_energy (Cross_sections.f90:2020-2045) from the two row samples in log form
+TRK_HD double combine_rows_log(const Csr &t, int i_E, double lhw_1, double hw_1, bool d1, double lhw_2, double hw_2, bool d2, double Ele, double lE) {
+    const double E1 = t.Eg[i_E - 1], E2 = t.Eg[i_E];
+    const bool tiny = (d1 ? hw_1 < 1.0e-10 : lhw_1 < TRK_LN_1E_10) || (d2 ? hw_2 < 1.0e-10 : lhw_2 < TRK_LN_1E_10);
+    if (tiny || fabs(E2 - E1) < 1.0e-6 || Ele == E1) {           // the branches that need the samples themselves: rare
+        if (!d1) hw_1 = m_exp(lhw_1);
+        if (!d2) hw_2 = m_exp(lhw_2);
+        if (hw_1 < 1.0e-10 || hw_2 < 1.0e-10) return interp1(E1, E2, hw_1, hw_2, Ele);
+        return interp5t(E1, E2, hw_1, hw_2, t.lEg[i_E - 1], t.lEg[i_E], lhw_1, lhw_2, Ele, lE);
+    }
+    return m_exp(lhw_1 + m_div(lhw_2 - lhw_1, t.lEg[i_E] - t.lEg[i_E - 1]) * (lE - t.lEg[i_E - 1]));      // interp5t, same arithmetic
+}
 TRK_HD double sample_row(const Csr &t, int64_t o, int n, double L_need, double lLn) {
     const double *L = t.L + o, *hw = t.hw + o;
     int i_hw = find_dec(L, n, L_need);
@@ -379,12 +406,12 @@ TRK_HDN double transferred_energy(const Csr &t, double Ele, double lE, int i_E, 
     const int n1 = (int)(t.off[i_E] - o), n2 = (int)(o - o2);
     int i1, i2;
     find_dec2(t.L + o, n1, t.L + o2, n2, L_need, i1, i2);
-    double lhw_1, lhw_2;
-    double hw_1 = sample_row_at(t, o, n1, i1, L_need, lLn, lhw_1);
+    double lhw_1, lhw_2, hw_1 = 0.0, hw_2 = 0.0;
+    bool d1, d2;
+    sample_row_log(t, o, n1, i1, L_need, lLn, lhw_1, hw_1, d1);
     i_E = i_E - 1;
-    double hw_2 = sample_row_at(t, o2, n2, i2, L_need, lLn, lhw_2);
-    if (hw_1 < 1.0e-10 || hw_2 < 1.0e-10) return interp1(t.Eg[i_E - 1], t.Eg[i_E], hw_1, hw_2, Ele);
-    return interp5t(t.Eg[i_E - 1], t.Eg[i_E], hw_1, hw_2, t.lEg[i_E - 1], t.lEg[i_E], lhw_1, lhw_2, Ele, lE);
+    sample_row_log(t, o2, n2, i2, L_need, lLn, lhw_2, hw_2, d2);
+    return combine_rows_log(t, i_E, lhw_1, hw_1, d1, lhw_2, hw_2, d2, Ele, lE);
 }
 TRK_HD Csr csr_eid(const DevP &p, int shell) { return Csr{p.ei_E, p.lei_E, p.n_ei, p.eid_off + (size_t)shell * p.n_ei, p.eid_hw, p.eid_L, p.leid_hw, p.leid_L}; }
 TRK_HD Csr csr_eed(const DevP &p) { return Csr{p.ee_E, p.lee_E, p.n_ee, p.eed_off, p.eed_hw, p.eed_L, p.leed_hw, p.leed_L}; }
@@ -584,7 +611,7 @@ TRK_HD double elastic_dE(const DevP &p, Rec &r, double Eel, const Cache &k, doub
 
 // cos_theta_from_W + Update_particle_angles_lat, Monte_Carlo.f90:1252-1299
 TRK_HD void angles_lattice(const DevP &p, Rec &r, double E, double W, double M_eff, double &theta, double &phi) {
-    double Erest_in = rest_energy(M_eff * TRK_ME), Erest_t = rest_energy(p.Mtarget);
+    double Erest_in = rest_energy(M_eff * TRK_ME), Erest_t = p.Erest_target;
     double E2mc = E + 2.0 * Erest_in, EmW = E - W;
     double W1 = E * E2mc - W * (E + Erest_in + Erest_t);
     double W2 = E * E2mc * EmW * (E2mc - W);
@@ -1392,7 +1419,11 @@ TRK_HD int step_vbhole(C &c, Rec &h, int &ig, Cache &k, bool warm = false) {
         if (!warm) { event_begin(h); RN = rn(p, h); }
         vbhole_event_t<EV_ELASTIC>(c, h, ig, k, RN);
         if (warm) return (h.Ehkin < p.h_cold || !(h.tn < p.Tim) || !(h.Ehkin < p.h_warm)) ? ST_MOVE : ST_CONT;
-        return (h.Ehkin < p.h_cold) ? ST_CONT : ST_MOVE;
+        // A hole that a collision has lifted out of the cold range (level snapping; absorption of lattice energy with DSF
+        // scattering) goes back to the full handlers -- unless it has no collision left before Tim: then it only has snapshots to
+        // deposit and stays here.  (Handed to push() it would be routed to the cold queue again, behind the records the running
+        // cold launch covers, and its last snapshots would be lost.)
+        return (h.Ehkin < p.h_cold || !(h.tn < p.Tim)) ? ST_CONT : ST_MOVE;
     }
     event_begin(h);
     vbhole_event_t<EV_ANY>(c, h, ig, k, rn(p, h));
