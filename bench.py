@@ -482,7 +482,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--nmc", type=int, default=None, help="iterations per step (default: the config's NMC)")
-    ap.add_argument("--batch", type=int, default=1024, help="iterations in flight on the GPU")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="iterations in flight on the GPU (default: 4096 for the high-statistics configuration C5, else 1024: a C2 step "
+                         "of 1000 iterations is one batch)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
@@ -491,6 +493,8 @@ def main():
     args = ap.parse_args()
     if args.scaling is None:
         args.scaling = "strong" if args.config == "C5" else "weak"
+    if args.batch is None:
+        args.batch = 4096 if args.config == "C5" else 1024
     protect_stdout()
     import trekis3_b200 as tk
     if args.nmc is None:

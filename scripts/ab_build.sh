@@ -7,7 +7,7 @@
 set -eu
 cd "$(dirname "$0")/../trekis-3_b200/csrc"
 mkdir -p ../../.ab
-BASE="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -DTRK_MATH_OUTLINE -DTRK_PHILOX_ROLLED"
+BASE="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -DTRK_MATH_OUTLINE"   # + the switches under test (the Makefile adds -DTRK_PHILOX_UNROLL=5)
 [ -f cuda/tables_gpu.o ] || nvcc $BASE -fmad=false -c -o cuda/tables_gpu.o cuda/tables_gpu.cu
 while [ $# -ge 2 ]; do
     name=$1; flags=$2; shift 2

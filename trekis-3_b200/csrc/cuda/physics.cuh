@@ -74,23 +74,44 @@ TRK_HD uint32_t trk_mulhi(uint32_t a, uint32_t b) {
     return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
-// The wave kernels are bound by instruction FETCH (ncu: gcc__cache_requests_type_instruction at 98 % of peak, SM
-// instruction-cache hit rate 58 %): what counts is the number of distinct instruction lines a collision streams through,
-// not the number of instructions it executes.  TRK_PHILOX_ROLLED keeps the ten rounds as a loop (one round of code).
-TRK_HDN void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3) {
-#if defined(TRK_PHILOX_ROLLED) && defined(__CUDA_ARCH__)
-#pragma unroll 1
+// The wave kernels are bound by instruction issue AND fetch (a 66 KB loop body against a 32 KB instruction cache): the ten
+// rounds stay a loop, but of FIVE rounds per trip (measured, profiles/r2u_sweep_philox_builds.txt, C2 step / 4096-iteration
+// batch in ms: one round per trip 12.81 / 53.89, two 12.77 / 53.05, five 12.77 / 52.61, straight-line 12.87 / 53.04, one
+// out-of-line straight-line copy 12.83 / 53.46).  Per cold collision the two Philox blocks were 17 % of the thread instructions.
+// Build switches (A/B builds: scripts/ab_build.sh, profiles/r2u_*): TRK_PHILOX_UNROLL = rounds per trip of the loop (1 = rolled,
+// 10 = straight-line code), TRK_PHILOX_OUTLINE = one out-of-line copy per kernel that returns its four words in registers.
+// The products are formed as 64-bit mul.wide (one IMAD.WIDE per pair of halves instead of IMAD.HI + IMAD).
+struct Phx4 { uint32_t x, y, z, w; };
+#if defined(__CUDA_ARCH__) && defined(TRK_PHILOX_OUTLINE)
+#define TRK_PHX __device__ __noinline__
 #else
-#pragma unroll
+#define TRK_PHX TRK_HD
+#endif
+#if !defined(TRK_PHILOX_UNROLL)
+#if defined(TRK_PHILOX_ROLLED)
+#define TRK_PHILOX_UNROLL 1
+#else
+#define TRK_PHILOX_UNROLL 10
+#endif
+#endif
+#define TRK_PRAGMA(x) _Pragma(#x)
+#define TRK_UNROLL(n) TRK_PRAGMA(unroll n)
+TRK_PHX Phx4 philox4x32_10v(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#if defined(__CUDA_ARCH__)
+    TRK_UNROLL(TRK_PHILOX_UNROLL)
 #endif
     for (int r = 0; r < 10; ++r) {
-        uint32_t h0 = trk_mulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        uint32_t h1 = trk_mulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
-        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+    Phx4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+TRK_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3) {
+    const Phx4 o = philox4x32_10v(c0, c1, c2, c3, k0, k1);
+    o0 = o.x; o1 = o.y; o2 = o.z; o3 = o.w;
 }
 // uniform in (0,1]: the reference can draw RN = 0 (m_log(RN), L/RN -> inf); we exclude it
 // Draw k of a stream is half (k & 1) of Philox block k >> 1: one Philox evaluation serves two consecutive draws (the
@@ -629,8 +650,10 @@ TRK_HDN void new_angles_c(double phi0, double theta0, double cos_theta0, double 
     theta1 = theta0 + theta * ps.c;
     while (theta1 < 0.0) { theta1 = fabs(theta1); phi1 = phi1 + TRK_PI; }
     while (theta1 > TRK_PI) { theta1 = 2.0 * TRK_PI - theta1; phi1 = phi1 - TRK_PI; }
-    if (phi1 > 2.0 * TRK_PI) phi1 = phi1 - floor(phi1 / (2.0 * TRK_PI)) * 2.0 * TRK_PI;
-    if (phi1 < 0.0) phi1 = phi1 + ceil(fabs(phi1) / (2.0 * TRK_PI)) * 2.0 * TRK_PI;
+    // (:1353-1358) phi0 is in [0, 2 pi] and the steps above move it by at most 2 pi, so the number of turns to take off is ONE
+    // almost always: floor / ceil of the quotient is then 1 and the division need not be evaluated (same value: 1 * 2 * pi)
+    if (phi1 > 2.0 * TRK_PI) phi1 = (phi1 < 4.0 * TRK_PI) ? phi1 - 2.0 * TRK_PI : phi1 - floor(phi1 / (2.0 * TRK_PI)) * 2.0 * TRK_PI;
+    if (phi1 < 0.0) phi1 = (phi1 >= -2.0 * TRK_PI) ? phi1 + 2.0 * TRK_PI : phi1 + ceil(fabs(phi1) / (2.0 * TRK_PI)) * 2.0 * TRK_PI;
 }
 TRK_HD void new_angles(double phi0, double theta0, double theta, double psi, double &phi1, double &theta1) { new_angles_c(phi0, theta0, m_cos(theta0), theta, psi, phi1, theta1); }
 // Update_holes_angles_SHI, :1132-1140: isotropic in ANGLE (theta uniform), as the reference
