@@ -438,6 +438,20 @@ def run_ours(args):
                         "stall no_instruction 2-3 cycles per issued instruction), the hot cascade also by the latency of its longest history; "
                         "the hot/warm/core-hole/photon kernels of one generation run on concurrent streams, so their class times overlap"}
 
+    # ---- the same workload with the GPU filled: a step of `nmc` iterations is one latency-bound batch (a chain of ~10 hot
+    # generations whatever the batch size); 4096 iterations in flight give the throughput figure of the engine (state both)
+    throughput = None
+    if world == 1 and args.config != "C5" and not args.no_throughput:
+        try:
+            eng_t = tk.Engine(case, device=local_rank, batch=4096)
+            eng_t.run_device(10_000_000, 10_000_000 + 4096)                       # warm-up: allocates the queues of 4096 iterations
+            best = min(eng_t.run_device(10_000_000 + 4096 * (i + 1), 10_000_000 + 4096 * (i + 2))["device_ms"] for i in range(2))
+            throughput = {"iterations_in_flight": 4096, "ms_per_4096_iterations": best, "value": 4096.0 / (best * 1e-3), "unit": UNIT,
+                          "note": "device time of one 4096-iteration batch of the same configuration, tables resident (min of 2 after a warm-up)"}
+            eng_t.close()
+        except Exception as e:                       # never lose the headline over the side figure
+            throughput = {"error": str(e)}
+
     # ---- CPU baseline: oracle on the host cores, bounded sample of the same workload
     cpu = None
     if not args.no_cpu_baseline:
@@ -451,6 +465,8 @@ def run_ours(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.config, nmc), "iterations_in_flight": args.batch,
+                   "step": f"one step = one call of {nmc} iterations = ONE batch: latency-bound by the chain of hot generations; "
+                           "`throughput` holds the same configuration with 4096 iterations in flight",
                    "l2": "256 MiB buffer written between timed steps (L2 flush); queues stream through HBM",
                    "parallelism": (f"{nmc} iterations per step split contiguously over {world} GPU(s) (strong scaling)" if strong else
                                    f"every one of {world} GPU(s) runs its own {nmc} iterations per step (weak scaling)") +
@@ -464,6 +480,7 @@ def run_ours(args):
                 "note": "trekis3_b200.do_Monte_Carlo(case) with host buffers: configuration + tables host->device, MC, tallies and "
                         "per-iteration energies device->host in every call; the plugin handle (device queues) persists between calls"},
         "gpu_launches": launches,
+        "throughput": throughput,
         "kernel_times_ms": ktimes,
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -487,6 +504,7 @@ def main():
                          "of 1000 iterations is one batch)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-throughput", action="store_true", help="skip the side figure with 4096 iterations in flight")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="N > 1: weak = NMC iterations per rank and step (default), strong = NMC iterations per step split over the "
                          "ranks (default for --config C5, the configuration BASELINE.json names for 1/2/4/8 GPUs)")

@@ -19,7 +19,7 @@ METRICS=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__
 mkdir -p $OUT
 for stage in $STAGES; do case $stage in
 list)
-    timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches_ncu.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_ncu_bench.log 2>&1
+    timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches_ncu.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-throughput > $OUT/${TAG}_ncu_bench.log 2>&1
     ;;
 classes)
     for spec in "C2 C2 1000" "C5 C1 4096 batch=4096"; do
