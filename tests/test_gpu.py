@@ -535,3 +535,30 @@ def test_two_engines_on_one_device_from_two_threads(case_c1):
         assert out["a"][1]["total_events"] == sa["total_events"] and out["b"][1]["total_events"] == sb["total_events"]
         assert rel_close(out["a"][0], ref_a, 1e-9) and rel_close(out["b"][0], ref_b, 1e-9)
         assert not out["a"][1]["errors"] and not out["b"][1]["errors"]
+
+
+def test_persistent_handle_rebinds_tables_of_the_same_shapes(tmp_path, case_c1):
+    """do_Monte_Carlo keeps its engine between calls and copies the inputs host->device again in every call (the call a host
+    code makes, bench.py's e2e path): the re-binding goes through the pinned staging mirror in one DMA per run of arrays.
+    Two materials' worth of inputs with the same table shapes (two charge models of the ion) alternate on one handle: every
+    call must give exactly what a fresh engine gives, with the staged and with the direct upload path."""
+    other = tk.Case.load(tk.make_run_dir(str(tmp_path / "r"), "C1", edits={10: "1   23.5   ! kind of Zeff; fixed value"}))
+    other.build_tables(cache_dir=CACHE, **FULL)
+    assert tk.engine._shape_key(other, -1) == tk.engine._shape_key(case_c1, -1)
+    fresh = {}
+    for name, case in (("a", case_c1), ("b", other)):
+        eng = tk.Engine(case)
+        fresh[name] = eng.run(3, 9)
+        eng.close()
+    assert fresh["a"][1]["events"] != fresh["b"][1]["events"]          # the two inputs do differ
+    tk.release_handles()
+    try:
+        for stage in (1, 0):
+            for name, case in (("a", case_c1), ("b", other), ("b", other), ("a", case_c1)):
+                t, s = tk.do_Monte_Carlo(case, NMC=6, it_begin=3, stage_uploads=stage)
+                assert s["events"] == fresh[name][1]["events"], (stage, name)
+                assert rel_close(t, fresh[name][0], 1e-9), (stage, name)          # fp64 atomics: the order of the additions is free
+                assert not s["errors"]
+        assert len(tk.engine._handles) == 1
+    finally:
+        tk.release_handles()

@@ -871,9 +871,14 @@ __global__ void k_fold(TRK_P2, FoldAux a, int64_t njobs) {      // one warp per 
     if ((threadIdx.x & 31) == 0 && dst) *dst += sum;
 }
 // companion arrays of the tables (TRK3_COMPANIONS): evaluated on the device so that they carry the device's log()
-__global__ void k_companion(double *dst, const double *src, size_t n, int op) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = companion_value(src[i], op);
+struct CompanionJob { double *dst; const double *src; unsigned long long n; int op; };
+#define TRK_MAX_COMPANIONS 32
+struct CompanionJobs { CompanionJob j[TRK_MAX_COMPANIONS]; int nj; };
+// all companion arrays in one launch: blockIdx.y = array, the blocks of a row stride over its elements
+__global__ void k_companions(const CompanionJobs jobs) {
+    const CompanionJob jb = jobs.j[blockIdx.y];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < jb.n; i += (size_t)gridDim.x * blockDim.x)
+        jb.dst[i] = companion_value(jb.src[i], jb.op);
 }
 // end of a generation: remember the fill of the ionisation queue (overflow check on the host) and empty it
 __global__ void k_ion_reset(uint32_t *cnt) { if (threadIdx.x == 0) { if (cnt[0] > cnt[1]) cnt[1] = cnt[0]; cnt[0] = 0; } }
@@ -937,6 +942,13 @@ struct trk3_engine {
     char *tab_arena = nullptr; size_t tab_arena_cap = 0, tab_arena_used = 0;
     int opt_l2_persist = 1, l2_persist_applied = 0;
     uint64_t h2d_bytes = 0;                 // bytes of the last table binding
+    // A table RE-binding (the per-call input copy of a persistent handle) goes through a pinned host mirror of the arena: every
+    // array is copied into the mirror at its arena offset and a contiguous run of arrays leaves in ONE DMA (stage_flush),
+    // instead of ~60 pageable copies with a synchronisation behind every temporary (option "stage_uploads", default on).
+    char *stage = nullptr; size_t stage_cap = 0, stage_lo = (size_t)-1, stage_hi = 0;
+    bool staging = false, direct_pending = false, stage_in_flight = false;
+    cudaEvent_t ev_stage = nullptr;
+    int opt_stage_uploads = 1;
     double nel_est = 1000.0;
     // options
     uint32_t *h_qcount = nullptr;       // pinned ring of counter snapshots (run-ahead generation loop)
@@ -1119,9 +1131,35 @@ int dev_upload(trk3_engine *eng, const T **dst, const T *src, size_t n) {
     T *d = nullptr;
     int rc = tab_alloc(eng, &d, n);
     if (rc) return rc;
-    if (n && src) CK(cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, eng->stream));
+    if (n && src) {
+        const size_t bytes = n * sizeof(T);
+        const char *dc = (const char *)d;
+        if (eng->staging && dc >= eng->tab_arena && dc + bytes <= eng->tab_arena + eng->stage_cap) {
+            const size_t at = (size_t)(dc - eng->tab_arena);
+            std::memcpy(eng->stage + at, src, bytes);
+            eng->stage_lo = std::min(eng->stage_lo, at); eng->stage_hi = std::max(eng->stage_hi, at + bytes);
+        } else {
+            CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, eng->stream));
+            eng->direct_pending = true;
+        }
+    }
     *dst = d;
     eng->h2d_bytes += n * sizeof(T);
+    return TRK3_OK;
+}
+// the staged arrays collected since the last flush: one DMA out of the pinned mirror (the alignment gaps travel with them)
+int stage_flush(trk3_engine *eng) {
+    if (eng->stage_hi > eng->stage_lo) {
+        CK(cudaMemcpyAsync(eng->tab_arena + eng->stage_lo, eng->stage + eng->stage_lo, eng->stage_hi - eng->stage_lo, cudaMemcpyHostToDevice, eng->stream));
+        CK(cudaEventRecord(eng->ev_stage, eng->stream));
+        eng->stage_in_flight = true;
+    }
+    eng->stage_lo = (size_t)-1; eng->stage_hi = 0;
+    return TRK3_OK;
+}
+// a host temporary that was handed to dev_upload is about to go out of scope (or to be re-used)
+int release_sources(trk3_engine *eng) {
+    if (eng->direct_pending) { CK(cudaStreamSynchronize(eng->stream)); eng->direct_pending = false; }
     return TRK3_OK;
 }
 void dev_free(trk3_engine *eng, void *p) {
@@ -1309,6 +1347,20 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
     // everything of the previous DevP that does not come from the tables survives a reload
     const DevP old = eng->hp;
     eng->tab_cursor = 0; eng->h2d_bytes = 0;
+    // re-binding into the arrays of an earlier binding: stage the uploads (see trk3_engine::stage)
+    eng->staging = false; eng->direct_pending = false; eng->stage_lo = (size_t)-1; eng->stage_hi = 0;
+    if (eng->opt_stage_uploads && !eng->tab_allocs.empty() && eng->tab_arena && eng->tab_arena_used) {
+        if (eng->stage_cap < eng->tab_arena_used) {
+            if (eng->stage) { CK(cudaStreamSynchronize(eng->stream)); cudaFreeHost(eng->stage); eng->stage = nullptr; eng->stage_cap = 0; eng->stage_in_flight = false; }
+            if (cudaHostAlloc((void **)&eng->stage, eng->tab_arena_used, cudaHostAllocDefault) == cudaSuccess) eng->stage_cap = eng->tab_arena_used;
+            else { eng->stage = nullptr; (void)cudaGetLastError(); }          // no pinned memory to be had: direct copies
+        }
+        if (!eng->ev_stage) CK(cudaEventCreateWithFlags(&eng->ev_stage, cudaEventDisableTiming));
+        if (eng->stage) {
+            if (eng->stage_in_flight) { CK(cudaEventSynchronize(eng->ev_stage)); eng->stage_in_flight = false; }   // the mirror is read by the previous binding's DMA
+            eng->staging = true;
+        }
+    }
     eng->cfg = *cfg;
     int rc = trk3_tally_layout_init(cfg, tab, &eng->lay);
     if (rc != TRK3_OK) { eng->err = "invalid time grid / layout"; return rc; }
@@ -1331,15 +1383,10 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
     UP(hid_off, tab->hid_off, tab->n_hi + 1); UP(hid_hw, tab->hid_hw, tab->hid_off[tab->n_hi]); UP(hid_L, tab->hid_L, tab->hid_off[tab->n_hi]);
     UP(hed_off, tab->hed_off, tab->n_he + 1); UP(hed_hw, tab->hed_hw, tab->hed_off[tab->n_he]); UP(hed_L, tab->hed_L, tab->hed_off[tab->n_he]);
     {   // rows of the electron differential tables that are non-increasing (see DevP::eid_mono)
-        auto mono_flags = [](const int64_t *off, const double *L, size_t nrows) {
-            std::vector<uint8_t> f(nrows, 1);
-            for (size_t r = 0; r < nrows; ++r)
-                for (int64_t j = off[r]; j + 1 < off[r + 1]; ++j) if (!(L[j + 1] <= L[j])) { f[r] = 0; break; }
-            return f;
-        };
-        const std::vector<uint8_t> fe = mono_flags(tab->eid_off, tab->eid_L, n_eid), fl = mono_flags(tab->eed_off, tab->eed_L, (size_t)tab->n_ee);
+        std::vector<uint8_t> fe(n_eid), fl((size_t)tab->n_ee);
+        monotone_rows(tab->eid_off, tab->eid_L, n_eid, fe.data()); monotone_rows(tab->eed_off, tab->eed_L, (size_t)tab->n_ee, fl.data());
         UP(eid_mono, fe.data(), fe.size()); UP(eed_mono, fl.data(), fl.size());
-        CK(cudaStreamSynchronize(eng->stream));          // the vectors go out of scope
+        if ((rc = release_sources(eng))) return rc;       // the vectors go out of scope
     }
     UP(dos_E, tab->dos_E, tab->n_dos); UP(dos_DOS, tab->dos_DOS, tab->n_dos); UP(dos_int, tab->dos_int, tab->n_dos); UP(dos_effm, tab->dos_effm, tab->n_dos);
     UP(out_R, tab->out_R, tab->n_r); UP(out_V, tab->out_V, tab->n_r);
@@ -1353,14 +1400,23 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
 #undef UP
     {   // log / reciprocal companions (one exp() per log-log interpolation instead of five log() + exp())
         const trk3_tables &T = *tab;
+        if ((rc = stage_flush(eng))) return rc;          // the companions are computed from the arrays uploaded so far
+        CompanionJobs jobs; jobs.nj = 0;
+        size_t n_max = 0;
+        auto launch_companions = [&]() -> int {
+            if (jobs.nj) k_companions<<<dim3((unsigned)std::min<size_t>((n_max + 255) / 256, (size_t)eng->n_sm * 2), (unsigned)jobs.nj), 256, 0, eng->stream>>>(jobs);
+            jobs.nj = 0; n_max = 0;
+            CK(cudaGetLastError());
+            return TRK3_OK;
+        };
 #define X(dst, src, n, op) { double *d_ = nullptr; const size_t n_ = (size_t)(n); if ((rc = tab_alloc(eng, &d_, n_))) return rc; \
-        if (n_) k_companion<<<(unsigned)((n_ + 255) / 256), 256, 0, eng->stream>>>(d_, src, n_, op); p.dst = d_; }
+        if (n_) { if (jobs.nj == TRK_MAX_COMPANIONS && (rc = launch_companions())) return rc; \
+                  jobs.j[jobs.nj++] = CompanionJob{d_, src, (unsigned long long)n_, op}; n_max = std::max(n_max, n_); } p.dst = d_; }
         TRK3_COMPANIONS(X, p, T, NS)
 #undef X
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(eng->stream));
+        if ((rc = launch_companions())) return rc;
         std::vector<uint16_t> lut;
-#define X(id, E, n) { build_lut(E, n, lut, p.lut[id].l0, p.lut[id].scale); rc = dev_upload(eng, &p.lut[id].lut, lut.data(), lut.size()); if (rc) return rc; CK(cudaStreamSynchronize(eng->stream)); }
+#define X(id, E, n) { build_lut(E, n, lut, p.lut[id].l0, p.lut[id].scale); rc = dev_upload(eng, &p.lut[id].lut, lut.data(), lut.size()); if (rc) return rc; if ((rc = release_sources(eng))) return rc; }
         TRK3_LUT_GRIDS(X, T)
 #undef X
         p.dos_inv_step = uniform_inv_step(T.dos_E, T.n_dos);
@@ -1369,8 +1425,9 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
             shi_threshold(T.dshi_E + T.dshi_off[sh], T.dshi_L + T.dshi_off[sh], Nsh, T.shell_Ip[sh], Mt, dl);
             build_inverse_lut(T.dshi_L + T.dshi_off[sh], Nsh, Mt, lut, p.dshi_lut[sh].l0, p.dshi_lut[sh].scale);
             rc = dev_upload(eng, &p.dshi_lut[sh].lut, lut.data(), lut.size()); if (rc) return rc;
-            CK(cudaStreamSynchronize(eng->stream));
+            if ((rc = release_sources(eng))) return rc;
         }
+        if ((rc = stage_flush(eng))) return rc;
     for (int sh = 0; sh < T.n_shells; ++sh) shi_threshold(T.dshi_E + T.dshi_off[sh], T.dshi_L + T.dshi_off[sh], (int)(T.dshi_off[sh + 1] - T.dshi_off[sh]), T.shell_Ip[sh], p.shi_Mtemp[sh], p.shi_dL[sh]);
         cold_range(tab->ei_E, tot.ei_tot.data(), tab->n_ei, p.e_cold, p.e_imfp_cold);
         cold_range(tab->hi_E, tot.hi_tot.data(), tab->n_hi, p.h_cold, p.h_imfp_cold);
@@ -1398,7 +1455,9 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
         eng->warm_Ph[i] = (ii + ie > 0.0) ? ii / (ii + ie) : 0.0;
     }
     eng->h_warm_auto = -1.0;
-    CK(cudaStreamSynchronize(eng->stream));
+    // a first binding ends synchronised; a staged re-binding leaves its DMAs and the companion kernel in flight on the engine's
+    // stream, in front of the run that follows (nothing on the host refers to the caller's arrays any more)
+    if (!eng->staging) CK(cudaStreamSynchronize(eng->stream));
     p.tally = old.tally; p.events = old.events; p.errors = old.errors; p.cnt_el = old.cnt_el; p.cnt_ph = old.cnt_ph; p.it = old.it;
 
     eng->nel_est = estimate_nel(*cfg, *tab);
@@ -1491,6 +1550,7 @@ int trk3_mc_set_option(trk3_engine *eng, const char *name, double v) {
     else if (k == "coop") eng->opt_coop = (v != 0.0);
     else if (k == "weighted") eng->opt_weighted = (v != 0.0);
     else if (k == "l2_persist") eng->opt_l2_persist = (v != 0.0);
+    else if (k == "stage_uploads") eng->opt_stage_uploads = (v != 0.0);
     else if (k == "run_ahead") eng->opt_run_ahead = std::min(6, std::max(0, (int)v));
     else if (k == "warm_pinel") { eng->opt_warm_pinel = std::min(0.99, std::max(0.0, v)); eng->nb_alloc = 0; eng->e_warm_auto = -1.0; eng->h_warm_auto = -1.0; }
     else if (k == "warm_holes") eng->opt_warm_holes = (v != 0.0);
@@ -1882,9 +1942,9 @@ static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, t
 
 int trk3_mc_run(trk3_engine *eng, int64_t it_begin, int64_t it_end, double *tallies, trk3_stats *stats) {
     if (!eng || !tallies) return TRK3_E_INVALID;
-    int rc = trk3_mc_zero_device_tallies(eng);
-    if (rc) return rc;
-    rc = trk3_mc_run_device(eng, it_begin, it_end, stats);
+    CK(cudaSetDevice(eng->device));
+    CK(cudaMemsetAsync(eng->d_tally, 0, (size_t)eng->lay.total * sizeof(double), eng->stream));     // stream order is all the run needs
+    int rc = trk3_mc_run_device(eng, it_begin, it_end, stats);
     if (rc) return rc;
     return trk3_mc_download_tallies(eng, tallies);
 }
@@ -1989,6 +2049,8 @@ void trk3_mc_destroy(trk3_engine *eng) {
     if (eng->ev_fork) cudaEventDestroy(eng->ev_fork);
     if (eng->ev_join) cudaEventDestroy(eng->ev_join);
     if (eng->h_qcount) cudaFreeHost(eng->h_qcount);
+    if (eng->stage) { cudaStreamSynchronize(eng->stream); cudaFreeHost(eng->stage); }
+    if (eng->ev_stage) cudaEventDestroy(eng->ev_stage);
     for (auto e : eng->ring_ev) cudaEventDestroy(e);
     delete eng;
 }

@@ -51,9 +51,10 @@ inline void build_lut(const double *E, int N, std::vector<uint16_t> &lut, double
     if (!(l1 > l0)) return;
     scale = (double)TRK_NLUT / (l1 - l0);
     int j = 1;
+    double lj = std::log(E[1]);                                      // log(E[j]), evaluated once per grid point (per-call cost of a table reload)
     for (int b = 0; b < TRK_NLUT; ++b) {
         const double edge = l0 + (double)b / scale;                  // lower edge of the bin
-        while (j < N - 1 && std::log(E[j]) <= edge) ++j;            // j = number of grid points <= edge (clamped to [1, N-1])
+        while (j < N - 1 && lj <= edge) { ++j; lj = std::log(E[j]); }   // j = number of grid points <= edge (clamped to [1, N-1])
         lut[b] = (uint16_t)j;
     }
 }
@@ -72,10 +73,21 @@ inline void build_inverse_lut(const double *L, int N, int M_temp, std::vector<ui
     if (!(l1 > l0) || !std::isfinite(l0) || !std::isfinite(l1)) { l0 = 0.0; return; }
     scale = (double)TRK_NLUT / (l1 - l0);
     int j = first + 1;                                                  // 1-based
+    double ij = (L[j - 1] > 0.0) ? 1.0 / L[j - 1] : -1.0;              // 1 / L[j-1] (or "never >= edge"), evaluated once per table entry
     for (int b = 0; b < TRK_NLUT; ++b) {
         const double edge = l0 + (double)b / scale;
-        while (j < N && !(L[j - 1] > 0.0 && 1.0 / L[j - 1] >= edge)) ++j;
+        while (j < N && !(L[j - 1] > 0.0 && ij >= edge)) { ++j; ij = (L[j - 1] > 0.0) ? 1.0 / L[j - 1] : -1.0; }
         lut[b] = (uint16_t)j;
+    }
+}
+// Rows of a differential table (CSR offsets `off`) that are non-increasing: flag 1.  Branch-free inner loop (vectorised): this
+// runs over every element of the table in every table binding.
+inline void monotone_rows(const int64_t *off, const double *L, size_t nrows, uint8_t *flag) {
+    for (size_t r = 0; r < nrows; ++r) {
+        const int64_t a = off[r], b = off[r + 1];
+        unsigned bad = 0;
+        for (int64_t j = a; j + 1 < b; ++j) bad |= (unsigned)!(L[j + 1] <= L[j]);
+        flag[r] = bad ? 0 : 1;
     }
 }
 inline double uniform_inv_step(const double *E, int N) {
