@@ -871,6 +871,17 @@ __global__ void k_fold(TRK_P2, FoldAux a, int64_t njobs) {      // one warp per 
     if ((threadIdx.x & 31) == 0 && dst) *dst += sum;
 }
 // companion arrays of the tables (TRK3_COMPANIONS): evaluated on the device so that they carry the device's log()
+// DevP::eid_mono / eed_mono: 1 for the rows of a differential table (CSR offsets `off`) that are non-increasing; one warp per row
+__global__ void k_monotone_rows(const int64_t *off, const double *L, size_t nrows, uint8_t *flag) {
+    const size_t r = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= nrows) return;                                         // whole warps leave together
+    const int lane = threadIdx.x & 31;
+    const int64_t a = off[r], b = off[r + 1];
+    int bad = 0;
+    for (int64_t j = a + lane; j + 1 < b; j += 32) bad |= !(L[j + 1] <= L[j]);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) flag[r] = bad ? 0 : 1;
+}
 struct CompanionJob { double *dst; const double *src; unsigned long long n; int op; };
 #define TRK_MAX_COMPANIONS 32
 struct CompanionJobs { CompanionJob j[TRK_MAX_COMPANIONS]; int nj; };
@@ -1383,10 +1394,11 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
     UP(hid_off, tab->hid_off, tab->n_hi + 1); UP(hid_hw, tab->hid_hw, tab->hid_off[tab->n_hi]); UP(hid_L, tab->hid_L, tab->hid_off[tab->n_hi]);
     UP(hed_off, tab->hed_off, tab->n_he + 1); UP(hed_hw, tab->hed_hw, tab->hed_off[tab->n_he]); UP(hed_L, tab->hed_L, tab->hed_off[tab->n_he]);
     {   // rows of the electron differential tables that are non-increasing (see DevP::eid_mono)
-        std::vector<uint8_t> fe(n_eid), fl((size_t)tab->n_ee);
-        monotone_rows(tab->eid_off, tab->eid_L, n_eid, fe.data()); monotone_rows(tab->eed_off, tab->eed_L, (size_t)tab->n_ee, fl.data());
-        UP(eid_mono, fe.data(), fe.size()); UP(eed_mono, fl.data(), fl.size());
-        if ((rc = release_sources(eng))) return rc;       // the vectors go out of scope
+        // evaluated on the device from the uploaded rows (k_monotone_rows, launched with the companions below)
+        uint8_t *fe = nullptr, *fl = nullptr;
+        if ((rc = tab_alloc(eng, &fe, n_eid))) return rc;
+        if ((rc = tab_alloc(eng, &fl, (size_t)tab->n_ee))) return rc;
+        p.eid_mono = fe; p.eed_mono = fl;
     }
     UP(dos_E, tab->dos_E, tab->n_dos); UP(dos_DOS, tab->dos_DOS, tab->n_dos); UP(dos_int, tab->dos_int, tab->n_dos); UP(dos_effm, tab->dos_effm, tab->n_dos);
     UP(out_R, tab->out_R, tab->n_r); UP(out_V, tab->out_V, tab->n_r);
@@ -1401,6 +1413,10 @@ int bind_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab
     {   // log / reciprocal companions (one exp() per log-log interpolation instead of five log() + exp())
         const trk3_tables &T = *tab;
         if ((rc = stage_flush(eng))) return rc;          // the companions are computed from the arrays uploaded so far
+        {   const size_t n_eid = NS * T.n_ei;
+            if (n_eid) k_monotone_rows<<<(unsigned)((n_eid * 32 + 255) / 256), 256, 0, eng->stream>>>(p.eid_off, p.eid_L, n_eid, const_cast<uint8_t *>(p.eid_mono));
+            if (T.n_ee) k_monotone_rows<<<(unsigned)(((size_t)T.n_ee * 32 + 255) / 256), 256, 0, eng->stream>>>(p.eed_off, p.eed_L, (size_t)T.n_ee, const_cast<uint8_t *>(p.eed_mono));
+            CK(cudaGetLastError()); }
         CompanionJobs jobs; jobs.nj = 0;
         size_t n_max = 0;
         auto launch_companions = [&]() -> int {
@@ -1497,6 +1513,10 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
     CK(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&eng->ev_join, cudaEventDisableTiming));
     int rc = bind_tables(eng, cfg, tab);
     if (rc) return rc;
+    // the pinned mirror of the table arena for the re-bindings of this handle (see trk3_engine::stage): allocated here, not in the
+    // first trk3_mc_reload_tables call, where it would cost that call milliseconds; without it re-bindings copy array by array
+    if (eng->opt_stage_uploads && eng->tab_arena_used && cudaHostAlloc((void **)&eng->stage, eng->tab_arena_used, cudaHostAllocDefault) == cudaSuccess) eng->stage_cap = eng->tab_arena_used;
+    else { eng->stage = nullptr; (void)cudaGetLastError(); }
     DevP &p = eng->hp;
     if ((rc = dev_alloc(eng, &eng->d_tally, (size_t)eng->lay.total))) return rc;
     CK(cudaMemset(eng->d_tally, 0, (size_t)eng->lay.total * sizeof(double)));
@@ -2049,7 +2069,7 @@ void trk3_mc_destroy(trk3_engine *eng) {
     if (eng->ev_fork) cudaEventDestroy(eng->ev_fork);
     if (eng->ev_join) cudaEventDestroy(eng->ev_join);
     if (eng->h_qcount) cudaFreeHost(eng->h_qcount);
-    if (eng->stage) { cudaStreamSynchronize(eng->stream); cudaFreeHost(eng->stage); }
+    if (eng->stage) cudaFreeHost(eng->stage);            // the device is idle: cudaFree above synchronised it
     if (eng->ev_stage) cudaEventDestroy(eng->ev_stage);
     for (auto e : eng->ring_ev) cudaEventDestroy(e);
     delete eng;

@@ -80,16 +80,6 @@ inline void build_inverse_lut(const double *L, int N, int M_temp, std::vector<ui
         lut[b] = (uint16_t)j;
     }
 }
-// Rows of a differential table (CSR offsets `off`) that are non-increasing: flag 1.  Branch-free inner loop (vectorised): this
-// runs over every element of the table in every table binding.
-inline void monotone_rows(const int64_t *off, const double *L, size_t nrows, uint8_t *flag) {
-    for (size_t r = 0; r < nrows; ++r) {
-        const int64_t a = off[r], b = off[r + 1];
-        unsigned bad = 0;
-        for (int64_t j = a; j + 1 < b; ++j) bad |= (unsigned)!(L[j + 1] <= L[j]);
-        flag[r] = bad ? 0 : 1;
-    }
-}
 inline double uniform_inv_step(const double *E, int N) {
     if (N < 3) return 0.0;
     const double step = (E[N - 1] - E[0]) / (double)(N - 1);
