@@ -562,3 +562,25 @@ def test_persistent_handle_rebinds_tables_of_the_same_shapes(tmp_path, case_c1):
         assert len(tk.engine._handles) == 1
     finally:
         tk.release_handles()
+
+
+def test_edge_cases_of_the_iteration_range(case_c1):
+    """Empty range, the top of the 32-bit iteration index, refused arguments (tests/test_oracle.py has the CPU twin): the
+    CUDA engine against the oracle; a refused call leaves the handle usable."""
+    eng = tk.Engine(case_c1)
+    t, s = eng.run(7, 7)
+    assert not t.any() and s["total_events"] == 0 and not s["errors"] and eng.iteration_energies(4).shape[0] == 0
+    top = 0xffffffff
+    tg, sg = eng.run(top - 3, top, )
+    to, so, eo, _ = oracle_api.run(case_c1, top - 3, top, rng_mode=1)
+    assert not sg["errors"] and so["total_events"] > 1000
+    for k in so["events"]:
+        assert abs(sg["events"][k] - so["events"][k]) <= max(2, 2e-3 * so["events"][k]), k
+    if sg["events"] == so["events"]:
+        assert np.allclose(eng.iteration_energies(3), eo, rtol=1e-9)
+    for lo, hi in ((3, 2), (-1, 2), (top - 1, top + 1)):
+        with pytest.raises(RuntimeError):
+            eng.run(lo, hi)
+    t2, s2 = eng.run(top - 3, top)                      # still in working order, same histories
+    assert s2["events"] == sg["events"] and rel_close(t2, tg, 1e-9)
+    eng.close()

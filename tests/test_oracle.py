@@ -179,3 +179,28 @@ def test_high_multiplicity_metal_runs_in_the_wavefront_engine(case_c4):
     te, se, ee, ne = emul_api.run(case_c4, 0, 1, batch=1)
     assert ne[0, -1] > 5e4 and not se["errors"]
     assert abs(ee[0, 2] - ee[0, -1]) / ee[0, -1] < 1e-9
+
+
+def test_edge_cases_of_the_iteration_range(case_c1):
+    """An empty range gives zero tallies and no events; the iterations just below the 32-bit limit of the iteration index (one
+    word of the Philox counter on both sides) run like any other; ranges compose (a ragged split adds up to the whole)."""
+    to, so, eo, _ = oracle_api.run(case_c1, 7, 7, rng_mode=1)
+    te, se, ee, _ = emul_api.run(case_c1, 7, 7, batch=4)
+    assert not to.any() and not te.any() and so["total_events"] == 0 and se["total_events"] == 0 and eo.shape[0] == 0 and ee.shape[0] == 0
+    top = 0xffffffff
+    to, so, eo, no = oracle_api.run(case_c1, top - 3, top, rng_mode=1)
+    te, se, ee, ne = emul_api.run(case_c1, top - 3, top, batch=2)
+    assert so["total_events"] > 1000 and not so["errors"]
+    assert_same(case_c1, to, te, so, se)
+    assert np.array_equal(no, ne) and np.allclose(eo, ee, rtol=1e-12)
+    # the histories at the top of the range are not those of the bottom (the iteration index keys the random streams)
+    t0, s0, _, _ = oracle_api.run(case_c1, 0, 3, rng_mode=1)
+    assert s0["events"] != so["events"]
+    # ragged split: [top-3, top-2) + [top-2, top) == [top-3, top)
+    ta, sa, _, _ = emul_api.run(case_c1, top - 3, top - 2, batch=2)
+    tb, sb, _, _ = emul_api.run(case_c1, top - 2, top, batch=2)
+    assert {k: sa["events"][k] + sb["events"][k] for k in sa["events"]} == se["events"]
+    lay = case_c1.layout()
+    i = tk.TALLY_NAMES.index("Out_diff_coeff")          # a running mean over the iterations, not a sum (Monte_Carlo.f90:1094-1098)
+    keep = np.ones(lay.total, bool); keep[lay.off[i]: lay.off[i] + lay.len[i]] = False
+    assert np.allclose((ta + tb)[keep], te[keep], rtol=1e-12, atol=1e-300)
