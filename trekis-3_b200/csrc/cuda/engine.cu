@@ -19,6 +19,7 @@
 #include <dlfcn.h>
 #include <algorithm>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -1923,8 +1924,26 @@ static int run_device_impl(trk3_engine *eng, int64_t it_begin, int64_t it_end, t
     if (eng->comm && eng->comm_size > 1) {
         // the single collective of the path (26 x MPI_Reduce in the reference, Monte_Carlo.f90:131-389): in place, on the
         // engine's stream, right behind the folding kernels -- no host synchronisation in between
+        // TRK3_NCCL_PROBE=1 (diagnostic, synchronises): time the collective -- the first all-reduce includes the wait for the
+        // slowest rank, a second one on a scratch buffer right behind it is the collective's own latency
+        static const bool probe = std::getenv("TRK3_NCCL_PROBE") != nullptr;
+        cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
+        if (probe) { for (auto &e : pe) CK(cudaEventCreate(&e)); CK(cudaEventRecord(pe[0], eng->stream)); }
+        const auto h0 = std::chrono::steady_clock::now();
         const int nrc = nccl_rt::api().AllReduce(eng->d_tally, eng->d_tally, (size_t)eng->lay.total, nccl_rt::kFloat64, nccl_rt::kSum, eng->comm, eng->stream);
         if (nrc != nccl_rt::kSuccess) { eng->err = std::string("ncclAllReduce: ") + nccl_rt::api().GetErrorString(nrc); return TRK3_E_CUDA; }
+        if (probe) {
+            const double host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h0).count();
+            CK(cudaEventRecord(pe[1], eng->stream));
+            nccl_rt::api().AllReduce(eng->d_tally_bak, eng->d_tally_bak, (size_t)eng->lay.total, nccl_rt::kFloat64, nccl_rt::kSum, eng->comm, eng->stream);
+            CK(cudaEventRecord(pe[2], eng->stream));
+            CK(cudaStreamSynchronize(eng->stream));
+            float a = 0.f, b = 0.f, c = 0.f;
+            cudaEventElapsedTime(&a, pe[0], pe[1]); cudaEventElapsedTime(&b, pe[1], pe[2]); cudaEventElapsedTime(&c, eng->ev1, pe[0]);
+            fprintf(stderr, "[trk3 nccl probe] %d ranks: all-reduce of %lld doubles %.3f ms (with the wait for the slowest rank), repeated at once %.3f ms, host call %.1f us, folded tallies -> all-reduce %.3f ms\n",
+                    eng->comm_size, (long long)eng->lay.total, a, b, host_us, c);
+            for (auto &e : pe) cudaEventDestroy(e);
+        }
     }
     // No synchronisation here: the last two operations (the Out_diff_coeff update and the all-reduce) stay in flight on the
     // engine's stream when the call returns, so that a rank does not sit in cudaStreamSynchronize until the slowest rank has
