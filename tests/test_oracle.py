@@ -204,3 +204,55 @@ def test_edge_cases_of_the_iteration_range(case_c1):
     i = tk.TALLY_NAMES.index("Out_diff_coeff")          # a running mean over the iterations, not a sum (Monte_Carlo.f90:1094-1098)
     keep = np.ones(lay.total, bool); keep[lay.off[i]: lay.off[i] + lay.len[i]] = False
     assert np.allclose((ta + tb)[keep], te[keep], rtol=1e-12, atol=1e-300)
+
+
+_REF = "/root/reference"
+# shipped materials beyond the five of the BASELINE configurations and H2O: compounds of three and four elements, an ionic crystal,
+# a polymer with an atom without shells of its own, a semiconductor given by its chemical formula, metals
+_MORE_MATERIALS = ["LiF", "yag", "Olivine", "Si_sp", "C2H4", "Si", "Cu", "Al"]
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(_REF + "/INPUT_CDF"), reason="the reference tree is only mounted in the build container")
+@pytest.mark.parametrize("material", _MORE_MATERIALS)
+def test_wavefront_equals_time_ordered_loop_on_more_shipped_materials(tmp_path, material):
+    """The input contract over more of the .cdf / .dos files the reference ships (read in place): tables built by the host half,
+    then the wavefront engine (the CUDA kernels' physics header) against the time-ordered oracle on the same random streams."""
+    import os
+    import shutil
+    if not os.path.exists(f"{_REF}/INPUT_CDF/{material}.cdf"):
+        pytest.skip("not shipped")
+    dd = tmp_path / "data"
+    os.makedirs(dd)
+    os.symlink(f"{_REF}/INPUT_CDF", dd / "INPUT_CDF")
+    os.symlink(f"{_REF}/INPUT_DOS", dd / "INPUT_DOS")
+    os.symlink(os.path.join(tk._abi.REPO, "data", "INPUT_EADL"), dd / "INPUT_EADL")
+    shutil.copy(os.path.join(tk._abi.REPO, "data", "INPUT_PARAMETERS.default.txt"), dd)
+    try:
+        case = tk.Case.load(tk.make_run_dir(str(tmp_path / "run"), (material, 54, 167.0, 0, 3), data_dir=str(dd),
+                                            edits={5: "10.0"}))          # 10 fs: the oracle's cost grows with the square of the cascade
+    except RuntimeError as e:
+        pytest.skip(f"refused by the reader: {e}")
+    case.build_tables(shi_window_only=True, cache_dir=CACHE)
+    to, so, eo, no = oracle_api.run(case, 0, 2, rng_mode=1)
+    te, se, ee, ne = emul_api.run(case, 0, 2, batch=2)
+    assert not so["errors"], so["errors"]
+    assert so["events"]["shi"] > 50 and so["events"]["el_inelastic"] > 100 and so["total_events"] > 1000, so["events"]
+    if so["events"] == se["events"]:
+        assert_same(case, to, te, so, se)
+        assert np.array_equal(no, ne) and np.allclose(eo, ee, rtol=1e-12)
+    else:
+        # Cu: the d band's DOS has gaps, check_hole_parameters (Monte_Carlo.f90:682-721) snaps many holes exactly onto grid
+        # energies, and there one unit in the last place decides the bin of the next lookup.  The engine interpolates across
+        # energies with the LOGARITHMS of its two row samples where the oracle (as the reference) takes exp and log again, so
+        # transferred energies differ in the last bits (traced: the first differing event of a run is always such a last-bit
+        # difference); a handful of histories per iteration then take the other branch.  Held to the bound of the GPU tests.
+        assert material in ("Cu",), (material, so["events"], se["events"])
+        for k in so["events"]:
+            assert abs(so["events"][k] - se["events"][k]) <= max(2, 2e-3 * so["events"][k]), (k, so["events"][k], se["events"][k])
+        lay = case.layout()
+        To, Te = split_tallies(lay, to), split_tallies(lay, te)
+        for k in To:
+            assert np.isclose(To[k].sum(), Te[k].sum(), rtol=5e-3), k
+        assert np.allclose(eo, ee, rtol=1e-9)          # total energy per iteration and grid time
+    drift = np.abs(eo[:, 1:] - eo[:, -1:]) / eo[:, -1:]
+    assert drift.max() < 1e-9
