@@ -603,7 +603,8 @@ bool read_case(const std::string &dir, Case &c, std::string &err) {
     if (c.SHI.Kind_ion != 0 && c.SHI.Kind_ion != 1) c.SHI.Kind_ion = 0;       // anything but 1 is the point charge (select case default)
     if (c.numpar.kind_of_DR == 4) {
         // Delta-CDF: the weights follow the oscillators as they are read (Reading_files_and_parameters.f90:1565-1575, 1608-1610)
-        if (c.numpar.kind_of_CDF == 1) { err = "Delta-CDF (kind_of_DR=4) with a .cdf that leaves its shells to the atomic database (single-pole CDFs) is not supported"; return false; }
+        if (c.numpar.kind_of_CDF == 1) { err = "Delta-CDF (kind_of_DR=4) with a .cdf that leaves its shells to the atomic database (single-pole CDFs) is not supported: "
+                                              "the reference allocates the delta-function weights of such shells and never assigns them (Reading_files_and_parameters.f90:1482-1484)"; return false; }
         for (auto &a : c.atoms) for (int k = 0; k < a.nshl(); ++k) {
             CDFosc &o = a.Ritchi[(size_t)k];
             o.alpha.resize(o.E0.size());
