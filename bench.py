@@ -51,6 +51,21 @@ def workload_name(config, nmc):
     return f"{config}: {ion} {e:g} MeV in {mat}, photons {'on' if ph else 'off'}, {nmc} MC iterations per step, T=100 fs"
 
 
+def bench_config(args, world, tally_doubles):
+    """The `config` object of the JSON line: the workload and how the GPU arm runs it.  Both arms print the SAME object (the reference
+    arm runs "on your arm's config"), what is specific to the CPU run is in its `cpu_baseline.sample`."""
+    nmc, strong = args.nmc, args.scaling == "strong"
+    return {"workload": workload_name(args.config, nmc), "iterations_in_flight": args.batch,
+            "step": f"one step = one call of {nmc} iterations = ONE batch: latency-bound by the chain of hot generations; "
+                    "`throughput` holds the same configuration with 4096 iterations in flight",
+            "l2": "256 MiB buffer written between timed steps (L2 flush); queues stream through HBM",
+            "parallelism": (f"{nmc} iterations per step split contiguously over {world} GPU(s) (strong scaling)" if strong else
+                            f"every one of {world} GPU(s) runs its own {nmc} iterations per step (weak scaling)") +
+                           f"; one ncclAllReduce of {tally_doubles} doubles per step, issued by libtrekis3_gpu.so on its own stream",
+            "inputs": "shipped INPUT_CDF/INPUT_DOS files; radiative widths from data/INPUT_EADL/radiative_widths.dat "
+                      "(approximate, EADL2023.ALL is not redistributable)"}
+
+
 _JSON_FD = None
 
 
@@ -211,7 +226,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, args.nmc), "sample": f"{n_tot} iterations in {t_tot:.1f} s"},
+        "config": bench_config(args, max(1, args.gpus), case.layout().total),
+        "sample": f"{n_tot} iterations in {t_tot:.1f} s",
         "events_per_s": sum(ev_rates) / len(ev_rates),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                          "sample": f"oracle/trk3_oracle.cpp (reference algorithm incl. O(N) next-event search, {flags}), "
@@ -469,15 +485,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, nmc), "iterations_in_flight": args.batch,
-                   "step": f"one step = one call of {nmc} iterations = ONE batch: latency-bound by the chain of hot generations; "
-                           "`throughput` holds the same configuration with 4096 iterations in flight",
-                   "l2": "256 MiB buffer written between timed steps (L2 flush); queues stream through HBM",
-                   "parallelism": (f"{nmc} iterations per step split contiguously over {world} GPU(s) (strong scaling)" if strong else
-                                   f"every one of {world} GPU(s) runs its own {nmc} iterations per step (weak scaling)") +
-                                  f"; one ncclAllReduce of {lay.total} doubles per step, issued by libtrekis3_gpu.so on its own stream",
-                   "inputs": "shipped INPUT_CDF/INPUT_DOS files; radiative widths from data/INPUT_EADL/radiative_widths.dat "
-                             "(approximate, EADL2023.ALL is not redistributable)"},
+        "config": bench_config(args, world, lay.total),
         "events_per_s": events_all / (ms * 1e-3), "events_per_s_per_gpu": events_all / (ms * 1e-3) / world,
         "events_by_class": ev_by_class, "cold_events": cold_ev, "warm_events": warm_ev, "wall_s": t_wall,
         "clocks": clk,
