@@ -56,8 +56,9 @@ def bench_config(args, world, tally_doubles):
     arm runs "on your arm's config"), what is specific to the CPU run is in its `cpu_baseline.sample`."""
     nmc, strong = args.nmc, args.scaling == "strong"
     return {"workload": workload_name(args.config, nmc), "iterations_in_flight": args.batch,
-            "step": f"one step = one call of {nmc} iterations = ONE batch: latency-bound by the chain of hot generations; "
-                    "`throughput` holds the same configuration with 4096 iterations in flight",
+            "step": (f"one step = one call of {nmc} iterations = ONE batch: latency-bound by the chain of hot generations; "
+                     "`throughput` holds the same configuration with 4096 iterations in flight") if nmc <= args.batch else
+                    f"one step = one call of {nmc} iterations, run as batches of {args.batch} iterations in flight",
             "l2": "256 MiB buffer written between timed steps (L2 flush); queues stream through HBM",
             "parallelism": (f"{nmc} iterations per step split contiguously over {world} GPU(s) (strong scaling)" if strong else
                             f"every one of {world} GPU(s) runs its own {nmc} iterations per step (weak scaling)") +
