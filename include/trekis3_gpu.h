@@ -227,6 +227,10 @@ int trk3_mc_create(const trk3_config *cfg, const trk3_tables *tab, int device, t
 
 /* Copy configuration + tables into an existing engine again (same shapes as at creation): what a persistent plugin
  * handle does at every do_Monte_Carlo call -- the inputs go host->device, queues and scratch stay allocated.
+ * The arrays are copied into a pinned mirror owned by the handle and leave in two DMAs on the engine's stream; the call
+ * returns with them in flight: `cfg` and `tab` (and the arrays they point to) may be changed or freed as soon as it has
+ * returned, and the next trk3_mc_run / trk3_mc_run_device is ordered behind the copies (option "stage_uploads" = 0:
+ * array-by-array copies, synchronised before the call returns).
  * trk3_mc_table_bytes = bytes copied host->device by the last binding. */
 int trk3_mc_reload_tables(trk3_engine *eng, const trk3_config *cfg, const trk3_tables *tab);
 uint64_t trk3_mc_table_bytes(const trk3_engine *eng);
