@@ -233,8 +233,9 @@ def test_wavefront_equals_time_ordered_loop_on_more_shipped_materials(tmp_path, 
     except RuntimeError as e:
         pytest.skip(f"refused by the reader: {e}")
     case.build_tables(shi_window_only=True, cache_dir=CACHE)
-    to, so, eo, no = oracle_api.run(case, 0, 2, rng_mode=1)
-    te, se, ee, ne = emul_api.run(case, 0, 2, batch=2)
+    n_it = 1 if material == "Cu" else 2           # copper's cascade is the largest of the set (the oracle's cost is quadratic in it)
+    to, so, eo, no = oracle_api.run(case, 0, n_it, rng_mode=1)
+    te, se, ee, ne = emul_api.run(case, 0, n_it, batch=2)
     assert not so["errors"], so["errors"]
     assert so["events"]["shi"] > 50 and so["events"]["el_inelastic"] > 100 and so["total_events"] > 1000, so["events"]
     if so["events"] == se["events"]:
